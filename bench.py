@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the BP message-update hot path (BASELINE.json metric: BP message updates/s).
+
+  python bench.py --gpus N --steps K --warmup W [--workload cfg2] [--impl reference]
+
+A "step" is ONE synchronous BP sweep (every directed edge updated once) over a synthetic PEPS norm
+network.  N = 1 runs BASELINE config 2 (32x32 square lattice, chi = 8, d = 2, Float64); for N > 1 the
+lattice is vertex-partitioned into N strips of 32 rows (weak scaling: every rank owns a 32x32 block of a
+(32N)x32 lattice), cut-edge messages are pushed to the neighbour ranks over NVLink every sweep and the
+residual is max-reduced over the ranks.
+
+One JSON line on rank 0 (see the task contract): `value` = updates/s with everything resident in HBM,
+`e2e` = the same through the C ABI with HOST buffers (message upload + sweep + message download per
+step), `roofline` for the dominant bucket's kernel, `cpu_baseline` = the CPU restatement of the reference
+algorithm (oracle/bp_oracle.c, all host cores) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC = "bp_message_updates_per_s"
+UNIT = "updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "cfg5s"])
+    ap.add_argument("--kernel", type=int, default=0, help="force a kernel family (include/bpx.h BPX_KERNEL_*)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------
+def build_workload(name: str, world: int):
+    """-> (SyntheticProblem, owner list or None, description)."""
+    from itnn_b200 import graphs, problems
+
+    if name == "cfg5s":  # cfg5's buckets on a lattice the default run can generate quickly
+        g = graphs.named_grid((24, 24))
+        p = problems.make_config("cfg5", graph=g)
+        return p, None, "24x24 square-lattice PEPS norm network (cfg5 buckets), chi=16, d=2, Float64"
+    if world == 1 or name != "cfg2":
+        p = problems.make_config(name)
+        desc = {
+            "cfg1": "4x4 square-lattice PEPS norm network, chi=2, d=2, Float64",
+            "cfg2": "32x32 square-lattice PEPS norm network, chi=8, d=2, Float64",
+            "cfg3": "heavy-hex 127-site PEPS norm network, chi=16, d=2, ComplexF64",
+            "cfg4": "16x16x16 periodic cubic PEPS norm network, chi=4, d=2, Float64",
+            "cfg5": "256x256 square-lattice PEPS norm network, chi=16, d=2, Float64",
+        }[name]
+        return p, None, desc
+    g = graphs.named_grid((32, 32 * world))
+    p = problems.make_config("cfg2", graph=g)
+    owner = [(v[1] - 1) // 32 for v in p.ga.vertices]
+    return p, owner, f"32x{32 * world} square-lattice PEPS norm network (32x32 block per GPU), chi=8, d=2, Float64"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu = gpu
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline: the reference algorithm restated (oracle/bp_oracle.c), all host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_arm(p, seconds: float, max_steps: int = 1000, warmup: int = 1):
+    """Times synchronous sweeps of the C oracle (absorption order, OpenMP over edges).  If one full sweep
+    exceeds the budget, a random sample of edges is timed instead.  -> (updates/s, cores, sample, ms/step, steps)"""
+    from oracle.c_oracle import COracle
+
+    co = COracle(p.ga, p.phys_dim, p.link_dim, p.tensors, p.dtype)
+    cores = co.num_threads()
+    flat = co.pack(p.messages)
+    ne = p.ga.ne
+    # probe cost on a small sample
+    rng = np.random.default_rng(0)
+    probe = np.sort(rng.choice(ne, size=min(ne, 4 * cores), replace=False))
+    co.sweep_jacobi(flat, edges=probe)  # cold (thread pool start-up, page faults)
+    t0 = time.perf_counter()
+    co.sweep_jacobi(flat, edges=probe)
+    per_update = (time.perf_counter() - t0) / len(probe)
+    full = per_update * ne
+    if full <= seconds / 3:
+        edges, n_upd, sample = None, ne, f"full sweeps of all {ne} directed edges"
+    else:
+        k = max(cores, int(seconds / 3 / per_update))
+        edges = np.sort(rng.choice(ne, size=min(ne, k), replace=False))
+        n_upd, sample = len(edges), f"{len(edges)} randomly sampled directed edges of {ne} per step"
+    for _ in range(warmup):
+        co.sweep_jacobi(flat, edges=edges)
+    times = []
+    t_end = time.perf_counter() + seconds
+    while len(times) < max_steps and (time.perf_counter() < t_end or len(times) < 2):
+        t0 = time.perf_counter()
+        co.sweep_jacobi(flat, edges=edges)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    return n_upd / (ms * 1e-3), cores, sample, ms, len(times)
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    entry.import_package()
+    p, _, desc = build_workload(args.workload, 1)
+    budget = max(10.0, min(120.0, 4.0 * args.steps))
+    val, cores, sample, ms, steps = cpu_reference_arm(p, budget, max_steps=args.steps, warmup=max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if p.dtype.kind != "c" else "c128", "data": "synthetic",
+        "config": {"workload": desc, "schedule": "synchronous", "note": "reference CPU path restated in C (oracle/bp_oracle.c, "
+                   "absorption order, OpenMP over edges); the Julia reference itself cannot run in this image"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ours
+# ---------------------------------------------------------------------------------------------------
+def measure_fp64_peak(torch, n: int = 4096, reps: int = 5) -> float:
+    """cuBLAS DGEMM n^3 (torch.matmul, float64), best of `reps`, TFLOP/s -- the same method the driver used
+    for the bf16 entry of MEASURED_PEAKS.json, which has no FP64 figure."""
+    a = torch.randn(n, n, device="cuda", dtype=torch.float64)
+    b = torch.randn(n, n, device="cuda", dtype=torch.float64)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) * 1e-12
+
+
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+
+    pkg = entry.import_package()
+    from itnn_b200 import _lib, problems
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    p, owner, desc = build_workload(args.workload, world)
+    ctx = pkg.BPXContext(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_graph(p.ga.src, p.ga.dst, p.ga.slot, p.ga.nv)
+    if args.kernel:
+        ctx.set_kernel_policy(args.kernel)
+    ctx.set_dims(p.dtype, "norm", p.phys_dim, p.link_dim)
+    ctx.set_site_tensors(p.tensors)
+    flat0 = ctx.pack_messages(p.messages)
+    ctx.set_messages(flat0)
+    if world > 1:
+        from itnn_b200 import partition
+
+        partition.connect(ctx, owner, rank, world)
+    n_local_updates = sum(b["edges"] for b in ctx.buckets())
+    n_total_updates = p.ga.ne
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allreduce_residual():
+        if world > 1:
+            partition.allreduce_residual(ctx)
+
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    # ---- value: everything resident, device-timed per step, L2 flushed between steps -------------------
+    for _ in range(args.warmup):
+        ctx.sweep_async(1)
+        allreduce_residual()
+    barrier()
+    ctx.counters(reset=True)
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        l2_flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.sweep_async(1)
+        allreduce_residual()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = np.array([a.elapsed_time(b) for a, b in evs])
+    total_ms = float(step_ms.sum())
+    counters = ctx.counters()
+    bucket_times = []
+    for b, info in enumerate(ctx.buckets()):
+        ms, n = ctx.bucket_time(b)
+        bucket_times.append((info, ms, n))
+    ctx.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n_total_updates / (ms_per_step * 1e-3)
+    residual = ctx.last_residual()
+
+    # ---- roofline of the dominant bucket's kernel ----------------------------------------------------
+    cplx = 4.0 if p.dtype.kind == "c" else 1.0
+    w = p.dtype.itemsize
+    dom, dom_ms, dom_n = max(bucket_times, key=lambda t: t[1])
+    z, chi, d = dom["degree"], dom["chi"], dom["phys"]
+    flops_per_launch = dom["edges"] * 2.0 * z * d * float(chi) ** (z + 1) * cplx
+    bytes_per_launch = dom["vertices"] * d * float(chi) ** z * w + 3.0 * dom["edges"] * chi * chi * w
+    avg_ms = dom_ms / max(dom_n, 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    fp64_peak = measure_fp64_peak(torch)
+    t_flop = flops_per_launch / (fp64_peak * 1e12)
+    t_byte = bytes_per_launch / (hbm_peak * 1e9)
+    if t_flop >= t_byte:
+        roof = {"bound": "tensor", "achieved": flops_per_launch / (avg_ms * 1e-3) * 1e-12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "peak_source": "measured live: cuBLAS DGEMM 4096^3 via torch.matmul(float64), best of 5 (MEASURED_PEAKS.json has no FP64 entry)"}
+    else:
+        roof = {"bound": "hbm", "achieved": bytes_per_launch / (avg_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["kernel"] = {1: "bp_update_generic", 2: "bp_update_onchip", 3: "bp_update_sliced"}.get(dom["kernel"], "?")
+    roof["bucket"] = {"degree": z, "chi": chi, "phys": d, "updates_per_launch": dom["edges"]}
+    roof["avg_launch_ms"] = avg_ms
+    roof["flops_per_launch"] = flops_per_launch
+    roof["bytes_per_launch"] = bytes_per_launch
+    roof["hbm_gbs_achieved"] = bytes_per_launch / (avg_ms * 1e-3) * 1e-9
+    roof["share_of_step"] = dom_ms / max(sum(t[1] for t in bucket_times), 1e-30)
+
+    # ---- e2e: host buffers through the C ABI, H2D + sweep + D2H inside the timed region -----------------
+    e2e = None
+    if not args.no_e2e:
+        nbytes = flat0.nbytes
+        pin_in = torch.empty(flat0.size, dtype=torch.float64 if p.dtype.kind != "c" else torch.complex128).pin_memory()
+        pin_out = torch.empty_like(pin_in).pin_memory()
+        h_in, h_out = pin_in.numpy(), pin_out.numpy()
+        h_in[:] = flat0
+        for _ in range(2):
+            ctx.set_messages(h_in)
+            ctx.sweep_async(1)
+            allreduce_residual()
+            ctx.get_messages_flat(h_out)
+        barrier()
+        ee = []
+        for _ in range(args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.set_messages(h_in)        # H2D of this step's iterate (pinned)
+            ctx.sweep_async(1)
+            allreduce_residual()
+            ctx.get_messages_flat(h_out)  # D2H of the result
+            res_e2e = ctx.last_residual()  # + the scalar the stopping criterion consumes
+            e1.record(stream)
+            ee.append((e0, e1))
+            h_in, h_out = h_out, h_in     # next step consumes this step's result
+        barrier()
+        e_ms = float(sum(a.elapsed_time(b) for a, b in ee))
+        if world > 1:
+            t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": n_total_updates / (e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
+               "d2h_bytes_per_step": int(nbytes + 8), "ms_per_step": e_ms / args.steps,
+               "what": "bpx_set_messages(host) + bpx_sweep_async(1) + bpx_get_messages(host) + residual per step; site tensors resident"}
+
+    # ---- CPU baseline (rank 0, N = 1) -----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, ms, steps = cpu_reference_arm(p, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{sample}; {steps} steps of {ms:.1f} ms"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if p.dtype.kind != "c" else "c128", "data": "synthetic",
+            "config": {"workload": desc, "schedule": "synchronous (Jacobi) sweep, sum-normalised, residual fused",
+                       "updates_per_step": n_total_updates, "updates_per_gpu": n_local_updates,
+                       "l2": "flushed between timed steps (256 MiB memset)", "timing": "CUDA events per step on the launching stream"},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(counters["launches"]), "residual_after_bench": residual,
+            "wall_s_timed_region": t_wall,
+            "buckets": [{"degree": i["degree"], "chi": i["chi"], "edges": i["edges"], "kernel": i["kernel"],
+                         "ms_per_launch": ms / max(n, 1)} for i, ms, n in bucket_times],
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,175 @@
+/*
+ * bpx.h -- C ABI of libbpx.so: B200-native (sm_100a) belief-propagation message updates for
+ * ITensorNetworksNext.jl's `beliefpropagation` hot path.
+ *
+ * The reference (pure Julia, /root/reference) has no FFI for this path; its extension point is
+ *   "Plug in a new strategy by subtyping `MessageUpdateAlgorithm` and overloading `message_update!`"
+ *   (src/beliefpropagation/beliefpropagation.jl:214-220), reached through the
+ *   `message_update_algorithm=` keyword of `beliefpropagation` (:69-92) and `select_algorithm`
+ *   (src/select_algorithm.jl:41-48).
+ * The entry points below are what a Julia `ccall` glue for that strategy binds (julia/BPX.jl,
+ * INTEGRATION.md).  Each one cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns BPX_OK (0) or a negative bpx_status; the message of the last failure on
+ *     a context is available from bpx_last_error().  No C++ exception crosses this boundary.
+ *   - plain pointers and sizes only.  Host buffers are owned by the caller and are only touched during
+ *     the call (all calls are synchronous w.r.t. the host buffers they read or write).
+ *   - the library owns all device memory.  A context is bound to ONE CUDA device (one process per GPU;
+ *     multi-GPU runs create one context per rank and connect them with bpx_halo_*).
+ *   - a context is not thread-safe; several contexts may coexist.
+ *   - there is no CPU fallback: every compute entry point fails with BPX_ERR_CUDA if no sm_100 device
+ *     is usable.
+ *
+ * Canonical data layout at the boundary (column-major, first index fastest, like Julia arrays)
+ *   graph      vertices 0..nv-1; DIRECTED edges 0..ne-1, both orientations of every link present.
+ *              slot[e] = position of link e among the link legs of src[e]  (0..deg(src[e])-1).
+ *   site       NORM mode:   A_v[s, l_0, ..., l_{z-1}]  (physical leg fastest, link legs in slot order)
+ *              SINGLE mode: T_v[l_0, ..., l_{z-1}]
+ *              packed for all vertices in vertex order (bpx_site_offset gives element offsets).
+ *   message    NORM mode:   M_e[bra, ket], chi_e x chi_e (src/beliefpropagation/messagecache.jl:205-225)
+ *              SINGLE mode: m_e[chi_e]
+ *              packed for all directed edges in edge order (bpx_message_offset).
+ *   element    BPX_F64: double;  BPX_C64: interleaved (re, im) doubles == Julia ComplexF64.
+ */
+#ifndef BPX_H
+#define BPX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPX_VERSION 100
+#define BPX_MAX_DEGREE 12
+
+typedef struct bpx_ctx bpx_ctx;
+
+typedef enum {
+  BPX_OK = 0,
+  BPX_ERR_INVALID = -1, /* bad argument / call order */
+  BPX_ERR_CUDA = -2,    /* CUDA runtime failure or no usable device */
+  BPX_ERR_ALLOC = -3,   /* host or device allocation failed */
+  BPX_ERR_UNSUPPORTED = -4
+} bpx_status;
+
+enum { BPX_F64 = 0, BPX_C64 = 1 };
+enum { BPX_MODE_NORM = 0, BPX_MODE_SINGLE = 1 };
+
+/* Kernel families a bucket of updates can be routed to (bpx_bucket_info / bpx_set_kernel_policy). */
+enum {
+  BPX_KERNEL_AUTO = 0,
+  BPX_KERNEL_GENERIC = 1, /* edge-centric, any shape, strided loops            */
+  BPX_KERNEL_ONCHIP = 2,  /* vertex-centric, site tensor resident in shared memory, FP64 DMMA chain */
+  BPX_KERNEL_SLICED = 3   /* vertex-centric, site tensor streamed in leg slices, FP64 DMMA chain    */
+};
+
+int bpx_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int bpx_create(int device, bpx_ctx** out);
+int bpx_destroy(bpx_ctx* ctx);
+/* ctx may be NULL: returns the message of the last failed bpx_create on this thread. */
+const char* bpx_last_error(const bpx_ctx* ctx);
+
+/* ---- problem description ------------------------------------------------------------------------
+ * Replaces the graph/dictionary walk of `incoming_messages` (messagecache.jl:124-131) and the factor
+ * fetch `factors[src(edge)]` (beliefpropagation.jl:244, normnetwork.jl:49-54) by a one-off upload. */
+int bpx_set_graph(bpx_ctx* ctx, int64_t nv, int64_t ne, const int64_t* src, const int64_t* dst,
+                  const int32_t* slot);
+/* phys_dim[nv] (ignored, may be NULL, in SINGLE mode); link_dim[ne] with link_dim[e] == link_dim[rev e].
+ * Allocates device storage for site tensors and two message sets (synchronous ping-pong), buckets the
+ * directed edges by (degree, link dims, physical dim). */
+int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* phys_dim, const int32_t* link_dim);
+
+int64_t bpx_num_vertices(const bpx_ctx* ctx);
+int64_t bpx_num_edges(const bpx_ctx* ctx);
+int64_t bpx_rev(const bpx_ctx* ctx, int64_t e);
+/* element (not byte) offsets / sizes in the packed host layouts; totals with v == nv / e == ne */
+int64_t bpx_site_offset(const bpx_ctx* ctx, int64_t v);
+int64_t bpx_message_offset(const bpx_ctx* ctx, int64_t e);
+
+/* kettensor(nn, v) for every v (normnetwork.jl:77), canonical layout, packed. */
+int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed);
+int bpx_set_site_tensor(bpx_ctx* ctx, int64_t v, const void* data);
+/* The iterate: `MessageCache(messages)` (beliefpropagation.jl:76, messagecache.jl:33-49). */
+int bpx_set_messages(bpx_ctx* ctx, const void* packed);
+int bpx_get_messages(bpx_ctx* ctx, void* packed);
+int bpx_get_message(bpx_ctx* ctx, int64_t e, void* data);
+
+/* ---- the hot path -------------------------------------------------------------------------------
+ * bpx_sweep: up to `max_sweeps` SYNCHRONOUS sweeps.  One sweep performs, for every directed edge,
+ * `message_update!(::SimpleMessageUpdate, cache, factors, edge)` (beliefpropagation.jl:242-257) from the
+ * previous sweep's messages, with the sum-normalisation (:248-253, `normalize` != 0) and the per-edge
+ * term of `iterate_diff` (:261-267) fused into the kernel epilogue.  After each sweep the maximum
+ * residual is compared with `tol` on the device: the loop stops after the first sweep whose residual
+ * is < tol (StopWhenConverged, AlgorithmsInterfaceExtensions.jl:84-119) or after max_sweeps
+ * (StopAfterIteration).  tol <= 0 disables the convergence test.
+ * residual_out: residual of the last executed sweep; sweeps_done: number executed (either may be NULL). */
+int bpx_sweep(bpx_ctx* ctx, int max_sweeps, double tol, int normalize, double* residual_out,
+              int* sweeps_done);
+/* Enqueue `n_sweeps` synchronous sweeps on the context's stream and return without waiting (no
+ * convergence test).  Pair with bpx_synchronize / bpx_device_residual / bpx_residual_history. */
+int bpx_sweep_async(bpx_ctx* ctx, int n_sweeps, int normalize);
+/* Reference schedule: in-place (Gauss-Seidel) updates along an explicit directed-edge list
+ * (beliefpropagation.jl:200-210, 255).  Runs of consecutive, mutually independent updates are batched. */
+int bpx_sweep_sequence(bpx_ctx* ctx, const int64_t* edge_seq, int64_t n_seq, int max_sweeps, double tol,
+                       int normalize, double* residual_out, int* sweeps_done);
+/* residuals of the sweeps of the last bpx_sweep* call (up to n). Returns the count via *n_out. */
+int bpx_residual_history(bpx_ctx* ctx, double* out, int n, int* n_out);
+/* residual of the most recent sweep (synchronises the stream) */
+int bpx_last_residual(bpx_ctx* ctx, double* out);
+/* `iterate_diff(cache, other)` against a host copy of another message set (beliefpropagation.jl:261). */
+int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* out);
+
+/* ---- beliefs (messagecache.jl:139-201), same contraction kernels with all z messages absorbed ---- */
+int bpx_vertex_scalars(bpx_ctx* ctx, void* out /* nv elements */);
+int bpx_edge_scalars(bpx_ctx* ctx, void* out /* ne/2 elements, edges with e < rev(e) in edge order */);
+/* numerator of <O_v>: vertex contraction with the d x d operator `op[s_out, s_in]` applied to the ket
+ * site leg, for every vertex (ops packed per vertex, d_v*d_v elements each).  Build-defined extension:
+ * the reference has no `expect`. */
+int bpx_vertex_expect_numerators(bpx_ctx* ctx, const void* ops_packed, void* out /* nv elements */);
+
+/* ---- introspection --------------------------------------------------------------------------------- */
+int bpx_num_buckets(const bpx_ctx* ctx);
+/* info[0]=degree, [1]=chi (0 if non-uniform), [2]=phys dim, [3]=#vertices, [4]=#directed edges,
+ * [5]=kernel family in use */
+int bpx_bucket_info(const bpx_ctx* ctx, int bucket, int64_t info[6]);
+/* force a kernel family for all buckets that support it (testing / profiling); BPX_KERNEL_AUTO resets */
+int bpx_set_kernel_policy(bpx_ctx* ctx, int kernel);
+/* per-bucket device timing: when enabled, every bucket launch of a sweep is bracketed by CUDA events on
+ * the context's stream.  bpx_bucket_time returns the summed milliseconds and the number of launches
+ * timed since profiling was (re-)enabled (it synchronises the stream). */
+int bpx_set_profiling(bpx_ctx* ctx, int enable);
+int bpx_bucket_time(bpx_ctx* ctx, int bucket, double* total_ms, int64_t* launches);
+/* counters since the last reset: [0]=kernel launches issued by this library, [1]=message updates,
+ * [2]=sweeps */
+int bpx_counters(bpx_ctx* ctx, int64_t out[3], int reset);
+
+/* ---- device-side access for callers that already hold device memory ------------------------------ */
+/* use an external cudaStream_t (e.g. torch's current stream); NULL restores the internal stream */
+int bpx_set_stream(bpx_ctx* ctx, void* cuda_stream);
+void* bpx_device_messages(bpx_ctx* ctx);     /* current message set, packed, device pointer */
+void* bpx_device_site_tensors(bpx_ctx* ctx); /* packed, device pointer */
+void* bpx_device_residual(bpx_ctx* ctx);     /* one double: residual of the last sweep */
+int bpx_synchronize(bpx_ctx* ctx);
+
+/* ---- multi-GPU: vertex partition, one context per rank ------------------------
+ * owner[v] = rank that updates the out-edges of v.  A rank stores all site tensors it owns and all
+ * messages; per sweep it updates only its own edges and pushes the messages on cut edges straight into
+ * the peers' message sets over NVLink (peer pointers from bpx_halo_export / bpx_halo_connect).       */
+int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32_t* owner);
+/* 64-byte cudaIpcMemHandle_t of each of the two message sets */
+int bpx_halo_export(bpx_ctx* ctx, void* handles_2x64);
+int bpx_halo_connect(bpx_ctx* ctx, int peer_rank, const void* handles_2x64);
+int64_t bpx_num_cut_edges(const bpx_ctx* ctx);
+
+/* ---- shared deterministic RNG (host): splitmix64 counter -> Box-Muller standard normals ----------
+ * out[i] depends only on (seed, stream, i); complex: (N(0,1) + i N(0,1)) / sqrt(2).                 */
+int bpx_fill_randn(uint64_t seed, uint64_t stream, int dtype, int64_t n, void* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPX_H */

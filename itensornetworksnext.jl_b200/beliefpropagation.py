@@ -1,0 +1,496 @@
+"""Host-side mirror of the reference's belief-propagation interface, backed by libbpx (CUDA, sm_100a).
+
+Same names, argument meaning and error behaviour as /root/reference:
+  beliefpropagation(factors, messages; edges, stopping_criterion, message_update_algorithm)
+        ........................ src/beliefpropagation/beliefpropagation.jl:69-92
+  stopping-criterion shorthand .. :16-55      StopWhenConverged .. AlgorithmsInterfaceExtensions.jl:63-119
+  MessageUpdateAlgorithm / SimpleMessageUpdate / message_update!  :214-257
+  select_algorithm / default_algorithm .. src/select_algorithm.jl:9-51
+  MessageCache, messagecache, message_environment, incoming_messages, vertex_scalar(s), edge_scalar(s),
+  region_scalar, bethe_free_energy ........ src/beliefpropagation/messagecache.jl:15-229
+  iterate_diff ........................... beliefpropagation.jl:261-267
+
+Julia is not available in this image, so this module plays the role of julia/BPX.jl: it lowers the
+reference's containers to the canonical layout and calls the C ABI.  ALL arithmetic of the path (message
+updates, normalisation, residuals, vertex/edge scalars) runs in the CUDA library; nothing here falls
+back to the CPU, and the oracle under oracle/ is never imported.
+"""
+from __future__ import annotations
+
+import cmath
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Dict, Hashable, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .device import BPXContext
+from .graphs import NamedEdge, forest_cover_edge_sequence, to_edge
+from .tensornetwork import CanonicalProblem, Index, ITensor, ITensorNetwork, NormNetwork, canonical_arrays
+
+
+class ArgumentError(ValueError):
+    """Julia `ArgumentError` analogue."""
+
+
+# ---------------------------------------------------------------------------------------------------
+# stopping criteria (AlgorithmsInterface.StopAfterIteration, AIE.StopWhenConverged, `|`)
+# ---------------------------------------------------------------------------------------------------
+class StoppingCriterion:
+    def __or__(self, other: "StoppingCriterion") -> "StopWhenAny":
+        return StopWhenAny([self, other])
+
+
+@dataclass
+class StopAfterIteration(StoppingCriterion):
+    maxiter: int
+
+
+@dataclass
+class StopWhenConverged(StoppingCriterion):
+    tol: float
+
+    def __post_init__(self):
+        self.tol = float(self.tol)  # `tol::Float64` (AIE.jl:63-65)
+
+
+@dataclass
+class StopWhenAny(StoppingCriterion):
+    criteria: List[StoppingCriterion]
+
+    def __or__(self, other):
+        return StopWhenAny(self.criteria + [other])
+
+
+def select_beliefpropagation_stopping_criterion(c=None, **kwargs) -> StoppingCriterion:
+    """beliefpropagation.jl:16-55."""
+    if isinstance(c, StoppingCriterion):
+        return c
+    if c is None and not kwargs:
+        raise ArgumentError(
+            "`stopping_criterion` must be specified, e.g.\n"
+            "  `stopping_criterion = dict(maxiter = 10)`,\n"
+            "  `stopping_criterion = dict(maxiter = 10, tol = 1.0e-10)`, or\n"
+            "  `stopping_criterion = StopAfterIteration(10) | StopWhenConverged(1.0e-10)`."
+        )
+    if c is not None:
+        if not isinstance(c, dict):
+            raise ArgumentError(f"unsupported `stopping_criterion` {c!r}")
+        kwargs = dict(c)
+    maxiter = kwargs.pop("maxiter", None)
+    tol = kwargs.pop("tol", None)
+    if kwargs:
+        raise ArgumentError(f"Unrecognized `stopping_criterion` kwargs: {tuple(kwargs)}. Supported: `maxiter`, `tol`.")
+    if maxiter is None and tol is None:
+        raise ArgumentError("At least one of `maxiter` or `tol` must be specified.")
+    crit = None
+    if maxiter is not None:
+        crit = StopAfterIteration(int(maxiter))
+    if tol is not None:
+        conv = StopWhenConverged(tol)
+        crit = conv if crit is None else crit | conv
+    return crit
+
+
+def _flatten_criterion(c: StoppingCriterion):
+    """-> (maxiter or None, tol or None) of an OR-combination."""
+    maxiter = tol = None
+    items = c.criteria if isinstance(c, StopWhenAny) else [c]
+    for it in items:
+        if isinstance(it, StopWhenAny):
+            m, t = _flatten_criterion(it)
+        elif isinstance(it, StopAfterIteration):
+            m, t = it.maxiter, None
+        elif isinstance(it, StopWhenConverged):
+            m, t = None, it.tol
+        else:
+            raise ArgumentError(f"unsupported stopping criterion {it!r}")
+        if m is not None:
+            maxiter = m if maxiter is None else min(maxiter, m)
+        if t is not None:
+            tol = t if tol is None else max(tol, t)
+    return maxiter, tol
+
+
+# ---------------------------------------------------------------------------------------------------
+# algorithm selection (src/select_algorithm.jl)
+# ---------------------------------------------------------------------------------------------------
+class AbstractAlgorithm:
+    pass
+
+
+class MessageUpdateAlgorithm(AbstractAlgorithm):
+    """Strategy interface of beliefpropagation.jl:214-220."""
+
+
+@dataclass
+class SimpleMessageUpdate(MessageUpdateAlgorithm):
+    """The reference's default strategy (beliefpropagation.jl:237-257): per-edge exact contraction with
+    sum-normalisation, applied IN PLACE along the edge sequence (sequential schedule).  Here every
+    update of the sequence runs in the CUDA library (bpx_sweep_sequence); runs of independent updates
+    are batched into one launch."""
+
+    normalize: bool = True
+    device: int = 0
+    schedule: str = "sequential"
+
+
+@dataclass
+class B200MessageUpdate(MessageUpdateAlgorithm):
+    """The B200-native strategy: whole synchronous sweeps (every directed edge updated from the previous
+    sweep's messages) in one C-ABI call, residual fused into the kernel epilogue (bpx_sweep)."""
+
+    normalize: bool = True
+    device: int = 0
+    schedule: str = "synchronous"  # or "sequential"
+    kernel: int = _lib.BPX_KERNEL_AUTO
+
+
+def default_algorithm(f, args=None, **kwargs) -> AbstractAlgorithm:
+    if f is message_update:
+        return SimpleMessageUpdate(**kwargs)  # beliefpropagation.jl:223-225
+    raise TypeError(f"no default algorithm for {getattr(f, '__name__', f)!r}")  # MethodError analogue
+
+
+def select_algorithm(f, alg, args=None, **kwargs) -> AbstractAlgorithm:
+    """src/select_algorithm.jl:16-51: None -> default; dict (NamedTuple) -> kwargs of the default;
+    an AbstractAlgorithm instance is passed through untouched (the plugin point)."""
+    if alg is None:
+        return default_algorithm(f, args, **kwargs)
+    if isinstance(alg, dict):
+        if kwargs:
+            raise ArgumentError("Additional keyword arguments are not allowed when `alg` is a `NamedTuple`.")
+        return default_algorithm(f, args, **alg)
+    if isinstance(alg, AbstractAlgorithm):
+        if kwargs:
+            raise ArgumentError(
+                "Additional keyword arguments are not allowed when `alg` is an `AbstractAlgorithm` instance."
+            )
+        return alg
+    raise TypeError(f"cannot select an algorithm from {alg!r}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# MessageCache (messagecache.jl:15-120)
+# ---------------------------------------------------------------------------------------------------
+class MessageCache:
+    """Directed edge -> message.  Values are `ITensor`s for BP; any value type is storable (the
+    reference's container tests use strings)."""
+
+    def __init__(self, messages=None):
+        self._m: Dict[NamedEdge, object] = {}
+        self._session: Optional["_Session"] = None
+        if messages is not None:
+            items = messages.items() if hasattr(messages, "items") else messages
+            for e, m in items:
+                self._m[to_edge(e)] = m
+
+    # dictionary interface
+    def __getitem__(self, e):
+        return self._m[to_edge(e)]
+
+    def __setitem__(self, e, m):
+        self._m[to_edge(e)] = m
+        self._session = None  # device copy is stale
+
+    def __contains__(self, e):
+        return to_edge(e) in self._m
+
+    def __len__(self):
+        return len(self._m)
+
+    def keys(self):
+        return self._m.keys()
+
+    def values(self):
+        return self._m.values()
+
+    def items(self):
+        return self._m.items()
+
+    def edges(self):
+        return list(self._m.keys())
+
+    def has_edge(self, e):
+        return to_edge(e) in self._m
+
+    def vertices(self):
+        seen = {}
+        for e in self._m:
+            seen.setdefault(e.src)
+            seen.setdefault(e.dst)
+        return list(seen)
+
+    def copy(self) -> "MessageCache":
+        c = MessageCache()
+        c._m = {e: (m.copy() if hasattr(m, "copy") else m) for e, m in self._m.items()}
+        return c
+
+    def copyto(self, src, edges: Optional[Iterable] = None) -> "MessageCache":
+        items = src.items() if hasattr(src, "items") else src
+        if edges is not None:
+            edges = {to_edge(e) for e in edges}
+        for e, m in items:
+            if edges is None or to_edge(e) in edges:
+                self[e] = m
+        return self
+
+    def map(self, f: Callable) -> "MessageCache":
+        return MessageCache({e: f(m) for e, m in self._m.items()})
+
+    def in_incident_edges(self, v) -> List[NamedEdge]:
+        return [e for e in self._m if e.dst == v]
+
+    def subgraph(self, vertices) -> "MessageCache":
+        vs = set(vertices)
+        return MessageCache({e: m for e, m in self._m.items() if e.src in vs and e.dst in vs})
+
+
+def messagecache(f_or_pairs, edges=None) -> MessageCache:
+    if edges is None:
+        return MessageCache(dict(f_or_pairs))
+    return MessageCache({to_edge(e): f_or_pairs(to_edge(e)) for e in edges})
+
+
+def incoming_messages(cache: MessageCache, edge) -> List:
+    """All messages into src(edge) except the one along reverse(edge) (messagecache.jl:124-131)."""
+    e = to_edge(edge)
+    return [cache[f] for f in cache.in_incident_edges(e.src) if f != e.reverse()]
+
+
+def similar_message_environment(nn: NormNetwork) -> MessageCache:
+    """One operator-shaped message per directed edge, axes (bra link, ket link) (messagecache.jl:205-225)."""
+    out = {}
+    for v in nn.vertices():
+        for w in nn.graph.neighbors(v):
+            e = NamedEdge(w, v)
+            ket = nn.ket.linkind(e)
+            bra = Index(ket.dim, nn.braname(ket.name))
+            out[e] = ITensor(np.zeros((ket.dim, ket.dim), dtype=nn.dtype), (bra, ket))
+    return MessageCache(out)
+
+
+def message_environment(f: Callable, nn: NormNetwork) -> MessageCache:
+    return similar_message_environment(nn).map(f)
+
+
+def ones_message(m: ITensor) -> ITensor:
+    """`msg -> state(fill!(msg, true))` of test/test_apply_operator.jl:72."""
+    return ITensor(np.ones_like(m.data), m.inds)
+
+
+def identity_message(m: ITensor) -> ITensor:
+    """`one` of test/test_apply_operator.jl:37."""
+    return ITensor(np.eye(m.data.shape[0], dtype=m.data.dtype), m.inds)
+
+
+# ---------------------------------------------------------------------------------------------------
+# device session: factors + messages resident on one GPU
+# ---------------------------------------------------------------------------------------------------
+class _Session:
+    def __init__(self, factors, device: int = 0, kernel: int = _lib.BPX_KERNEL_AUTO):
+        self.factors = factors
+        self.cp: CanonicalProblem = canonical_arrays(factors)
+        ga = self.cp.ga
+        self.ctx = BPXContext(device)
+        self.ctx.set_graph(ga.src, ga.dst, ga.slot, ga.nv)
+        if kernel != _lib.BPX_KERNEL_AUTO:
+            self.ctx.set_kernel_policy(kernel)
+        self.ctx.set_dims(self.cp.dtype, self.cp.mode, self.cp.phys_dim if self.cp.mode == "norm" else None,
+                          self.cp.link_dim)
+        self.ctx.set_site_tensors(self.cp.tensors)
+
+    def _msg_array(self, e: int, m) -> np.ndarray:
+        if isinstance(m, ITensor):
+            if self.cp.mode == "norm":
+                return m.array(self.cp.bra_names[e], self.cp.ket_names[e])  # canonicalise to [bra, ket]
+            return m.array(self.cp.ket_names[e])
+        return np.asarray(m)
+
+    def upload_messages(self, cache: MessageCache):
+        ga = self.cp.ga
+        msgs = []
+        for e in range(ga.ne):
+            ne_ = ga.named_edge(e)
+            if ne_ not in cache:
+                raise KeyError(f"no message on edge {ne_!r}")
+            msgs.append(self._msg_array(e, cache[ne_]))
+        self.ctx.set_messages(msgs)
+
+    def download_messages(self, like: MessageCache) -> MessageCache:
+        ga = self.cp.ga
+        arrs = self.ctx.get_messages()
+        out = {}
+        for e in range(ga.ne):
+            ne_ = ga.named_edge(e)
+            old = like[ne_] if ne_ in like else None
+            if self.cp.mode == "norm":
+                if isinstance(old, ITensor):
+                    by = {i.name: i for i in old.inds}
+                    inds = (by[self.cp.bra_names[e]], by[self.cp.ket_names[e]])
+                else:
+                    chi = self.cp.link_dim[e]
+                    inds = (Index(chi, self.cp.bra_names[e]), Index(chi, self.cp.ket_names[e]))
+            else:
+                inds = old.inds if isinstance(old, ITensor) else (Index(self.cp.link_dim[e], self.cp.ket_names[e]),)
+            out[ne_] = ITensor(arrs[e], inds)
+        c = MessageCache(out)
+        c._session = self
+        return c
+
+
+def _session_for(factors, cache: MessageCache, device: int = 0) -> _Session:
+    s = cache._session
+    if s is not None and s.factors is factors:
+        return s
+    s = _Session(factors, device)
+    s.upload_messages(cache)
+    cache._session = s
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------
+# beliefpropagation (beliefpropagation.jl:69-92)
+# ---------------------------------------------------------------------------------------------------
+def default_beliefpropagation_edges(factors) -> List[NamedEdge]:
+    return forest_cover_edge_sequence(factors.graph)
+
+
+@dataclass
+class BeliefPropagationResult:
+    """What `StopWhenConvergedState` records (AIE.jl:67-71) plus the per-sweep residual history."""
+
+    iterations: int = 0
+    delta: float = math.inf
+    at_iteration: int = -1
+    residual_history: List[float] = field(default_factory=list)
+
+
+def beliefpropagation(factors, messages, *, edges=None, stopping_criterion=None, message_update_algorithm=None,
+                      info: Optional[BeliefPropagationResult] = None) -> MessageCache:
+    """Run belief propagation on `factors` (a NormNetwork or a single-layer ITensorNetwork) starting
+    from `messages` (dict / MessageCache keyed by directed edges).  Returns the final MessageCache."""
+    cache = messages if isinstance(messages, MessageCache) else MessageCache(messages)
+    alg = select_algorithm(message_update, message_update_algorithm, (cache, factors, None))
+    criterion = select_beliefpropagation_stopping_criterion(stopping_criterion)
+    maxiter, tol = _flatten_criterion(criterion)
+    if not isinstance(alg, (SimpleMessageUpdate, B200MessageUpdate)):
+        raise TypeError(f"unsupported message update algorithm {type(alg).__name__}")
+    if maxiter is None:
+        maxiter = 2 ** 31 - 1
+    session = _Session(factors, alg.device, getattr(alg, "kernel", _lib.BPX_KERNEL_AUTO))
+    session.upload_messages(cache)
+    if alg.schedule == "synchronous":
+        if edges is not None:
+            raise ArgumentError("`edges` selects the sequential schedule; the synchronous sweep updates every edge")
+        res, done = session.ctx.sweep(maxiter, tol if tol is not None else 0.0, alg.normalize)
+    elif alg.schedule == "sequential":
+        if edges is None:
+            edges = default_beliefpropagation_edges(factors)
+        seq = [session.cp.ga.edge_id(e) for e in edges]
+        res, done = session.ctx.sweep_sequence(seq, maxiter, tol if tol is not None else 0.0, alg.normalize)
+    else:
+        raise ArgumentError(f"unknown schedule {alg.schedule!r}")
+    if info is not None:
+        info.iterations = done
+        info.delta = res
+        info.residual_history = list(session.ctx.residual_history())
+        info.at_iteration = done if (tol is not None and done > 0 and res < tol) else -1
+    return session.download_messages(cache)
+
+
+def message_update(cache: MessageCache, factors, edge, alg=None, **kwargs) -> MessageCache:
+    """Single in-place update `message_update!(cache, factors, edge)` (beliefpropagation.jl:230-257)."""
+    alg = select_algorithm(message_update, alg, (cache, factors, edge), **kwargs)
+    s = _session_for(factors, cache, alg.device)
+    e = to_edge(edge)
+    s.ctx.sweep_sequence([s.cp.ga.edge_id(e)], 1, 0.0, alg.normalize)
+    new = s.download_messages(cache)
+    cache._m[e] = new[e]
+    cache._session = s
+    return cache
+
+
+def iterate_diff(cache1: MessageCache, cache2: MessageCache) -> float:
+    """max_e 1 - |<m1^, m2^>|^2 (beliefpropagation.jl:261-267), evaluated on the device."""
+    s = cache1._session
+    if s is None:
+        raise ArgumentError("iterate_diff needs a cache produced by (or uploaded for) a device session")
+    ga = s.cp.ga
+    other = [s._msg_array(e, cache2[ga.named_edge(e)]) for e in range(ga.ne)]
+    return s.ctx.iterate_diff(other)
+
+
+# ---------------------------------------------------------------------------------------------------
+# beliefs (messagecache.jl:139-201)
+# ---------------------------------------------------------------------------------------------------
+def vertex_scalars(factors, messages: MessageCache, vertices=None):
+    s = _session_for(factors, messages)
+    vals = s.ctx.vertex_scalars()
+    if vertices is None:
+        return list(vals)
+    return [vals[s.cp.ga.vindex[v]] for v in vertices]
+
+
+def vertex_scalar(factors, messages: MessageCache, vertex):
+    return vertex_scalars(factors, messages, [vertex])[0]
+
+
+def _edge_session(messages: MessageCache, factors=None) -> _Session:
+    if factors is not None:
+        return _session_for(factors, messages)
+    if messages._session is None:
+        raise ArgumentError("edge scalars run on the device: pass `factors=` or a cache returned by beliefpropagation")
+    return messages._session
+
+
+def edge_scalars(messages: MessageCache, factors=None):
+    """One scalar per undirected edge (repeated edges and reverses ignored, messagecache.jl:161-178)."""
+    return list(_edge_session(messages, factors).ctx.edge_scalars())
+
+
+def edge_scalar(messages: MessageCache, edge, factors=None):
+    s = _edge_session(messages, factors)
+    ga = s.cp.ga
+    e = ga.edge_id(edge)
+    k = min(e, ga.rev[e])
+    order = [x for x in range(ga.ne) if x < ga.rev[x]]
+    return s.ctx.edge_scalars()[order.index(k)]
+
+
+def region_scalar(factors, messages: MessageCache, region):
+    out = 1.0
+    for x in vertex_scalars(factors, messages, list(region)):
+        out = out * x
+    return out
+
+
+def bethe_free_energy(factors, messages: MessageCache):
+    """sum(log.(vertex scalars)) - sum(log.(edge scalars)) with the reference's complex promotion and
+    -Inf rules (messagecache.jl:185-201).  The scalars come from the device; the handful of logs are
+    host-side bookkeeping."""
+    s = _session_for(factors, messages)
+    num = np.asarray(s.ctx.vertex_scalars())
+    den = np.asarray(s.ctx.edge_scalars())
+    if np.any(num.real < 0):
+        num = num.astype(np.complex128)
+    if np.any(den.real < 0):
+        den = den.astype(np.complex128)
+    if np.any(den == 0):
+        return -math.inf
+    return np.sum(np.log(num)) - np.sum(np.log(den))
+
+
+def expect(factors: NormNetwork, messages: MessageCache, op: np.ndarray, vertices=None):
+    """Local expectation values <O_v> = (vertex contraction with O on the ket site leg) / vertex_scalar.
+    Build-defined extension (the reference has no `expect`); BASELINE.json's parity target
+    names converged local expectation values."""
+    s = _session_for(factors, messages)
+    ops = [np.asarray(op, dtype=s.cp.dtype)] * s.cp.ga.nv
+    num = s.ctx.vertex_expect_numerators(ops)
+    den = s.ctx.vertex_scalars()
+    vals = num / den
+    if vertices is None:
+        return list(vals)
+    return [vals[s.cp.ga.vindex[v]] for v in vertices]

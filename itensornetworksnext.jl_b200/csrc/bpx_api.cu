@@ -1,0 +1,907 @@
+// libbpx.so: context, bucketing, launch logic and the extern "C" surface declared in include/bpx.h.
+// Built for sm_100a only (see build.py).  No CPU fallback: compute entry points need the device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "bpx_common.cuh"
+#include "bpx_generic.cuh"
+#include "bpx_ctx.h"
+#include "bpx_fast.cuh"
+#include "bpx_halo.cuh"
+
+using namespace bpx;
+
+static thread_local std::string g_create_error;
+
+void bpx::set_error(bpx_ctx* ctx, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->err = buf;
+  else
+    g_create_error = buf;
+}
+
+#define REQUIRE(ctx, cond, ...)           \
+  do {                                    \
+    if (!(cond)) {                        \
+      set_error(ctx, __VA_ARGS__);        \
+      return BPX_ERR_INVALID;             \
+    }                                     \
+  } while (0)
+
+template <typename T>
+static int dev_alloc(bpx_ctx* ctx, T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error(ctx, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    cudaGetLastError();
+    return BPX_ERR_ALLOC;
+  }
+  return BPX_OK;
+}
+
+template <typename T>
+static int upload(bpx_ctx* ctx, T** dptr, const std::vector<T>& h) {
+  int rc = dev_alloc(ctx, dptr, h.size());
+  if (rc) return rc;
+  if (!h.empty()) BPX_CUDA(ctx, cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return BPX_OK;
+}
+
+static void free_problem(bpx_ctx* c) {
+  auto F = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  F(c->d_vdesc);
+  F(c->d_src);
+  F(c->d_slot);
+  F(c->d_rev);
+  F(c->d_msg_off);
+  F(c->d_sites);
+  F(c->d_msg[0]);
+  F(c->d_msg[1]);
+  F(c->d_msg_snapshot);
+  F(c->d_residual);
+  F(c->d_resmax);
+  F(c->d_history);
+  F(c->d_scratch);
+  F(c->d_und_edge);
+  F(c->d_owned_edges);
+  F(c->d_all_edges);
+  F(c->d_fast_scratch);
+  for (auto& b : c->buckets) {
+    F(b.d_vertices);
+    F(b.d_edges);
+    for (auto& ev : b.timing) {
+      cudaEventDestroy(ev.first);
+      cudaEventDestroy(ev.second);
+    }
+  }
+  c->buckets.clear();
+  c->dims_set = false;
+}
+
+extern "C" int bpx_version(void) { return BPX_VERSION; }
+
+extern "C" int bpx_create(int device, bpx_ctx** out) {
+  if (!out) {
+    set_error(nullptr, "bpx_create: out is NULL");
+    return BPX_ERR_INVALID;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(nullptr, "bpx_create: no CUDA device (%s); libbpx has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    cudaGetLastError();
+    return BPX_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error(nullptr, "bpx_create: device %d out of range (0..%d)", device, ndev - 1);
+    return BPX_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    set_error(nullptr, "bpx_create: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return BPX_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    set_error(nullptr, "bpx_create: device %d is sm_%d%d; libbpx is built for sm_100a only", device, prop.major,
+              prop.minor);
+    return BPX_ERR_UNSUPPORTED;
+  }
+  bpx_ctx* c = new (std::nothrow) bpx_ctx();
+  if (!c) {
+    set_error(nullptr, "bpx_create: out of host memory");
+    return BPX_ERR_ALLOC;
+  }
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error(nullptr, "bpx_create: %s", cudaGetErrorString(e));
+    delete c;
+    return BPX_ERR_CUDA;
+  }
+  c->stream = c->own_stream;
+  *out = c;
+  return BPX_OK;
+}
+
+extern "C" int bpx_destroy(bpx_ctx* ctx) {
+  if (!ctx) return BPX_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& p : ctx->peers)
+    for (int k = 0; k < 2; ++k)
+      if (p.msg[k]) cudaIpcCloseMemHandle(p.msg[k]);
+  if (ctx->d_peer_msg) cudaFree(ctx->d_peer_msg);
+  if (ctx->d_cut) cudaFree(ctx->d_cut);
+  free_problem(ctx);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return BPX_OK;
+}
+
+extern "C" const char* bpx_last_error(const bpx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+// ---- problem description -----------------------------------------------------------------------
+extern "C" int bpx_set_graph(bpx_ctx* ctx, int64_t nv, int64_t ne, const int64_t* src, const int64_t* dst,
+                             const int32_t* slot) {
+  if (!ctx) return BPX_ERR_INVALID;
+  REQUIRE(ctx, nv >= 0 && ne >= 0 && (ne == 0 || (src && dst && slot)), "bpx_set_graph: bad arguments");
+  REQUIRE(ctx, nv < (1ll << 31) && ne < (1ll << 31), "bpx_set_graph: more than 2^31 vertices/edges");
+  BPX_CUDA(ctx, cudaSetDevice(ctx->device));
+  free_problem(ctx);
+  ctx->graph_set = false;
+  ctx->nv = nv;
+  ctx->ne = ne;
+  ctx->src.assign(ne, 0);
+  ctx->dst.assign(ne, 0);
+  ctx->slot.assign(ne, 0);
+  ctx->rev.assign(ne, -1);
+  ctx->deg.assign(nv, 0);
+  std::map<std::pair<int64_t, int64_t>, int32_t> index;
+  for (int64_t e = 0; e < ne; ++e) {
+    REQUIRE(ctx, src[e] >= 0 && src[e] < nv && dst[e] >= 0 && dst[e] < nv, "bpx_set_graph: edge %lld endpoint out of range",
+            (long long)e);
+    REQUIRE(ctx, src[e] != dst[e], "bpx_set_graph: self loop on edge %lld", (long long)e);
+    REQUIRE(ctx, index.emplace(std::make_pair(src[e], dst[e]), (int32_t)e).second, "bpx_set_graph: duplicate edge %lld",
+            (long long)e);
+    ctx->src[e] = (int32_t)src[e];
+    ctx->dst[e] = (int32_t)dst[e];
+    ctx->slot[e] = slot[e];
+    ctx->deg[src[e]]++;
+  }
+  ctx->out_edge.assign(nv, std::vector<int32_t>());
+  for (int64_t v = 0; v < nv; ++v) {
+    REQUIRE(ctx, ctx->deg[v] <= BPX_MAX_DEGREE, "bpx_set_graph: vertex %lld has degree %d > BPX_MAX_DEGREE", (long long)v,
+            ctx->deg[v]);
+    ctx->out_edge[v].assign(ctx->deg[v], -1);
+  }
+  for (int64_t e = 0; e < ne; ++e) {
+    auto it = index.find(std::make_pair(dst[e], src[e]));
+    REQUIRE(ctx, it != index.end(), "bpx_set_graph: edge %lld has no reverse edge", (long long)e);
+    ctx->rev[e] = it->second;
+    const int32_t u = ctx->src[e], s = ctx->slot[e];
+    REQUIRE(ctx, s >= 0 && s < ctx->deg[u], "bpx_set_graph: slot[%lld] = %d out of range", (long long)e, s);
+    REQUIRE(ctx, ctx->out_edge[u][s] < 0, "bpx_set_graph: slot %d used twice at vertex %d", s, u);
+    ctx->out_edge[u][s] = (int32_t)e;
+  }
+  ctx->graph_set = true;
+  return BPX_OK;
+}
+
+static int pick_kernel(bpx_ctx* ctx, const Bucket& b);
+
+extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* phys_dim, const int32_t* link_dim) {
+  if (!ctx) return BPX_ERR_INVALID;
+  REQUIRE(ctx, ctx->graph_set, "bpx_set_dims: call bpx_set_graph first");
+  REQUIRE(ctx, dtype == BPX_F64 || dtype == BPX_C64, "bpx_set_dims: unknown dtype %d", dtype);
+  REQUIRE(ctx, mode == BPX_MODE_NORM || mode == BPX_MODE_SINGLE, "bpx_set_dims: unknown mode %d", mode);
+  REQUIRE(ctx, ctx->ne == 0 || link_dim, "bpx_set_dims: link_dim is NULL");
+  REQUIRE(ctx, mode == BPX_MODE_SINGLE || ctx->nv == 0 || phys_dim, "bpx_set_dims: phys_dim is NULL");
+  BPX_CUDA(ctx, cudaSetDevice(ctx->device));
+  free_problem(ctx);
+  ctx->dtype = dtype;
+  ctx->mode = mode;
+  ctx->esize = dtype == BPX_F64 ? 8 : 16;
+  const int64_t nv = ctx->nv, ne = ctx->ne;
+  ctx->link_dim.assign(link_dim, link_dim + ne);
+  for (int64_t e = 0; e < ne; ++e) {
+    REQUIRE(ctx, link_dim[e] >= 1, "bpx_set_dims: link_dim[%lld] < 1", (long long)e);
+    REQUIRE(ctx, link_dim[e] == link_dim[ctx->rev[e]], "bpx_set_dims: link_dim differs between edge %lld and its reverse",
+            (long long)e);
+  }
+  ctx->phys_dim.assign(nv, 1);
+  if (mode == BPX_MODE_NORM)
+    for (int64_t v = 0; v < nv; ++v) {
+      REQUIRE(ctx, phys_dim[v] >= 1, "bpx_set_dims: phys_dim[%lld] < 1", (long long)v);
+      ctx->phys_dim[v] = phys_dim[v];
+    }
+  // packed layouts
+  ctx->site_off.assign(nv + 1, 0);
+  ctx->msg_off.assign(ne + 1, 0);
+  std::vector<VDesc> vdesc(nv);
+  int64_t max_n = 1;
+  int max_out = 1;
+  for (int64_t v = 0; v < nv; ++v) {
+    VDesc& d = vdesc[v];
+    memset(&d, 0, sizeof(d));
+    d.z = ctx->deg[v];
+    d.d = ctx->phys_dim[v];
+    int64_t n = d.d;
+    for (int i = 0; i < d.z; ++i) {
+      const int32_t e = ctx->out_edge[v][i];
+      d.dim[i] = ctx->link_dim[e];
+      d.out_edge[i] = e;
+      d.in_edge[i] = ctx->rev[e];
+      n *= d.dim[i];
+      REQUIRE(ctx, n < (1ll << 40), "bpx_set_dims: site tensor of vertex %lld too large", (long long)v);
+    }
+    d.n = n;
+    d.site_off = ctx->site_off[v];
+    ctx->site_off[v + 1] = ctx->site_off[v] + n;
+    max_n = std::max(max_n, n);
+  }
+  for (int64_t e = 0; e < ne; ++e) {
+    const int64_t chi = ctx->link_dim[e];
+    const int64_t n = mode == BPX_MODE_NORM ? chi * chi : chi;
+    ctx->msg_off[e + 1] = ctx->msg_off[e] + n;
+    max_out = std::max<int64_t>(max_out, n);
+  }
+  ctx->max_site_elems = max_n;
+  ctx->max_msg_elems = max_out;
+
+  int rc;
+  if ((rc = upload(ctx, &ctx->d_vdesc, vdesc))) return rc;
+  if ((rc = upload(ctx, &ctx->d_src, ctx->src))) return rc;
+  if ((rc = upload(ctx, &ctx->d_slot, ctx->slot))) return rc;
+  if ((rc = upload(ctx, &ctx->d_rev, ctx->rev))) return rc;
+  if ((rc = upload(ctx, &ctx->d_msg_off, ctx->msg_off))) return rc;
+  const size_t es = ctx->esize;
+  if ((rc = dev_alloc(ctx, (char**)&ctx->d_sites, (size_t)ctx->site_off[nv] * es))) return rc;
+  for (int k = 0; k < 2; ++k) {
+    if ((rc = dev_alloc(ctx, (char**)&ctx->d_msg[k], (size_t)ctx->msg_off[ne] * es))) return rc;
+    BPX_CUDA(ctx, cudaMemset(ctx->d_msg[k], 0, std::max<size_t>(1, (size_t)ctx->msg_off[ne] * es)));
+  }
+  ctx->cur = 0;
+  if ((rc = dev_alloc(ctx, &ctx->d_residual, (size_t)ne))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_resmax, 2))) return rc;
+  ctx->history_cap = 4096;
+  if ((rc = dev_alloc(ctx, &ctx->d_history, (size_t)ctx->history_cap))) return rc;
+  std::vector<int32_t> und;
+  for (int64_t e = 0; e < ne; ++e)
+    if (e < ctx->rev[e]) und.push_back((int32_t)e);
+  ctx->n_und = (int64_t)und.size();
+  if ((rc = upload(ctx, &ctx->d_und_edge, und))) return rc;
+
+  // generic-kernel geometry: shared memory if two tensor copies (+ one output) fit, else global scratch
+  const int64_t smem_need = (2 * max_n + max_out) * (int64_t)es;
+  if (smem_need <= (int64_t)ctx->max_smem_optin - 2048) {
+    ctx->gen_smem_elems = (int)max_n;
+    ctx->gen_smem_bytes = (int)smem_need;
+    ctx->gen_grid = ctx->num_sms * 8;
+  } else {
+    ctx->gen_smem_elems = 0;
+    ctx->gen_smem_bytes = (int)(max_out * es);
+    ctx->gen_grid = ctx->num_sms * 4;
+    if ((rc = dev_alloc(ctx, (char**)&ctx->d_scratch, (size_t)ctx->gen_grid * 2 * max_n * es))) return rc;
+  }
+
+  // buckets: vertices sharing (degree, phys dim, link dims)
+  std::map<std::vector<int32_t>, int> bucket_of;
+  for (int64_t v = 0; v < nv; ++v) {
+    std::vector<int32_t> key;
+    key.push_back(ctx->deg[v]);
+    key.push_back(ctx->phys_dim[v]);
+    for (int i = 0; i < ctx->deg[v]; ++i) key.push_back(vdesc[v].dim[i]);
+    auto it = bucket_of.find(key);
+    if (it == bucket_of.end()) {
+      it = bucket_of.emplace(key, (int)ctx->buckets.size()).first;
+      Bucket b;
+      b.z = ctx->deg[v];
+      b.d = ctx->phys_dim[v];
+      b.chi = b.z > 0 ? vdesc[v].dim[0] : 0;
+      for (int i = 1; i < b.z; ++i)
+        if (vdesc[v].dim[i] != b.chi) b.chi = 0;
+      ctx->buckets.push_back(b);
+    }
+    ctx->buckets[it->second].vertices.push_back((int32_t)v);
+  }
+  ctx->owner.clear();
+  ctx->rank = 0;
+  ctx->nranks = 1;
+  ctx->dims_set = true;
+  return rebuild_work_lists(ctx);
+}
+
+// (re)derive per-bucket vertex/edge lists restricted to the vertices this rank owns
+int bpx::rebuild_work_lists(bpx_ctx* ctx) {
+  auto F = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  std::vector<int32_t> owned_edges;
+  for (auto& b : ctx->buckets) {
+    F(b.d_vertices);
+    F(b.d_edges);
+    b.my_vertices.clear();
+    b.my_edges.clear();
+    for (int32_t v : b.vertices) {
+      if (!ctx->owner.empty() && ctx->owner[v] != ctx->rank) continue;
+      b.my_vertices.push_back(v);
+      for (int32_t e : ctx->out_edge[v]) b.my_edges.push_back(e);
+    }
+    int rc;
+    if ((rc = upload(ctx, &b.d_vertices, b.my_vertices))) return rc;
+    if ((rc = upload(ctx, &b.d_edges, b.my_edges))) return rc;
+    b.kernel = pick_kernel(ctx, b);
+    owned_edges.insert(owned_edges.end(), b.my_edges.begin(), b.my_edges.end());
+  }
+  std::sort(owned_edges.begin(), owned_edges.end());
+  F(ctx->d_owned_edges);
+  ctx->n_owned_edges = (int64_t)owned_edges.size();
+  int rc = upload(ctx, &ctx->d_owned_edges, owned_edges);
+  if (rc) return rc;
+  return fast_prepare(ctx);
+}
+
+static int pick_kernel(bpx_ctx* ctx, const Bucket& b) {
+  const int want = ctx->kernel_policy;
+  if (want == BPX_KERNEL_GENERIC) return BPX_KERNEL_GENERIC;
+  const int best = fast_kernel_for(ctx, b);  // BPX_KERNEL_GENERIC if no specialised kernel applies
+  if (want == BPX_KERNEL_AUTO) return best;
+  return fast_kernel_supported(ctx, b, want) ? want : BPX_KERNEL_GENERIC;
+}
+
+extern "C" int64_t bpx_num_vertices(const bpx_ctx* ctx) { return ctx ? ctx->nv : -1; }
+extern "C" int64_t bpx_num_edges(const bpx_ctx* ctx) { return ctx ? ctx->ne : -1; }
+extern "C" int64_t bpx_rev(const bpx_ctx* ctx, int64_t e) {
+  return (ctx && ctx->graph_set && e >= 0 && e < ctx->ne) ? ctx->rev[e] : -1;
+}
+extern "C" int64_t bpx_site_offset(const bpx_ctx* ctx, int64_t v) {
+  return (ctx && ctx->dims_set && v >= 0 && v <= ctx->nv) ? ctx->site_off[v] : -1;
+}
+extern "C" int64_t bpx_message_offset(const bpx_ctx* ctx, int64_t e) {
+  return (ctx && ctx->dims_set && e >= 0 && e <= ctx->ne) ? ctx->msg_off[e] : -1;
+}
+
+#define NEED_DIMS(ctx, name)                                     \
+  do {                                                           \
+    if (!ctx) return BPX_ERR_INVALID;                            \
+    REQUIRE(ctx, ctx->dims_set, name ": call bpx_set_dims first"); \
+    BPX_CUDA(ctx, cudaSetDevice(ctx->device));                   \
+  } while (0)
+
+extern "C" int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed) {
+  NEED_DIMS(ctx, "bpx_set_site_tensors");
+  REQUIRE(ctx, packed || ctx->site_off[ctx->nv] == 0, "bpx_set_site_tensors: NULL data");
+  // a rank only needs the tensors it owns, but uploading all keeps offsets identical everywhere
+  BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sites, packed, (size_t)ctx->site_off[ctx->nv] * ctx->esize, cudaMemcpyHostToDevice,
+                                ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
+extern "C" int bpx_set_site_tensor(bpx_ctx* ctx, int64_t v, const void* data) {
+  NEED_DIMS(ctx, "bpx_set_site_tensor");
+  REQUIRE(ctx, v >= 0 && v < ctx->nv && data, "bpx_set_site_tensor: bad arguments");
+  const size_t off = (size_t)ctx->site_off[v] * ctx->esize, n = (size_t)(ctx->site_off[v + 1] - ctx->site_off[v]) * ctx->esize;
+  BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_sites + off, data, n, cudaMemcpyHostToDevice, ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
+extern "C" int bpx_set_messages(bpx_ctx* ctx, const void* packed) {
+  NEED_DIMS(ctx, "bpx_set_messages");
+  REQUIRE(ctx, packed || ctx->msg_off[ctx->ne] == 0, "bpx_set_messages: NULL data");
+  const size_t n = (size_t)ctx->msg_off[ctx->ne] * ctx->esize;
+  ctx->cur = 0;  // all ranks of a partitioned run restart on the same parity
+  BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[ctx->cur], packed, n, cudaMemcpyHostToDevice, ctx->stream));
+  // both sets hold every message, so that edges a rank does not own keep their value across ping-pong
+  BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[ctx->cur ^ 1], ctx->d_msg[ctx->cur], n, cudaMemcpyDeviceToDevice, ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
+extern "C" int bpx_get_messages(bpx_ctx* ctx, void* packed) {
+  NEED_DIMS(ctx, "bpx_get_messages");
+  REQUIRE(ctx, packed || ctx->msg_off[ctx->ne] == 0, "bpx_get_messages: NULL data");
+  BPX_CUDA(ctx, cudaMemcpyAsync(packed, ctx->d_msg[ctx->cur], (size_t)ctx->msg_off[ctx->ne] * ctx->esize, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
+extern "C" int bpx_get_message(bpx_ctx* ctx, int64_t e, void* data) {
+  NEED_DIMS(ctx, "bpx_get_message");
+  REQUIRE(ctx, e >= 0 && e < ctx->ne && data, "bpx_get_message: bad arguments");
+  const size_t off = (size_t)ctx->msg_off[e] * ctx->esize, n = (size_t)(ctx->msg_off[e + 1] - ctx->msg_off[e]) * ctx->esize;
+  BPX_CUDA(ctx, cudaMemcpyAsync(data, (char*)ctx->d_msg[ctx->cur] + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
+// ---- launches -----------------------------------------------------------------------------------
+static GenericArgs generic_args(bpx_ctx* ctx, const void* msg_in, void* msg_out, const int32_t* work, int64_t n_work,
+                                int normalize) {
+  GenericArgs g;
+  memset(&g, 0, sizeof(g));
+  g.vdesc = ctx->d_vdesc;
+  g.src = ctx->d_src;
+  g.slot = ctx->d_slot;
+  g.msg_off = ctx->d_msg_off;
+  g.sites = ctx->d_sites;
+  g.msg_in = msg_in;
+  g.msg_out = msg_out;
+  g.residual = ctx->d_residual;
+  g.work = work;
+  g.n_work = n_work;
+  g.scratch = ctx->d_scratch;
+  g.scratch_elems = ctx->max_site_elems;
+  g.smem_elems = ctx->gen_smem_elems;
+  g.normalize = normalize;
+  g.mode = ctx->mode;
+  return g;
+}
+
+template <typename K>
+static int set_smem(bpx_ctx* ctx, K kernel, int bytes) {
+  if (bytes > 48 * 1024) BPX_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return BPX_OK;
+}
+
+int bpx::launch_generic_update(bpx_ctx* ctx, const void* msg_in, void* msg_out, const int32_t* d_work, int64_t n_work,
+                               int normalize) {
+  if (n_work == 0) return BPX_OK;
+  GenericArgs g = generic_args(ctx, msg_in, msg_out, d_work, n_work, normalize);
+  const int grid = (int)std::min<int64_t>(n_work, ctx->gen_grid);
+  int rc;
+  if (ctx->dtype == BPX_F64) {
+    if ((rc = set_smem(ctx, bp_update_generic<double>, ctx->gen_smem_bytes))) return rc;
+    bp_update_generic<double><<<grid, 256, ctx->gen_smem_bytes, ctx->stream>>>(g);
+  } else {
+    if ((rc = set_smem(ctx, bp_update_generic<c64>, ctx->gen_smem_bytes))) return rc;
+    bp_update_generic<c64><<<grid, 256, ctx->gen_smem_bytes, ctx->stream>>>(g);
+  }
+  ctx->n_launches++;
+  BPX_CUDA(ctx, cudaGetLastError());
+  return BPX_OK;
+}
+
+static int launch_residual_max(bpx_ctx* ctx, const int32_t* list, int64_t n, int hist_idx) {
+  bp_residual_max<<<1, 1024, 0, ctx->stream>>>(ctx->d_residual, list, n, ctx->d_resmax,
+                                               hist_idx < ctx->history_cap ? ctx->d_history : nullptr, hist_idx);
+  ctx->n_launches++;
+  BPX_CUDA(ctx, cudaGetLastError());
+  return BPX_OK;
+}
+
+// one synchronous sweep: every owned directed edge, bucket by bucket, from d_msg[cur] into d_msg[cur^1]
+static int sweep_once(bpx_ctx* ctx, int normalize, int hist_idx) {
+  const void* in = ctx->d_msg[ctx->cur];
+  void* out = ctx->d_msg[ctx->cur ^ 1];
+  int rc;
+  for (auto& b : ctx->buckets) {
+    if (b.my_edges.empty()) continue;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->profiling && b.timing.size() < 8192) {
+      BPX_CUDA(ctx, cudaEventCreate(&ev0));
+      BPX_CUDA(ctx, cudaEventCreate(&ev1));
+      b.timing.emplace_back(ev0, ev1);
+      BPX_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    if (b.kernel == BPX_KERNEL_GENERIC)
+      rc = launch_generic_update(ctx, in, out, b.d_edges, (int64_t)b.my_edges.size(), normalize);
+    else
+      rc = launch_fast_update(ctx, b, in, out, normalize);
+    if (rc) return rc;
+    if (ev1) BPX_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+  }
+  if ((rc = halo_push(ctx, out))) return rc;
+  if ((rc = launch_residual_max(ctx, ctx->nranks > 1 ? ctx->d_owned_edges : nullptr,
+                                ctx->nranks > 1 ? ctx->n_owned_edges : ctx->ne, hist_idx)))
+    return rc;
+  ctx->cur ^= 1;
+  ctx->n_updates += ctx->n_owned_edges;
+  ctx->n_sweeps++;
+  return BPX_OK;
+}
+
+extern "C" int bpx_sweep(bpx_ctx* ctx, int max_sweeps, double tol, int normalize, double* residual_out, int* sweeps_done) {
+  NEED_DIMS(ctx, "bpx_sweep");
+  REQUIRE(ctx, max_sweeps >= 0, "bpx_sweep: max_sweeps < 0");
+  int done = 0;
+  double res = INFINITY;
+  ctx->history_len = 0;
+  for (int it = 0; it < max_sweeps; ++it) {
+    int rc = sweep_once(ctx, normalize, it);
+    if (rc) return rc;
+    ++done;
+    ctx->history_len = std::min(done, ctx->history_cap);
+    if (tol > 0.0 && ctx->nranks == 1) {
+      // StopWhenConverged: stop after the first sweep whose residual is below tol
+      BPX_CUDA(ctx, cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (res < tol) break;
+    }
+  }
+  if (done > 0 && (residual_out || !(tol > 0.0 && ctx->nranks == 1))) {
+    BPX_CUDA(ctx, cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (residual_out) *residual_out = res;
+  if (sweeps_done) *sweeps_done = done;
+  return BPX_OK;
+}
+
+extern "C" int bpx_sweep_async(bpx_ctx* ctx, int n_sweeps, int normalize) {
+  NEED_DIMS(ctx, "bpx_sweep_async");
+  REQUIRE(ctx, n_sweeps >= 0, "bpx_sweep_async: n_sweeps < 0");
+  for (int it = 0; it < n_sweeps; ++it) {
+    int rc = sweep_once(ctx, normalize, ctx->history_len < ctx->history_cap ? ctx->history_len : ctx->history_cap);
+    if (rc) return rc;
+    if (ctx->history_len < ctx->history_cap) ctx->history_len++;
+  }
+  return BPX_OK;
+}
+
+extern "C" int bpx_set_profiling(bpx_ctx* ctx, int enable) {
+  NEED_DIMS(ctx, "bpx_set_profiling");
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& b : ctx->buckets) {
+    for (auto& ev : b.timing) {
+      cudaEventDestroy(ev.first);
+      cudaEventDestroy(ev.second);
+    }
+    b.timing.clear();
+    b.timed_ms = 0.0;
+    b.timed_launches = 0;
+  }
+  ctx->profiling = enable != 0;
+  return BPX_OK;
+}
+
+extern "C" int bpx_bucket_time(bpx_ctx* ctx, int bucket, double* total_ms, int64_t* launches) {
+  NEED_DIMS(ctx, "bpx_bucket_time");
+  REQUIRE(ctx, bucket >= 0 && bucket < (int)ctx->buckets.size(), "bpx_bucket_time: bucket out of range");
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  Bucket& b = ctx->buckets[bucket];
+  for (auto& ev : b.timing) {
+    float ms = 0.f;
+    BPX_CUDA(ctx, cudaEventElapsedTime(&ms, ev.first, ev.second));
+    b.timed_ms += ms;
+    b.timed_launches++;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  b.timing.clear();
+  if (total_ms) *total_ms = b.timed_ms;
+  if (launches) *launches = b.timed_launches;
+  return BPX_OK;
+}
+
+extern "C" int bpx_sweep_sequence(bpx_ctx* ctx, const int64_t* edge_seq, int64_t n_seq, int max_sweeps, double tol,
+                                  int normalize, double* residual_out, int* sweeps_done) {
+  NEED_DIMS(ctx, "bpx_sweep_sequence");
+  REQUIRE(ctx, ctx->nranks == 1, "bpx_sweep_sequence: the sequential schedule is single-GPU only");
+  REQUIRE(ctx, max_sweeps >= 0 && n_seq >= 0 && (n_seq == 0 || edge_seq), "bpx_sweep_sequence: bad arguments");
+  const int64_t ne = ctx->ne;
+  // split the sequence into maximal runs of consecutive updates whose write set is disjoint from the
+  // run's read set: inside a run the in-place updates are independent and go out as one launch
+  std::vector<int32_t> flat;
+  std::vector<int64_t> batch_ptr(1, 0);
+  {
+    std::vector<int> r_stamp(ne, -1), w_stamp(ne, -1);
+    int batch = 0;
+    for (int64_t i = 0; i < n_seq; ++i) {
+      const int64_t e = edge_seq[i];
+      REQUIRE(ctx, e >= 0 && e < ne, "bpx_sweep_sequence: edge_seq[%lld] out of range", (long long)i);
+      const int32_t u = ctx->src[e];
+      bool conflict = (r_stamp[e] == batch) || (w_stamp[e] == batch);
+      for (int32_t f : ctx->out_edge[u])
+        if (f != e && w_stamp[ctx->rev[f]] == batch) conflict = true;
+      if (conflict) {
+        batch_ptr.push_back((int64_t)flat.size());
+        ++batch;
+      }
+      w_stamp[e] = batch;
+      for (int32_t f : ctx->out_edge[u])
+        if (f != e) r_stamp[ctx->rev[f]] = batch;
+      flat.push_back((int32_t)e);
+    }
+    batch_ptr.push_back((int64_t)flat.size());
+  }
+  int32_t* d_flat = nullptr;
+  int rc = upload(ctx, &d_flat, flat);
+  if (rc) return rc;
+  const size_t msg_bytes = (size_t)ctx->msg_off[ne] * ctx->esize;
+  if (!ctx->d_msg_snapshot && (rc = dev_alloc(ctx, (char**)&ctx->d_msg_snapshot, msg_bytes))) {
+    cudaFree(d_flat);
+    return rc;
+  }
+  int done = 0;
+  double res = INFINITY;
+  ctx->history_len = 0;
+  void* m = ctx->d_msg[ctx->cur];
+  for (int it = 0; it < max_sweeps && rc == BPX_OK; ++it) {
+    cudaMemcpyAsync(ctx->d_msg_snapshot, m, msg_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    for (size_t b = 0; b + 1 < batch_ptr.size() && rc == BPX_OK; ++b) {
+      const int64_t n = batch_ptr[b + 1] - batch_ptr[b];
+      // edges of one run may belong to different buckets: the generic kernel takes any mix
+      rc = launch_generic_update(ctx, m, m, d_flat + batch_ptr[b], n, normalize);
+    }
+    if (rc) break;
+    // iterate_diff against the previous sweep over ALL edges (beliefpropagation.jl:261-267)
+    if (ne > 0) {
+      const int threads = 256;
+      const int64_t blocks = (ne * 32 + threads - 1) / threads;
+      if (ctx->dtype == BPX_F64)
+        bp_edge_residual<double><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const double*)ctx->d_msg_snapshot, (const double*)m,
+                                                                               ctx->d_msg_off, ne, ctx->d_residual);
+      else
+        bp_edge_residual<c64><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const c64*)ctx->d_msg_snapshot, (const c64*)m,
+                                                                            ctx->d_msg_off, ne, ctx->d_residual);
+      ctx->n_launches++;
+    }
+    rc = launch_residual_max(ctx, nullptr, ne, it);
+    if (rc) break;
+    ++done;
+    ctx->n_updates += n_seq;
+    ctx->n_sweeps++;
+    ctx->history_len = std::min(done, ctx->history_cap);
+    if (tol > 0.0) {
+      cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      if (res < tol) break;
+    }
+  }
+  if (rc == BPX_OK && done > 0) cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_flat);
+  if (rc) return rc;
+  BPX_CUDA(ctx, ce);
+  // keep both sets identical so a later synchronous sweep starts from the same iterate
+  BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[ctx->cur ^ 1], m, msg_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (residual_out) *residual_out = res;
+  if (sweeps_done) *sweeps_done = done;
+  return BPX_OK;
+}
+
+extern "C" int bpx_residual_history(bpx_ctx* ctx, double* out, int n, int* n_out) {
+  NEED_DIMS(ctx, "bpx_residual_history");
+  const int k = std::max(0, std::min(n, ctx->history_len));
+  if (k > 0) {
+    REQUIRE(ctx, out, "bpx_residual_history: out is NULL");
+    BPX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_history, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (n_out) *n_out = k;
+  return BPX_OK;
+}
+
+extern "C" int bpx_last_residual(bpx_ctx* ctx, double* out) {
+  NEED_DIMS(ctx, "bpx_last_residual");
+  REQUIRE(ctx, out, "bpx_last_residual: out is NULL");
+  BPX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
+extern "C" int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* out) {
+  NEED_DIMS(ctx, "bpx_iterate_diff");
+  REQUIRE(ctx, out && (other_packed || ctx->ne == 0), "bpx_iterate_diff: bad arguments");
+  const int64_t ne = ctx->ne;
+  if (ne == 0) {
+    *out = -INFINITY;
+    return BPX_OK;
+  }
+  const size_t msg_bytes = (size_t)ctx->msg_off[ne] * ctx->esize;
+  int rc;
+  if (!ctx->d_msg_snapshot && (rc = dev_alloc(ctx, (char**)&ctx->d_msg_snapshot, msg_bytes))) return rc;
+  BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg_snapshot, other_packed, msg_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = 256;
+  const int64_t blocks = (ne * 32 + threads - 1) / threads;
+  if (ctx->dtype == BPX_F64)
+    bp_edge_residual<double><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const double*)ctx->d_msg[ctx->cur],
+                                                                           (const double*)ctx->d_msg_snapshot, ctx->d_msg_off, ne,
+                                                                           ctx->d_residual);
+  else
+    bp_edge_residual<c64><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const c64*)ctx->d_msg[ctx->cur],
+                                                                        (const c64*)ctx->d_msg_snapshot, ctx->d_msg_off, ne,
+                                                                        ctx->d_residual);
+  ctx->n_launches++;
+  BPX_CUDA(ctx, cudaGetLastError());
+  if ((rc = launch_residual_max(ctx, nullptr, ne, ctx->history_cap))) return rc;
+  BPX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
+// ---- beliefs --------------------------------------------------------------------------------------
+static int vertex_scalars_impl(bpx_ctx* ctx, const void* ops_packed, void* out) {
+  const int64_t nv = ctx->nv;
+  if (nv == 0) return BPX_OK;
+  REQUIRE(ctx, out, "vertex scalars: out is NULL");
+  char* d_out = nullptr;
+  char* d_ops = nullptr;
+  int64_t* d_op_off = nullptr;
+  int rc = dev_alloc(ctx, &d_out, (size_t)nv * ctx->esize);
+  if (rc) return rc;
+  if (ops_packed) {
+    std::vector<int64_t> op_off(nv + 1, 0);
+    for (int64_t v = 0; v < nv; ++v) op_off[v + 1] = op_off[v] + (int64_t)ctx->phys_dim[v] * ctx->phys_dim[v];
+    if ((rc = upload(ctx, &d_op_off, op_off)) || (rc = dev_alloc(ctx, &d_ops, (size_t)op_off[nv] * ctx->esize))) {
+      cudaFree(d_out);
+      cudaFree(d_op_off);
+      return rc;
+    }
+    cudaMemcpyAsync(d_ops, ops_packed, (size_t)op_off[nv] * ctx->esize, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  GenericArgs g = generic_args(ctx, ctx->d_msg[ctx->cur], nullptr, nullptr, nv, 0);
+  g.ops = d_ops;
+  g.op_off = d_op_off;
+  g.scalars_out = d_out;
+  const int grid = (int)std::min<int64_t>(nv, ctx->gen_grid);
+  // the scalar kernel needs no output staging, but sharing the update kernel's geometry keeps it simple
+  if (ctx->dtype == BPX_F64) {
+    rc = set_smem(ctx, bp_vertex_scalar_generic<double>, ctx->gen_smem_bytes);
+    if (!rc) bp_vertex_scalar_generic<double><<<grid, 256, ctx->gen_smem_bytes, ctx->stream>>>(g);
+  } else {
+    rc = set_smem(ctx, bp_vertex_scalar_generic<c64>, ctx->gen_smem_bytes);
+    if (!rc) bp_vertex_scalar_generic<c64><<<grid, 256, ctx->gen_smem_bytes, ctx->stream>>>(g);
+  }
+  ctx->n_launches++;
+  cudaError_t ce = cudaGetLastError();
+  if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_out, (size_t)nv * ctx->esize, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out);
+  cudaFree(d_ops);
+  cudaFree(d_op_off);
+  if (rc) return rc;
+  BPX_CUDA(ctx, ce);
+  BPX_CUDA(ctx, ce2);
+  return BPX_OK;
+}
+
+extern "C" int bpx_vertex_scalars(bpx_ctx* ctx, void* out) {
+  NEED_DIMS(ctx, "bpx_vertex_scalars");
+  return vertex_scalars_impl(ctx, nullptr, out);
+}
+
+extern "C" int bpx_vertex_expect_numerators(bpx_ctx* ctx, const void* ops_packed, void* out) {
+  NEED_DIMS(ctx, "bpx_vertex_expect_numerators");
+  REQUIRE(ctx, ctx->mode == BPX_MODE_NORM, "bpx_vertex_expect_numerators: NORM mode only");
+  REQUIRE(ctx, ops_packed || ctx->nv == 0, "bpx_vertex_expect_numerators: ops is NULL");
+  return vertex_scalars_impl(ctx, ops_packed, out);
+}
+
+extern "C" int bpx_edge_scalars(bpx_ctx* ctx, void* out) {
+  NEED_DIMS(ctx, "bpx_edge_scalars");
+  const int64_t n = ctx->n_und;
+  if (n == 0) return BPX_OK;
+  REQUIRE(ctx, out, "bpx_edge_scalars: out is NULL");
+  char* d_out = nullptr;
+  int rc = dev_alloc(ctx, &d_out, (size_t)n * ctx->esize);
+  if (rc) return rc;
+  const int threads = 256;
+  const int64_t blocks = (n * 32 + threads - 1) / threads;
+  if (ctx->dtype == BPX_F64)
+    bp_edge_scalar<double><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const double*)ctx->d_msg[ctx->cur], ctx->d_msg_off,
+                                                                         ctx->d_und_edge, ctx->d_rev, n, (double*)d_out);
+  else
+    bp_edge_scalar<c64><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const c64*)ctx->d_msg[ctx->cur], ctx->d_msg_off,
+                                                                      ctx->d_und_edge, ctx->d_rev, n, (c64*)d_out);
+  ctx->n_launches++;
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_out, (size_t)n * ctx->esize, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out);
+  BPX_CUDA(ctx, ce);
+  BPX_CUDA(ctx, ce2);
+  return BPX_OK;
+}
+
+// ---- introspection ------------------------------------------------------------------------------
+extern "C" int bpx_num_buckets(const bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? (int)ctx->buckets.size() : -1; }
+
+extern "C" int bpx_bucket_info(const bpx_ctx* ctx, int bucket, int64_t info[6]) {
+  if (!ctx || !ctx->dims_set || bucket < 0 || bucket >= (int)ctx->buckets.size() || !info) return BPX_ERR_INVALID;
+  const Bucket& b = ctx->buckets[bucket];
+  info[0] = b.z;
+  info[1] = b.chi;
+  info[2] = b.d;
+  info[3] = (int64_t)b.my_vertices.size();
+  info[4] = (int64_t)b.my_edges.size();
+  info[5] = b.kernel;
+  return BPX_OK;
+}
+
+extern "C" int bpx_set_kernel_policy(bpx_ctx* ctx, int kernel) {
+  if (!ctx) return BPX_ERR_INVALID;
+  REQUIRE(ctx, kernel >= BPX_KERNEL_AUTO && kernel <= BPX_KERNEL_SLICED, "bpx_set_kernel_policy: unknown kernel %d", kernel);
+  ctx->kernel_policy = kernel;
+  if (ctx->dims_set) {
+    BPX_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (auto& b : ctx->buckets) b.kernel = pick_kernel(ctx, b);
+    return fast_prepare(ctx);
+  }
+  return BPX_OK;
+}
+
+extern "C" int bpx_counters(bpx_ctx* ctx, int64_t out[3], int reset) {
+  if (!ctx) return BPX_ERR_INVALID;
+  if (out) {
+    out[0] = ctx->n_launches;
+    out[1] = ctx->n_updates;
+    out[2] = ctx->n_sweeps;
+  }
+  if (reset) ctx->n_launches = ctx->n_updates = ctx->n_sweeps = 0;
+  return BPX_OK;
+}
+
+extern "C" int bpx_set_stream(bpx_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return BPX_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return BPX_OK;
+}
+
+extern "C" void* bpx_device_messages(bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? ctx->d_msg[ctx->cur] : nullptr; }
+extern "C" void* bpx_device_site_tensors(bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? ctx->d_sites : nullptr; }
+extern "C" void* bpx_device_residual(bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? ctx->d_resmax : nullptr; }
+
+extern "C" int bpx_synchronize(bpx_ctx* ctx) {
+  if (!ctx) return BPX_ERR_INVALID;
+  BPX_CUDA(ctx, cudaSetDevice(ctx->device));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
+// ---- shared RNG -----------------------------------------------------------------------------------
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+static inline double randn_at(uint64_t seed, uint64_t stream, uint64_t i) {
+  const uint64_t base = splitmix64(seed ^ splitmix64(stream + 0x632BE59BD9B4E019ull));
+  const uint64_t a = splitmix64(base + 2 * i), b = splitmix64(base + 2 * i + 1);
+  const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0, 1]
+  const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);          // [0, 1)
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+
+extern "C" int bpx_fill_randn(uint64_t seed, uint64_t stream, int dtype, int64_t n, void* out) {
+  if (n < 0 || (n > 0 && !out) || (dtype != BPX_F64 && dtype != BPX_C64)) return BPX_ERR_INVALID;
+  double* o = (double*)out;
+  if (dtype == BPX_F64) {
+    for (int64_t i = 0; i < n; ++i) o[i] = randn_at(seed, stream, (uint64_t)i);
+  } else {
+    const double s = 0.70710678118654752440;
+    for (int64_t i = 0; i < 2 * n; ++i) o[i] = s * randn_at(seed, stream, (uint64_t)i);
+  }
+  return BPX_OK;
+}

@@ -1,0 +1,127 @@
+// Shared device/host types for libbpx (B200 / sm_100a).  See include/bpx.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bpx.h"
+
+namespace bpx {
+
+// ---- element types -------------------------------------------------------------------------------
+struct c64 {  // Julia ComplexF64: interleaved (re, im)
+  double re, im;
+};
+
+__host__ __device__ __forceinline__ c64 make_c64(double r, double i) {
+  c64 z;
+  z.re = r;
+  z.im = i;
+  return z;
+}
+
+template <typename T>
+struct Elem;
+
+template <>
+struct Elem<double> {
+  static constexpr bool is_complex = false;
+  __host__ __device__ static __forceinline__ double zero() { return 0.0; }
+  __host__ __device__ static __forceinline__ double conj(double a) { return a; }
+  // acc + a*b
+  __host__ __device__ static __forceinline__ double fma(double a, double b, double acc) {
+    return ::fma(a, b, acc);
+  }
+  __host__ __device__ static __forceinline__ double add(double a, double b) { return a + b; }
+  __host__ __device__ static __forceinline__ double mul(double a, double b) { return a * b; }
+  __host__ __device__ static __forceinline__ bool is_zero(double a) { return a == 0.0; }
+  __host__ __device__ static __forceinline__ double div(double a, double b) { return a / b; }
+  __host__ __device__ static __forceinline__ double abs2(double a) { return a * a; }
+  __device__ static __forceinline__ double shfl_xor(double a, int m) { return __shfl_xor_sync(0xffffffffu, a, m); }
+};
+
+template <>
+struct Elem<c64> {
+  static constexpr bool is_complex = true;
+  __host__ __device__ static __forceinline__ c64 zero() { return make_c64(0.0, 0.0); }
+  __host__ __device__ static __forceinline__ c64 conj(c64 a) { return make_c64(a.re, -a.im); }
+  __host__ __device__ static __forceinline__ c64 fma(c64 a, c64 b, c64 acc) {
+    acc.re = ::fma(a.re, b.re, acc.re);
+    acc.re = ::fma(-a.im, b.im, acc.re);
+    acc.im = ::fma(a.re, b.im, acc.im);
+    acc.im = ::fma(a.im, b.re, acc.im);
+    return acc;
+  }
+  __host__ __device__ static __forceinline__ c64 add(c64 a, c64 b) { return make_c64(a.re + b.re, a.im + b.im); }
+  __host__ __device__ static __forceinline__ c64 mul(c64 a, c64 b) {
+    return make_c64(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+  }
+  __host__ __device__ static __forceinline__ bool is_zero(c64 a) { return a.re == 0.0 && a.im == 0.0; }
+  __host__ __device__ static __forceinline__ c64 div(c64 a, c64 b) {
+    // Smith's algorithm (what Julia's complex division is built on): robust against overflow
+    if (fabs(b.re) >= fabs(b.im)) {
+      double r = b.im / b.re, den = b.re + b.im * r;
+      return make_c64((a.re + a.im * r) / den, (a.im - a.re * r) / den);
+    } else {
+      double r = b.re / b.im, den = b.re * r + b.im;
+      return make_c64((a.re * r + a.im) / den, (a.im * r - a.re) / den);
+    }
+  }
+  __host__ __device__ static __forceinline__ double abs2(c64 a) { return a.re * a.re + a.im * a.im; }
+  __device__ static __forceinline__ c64 shfl_xor(c64 a, int m) {
+    return make_c64(__shfl_xor_sync(0xffffffffu, a.re, m), __shfl_xor_sync(0xffffffffu, a.im, m));
+  }
+};
+
+// ---- per-vertex descriptor (device copy of the graph walk the reference does per update) ---------
+struct VDesc {
+  int64_t site_off;                 // element offset of A_v in the packed site buffer
+  int64_t n;                        // elements of A_v
+  int32_t z;                        // degree
+  int32_t d;                        // physical dimension (1 in SINGLE mode)
+  int32_t dim[BPX_MAX_DEGREE];      // link dims, slot order
+  int32_t out_edge[BPX_MAX_DEGREE]; // directed edge v -> w_i
+  int32_t in_edge[BPX_MAX_DEGREE];  // directed edge w_i -> v  (the message that arrives on leg i)
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v = Elem<T>::add(v, Elem<T>::shfl_xor(v, m));
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+// Epilogue shared by every update kernel: sum-normalise (beliefpropagation.jl:248-253), residual term
+// 1 - |<old^, new^>|^2 (beliefpropagation.jl:261-267), store.  Executed by ONE warp; `raw` holds the
+// unnormalised message (nelem entries, any address space), `old_m` / `new_m` the global slots.
+template <typename T>
+__device__ __forceinline__ void warp_epilogue(const T* raw, const T* old_m, T* new_m, int nelem, int normalize,
+                                              double* residual_slot, int lane) {
+  using E = Elem<T>;
+  T s = E::zero();
+  for (int i = lane; i < nelem; i += 32) s = E::add(s, raw[i]);
+  s = warp_sum<T>(s);
+  const bool scale = normalize && !E::is_zero(s);
+  T dot = E::zero();
+  double n_old = 0.0, n_new = 0.0;
+  for (int i = lane; i < nelem; i += 32) {
+    T v = raw[i];
+    if (scale) v = E::div(v, s);
+    T o = old_m[i];
+    dot = E::fma(E::conj(o), v, dot);
+    n_old += E::abs2(o);
+    n_new += E::abs2(v);
+    new_m[i] = v;
+  }
+  dot = warp_sum<T>(dot);
+  n_old = warp_sum_d(n_old);
+  n_new = warp_sum_d(n_new);
+  if (lane == 0 && residual_slot) *residual_slot = 1.0 - E::abs2(dot) / (n_old * n_new);
+}
+
+}  // namespace bpx

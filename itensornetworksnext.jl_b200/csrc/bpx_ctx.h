@@ -1,0 +1,110 @@
+// Internal context layout of libbpx (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "bpx_common.cuh"
+
+namespace bpx {
+
+struct Bucket {
+  int z = 0, d = 1, chi = 0;          // chi == 0: link dims not uniform
+  std::vector<int32_t> vertices;      // all vertices of the bucket
+  std::vector<int32_t> my_vertices;   // ... owned by this rank
+  std::vector<int32_t> my_edges;      // out-edges of my_vertices (vertex-major, slot order)
+  int32_t* d_vertices = nullptr;
+  int32_t* d_edges = nullptr;
+  int kernel = BPX_KERNEL_GENERIC;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // profiling: one event pair per timed launch
+  double timed_ms = 0.0;
+  int64_t timed_launches = 0;
+};
+
+struct Peer {
+  int rank = -1;
+  void* msg[2] = {nullptr, nullptr};  // peer's two message sets (cudaIpcOpenMemHandle)
+};
+
+}  // namespace bpx
+
+struct bpx_ctx {
+  int device = 0;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // graph (host)
+  bool graph_set = false, dims_set = false;
+  int64_t nv = 0, ne = 0, n_und = 0;
+  std::vector<int32_t> src, dst, slot, rev, deg;
+  std::vector<std::vector<int32_t>> out_edge;  // per vertex, slot order
+  std::vector<int32_t> link_dim, phys_dim;
+  std::vector<int64_t> site_off, msg_off;
+  int dtype = BPX_F64, mode = BPX_MODE_NORM, esize = 8;
+  int64_t max_site_elems = 1, max_msg_elems = 1;
+
+  // device
+  bpx::VDesc* d_vdesc = nullptr;
+  int32_t *d_src = nullptr, *d_slot = nullptr, *d_rev = nullptr, *d_und_edge = nullptr;
+  int64_t* d_msg_off = nullptr;
+  void* d_sites = nullptr;
+  void* d_msg[2] = {nullptr, nullptr};
+  void* d_msg_snapshot = nullptr;
+  int cur = 0;
+  double *d_residual = nullptr, *d_resmax = nullptr, *d_history = nullptr;
+  int history_cap = 0, history_len = 0;
+  void* d_scratch = nullptr;
+  int gen_smem_elems = 0, gen_smem_bytes = 0, gen_grid = 0;
+  void* d_fast_scratch = nullptr;
+  size_t fast_scratch_bytes = 0;
+
+  std::vector<bpx::Bucket> buckets;
+  int kernel_policy = BPX_KERNEL_AUTO;
+  bool profiling = false;
+
+  // partition
+  int rank = 0, nranks = 1;
+  std::vector<int32_t> owner;
+  int32_t* d_owned_edges = nullptr;
+  int32_t* d_all_edges = nullptr;
+  int64_t n_owned_edges = 0;
+  std::vector<bpx::Peer> peers;
+  void** d_peer_msg = nullptr;  // [2][nranks] device table of peer message-set pointers
+  int32_t* d_cut = nullptr;     // (edge, peer) pairs of owned edges whose head lives on another rank
+  int64_t n_cut = 0;
+  void* nccl_comm = nullptr;
+
+  // counters
+  int64_t n_launches = 0, n_updates = 0, n_sweeps = 0;
+};
+
+namespace bpx {
+
+void set_error(bpx_ctx* ctx, const char* fmt, ...);
+
+#define BPX_CUDA(ctx, call)                                                                       \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      bpx::set_error(ctx, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      cudaGetLastError();                                                                         \
+      return BPX_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+int rebuild_work_lists(bpx_ctx* ctx);
+int launch_generic_update(bpx_ctx* ctx, const void* msg_in, void* msg_out, const int32_t* d_work, int64_t n_work,
+                          int normalize);
+// specialised kernels (bpx_fast.cuh)
+int fast_kernel_for(bpx_ctx* ctx, const Bucket& b);
+bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel);
+int fast_prepare(bpx_ctx* ctx);
+int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize);
+// multi-GPU (bpx_halo.cuh)
+int halo_push(bpx_ctx* ctx, void* msg_out);
+
+}  // namespace bpx

@@ -1,0 +1,217 @@
+"""`BPXContext`: one libbpx context (one GPU) driven with numpy host buffers.
+
+Thin, mechanical wrapper over the C ABI (include/bpx.h); all arithmetic happens in the CUDA kernels.
+The canonical layout is column-major: site tensors and messages are handed over as Fortran-order flats.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import BPXError
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class BPXContext:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.bpx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise BPXError(rc, self.lib.bpx_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self.dtype = None
+        self.mode = None
+        self.nv = self.ne = 0
+
+    # -- plumbing ----------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise BPXError(rc, self.lib.bpx_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bpx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- problem description -----------------------------------------------------------------------
+    def set_graph(self, src: Sequence[int], dst: Sequence[int], slot: Sequence[int], nv: int):
+        src = np.ascontiguousarray(src, dtype=np.int64)
+        dst = np.ascontiguousarray(dst, dtype=np.int64)
+        slot = np.ascontiguousarray(slot, dtype=np.int32)
+        self._check(self.lib.bpx_set_graph(self.h, int(nv), len(src), _ptr(src), _ptr(dst), _ptr(slot)))
+        self.nv, self.ne = int(nv), len(src)
+
+    def set_dims(self, dtype, mode: str, phys_dim: Optional[Sequence[int]], link_dim: Sequence[int]):
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float64), np.dtype(np.complex128)):
+            raise TypeError("libbpx computes in Float64 / ComplexF64 only")
+        self.mode = mode
+        code = _lib.BPX_F64 if self.dtype == np.float64 else _lib.BPX_C64
+        m = {"norm": _lib.BPX_MODE_NORM, "single": _lib.BPX_MODE_SINGLE}[mode]
+        pd = None if phys_dim is None else np.ascontiguousarray(phys_dim, dtype=np.int32)
+        ld = np.ascontiguousarray(link_dim, dtype=np.int32)
+        self._check(self.lib.bpx_set_dims(self.h, code, m, _ptr(pd), _ptr(ld)))
+        self.site_off = np.array([self.lib.bpx_site_offset(self.h, v) for v in range(self.nv + 1)], dtype=np.int64)
+        self.msg_off = np.array([self.lib.bpx_message_offset(self.h, e) for e in range(self.ne + 1)], dtype=np.int64)
+        self.link_dim = ld
+
+    # -- data --------------------------------------------------------------------------------------
+    def pack_sites(self, tensors: Sequence[np.ndarray]) -> np.ndarray:
+        out = np.empty(int(self.site_off[-1]), dtype=self.dtype)
+        for v, t in enumerate(tensors):
+            n = int(self.site_off[v + 1] - self.site_off[v])
+            if t.size != n:
+                raise ValueError(f"site tensor {v} has {t.size} elements, expected {n}")
+            out[self.site_off[v]:self.site_off[v + 1]] = np.asarray(t, dtype=self.dtype).ravel(order="F")
+        return out
+
+    def pack_messages(self, msgs: Sequence[np.ndarray]) -> np.ndarray:
+        out = np.empty(int(self.msg_off[-1]), dtype=self.dtype)
+        for e, m in enumerate(msgs):
+            n = int(self.msg_off[e + 1] - self.msg_off[e])
+            if m.size != n:
+                raise ValueError(f"message {e} has {m.size} elements, expected {n}")
+            out[self.msg_off[e]:self.msg_off[e + 1]] = np.asarray(m, dtype=self.dtype).ravel(order="F")
+        return out
+
+    def unpack_messages(self, flat: np.ndarray) -> List[np.ndarray]:
+        out = []
+        for e in range(self.ne):
+            chi = int(self.link_dim[e])
+            shape = (chi, chi) if self.mode == "norm" else (chi,)
+            out.append(flat[self.msg_off[e]:self.msg_off[e + 1]].reshape(shape, order="F").copy())
+        return out
+
+    def set_site_tensors(self, tensors):
+        flat = tensors if isinstance(tensors, np.ndarray) and tensors.ndim == 1 else self.pack_sites(tensors)
+        flat = np.ascontiguousarray(flat, dtype=self.dtype)
+        self._check(self.lib.bpx_set_site_tensors(self.h, _ptr(flat)))
+
+    def set_messages(self, msgs):
+        flat = msgs if isinstance(msgs, np.ndarray) and msgs.ndim == 1 else self.pack_messages(msgs)
+        flat = np.ascontiguousarray(flat, dtype=self.dtype)
+        self._check(self.lib.bpx_set_messages(self.h, _ptr(flat)))
+
+    def get_messages_flat(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(int(self.msg_off[-1]), dtype=self.dtype)
+        self._check(self.lib.bpx_get_messages(self.h, _ptr(out)))
+        return out
+
+    def get_messages(self) -> List[np.ndarray]:
+        return self.unpack_messages(self.get_messages_flat())
+
+    # -- hot path ----------------------------------------------------------------------------------
+    def sweep(self, max_sweeps: int = 1, tol: float = 0.0, normalize: bool = True):
+        res, done = C.c_double(), C.c_int()
+        self._check(self.lib.bpx_sweep(self.h, int(max_sweeps), float(tol), int(bool(normalize)), C.byref(res), C.byref(done)))
+        return res.value, done.value
+
+    def sweep_async(self, n_sweeps: int = 1, normalize: bool = True):
+        self._check(self.lib.bpx_sweep_async(self.h, int(n_sweeps), int(bool(normalize))))
+
+    def set_profiling(self, enable: bool):
+        self._check(self.lib.bpx_set_profiling(self.h, int(bool(enable))))
+
+    def bucket_time(self, bucket: int):
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self.lib.bpx_bucket_time(self.h, int(bucket), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def last_residual(self) -> float:
+        """Residual of the last enqueued sweep (synchronises)."""
+        res = C.c_double()
+        self._check(self.lib.bpx_last_residual(self.h, C.byref(res)))
+        return res.value
+
+    def sweep_sequence(self, edge_seq: Sequence[int], max_sweeps: int = 1, tol: float = 0.0, normalize: bool = True):
+        seq = np.ascontiguousarray(edge_seq, dtype=np.int64)
+        res, done = C.c_double(), C.c_int()
+        self._check(self.lib.bpx_sweep_sequence(self.h, _ptr(seq), len(seq), int(max_sweeps), float(tol),
+                                                int(bool(normalize)), C.byref(res), C.byref(done)))
+        return res.value, done.value
+
+    def residual_history(self, n: int = 4096) -> np.ndarray:
+        out = np.empty(n, dtype=np.float64)
+        k = C.c_int()
+        self._check(self.lib.bpx_residual_history(self.h, _ptr(out), n, C.byref(k)))
+        return out[:k.value].copy()
+
+    def iterate_diff(self, other) -> float:
+        flat = other if isinstance(other, np.ndarray) and other.ndim == 1 else self.pack_messages(other)
+        flat = np.ascontiguousarray(flat, dtype=self.dtype)
+        res = C.c_double()
+        self._check(self.lib.bpx_iterate_diff(self.h, _ptr(flat), C.byref(res)))
+        return res.value
+
+    # -- beliefs -----------------------------------------------------------------------------------
+    def vertex_scalars(self) -> np.ndarray:
+        out = np.empty(self.nv, dtype=self.dtype)
+        self._check(self.lib.bpx_vertex_scalars(self.h, _ptr(out)))
+        return out
+
+    def edge_scalars(self) -> np.ndarray:
+        out = np.empty(self.ne // 2, dtype=self.dtype)
+        self._check(self.lib.bpx_edge_scalars(self.h, _ptr(out)))
+        return out
+
+    def vertex_expect_numerators(self, ops: Sequence[np.ndarray]) -> np.ndarray:
+        flat = np.concatenate([np.asarray(o, dtype=self.dtype).ravel(order="F") for o in ops]) if len(ops) else np.empty(0, self.dtype)
+        out = np.empty(self.nv, dtype=self.dtype)
+        self._check(self.lib.bpx_vertex_expect_numerators(self.h, _ptr(np.ascontiguousarray(flat)), _ptr(out)))
+        return out
+
+    # -- introspection -----------------------------------------------------------------------------
+    def buckets(self):
+        out = []
+        for b in range(self.lib.bpx_num_buckets(self.h)):
+            info = (C.c_int64 * 6)()
+            self._check(self.lib.bpx_bucket_info(self.h, b, info))
+            out.append(dict(degree=info[0], chi=info[1], phys=info[2], vertices=info[3], edges=info[4], kernel=info[5]))
+        return out
+
+    def set_kernel_policy(self, kernel: int):
+        self._check(self.lib.bpx_set_kernel_policy(self.h, int(kernel)))
+
+    def counters(self, reset: bool = False):
+        out = (C.c_int64 * 3)()
+        self._check(self.lib.bpx_counters(self.h, out, int(reset)))
+        return dict(launches=out[0], updates=out[1], sweeps=out[2])
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.bpx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.bpx_synchronize(self.h))
+
+
+def fill_randn(seed: int, stream: int, dtype, n: int) -> np.ndarray:
+    """Shared deterministic RNG of the library (host function; needs no GPU)."""
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    out = np.empty(n, dtype=dtype)
+    code = _lib.BPX_F64 if dtype == np.float64 else _lib.BPX_C64
+    rc = lib.bpx_fill_randn(seed, stream, code, n, _ptr(out))
+    if rc != 0:
+        raise BPXError(rc, "bpx_fill_randn: invalid arguments")
+    return out

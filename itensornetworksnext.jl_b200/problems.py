@@ -1,0 +1,102 @@
+"""Synthetic inputs for BASELINE.json's configurations, in the canonical layout of include/bpx.h.
+
+Recipe: site tensors i.i.d. standard normal from the library's counter-based RNG
+(`bpx_fill_randn`, seed 123 -- the seed of test/test_beliefpropagation.jl:155 -- stream = vertex id),
+rescaled by (d * prod chi)^(-1/2); initial messages M = I + 0.1 |randn| sum-normalised (stream =
+nv + edge id), or all ones (test/test_apply_operator.jl:72).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from .device import fill_randn
+from .graphs import GraphArrays, NamedGraph, graph_arrays, heavy_hex_127, named_grid
+
+
+@dataclass
+class SyntheticProblem:
+    name: str
+    ga: GraphArrays
+    dtype: np.dtype
+    chi: int
+    d: int
+    phys_dim: List[int]
+    link_dim: List[int]
+    tensors: List[np.ndarray]   # (d, chi, ..., chi), Fortran order
+    messages: List[np.ndarray]  # (chi, chi) [bra, ket]
+
+    @property
+    def n_updates(self) -> int:
+        return self.ga.ne
+
+    def flops_per_sweep(self) -> float:
+        """Algorithmic flops: 2 z d chi^(z+1) per update, x4 for complex."""
+        c = 4.0 if self.dtype.kind == "c" else 1.0
+        tot = 0.0
+        for v in range(self.ga.nv):
+            z = self.ga.row_ptr[v + 1] - self.ga.row_ptr[v]
+            tot += z * (2.0 * z * self.d * float(self.chi) ** (z + 1)) * c
+        return tot
+
+    def bytes_per_sweep(self) -> float:
+        """Algorithmic bytes: every site tensor once + 3 x every message (in, old, out)."""
+        w = self.dtype.itemsize
+        site = sum(t.size for t in self.tensors) * w
+        return site + 3.0 * self.ga.ne * self.chi * self.chi * w
+
+
+def synthetic_peps(g: NamedGraph, chi: int, d: int = 2, dtype=np.float64, seed: int = 123, init: str = "positive",
+                   name: str = "") -> SyntheticProblem:
+    dtype = np.dtype(dtype)
+    ga = graph_arrays(g)
+    tensors = []
+    for v in range(ga.nv):
+        z = ga.row_ptr[v + 1] - ga.row_ptr[v]
+        shape = (d,) + (chi,) * z
+        n = int(np.prod(shape))
+        t = fill_randn(seed, v, dtype, n) * (1.0 / np.sqrt(n))
+        tensors.append(t.reshape(shape, order="F"))
+    msgs = []
+    for e in range(ga.ne):
+        if init == "ones":
+            m = np.ones((chi, chi), dtype=dtype)
+        elif init == "positive":
+            r = fill_randn(seed, ga.nv + e, np.float64, chi * chi).reshape((chi, chi), order="F")
+            m = (np.eye(chi) + 0.1 * np.abs(r)).astype(dtype)
+            m = m / m.sum()
+        elif init == "randn":
+            m = fill_randn(seed, ga.nv + e, dtype, chi * chi).reshape((chi, chi), order="F")
+        else:
+            raise ValueError(init)
+        msgs.append(np.asfortranarray(m))
+    return SyntheticProblem(name, ga, dtype, chi, d, [d] * ga.nv, [chi] * ga.ne, tensors, msgs)
+
+
+CONFIGS = {
+    # BASELINE.json `configs`, in order
+    "cfg1": dict(graph=lambda: named_grid((4, 4)), chi=2, d=2, dtype=np.float64),
+    "cfg2": dict(graph=lambda: named_grid((32, 32)), chi=8, d=2, dtype=np.float64),
+    "cfg3": dict(graph=heavy_hex_127, chi=16, d=2, dtype=np.complex128),
+    "cfg4": dict(graph=lambda: named_grid((16, 16, 16), periodic=True), chi=4, d=2, dtype=np.float64),
+    "cfg5": dict(graph=lambda: named_grid((256, 256)), chi=16, d=2, dtype=np.float64),
+}
+
+
+def make_config(name: str, seed: int = 123, init: str = "positive", graph: Optional[NamedGraph] = None) -> SyntheticProblem:
+    c = CONFIGS[name]
+    g = c["graph"]() if graph is None else graph
+    return synthetic_peps(g, c["chi"], c["d"], c["dtype"], seed, init, name)
+
+
+def upload(ctx, p: SyntheticProblem, kernel: Optional[int] = None):
+    """Describe `p` to a BPXContext and make site tensors and messages resident."""
+    ctx.set_graph(p.ga.src, p.ga.dst, p.ga.slot, p.ga.nv)
+    if kernel is not None:
+        ctx.set_kernel_policy(kernel)
+    ctx.set_dims(p.dtype, "norm", p.phys_dim, p.link_dim)
+    ctx.set_site_tensors(p.tensors)
+    ctx.set_messages(p.messages)
+    return ctx

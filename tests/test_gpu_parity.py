@@ -1,0 +1,266 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): per-sweep messages within 1e-10 relative; converged local expectation
+values within 1e-9.  Every test here needs a B200 and is marked `gpu`."""
+import numpy as np
+import pytest
+
+import itnn_b200 as B
+from helpers import peps_tensors, positive_messages, randn, rel_err, single_layer_tensors, spin_ice_tensors
+from itnn_b200 import _lib, graphs, problems
+
+pytestmark = pytest.mark.gpu
+
+MSG_RTOL = 1e-10
+EXPECT_ATOL = 1e-9
+KERNELS = [_lib.BPX_KERNEL_AUTO, _lib.BPX_KERNEL_GENERIC]
+
+
+def make_ctx(ga, dtype, mode, phys_dim, link_dim, tensors, msgs, kernel=_lib.BPX_KERNEL_AUTO):
+    ctx = B.BPXContext(0)
+    ctx.set_graph(ga.src, ga.dst, ga.slot, ga.nv)
+    ctx.set_kernel_policy(kernel)
+    ctx.set_dims(dtype, mode, phys_dim, link_dim)
+    ctx.set_site_tensors(tensors)
+    ctx.set_messages(msgs)
+    return ctx
+
+
+def check_sweeps(oracle, ga, dtype, mode, phys_dim, link_dim, tensors, msgs, nsweeps=3, kernel=_lib.BPX_KERNEL_AUTO,
+                 normalize=True):
+    p = oracle.make_problem(ga, tensors, mode)
+    with make_ctx(ga, dtype, mode, phys_dim, link_dim, tensors, msgs, kernel) as ctx:
+        want = list(msgs)
+        for k in range(nsweeps):
+            prev, want = want, oracle.sweep_jacobi(p, want, normalize)
+            res, done = ctx.sweep(1, 0.0, normalize)
+            got = ctx.get_messages()
+            assert done == 1
+            assert rel_err(got, want) < MSG_RTOL, f"sweep {k}"
+            assert abs(res - oracle.iterate_diff(want, prev)) < 1e-11
+        return ctx.buckets()
+
+
+# ---- BASELINE configs ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("init", ["positive", "ones"])
+def test_cfg1_4x4_chi2(oracle, kernel, init):
+    p = problems.make_config("cfg1", init=init)
+    check_sweeps(oracle, p.ga, p.dtype, "norm", p.phys_dim, p.link_dim, p.tensors, p.messages, 4, kernel)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cfg2_32x32_chi8(oracle, kernel):
+    p = problems.make_config("cfg2")
+    check_sweeps(oracle, p.ga, p.dtype, "norm", p.phys_dim, p.link_dim, p.tensors, p.messages, 2, kernel)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cfg3_heavy_hex_chi16_complex(oracle, kernel):
+    p = problems.make_config("cfg3")
+    buckets = check_sweeps(oracle, p.ga, p.dtype, "norm", p.phys_dim, p.link_dim, p.tensors, p.messages, 2, kernel)
+    assert sorted(b["degree"] for b in buckets) == [1, 2, 3]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cfg4_cubic_chi4_reduced(oracle, kernel):
+    # same bucket as cfg4 (degree 6, chi 4, d 2) on a 4x4x4 periodic lattice so the oracle stays fast
+    g = graphs.named_grid((4, 4, 4), periodic=True)
+    p = problems.make_config("cfg4", graph=g)
+    check_sweeps(oracle, p.ga, p.dtype, "norm", p.phys_dim, p.link_dim, p.tensors, p.messages, 2, kernel)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cfg5_bucket_chi16_reduced(oracle, kernel):
+    # same buckets as cfg5 (degrees 2/3/4, chi 16, d 2) on a 5x5 lattice
+    g = graphs.named_grid((5, 5))
+    p = problems.make_config("cfg5", graph=g)
+    check_sweeps(oracle, p.ga, p.dtype, "norm", p.phys_dim, p.link_dim, p.tensors, p.messages, 2, kernel)
+
+
+# ---- edge cases ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_ragged_link_dims_and_degree_one(oracle, dtype):
+    g = graphs.named_comb_tree((3, 3))
+    g.add_edge((1, 3), (2, 3))  # one loop
+    ga = graphs.graph_arrays(g)
+    rng = np.random.default_rng(3)
+    link_dim = [0] * ga.ne
+    for e in range(ga.ne):
+        link_dim[e] = link_dim[ga.rev[e]] = 1 + (min(e, ga.rev[e]) % 4)  # dims 1..4, including 1
+    phys = [1 + (v % 3) for v in range(ga.nv)]
+    tensors = []
+    for v in range(ga.nv):
+        dims = [link_dim[f] for f in range(ga.row_ptr[v], ga.row_ptr[v + 1])]
+        tensors.append(randn(rng, dtype, (phys[v], *dims)))
+    msgs = positive_messages(ga, link_dim, dtype, rng)
+    check_sweeps(oracle, ga, dtype, "norm", phys, link_dim, tensors, msgs, 3)
+
+
+def test_isolated_vertex_and_empty_graph(oracle):
+    with B.BPXContext(0) as ctx:
+        ctx.set_graph([], [], [], 0)
+        ctx.set_dims(np.float64, "norm", [], [])
+        res, done = ctx.sweep(2, 0.0)
+        assert done == 2
+    g = graphs.NamedGraph([0, 1, 2])
+    g.add_edge(0, 1)  # vertex 2 isolated
+    ga = graphs.graph_arrays(g)
+    rng = np.random.default_rng(0)
+    tensors = [randn(rng, np.float64, (2, 3)), randn(rng, np.float64, (2, 3)), randn(rng, np.float64, (2,))]
+    msgs = positive_messages(ga, [3] * ga.ne, np.float64, rng)
+    check_sweeps(oracle, ga, np.float64, "norm", [2, 2, 2], [3] * ga.ne, tensors, msgs, 1)
+    p = oracle.make_problem(ga, tensors, "norm")
+    with make_ctx(ga, np.float64, "norm", [2, 2, 2], [3, 3], tensors, msgs) as ctx:
+        assert np.allclose(ctx.vertex_scalars(), oracle.vertex_scalars(p, msgs), rtol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_zero_sum_guard_and_no_normalize(oracle, dtype):
+    # antisymmetric site tensors make some raw messages sum to exactly zero -> left unnormalised
+    g = graphs.named_path_graph(3)
+    ga = graphs.graph_arrays(g)
+    A0 = np.zeros((2, 2), dtype=dtype)
+    A0[0, 0], A0[1, 1] = 1.0, 1.0
+    A1 = np.zeros((2, 2, 2), dtype=dtype)
+    A1[0, 0, 1], A1[0, 1, 0] = 1.0, -1.0
+    A1[1, 0, 1], A1[1, 1, 0] = 1.0, 1.0
+    tensors = [A0, A1, A0.copy()]
+    msgs = [np.array([[1.0, -1.0], [1.0, -1.0]], dtype=dtype) for _ in range(ga.ne)]  # sum == 0 exactly
+    p = oracle.make_problem(ga, tensors, "norm")
+    want = oracle.sweep_jacobi(p, msgs)
+    with make_ctx(ga, dtype, "norm", [2] * 3, [2] * ga.ne, tensors, msgs) as ctx:
+        ctx.sweep(1)
+        got = ctx.get_messages()
+    for a, b in zip(got, want):
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-15)
+    assert any(abs(w.sum()) < 1e-300 for w in want), "the case must exercise the iszero branch"
+    rng = np.random.default_rng(1)
+    tensors = peps_tensors(ga, 2, 2, dtype, rng)
+    msgs = positive_messages(ga, [2] * ga.ne, dtype, rng)
+    check_sweeps(oracle, ga, dtype, "norm", [2] * 3, [2] * ga.ne, tensors, msgs, 2, normalize=False)
+
+
+# ---- reference known answers end to end on the GPU (sequential schedule + single-layer mode) ----------
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_tree_exact_one_sequential_sweep_gpu(oracle, dtype):
+    # test/test_beliefpropagation.jl:157-202 through the reference-shaped API
+    for g, chi in ((graphs.named_grid((2, 1)), 2), (graphs.named_comb_tree((4, 3)), 3)):
+        rng = np.random.default_rng(123)
+        links = {frozenset((e.src, e.dst)): B.Index(chi) for e in g.edges()}
+        tn = B.tensornetwork(lambda v: B.randn_itensor(rng, dtype, [links[frozenset((e.src, e.dst))] for e in g.incident_edges(v)]),
+                             g.vertices())
+        messages = {e: B.ITensor(np.ones(chi, dtype=dtype), (tn.linkind(e),)) for e in g.all_edges()}
+        cache = B.beliefpropagation(tn, messages, stopping_criterion=dict(maxiter=1))
+        z_bp = np.exp(B.bethe_free_energy(tn, cache))
+        cp = B.canonical_arrays(tn)
+        z_exact = oracle.contract_all(oracle.make_problem(cp.ga, cp.tensors, "single"))
+        assert np.isclose(z_bp, z_exact, rtol=np.finfo(np.float64).eps ** (1 / 3))
+
+
+@pytest.mark.parametrize("n", [3, 4, 5])
+def test_spin_ice_gpu(oracle, n):
+    # test/test_beliefpropagation.jl:204-225
+    g = graphs.named_grid((n, n), periodic=True)
+    rng = np.random.default_rng(123)
+    links = {frozenset((e.src, e.dst)): B.Index(2) for e in g.edges()}
+    ga0 = graphs.graph_arrays(g)
+    t = spin_ice_tensors(ga0)[0]
+    tn = B.tensornetwork(lambda v: B.ITensor(t, [links[frozenset((e.src, e.dst))] for e in g.incident_edges(v)]), g.vertices())
+    messages = {e: B.ITensor(rng.random(2), (tn.linkind(e),)) for e in g.all_edges()}
+    info = B.BeliefPropagationResult()
+    cache = B.beliefpropagation(tn, messages, stopping_criterion=dict(maxiter=10, tol=1e-10), info=info)
+    assert np.isclose(np.exp(B.bethe_free_energy(tn, cache)), 1.5 ** (n * n))
+    assert 1 <= info.iterations <= 10
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_sequential_schedule_matches_oracle(oracle, dtype):
+    g = graphs.named_grid((3, 4))
+    ga = graphs.graph_arrays(g)
+    rng = np.random.default_rng(9)
+    tensors = peps_tensors(ga, 3, 2, dtype, rng)
+    msgs = positive_messages(ga, [3] * ga.ne, dtype, rng)
+    seq = [ga.edge_id(e) for e in graphs.forest_cover_edge_sequence(g)]
+    p = oracle.make_problem(ga, tensors, "norm")
+    with make_ctx(ga, dtype, "norm", [2] * ga.nv, [3] * ga.ne, tensors, msgs) as ctx:
+        want = list(msgs)
+        for _ in range(3):
+            prev, want = want, oracle.sweep_sequential(p, want, seq)
+            res, done = ctx.sweep_sequence(seq, 1)
+            assert rel_err(ctx.get_messages(), want) < MSG_RTOL
+            assert abs(res - oracle.iterate_diff(want, prev)) < 1e-11
+        # a sequence that repeats an edge and skips others is still honoured literally
+        odd = [seq[0], seq[5], seq[0], seq[7]]
+        want = oracle.sweep_sequential(p, want, odd)
+        ctx.sweep_sequence(odd, 1)
+        assert rel_err(ctx.get_messages(), want) < MSG_RTOL
+
+
+# ---- NormNetwork BP through the reference-shaped API: test/test_apply_operator.jl:62-74 ---------------
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("gname", ["cycle4", "path4"])
+def test_normnetwork_bp_api_and_expectation_values(oracle, dtype, gname):
+    g = graphs.named_cycle_graph(4) if gname == "cycle4" else graphs.named_path_graph(4)
+    tn, _, _ = B.random_state(dtype, g, d=3, chi=3, rng=np.random.default_rng(123))
+    nn = B.normnetwork(tn)
+    env0 = B.message_environment(B.ones_message, nn)
+    info = B.BeliefPropagationResult()
+    env = B.beliefpropagation(nn, env0, stopping_criterion=dict(maxiter=100, tol=1e-13), info=info)
+    cp = B.canonical_arrays(nn)
+    p = oracle.make_problem(cp.ga, cp.tensors, "norm")
+    seq = [cp.ga.edge_id(e) for e in B.default_beliefpropagation_edges(nn)]
+    msgs0 = [np.ones((3, 3), dtype=dtype) for _ in range(cp.ga.ne)]
+    want, it, delta = oracle.beliefpropagation(p, msgs0, maxiter=100, tol=1e-13, schedule="sequential", edge_seq=seq)
+    assert info.iterations == it
+    got = [env[cp.ga.named_edge(e)].array(cp.bra_names[e], cp.ket_names[e]) for e in range(cp.ga.ne)]
+    assert rel_err(got, want) < 1e-9
+    # synchronous strategy: same fixed point -> same local expectation values (1e-9)
+    env_sync = B.beliefpropagation(nn, env0, stopping_criterion=dict(maxiter=500, tol=1e-15),
+                                   message_update_algorithm=B.B200MessageUpdate())
+    sz = np.diag([1.0, 0.0, -1.0])
+    e_gpu = np.array(B.expect(nn, env_sync, sz))
+    e_ref = np.array([oracle.local_expect(p, want, v, sz.astype(dtype)) for v in range(cp.ga.nv)])
+    assert np.allclose(e_gpu, e_ref, atol=EXPECT_ATOL)
+    assert np.allclose(B.vertex_scalars(nn, env), oracle.vertex_scalars(p, want), rtol=1e-9)
+    assert np.allclose(B.edge_scalars(env), oracle.edge_scalars(p, want), rtol=1e-9)
+    if gname == "path4":  # tree: BP is exact
+        z = np.exp(B.bethe_free_energy(nn, env))
+        assert np.isclose(z, oracle.contract_all(p).real, rtol=1e-9)
+
+
+def test_converged_expectation_values_cfg1(oracle):
+    p = problems.make_config("cfg1")
+    op = oracle.make_problem(p.ga, p.tensors, "norm")
+    want, it, delta = oracle.beliefpropagation(op, p.messages, maxiter=300, tol=1e-14)
+    with B.BPXContext(0) as ctx:
+        problems.upload(ctx, p)
+        res, done = ctx.sweep(300, 1e-14)
+        assert done == it and res < 1e-14
+        hist = ctx.residual_history()
+        assert len(hist) == done and hist[-1] == res
+        sz = np.diag([1.0, -1.0])
+        num = ctx.vertex_expect_numerators([sz] * p.ga.nv)
+        den = ctx.vertex_scalars()
+        e_ref = [oracle.local_expect(op, want, v, sz) for v in range(p.ga.nv)]
+        assert np.allclose(num / den, e_ref, atol=EXPECT_ATOL)
+        assert abs(ctx.iterate_diff(want)) < 1e-12
+        assert abs(ctx.iterate_diff(p.messages) - oracle.iterate_diff(want, p.messages)) < 1e-11
+
+
+def test_message_update_single_edge_and_iterate_diff(oracle):
+    g = graphs.named_grid((3, 3))
+    tn, _, _ = B.random_state(np.float64, g, d=2, chi=2, rng=np.random.default_rng(4))
+    nn = B.normnetwork(tn)
+    cache = B.message_environment(B.identity_message, nn)
+    before = cache.copy()
+    e = graphs.NamedEdge((2, 2), (2, 3))
+    B.message_update(cache, nn, e)
+    cp = B.canonical_arrays(nn)
+    p = oracle.make_problem(cp.ga, cp.tensors, "norm")
+    want = oracle.message_update(p, [np.eye(2) for _ in range(cp.ga.ne)], cp.ga.edge_id(e))
+    assert np.allclose(cache[e].array(cp.bra_names[cp.ga.edge_id(e)], cp.ket_names[cp.ga.edge_id(e)]), want, rtol=1e-12)
+    d = B.iterate_diff(cache, before)
+    msgs_after = [np.eye(2) for _ in range(cp.ga.ne)]
+    msgs_after[cp.ga.edge_id(e)] = want
+    assert abs(d - oracle.iterate_diff(msgs_after, [np.eye(2)] * cp.ga.ne)) < 1e-12

@@ -1,0 +1,132 @@
+"""Host-side mirror of the reference interface: containers, criteria, algorithm selection (CPU only)."""
+import numpy as np
+import pytest
+
+import itnn_b200 as B
+from itnn_b200 import graphs
+
+
+def test_named_grid_matches_baseline_counts():
+    g = graphs.named_grid((4, 4))
+    assert (g.nv(), 2 * g.ne()) == (16, 48)
+    degs = sorted(g.degree(v) for v in g.vertices())
+    assert (degs.count(2), degs.count(3), degs.count(4)) == (4, 8, 4)
+    g = graphs.named_grid((32, 32))
+    assert (g.nv(), 2 * g.ne()) == (1024, 3968)
+    g = graphs.named_grid((16, 16, 16), periodic=True)
+    assert (g.nv(), 2 * g.ne()) == (4096, 24576) and all(g.degree(v) == 6 for v in g.vertices())
+    g = graphs.heavy_hex_127()
+    assert (g.nv(), 2 * g.ne()) == (127, 288)
+    assert max(g.degree(v) for v in g.vertices()) == 3 and min(g.degree(v) for v in g.vertices()) == 1
+    assert len(graphs.connected_components(g)) == 1
+
+
+def test_graph_arrays_are_consistent():
+    g = graphs.named_grid((3, 4), periodic=True)
+    ga = graphs.graph_arrays(g)
+    for e in range(ga.ne):
+        r = ga.rev[e]
+        assert (ga.src[r], ga.dst[r]) == (ga.dst[e], ga.src[e])
+        assert ga.row_ptr[ga.src[e]] + ga.slot[e] == e
+
+
+# -- MessageCache container semantics: test/test_beliefpropagation.jl:39-82 ---------------------------
+def test_messagecache_basics():
+    g = graphs.named_grid((3, 3))
+    bpc = B.messagecache(lambda e: f"{e.src} => {e.dst}", g.all_edges())
+    assert len(bpc) == 2 * g.ne()
+    assert bpc[((1, 1), (1, 2))] == "(1, 1) => (1, 2)"
+    bpc[((1, 1), (1, 2))] = "new message"
+    assert bpc[((1, 1), (1, 2))] == "new message"
+    pairs = {((1, 2), (2, 2)): "m1", ((2, 2), (2, 3)): "m2"}
+    new = bpc.copy().copyto(pairs)
+    assert new[((1, 1), (1, 2))] == "new message" and new[((1, 2), (2, 2))] == "m1" and new[((2, 2), (2, 3))] == "m2"
+    dst = B.messagecache(lambda e: "", g.all_edges())
+    dst.copyto(bpc, [((1, 2), (2, 2)), ((2, 2), (2, 3))])
+    assert dst[((1, 1), (1, 2))] == "" and dst[((1, 2), (2, 2))] == "(1, 2) => (2, 2)"
+
+
+def test_incoming_messages_exclusion_rule():  # test/test_beliefpropagation.jl:104-114
+    g = graphs.named_path_graph(3)
+    bpc = B.messagecache(lambda e: (e.src, e.dst), g.all_edges())
+    assert B.incoming_messages(bpc, (2, 3)) == [(1, 2)]
+    assert B.incoming_messages(bpc, (1, 2)) == []
+    assert B.incoming_messages(bpc, (2, 1)) == [(3, 2)]
+
+
+def test_subgraph():  # test/test_beliefpropagation.jl:117-133
+    g = graphs.named_grid((3,))
+    bpc = B.messagecache(lambda e: 1, g.all_edges())
+    sub = bpc.subgraph([(1,), (2,)])
+    assert set(sub.vertices()) == {(1,), (2,)} and sub.has_edge(((1,), (2,)))
+
+
+# -- stopping criterion shorthand: beliefpropagation.jl:16-55 -----------------------------------------
+def test_stopping_criterion_selection():
+    sel = B.select_beliefpropagation_stopping_criterion
+    assert sel(dict(maxiter=3)) == B.StopAfterIteration(3)
+    assert sel(dict(tol=1e-8)) == B.StopWhenConverged(1e-8)
+    c = sel(dict(maxiter=3, tol=1e-8))
+    assert c.criteria == [B.StopAfterIteration(3), B.StopWhenConverged(1e-8)]
+    explicit = B.StopAfterIteration(10) | B.StopWhenConverged(1e-10)
+    assert sel(explicit) is explicit
+    with pytest.raises(B.ArgumentError, match="must be specified"):
+        sel(None)
+    with pytest.raises(B.ArgumentError, match="Unrecognized"):
+        sel(dict(maxiter=1, foo=2))
+    with pytest.raises(B.ArgumentError, match="At least one"):
+        sel(dict())
+
+
+# -- select_algorithm: src/select_algorithm.jl:16-51 --------------------------------------------------
+def test_select_algorithm():
+    f = B.message_update
+    assert isinstance(B.select_algorithm(f, None), B.SimpleMessageUpdate)
+    assert B.select_algorithm(f, dict(normalize=False)).normalize is False
+    inst = B.B200MessageUpdate(normalize=False)
+    assert B.select_algorithm(f, inst) is inst
+    with pytest.raises(B.ArgumentError):
+        B.select_algorithm(f, inst, normalize=True)
+    with pytest.raises(B.ArgumentError):
+        B.select_algorithm(f, dict(normalize=True), normalize=True)
+    with pytest.raises(TypeError):
+        B.default_algorithm(print)
+
+
+# -- NormNetwork name map and views: test/test_normnetwork.jl:60-135 ----------------------------------
+def test_normnetwork_names_and_canonical_layout():
+    g = graphs.named_path_graph(3)
+    tn, l, s = B.random_state(np.float64, g, d=2, chi=3)
+    nn = B.normnetwork(tn)
+    assert set(nn.vertices()) == set(tn.vertices())
+    e = graphs.NamedEdge(1, 2)
+    kn = tn.linkname(e)
+    assert nn.braname(kn) != kn and nn.braname(s[1].name) == s[1].name
+    with pytest.raises(KeyError):
+        nn.braname("nope")
+    assert B.KetView(nn)[2] is tn[2]
+    assert np.array_equal(B.BraView(nn)[2].data, np.conj(tn[2].data))
+    assert B.BraView(nn).linkname(e) == nn.braname(kn)
+    custom = B.normnetwork(tn, {n: ("bra", n) for n in tn.dimname_vertices})
+    assert custom.braname(kn) == ("bra", kn)
+    cp = B.canonical_arrays(nn)
+    assert cp.mode == "norm" and cp.phys_dim == [2, 2, 2]
+    assert [t.shape for t in cp.tensors] == [(2, 3), (2, 3, 3), (2, 3)]
+    env = B.message_environment(B.ones_message, nn)
+    m = env[e]
+    assert m.dimnames() == (nn.braname(kn), kn) and np.all(m.data == 1)
+
+
+def test_canonical_arrays_permutes_by_name():
+    # a tensor stored as (link, site, link) must come out as [site, links in neighbour order]
+    a, b, s1, s2, s3 = (B.Index(2, "a"), B.Index(3, "b"), B.Index(2, "s1"), B.Index(2, "s2"), B.Index(2, "s3"))
+    rng = np.random.default_rng(0)
+    t1 = B.randn_itensor(rng, np.float64, (a, s1))
+    t2 = B.randn_itensor(rng, np.float64, (b, s2, a))
+    t3 = B.randn_itensor(rng, np.float64, (s3, b))
+    tn = B.ITensorNetwork({1: t1, 2: t2, 3: t3})
+    cp = B.canonical_arrays(B.normnetwork(tn))
+    assert cp.tensors[0].shape == (2, 2) and np.array_equal(cp.tensors[0], t1.data.T)
+    # vertex 2: neighbours in leg order (b -> 3, a -> 1)
+    assert [cp.ga.vertices[cp.ga.dst[e]] for e in range(cp.ga.row_ptr[1], cp.ga.row_ptr[2])] == [3, 1]
+    assert np.array_equal(cp.tensors[1], np.transpose(t2.data, (1, 0, 2)))
