@@ -223,7 +223,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     p, owner, desc = build_workload(args.workload, world)
     ctx = pkg.BPXContext(local_rank)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: torch events and the library's launches share it (handle 0, the
+    # legacy default stream, would mean "library-internal stream" to bpx_set_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_graph(p.ga.src, p.ga.dst, p.ga.slot, p.ga.nv)
     if args.kernel:
