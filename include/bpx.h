@@ -134,8 +134,9 @@ int bpx_vertex_expect_numerators(bpx_ctx* ctx, const void* ops_packed, void* out
 /* ---- introspection --------------------------------------------------------------------------------- */
 int bpx_num_buckets(const bpx_ctx* ctx);
 /* info[0]=degree, [1]=chi (0 if non-uniform), [2]=phys dim, [3]=#vertices, [4]=#directed edges,
- * [5]=kernel family in use */
-int bpx_bucket_info(const bpx_ctx* ctx, int bucket, int64_t info[6]);
+ * [5]=kernel family in use, [6]=bucket whose launch covers this bucket (buckets of one kernel family and
+ * chi/d share a launch; only the leader is timed by bpx_bucket_time), [7]=reserved */
+int bpx_bucket_info(const bpx_ctx* ctx, int bucket, int64_t info[8]);
 /* force a kernel family for all buckets that support it (testing / profiling); BPX_KERNEL_AUTO resets */
 int bpx_set_kernel_policy(bpx_ctx* ctx, int kernel);
 /* per-bucket device timing: when enabled, every bucket launch of a sweep is bracketed by CUDA events on

@@ -82,6 +82,7 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_owned_edges);
   F(c->d_all_edges);
   F(c->d_fast_scratch);
+  F(c->d_onchip_items);
   for (auto& b : c->buckets) {
     F(b.d_vertices);
     F(b.d_edges);
@@ -500,8 +501,9 @@ static int sweep_once(bpx_ctx* ctx, int normalize, int hist_idx) {
   const void* in = ctx->d_msg[ctx->cur];
   void* out = ctx->d_msg[ctx->cur ^ 1];
   int rc;
-  for (auto& b : ctx->buckets) {
-    if (b.my_edges.empty()) continue;
+  for (int bi = 0; bi < (int)ctx->buckets.size(); ++bi) {
+    Bucket& b = ctx->buckets[bi];
+    if (b.my_edges.empty() || b.leader != bi) continue;  // merged into its group leader's launch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->profiling && b.timing.size() < 8192) {
       BPX_CUDA(ctx, cudaEventCreate(&ev0));
@@ -824,7 +826,7 @@ extern "C" int bpx_edge_scalars(bpx_ctx* ctx, void* out) {
 // ---- introspection ------------------------------------------------------------------------------
 extern "C" int bpx_num_buckets(const bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? (int)ctx->buckets.size() : -1; }
 
-extern "C" int bpx_bucket_info(const bpx_ctx* ctx, int bucket, int64_t info[6]) {
+extern "C" int bpx_bucket_info(const bpx_ctx* ctx, int bucket, int64_t info[8]) {
   if (!ctx || !ctx->dims_set || bucket < 0 || bucket >= (int)ctx->buckets.size() || !info) return BPX_ERR_INVALID;
   const Bucket& b = ctx->buckets[bucket];
   info[0] = b.z;
@@ -833,6 +835,8 @@ extern "C" int bpx_bucket_info(const bpx_ctx* ctx, int bucket, int64_t info[6]) 
   info[3] = (int64_t)b.my_vertices.size();
   info[4] = (int64_t)b.my_edges.size();
   info[5] = b.kernel;
+  info[6] = b.leader;
+  info[7] = 0;
   return BPX_OK;
 }
 

@@ -17,6 +17,7 @@ struct Bucket {
   int32_t* d_vertices = nullptr;
   int32_t* d_edges = nullptr;
   int kernel = BPX_KERNEL_GENERIC;
+  int leader = 0;  // bucket index whose launch covers this bucket (launch groups, bpx_fast.cuh)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // profiling: one event pair per timed launch
   double timed_ms = 0.0;
   int64_t timed_launches = 0;
@@ -59,6 +60,8 @@ struct bpx_ctx {
   int history_cap = 0, history_len = 0;
   void* d_scratch = nullptr;
   int gen_smem_elems = 0, gen_smem_bytes = 0, gen_grid = 0;
+  void* d_onchip_items = nullptr;
+  int n_onchip_items = 0;
   void* d_fast_scratch = nullptr;
   size_t fast_scratch_bytes = 0;
 

@@ -1,5 +1,7 @@
 // Specialised (bucket-specific) kernels: dispatch.  Kernels live in bpx_onchip.cuh / bpx_sliced.cuh.
 #pragma once
+#include <algorithm>
+
 #include "bpx_ctx.h"
 #include "bpx_onchip.cuh"
 
@@ -9,7 +11,7 @@ inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
   if (kernel == BPX_KERNEL_GENERIC) return true;
   if (ctx->mode != BPX_MODE_NORM) return false;
   if (kernel == BPX_KERNEL_ONCHIP)
-    return ctx->dtype == BPX_F64 && b.z == 4 && b.chi == 8 && b.d == 2 &&
+    return ctx->dtype == BPX_F64 && b.z >= 2 && b.z <= 4 && b.chi == 8 && b.d == 2 &&
            (size_t)ctx->max_smem_optin >= onchip::SMEM_BYTES;
   return false;
 }
@@ -19,30 +21,64 @@ inline int fast_kernel_for(bpx_ctx* ctx, const Bucket& b) {
   return BPX_KERNEL_GENERIC;
 }
 
+// Build the launch groups: all ONCHIP buckets share ONE persistent launch over a cost-sorted item list
+// (degree 4 first); the first of them is the group leader, the others are skipped by the sweep loop.
 inline int fast_prepare(bpx_ctx* ctx) {
-  bool any = false;
-  for (auto& b : ctx->buckets) any |= (b.kernel == BPX_KERNEL_ONCHIP);
-  if (any)
-    BPX_CUDA(ctx, cudaFuncSetAttribute(onchip::bp_update_onchip_z4c8, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)onchip::SMEM_BYTES));
+  if (ctx->d_onchip_items) {
+    cudaFree(ctx->d_onchip_items);
+    ctx->d_onchip_items = nullptr;
+  }
+  ctx->n_onchip_items = 0;
+  std::vector<int> group;
+  for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
+    ctx->buckets[i].leader = i;
+    if (ctx->buckets[i].kernel == BPX_KERNEL_ONCHIP && !ctx->buckets[i].my_vertices.empty()) group.push_back(i);
+  }
+  if (group.empty()) return BPX_OK;
+  std::sort(group.begin(), group.end(), [&](int a, int b) { return ctx->buckets[a].z > ctx->buckets[b].z; });
+  std::vector<onchip::ItemDesc> items;
+  for (int bi : group) {
+    Bucket& b = ctx->buckets[bi];
+    b.leader = group[0];
+    for (int32_t v : b.my_vertices) {
+      onchip::ItemDesc d;
+      memset(&d, 0, sizeof(d));
+      d.site_off = ctx->site_off[v];
+      d.z = b.z;
+      for (int i = 0; i < b.z; ++i) {
+        const int32_t e = ctx->out_edge[v][i];
+        d.out_edge[i] = e;
+        d.out_off[i] = ctx->msg_off[e];
+        d.in_off[i] = ctx->msg_off[ctx->rev[e]];
+      }
+      items.push_back(d);
+    }
+  }
+  ctx->n_onchip_items = (int)items.size();
+  cudaError_t e = cudaMalloc((void**)&ctx->d_onchip_items, items.size() * sizeof(onchip::ItemDesc));
+  if (e != cudaSuccess) {
+    set_error(ctx, "cudaMalloc(item descriptors) failed: %s", cudaGetErrorString(e));
+    return BPX_ERR_ALLOC;
+  }
+  BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip_items, items.data(), items.size() * sizeof(onchip::ItemDesc), cudaMemcpyHostToDevice));
+  BPX_CUDA(ctx, cudaFuncSetAttribute(onchip::bp_update_onchip_c8, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)onchip::SMEM_BYTES));
   return BPX_OK;
 }
 
 inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize) {
   if (b.kernel == BPX_KERNEL_ONCHIP) {
     onchip::Args k;
-    k.vdesc = ctx->d_vdesc;
-    k.vertices = b.d_vertices;
-    k.n_vertices = (int)b.my_vertices.size();
-    k.msg_off = ctx->d_msg_off;
+    k.items = (const onchip::ItemDesc*)ctx->d_onchip_items;
+    k.n_items = ctx->n_onchip_items;
     k.sites = (const double*)ctx->d_sites;
     k.msg_in = (const double*)msg_in;
     k.msg_out = (double*)msg_out;
     k.residual = ctx->d_residual;
     k.normalize = normalize;
-    const int grid = std::min(k.n_vertices, ctx->num_sms);
+    const int grid = std::min(k.n_items, ctx->num_sms);
     if (grid == 0) return BPX_OK;
-    onchip::bp_update_onchip_z4c8<<<grid, onchip::NTHREADS, onchip::SMEM_BYTES, ctx->stream>>>(k);
+    onchip::bp_update_onchip_c8<<<grid, onchip::NTHREADS, onchip::SMEM_BYTES, ctx->stream>>>(k);
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
     return BPX_OK;

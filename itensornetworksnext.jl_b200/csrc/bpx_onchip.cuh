@@ -1,8 +1,9 @@
 // BPX_KERNEL_ONCHIP: vertex-centric update kernel for buckets whose site tensor fits in shared memory
-// (degree 4, chi = 8, d = 2, Float64: 8192 doubles = 64 KiB) -- BASELINE config 2's dominant bucket.
+// (chi = 8, d = 2, Float64, degree 2..4: at most 8192 doubles = 64 KiB) -- BASELINE config 2.
 //
-// One persistent CTA per SM loops over the bucket's vertices.  For a vertex u with link legs 0..3 it
-// produces all four outgoing messages from ONE read of A_u with the leave-one-out tree
+// One persistent CTA per SM loops over a cost-sorted list of vertices (degree 4 first, then 3, then 2; the
+// cheap boundary vertices fill the last, partially empty wave).  For a vertex u it produces ALL outgoing
+// messages from ONE read of A_u with a leave-one-out tree, e.g. for degree 4
 //     P = A·M0·M1 ;  out3 = close_3(P·M2) ; out2 = close_2(P·M3)
 //     Q = A·M2·M3 ;  out1 = close_1(Q·M0) ; out0 = close_0(Q·M1)
 // (8 absorptions + 4 closures = 12 GEMM units of d·chi^5 MACs instead of 16 for four independent
@@ -18,9 +19,13 @@
 // Shared-memory layout.  Both physical values s = 0,1 of one (a0..a3) sit in one 16-byte chunk, so one
 // LDS.128 / STS.128 feeds the two DMMA chains of s = 0 and s = 1.  The chunk position is an XOR swizzle
 // of the canonical index, linear over GF(2), chosen such that every fragment access pattern used below
-// (g <-> one leg of a pair, t <-> two bits of the other leg of the same pair, pairs (0,1) and (2,3))
-// touches 8 distinct 16-byte bank groups per quarter warp: conflict free.  cp.async (LDGSTS, 16 B)
-// scatters the canonical HBM tensor into that layout while the previous vertex is being computed.
+// (g <-> one leg, t <-> two bits of another leg; leg pairs (0,1), (2,3), (1,2), (0,3)) touches 8 distinct
+// 16-byte bank groups per quarter warp: conflict free.  cp.async (LDGSTS, 16 B) scatters the canonical
+// HBM tensor (and the incoming messages) into shared memory while the previous vertex is computed.
+//
+// Warp roles.  16 compute warps issue the DMMA chains; a 17th warp owns the epilogue (cross-warp tile
+// reduction, sum-normalisation, residual, store), handed over through named barriers so the compute warps
+// never wait for the division / global-memory latency of the epilogue.
 #pragma once
 #include "bpx_common.cuh"
 
@@ -28,10 +33,26 @@ namespace bpx {
 namespace onchip {
 
 constexpr int CHI = 8;
-constexpr int NELEM = 2 * CHI * CHI * CHI * CHI;  // 8192 doubles
-constexpr int NWARPS = 16;
-constexpr int NTHREADS = NWARPS * 32;
+constexpr int NELEM = 2 * CHI * CHI * CHI * CHI;  // 8192 doubles (degree 4)
+constexpr int NCW = 16;                            // compute warps
+constexpr int NCT = NCW * 32;                      // compute threads
+constexpr int NTHREADS = NCT + 32;                 // + epilogue warp
 constexpr int MSG = CHI * CHI;
+
+enum { BAR_LANDED = 1, BAR_PHASE = 2, BAR_RED_FULL = 3, BAR_RED_FREE = 4 };
+
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+
+// per work item, built on the host (fast_prepare): everything the kernel needs without pointer chasing
+struct ItemDesc {
+  int64_t site_off;    // elements
+  int64_t in_off[4];   // message offsets (elements) of the message arriving on leg i
+  int64_t out_off[4];  // message offsets of the outgoing message on leg i
+  int32_t out_edge[4];
+  int32_t z;
+  int32_t pad[3];
+};
 
 // ---- swizzled position (in doubles, s = 0) of element (a0,a1,a2,a3); XOR-linear in every index bit ----
 // bit 0: s | bits 1-3: bank group | bits 4-12: a0[2], a1[1], a1[2], a2[0..2], a3[0..2]
@@ -41,7 +62,8 @@ __device__ __forceinline__ uint32_t leg_pos(int leg, uint32_t a) {
     case 0: return (x02 << 1) | (b1 << 2) | (b2 << 4);
     case 1: return (b1 << 2) | (x02 << 3) | (b1 << 5) | (b2 << 6);
     case 2: return (x02 << 1) | (b1 << 2) | (a << 7);
-    default: return (b1 << 2) | (x02 << 3) | (a << 10);
+    case 3: return (b1 << 2) | (x02 << 3) | (a << 10);
+    default: return 0;  // leg -1: absent
   }
 }
 
@@ -61,12 +83,12 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-// message fragments (M[bra, ket] column-major: (a', a) at a' + CHI*a)
+// message fragments (M[bra, ket] column-major: (a', a) at a' + CHI*a), read from the staged copy
 struct MsgFrag {
   double ma[2];  // M[g, t + 4j]   : A operand of "absorb first leg", B operand of the T-GEMM
   double mb[2];  // M[g, 2t + i]   : B operand of "absorb second leg" (register-chained)
 };
-__device__ __forceinline__ MsgFrag load_frag(const double* __restrict__ M, int g, int t) {
+__device__ __forceinline__ MsgFrag load_frag(const double* M, int g, int t) {
   MsgFrag f;
   f.ma[0] = M[g + CHI * t];
   f.ma[1] = M[g + CHI * (t + 4)];
@@ -75,16 +97,25 @@ __device__ __forceinline__ MsgFrag load_frag(const double* __restrict__ M, int g
   return f;
 }
 
-// Phase 1:  dst[.., x', y', ..] = sum_{x,y} MX[x', x] MY[y', y] src[.., x, y, ..]   (legs X, Y absorbed;
-// U, V are the two other legs).  64 (u, v) columns are split over the warps.
-template <int X, int Y, int U, int V>
-__device__ __forceinline__ void absorb_pair(const double* __restrict__ src, double* __restrict__ dst, const MsgFrag& mx,
-                                            const MsgFrag& my, int warp, int g, int t) {
+// columns: the index values of up to two "spectator" legs C0, C1 (leg -1: absent)
+template <int C0, int C1>
+__device__ __forceinline__ uint32_t col_pos(int col) {
+  return leg_pos(C0, col & 7) ^ leg_pos(C1, col >> 3);
+}
+template <int C0, int C1>
+__device__ __forceinline__ constexpr int n_cols() {
+  return (C0 >= 0 ? CHI : 1) * (C1 >= 0 ? CHI : 1);
+}
+
+// dst[.., x', y', ..] = sum_{x,y} MX[x', x] MY[y', y] src[.., x, y, ..]      (legs X then Y absorbed)
+template <int X, int Y, int C0, int C1>
+__device__ __forceinline__ void absorb_pair(const double* src, double* dst, const MsgFrag& mx, const MsgFrag& my, int warp, int g,
+                                            int t) {
   const uint32_t ld0 = leg_pos(X, t) ^ leg_pos(Y, g), ld1 = leg_pos(X, t + 4) ^ leg_pos(Y, g);
   const uint32_t st0 = leg_pos(X, g) ^ leg_pos(Y, 2 * t), st1 = leg_pos(X, g) ^ leg_pos(Y, 2 * t + 1);
 #pragma unroll 2
-  for (int col = warp; col < CHI * CHI; col += NWARPS) {
-    const uint32_t base = leg_pos(U, col & 7) ^ leg_pos(V, col >> 3);
+  for (int col = warp; col < n_cols<C0, C1>(); col += NCW) {
+    const uint32_t base = col_pos<C0, C1>(col);
     const double2 b0 = *reinterpret_cast<const double2*>(src + (base ^ ld0));
     const double2 b1 = *reinterpret_cast<const double2*>(src + (base ^ ld1));
     // absorb X: D[x' = g, y = 2t+i] = sum_x MX[x', x] src[x, y]      (one chain per physical value s)
@@ -104,18 +135,37 @@ __device__ __forceinline__ void absorb_pair(const double* __restrict__ src, doub
   }
 }
 
-// Phase 2:  out[v', v] = sum_{s, x', y', u'} conj(A[.., u', v']) * ( sum_u MU[u', u] P[.., u, v] )
+// dst[.., x', y, ..] = sum_x MX[x', x] src[.., x, y, ..]      (single absorption; Y is a passive tile leg)
+template <int X, int Y, int C0, int C1>
+__device__ __forceinline__ void absorb_one(const double* src, double* dst, const MsgFrag& mx, int warp, int g, int t) {
+  const uint32_t ld0 = leg_pos(X, t) ^ leg_pos(Y, g), ld1 = leg_pos(X, t + 4) ^ leg_pos(Y, g);
+  const uint32_t st0 = leg_pos(X, g) ^ leg_pos(Y, 2 * t), st1 = leg_pos(X, g) ^ leg_pos(Y, 2 * t + 1);
+  for (int col = warp; col < n_cols<C0, C1>(); col += NCW) {
+    const uint32_t base = col_pos<C0, C1>(col);
+    const double2 b0 = *reinterpret_cast<const double2*>(src + (base ^ ld0));
+    const double2 b1 = *reinterpret_cast<const double2*>(src + (base ^ ld1));
+    double xa0 = 0, xa1 = 0, xb0 = 0, xb1 = 0;
+    dmma(xa0, xa1, mx.ma[0], b0.x);
+    dmma(xb0, xb1, mx.ma[0], b0.y);
+    dmma(xa0, xa1, mx.ma[1], b1.x);
+    dmma(xb0, xb1, mx.ma[1], b1.y);
+    *reinterpret_cast<double2*>(dst + (base ^ st0)) = make_double2(xa0, xb0);
+    *reinterpret_cast<double2*>(dst + (base ^ st1)) = make_double2(xa1, xb1);
+  }
+}
+
+// out[v', v] = sum_{s, cols, u'} conj(A[.., u', v']) * ( sum_u MU[u', u] P[.., u, v] )
 // (leg U absorbed on the fly, leg V left open).  Returns this warp's partial 8x8 tile: thread (g, t) holds
 // out[v' = g, v = 2t], out[v' = g, v = 2t + 1].
-template <int X, int Y, int U, int V>
-__device__ __forceinline__ void absorb_close(const double* __restrict__ P, const double* __restrict__ A, const MsgFrag& mu, int warp,
-                                             int g, int t, double& o0, double& o1) {
+template <int U, int V, int C0, int C1>
+__device__ __forceinline__ void absorb_close(const double* P, const double* A, const MsgFrag& mu, int warp, int g, int t, double& o0,
+                                             double& o1) {
   const uint32_t lp0 = leg_pos(U, t) ^ leg_pos(V, g), lp1 = leg_pos(U, t + 4) ^ leg_pos(V, g);
   const uint32_t la0 = leg_pos(U, 2 * t) ^ leg_pos(V, g), la1 = leg_pos(U, 2 * t + 1) ^ leg_pos(V, g);
   double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
 #pragma unroll 2
-  for (int col = warp; col < CHI * CHI; col += NWARPS) {
-    const uint32_t base = leg_pos(X, col & 7) ^ leg_pos(Y, col >> 3);
+  for (int col = warp; col < n_cols<C0, C1>(); col += NCW) {
+    const uint32_t base = col_pos<C0, C1>(col);
     const double2 p0 = *reinterpret_cast<const double2*>(P + (base ^ lp0));
     const double2 p1 = *reinterpret_cast<const double2*>(P + (base ^ lp1));
     const double2 a0 = *reinterpret_cast<const double2*>(A + (base ^ la0));
@@ -137,10 +187,8 @@ __device__ __forceinline__ void absorb_close(const double* __restrict__ P, const
 }
 
 struct Args {
-  const VDesc* vdesc;
-  const int32_t* vertices;  // the bucket's vertices owned by this rank
-  int n_vertices;
-  const int64_t* msg_off;
+  const ItemDesc* items;
+  int n_items;
   const double* sites;
   const double* msg_in;
   double* msg_out;
@@ -148,84 +196,167 @@ struct Args {
   int normalize;
 };
 
-constexpr size_t SMEM_BYTES = (size_t)(3 * NELEM + 2 * NWARPS * MSG + 2 * MSG) * sizeof(double);
+// shared memory (doubles): A[2][NELEM] | P[NELEM] | red[2][NCW][MSG] | msgs[2][4][MSG]
+constexpr size_t SMEM_DOUBLES = (size_t)3 * NELEM + 2 * NCW * MSG + 2 * 4 * MSG;
+constexpr size_t SMEM_BYTES = SMEM_DOUBLES * sizeof(double);
 
-// scatter the canonical tensor (HBM) into the swizzled shared-memory image, asynchronously
-__device__ __forceinline__ void prefetch_site(double* dst, const double* __restrict__ src) {
-  for (int c = threadIdx.x; c < NELEM / 2; c += NTHREADS) {
+// conflict-free position of tile element el = v' + 8 v inside a 64-element partial tile
+__device__ __forceinline__ int red_pos(int el) { return el ^ (((el >> 4) & 3) << 2); }
+
+// scatter the canonical tensor (HBM) into the swizzled image and stage the incoming messages; asynchronous
+__device__ __forceinline__ void prefetch_item(double* Adst, double* Mdst, const Args& k, int64_t site_off, int64_t in0, int64_t in1,
+                                              int64_t in2, int64_t in3, int z, int tid) {
+  const double* src = k.sites + site_off;
+  const int nchunks = 1 << (3 * z);  // 16-byte chunks: chi^z
+  for (int c = tid; c < nchunks; c += NCT) {
     const uint32_t pos = leg_pos(0, c & 7) ^ leg_pos(1, (c >> 3) & 7) ^ leg_pos(2, (c >> 6) & 7) ^ leg_pos(3, c >> 9);
-    cp_async16(dst + pos, src + 2 * c);
+    cp_async16(Adst + pos, src + 2 * c);
+  }
+  if (tid < z * (MSG / 2)) {
+    const int leg = tid / (MSG / 2), c = tid % (MSG / 2);
+    const int64_t off = leg == 0 ? in0 : leg == 1 ? in1 : leg == 2 ? in2 : in3;
+    cp_async16(Mdst + leg * MSG + 2 * c, k.msg_in + off + 2 * c);
   }
   cp_async_commit();
 }
 
-// cross-warp sum of two 8x8 partial tiles, then the fused normalise/residual/store epilogue
-__device__ __forceinline__ void finish_pair(double* red, double* raw, int warp, int lane, int g, int t, double a0, double a1,
-                                            double b0, double b1, int e_a, int e_b, const Args& k) {
-  // thread (g, t) holds out[v' = g, v = 2t + i] -> element v' + CHI * v
-  red[(0 * NWARPS + warp) * MSG + g + CHI * (2 * t)] = a0;
-  red[(0 * NWARPS + warp) * MSG + g + CHI * (2 * t + 1)] = a1;
-  red[(1 * NWARPS + warp) * MSG + g + CHI * (2 * t)] = b0;
-  red[(1 * NWARPS + warp) * MSG + g + CHI * (2 * t + 1)] = b1;
-  __syncthreads();
-  if (threadIdx.x < 2 * MSG) {
-    const int which = threadIdx.x / MSG, el = threadIdx.x % MSG;
-    double s = 0;
-#pragma unroll
-    for (int w = 0; w < NWARPS; ++w) s += red[(which * NWARPS + w) * MSG + el];
-    raw[which * MSG + el] = s;
-  }
-  __syncthreads();
-  if (warp < 2) {
-    const int e = warp == 0 ? e_a : e_b;
-    const int64_t off = k.msg_off[e];
-    warp_epilogue<double>(raw + warp * MSG, k.msg_in + off, k.msg_out + off, MSG, k.normalize,
-                          k.residual ? k.residual + e : nullptr, lane);
-  }
+// compute warps: hand a branch's two partial tiles to the epilogue warp
+__device__ __forceinline__ void publish(double* red, int warp, int g, int t, double a0, double a1, double b0, double b1) {
+  bar_sync(BAR_RED_FREE, NTHREADS);  // previous branch's tiles consumed; also: every compute warp is done reading P
+  double* r0 = red + warp * MSG;
+  double* r1 = red + (NCW + warp) * MSG;
+  r0[red_pos(g + CHI * (2 * t))] = a0;
+  r0[red_pos(g + CHI * (2 * t + 1))] = a1;
+  r1[red_pos(g + CHI * (2 * t))] = b0;
+  r1[red_pos(g + CHI * (2 * t + 1))] = b1;
+  bar_arrive(BAR_RED_FULL, NTHREADS);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_z4c8(Args k) {
+// epilogue warp: cross-warp sum of one 8x8 tile, then sum-normalise (beliefpropagation.jl:248-253), residual
+// term (beliefpropagation.jl:261-267) and store.  Lane holds elements lane and lane + 32.
+__device__ __forceinline__ void epilogue_tile(const double* red, int lane, const double* old_m, double* new_m, int normalize,
+                                              double* residual_slot) {
+  double v0 = 0, v1 = 0;
+  const int p0 = red_pos(lane), p1 = red_pos(lane + 32);
+#pragma unroll
+  for (int w = 0; w < NCW; ++w) {
+    v0 += red[w * MSG + p0];
+    v1 += red[w * MSG + p1];
+  }
+  const double o0 = old_m[lane], o1 = old_m[lane + 32];
+  const double s = warp_sum_d(v0 + v1);
+  if (normalize && s != 0.0) {
+    v0 /= s;
+    v1 /= s;
+  }
+  new_m[lane] = v0;
+  new_m[lane + 32] = v1;
+  const double dot = warp_sum_d(o0 * v0 + o1 * v1);
+  const double n_old = warp_sum_d(o0 * o0 + o1 * o1);
+  const double n_new = warp_sum_d(v0 * v0 + v1 * v1);
+  if (lane == 0 && residual_slot) *residual_slot = 1.0 - dot * dot / (n_old * n_new);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
   extern __shared__ __align__(16) double smem[];
   double* Pbuf = smem + 2 * NELEM;
   double* red = smem + 3 * NELEM;
-  double* raw = red + 2 * NWARPS * MSG;
+  double* msgs = red + 2 * NCW * MSG;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int G = gridDim.x;
+  if ((int)blockIdx.x >= k.n_items) return;
 
+  if (warp == NCW) {
+    // ================= epilogue warp =================
+    bar_arrive(BAR_RED_FREE, NTHREADS);  // red starts free
+    for (int item = blockIdx.x; item < k.n_items; item += G) {
+      const ItemDesc* d = k.items + item;
+      const int z = d->z;
+      // branch list mirrors the compute warps: (leg of tile 0, leg of tile 1 or -1)
+      const int nb = z == 2 ? 1 : 2;
+      for (int b = 0; b < nb; ++b) {
+        int l0, l1;
+        if (z == 4) { l0 = b == 0 ? 3 : 1; l1 = b == 0 ? 2 : 0; }
+        else if (z == 3) { l0 = b == 0 ? 2 : 0; l1 = b == 0 ? 1 : -1; }
+        else { l0 = 1; l1 = 0; }
+        const int64_t off0 = d->out_off[l0];
+        const int e0 = d->out_edge[l0];
+        const int64_t off1 = l1 >= 0 ? d->out_off[l1] : 0;
+        const int e1 = l1 >= 0 ? d->out_edge[l1] : 0;
+        bar_sync(BAR_RED_FULL, NTHREADS);
+        epilogue_tile(red, lane, k.msg_in + off0, k.msg_out + off0, k.normalize, k.residual ? k.residual + e0 : nullptr);
+        if (l1 >= 0)
+          epilogue_tile(red + NCW * MSG, lane, k.msg_in + off1, k.msg_out + off1, k.normalize, k.residual ? k.residual + e1 : nullptr);
+        bar_arrive(BAR_RED_FREE, NTHREADS);
+      }
+    }
+    return;
+  }
+
+  // ================= compute warps =================
+  const int tid = threadIdx.x;
   int item = blockIdx.x;
-  if (item >= k.n_vertices) return;
+  // descriptor of the item being prefetched is held in registers one iteration ahead of its use
+  {
+    const ItemDesc* d = k.items + item;
+    prefetch_item(smem, msgs, k, d->site_off, d->in_off[0], d->in_off[1], d->in_off[2], d->in_off[3], d->z, tid);
+  }
+  int n_z = k.items[item].z;
   int cur = 0;
-  prefetch_site(smem, k.sites + k.vdesc[k.vertices[item]].site_off);
-  for (; item < k.n_vertices; item += gridDim.x, cur ^= 1) {
-    const VDesc& vd = k.vdesc[k.vertices[item]];
-    const int next = item + gridDim.x;
-    if (next < k.n_vertices) {
-      prefetch_site(smem + (cur ^ 1) * NELEM, k.sites + k.vdesc[k.vertices[next]].site_off);
+  for (; item < k.n_items; item += G, cur ^= 1) {
+    const int z = n_z;
+    const int next = item + G;
+    if (next < k.n_items) {
+      // descriptor loads are L1/L2 hits issued a full vertex ahead of the data they steer
+      const ItemDesc* d = k.items + next;
+      n_z = d->z;
+      prefetch_item(smem + (cur ^ 1) * NELEM, msgs + (cur ^ 1) * 4 * MSG, k, d->site_off, d->in_off[0], d->in_off[1], d->in_off[2],
+                    d->in_off[3], n_z, tid);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
-    const MsgFrag m0 = load_frag(k.msg_in + k.msg_off[vd.in_edge[0]], g, t);
-    const MsgFrag m1 = load_frag(k.msg_in + k.msg_off[vd.in_edge[1]], g, t);
-    const MsgFrag m2 = load_frag(k.msg_in + k.msg_off[vd.in_edge[2]], g, t);
-    const MsgFrag m3 = load_frag(k.msg_in + k.msg_off[vd.in_edge[3]], g, t);
-    __syncthreads();  // A_u landed (all threads' cp.async groups), previous vertex's epilogue done
+    bar_sync(BAR_LANDED, NCT);  // A_u and its messages landed (all compute threads' cp.async groups)
     const double* A = smem + cur * NELEM;
-    double a0, a1, b0, b1;
-
-    // branch P = A·M0·M1  ->  out3 (absorb 2, close 3), out2 (absorb 3, close 2)
-    absorb_pair<0, 1, 2, 3>(A, Pbuf, m0, m1, warp, g, t);
-    __syncthreads();
-    absorb_close<0, 1, 2, 3>(Pbuf, A, m2, warp, g, t, a0, a1);
-    absorb_close<0, 1, 3, 2>(Pbuf, A, m3, warp, g, t, b0, b1);
-    finish_pair(red, raw, warp, lane, g, t, a0, a1, b0, b1, vd.out_edge[3], vd.out_edge[2], k);
-
-    // branch Q = A·M2·M3  ->  out1 (absorb 0, close 1), out0 (absorb 1, close 0)
-    absorb_pair<2, 3, 0, 1>(A, Pbuf, m2, m3, warp, g, t);
-    __syncthreads();
-    absorb_close<2, 3, 0, 1>(Pbuf, A, m0, warp, g, t, a0, a1);
-    absorb_close<2, 3, 1, 0>(Pbuf, A, m1, warp, g, t, b0, b1);
-    finish_pair(red, raw, warp, lane, g, t, a0, a1, b0, b1, vd.out_edge[1], vd.out_edge[0], k);
+    const double* M = msgs + cur * 4 * MSG;
+    double a0, a1, b0 = 0, b1 = 0;
+    if (z == 4) {
+      const MsgFrag m0 = load_frag(M, g, t), m1 = load_frag(M + MSG, g, t), m2 = load_frag(M + 2 * MSG, g, t),
+                    m3 = load_frag(M + 3 * MSG, g, t);
+      // branch P = A·M0·M1  ->  out3 (absorb 2, close 3), out2 (absorb 3, close 2)
+      absorb_pair<0, 1, 2, 3>(A, Pbuf, m0, m1, warp, g, t);
+      bar_sync(BAR_PHASE, NCT);
+      absorb_close<2, 3, 0, 1>(Pbuf, A, m2, warp, g, t, a0, a1);
+      absorb_close<3, 2, 0, 1>(Pbuf, A, m3, warp, g, t, b0, b1);
+      publish(red, warp, g, t, a0, a1, b0, b1);
+      // branch Q = A·M2·M3  ->  out1 (absorb 0, close 1), out0 (absorb 1, close 0)
+      absorb_pair<2, 3, 0, 1>(A, Pbuf, m2, m3, warp, g, t);
+      bar_sync(BAR_PHASE, NCT);
+      absorb_close<0, 1, 2, 3>(Pbuf, A, m0, warp, g, t, a0, a1);
+      absorb_close<1, 0, 2, 3>(Pbuf, A, m1, warp, g, t, b0, b1);
+      publish(red, warp, g, t, a0, a1, b0, b1);
+    } else if (z == 3) {
+      const MsgFrag m0 = load_frag(M, g, t), m1 = load_frag(M + MSG, g, t), m2 = load_frag(M + 2 * MSG, g, t);
+      // X = A·M0  ->  out2 (absorb 1, close 2), out1 (absorb 2, close 1)
+      absorb_one<0, 1, 2, -1>(A, Pbuf, m0, warp, g, t);
+      bar_sync(BAR_PHASE, NCT);
+      absorb_close<1, 2, 0, -1>(Pbuf, A, m1, warp, g, t, a0, a1);
+      absorb_close<2, 1, 0, -1>(Pbuf, A, m2, warp, g, t, b0, b1);
+      publish(red, warp, g, t, a0, a1, b0, b1);
+      // X = A·M2  ->  out0 (absorb 1, close 0)
+      absorb_one<2, 1, 0, -1>(A, Pbuf, m2, warp, g, t);
+      bar_sync(BAR_PHASE, NCT);
+      absorb_close<1, 0, 2, -1>(Pbuf, A, m1, warp, g, t, a0, a1);
+      publish(red, warp, g, t, a0, a1, 0.0, 0.0);
+    } else {  // z == 2: out1 (absorb 0, close 1), out0 (absorb 1, close 0) straight from A
+      const MsgFrag m0 = load_frag(M, g, t), m1 = load_frag(M + MSG, g, t);
+      absorb_close<0, 1, -1, -1>(A, A, m0, warp, g, t, a0, a1);
+      absorb_close<1, 0, -1, -1>(A, A, m1, warp, g, t, b0, b1);
+      publish(red, warp, g, t, a0, a1, b0, b1);
+    }
   }
+  // let the epilogue warp's last arrive complete
+  bar_sync(BAR_RED_FREE, NTHREADS);
 }
 
 }  // namespace onchip

@@ -185,9 +185,10 @@ class BPXContext:
     def buckets(self):
         out = []
         for b in range(self.lib.bpx_num_buckets(self.h)):
-            info = (C.c_int64 * 6)()
+            info = (C.c_int64 * 8)()
             self._check(self.lib.bpx_bucket_info(self.h, b, info))
-            out.append(dict(degree=info[0], chi=info[1], phys=info[2], vertices=info[3], edges=info[4], kernel=info[5]))
+            out.append(dict(degree=info[0], chi=info[1], phys=info[2], vertices=info[3], edges=info[4], kernel=info[5],
+                            leader=info[6]))
         return out
 
     def set_kernel_policy(self, kernel: int):
