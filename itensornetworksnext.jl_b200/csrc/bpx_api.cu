@@ -83,6 +83,7 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_all_edges);
   F(c->d_fast_scratch);
   F(c->d_onchip_items);
+  F(c->d_sites_swz);
   for (auto& b : c->buckets) {
     F(b.d_vertices);
     F(b.d_edges);
@@ -396,6 +397,7 @@ extern "C" int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed) {
   NEED_DIMS(ctx, "bpx_set_site_tensors");
   REQUIRE(ctx, packed || ctx->site_off[ctx->nv] == 0, "bpx_set_site_tensors: NULL data");
   // a rank only needs the tensors it owns, but uploading all keeps offsets identical everywhere
+  ctx->sites_dirty = true;
   BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sites, packed, (size_t)ctx->site_off[ctx->nv] * ctx->esize, cudaMemcpyHostToDevice,
                                 ctx->stream));
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -406,6 +408,7 @@ extern "C" int bpx_set_site_tensor(bpx_ctx* ctx, int64_t v, const void* data) {
   NEED_DIMS(ctx, "bpx_set_site_tensor");
   REQUIRE(ctx, v >= 0 && v < ctx->nv && data, "bpx_set_site_tensor: bad arguments");
   const size_t off = (size_t)ctx->site_off[v] * ctx->esize, n = (size_t)(ctx->site_off[v + 1] - ctx->site_off[v]) * ctx->esize;
+  ctx->sites_dirty = true;
   BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_sites + off, data, n, cudaMemcpyHostToDevice, ctx->stream));
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return BPX_OK;
@@ -501,6 +504,7 @@ static int sweep_once(bpx_ctx* ctx, int normalize, int hist_idx) {
   const void* in = ctx->d_msg[ctx->cur];
   void* out = ctx->d_msg[ctx->cur ^ 1];
   int rc;
+  if ((rc = fast_refresh_sites(ctx))) return rc;
   for (int bi = 0; bi < (int)ctx->buckets.size(); ++bi) {
     Bucket& b = ctx->buckets[bi];
     if (b.my_edges.empty() || b.leader != bi) continue;  // merged into its group leader's launch
@@ -907,5 +911,19 @@ extern "C" int bpx_fill_randn(uint64_t seed, uint64_t stream, int dtype, int64_t
     const double s = 0.70710678118654752440;
     for (int64_t i = 0; i < 2 * n; ++i) o[i] = s * randn_at(seed, stream, (uint64_t)i);
   }
+  return BPX_OK;
+}
+
+// debug only (not part of include/bpx.h): per-phase timestamps of CTA 0 in BPX_ONCHIP_TIMING builds
+extern "C" int bpx_debug_timing(bpx_ctx* ctx, long long* out, int n) {
+  if (!ctx) return BPX_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (!ctx->d_timing) {
+    if (cudaMalloc(&ctx->d_timing, 8 * 32 * 16 * sizeof(long long)) != cudaSuccess) return BPX_ERR_ALLOC;
+    cudaMemset(ctx->d_timing, 0, 8 * 32 * 16 * sizeof(long long));
+    return BPX_OK;
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaMemcpy(out, ctx->d_timing, sizeof(long long) * std::min(n, 8 * 32 * 16), cudaMemcpyDeviceToHost);
   return BPX_OK;
 }

@@ -60,7 +60,10 @@ struct bpx_ctx {
   int history_cap = 0, history_len = 0;
   void* d_scratch = nullptr;
   int gen_smem_elems = 0, gen_smem_bytes = 0, gen_grid = 0;
+  void* d_timing = nullptr;  // debug: per-phase clock64 stamps (BPX_ONCHIP_TIMING builds)
   void* d_onchip_items = nullptr;
+  void* d_sites_swz = nullptr;  // pre-swizzled site tensors for the ONCHIP kernel (bpx_onchip.cuh)
+  bool sites_dirty = true;
   int n_onchip_items = 0;
   void* d_fast_scratch = nullptr;
   size_t fast_scratch_bytes = 0;
@@ -106,6 +109,7 @@ int launch_generic_update(bpx_ctx* ctx, const void* msg_in, void* msg_out, const
 int fast_kernel_for(bpx_ctx* ctx, const Bucket& b);
 bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel);
 int fast_prepare(bpx_ctx* ctx);
+int fast_refresh_sites(bpx_ctx* ctx);
 int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize);
 // multi-GPU (bpx_halo.cuh)
 int halo_push(bpx_ctx* ctx, void* msg_out);

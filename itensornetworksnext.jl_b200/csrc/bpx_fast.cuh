@@ -28,6 +28,10 @@ inline int fast_prepare(bpx_ctx* ctx) {
     cudaFree(ctx->d_onchip_items);
     ctx->d_onchip_items = nullptr;
   }
+  if (ctx->d_sites_swz) {
+    cudaFree(ctx->d_sites_swz);
+    ctx->d_sites_swz = nullptr;
+  }
   ctx->n_onchip_items = 0;
   std::vector<int> group;
   for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
@@ -51,6 +55,11 @@ inline int fast_prepare(bpx_ctx* ctx) {
         d.out_off[i] = ctx->msg_off[e];
         d.in_off[i] = ctx->msg_off[ctx->rev[e]];
       }
+      if (b.z == 4) {  // two half items (branch P, branch Q): finer granularity for the last wave
+        d.branch = 0;
+        items.push_back(d);
+        d.branch = 1;
+      }
       items.push_back(d);
     }
   }
@@ -63,15 +72,36 @@ inline int fast_prepare(bpx_ctx* ctx) {
   BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip_items, items.data(), items.size() * sizeof(onchip::ItemDesc), cudaMemcpyHostToDevice));
   BPX_CUDA(ctx, cudaFuncSetAttribute(onchip::bp_update_onchip_c8, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)onchip::SMEM_BYTES));
+  // private pre-swizzled image of the site tensors (same offsets as the canonical buffer), refreshed lazily
+  e = cudaMalloc(&ctx->d_sites_swz, std::max<size_t>(16, (size_t)ctx->site_off[ctx->nv] * ctx->esize));
+  if (e != cudaSuccess) {
+    set_error(ctx, "cudaMalloc(pre-swizzled site image) failed: %s", cudaGetErrorString(e));
+    return BPX_ERR_ALLOC;
+  }
+  ctx->sites_dirty = true;
+  return BPX_OK;
+}
+
+// re-derive kernel-private images of the site tensors after an upload
+inline int fast_refresh_sites(bpx_ctx* ctx) {
+  if (!ctx->sites_dirty) return BPX_OK;
+  if (ctx->d_sites_swz && ctx->n_onchip_items > 0) {
+    onchip::swizzle_sites<<<std::min(ctx->n_onchip_items, 4 * ctx->num_sms), 256, 0, ctx->stream>>>(
+        (const onchip::ItemDesc*)ctx->d_onchip_items, ctx->n_onchip_items, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+  }
+  ctx->sites_dirty = false;
   return BPX_OK;
 }
 
 inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize) {
   if (b.kernel == BPX_KERNEL_ONCHIP) {
     onchip::Args k;
+    k.timing = (long long*)ctx->d_timing;
     k.items = (const onchip::ItemDesc*)ctx->d_onchip_items;
     k.n_items = ctx->n_onchip_items;
-    k.sites = (const double*)ctx->d_sites;
+    k.sites = (const double*)ctx->d_sites_swz;
     k.msg_in = (const double*)msg_in;
     k.msg_out = (double*)msg_out;
     k.residual = ctx->d_residual;

@@ -20,12 +20,14 @@
 // LDS.128 / STS.128 feeds the two DMMA chains of s = 0 and s = 1.  The chunk position is an XOR swizzle
 // of the canonical index, linear over GF(2), chosen such that every fragment access pattern used below
 // (g <-> one leg, t <-> two bits of another leg; leg pairs (0,1), (2,3), (1,2), (0,3)) touches 8 distinct
-// 16-byte bank groups per quarter warp: conflict free.  cp.async (LDGSTS, 16 B) scatters the canonical
-// HBM tensor (and the incoming messages) into shared memory while the previous vertex is computed.
+// 16-byte bank groups per quarter warp: conflict free.  The library keeps a private, PRE-SWIZZLED HBM image of
+// every on-chip site tensor (built once per upload by swizzle_sites), so the whole 64 KiB tensor and its
+// incoming messages arrive by TMA bulk copies (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP) issued by
+// one thread while the previous vertex is being computed -- no LSU / issue-slot cost for the copy.
 //
-// Warp roles.  16 compute warps issue the DMMA chains; a 17th warp owns the epilogue (cross-warp tile
-// reduction, sum-normalisation, residual, store), handed over through named barriers so the compute warps
-// never wait for the division / global-memory latency of the epilogue.
+// Warp roles.  16 compute warps issue the DMMA chains and reduce the per-warp partial 8x8 tiles; two more
+// warps own the epilogue (sum-normalisation, residual, store), handed over through named barriers so the
+// compute warps never wait for the division / global-memory latency of the epilogue.
 #pragma once
 #include "bpx_common.cuh"
 
@@ -36,10 +38,12 @@ constexpr int CHI = 8;
 constexpr int NELEM = 2 * CHI * CHI * CHI * CHI;  // 8192 doubles (degree 4)
 constexpr int NCW = 16;                            // compute warps
 constexpr int NCT = NCW * 32;                      // compute threads
-constexpr int NTHREADS = NCT + 32;                 // + epilogue warp
+constexpr int NEW = 2;                             // epilogue warps (one per tile of a branch)
+constexpr int NTHREADS = NCT + 32 * NEW + 32;      // + TMA producer warp
 constexpr int MSG = CHI * CHI;
 
-enum { BAR_LANDED = 1, BAR_PHASE = 2, BAR_RED_FULL = 3, BAR_RED_FREE = 4 };
+enum { BAR_PHASE = 1, BAR_RED = 2, BAR_RAW_FULL = 3, BAR_RAW_FREE = 4, BAR_SLOT_FREE = 5 /* and 6 */ };
+constexpr int NRAW = NCT + 32 * NEW;  // participants of the raw-tile hand-over
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
@@ -51,7 +55,8 @@ struct ItemDesc {
   int64_t out_off[4];  // message offsets of the outgoing message on leg i
   int32_t out_edge[4];
   int32_t z;
-  int32_t pad[3];
+  int32_t branch;  // degree 4 only: 0 = branch P (out3, out2), 1 = branch Q (out1, out0); each is its own work item
+  int32_t pad[2];
 };
 
 // ---- swizzled position (in doubles, s = 0) of element (a0,a1,a2,a3); XOR-linear in every index bit ----
@@ -73,15 +78,34 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+// ---- mbarrier + TMA bulk copy (global -> shared::cta) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // message fragments (M[bra, ket] column-major: (a', a) at a' + CHI*a), read from the staged copy
 struct MsgFrag {
@@ -186,155 +210,203 @@ __device__ __forceinline__ void absorb_close(const double* P, const double* A, c
   o1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
 }
 
+#ifdef BPX_ONCHIP_TIMING
+#define TSTAMP(i) do { if (lane == 0 && blockIdx.x == 0 && k.timing && n_iter < 8) k.timing[(n_iter * 32 + warp) * 16 + (i)] = clock64(); } while (0)
+#else
+#define TSTAMP(i) do { } while (0)
+#endif
+
 struct Args {
+  long long* timing;
   const ItemDesc* items;
   int n_items;
-  const double* sites;
+  const double* sites;  // PRE-SWIZZLED image (same offsets as the canonical buffer)
   const double* msg_in;
   double* msg_out;
   double* residual;
   int normalize;
 };
 
-// shared memory (doubles): A[2][NELEM] | P[NELEM] | red[2][NCW][MSG] | msgs[2][4][MSG]
-constexpr size_t SMEM_DOUBLES = (size_t)3 * NELEM + 2 * NCW * MSG + 2 * 4 * MSG;
+// shared memory (doubles): A[2][NELEM] | P[NELEM] | red[2][NCW][MSG] | raw[2][MSG] | msgs[2][4][MSG] | 2 mbarriers
+constexpr size_t SMEM_DOUBLES = (size_t)3 * NELEM + 2 * NCW * MSG + 2 * MSG + 2 * 4 * MSG + 2;
 constexpr size_t SMEM_BYTES = SMEM_DOUBLES * sizeof(double);
 
 // conflict-free position of tile element el = v' + 8 v inside a 64-element partial tile
 __device__ __forceinline__ int red_pos(int el) { return el ^ (((el >> 4) & 3) << 2); }
 
-// scatter the canonical tensor (HBM) into the swizzled image and stage the incoming messages; asynchronous
-__device__ __forceinline__ void prefetch_item(double* Adst, double* Mdst, const Args& k, int64_t site_off, int64_t in0, int64_t in1,
-                                              int64_t in2, int64_t in3, int z, int tid) {
-  const double* src = k.sites + site_off;
-  const int nchunks = 1 << (3 * z);  // 16-byte chunks: chi^z
-  for (int c = tid; c < nchunks; c += NCT) {
-    const uint32_t pos = leg_pos(0, c & 7) ^ leg_pos(1, (c >> 3) & 7) ^ leg_pos(2, (c >> 6) & 7) ^ leg_pos(3, c >> 9);
-    cp_async16(Adst + pos, src + 2 * c);
+// one thread: TMA the pre-swizzled tensor and the incoming messages of an item into buffer slot `slot`
+__device__ __forceinline__ void tma_item(double* Adst, double* Mdst, uint64_t* bar, const Args& k, const ItemDesc* d) {
+  const int z = d->z;
+  const uint32_t abytes = (16u << (3 * z));  // 2 * 8^z doubles
+  fence_proxy_async();  // generic-proxy reads of this slot (previous tenant) happen-before the async-proxy writes
+  mbar_expect_tx(bar, abytes + z * MSG * 8);
+  const char* src = reinterpret_cast<const char*>(k.sites + d->site_off);
+  for (uint32_t off = 0; off < abytes; off += 16384) {
+    const uint32_t n = abytes - off < 16384 ? abytes - off : 16384;
+    tma_bulk_g2s(reinterpret_cast<char*>(Adst) + off, src + off, n, bar);
   }
-  if (tid < z * (MSG / 2)) {
-    const int leg = tid / (MSG / 2), c = tid % (MSG / 2);
-    const int64_t off = leg == 0 ? in0 : leg == 1 ? in1 : leg == 2 ? in2 : in3;
-    cp_async16(Mdst + leg * MSG + 2 * c, k.msg_in + off + 2 * c);
-  }
-  cp_async_commit();
+  for (int i = 0; i < z; ++i) tma_bulk_g2s(Mdst + i * MSG, k.msg_in + d->in_off[i], MSG * 8, bar);
 }
 
-// compute warps: hand a branch's two partial tiles to the epilogue warp
-__device__ __forceinline__ void publish(double* red, int warp, int g, int t, double a0, double a1, double b0, double b1) {
-  bar_sync(BAR_RED_FREE, NTHREADS);  // previous branch's tiles consumed; also: every compute warp is done reading P
+// compute warps: reduce the 16 per-warp partial tiles of a branch (two 8x8 outputs) and hand them over
+__device__ __forceinline__ void publish(double* red, double* raw, int warp, int lane, int g, int t, double a0, double a1, double b0,
+                                        double b1) {
   double* r0 = red + warp * MSG;
   double* r1 = red + (NCW + warp) * MSG;
   r0[red_pos(g + CHI * (2 * t))] = a0;
   r0[red_pos(g + CHI * (2 * t + 1))] = a1;
   r1[red_pos(g + CHI * (2 * t))] = b0;
   r1[red_pos(g + CHI * (2 * t + 1))] = b1;
-  bar_arrive(BAR_RED_FULL, NTHREADS);
+  bar_sync(BAR_RED, NCT);  // partial tiles visible; every compute warp is done reading P and A of this branch
+  // warp w reduces elements 8w'..8w'+7 of tile (w / 8): lane = 8 * q + e sums partial warps 4q..4q+3 of element e
+  const int tile = warp >> 3, el = (warp & 7) * 8 + (lane & 7), q = lane >> 3;
+  const double* r = red + tile * NCW * MSG + red_pos(el);
+  double s = (r[(4 * q) * MSG] + r[(4 * q + 1) * MSG]) + (r[(4 * q + 2) * MSG] + r[(4 * q + 3) * MSG]);
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  bar_sync(BAR_RAW_FREE, NRAW);  // epilogue warps are done with the previous branch's raw tiles
+  if (lane < 8) raw[tile * MSG + el] = s;
+  bar_arrive(BAR_RAW_FULL, NRAW);
 }
 
-// epilogue warp: cross-warp sum of one 8x8 tile, then sum-normalise (beliefpropagation.jl:248-253), residual
-// term (beliefpropagation.jl:261-267) and store.  Lane holds elements lane and lane + 32.
-__device__ __forceinline__ void epilogue_tile(const double* red, int lane, const double* old_m, double* new_m, int normalize,
+// epilogue warp: sum-normalise (beliefpropagation.jl:248-253), residual term (beliefpropagation.jl:261-267), store.
+// Lane holds elements lane and lane + 32.  The residual 1 - |<old^, new^>|^2 is invariant under the scaling,
+// so all four reductions run interleaved on the raw tile.
+__device__ __forceinline__ void epilogue_tile(double v0, double v1, double o0, double o1, int lane, double* new_m, int normalize,
                                               double* residual_slot) {
-  double v0 = 0, v1 = 0;
-  const int p0 = red_pos(lane), p1 = red_pos(lane + 32);
+  double s = v0 + v1, dot = o0 * v0 + o1 * v1, n_old = o0 * o0 + o1 * o1, n_new = v0 * v0 + v1 * v1;
 #pragma unroll
-  for (int w = 0; w < NCW; ++w) {
-    v0 += red[w * MSG + p0];
-    v1 += red[w * MSG + p1];
+  for (int m = 16; m > 0; m >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, m);
+    dot += __shfl_xor_sync(0xffffffffu, dot, m);
+    n_old += __shfl_xor_sync(0xffffffffu, n_old, m);
+    n_new += __shfl_xor_sync(0xffffffffu, n_new, m);
   }
-  const double o0 = old_m[lane], o1 = old_m[lane + 32];
-  const double s = warp_sum_d(v0 + v1);
   if (normalize && s != 0.0) {
     v0 /= s;
     v1 /= s;
   }
   new_m[lane] = v0;
   new_m[lane + 32] = v1;
-  const double dot = warp_sum_d(o0 * v0 + o1 * v1);
-  const double n_old = warp_sum_d(o0 * o0 + o1 * o1);
-  const double n_new = warp_sum_d(v0 * v0 + v1 * v1);
   if (lane == 0 && residual_slot) *residual_slot = 1.0 - dot * dot / (n_old * n_new);
 }
 
+// Build the pre-swizzled image: dst[site_off + pos(c)] = src[site_off + 2c .. 2c+1] for every 16-byte chunk c.
+__global__ void swizzle_sites(const ItemDesc* items, int n_items, const double* __restrict__ src, double* __restrict__ dst) {
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int64_t off = items[item].site_off;
+    const int nchunks = 1 << (3 * items[item].z);
+    for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
+      const uint32_t pos = leg_pos(0, c & 7) ^ leg_pos(1, (c >> 3) & 7) ^ leg_pos(2, (c >> 6) & 7) ^ leg_pos(3, c >> 9);
+      const double2 v = *reinterpret_cast<const double2*>(src + off + 2 * c);
+      *reinterpret_cast<double2*>(dst + off + pos) = v;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   double* Pbuf = smem + 2 * NELEM;
   double* red = smem + 3 * NELEM;
-  double* msgs = red + 2 * NCW * MSG;
+  double* raw = red + 2 * NCW * MSG;
+  double* msgs = raw + 2 * MSG;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(msgs + 2 * 4 * MSG);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int G = gridDim.x;
   if ((int)blockIdx.x >= k.n_items) return;
 
-  if (warp == NCW) {
-    // ================= epilogue warp =================
-    bar_arrive(BAR_RED_FREE, NTHREADS);  // red starts free
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NCW + NEW) {
+    // ================= producer warp: TMA of item n into slot n & 1, two items ahead of the compute warps ==========
+    int n = 0;
+    for (int item = blockIdx.x; item < k.n_items; item += G, ++n) {
+      if (n >= 2) bar_sync(BAR_SLOT_FREE + (n & 1), NCT + 32);  // compute warps are done with the slot's previous tenant
+      if (lane == 0) tma_item(smem + (n & 1) * NELEM, msgs + (n & 1) * 4 * MSG, &mbar[n & 1], k, k.items + item);
+    }
+    return;
+  }
+
+  if (warp >= NCW) {
+    // ================= epilogue warps: warp NCW + i owns tile i of every branch =================
+    const int which = warp - NCW;
+    bar_arrive(BAR_RAW_FREE, NRAW);  // raw starts free
     for (int item = blockIdx.x; item < k.n_items; item += G) {
       const ItemDesc* d = k.items + item;
-      const int z = d->z;
-      // branch list mirrors the compute warps: (leg of tile 0, leg of tile 1 or -1)
-      const int nb = z == 2 ? 1 : 2;
+      const int z = d->z, br = d->branch;
+      const int nb = z == 3 ? 2 : 1;
       for (int b = 0; b < nb; ++b) {
+        // branch list mirrors the compute warps: (leg of tile 0, leg of tile 1 or -1)
         int l0, l1;
-        if (z == 4) { l0 = b == 0 ? 3 : 1; l1 = b == 0 ? 2 : 0; }
+        if (z == 4) { l0 = br == 0 ? 3 : 1; l1 = br == 0 ? 2 : 0; }
         else if (z == 3) { l0 = b == 0 ? 2 : 0; l1 = b == 0 ? 1 : -1; }
         else { l0 = 1; l1 = 0; }
-        const int64_t off0 = d->out_off[l0];
-        const int e0 = d->out_edge[l0];
-        const int64_t off1 = l1 >= 0 ? d->out_off[l1] : 0;
-        const int e1 = l1 >= 0 ? d->out_edge[l1] : 0;
-        bar_sync(BAR_RED_FULL, NTHREADS);
-        epilogue_tile(red, lane, k.msg_in + off0, k.msg_out + off0, k.normalize, k.residual ? k.residual + e0 : nullptr);
-        if (l1 >= 0)
-          epilogue_tile(red + NCW * MSG, lane, k.msg_in + off1, k.msg_out + off1, k.normalize, k.residual ? k.residual + e1 : nullptr);
-        bar_arrive(BAR_RED_FREE, NTHREADS);
+        const int l = which == 0 ? l0 : l1;
+        double o0 = 0, o1 = 0;
+        int64_t off = 0;
+        int e = 0;
+        if (l >= 0) {  // old message: issued before the hand-over so its latency overlaps the compute
+          off = d->out_off[l];
+          e = d->out_edge[l];
+          o0 = k.msg_in[off + lane];
+          o1 = k.msg_in[off + lane + 32];
+        }
+        bar_sync(BAR_RAW_FULL, NRAW);
+        const double v0 = raw[which * MSG + lane], v1 = raw[which * MSG + lane + 32];
+        bar_arrive(BAR_RAW_FREE, NRAW);  // values are in registers: raw may be overwritten
+        if (l >= 0) epilogue_tile(v0, v1, o0, o1, lane, k.msg_out + off, k.normalize, k.residual ? k.residual + e : nullptr);
       }
     }
     return;
   }
 
   // ================= compute warps =================
-  const int tid = threadIdx.x;
-  int item = blockIdx.x;
-  // descriptor of the item being prefetched is held in registers one iteration ahead of its use
-  {
+  int n_iter = 0;
+  for (int item = blockIdx.x; item < k.n_items; item += G, ++n_iter) {
+    const int cur = n_iter & 1;
     const ItemDesc* d = k.items + item;
-    prefetch_item(smem, msgs, k, d->site_off, d->in_off[0], d->in_off[1], d->in_off[2], d->in_off[3], d->z, tid);
-  }
-  int n_z = k.items[item].z;
-  int cur = 0;
-  for (; item < k.n_items; item += G, cur ^= 1) {
-    const int z = n_z;
-    const int next = item + G;
-    if (next < k.n_items) {
-      // descriptor loads are L1/L2 hits issued a full vertex ahead of the data they steer
-      const ItemDesc* d = k.items + next;
-      n_z = d->z;
-      prefetch_item(smem + (cur ^ 1) * NELEM, msgs + (cur ^ 1) * 4 * MSG, k, d->site_off, d->in_off[0], d->in_off[1], d->in_off[2],
-                    d->in_off[3], n_z, tid);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    bar_sync(BAR_LANDED, NCT);  // A_u and its messages landed (all compute threads' cp.async groups)
+    const int z = d->z, br = d->branch;  // L1/L2 hits; consumed only after the mbarrier wait
+    TSTAMP(0);
+    mbar_wait(&mbar[cur], (n_iter >> 1) & 1);  // A_u and its messages landed
+    TSTAMP(2);
     const double* A = smem + cur * NELEM;
     const double* M = msgs + cur * 4 * MSG;
     double a0, a1, b0 = 0, b1 = 0;
     if (z == 4) {
-      const MsgFrag m0 = load_frag(M, g, t), m1 = load_frag(M + MSG, g, t), m2 = load_frag(M + 2 * MSG, g, t),
-                    m3 = load_frag(M + 3 * MSG, g, t);
-      // branch P = A·M0·M1  ->  out3 (absorb 2, close 3), out2 (absorb 3, close 2)
-      absorb_pair<0, 1, 2, 3>(A, Pbuf, m0, m1, warp, g, t);
-      bar_sync(BAR_PHASE, NCT);
-      absorb_close<2, 3, 0, 1>(Pbuf, A, m2, warp, g, t, a0, a1);
-      absorb_close<3, 2, 0, 1>(Pbuf, A, m3, warp, g, t, b0, b1);
-      publish(red, warp, g, t, a0, a1, b0, b1);
-      // branch Q = A·M2·M3  ->  out1 (absorb 0, close 1), out0 (absorb 1, close 0)
-      absorb_pair<2, 3, 0, 1>(A, Pbuf, m2, m3, warp, g, t);
-      bar_sync(BAR_PHASE, NCT);
-      absorb_close<0, 1, 2, 3>(Pbuf, A, m0, warp, g, t, a0, a1);
-      absorb_close<1, 0, 2, 3>(Pbuf, A, m1, warp, g, t, b0, b1);
-      publish(red, warp, g, t, a0, a1, b0, b1);
+      if (br == 0) {
+        // branch P = A·M0·M1  ->  out3 (absorb 2, close 3), out2 (absorb 3, close 2)
+        const MsgFrag m0 = load_frag(M, g, t), m1 = load_frag(M + MSG, g, t), m2 = load_frag(M + 2 * MSG, g, t),
+                      m3 = load_frag(M + 3 * MSG, g, t);
+        TSTAMP(3);
+        absorb_pair<0, 1, 2, 3>(A, Pbuf, m0, m1, warp, g, t);
+        TSTAMP(4);
+        bar_sync(BAR_PHASE, NCT);
+        TSTAMP(5);
+        absorb_close<2, 3, 0, 1>(Pbuf, A, m2, warp, g, t, a0, a1);
+        TSTAMP(6);
+        absorb_close<3, 2, 0, 1>(Pbuf, A, m3, warp, g, t, b0, b1);
+        TSTAMP(7);
+      } else {
+        // branch Q = A·M2·M3  ->  out1 (absorb 0, close 1), out0 (absorb 1, close 0)
+        const MsgFrag m0 = load_frag(M, g, t), m1 = load_frag(M + MSG, g, t), m2 = load_frag(M + 2 * MSG, g, t),
+                      m3 = load_frag(M + 3 * MSG, g, t);
+        TSTAMP(3);
+        absorb_pair<2, 3, 0, 1>(A, Pbuf, m2, m3, warp, g, t);
+        TSTAMP(4);
+        bar_sync(BAR_PHASE, NCT);
+        TSTAMP(5);
+        absorb_close<0, 1, 2, 3>(Pbuf, A, m0, warp, g, t, a0, a1);
+        TSTAMP(6);
+        absorb_close<1, 0, 2, 3>(Pbuf, A, m1, warp, g, t, b0, b1);
+        TSTAMP(7);
+      }
+      publish(red, raw, warp, lane, g, t, a0, a1, b0, b1);
+      TSTAMP(8);
     } else if (z == 3) {
       const MsgFrag m0 = load_frag(M, g, t), m1 = load_frag(M + MSG, g, t), m2 = load_frag(M + 2 * MSG, g, t);
       // X = A·M0  ->  out2 (absorb 1, close 2), out1 (absorb 2, close 1)
@@ -342,21 +414,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
       bar_sync(BAR_PHASE, NCT);
       absorb_close<1, 2, 0, -1>(Pbuf, A, m1, warp, g, t, a0, a1);
       absorb_close<2, 1, 0, -1>(Pbuf, A, m2, warp, g, t, b0, b1);
-      publish(red, warp, g, t, a0, a1, b0, b1);
+      publish(red, raw, warp, lane, g, t, a0, a1, b0, b1);
       // X = A·M2  ->  out0 (absorb 1, close 0)
       absorb_one<2, 1, 0, -1>(A, Pbuf, m2, warp, g, t);
       bar_sync(BAR_PHASE, NCT);
       absorb_close<1, 0, 2, -1>(Pbuf, A, m1, warp, g, t, a0, a1);
-      publish(red, warp, g, t, a0, a1, 0.0, 0.0);
+      publish(red, raw, warp, lane, g, t, a0, a1, 0.0, 0.0);
     } else {  // z == 2: out1 (absorb 0, close 1), out0 (absorb 1, close 0) straight from A
       const MsgFrag m0 = load_frag(M, g, t), m1 = load_frag(M + MSG, g, t);
       absorb_close<0, 1, -1, -1>(A, A, m0, warp, g, t, a0, a1);
       absorb_close<1, 0, -1, -1>(A, A, m1, warp, g, t, b0, b1);
-      publish(red, warp, g, t, a0, a1, b0, b1);
+      publish(red, raw, warp, lane, g, t, a0, a1, b0, b1);
     }
+    // every compute warp passed the item's last BAR_RED: nobody reads slot `cur` any more
+    if (item + 2 * G < k.n_items) bar_arrive(BAR_SLOT_FREE + cur, NCT + 32);
   }
-  // let the epilogue warp's last arrive complete
-  bar_sync(BAR_RED_FREE, NTHREADS);
+  // let the epilogue warps' last arrive complete
+  bar_sync(BAR_RAW_FREE, NRAW);
 }
 
 }  // namespace onchip

@@ -25,7 +25,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [
         nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
         "-Xcompiler", "-fPIC", "-shared", "-o", OUT,
-    ] + [os.path.join(HERE, s) for s in SOURCES] + ["-ldl"]
+    ] + os.environ.get("NVCC_EXTRA", "").split() + [os.path.join(HERE, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
