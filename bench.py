@@ -247,16 +247,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def allreduce_residual():
-        if world > 1:
-            partition.allreduce_residual(ctx)
-
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     # ---- value: everything resident, device-timed per step, L2 flushed between steps -------------------
     for _ in range(args.warmup):
         ctx.sweep_async(1)
-        allreduce_residual()
     barrier()
     ctx.counters(reset=True)
     ctx.set_profiling(True)
@@ -270,7 +265,6 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         ctx.sweep_async(1)
-        allreduce_residual()
         e1.record(stream)
         evs.append((e0, e1))
     barrier()
@@ -295,10 +289,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # ---- roofline of the dominant bucket's kernel ----------------------------------------------------
     cplx = 4.0 if p.dtype.kind == "c" else 1.0
     w = p.dtype.itemsize
-    dom, dom_ms, dom_n = max(bucket_times, key=lambda t: t[1])
+    all_buckets = ctx.buckets()
+    dom_idx = max(range(len(bucket_times)), key=lambda i: bucket_times[i][1])
+    dom, dom_ms, dom_n = bucket_times[dom_idx]
     z, chi, d = dom["degree"], dom["chi"], dom["phys"]
-    flops_per_launch = dom["edges"] * 2.0 * z * d * float(chi) ** (z + 1) * cplx
-    bytes_per_launch = dom["vertices"] * d * float(chi) ** z * w + 3.0 * dom["edges"] * chi * chi * w
+    # the dominant LAUNCH covers every bucket merged into it (bpx_bucket_info leader): sum their algorithmic work
+    flops_per_launch = bytes_per_launch = 0.0
+    merged = [b for b in all_buckets if b["leader"] == dom["leader"]]
+    for b in merged:
+        flops_per_launch += b["edges"] * 2.0 * b["degree"] * b["phys"] * float(b["chi"]) ** (b["degree"] + 1) * cplx
+        bytes_per_launch += b["vertices"] * b["phys"] * float(b["chi"]) ** b["degree"] * w + 3.0 * b["edges"] * b["chi"] ** 2 * w
     avg_ms = dom_ms / max(dom_n, 1)
     peaks = {}
     try:
@@ -318,7 +318,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["traffic"] = None
     roof["kernel"] = {1: "bp_update_generic", 2: "bp_update_onchip", 3: "bp_update_sliced"}.get(dom["kernel"], "?")
-    roof["bucket"] = {"degree": z, "chi": chi, "phys": d, "updates_per_launch": dom["edges"]}
+    roof["bucket"] = {"degree": z, "chi": chi, "phys": d, "updates_per_launch": sum(b["edges"] for b in merged),
+                      "degrees_in_launch": sorted(b["degree"] for b in merged)}
     roof["avg_launch_ms"] = avg_ms
     roof["flops_per_launch"] = flops_per_launch
     roof["bytes_per_launch"] = bytes_per_launch
@@ -336,7 +337,6 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         for _ in range(2):
             ctx.set_messages(h_in)
             ctx.sweep_async(1)
-            allreduce_residual()
             ctx.get_messages_flat(h_out)
         barrier()
         ee = []
@@ -345,7 +345,6 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             e0.record(stream)
             ctx.set_messages(h_in)        # H2D of this step's iterate (pinned)
             ctx.sweep_async(1)
-            allreduce_residual()
             ctx.get_messages_flat(h_out)  # D2H of the result
             res_e2e = ctx.last_residual()  # + the scalar the stopping criterion consumes
             e1.record(stream)

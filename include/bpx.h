@@ -161,9 +161,11 @@ int bpx_synchronize(bpx_ctx* ctx);
  * messages; per sweep it updates only its own edges and pushes the messages on cut edges straight into
  * the peers' message sets over NVLink (peer pointers from bpx_halo_export / bpx_halo_connect).       */
 int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32_t* owner);
-/* 64-byte cudaIpcMemHandle_t of each of the two message sets */
-int bpx_halo_export(bpx_ctx* ctx, void* handles_2x64);
-int bpx_halo_connect(bpx_ctx* ctx, int peer_rank, const void* handles_2x64);
+/* three 64-byte cudaIpcMemHandle_t: message set 0, message set 1, residual mailbox.  Exchange them between
+ * the ranks by any host-side means (torch.distributed / MPI) and connect every peer; sweeps then push
+ * cut-edge messages into the peers and exchange the residual through the mailboxes (no NCCL involved). */
+int bpx_halo_export(bpx_ctx* ctx, void* handles_3x64);
+int bpx_halo_connect(bpx_ctx* ctx, int peer_rank, const void* handles_3x64);
 int64_t bpx_num_cut_edges(const bpx_ctx* ctx);
 
 /* ---- shared deterministic RNG (host): splitmix64 counter -> Box-Muller standard normals ----------

@@ -61,6 +61,10 @@ static int upload(bpx_ctx* ctx, T** dptr, const std::vector<T>& h) {
 }
 
 static void free_problem(bpx_ctx* c) {
+  halo_release(c);
+  c->rank = 0;
+  c->nranks = 1;
+  c->owner.clear();
   auto F = [](auto*& p) {
     if (p) cudaFree(p);
     p = nullptr;
@@ -151,11 +155,7 @@ extern "C" int bpx_destroy(bpx_ctx* ctx) {
   if (!ctx) return BPX_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (auto& p : ctx->peers)
-    for (int k = 0; k < 2; ++k)
-      if (p.msg[k]) cudaIpcCloseMemHandle(p.msg[k]);
-  if (ctx->d_peer_msg) cudaFree(ctx->d_peer_msg);
-  if (ctx->d_cut) cudaFree(ctx->d_cut);
+  halo_release(ctx);
   free_problem(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -428,6 +428,7 @@ extern "C" int bpx_set_messages(bpx_ctx* ctx, const void* packed) {
 
 extern "C" int bpx_get_messages(bpx_ctx* ctx, void* packed) {
   NEED_DIMS(ctx, "bpx_get_messages");
+  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, packed || ctx->msg_off[ctx->ne] == 0, "bpx_get_messages: NULL data");
   BPX_CUDA(ctx, cudaMemcpyAsync(packed, ctx->d_msg[ctx->cur], (size_t)ctx->msg_off[ctx->ne] * ctx->esize, cudaMemcpyDeviceToHost,
                                 ctx->stream));
@@ -437,6 +438,7 @@ extern "C" int bpx_get_messages(bpx_ctx* ctx, void* packed) {
 
 extern "C" int bpx_get_message(bpx_ctx* ctx, int64_t e, void* data) {
   NEED_DIMS(ctx, "bpx_get_message");
+  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, e >= 0 && e < ctx->ne && data, "bpx_get_message: bad arguments");
   const size_t off = (size_t)ctx->msg_off[e] * ctx->esize, n = (size_t)(ctx->msg_off[e + 1] - ctx->msg_off[e]) * ctx->esize;
   BPX_CUDA(ctx, cudaMemcpyAsync(data, (char*)ctx->d_msg[ctx->cur] + off, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -491,9 +493,9 @@ int bpx::launch_generic_update(bpx_ctx* ctx, const void* msg_in, void* msg_out, 
   return BPX_OK;
 }
 
-static int launch_residual_max(bpx_ctx* ctx, const int32_t* list, int64_t n, int hist_idx) {
-  bp_residual_max<<<1, 1024, 0, ctx->stream>>>(ctx->d_residual, list, n, ctx->d_resmax,
-                                               hist_idx < ctx->history_cap ? ctx->d_history : nullptr, hist_idx);
+static int launch_residual_max(bpx_ctx* ctx, const int32_t* list, int64_t n, int hist_idx, double* out = nullptr) {
+  bp_residual_max<<<1, 1024, 0, ctx->stream>>>(ctx->d_residual, list, n, out ? out : ctx->d_resmax,
+                                               (hist_idx >= 0 && hist_idx < ctx->history_cap) ? ctx->d_history : nullptr, hist_idx);
   ctx->n_launches++;
   BPX_CUDA(ctx, cudaGetLastError());
   return BPX_OK;
@@ -504,6 +506,7 @@ static int sweep_once(bpx_ctx* ctx, int normalize, int hist_idx) {
   const void* in = ctx->d_msg[ctx->cur];
   void* out = ctx->d_msg[ctx->cur ^ 1];
   int rc;
+  if ((rc = halo_gate(ctx))) return rc;  // partitioned runs: previous sweep's cut messages and residuals have arrived
   if ((rc = fast_refresh_sites(ctx))) return rc;
   for (int bi = 0; bi < (int)ctx->buckets.size(); ++bi) {
     Bucket& b = ctx->buckets[bi];
@@ -523,9 +526,14 @@ static int sweep_once(bpx_ctx* ctx, int normalize, int hist_idx) {
     if (ev1) BPX_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
   }
   if ((rc = halo_push(ctx, out))) return rc;
-  if ((rc = launch_residual_max(ctx, ctx->nranks > 1 ? ctx->d_owned_edges : nullptr,
-                                ctx->nranks > 1 ? ctx->n_owned_edges : ctx->ne, hist_idx)))
-    return rc;
+  if (ctx->nranks == 1) {
+    if ((rc = launch_residual_max(ctx, nullptr, ctx->ne, hist_idx))) return rc;
+  } else {
+    // local max over the owned edges -> mailbox of every rank; the gate folds them before the next sweep
+    if ((rc = launch_residual_max(ctx, ctx->d_owned_edges, ctx->n_owned_edges, -1, ctx->d_resmax + 1))) return rc;
+    if ((rc = halo_post_residual(ctx))) return rc;
+    ctx->gate_hist_idx = hist_idx < ctx->history_cap ? hist_idx : -1;
+  }
   ctx->cur ^= 1;
   ctx->n_updates += ctx->n_owned_edges;
   ctx->n_sweeps++;
@@ -543,17 +551,28 @@ extern "C" int bpx_sweep(bpx_ctx* ctx, int max_sweeps, double tol, int normalize
     if (rc) return rc;
     ++done;
     ctx->history_len = std::min(done, ctx->history_cap);
-    if (tol > 0.0 && ctx->nranks == 1) {
-      // StopWhenConverged: stop after the first sweep whose residual is below tol
+    if (tol > 0.0) {
+      // StopWhenConverged: stop after the first sweep whose (global) residual is below tol
+      if ((rc = halo_gate(ctx))) return rc;
       BPX_CUDA(ctx, cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       if (res < tol) break;
     }
   }
-  if (done > 0 && (residual_out || !(tol > 0.0 && ctx->nranks == 1))) {
-    BPX_CUDA(ctx, cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  {
+    int rc = halo_gate(ctx);
+    if (rc) return rc;
   }
+  if (done > 0) BPX_CUDA(ctx, cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_halo_error) {
+    int flag = 0;
+    BPX_CUDA(ctx, cudaMemcpy(&flag, ctx->d_halo_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+      set_error(ctx, "bpx_sweep: timed out waiting for a peer rank's sweep post");
+      return BPX_ERR_CUDA;
+    }
+  }
   if (residual_out) *residual_out = res;
   if (sweeps_done) *sweeps_done = done;
   return BPX_OK;
@@ -695,6 +714,7 @@ extern "C" int bpx_sweep_sequence(bpx_ctx* ctx, const int64_t* edge_seq, int64_t
 
 extern "C" int bpx_residual_history(bpx_ctx* ctx, double* out, int n, int* n_out) {
   NEED_DIMS(ctx, "bpx_residual_history");
+  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   const int k = std::max(0, std::min(n, ctx->history_len));
   if (k > 0) {
     REQUIRE(ctx, out, "bpx_residual_history: out is NULL");
@@ -707,6 +727,7 @@ extern "C" int bpx_residual_history(bpx_ctx* ctx, double* out, int n, int* n_out
 
 extern "C" int bpx_last_residual(bpx_ctx* ctx, double* out) {
   NEED_DIMS(ctx, "bpx_last_residual");
+  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, out, "bpx_last_residual: out is NULL");
   BPX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -715,6 +736,7 @@ extern "C" int bpx_last_residual(bpx_ctx* ctx, double* out) {
 
 extern "C" int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* out) {
   NEED_DIMS(ctx, "bpx_iterate_diff");
+  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, out && (other_packed || ctx->ne == 0), "bpx_iterate_diff: bad arguments");
   const int64_t ne = ctx->ne;
   if (ne == 0) {
@@ -791,11 +813,13 @@ static int vertex_scalars_impl(bpx_ctx* ctx, const void* ops_packed, void* out) 
 
 extern "C" int bpx_vertex_scalars(bpx_ctx* ctx, void* out) {
   NEED_DIMS(ctx, "bpx_vertex_scalars");
+  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   return vertex_scalars_impl(ctx, nullptr, out);
 }
 
 extern "C" int bpx_vertex_expect_numerators(bpx_ctx* ctx, const void* ops_packed, void* out) {
   NEED_DIMS(ctx, "bpx_vertex_expect_numerators");
+  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, ctx->mode == BPX_MODE_NORM, "bpx_vertex_expect_numerators: NORM mode only");
   REQUIRE(ctx, ops_packed || ctx->nv == 0, "bpx_vertex_expect_numerators: ops is NULL");
   return vertex_scalars_impl(ctx, ops_packed, out);
@@ -803,6 +827,7 @@ extern "C" int bpx_vertex_expect_numerators(bpx_ctx* ctx, const void* ops_packed
 
 extern "C" int bpx_edge_scalars(bpx_ctx* ctx, void* out) {
   NEED_DIMS(ctx, "bpx_edge_scalars");
+  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   const int64_t n = ctx->n_und;
   if (n == 0) return BPX_OK;
   REQUIRE(ctx, out, "bpx_edge_scalars: out is NULL");
@@ -882,6 +907,10 @@ extern "C" void* bpx_device_residual(bpx_ctx* ctx) { return (ctx && ctx->dims_se
 extern "C" int bpx_synchronize(bpx_ctx* ctx) {
   if (!ctx) return BPX_ERR_INVALID;
   BPX_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->dims_set) {
+    int rc_ = halo_gate(ctx);
+    if (rc_) return rc_;
+  }
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return BPX_OK;
 }

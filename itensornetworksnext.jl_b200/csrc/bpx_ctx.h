@@ -26,6 +26,7 @@ struct Bucket {
 struct Peer {
   int rank = -1;
   void* msg[2] = {nullptr, nullptr};  // peer's two message sets (cudaIpcOpenMemHandle)
+  void* mailbox = nullptr;            // peer's mailbox array
 };
 
 }  // namespace bpx
@@ -82,7 +83,12 @@ struct bpx_ctx {
   void** d_peer_msg = nullptr;  // [2][nranks] device table of peer message-set pointers
   int32_t* d_cut = nullptr;     // (edge, peer) pairs of owned edges whose head lives on another rank
   int64_t n_cut = 0;
-  void* nccl_comm = nullptr;
+  void** d_peer_mailbox = nullptr;  // [nranks] device table of mailbox arrays (own entry included)
+  void* d_mailbox = nullptr;        // this rank's mailbox array: one slot per source rank
+  int* d_halo_error = nullptr;
+  unsigned long long sweep_id = 0;  // sweeps posted since bpx_set_partition (identical on all ranks)
+  bool gate_pending = false, halo_connected = false;
+  int gate_hist_idx = -1;
 
   // counters
   int64_t n_launches = 0, n_updates = 0, n_sweeps = 0;
@@ -113,5 +119,8 @@ int fast_refresh_sites(bpx_ctx* ctx);
 int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize);
 // multi-GPU (bpx_halo.cuh)
 int halo_push(bpx_ctx* ctx, void* msg_out);
+int halo_post_residual(bpx_ctx* ctx);
+int halo_gate(bpx_ctx* ctx);
+void halo_release(bpx_ctx* ctx);
 
 }  // namespace bpx

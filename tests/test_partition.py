@@ -1,0 +1,190 @@
+"""Vertex-partitioned BP: host-side plan + a world_size-2 run.
+
+CPU (gloo): the partition plan of itnn_b200.partition drives a 2-process run in which every rank updates
+only its own edges (with the oracle standing in for the kernels), ships the cut-edge messages and
+max-reduces the residual -- the result must equal the single-process sweep.
+GPU (marked `gpu`, needs 2 devices): the same through libbpx with the NVLink peer-memory halo push."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _setup(rank, world, port, backend):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    import __graft_entry__ as entry
+
+    return entry.import_package(), entry.import_oracle()
+
+
+def _problem(pkg, dims=(6, 4), chi=3, dtype=np.float64):
+    from itnn_b200 import graphs, problems
+
+    g = graphs.named_grid(dims)
+    return g, problems.synthetic_peps(g, chi, 2, dtype, seed=7)
+
+
+def _worker_cpu(rank, world, port, nsweeps, q):
+    pkg, o = _setup(rank, world, port, "gloo")
+    from itnn_b200 import partition
+
+    g, p = _problem(pkg)
+    owner = partition.strip_owner(p.ga.vertices, world, axis=0)
+    pl = partition.plan(p.ga.src, p.ga.dst, owner, rank)
+    op = o.make_problem(p.ga, p.tensors, "norm")
+    msgs = [m.copy() for m in p.messages]
+    res_hist = []
+    for _ in range(nsweeps):
+        new = o.sweep_jacobi(op, msgs, edges=pl.owned_edges)  # only this rank's updates
+        local = max(o.edge_residual(msgs[e], new[e]) for e in pl.owned_edges)
+        # halo exchange: cut-edge messages to the rank that owns their head
+        for peer in range(world):
+            if peer == rank:
+                continue
+            out = [torch.from_numpy(np.ascontiguousarray(new[e])) for e in pl.send.get(peer, [])]
+            inc = [torch.empty(p.chi, p.chi, dtype=torch.float64) for _ in pl.recv.get(peer, [])]
+            reqs = [dist.isend(t, peer) for t in out] + [dist.irecv(t, peer) for t in inc]
+            for r in reqs:
+                r.wait()
+            for e, t in zip(pl.recv.get(peer, []), inc):
+                new[e] = t.numpy().copy()
+        t = torch.tensor([local], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res_hist.append(float(t.item()))
+        msgs = new
+    # every rank must hold the correct value of every message it reads: own edges + incoming cut edges
+    need = set(pl.owned_edges) | {e for es in pl.recv.values() for e in es}
+    q.put((rank, {e: msgs[e] for e in need}, res_hist, pl))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_partition_matches_single_process_gloo():
+    world, nsweeps = 2, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_cpu, args=(r, world, port, nsweeps, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+
+    pkg, o = entry.import_package(), entry.import_oracle()
+    g, p = _problem(pkg)
+    op = o.make_problem(p.ga, p.tensors, "norm")
+    want = list(p.messages)
+    hist = []
+    for _ in range(nsweeps):
+        prev, want = want, o.sweep_jacobi(op, want)
+        hist.append(o.iterate_diff(want, prev))
+    covered = set()
+    for rank, msgs, res_hist, pl in results:
+        assert np.allclose(res_hist, hist, rtol=0, atol=1e-14)
+        for e, m in msgs.items():
+            assert np.allclose(m, want[e], rtol=1e-13, atol=0)
+        covered |= set(pl.owned_edges)
+        # plan sanity: what one rank sends is what the other expects
+        for peer, es in pl.send.items():
+            other = next(r for r in results if r[0] == peer)[3]
+            assert other.recv[rank] == es
+    assert covered == set(range(p.ga.ne))
+
+
+def test_plan_counts_strips():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+
+    entry.import_package()
+    from itnn_b200 import graphs, partition
+
+    g = graphs.named_grid((32, 64))
+    ga = graphs.graph_arrays(g)
+    owner = partition.strip_owner(ga.vertices, 2, axis=1)
+    pl0, pl1 = (partition.plan(ga.src, ga.dst, owner, r) for r in range(2))
+    assert len(pl0.owned_vertices) == len(pl1.owned_vertices) == 1024
+    assert len(pl0.send[1]) == len(pl1.send[0]) == 32  # one cut edge per lattice column in each direction
+    assert len(pl0.owned_edges) + len(pl1.owned_edges) == ga.ne
+    assert partition.block_owner(10, 3) == [0, 0, 0, 0, 1, 1, 1, 2, 2, 2]
+
+
+# ---------------------------------------------------------------------------------------------------
+def _worker_gpu(rank, world, port, nsweeps, q):
+    pkg, o = _setup(rank, world, port, "gloo")
+    from itnn_b200 import partition, problems
+
+    torch.cuda.set_device(rank)
+    g, p = _problem(pkg, dims=(8, 12), chi=8)
+    owner = partition.strip_owner(p.ga.vertices, world, axis=1)
+    ctx = pkg.BPXContext(rank)
+    problems.upload(ctx, p)
+    partition.connect(ctx, owner, rank, world)
+    hist = []
+    for _ in range(nsweeps):
+        res, done = ctx.sweep(1, 0.0)
+        hist.append(res)
+    got = ctx.get_messages()
+    res_tol, done_tol = ctx.sweep(50, 1e-3)  # convergence test on the GLOBAL residual
+    pl = partition.plan(p.ga.src, p.ga.dst, owner, rank)
+    need = set(pl.owned_edges) | {e for es in pl.recv.values() for e in es}
+    q.put((rank, {e: got[e] for e in need}, hist, (res_tol, done_tol), ctx.buckets()))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_rank_partition_gpu_peer_halo():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, nsweeps = 2, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_gpu, args=(r, world, port, nsweeps, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+
+    pkg, o = entry.import_package(), entry.import_oracle()
+    g, p = _problem(pkg, dims=(8, 12), chi=8)
+    op = o.make_problem(p.ga, p.tensors, "norm")
+    want = list(p.messages)
+    hist = []
+    for _ in range(nsweeps):
+        prev, want = want, o.sweep_jacobi(op, want)
+        hist.append(o.iterate_diff(want, prev))
+    _, it, delta = o.beliefpropagation(op, want, maxiter=50, tol=1e-3)
+    for rank, msgs, h, (res_tol, done_tol), buckets in results:
+        assert np.allclose(h, hist, rtol=0, atol=1e-12)
+        for e, m in msgs.items():
+            assert np.abs(m - want[e]).max() / np.abs(want[e]).max() < 1e-10
+        assert done_tol == it and abs(res_tol - delta) < 1e-11
