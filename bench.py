@@ -219,7 +219,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # host-side plumbing only (IPC-handle exchange, barriers, max of the timings): gloo.  The data path
+        # (cut-edge messages, residual) goes over NVLink peer memory inside libbpx, not through a collective library.
+        dist.init_process_group("gloo")
 
     p, owner, desc = build_workload(args.workload, world)
     ctx = pkg.BPXContext(local_rank)
@@ -279,7 +281,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         bucket_times.append((info, ms, n))
     ctx.set_profiling(False)
     if world > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([total_ms], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
@@ -353,7 +355,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         barrier()
         e_ms = float(sum(a.elapsed_time(b) for a, b in ee))
         if world > 1:
-            t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
+            t = torch.tensor([e_ms], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
         e2e = {"value": n_total_updates / (e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes),

@@ -1,0 +1,202 @@
+# BPX.jl -- thin `ccall` glue between ITensorNetworksNext.jl and libbpx.so (include/bpx.h).
+#
+# NOT RUNNABLE IN THIS IMAGE (no Julia toolchain, SURVEY.md F9): everything behavioural lives behind the C ABI
+# and is tested from Python through the very same entry points (itensornetworksnext.jl_b200/_lib.py).  This file
+# shows the reference-side binding a maintainer adds; it touches no reference source.
+#
+# Plug-in points used (all in /root/reference):
+#   * `MessageUpdateAlgorithm` strategy interface ........ src/beliefpropagation/beliefpropagation.jl:214-220
+#   * instance pass-through of `select_algorithm` ........ src/select_algorithm.jl:41-48
+#   * nested `AI.step!` (one outer step = one sweep) ..... src/AlgorithmsInterfaceExtensions/AlgorithmsInterfaceExtensions.jl:27-32
+#   * `AIE.iterate_diff` used by `StopWhenConverged` ...... src/beliefpropagation/beliefpropagation.jl:261-267
+module BPX
+
+using ITensorNetworksNext: ITensorNetworksNext, NormNetwork, MessageCache, MessageUpdateAlgorithm,
+    BeliefPropagationProblem, BeliefPropagationAlgorithm, BeliefPropagationSweepAlgorithm,
+    kettensor, braname, linknames, sitenames
+import ITensorNetworksNext: message_update!
+using ITensorNetworksNext.AlgorithmsInterfaceExtensions: AlgorithmsInterfaceExtensions as AIE
+import AlgorithmsInterface as AI
+using Graphs: vertices, src, dst, neighbors
+using NamedGraphs: NamedEdge
+using ITensorBase: ITensor, dimnames, unnamed
+
+const libbpx = get(ENV, "LIBBPX", "libbpx.so")
+const BPX_F64, BPX_C64 = Cint(0), Cint(1)
+const BPX_MODE_NORM = Cint(0)
+
+struct BPXError <: Exception
+    status::Cint
+    msg::String
+end
+function check(ctx::Ptr{Cvoid}, rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:bpx_last_error, libbpx), Cstring, (Ptr{Cvoid},), ctx))
+    return throw(BPXError(rc, msg))
+end
+
+"""
+    B200MessageUpdate(; normalize = true, device = 0)
+
+Message-update strategy that runs whole synchronous BP sweeps on one B200 through libbpx.  Pass it as
+`beliefpropagation(nn, messages; message_update_algorithm = B200MessageUpdate(), stopping_criterion = ...)`.
+The device context is created lazily on the first sweep and kept in the (mutable) strategy object.
+"""
+mutable struct B200MessageUpdate <: MessageUpdateAlgorithm
+    normalize::Bool
+    device::Int
+    ctx::Ptr{Cvoid}
+    edge_ids::Dict{Any, Int}      # NamedEdge -> directed edge id of the C ABI
+    vertex_ids::Dict{Any, Int}
+    bra_ket::Vector{Tuple{Any, Any}}  # per directed edge: (bra name, ket name) of the message axes
+    dirty::Bool                   # host cache newer than the device copy
+    last_residual::Float64
+end
+B200MessageUpdate(; normalize = true, device = 0) =
+    B200MessageUpdate(normalize, device, C_NULL, Dict(), Dict(), Tuple{Any, Any}[], true, Inf)
+
+# ---- lowering to the canonical layout (include/bpx.h; SURVEY.md §8 b2 iv) -------------------------------
+function upload!(alg::B200MessageUpdate, nn::NormNetwork, cache::MessageCache)
+    vs = collect(vertices(nn))
+    alg.vertex_ids = Dict(v => i - 1 for (i, v) in enumerate(vs))
+    srcs, dsts, slots = Int64[], Int64[], Int32[]
+    for v in vs, (k, w) in enumerate(neighbors(nn, v))
+        alg.edge_ids[NamedEdge(v => w)] = length(srcs)
+        push!(srcs, alg.vertex_ids[v]); push!(dsts, alg.vertex_ids[w]); push!(slots, k - 1)
+    end
+    ctxref = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:bpx_create, libbpx), Cint, (Cint, Ref{Ptr{Cvoid}}), alg.device, ctxref)
+    rc == 0 || throw(BPXError(rc, unsafe_string(ccall((:bpx_last_error, libbpx), Cstring, (Ptr{Cvoid},), C_NULL))))
+    ctx = alg.ctx = ctxref[]
+    check(ctx, ccall((:bpx_set_graph, libbpx), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}),
+        ctx, length(vs), length(srcs), srcs, dsts, slots))
+    T = eltype(unnamed(kettensor(nn, first(vs))))
+    dtype = T <: Complex ? BPX_C64 : BPX_F64
+    E = T <: Complex ? ComplexF64 : Float64
+    phys, link = Int32[], Int32[]
+    sites = E[]
+    alg.bra_ket = Tuple{Any, Any}[]
+    for v in vs
+        A = kettensor(nn, v)                                   # normnetwork.jl:77
+        snames = collect(sitenames(nn.ket, v))
+        lnames = [only(linknames(nn.ket, NamedEdge(v => w))) for w in neighbors(nn, v)]
+        arr = Array{E}(unnamed(A, (snames..., lnames...)))      # permute to [sites..., links in neighbour order]
+        push!(phys, prod(size(arr)[1:length(snames)]; init = 1))
+        for (w, ln) in zip(neighbors(nn, v), lnames)
+            push!(link, size(arr, length(snames) + findfirst(==(ln), lnames)))
+            push!(alg.bra_ket, (braname(nn, ln), ln))
+        end
+        append!(sites, vec(arr))
+    end
+    check(ctx, ccall((:bpx_set_dims, libbpx), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int32}),
+        ctx, dtype, BPX_MODE_NORM, phys, link))
+    GC.@preserve sites check(ctx, ccall((:bpx_set_site_tensors, libbpx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx, sites))
+    push_messages!(alg, cache, E)
+    return alg
+end
+
+function push_messages!(alg::B200MessageUpdate, cache::MessageCache, ::Type{E}) where {E}
+    packed = E[]
+    for (e, id) in sort(collect(alg.edge_ids); by = last)
+        bra, ket = alg.bra_ket[id + 1]
+        append!(packed, vec(Array{E}(unnamed(cache[e], (bra, ket)))))   # canonicalise to [bra, ket]
+    end
+    GC.@preserve packed check(alg.ctx, ccall((:bpx_set_messages, libbpx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), alg.ctx, packed))
+    alg.dirty = false
+    return alg
+end
+
+function pull_messages!(alg::B200MessageUpdate, cache::MessageCache)
+    ne = length(alg.edge_ids)
+    total = ccall((:bpx_message_offset, libbpx), Int64, (Ptr{Cvoid}, Int64), alg.ctx, ne)
+    E = eltype(unnamed(first(values(cache.messages))))
+    E = E <: Complex ? ComplexF64 : Float64
+    packed = Vector{E}(undef, total)
+    GC.@preserve packed check(alg.ctx, ccall((:bpx_get_messages, libbpx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), alg.ctx, packed))
+    for (e, id) in alg.edge_ids
+        off = ccall((:bpx_message_offset, libbpx), Int64, (Ptr{Cvoid}, Int64), alg.ctx, id)
+        bra, ket = alg.bra_ket[id + 1]
+        old = cache[e]
+        χ = size(unnamed(old, (bra, ket)), 1)
+        cache[e] = ITensor(reshape(packed[(off + 1):(off + χ * χ)], χ, χ), (bra, ket))  # messagecache.jl:92-96
+    end
+    return cache
+end
+
+# ---- one outer iteration = one synchronous sweep in ONE ccall --------------------------------------------
+# More specific than the NestedAlgorithm method at AIE.jl:27, so dispatch picks it whenever the sweep's
+# strategy is a B200MessageUpdate; `beliefpropagation()` itself is unchanged.
+function AI.step!(
+        problem::BeliefPropagationProblem,
+        algorithm::BeliefPropagationAlgorithm{<:Any, <:BeliefPropagationSweepAlgorithm{<:B200MessageUpdate}},
+        state::AI.State
+    )
+    alg = algorithm.subalgorithm.message_update_algorithm
+    cache = state.iterate
+    alg.ctx == C_NULL && upload!(alg, problem.factors, cache)
+    res, done = Ref{Cdouble}(Inf), Ref{Cint}(0)
+    check(alg.ctx, ccall((:bpx_sweep, libbpx), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cint, Ref{Cdouble}, Ref{Cint}),
+        alg.ctx, 1, 0.0, alg.normalize, res, done))
+    alg.last_residual = res[]
+    # Variant (A) of SURVEY.md §8 b2: plain ITensor messages, downloaded every sweep so that the stock
+    # `StopWhenConverged` (AIE.jl:84-109) keeps working.  Use `B200Converged` below to skip the download.
+    pull_messages!(alg, cache)
+    return state
+end
+
+# Per-edge entry kept for API completeness (`message_update!(alg, cache, factors, edge)`, beliefpropagation.jl:242):
+# a one-edge sequential "sweep" on the device.
+function message_update!(alg::B200MessageUpdate, cache, factors, edge)
+    alg.ctx == C_NULL && upload!(alg, factors, cache)
+    seq = Int64[alg.edge_ids[edge]]
+    check(alg.ctx, ccall((:bpx_sweep_sequence, libbpx), Cint,
+        (Ptr{Cvoid}, Ptr{Int64}, Int64, Cint, Cdouble, Cint, Ptr{Cdouble}, Ptr{Cint}),
+        alg.ctx, seq, 1, 1, 0.0, alg.normalize, C_NULL, C_NULL))
+    return pull_messages!(alg, cache)
+end
+
+"""
+    B200Converged(tol, alg)
+
+Stopping criterion that consumes the residual fused into the sweep kernel's epilogue instead of a second pass
+over two host-side caches (`iterate_diff`, beliefpropagation.jl:261-267).  Explicit criteria are accepted as-is
+by `beliefpropagation` (beliefpropagation.jl:16).
+"""
+struct B200Converged <: AI.StoppingCriterion
+    tol::Float64
+    alg::B200MessageUpdate
+end
+mutable struct B200ConvergedState <: AI.StoppingCriterionState
+    delta::Float64
+    at_iteration::Int
+end
+AI.initialize_state(::AI.Problem, ::AI.Algorithm, ::B200Converged; kwargs...) = B200ConvergedState(Inf, -1)
+AI.initialize_state!(::AI.Problem, ::AI.Algorithm, ::B200Converged, st::B200ConvergedState) = (st.delta = Inf; st)
+function AI.is_finished!(::AI.Problem, ::AI.Algorithm, state::AI.State, c::B200Converged, st::B200ConvergedState)
+    state.iteration == 0 && return false
+    st.delta = c.alg.last_residual
+    st.delta < c.tol || return false
+    st.at_iteration = state.iteration
+    return true
+end
+AI.is_finished(::AI.Problem, ::AI.Algorithm, ::AI.State, c::B200Converged, st::B200ConvergedState) = st.delta < c.tol
+
+# beliefs on the device (messagecache.jl:139-201)
+function vertex_scalars(alg::B200MessageUpdate, ::Type{E} = Float64) where {E}
+    out = Vector{E}(undef, length(alg.vertex_ids))
+    GC.@preserve out check(alg.ctx, ccall((:bpx_vertex_scalars, libbpx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), alg.ctx, out))
+    return out
+end
+function edge_scalars(alg::B200MessageUpdate, ::Type{E} = Float64) where {E}
+    out = Vector{E}(undef, length(alg.edge_ids) ÷ 2)
+    GC.@preserve out check(alg.ctx, ccall((:bpx_edge_scalars, libbpx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), alg.ctx, out))
+    return out
+end
+
+function Base.close(alg::B200MessageUpdate)
+    alg.ctx == C_NULL || ccall((:bpx_destroy, libbpx), Cint, (Ptr{Cvoid},), alg.ctx)
+    alg.ctx = C_NULL
+    return nothing
+end
+
+end # module
