@@ -87,6 +87,7 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_all_edges);
   F(c->d_fast_scratch);
   F(c->d_onchip_items);
+  F(c->d_sliced_items);
   F(c->d_sites_swz);
   for (auto& b : c->buckets) {
     F(b.d_vertices);

@@ -61,6 +61,8 @@ struct bpx_ctx {
   int history_cap = 0, history_len = 0;
   void* d_scratch = nullptr;
   int gen_smem_elems = 0, gen_smem_bytes = 0, gen_grid = 0;
+  void* d_sliced_items = nullptr;
+  int n_sliced_items = 0;
   void* d_timing = nullptr;  // debug: per-phase clock64 stamps (BPX_ONCHIP_TIMING builds)
   void* d_onchip_items = nullptr;
   void* d_sites_swz = nullptr;  // pre-swizzled site tensors for the ONCHIP kernel (bpx_onchip.cuh)

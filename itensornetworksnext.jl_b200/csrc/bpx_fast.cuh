@@ -4,6 +4,7 @@
 
 #include "bpx_ctx.h"
 #include "bpx_onchip.cuh"
+#include "bpx_sliced.cuh"
 
 namespace bpx {
 
@@ -13,11 +14,14 @@ inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
   if (kernel == BPX_KERNEL_ONCHIP)
     return ctx->dtype == BPX_F64 && b.z >= 2 && b.z <= 4 && b.chi == 8 && b.d == 2 &&
            (size_t)ctx->max_smem_optin >= onchip::SMEM_BYTES;
+  if (kernel == BPX_KERNEL_SLICED)
+    return ctx->dtype == BPX_F64 && b.z == 4 && b.chi == 16 && b.d == 2 && (size_t)ctx->max_smem_optin >= sliced::SMEM_BYTES;
   return false;
 }
 
 inline int fast_kernel_for(bpx_ctx* ctx, const Bucket& b) {
   if (fast_kernel_supported(ctx, b, BPX_KERNEL_ONCHIP)) return BPX_KERNEL_ONCHIP;
+  if (fast_kernel_supported(ctx, b, BPX_KERNEL_SLICED)) return BPX_KERNEL_SLICED;
   return BPX_KERNEL_GENERIC;
 }
 
@@ -37,6 +41,64 @@ inline int fast_prepare(bpx_ctx* ctx) {
   for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
     ctx->buckets[i].leader = i;
     if (ctx->buckets[i].kernel == BPX_KERNEL_ONCHIP && !ctx->buckets[i].my_vertices.empty()) group.push_back(i);
+  }
+  if (ctx->d_sliced_items) {
+    cudaFree(ctx->d_sliced_items);
+    ctx->d_sliced_items = nullptr;
+  }
+  if (ctx->d_fast_scratch) {
+    cudaFree(ctx->d_fast_scratch);
+    ctx->d_fast_scratch = nullptr;
+  }
+  ctx->n_sliced_items = 0;
+  bool need_image = false;
+  // ---- SLICED buckets (chi = 16): two half items per vertex ----
+  {
+    std::vector<sliced::ItemDesc> sit;
+    for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
+      Bucket& b = ctx->buckets[i];
+      if (b.kernel != BPX_KERNEL_SLICED) continue;
+      for (int32_t v : b.my_vertices)
+        for (int br = 0; br < 2; ++br) {
+          sliced::ItemDesc d;
+          memset(&d, 0, sizeof(d));
+          d.site_off = ctx->site_off[v];
+          d.branch = br;
+          for (int l = 0; l < 4; ++l) {
+            const int32_t e = ctx->out_edge[v][l];
+            d.out_edge[l] = e;
+            d.out_off[l] = ctx->msg_off[e];
+            d.in_off[l] = ctx->msg_off[ctx->rev[e]];
+          }
+          sit.push_back(d);
+        }
+    }
+    if (!sit.empty()) {
+      ctx->n_sliced_items = (int)sit.size();
+      cudaError_t e = cudaMalloc((void**)&ctx->d_sliced_items, sit.size() * sizeof(sliced::ItemDesc));
+      if (e == cudaSuccess)
+        e = cudaMalloc(&ctx->d_fast_scratch, (size_t)std::min(ctx->n_sliced_items, ctx->num_sms) * sliced::NTENSOR * sizeof(double));
+      if (e != cudaSuccess) {
+        set_error(ctx, "cudaMalloc(sliced kernel items/scratch) failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return BPX_ERR_ALLOC;
+      }
+      BPX_CUDA(ctx, cudaMemcpy(ctx->d_sliced_items, sit.data(), sit.size() * sizeof(sliced::ItemDesc), cudaMemcpyHostToDevice));
+      BPX_CUDA(ctx, cudaFuncSetAttribute(sliced::bp_update_sliced_c16, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sliced::SMEM_BYTES));
+      need_image = true;
+    }
+  }
+  if (!group.empty()) need_image = true;
+  if (need_image) {
+    // private pre-swizzled image of the site tensors (same offsets as the canonical buffer), refreshed lazily
+    cudaError_t e = cudaMalloc(&ctx->d_sites_swz, std::max<size_t>(16, (size_t)ctx->site_off[ctx->nv] * ctx->esize));
+    if (e != cudaSuccess) {
+      set_error(ctx, "cudaMalloc(pre-swizzled site image) failed: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return BPX_ERR_ALLOC;
+    }
+    ctx->sites_dirty = true;
   }
   if (group.empty()) return BPX_OK;
   std::sort(group.begin(), group.end(), [&](int a, int b) { return ctx->buckets[a].z > ctx->buckets[b].z; });
@@ -72,13 +134,6 @@ inline int fast_prepare(bpx_ctx* ctx) {
   BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip_items, items.data(), items.size() * sizeof(onchip::ItemDesc), cudaMemcpyHostToDevice));
   BPX_CUDA(ctx, cudaFuncSetAttribute(onchip::bp_update_onchip_c8, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)onchip::SMEM_BYTES));
-  // private pre-swizzled image of the site tensors (same offsets as the canonical buffer), refreshed lazily
-  e = cudaMalloc(&ctx->d_sites_swz, std::max<size_t>(16, (size_t)ctx->site_off[ctx->nv] * ctx->esize));
-  if (e != cudaSuccess) {
-    set_error(ctx, "cudaMalloc(pre-swizzled site image) failed: %s", cudaGetErrorString(e));
-    return BPX_ERR_ALLOC;
-  }
-  ctx->sites_dirty = true;
   return BPX_OK;
 }
 
@@ -88,6 +143,12 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
   if (ctx->d_sites_swz && ctx->n_onchip_items > 0) {
     onchip::swizzle_sites<<<std::min(ctx->n_onchip_items, 4 * ctx->num_sms), 256, 0, ctx->stream>>>(
         (const onchip::ItemDesc*)ctx->d_onchip_items, ctx->n_onchip_items, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+  }
+  if (ctx->d_sites_swz && ctx->n_sliced_items > 0) {
+    sliced::swizzle_sites16<<<std::min(ctx->n_sliced_items, 8 * ctx->num_sms), 512, 0, ctx->stream>>>(
+        (const sliced::ItemDesc*)ctx->d_sliced_items, ctx->n_sliced_items, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
   }
@@ -109,6 +170,23 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     const int grid = std::min(k.n_items, ctx->num_sms);
     if (grid == 0) return BPX_OK;
     onchip::bp_update_onchip_c8<<<grid, onchip::NTHREADS, onchip::SMEM_BYTES, ctx->stream>>>(k);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+    return BPX_OK;
+  }
+  if (b.kernel == BPX_KERNEL_SLICED) {
+    sliced::Args k;
+    k.items = (const sliced::ItemDesc*)ctx->d_sliced_items;
+    k.n_items = ctx->n_sliced_items;
+    k.sites = (const double*)ctx->d_sites_swz;
+    k.scratch = (double*)ctx->d_fast_scratch;
+    k.msg_in = (const double*)msg_in;
+    k.msg_out = (double*)msg_out;
+    k.residual = ctx->d_residual;
+    k.normalize = normalize;
+    const int grid = std::min(k.n_items, ctx->num_sms);
+    if (grid == 0) return BPX_OK;
+    sliced::bp_update_sliced_c16<<<grid, sliced::NTHREADS, sliced::SMEM_BYTES, ctx->stream>>>(k);
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
     return BPX_OK;
