@@ -168,6 +168,12 @@ int bpx_halo_export(bpx_ctx* ctx, void* handles_3x64);
 int bpx_halo_connect(bpx_ctx* ctx, int peer_rank, const void* handles_3x64);
 int64_t bpx_num_cut_edges(const bpx_ctx* ctx);
 
+/* Fill the RESIDENT site tensors and messages with the synthetic benchmark recipe on the device (site tensor v =
+ * randn(seed, stream v) / sqrt(n_v); message e = (I + 0.1 |randn(seed, stream nv + e)|) sum-normalised): same
+ * counter-based generator as bpx_fill_randn, evaluated with device math (may differ from the host in the last ulp).
+ * For workloads whose inputs the host cannot stage (BASELINE config 5: 63 GiB of site tensors). */
+int bpx_fill_synthetic(bpx_ctx* ctx, uint64_t seed);
+
 /* ---- shared deterministic RNG (host): splitmix64 counter -> Box-Muller standard normals ----------
  * out[i] depends only on (seed, stream, i); complex: (N(0,1) + i N(0,1)) / sqrt(2).                 */
 int bpx_fill_randn(uint64_t seed, uint64_t stream, int dtype, int64_t n, void* out);

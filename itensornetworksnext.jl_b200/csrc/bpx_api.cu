@@ -916,6 +916,39 @@ extern "C" int bpx_synchronize(bpx_ctx* ctx) {
   return BPX_OK;
 }
 
+// ---- device-side synthetic inputs (benchmarks at sizes the host cannot stage) ----------------------------------
+extern "C" int bpx_fill_synthetic(bpx_ctx* ctx, uint64_t seed) {
+  NEED_DIMS(ctx, "bpx_fill_synthetic");
+  REQUIRE(ctx, ctx->mode == BPX_MODE_NORM, "bpx_fill_synthetic: NORM mode only");
+  const int dpe = ctx->esize / 8;
+  if (ctx->nv > 0) {
+    dim3 grid(32, (unsigned)std::min<int64_t>(ctx->nv, 4096));
+    fill_sites_randn<<<grid, 256, 0, ctx->stream>>>(ctx->d_vdesc, ctx->nv, seed, dpe, (double*)ctx->d_sites);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+  }
+  ctx->sites_dirty = true;
+  if (ctx->ne > 0) {
+    int32_t* d_chi = nullptr;
+    int rc = upload(ctx, &d_chi, ctx->link_dim);
+    if (rc) return rc;
+    ctx->cur = 0;
+    const int64_t blocks = (ctx->ne * 32 + 255) / 256;
+    fill_messages_positive<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ctx->d_msg_off, nullptr, ctx->ne, ctx->nv, seed, dpe, d_chi,
+                                                                    (double*)ctx->d_msg[0]);
+    ctx->n_launches++;
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(ctx->d_msg[1], ctx->d_msg[0], (size_t)ctx->msg_off[ctx->ne] * ctx->esize, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_chi);
+    BPX_CUDA(ctx, ce);
+    BPX_CUDA(ctx, ce2);
+  }
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
 // ---- shared RNG -----------------------------------------------------------------------------------
 static inline uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

@@ -286,4 +286,59 @@ __global__ void __launch_bounds__(1024) bp_residual_max(const double* __restrict
   }
 }
 
+// ---- device-side synthetic inputs (same counter-based recipe as the host bpx_fill_randn; libdevice log/cos may
+// differ from libm in the last ulp, so parity tests always use host-generated data) ---------------------------
+__device__ __forceinline__ unsigned long long splitmix64_dev(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ double randn_at_dev(unsigned long long seed, unsigned long long stream, unsigned long long i) {
+  const unsigned long long base = splitmix64_dev(seed ^ splitmix64_dev(stream + 0x632BE59BD9B4E019ull));
+  const unsigned long long a = splitmix64_dev(base + 2 * i), b = splitmix64_dev(base + 2 * i + 1);
+  const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+  const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+
+// site tensor v: randn(seed, stream = v, i) / sqrt(n_v)   (problems.synthetic_peps recipe); one CTA per vertex chunk
+__global__ void fill_sites_randn(const VDesc* __restrict__ vdesc, int64_t nv, unsigned long long seed, int doubles_per_elem,
+                                 double* __restrict__ sites) {
+  for (int64_t v = blockIdx.y; v < nv; v += gridDim.y) {
+    const int64_t n = vdesc[v].n * doubles_per_elem;
+    const double scale = (doubles_per_elem == 2 ? 0.70710678118654752440 : 1.0) / sqrt((double)vdesc[v].n);
+    double* dst = sites + vdesc[v].site_off * doubles_per_elem;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      dst[i] = scale * randn_at_dev(seed, (unsigned long long)v, (unsigned long long)i);
+  }
+}
+
+// message e: (I + 0.1 |randn(seed, stream = nv + e, i)|) / sum   (NORM mode, "positive" init); warp per edge
+__global__ void fill_messages_positive(const int64_t* __restrict__ msg_off, const int32_t* __restrict__ src_unused, int64_t ne,
+                                       int64_t nv, unsigned long long seed, int doubles_per_elem, const int32_t* __restrict__ chi,
+                                       double* __restrict__ msgs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= ne) return;
+  const int c = chi[e];
+  const int64_t n = (int64_t)c * c;
+  double* dst = msgs + msg_off[e] * doubles_per_elem;
+  double s = 0.0;
+  for (int64_t i = lane; i < n; i += 32) {
+    const double v = ((i % c) == (i / c) ? 1.0 : 0.0) + 0.1 * fabs(randn_at_dev(seed, (unsigned long long)(nv + e), (unsigned long long)i));
+    s += v;
+  }
+  s = warp_sum_d(s);
+  for (int64_t i = lane; i < n; i += 32) {
+    const double v = ((i % c) == (i / c) ? 1.0 : 0.0) + 0.1 * fabs(randn_at_dev(seed, (unsigned long long)(nv + e), (unsigned long long)i));
+    if (doubles_per_elem == 1) {
+      dst[i] = v / s;
+    } else {
+      dst[2 * i] = v / s;
+      dst[2 * i + 1] = 0.0;
+    }
+  }
+}
+
 }  // namespace bpx

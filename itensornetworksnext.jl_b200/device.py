@@ -121,6 +121,24 @@ class BPXContext:
     def get_messages(self) -> List[np.ndarray]:
         return self.unpack_messages(self.get_messages_flat())
 
+    def fill_synthetic(self, seed: int = 123):
+        """Generate the synthetic benchmark inputs on the device (no host staging)."""
+        self._check(self.lib.bpx_fill_synthetic(self.h, int(seed)))
+
+    def get_site_tensor(self, v: int) -> np.ndarray:
+        """Debug/test helper: download one canonical site tensor (flat, column-major)."""
+        import ctypes as C_
+
+        n = int(self.site_off[v + 1] - self.site_off[v])
+        out = np.empty(n, dtype=self.dtype)
+        ptr = self.lib.bpx_device_site_tensors(self.h)
+        cudart = C_.CDLL("libcudart.so")
+        rc = cudart.cudaMemcpy(out.ctypes.data_as(C_.c_void_p), C_.c_void_p(ptr + int(self.site_off[v]) * self.dtype.itemsize),
+                               C_.c_size_t(out.nbytes), 2)
+        if rc != 0:
+            raise RuntimeError(f"cudaMemcpy failed ({rc})")
+        return out
+
     # -- hot path ----------------------------------------------------------------------------------
     def sweep(self, max_sweeps: int = 1, tol: float = 0.0, normalize: bool = True):
         res, done = C.c_double(), C.c_int()

@@ -44,14 +44,18 @@ class SyntheticProblem:
     def bytes_per_sweep(self) -> float:
         """Algorithmic bytes: every site tensor once + 3 x every message (in, old, out)."""
         w = self.dtype.itemsize
-        site = sum(t.size for t in self.tensors) * w
+        site = sum(self.d * self.chi ** int(self.ga.row_ptr[v + 1] - self.ga.row_ptr[v]) for v in range(self.ga.nv)) * w
         return site + 3.0 * self.ga.ne * self.chi * self.chi * w
 
 
 def synthetic_peps(g: NamedGraph, chi: int, d: int = 2, dtype=np.float64, seed: int = 123, init: str = "positive",
-                   name: str = "") -> SyntheticProblem:
+                   name: str = "", host_data: bool = True) -> SyntheticProblem:
+    """`host_data = False` builds the structure only (inputs are then generated on the device by
+    `BPXContext.fill_synthetic`, same recipe) -- for workloads the host cannot stage (cfg5: 63 GiB)."""
     dtype = np.dtype(dtype)
     ga = graph_arrays(g)
+    if not host_data:
+        return SyntheticProblem(name, ga, dtype, chi, d, [d] * ga.nv, [chi] * ga.ne, None, None)
     tensors = []
     for v in range(ga.nv):
         z = ga.row_ptr[v + 1] - ga.row_ptr[v]
@@ -85,10 +89,11 @@ CONFIGS = {
 }
 
 
-def make_config(name: str, seed: int = 123, init: str = "positive", graph: Optional[NamedGraph] = None) -> SyntheticProblem:
+def make_config(name: str, seed: int = 123, init: str = "positive", graph: Optional[NamedGraph] = None,
+                host_data: bool = True) -> SyntheticProblem:
     c = CONFIGS[name]
     g = c["graph"]() if graph is None else graph
-    return synthetic_peps(g, c["chi"], c["d"], c["dtype"], seed, init, name)
+    return synthetic_peps(g, c["chi"], c["d"], c["dtype"], seed, init, name, host_data)
 
 
 def upload(ctx, p: SyntheticProblem, kernel: Optional[int] = None):
@@ -97,6 +102,9 @@ def upload(ctx, p: SyntheticProblem, kernel: Optional[int] = None):
     if kernel is not None:
         ctx.set_kernel_policy(kernel)
     ctx.set_dims(p.dtype, "norm", p.phys_dim, p.link_dim)
-    ctx.set_site_tensors(p.tensors)
-    ctx.set_messages(p.messages)
+    if p.tensors is None:
+        ctx.fill_synthetic(123)
+    else:
+        ctx.set_site_tensors(p.tensors)
+        ctx.set_messages(p.messages)
     return ctx

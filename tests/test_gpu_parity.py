@@ -264,3 +264,22 @@ def test_message_update_single_edge_and_iterate_diff(oracle):
     msgs_after = [np.eye(2) for _ in range(cp.ga.ne)]
     msgs_after[cp.ga.edge_id(e)] = want
     assert abs(d - oracle.iterate_diff(msgs_after, [np.eye(2)] * cp.ga.ne)) < 1e-12
+
+
+def test_device_side_synthetic_inputs_match_host_recipe(oracle):
+    # bpx_fill_synthetic must reproduce problems.synthetic_peps (up to the last ulp of device log/cos)
+    g = graphs.named_grid((3, 3))
+    p = problems.make_config("cfg2", graph=g)
+    q = problems.make_config("cfg2", graph=g, host_data=False)
+    with B.BPXContext(0) as ctx:
+        problems.upload(ctx, q)
+        msgs = ctx.get_messages()
+        for e in range(p.ga.ne):
+            assert np.allclose(msgs[e], p.messages[e], rtol=1e-12, atol=1e-15)
+        for v in (0, 4, 8):
+            assert np.allclose(ctx.get_site_tensor(v), p.tensors[v].ravel(order="F"), rtol=1e-11, atol=1e-14)
+        res, done = ctx.sweep(2)
+        got = ctx.get_messages()
+    op = oracle.make_problem(p.ga, p.tensors, "norm")
+    want = oracle.sweep_jacobi(op, oracle.sweep_jacobi(op, p.messages))
+    assert rel_err(got, want) < 1e-9
