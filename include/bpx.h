@@ -110,7 +110,7 @@ int bpx_get_message(bpx_ctx* ctx, int64_t e, void* data);
 int bpx_sweep(bpx_ctx* ctx, int max_sweeps, double tol, int normalize, double* residual_out,
               int* sweeps_done);
 /* Enqueue `n_sweeps` synchronous sweeps on the context's stream and return without waiting (no
- * convergence test).  Pair with bpx_synchronize / bpx_device_residual / bpx_residual_history. */
+ * convergence test).  Pair with bpx_synchronize / bpx_last_residual / bpx_residual_history. */
 int bpx_sweep_async(bpx_ctx* ctx, int n_sweeps, int normalize);
 /* Reference schedule: in-place (Gauss-Seidel) updates along an explicit directed-edge list
  * (beliefpropagation.jl:200-210, 255).  Runs of consecutive, mutually independent updates are batched. */
@@ -153,7 +153,6 @@ int bpx_counters(bpx_ctx* ctx, int64_t out[3], int reset);
 int bpx_set_stream(bpx_ctx* ctx, void* cuda_stream);
 void* bpx_device_messages(bpx_ctx* ctx);     /* current message set, packed, device pointer */
 void* bpx_device_site_tensors(bpx_ctx* ctx); /* packed, device pointer */
-void* bpx_device_residual(bpx_ctx* ctx);     /* one double: residual of the last sweep */
 int bpx_synchronize(bpx_ctx* ctx);
 
 /* ---- multi-GPU: vertex partition, one context per rank ------------------------

@@ -83,7 +83,6 @@ def load() -> C.CDLL:
         "bpx_set_stream": (C.c_int, [vp, vp]),
         "bpx_device_messages": (vp, [vp]),
         "bpx_device_site_tensors": (vp, [vp]),
-        "bpx_device_residual": (vp, [vp]),
         "bpx_synchronize": (C.c_int, [vp]),
         "bpx_set_partition": (C.c_int, [vp, C.c_int, C.c_int, vp]),
         "bpx_halo_export": (C.c_int, [vp, vp]),

@@ -79,8 +79,9 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_msg[1]);
   F(c->d_msg_snapshot);
   F(c->d_residual);
-  F(c->d_resmax);
-  F(c->d_history);
+  F(c->d_reskeys);
+  F(c->d_reskeys_local);
+  F(c->d_generic_edges);
   F(c->d_scratch);
   F(c->d_und_edge);
   F(c->d_owned_edges);
@@ -287,9 +288,12 @@ extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* ph
   }
   ctx->cur = 0;
   if ((rc = dev_alloc(ctx, &ctx->d_residual, (size_t)ne))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_resmax, 2))) return rc;
   ctx->history_cap = 4096;
-  if ((rc = dev_alloc(ctx, &ctx->d_history, (size_t)ctx->history_cap))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_reskeys, (size_t)ctx->history_cap + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_reskeys_local, (size_t)ctx->history_cap + 1))) return rc;
+  BPX_CUDA(ctx, cudaMemset(ctx->d_reskeys, 0, ((size_t)ctx->history_cap + 1) * sizeof(unsigned long long)));
+  BPX_CUDA(ctx, cudaMemset(ctx->d_reskeys_local, 0, ((size_t)ctx->history_cap + 1) * sizeof(unsigned long long)));
+  ctx->history_len = 0;
   std::vector<int32_t> und;
   for (int64_t e = 0; e < ne; ++e)
     if (e < ctx->rev[e]) und.push_back((int32_t)e);
@@ -360,6 +364,15 @@ int bpx::rebuild_work_lists(bpx_ctx* ctx) {
     owned_edges.insert(owned_edges.end(), b.my_edges.begin(), b.my_edges.end());
   }
   std::sort(owned_edges.begin(), owned_edges.end());
+  {
+    std::vector<int32_t> ge;
+    for (auto& b : ctx->buckets)
+      if (b.kernel == BPX_KERNEL_GENERIC) ge.insert(ge.end(), b.my_edges.begin(), b.my_edges.end());
+    F(ctx->d_generic_edges);
+    ctx->n_generic_edges = (int64_t)ge.size();
+    int rcg = upload(ctx, &ctx->d_generic_edges, ge);
+    if (rcg) return rcg;
+  }
   F(ctx->d_owned_edges);
   ctx->n_owned_edges = (int64_t)owned_edges.size();
   int rc = upload(ctx, &ctx->d_owned_edges, owned_edges);
@@ -494,21 +507,78 @@ int bpx::launch_generic_update(bpx_ctx* ctx, const void* msg_in, void* msg_out, 
   return BPX_OK;
 }
 
-static int launch_residual_max(bpx_ctx* ctx, const int32_t* list, int64_t n, int hist_idx, double* out = nullptr) {
-  bp_residual_max<<<1, 1024, 0, ctx->stream>>>(ctx->d_residual, list, n, out ? out : ctx->d_resmax,
-                                               (hist_idx >= 0 && hist_idx < ctx->history_cap) ? ctx->d_history : nullptr, hist_idx);
+// ---- per-sweep residual keys --------------------------------------------------------------------------------
+// Sweep number h (since the ring was last cleared) records into slot h % history_cap; kernels fold their per-edge
+// terms with atomicMax (residual_record), so a sweep needs no reduction kernel unless generic buckets took part.
+static int residual_ring_clear(bpx_ctx* ctx) {
+  const size_t bytes = ((size_t)ctx->history_cap + 1) * sizeof(unsigned long long);
+  BPX_CUDA(ctx, cudaMemsetAsync(ctx->d_reskeys, 0, bytes, ctx->stream));
+  BPX_CUDA(ctx, cudaMemsetAsync(ctx->d_reskeys_local, 0, bytes, ctx->stream));
+  ctx->history_len = 0;
+  return BPX_OK;
+}
+
+static int residual_begin_sweep(bpx_ctx* ctx) {
+  if (ctx->history_len >= ctx->history_cap) {  // ring full: start over (older history is dropped)
+    int rc = halo_gate(ctx);
+    if (rc) return rc;
+    if ((rc = residual_ring_clear(ctx))) return rc;
+  }
+  ctx->cur_slot = (ctx->nranks > 1 ? ctx->d_reskeys_local : ctx->d_reskeys) + ctx->history_len;
+  return BPX_OK;
+}
+
+static int launch_residual_max(bpx_ctx* ctx, const int32_t* list, int64_t n, unsigned long long* slot) {
+  if (n <= 0) return BPX_OK;
+  bp_residual_max<<<1, 1024, 0, ctx->stream>>>(ctx->d_residual, list, n, slot);
   ctx->n_launches++;
   BPX_CUDA(ctx, cudaGetLastError());
   return BPX_OK;
 }
 
+// residual of recorded sweep `idx` (host value; synchronises)
+static int residual_read(bpx_ctx* ctx, int idx, double* out) {
+  unsigned long long key = 0;
+  BPX_CUDA(ctx, cudaMemcpyAsync(&key, ctx->d_reskeys + idx, sizeof(key), cudaMemcpyDeviceToHost, ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = residual_from_key(key);
+  return BPX_OK;
+}
+
 // one synchronous sweep: every owned directed edge, bucket by bucket, from d_msg[cur] into d_msg[cur^1]
-static int sweep_once(bpx_ctx* ctx, int normalize, int hist_idx) {
+static int sweep_once(bpx_ctx* ctx, int normalize) {
   const void* in = ctx->d_msg[ctx->cur];
   void* out = ctx->d_msg[ctx->cur ^ 1];
   int rc;
-  if ((rc = halo_gate(ctx))) return rc;  // partitioned runs: previous sweep's cut messages and residuals have arrived
+  // Partitioned runs.  If this rank's whole sweep is one fast launch, that kernel itself waits for the peers' posts
+  // (producer-warp prologue), stores cut-edge messages into the peers from its epilogue and lets its last CTA post:
+  // no gate / halo / post launches.  Otherwise the exchange runs as separate small kernels.
+  int n_fast = 0, n_generic = 0;
+  for (int bi = 0; bi < (int)ctx->buckets.size(); ++bi) {
+    const Bucket& b = ctx->buckets[bi];
+    if (b.my_edges.empty()) continue;
+    if (b.kernel == BPX_KERNEL_GENERIC) ++n_generic;
+    else if (b.leader == bi) ++n_fast;
+  }
+  const bool fused = ctx->nranks > 1 && ctx->halo_connected && n_fast == 1 && n_generic == 0 && !ctx->sites_dirty;
+  ctx->peer_args = PeerArgs{};
+  if (!fused && (rc = halo_gate(ctx))) return rc;
   if ((rc = fast_refresh_sites(ctx))) return rc;
+  if ((rc = residual_begin_sweep(ctx))) return rc;
+  if (fused) {
+    PeerArgs& pa = ctx->peer_args;
+    pa.nranks = ctx->nranks;
+    pa.rank = ctx->rank;
+    pa.my_mailbox = reinterpret_cast<Mailbox*>(ctx->d_mailbox);
+    pa.peer_mailbox = reinterpret_cast<Mailbox* const*>(ctx->d_peer_mailbox);
+    pa.wait_id = ctx->gate_pending ? ctx->sweep_id : 0;
+    pa.prev_global_key = (ctx->gate_pending && ctx->gate_hist_idx >= 0) ? ctx->d_reskeys + ctx->gate_hist_idx : nullptr;
+    pa.post_id = ++ctx->sweep_id;
+    pa.local_key = ctx->cur_slot;
+    pa.peer_out = reinterpret_cast<double* const*>(ctx->d_peer_msg) + (size_t)(ctx->cur ^ 1) * ctx->nranks;
+    pa.ticket = ctx->d_ticket;
+    pa.error_flag = ctx->d_halo_error;
+  }
   for (int bi = 0; bi < (int)ctx->buckets.size(); ++bi) {
     Bucket& b = ctx->buckets[bi];
     if (b.my_edges.empty() || b.leader != bi) continue;  // merged into its group leader's launch
@@ -526,15 +596,19 @@ static int sweep_once(bpx_ctx* ctx, int normalize, int hist_idx) {
     if (rc) return rc;
     if (ev1) BPX_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
   }
-  if ((rc = halo_push(ctx, out))) return rc;
-  if (ctx->nranks == 1) {
-    if ((rc = launch_residual_max(ctx, nullptr, ctx->ne, hist_idx))) return rc;
-  } else {
-    // local max over the owned edges -> mailbox of every rank; the gate folds them before the next sweep
-    if ((rc = launch_residual_max(ctx, ctx->d_owned_edges, ctx->n_owned_edges, -1, ctx->d_resmax + 1))) return rc;
+  // edges updated by generic kernels left their terms in d_residual: fold them into the sweep's key
+  if ((rc = launch_residual_max(ctx, ctx->d_generic_edges, ctx->n_generic_edges, ctx->cur_slot))) return rc;
+  if (fused) {
+    ctx->gate_pending = true;  // the NEXT launch (or an explicit halo_gate) waits for this sweep's posts
+    ctx->gate_hist_idx = ctx->history_len;
+    ctx->peer_args = PeerArgs{};
+  } else if (ctx->nranks > 1) {
+    if ((rc = halo_push(ctx, out))) return rc;
+    // local key -> mailbox of every rank; the gate folds them (into d_reskeys[slot]) before the next sweep
+    ctx->gate_hist_idx = ctx->history_len;
     if ((rc = halo_post_residual(ctx))) return rc;
-    ctx->gate_hist_idx = hist_idx < ctx->history_cap ? hist_idx : -1;
   }
+  ctx->history_len++;
   ctx->cur ^= 1;
   ctx->n_updates += ctx->n_owned_edges;
   ctx->n_sweeps++;
@@ -544,27 +618,24 @@ static int sweep_once(bpx_ctx* ctx, int normalize, int hist_idx) {
 extern "C" int bpx_sweep(bpx_ctx* ctx, int max_sweeps, double tol, int normalize, double* residual_out, int* sweeps_done) {
   NEED_DIMS(ctx, "bpx_sweep");
   REQUIRE(ctx, max_sweeps >= 0, "bpx_sweep: max_sweeps < 0");
-  int done = 0;
+  int done = 0, rc;
   double res = INFINITY;
-  ctx->history_len = 0;
+  if ((rc = halo_gate(ctx))) return rc;
+  if ((rc = residual_ring_clear(ctx))) return rc;
   for (int it = 0; it < max_sweeps; ++it) {
-    int rc = sweep_once(ctx, normalize, it);
-    if (rc) return rc;
+    if ((rc = sweep_once(ctx, normalize))) return rc;
     ++done;
-    ctx->history_len = std::min(done, ctx->history_cap);
     if (tol > 0.0) {
       // StopWhenConverged: stop after the first sweep whose (global) residual is below tol
       if ((rc = halo_gate(ctx))) return rc;
-      BPX_CUDA(ctx, cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-      BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) return rc;
       if (res < tol) break;
     }
   }
-  {
-    int rc = halo_gate(ctx);
-    if (rc) return rc;
+  if ((rc = halo_gate(ctx))) return rc;
+  if (done > 0 && !(tol > 0.0)) {
+    if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) return rc;
   }
-  if (done > 0) BPX_CUDA(ctx, cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->d_halo_error) {
     int flag = 0;
@@ -583,9 +654,8 @@ extern "C" int bpx_sweep_async(bpx_ctx* ctx, int n_sweeps, int normalize) {
   NEED_DIMS(ctx, "bpx_sweep_async");
   REQUIRE(ctx, n_sweeps >= 0, "bpx_sweep_async: n_sweeps < 0");
   for (int it = 0; it < n_sweeps; ++it) {
-    int rc = sweep_once(ctx, normalize, ctx->history_len < ctx->history_cap ? ctx->history_len : ctx->history_cap);
+    int rc = sweep_once(ctx, normalize);
     if (rc) return rc;
-    if (ctx->history_len < ctx->history_cap) ctx->history_len++;
   }
   return BPX_OK;
 }
@@ -666,9 +736,10 @@ extern "C" int bpx_sweep_sequence(bpx_ctx* ctx, const int64_t* edge_seq, int64_t
   }
   int done = 0;
   double res = INFINITY;
-  ctx->history_len = 0;
+  rc = residual_ring_clear(ctx);
   void* m = ctx->d_msg[ctx->cur];
   for (int it = 0; it < max_sweeps && rc == BPX_OK; ++it) {
+    if (ctx->history_len >= ctx->history_cap && (rc = residual_ring_clear(ctx))) break;
     cudaMemcpyAsync(ctx->d_msg_snapshot, m, msg_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
     for (size_t b = 0; b + 1 < batch_ptr.size() && rc == BPX_OK; ++b) {
       const int64_t n = batch_ptr[b + 1] - batch_ptr[b];
@@ -688,19 +759,18 @@ extern "C" int bpx_sweep_sequence(bpx_ctx* ctx, const int64_t* edge_seq, int64_t
                                                                             ctx->d_msg_off, ne, ctx->d_residual);
       ctx->n_launches++;
     }
-    rc = launch_residual_max(ctx, nullptr, ne, it);
+    rc = launch_residual_max(ctx, nullptr, ne, ctx->d_reskeys + ctx->history_len);
     if (rc) break;
     ++done;
     ctx->n_updates += n_seq;
     ctx->n_sweeps++;
-    ctx->history_len = std::min(done, ctx->history_cap);
+    ctx->history_len++;
     if (tol > 0.0) {
-      cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-      cudaStreamSynchronize(ctx->stream);
+      if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) break;
       if (res < tol) break;
     }
   }
-  if (rc == BPX_OK && done > 0) cudaMemcpyAsync(&res, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (rc == BPX_OK && done > 0 && !(tol > 0.0)) rc = residual_read(ctx, ctx->history_len - 1, &res);
   cudaError_t ce = cudaStreamSynchronize(ctx->stream);
   cudaFree(d_flat);
   if (rc) return rc;
@@ -719,8 +789,10 @@ extern "C" int bpx_residual_history(bpx_ctx* ctx, double* out, int n, int* n_out
   const int k = std::max(0, std::min(n, ctx->history_len));
   if (k > 0) {
     REQUIRE(ctx, out, "bpx_residual_history: out is NULL");
-    BPX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_history, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> keys(k);
+    BPX_CUDA(ctx, cudaMemcpyAsync(keys.data(), ctx->d_reskeys, k * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < k; ++i) out[i] = residual_from_key(keys[i]);
   }
   if (n_out) *n_out = k;
   return BPX_OK;
@@ -730,9 +802,11 @@ extern "C" int bpx_last_residual(bpx_ctx* ctx, double* out) {
   NEED_DIMS(ctx, "bpx_last_residual");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, out, "bpx_last_residual: out is NULL");
-  BPX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return BPX_OK;
+  if (ctx->history_len == 0) {
+    *out = INFINITY;
+    return BPX_OK;
+  }
+  return residual_read(ctx, ctx->history_len - 1, out);
 }
 
 extern "C" int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* out) {
@@ -760,10 +834,9 @@ extern "C" int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* 
                                                                         ctx->d_residual);
   ctx->n_launches++;
   BPX_CUDA(ctx, cudaGetLastError());
-  if ((rc = launch_residual_max(ctx, nullptr, ne, ctx->history_cap))) return rc;
-  BPX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_resmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return BPX_OK;
+  BPX_CUDA(ctx, cudaMemsetAsync(ctx->d_reskeys + ctx->history_cap, 0, sizeof(unsigned long long), ctx->stream));
+  if ((rc = launch_residual_max(ctx, nullptr, ne, ctx->d_reskeys + ctx->history_cap))) return rc;
+  return residual_read(ctx, ctx->history_cap, out);
 }
 
 // ---- beliefs --------------------------------------------------------------------------------------
@@ -903,7 +976,6 @@ extern "C" int bpx_set_stream(bpx_ctx* ctx, void* cuda_stream) {
 
 extern "C" void* bpx_device_messages(bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? ctx->d_msg[ctx->cur] : nullptr; }
 extern "C" void* bpx_device_site_tensors(bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? ctx->d_sites : nullptr; }
-extern "C" void* bpx_device_residual(bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? ctx->d_resmax : nullptr; }
 
 extern "C" int bpx_synchronize(bpx_ctx* ctx) {
   if (!ctx) return BPX_ERR_INVALID;

@@ -1,7 +1,9 @@
 // Shared device/host types for libbpx (B200 / sm_100a).  See include/bpx.h for the ABI.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/bpx.h"
 
@@ -96,12 +98,41 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// ---- per-sweep residual maximum without an extra kernel: order-preserving 64-bit keys + atomicMax ----------
+// key(x) is monotone in x; NaN maps to the largest key (Julia's `maximum` propagates NaN); key 0 = "no value yet".
+__host__ __device__ __forceinline__ unsigned long long residual_key(double x) {
+  if (x != x) return ~0ull;
+  long long b;
+#ifdef __CUDA_ARCH__
+  b = __double_as_longlong(x);
+#else
+  memcpy(&b, &x, sizeof(b));
+#endif
+  return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double residual_from_key(unsigned long long k) {
+  if (k == 0ull) return -INFINITY;  // nothing was recorded (e.g. a graph without edges)
+  if (k == ~0ull) return NAN;
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+  double x;
+#ifdef __CUDA_ARCH__
+  x = __longlong_as_double((long long)b);
+#else
+  memcpy(&x, &b, sizeof(x));
+#endif
+  return x;
+}
+__device__ __forceinline__ void residual_record(unsigned long long* slot, double r) {
+  if (slot) atomicMax(slot, residual_key(r));
+}
+
 // Epilogue shared by every update kernel: sum-normalise (beliefpropagation.jl:248-253), residual term
 // 1 - |<old^, new^>|^2 (beliefpropagation.jl:261-267), store.  Executed by ONE warp; `raw` holds the
 // unnormalised message (nelem entries, any address space), `old_m` / `new_m` the global slots.
 template <typename T>
 __device__ __forceinline__ void warp_epilogue(const T* raw, const T* old_m, T* new_m, int nelem, int normalize,
-                                              double* residual_slot, int lane) {
+                                              double* residual_slot, int lane, unsigned long long* resmax = nullptr,
+                                              T* peer_m = nullptr) {
   using E = Elem<T>;
   T s = E::zero();
   for (int i = lane; i < nelem; i += 32) s = E::add(s, raw[i]);
@@ -117,11 +148,16 @@ __device__ __forceinline__ void warp_epilogue(const T* raw, const T* old_m, T* n
     n_old += E::abs2(o);
     n_new += E::abs2(v);
     new_m[i] = v;
+    if (peer_m) peer_m[i] = v;  // cut edge: also store into the owning rank's message set (NVLink peer memory)
   }
   dot = warp_sum<T>(dot);
   n_old = warp_sum_d(n_old);
   n_new = warp_sum_d(n_new);
-  if (lane == 0 && residual_slot) *residual_slot = 1.0 - E::abs2(dot) / (n_old * n_new);
+  if (lane == 0) {
+    const double r = 1.0 - E::abs2(dot) / (n_old * n_new);
+    if (residual_slot) *residual_slot = r;
+    residual_record(resmax, r);
+  }
 }
 
 }  // namespace bpx

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "bpx_common.cuh"
+#include "bpx_peer.cuh"
 
 namespace bpx {
 
@@ -57,8 +58,13 @@ struct bpx_ctx {
   void* d_msg[2] = {nullptr, nullptr};
   void* d_msg_snapshot = nullptr;
   int cur = 0;
-  double *d_residual = nullptr, *d_resmax = nullptr, *d_history = nullptr;
-  int history_cap = 0, history_len = 0;
+  double* d_residual = nullptr;               // per-edge residual terms of generic-kernel updates
+  unsigned long long* d_reskeys = nullptr;    // ring of per-sweep residual keys (residual_key), [history_cap + 1]
+  unsigned long long* d_reskeys_local = nullptr;  // partitioned runs: this rank's own maxima
+  unsigned long long* cur_slot = nullptr;     // where the kernels of the sweep being enqueued record
+  int history_cap = 0, history_len = 0;       // history_len: sweeps recorded since the ring was last cleared
+  int32_t* d_generic_edges = nullptr;         // owned edges updated by generic buckets (need bp_residual_max)
+  int64_t n_generic_edges = 0;
   void* d_scratch = nullptr;
   int gen_smem_elems = 0, gen_smem_bytes = 0, gen_grid = 0;
   void* d_sliced_items = nullptr;
@@ -91,6 +97,9 @@ struct bpx_ctx {
   unsigned long long sweep_id = 0;  // sweeps posted since bpx_set_partition (identical on all ranks)
   bool gate_pending = false, halo_connected = false;
   int gate_hist_idx = -1;
+  bpx::PeerArgs peer_args = {};     // what the next fast launch is told about the exchange (nranks 0: nothing)
+  unsigned int* d_ticket = nullptr;
+  bool single_launch = false;       // the whole sweep of this rank is ONE fast launch: exchange fused into it
 
   // counters
   int64_t n_launches = 0, n_updates = 0, n_sweeps = 0;

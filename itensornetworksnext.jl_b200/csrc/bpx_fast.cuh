@@ -69,6 +69,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
             d.out_edge[l] = e;
             d.out_off[l] = ctx->msg_off[e];
             d.in_off[l] = ctx->msg_off[ctx->rev[e]];
+            d.peer[l] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
           }
           sit.push_back(d);
         }
@@ -116,7 +117,9 @@ inline int fast_prepare(bpx_ctx* ctx) {
         d.out_edge[i] = e;
         d.out_off[i] = ctx->msg_off[e];
         d.in_off[i] = ctx->msg_off[ctx->rev[e]];
+        d.peer[i] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
       }
+      for (int i = b.z; i < 4; ++i) d.peer[i] = -1;
       if (b.z == 4) {  // two half items (branch P, branch Q): finer granularity for the last wave
         d.branch = 0;
         items.push_back(d);
@@ -165,8 +168,10 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.sites = (const double*)ctx->d_sites_swz;
     k.msg_in = (const double*)msg_in;
     k.msg_out = (double*)msg_out;
-    k.residual = ctx->d_residual;
+    k.residual = nullptr;
+    k.resmax = ctx->cur_slot;
     k.normalize = normalize;
+    k.peer = ctx->peer_args;
     const int grid = std::min(k.n_items, ctx->num_sms);
     if (grid == 0) return BPX_OK;
     onchip::bp_update_onchip_c8<<<grid, onchip::NTHREADS, onchip::SMEM_BYTES, ctx->stream>>>(k);
@@ -182,8 +187,10 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.scratch = (double*)ctx->d_fast_scratch;
     k.msg_in = (const double*)msg_in;
     k.msg_out = (double*)msg_out;
-    k.residual = ctx->d_residual;
+    k.residual = nullptr;
+    k.resmax = ctx->cur_slot;
     k.normalize = normalize;
+    k.peer = ctx->peer_args;
     const int grid = std::min(k.n_items, ctx->num_sms);
     if (grid == 0) return BPX_OK;
     sliced::bp_update_sliced_c16<<<grid, sliced::NTHREADS, sliced::SMEM_BYTES, ctx->stream>>>(k);

@@ -246,11 +246,11 @@ __global__ void bp_edge_residual(const T* __restrict__ m1, const T* __restrict__
   if (lane == 0) residual[e] = 1.0 - E::abs2(dot) / (na * nb);
 }
 
-// max over the per-edge residuals (Julia `maximum`: NaN propagates).  Single CTA, deterministic.
-// Writes out[0] = max and appends to history[hist_idx].
+// max over per-edge residuals (Julia `maximum`: NaN propagates), folded into the sweep's residual key (atomicMax,
+// order independent => deterministic).  Only needed for edges updated by kernels that do not record the key
+// themselves (the generic kernels and bp_edge_residual).
 __global__ void __launch_bounds__(1024) bp_residual_max(const double* __restrict__ residual, const int32_t* __restrict__ list,
-                                                        int64_t n, double* __restrict__ out, double* __restrict__ history,
-                                                        int hist_idx) {
+                                                        int64_t n, unsigned long long* __restrict__ slot) {
   __shared__ double red[32];
   __shared__ int nan_seen[32];
   double m = -INFINITY;
@@ -278,10 +278,9 @@ __global__ void __launch_bounds__(1024) bp_residual_max(const double* __restrict
       m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
       has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, s);
     }
-    if (lane == 0) {
+    if (lane == 0 && n > 0) {
       if (has_nan) m = nan("");
-      out[0] = m;
-      if (history) history[hist_idx] = m;
+      residual_record(slot, m);
     }
   }
 }

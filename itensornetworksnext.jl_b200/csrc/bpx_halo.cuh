@@ -16,13 +16,9 @@
 #include <cstring>
 
 #include "bpx_ctx.h"
+#include "bpx_peer.cuh"
 
 namespace bpx {
-
-struct Mailbox {  // one per source rank, lives in the RECEIVER's memory
-  unsigned long long sweep_id;
-  double residual;
-};
 
 // warp per cut edge: local out-message -> peer's out buffer (same offset)
 __global__ void halo_push_kernel(const int32_t* __restrict__ cut /* (edge, peer) pairs */, int64_t n_cut,
@@ -38,7 +34,7 @@ __global__ void halo_push_kernel(const int32_t* __restrict__ cut /* (edge, peer)
   for (int64_t i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
-__global__ void residual_post_kernel(const double* __restrict__ local_max, Mailbox* const* peer_mailbox, int rank, int nranks,
+__global__ void residual_post_kernel(const unsigned long long* __restrict__ local_key, Mailbox* const* peer_mailbox, int rank, int nranks,
                                      unsigned long long sweep_id) {
   const int p = threadIdx.x;
   if (p >= nranks) return;
@@ -46,15 +42,15 @@ __global__ void residual_post_kernel(const double* __restrict__ local_max, Mailb
   // system-wide before the flag
   __threadfence_system();
   Mailbox* mb = peer_mailbox[p] + rank;
-  mb->residual = *local_max;
+  mb->residual = residual_from_key(*local_key);
   __threadfence_system();
   *reinterpret_cast<volatile unsigned long long*>(&mb->sweep_id) = sweep_id;
 }
 
 // One thread per source rank waits for that rank's post of `sweep_id`; then the maxima are folded.
 // The spin is bounded (~4 s of SM clock): on time-out the error flag is raised instead of hanging the GPU.
-__global__ void residual_gate_kernel(Mailbox* my_mailbox, int nranks, unsigned long long sweep_id, double* resmax, double* history,
-                                     int hist_idx, int* error_flag) {
+__global__ void residual_gate_kernel(Mailbox* my_mailbox, int nranks, unsigned long long sweep_id, unsigned long long* global_key,
+                                     int* error_flag) {
   __shared__ double vals[64];
   const int p = threadIdx.x;
   double v = -INFINITY;
@@ -85,8 +81,7 @@ __global__ void residual_gate_kernel(Mailbox* my_mailbox, int nranks, unsigned l
       m = fmax(m, vals[i]);
     }
     if (has_nan) m = nan("");
-    resmax[0] = m;
-    if (history) history[hist_idx] = m;
+    if (global_key) *global_key = residual_key(m);
   }
 }
 
@@ -110,11 +105,10 @@ inline int halo_push(bpx_ctx* ctx, void* msg_out) {
 inline int halo_post_residual(bpx_ctx* ctx) {
   if (ctx->nranks <= 1) return BPX_OK;
   ctx->sweep_id++;
-  residual_post_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_resmax + 1, reinterpret_cast<Mailbox* const*>(ctx->d_peer_mailbox), ctx->rank,
-                                                 ctx->nranks, ctx->sweep_id);
+  residual_post_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_reskeys_local + ctx->gate_hist_idx, reinterpret_cast<Mailbox* const*>(ctx->d_peer_mailbox),
+                                                 ctx->rank, ctx->nranks, ctx->sweep_id);
   ctx->n_launches++;
   ctx->gate_pending = true;
-  ctx->gate_hist_idx = -1;
   BPX_CUDA(ctx, cudaGetLastError());
   return BPX_OK;
 }
@@ -122,8 +116,8 @@ inline int halo_post_residual(bpx_ctx* ctx) {
 // wait for every rank's post of the last sweep; d_resmax[0] (and the history slot) receive the global max
 inline int halo_gate(bpx_ctx* ctx) {
   if (ctx->nranks <= 1 || !ctx->gate_pending) return BPX_OK;
-  residual_gate_kernel<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<Mailbox*>(ctx->d_mailbox), ctx->nranks, ctx->sweep_id, ctx->d_resmax,
-                                                 ctx->gate_hist_idx >= 0 ? ctx->d_history : nullptr, ctx->gate_hist_idx, ctx->d_halo_error);
+  residual_gate_kernel<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<Mailbox*>(ctx->d_mailbox), ctx->nranks, ctx->sweep_id,
+                                                 ctx->gate_hist_idx >= 0 ? ctx->d_reskeys + ctx->gate_hist_idx : nullptr, ctx->d_halo_error);
   ctx->n_launches++;
   ctx->gate_pending = false;
   BPX_CUDA(ctx, cudaGetLastError());
@@ -146,6 +140,8 @@ inline void halo_release(bpx_ctx* ctx) {
   F(ctx->d_cut);
   F(ctx->d_mailbox);
   F(ctx->d_halo_error);
+  F(ctx->d_ticket);
+  ctx->peer_args = bpx::PeerArgs{};
   ctx->n_cut = 0;
   ctx->halo_connected = false;
   ctx->gate_pending = false;
@@ -195,6 +191,8 @@ extern "C" int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32
     BPX_CUDA(ctx, cudaMemset(ctx->d_mailbox, 0, 64 * sizeof(bpx::Mailbox)));
     BPX_CUDA(ctx, cudaMalloc((void**)&ctx->d_halo_error, sizeof(int)));
     BPX_CUDA(ctx, cudaMemset(ctx->d_halo_error, 0, sizeof(int)));
+    BPX_CUDA(ctx, cudaMalloc((void**)&ctx->d_ticket, sizeof(unsigned int)));
+    BPX_CUDA(ctx, cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
     ctx->sweep_id = 0;
   }
   return bpx::rebuild_work_lists(ctx);

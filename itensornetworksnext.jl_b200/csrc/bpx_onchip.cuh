@@ -30,6 +30,7 @@
 // compute warps never wait for the division / global-memory latency of the epilogue.
 #pragma once
 #include "bpx_common.cuh"
+#include "bpx_peer.cuh"
 
 namespace bpx {
 namespace onchip {
@@ -57,6 +58,7 @@ struct ItemDesc {
   int32_t z;
   int32_t branch;  // degree 4 only: 0 = branch P (out3, out2), 1 = branch Q (out1, out0); each is its own work item
   int32_t pad[2];
+  int32_t peer[4];  // rank that owns the head of out-edge i when it lives on another rank (cut edge), else -1
 };
 
 // ---- swizzled position (in doubles, s = 0) of element (a0,a1,a2,a3); XOR-linear in every index bit ----
@@ -223,8 +225,10 @@ struct Args {
   const double* sites;  // PRE-SWIZZLED image (same offsets as the canonical buffer)
   const double* msg_in;
   double* msg_out;
-  double* residual;
+  double* residual;              // per-edge residual terms (may be NULL)
+  unsigned long long* resmax;    // this sweep's residual key (atomicMax)
   int normalize;
+  PeerArgs peer;                 // multi-GPU: gate / direct peer stores / post (nranks <= 1: unused)
 };
 
 // shared memory (doubles): A[2][NELEM] | P[NELEM] | red[2][NCW][MSG] | raw[2][MSG] | msgs[2][4][MSG] | 2 mbarriers
@@ -273,7 +277,7 @@ __device__ __forceinline__ void publish(double* red, double* raw, int warp, int 
 // Lane holds elements lane and lane + 32.  The residual 1 - |<old^, new^>|^2 is invariant under the scaling,
 // so all four reductions run interleaved on the raw tile.
 __device__ __forceinline__ void epilogue_tile(double v0, double v1, double o0, double o1, int lane, double* new_m, int normalize,
-                                              double* residual_slot) {
+                                              double* residual_slot, unsigned long long* resmax, double* peer_m) {
   double s = v0 + v1, dot = o0 * v0 + o1 * v1, n_old = o0 * o0 + o1 * o1, n_new = v0 * v0 + v1 * v1;
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) {
@@ -288,7 +292,15 @@ __device__ __forceinline__ void epilogue_tile(double v0, double v1, double o0, d
   }
   new_m[lane] = v0;
   new_m[lane + 32] = v1;
-  if (lane == 0 && residual_slot) *residual_slot = 1.0 - dot * dot / (n_old * n_new);
+  if (peer_m) {  // cut edge: the owner of the head reads this message next sweep -- store it there too (NVLink)
+    peer_m[lane] = v0;
+    peer_m[lane + 32] = v1;
+  }
+  if (lane == 0) {
+    const double r = 1.0 - dot * dot / (n_old * n_new);
+    if (residual_slot) *residual_slot = r;
+    residual_record(resmax, r);
+  }
 }
 
 // Build the pre-swizzled image: dst[site_off + pos(c)] = src[site_off + 2c .. 2c+1] for every 16-byte chunk c.
@@ -324,15 +336,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
 
   if (warp == NCW + NEW) {
     // ================= producer warp: TMA of item n into slot n & 1, two items ahead of the compute warps ==========
+    peer_gate(k.peer, lane);  // multi-GPU: the peers' cut-edge messages of the previous sweep have landed
     int n = 0;
     for (int item = blockIdx.x; item < k.n_items; item += G, ++n) {
       if (n >= 2) bar_sync(BAR_SLOT_FREE + (n & 1), NCT + 32);  // compute warps are done with the slot's previous tenant
       if (lane == 0) tma_item(smem + (n & 1) * NELEM, msgs + (n & 1) * 4 * MSG, &mbar[n & 1], k, k.items + item);
     }
-    return;
-  }
+  } else if (warp >= NCW) {
 
-  if (warp >= NCW) {
     // ================= epilogue warps: warp NCW + i owns tile i of every branch =================
     const int which = warp - NCW;
     bar_arrive(BAR_RAW_FREE, NRAW);  // raw starts free
@@ -350,21 +361,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
         double o0 = 0, o1 = 0;
         int64_t off = 0;
         int e = 0;
+        double* peer_m = nullptr;
         if (l >= 0) {  // old message: issued before the hand-over so its latency overlaps the compute
           off = d->out_off[l];
           e = d->out_edge[l];
+          if (k.peer.nranks > 1 && d->peer[l] >= 0) peer_m = k.peer.peer_out[d->peer[l]] + off;
           o0 = k.msg_in[off + lane];
           o1 = k.msg_in[off + lane + 32];
         }
         bar_sync(BAR_RAW_FULL, NRAW);
         const double v0 = raw[which * MSG + lane], v1 = raw[which * MSG + lane + 32];
         bar_arrive(BAR_RAW_FREE, NRAW);  // values are in registers: raw may be overwritten
-        if (l >= 0) epilogue_tile(v0, v1, o0, o1, lane, k.msg_out + off, k.normalize, k.residual ? k.residual + e : nullptr);
+        if (l >= 0) epilogue_tile(v0, v1, o0, o1, lane, k.msg_out + off, k.normalize, k.residual ? k.residual + e : nullptr, k.resmax, peer_m);
       }
     }
-    return;
-  }
-
+  } else {
   // ================= compute warps =================
   int n_iter = 0;
   for (int item = blockIdx.x; item < k.n_items; item += G, ++n_iter) {
@@ -431,6 +442,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
   }
   // let the epilogue warps' last arrive complete
   bar_sync(BAR_RAW_FREE, NRAW);
+  }
+  // multi-GPU: every role of this CTA is done; the last CTA posts (sweep id, local residual) to all ranks
+  peer_post_when_last(k.peer);
 }
 
 }  // namespace onchip

@@ -1,0 +1,87 @@
+// Device-side pieces that let ONE persistent update kernel per sweep also do the multi-GPU exchange
+// (bpx_halo.cuh describes the protocol): wait for the peers' posts of the previous sweep before the first
+// cut-edge message is read, store new cut-edge messages straight into the owner's message set over NVLink from the
+// epilogue, and let the last CTA to finish post (sweep id, local residual) into every peer's mailbox.
+#pragma once
+#include "bpx_common.cuh"
+
+namespace bpx {
+
+struct Mailbox {  // one per source rank, lives in the RECEIVER's memory
+  unsigned long long sweep_id;
+  double residual;
+};
+
+struct PeerArgs {
+  int nranks;                              // <= 1: everything below is ignored
+  int rank;
+  Mailbox* my_mailbox;                     // [nranks]
+  Mailbox* const* peer_mailbox;            // [nranks] (own entry included)
+  unsigned long long wait_id;              // posts of this sweep id must have arrived before cut messages are read (0: none)
+  unsigned long long post_id;              // id to post when this kernel's updates are complete (0: do not post)
+  unsigned long long* prev_global_key;     // where CTA 0 folds the previous sweep's global residual (may be NULL)
+  const unsigned long long* local_key;     // this sweep's local residual key (the kernels' resmax slot)
+  double* const* peer_out;                 // [nranks] message set being written this sweep, per rank
+  unsigned int* ticket;                    // CTA completion counter (self-resetting)
+  int* error_flag;
+};
+
+// Called by ONE warp per CTA before it touches messages written by peers.  Lane p waits for rank p's post.
+__device__ __forceinline__ void peer_gate(const PeerArgs& pa, int lane) {
+  if (pa.nranks <= 1 || pa.wait_id == 0) return;
+  double v = -INFINITY;
+  for (int p = lane; p < pa.nranks; p += 32) {
+    volatile unsigned long long* flag = &pa.my_mailbox[p].sweep_id;
+    const long long t0 = clock64();
+    bool ok = true;
+    while (*flag < pa.wait_id) {
+      if (clock64() - t0 > 8000000000ll) {  // ~4 s: raise the error flag instead of hanging the GPU
+        ok = false;
+        break;
+      }
+      __nanosleep(100);
+    }
+    if (ok) {
+      const double r = *reinterpret_cast<volatile double*>(&pa.my_mailbox[p].residual);
+      v = (r != r || v != v) ? NAN : fmax(v, r);
+    } else {
+      atomicExch(pa.error_flag, 1);
+    }
+  }
+  __threadfence_system();  // acquire: the peers' message stores precede their flag
+  if (blockIdx.x == 0 && pa.prev_global_key) {
+    bool has_nan = v != v;
+    has_nan = __any_sync(0xffffffffu, has_nan);
+    double m = has_nan ? -INFINITY : v;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if (lane == 0) *pa.prev_global_key = residual_key(has_nan ? NAN : m);
+  }
+  __syncwarp();
+}
+
+// Called by every thread of every CTA when all of the CTA's global/peer stores have been issued (CTA-uniform).
+// The last CTA to arrive posts (post_id, local residual) to every rank.
+__device__ __forceinline__ void peer_post_when_last(const PeerArgs& pa) {
+  if (pa.nranks <= 1 || pa.post_id == 0) return;
+  __shared__ unsigned int s_last;
+  __threadfence_system();  // release this thread's message / residual-key stores
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(pa.ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x < pa.nranks) {
+      __threadfence_system();
+      Mailbox* mb = pa.peer_mailbox[threadIdx.x] + pa.rank;
+      mb->residual = residual_from_key(*reinterpret_cast<const volatile unsigned long long*>(pa.local_key));
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(&mb->sweep_id) = pa.post_id;
+    }
+    if (threadIdx.x == 0) *pa.ticket = 0u;  // ready for the next launch (stream-ordered)
+  }
+}
+
+}  // namespace bpx

@@ -19,6 +19,7 @@
 #pragma once
 #include "bpx_common.cuh"
 #include "bpx_onchip.cuh"
+#include "bpx_peer.cuh"
 
 namespace bpx {
 namespace sliced {
@@ -101,6 +102,7 @@ struct ItemDesc {
   int32_t out_edge[4];
   int32_t branch;      // 0: P (out3, out2), 1: Q (out1, out0)
   int32_t pad[3];
+  int32_t peer[4];     // rank owning the head of out-edge i if it lives elsewhere (cut edge), else -1
 };
 
 struct Args {
@@ -111,7 +113,9 @@ struct Args {
   const double* msg_in;
   double* msg_out;
   double* residual;
+  unsigned long long* resmax;  // this sweep's residual key (atomicMax)
   int normalize;
+  PeerArgs peer;               // multi-GPU: gate / direct peer stores / post (nranks <= 1: unused)
 };
 
 // message fragments for 16-wide legs
@@ -277,6 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_sliced_c16(Args k) {
 
   if (warp == NCW) {
     // ================================ producer warp ================================
+    peer_gate(k.peer, lane);  // multi-GPU: the peers' cut-edge messages of the previous sweep have landed
     int it = 0;
     for (int item = blockIdx.x; item < k.n_items; item += G, ++it) {
       const ItemDesc* d = k.items + item;
@@ -340,10 +345,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_sliced_c16(Args k) {
       // drain the two outstanding "empty" signals so that the counters stay aligned with the next item
       for (int st = 0; st < 2; ++st) mbar_wait(&mbar[MB_EMPTY2 + st], 1);  // 16th use of the item
     }
-    return;
-  }
-
+  } else {
   // ================================ compute warps ================================
+  // (they read peer-written messages too -- the fragments below -- so they wait for the gate as well)
+  if (k.peer.nranks > 1 && warp == 0) peer_gate(PeerArgs{k.peer.nranks, k.peer.rank, k.peer.my_mailbox, k.peer.peer_mailbox, k.peer.wait_id, 0,
+                                                        nullptr, nullptr, nullptr, nullptr, k.peer.error_flag}, lane);
+  if (k.peer.nranks > 1) onchip::bar_sync(BAR_COMPUTE, NCT);
   int it = 0;
   for (int item = blockIdx.x; item < k.n_items; item += G, ++it) {
     const ItemDesc* d = k.items + item;
@@ -422,11 +429,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_sliced_c16(Args k) {
     if (warp < 2) {
       const int leg = warp == 0 ? lv : lu;
       const int64_t off = d->out_off[leg];
+      double* peer_m = (k.peer.nranks > 1 && d->peer[leg] >= 0) ? k.peer.peer_out[d->peer[leg]] + off : nullptr;
       warp_epilogue<double>(raw + warp * MSG, k.msg_in + off, k.msg_out + off, MSG, k.normalize,
-                            k.residual ? k.residual + d->out_edge[leg] : nullptr, lane);
+                            k.residual ? k.residual + d->out_edge[leg] : nullptr, lane, k.resmax, peer_m);
     }
     onchip::bar_sync(BAR_COMPUTE, NCT);  // raw / red are re-used by the next item
   }
+  }
+  peer_post_when_last(k.peer);
 }
 
 }  // namespace sliced
