@@ -112,6 +112,10 @@ int bpx_sweep(bpx_ctx* ctx, int max_sweeps, double tol, int normalize, double* r
 /* Enqueue `n_sweeps` synchronous sweeps on the context's stream and return without waiting (no
  * convergence test).  Pair with bpx_synchronize / bpx_last_residual / bpx_residual_history. */
 int bpx_sweep_async(bpx_ctx* ctx, int n_sweeps, int normalize);
+/* One step with HOST buffers: upload the iterate (packed_in), one synchronous sweep, download the new iterate
+ * (packed_out) and the fused residual; a single host synchronisation.  What the per-sweep Julia hook
+ * (AI.step! specialisation + StopWhenConverged) calls when the messages live on the host. */
+int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_out, int normalize, double* residual_out);
 /* Reference schedule: in-place (Gauss-Seidel) updates along an explicit directed-edge list
  * (beliefpropagation.jl:200-210, 255).  Runs of consecutive, mutually independent updates are batched. */
 int bpx_sweep_sequence(bpx_ctx* ctx, const int64_t* edge_seq, int64_t n_seq, int max_sweeps, double tol,

@@ -66,6 +66,7 @@ def load() -> C.CDLL:
         "bpx_get_messages": (C.c_int, [vp, vp]),
         "bpx_get_message": (C.c_int, [vp, i64, vp]),
         "bpx_sweep": (C.c_int, [vp, C.c_int, dbl, C.c_int, P(dbl), P(C.c_int)]),
+        "bpx_sweep_host": (C.c_int, [vp, vp, vp, C.c_int, P(dbl)]),
         "bpx_sweep_async": (C.c_int, [vp, C.c_int, C.c_int]),
         "bpx_set_profiling": (C.c_int, [vp, C.c_int]),
         "bpx_bucket_time": (C.c_int, [vp, C.c_int, P(dbl), P(i64)]),

@@ -407,6 +407,9 @@ extern "C" int64_t bpx_message_offset(const bpx_ctx* ctx, int64_t e) {
     BPX_CUDA(ctx, cudaSetDevice(ctx->device));                   \
   } while (0)
 
+static int sweep_once(bpx_ctx* ctx, int normalize);
+static int residual_read(bpx_ctx* ctx, int idx, double* out);
+
 extern "C" int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed) {
   NEED_DIMS(ctx, "bpx_set_site_tensors");
   REQUIRE(ctx, packed || ctx->site_off[ctx->nv] == 0, "bpx_set_site_tensors: NULL data");
@@ -434,9 +437,29 @@ extern "C" int bpx_set_messages(bpx_ctx* ctx, const void* packed) {
   const size_t n = (size_t)ctx->msg_off[ctx->ne] * ctx->esize;
   ctx->cur = 0;  // all ranks of a partitioned run restart on the same parity
   BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[ctx->cur], packed, n, cudaMemcpyHostToDevice, ctx->stream));
-  // both sets hold every message, so that edges a rank does not own keep their value across ping-pong
-  BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[ctx->cur ^ 1], ctx->d_msg[ctx->cur], n, cudaMemcpyDeviceToDevice, ctx->stream));
+  // partitioned runs: both sets must hold every message, so that edges a rank does not own keep their value across
+  // ping-pong (a single rank rewrites every message each sweep, and the sequential path re-syncs the sets itself)
+  if (ctx->nranks > 1)
+    BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[ctx->cur ^ 1], ctx->d_msg[ctx->cur], n, cudaMemcpyDeviceToDevice, ctx->stream));
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
+// One reference-facing step with HOST buffers: upload the iterate, one synchronous sweep, download the new iterate
+// and the fused residual -- the per-sweep call of the Julia plugin (AI.step! + StopWhenConverged), one host sync.
+extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_out, int normalize, double* residual_out) {
+  NEED_DIMS(ctx, "bpx_sweep_host");
+  REQUIRE(ctx, ctx->nranks == 1, "bpx_sweep_host: single-rank contexts only");
+  REQUIRE(ctx, (packed_in && packed_out) || ctx->msg_off[ctx->ne] == 0, "bpx_sweep_host: NULL buffer");
+  const size_t n = (size_t)ctx->msg_off[ctx->ne] * ctx->esize;
+  ctx->cur = 0;
+  BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[0], packed_in, n, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = sweep_once(ctx, normalize);
+  if (rc) return rc;
+  BPX_CUDA(ctx, cudaMemcpyAsync(packed_out, ctx->d_msg[ctx->cur], n, cudaMemcpyDeviceToHost, ctx->stream));
+  double res = INFINITY;
+  if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) return rc;  // synchronises the stream
+  if (residual_out) *residual_out = res;
   return BPX_OK;
 }
 

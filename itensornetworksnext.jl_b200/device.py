@@ -145,6 +145,12 @@ class BPXContext:
         self._check(self.lib.bpx_sweep(self.h, int(max_sweeps), float(tol), int(bool(normalize)), C.byref(res), C.byref(done)))
         return res.value, done.value
 
+    def sweep_host(self, flat_in: np.ndarray, flat_out: np.ndarray, normalize: bool = True) -> float:
+        """Upload messages, one synchronous sweep, download messages + residual (one host sync)."""
+        res = C.c_double()
+        self._check(self.lib.bpx_sweep_host(self.h, _ptr(flat_in), _ptr(flat_out), int(bool(normalize)), C.byref(res)))
+        return res.value
+
     def sweep_async(self, n_sweeps: int = 1, normalize: bool = True):
         self._check(self.lib.bpx_sweep_async(self.h, int(n_sweeps), int(bool(normalize))))
 
