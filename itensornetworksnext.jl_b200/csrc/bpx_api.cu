@@ -89,6 +89,7 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_fast_scratch);
   F(c->d_onchip_items);
   F(c->d_sliced_items);
+  F(c->d_onchip16_items);
   F(c->d_sites_swz);
   for (auto& b : c->buckets) {
     F(b.d_vertices);
@@ -368,6 +369,7 @@ int bpx::rebuild_work_lists(bpx_ctx* ctx) {
     std::vector<int32_t> ge;
     for (auto& b : ctx->buckets)
       if (b.kernel == BPX_KERNEL_GENERIC) ge.insert(ge.end(), b.my_edges.begin(), b.my_edges.end());
+    std::sort(ge.begin(), ge.end());
     F(ctx->d_generic_edges);
     ctx->n_generic_edges = (int64_t)ge.size();
     int rcg = upload(ctx, &ctx->d_generic_edges, ge);
@@ -513,9 +515,10 @@ static int set_smem(bpx_ctx* ctx, K kernel, int bytes) {
 }
 
 int bpx::launch_generic_update(bpx_ctx* ctx, const void* msg_in, void* msg_out, const int32_t* d_work, int64_t n_work,
-                               int normalize) {
+                               int normalize, unsigned long long* resmax) {
   if (n_work == 0) return BPX_OK;
   GenericArgs g = generic_args(ctx, msg_in, msg_out, d_work, n_work, normalize);
+  g.resmax = resmax;
   const int grid = (int)std::min<int64_t>(n_work, ctx->gen_grid);
   int rc;
   if (ctx->dtype == BPX_F64) {
@@ -612,15 +615,13 @@ static int sweep_once(bpx_ctx* ctx, int normalize) {
       b.timing.emplace_back(ev0, ev1);
       BPX_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
     }
-    if (b.kernel == BPX_KERNEL_GENERIC)
-      rc = launch_generic_update(ctx, in, out, b.d_edges, (int64_t)b.my_edges.size(), normalize);
+    if (b.kernel == BPX_KERNEL_GENERIC)  // ONE launch for all generic buckets (the kernel takes any mix of edges)
+      rc = launch_generic_update(ctx, in, out, ctx->d_generic_edges, ctx->n_generic_edges, normalize, ctx->cur_slot);
     else
       rc = launch_fast_update(ctx, b, in, out, normalize);
     if (rc) return rc;
     if (ev1) BPX_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
   }
-  // edges updated by generic kernels left their terms in d_residual: fold them into the sweep's key
-  if ((rc = launch_residual_max(ctx, ctx->d_generic_edges, ctx->n_generic_edges, ctx->cur_slot))) return rc;
   if (fused) {
     ctx->gate_pending = true;  // the NEXT launch (or an explicit halo_gate) waits for this sweep's posts
     ctx->gate_hist_idx = ctx->history_len;
@@ -767,7 +768,7 @@ extern "C" int bpx_sweep_sequence(bpx_ctx* ctx, const int64_t* edge_seq, int64_t
     for (size_t b = 0; b + 1 < batch_ptr.size() && rc == BPX_OK; ++b) {
       const int64_t n = batch_ptr[b + 1] - batch_ptr[b];
       // edges of one run may belong to different buckets: the generic kernel takes any mix
-      rc = launch_generic_update(ctx, m, m, d_flat + batch_ptr[b], n, normalize);
+      rc = launch_generic_update(ctx, m, m, d_flat + batch_ptr[b], n, normalize, nullptr);
     }
     if (rc) break;
     // iterate_diff against the previous sweep over ALL edges (beliefpropagation.jl:261-267)
@@ -972,8 +973,7 @@ extern "C" int bpx_set_kernel_policy(bpx_ctx* ctx, int kernel) {
   ctx->kernel_policy = kernel;
   if (ctx->dims_set) {
     BPX_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (auto& b : ctx->buckets) b.kernel = pick_kernel(ctx, b);
-    return fast_prepare(ctx);
+    return rebuild_work_lists(ctx);  // re-picks every bucket's kernel, rebuilds launch groups and edge lists
   }
   return BPX_OK;
 }

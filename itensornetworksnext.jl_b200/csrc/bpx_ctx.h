@@ -67,6 +67,8 @@ struct bpx_ctx {
   int64_t n_generic_edges = 0;
   void* d_scratch = nullptr;
   int gen_smem_elems = 0, gen_smem_bytes = 0, gen_grid = 0;
+  void* d_onchip16_items = nullptr;
+  int n_onchip16_items = 0;
   void* d_sliced_items = nullptr;
   int n_sliced_items = 0;
   void* d_timing = nullptr;  // debug: per-phase clock64 stamps (BPX_ONCHIP_TIMING builds)
@@ -121,7 +123,7 @@ void set_error(bpx_ctx* ctx, const char* fmt, ...);
 
 int rebuild_work_lists(bpx_ctx* ctx);
 int launch_generic_update(bpx_ctx* ctx, const void* msg_in, void* msg_out, const int32_t* d_work, int64_t n_work,
-                          int normalize);
+                          int normalize, unsigned long long* resmax);
 // specialised kernels (bpx_fast.cuh)
 int fast_kernel_for(bpx_ctx* ctx, const Bucket& b);
 bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel);

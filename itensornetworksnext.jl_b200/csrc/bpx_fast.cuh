@@ -5,15 +5,20 @@
 #include "bpx_ctx.h"
 #include "bpx_onchip.cuh"
 #include "bpx_sliced.cuh"
+#include "bpx_onchip16.cuh"
 
 namespace bpx {
 
 inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
   if (kernel == BPX_KERNEL_GENERIC) return true;
   if (ctx->mode != BPX_MODE_NORM) return false;
-  if (kernel == BPX_KERNEL_ONCHIP)
-    return ctx->dtype == BPX_F64 && b.z >= 2 && b.z <= 4 && b.chi == 8 && b.d == 2 &&
-           (size_t)ctx->max_smem_optin >= onchip::SMEM_BYTES;
+  if (kernel == BPX_KERNEL_ONCHIP) {
+    if (ctx->dtype != BPX_F64 || b.d != 2) return false;
+    if (b.z >= 2 && b.z <= 4 && b.chi == 8) return (size_t)ctx->max_smem_optin >= onchip::SMEM_BYTES;
+    // 16-wide on-chip kernel: degree 3 / chi 16, or degree 6 / chi 4 with legs paired into super-legs
+    if ((b.z == 3 && b.chi == 16) || (b.z == 6 && b.chi == 4)) return (size_t)ctx->max_smem_optin >= onchip16::SMEM_BYTES16;
+    return false;
+  }
   if (kernel == BPX_KERNEL_SLICED)
     return ctx->dtype == BPX_F64 && b.z == 4 && b.chi == 16 && b.d == 2 && (size_t)ctx->max_smem_optin >= sliced::SMEM_BYTES;
   return false;
@@ -38,9 +43,14 @@ inline int fast_prepare(bpx_ctx* ctx) {
   }
   ctx->n_onchip_items = 0;
   std::vector<int> group;
+  int generic_leader = -1;
   for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
     ctx->buckets[i].leader = i;
-    if (ctx->buckets[i].kernel == BPX_KERNEL_ONCHIP && !ctx->buckets[i].my_vertices.empty()) group.push_back(i);
+    if (ctx->buckets[i].kernel == BPX_KERNEL_ONCHIP && ctx->buckets[i].chi == 8 && !ctx->buckets[i].my_vertices.empty()) group.push_back(i);
+    if (ctx->buckets[i].kernel == BPX_KERNEL_GENERIC && !ctx->buckets[i].my_edges.empty()) {
+      if (generic_leader < 0) generic_leader = i;
+      ctx->buckets[i].leader = generic_leader;  // all generic buckets share one launch
+    }
   }
   if (ctx->d_sliced_items) {
     cudaFree(ctx->d_sliced_items);
@@ -52,6 +62,50 @@ inline int fast_prepare(bpx_ctx* ctx) {
   }
   ctx->n_sliced_items = 0;
   bool need_image = false;
+  if (ctx->d_onchip16_items) {
+    cudaFree(ctx->d_onchip16_items);
+    ctx->d_onchip16_items = nullptr;
+  }
+  ctx->n_onchip16_items = 0;
+  // ---- 16-wide ON-CHIP buckets (degree 3 / chi 16; degree 6 / chi 4 in pair mode): one launch ----
+  {
+    std::vector<onchip16::ItemDesc> it16;
+    int leader16 = -1;
+    for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
+      Bucket& b = ctx->buckets[i];
+      if (b.kernel != BPX_KERNEL_ONCHIP || b.chi == 8 || b.my_vertices.empty()) continue;
+      if (leader16 < 0) leader16 = i;
+      b.leader = leader16;
+      for (int32_t v : b.my_vertices) {
+        onchip16::ItemDesc d;
+        memset(&d, 0, sizeof(d));
+        d.site_off = ctx->site_off[v];
+        d.pair_mode = b.z == 6 ? 1 : 0;
+        for (int l = 0; l < 6; ++l) d.peer[l] = -1;
+        for (int l = 0; l < b.z; ++l) {
+          const int32_t e = ctx->out_edge[v][l];
+          d.out_edge[l] = e;
+          d.out_off[l] = ctx->msg_off[e];
+          d.in_off[l] = ctx->msg_off[ctx->rev[e]];
+          d.peer[l] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
+        }
+        it16.push_back(d);
+      }
+    }
+    if (!it16.empty()) {
+      ctx->n_onchip16_items = (int)it16.size();
+      cudaError_t e = cudaMalloc((void**)&ctx->d_onchip16_items, it16.size() * sizeof(onchip16::ItemDesc));
+      if (e != cudaSuccess) {
+        set_error(ctx, "cudaMalloc(on-chip 16 items) failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return BPX_ERR_ALLOC;
+      }
+      BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip16_items, it16.data(), it16.size() * sizeof(onchip16::ItemDesc), cudaMemcpyHostToDevice));
+      BPX_CUDA(ctx, cudaFuncSetAttribute(onchip16::bp_update_onchip_c16, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)onchip16::SMEM_BYTES16));
+      need_image = true;
+    }
+  }
   // ---- SLICED buckets (chi = 16): two half items per vertex ----
   {
     std::vector<sliced::ItemDesc> sit;
@@ -149,6 +203,12 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
   }
+  if (ctx->d_sites_swz && ctx->n_onchip16_items > 0) {
+    onchip16::swizzle_sites_z3<<<std::min(ctx->n_onchip16_items, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
+        (const onchip16::ItemDesc*)ctx->d_onchip16_items, ctx->n_onchip16_items, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+  }
   if (ctx->d_sites_swz && ctx->n_sliced_items > 0) {
     sliced::swizzle_sites16<<<std::min(ctx->n_sliced_items, 8 * ctx->num_sms), 512, 0, ctx->stream>>>(
         (const sliced::ItemDesc*)ctx->d_sliced_items, ctx->n_sliced_items, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
@@ -160,6 +220,24 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
 }
 
 inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize) {
+  if (b.kernel == BPX_KERNEL_ONCHIP && b.chi != 8) {
+    onchip16::Args k;
+    k.items = (const onchip16::ItemDesc*)ctx->d_onchip16_items;
+    k.n_items = ctx->n_onchip16_items;
+    k.sites = (const double*)ctx->d_sites_swz;
+    k.msg_in = (const double*)msg_in;
+    k.msg_out = (double*)msg_out;
+    k.residual = nullptr;
+    k.resmax = ctx->cur_slot;
+    k.normalize = normalize;
+    k.peer = ctx->peer_args;
+    const int grid = std::min(k.n_items, ctx->num_sms);
+    if (grid == 0) return BPX_OK;
+    onchip16::bp_update_onchip_c16<<<grid, onchip16::NTHREADS16, onchip16::SMEM_BYTES16, ctx->stream>>>(k);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+    return BPX_OK;
+  }
   if (b.kernel == BPX_KERNEL_ONCHIP) {
     onchip::Args k;
     k.timing = (long long*)ctx->d_timing;

@@ -21,6 +21,7 @@ struct GenericArgs {
   const void* msg_in;
   void* msg_out;           // may alias msg_in (sequential schedule: in place)
   double* residual;        // per directed edge, may be NULL
+  unsigned long long* resmax;  // the sweep's residual key (atomicMax), may be NULL
   const int32_t* work;     // list of work items (edge ids / vertex ids) or NULL for identity
   int64_t n_work;
   void* scratch;           // per-CTA global scratch: 2 * scratch_elems elements each
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256) bp_update_generic(GenericArgs g) {
     if (warp == 0) {
       const int64_t off = g.msg_off[e];
       warp_epilogue<T>(out_s, msg_in + off, reinterpret_cast<T*>(g.msg_out) + off, nelem, g.normalize,
-                       g.residual ? g.residual + e : nullptr, lane);
+                       g.residual ? g.residual + e : nullptr, lane, g.resmax);
     }
   }
 }
