@@ -30,6 +30,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
+# DRAM traffic per launch of the dominant kernel, from one `ncu --set full` capture each
+# (dram__bytes_read.sum + dram__bytes_write.sum; summaries committed under profiles/).  Keyed by (workload, n_gpus).
+PROFILED_TRAFFIC = {
+    ("cfg2", 1): (62.28e6 + 0.59e6, "profiles/r1d_onchip_c8_final_ncu_summary.csv"),
+    ("cfg4", 1): (272.88e6 + 9.31e6, "profiles/r1e_onchip_c16_cfg4_ncu_summary.csv"),
+}
+# sliced chi=16 kernel: 926.9 MB read + 415.0 MB written for 196 degree-4 vertices (profiles/r1c_sliced_c16_ncu_summary.csv)
+SLICED_TRAFFIC_PER_VERTEX = (926.93e6 + 415.05e6) / 196.0
+
 METRIC = "bp_message_updates_per_s"
 UNIT = "updates/s"
 
@@ -332,6 +341,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["traffic"] = None
+    if (args.workload, world) in PROFILED_TRAFFIC:
+        roof["traffic"], roof["traffic_source"] = PROFILED_TRAFFIC[(args.workload, world)]
+    elif dom["kernel"] == 3 and world == 1:
+        roof["traffic"] = SLICED_TRAFFIC_PER_VERTEX * dom["vertices"]
+        roof["traffic_source"] = "profiles/r1c_sliced_c16_ncu_summary.csv (per-vertex DRAM bytes x degree-4 vertices of this workload)"
     roof["kernel"] = {1: "bp_update_generic", 2: "bp_update_onchip", 3: "bp_update_sliced"}.get(dom["kernel"], "?")
     roof["bucket"] = {"degree": z, "chi": chi, "phys": d, "updates_per_launch": sum(b["edges"] for b in merged),
                       "degrees_in_launch": sorted(b["degree"] for b in merged)}
