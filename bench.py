@@ -237,6 +237,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        try:  # keep the ranks' launch threads off each other's cores
+            ncpu = os.cpu_count() or 1
+            per = max(1, ncpu // world)
+            os.sched_setaffinity(0, set(range(local_rank * per, min(ncpu, (local_rank + 1) * per))))
+        except Exception:
+            pass
         # host-side plumbing only (IPC-handle exchange, barriers, max of the timings): gloo.  The data path
         # (cut-edge messages, residual) goes over NVLink peer memory inside libbpx, not through a collective library.
         dist.init_process_group("gloo")
@@ -280,20 +286,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     ctx.counters(reset=True)
     ctx.set_profiling(True)
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    evs = []
+    if rank == 0:  # one NVML poller per box is enough (and several perturb the launch path of every GPU)
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for e0, e1 in evs:
         l2_flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         ctx.sweep_async(1)
         e1.record(stream)
-        evs.append((e0, e1))
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     step_ms = np.array([a.elapsed_time(b) for a, b in evs])
     total_ms = float(step_ms.sum())
     counters = ctx.counters()

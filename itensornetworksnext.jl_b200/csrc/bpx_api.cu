@@ -598,7 +598,8 @@ static int sweep_once(bpx_ctx* ctx, int normalize) {
     pa.my_mailbox = reinterpret_cast<Mailbox*>(ctx->d_mailbox);
     pa.peer_mailbox = reinterpret_cast<Mailbox* const*>(ctx->d_peer_mailbox);
     pa.wait_id = ctx->gate_pending ? ctx->sweep_id : 0;
-    pa.prev_global_key = (ctx->gate_pending && ctx->gate_hist_idx >= 0) ? ctx->d_reskeys + ctx->gate_hist_idx : nullptr;
+    pa.wait_mask = ctx->recv_mask;  // only the ranks that feed this rank are awaited inside the kernel;
+    pa.prev_global_key = nullptr;   // the global residual is folded by the explicit gate when the host asks for it
     pa.post_id = ++ctx->sweep_id;
     pa.local_key = ctx->cur_slot;
     pa.peer_out = reinterpret_cast<double* const*>(ctx->d_peer_msg) + (size_t)(ctx->cur ^ 1) * ctx->nranks;

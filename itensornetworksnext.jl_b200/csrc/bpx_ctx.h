@@ -101,6 +101,7 @@ struct bpx_ctx {
   int gate_hist_idx = -1;
   bpx::PeerArgs peer_args = {};     // what the next fast launch is told about the exchange (nranks 0: nothing)
   unsigned int* d_ticket = nullptr;
+  unsigned long long recv_mask = 0;  // ranks that own the tail of an edge pointing into this rank's block
   bool single_launch = false;       // the whole sweep of this rank is ONE fast launch: exchange fused into it
 
   // counters

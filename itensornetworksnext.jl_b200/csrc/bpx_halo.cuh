@@ -42,7 +42,7 @@ __global__ void residual_post_kernel(const unsigned long long* __restrict__ loca
   // system-wide before the flag
   __threadfence_system();
   Mailbox* mb = peer_mailbox[p] + rank;
-  mb->residual = residual_from_key(*local_key);
+  mb->residual[sweep_id % MAILBOX_RING] = residual_from_key(*local_key);
   __threadfence_system();
   *reinterpret_cast<volatile unsigned long long*>(&mb->sweep_id) = sweep_id;
 }
@@ -67,7 +67,7 @@ __global__ void residual_gate_kernel(Mailbox* my_mailbox, int nranks, unsigned l
     }
     __threadfence_system();
     if (ok)
-      v = *reinterpret_cast<volatile double*>(&my_mailbox[p].residual);
+      v = *reinterpret_cast<volatile double*>(&my_mailbox[p].residual[sweep_id % MAILBOX_RING]);
     else
       atomicExch(error_flag, 1);
   }
@@ -183,6 +183,9 @@ extern "C" int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32
         cut.push_back(owner[ctx->dst[e]]);
       }
     ctx->n_cut = (int64_t)cut.size() / 2;
+    ctx->recv_mask = 0;
+    for (int64_t e = 0; e < ctx->ne; ++e)
+      if (owner[ctx->dst[e]] == rank && owner[ctx->src[e]] != rank) ctx->recv_mask |= 1ull << owner[ctx->src[e]];
     if (!cut.empty()) {
       BPX_CUDA(ctx, cudaMalloc((void**)&ctx->d_cut, cut.size() * sizeof(int32_t)));
       BPX_CUDA(ctx, cudaMemcpy(ctx->d_cut, cut.data(), cut.size() * sizeof(int32_t), cudaMemcpyHostToDevice));

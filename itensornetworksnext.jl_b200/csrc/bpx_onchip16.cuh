@@ -20,7 +20,9 @@ using namespace sliced;  // pos<>, FragA, absorb_close16, dmma, mbarrier/TMA hel
 
 constexpr int NCW16 = 8;
 constexpr int NCT16 = NCW16 * 32;
-constexpr int NTHREADS16 = NCT16 + 32;  // + producer warp
+constexpr int NEW16 = 2;                          // epilogue warps
+constexpr int NTHREADS16 = NCT16 + 32 * NEW16 + 32;  // + producer warp
+constexpr int NRAW16 = NCT16 + 32 * NEW16;       // participants of the raw-tile hand-over
 constexpr int NEL = 8192;
 
 struct ItemDesc {
@@ -88,7 +90,7 @@ __device__ __forceinline__ void absorb_one16(const double* src, double* dst, uin
 // shared memory (doubles): A[2][NEL] | X[NEL] | red[NCW16][256] | raw[256] | msgs[2][768] | 2 mbarriers
 constexpr size_t SMEM_DOUBLES16 = (size_t)3 * NEL + NCW16 * MSG + MSG + 2 * 3 * MSG + 2;
 constexpr size_t SMEM_BYTES16 = SMEM_DOUBLES16 * sizeof(double);
-enum { BAR_C16 = 1, BAR_SLOT16 = 2 /* and 3 */ };
+enum { BAR_C16 = 1, BAR_SLOT16 = 2 /* and 3 */, BAR_RAW_FULL16 = 4, BAR_RAW_FREE16 = 5 };
 
 __global__ void swizzle_sites_z3(const ItemDesc* items, int n_items, const double* __restrict__ src, double* __restrict__ dst) {
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -100,9 +102,8 @@ __global__ void swizzle_sites_z3(const ItemDesc* items, int n_items, const doubl
   }
 }
 
-// cross-warp sum of a 16x16 partial tile -> raw; then (warp 0/1) the fused epilogue(s)
-__device__ __forceinline__ void finish_tile16(double* red, double* raw, const double (&acc)[2][2][2], int warp, int lane, int g, int t,
-                                              const Args& k, const ItemDesc* d, int sleg, const double* M) {
+// compute warps: cross-warp sum of a 16x16 partial tile -> raw, handed to the epilogue warps
+__device__ __forceinline__ void publish16(double* red, double* raw, const double (&acc)[2][2][2], int warp, int g, int t) {
   double* mine = red + warp * MSG;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -110,47 +111,97 @@ __device__ __forceinline__ void finish_tile16(double* red, double* raw, const do
     for (int h = 0; h < 2; ++h)
 #pragma unroll
       for (int i = 0; i < 2; ++i) mine[(g + 8 * mt) + CHI * (2 * t + i + 8 * h)] = acc[mt][h][i];
-  onchip::bar_sync(BAR_C16, NCT16);
-  {
-    const int el = threadIdx.x;
-    double s = 0;
+  onchip::bar_sync(BAR_C16, NCT16);  // partial tiles visible; every compute warp is done with X / A of this phase
+  const int el = threadIdx.x;
+  double s = 0;
 #pragma unroll
-    for (int w = 0; w < NCW16; ++w) s += red[w * MSG + el];
-    raw[el] = s;
-  }
-  onchip::bar_sync(BAR_C16, NCT16);
+  for (int w = 0; w < NCW16; ++w) s += red[w * MSG + el];
+  onchip::bar_sync(BAR_RAW_FREE16, NRAW16);  // epilogue warps have consumed the previous tile (also: red fully read)
+  raw[el] = s;
+  onchip::bar_arrive(BAR_RAW_FULL16, NRAW16);
+}
+
+// epilogue warps: tile of super-leg `sleg` -> message(s): sum-normalise, residual, store (+ peer store)
+__device__ __forceinline__ void epilogue16(const double* raw, const double* Mst, int which, int lane, const Args& k, const ItemDesc* d,
+                                           int sleg) {
   if (!d->pair_mode) {
-    if (warp == 0) {
-      const int64_t off = d->out_off[sleg];
-      double* peer_m = (k.peer.nranks > 1 && d->peer[sleg] >= 0) ? k.peer.peer_out[d->peer[sleg]] + off : nullptr;
-      warp_epilogue<double>(raw, k.msg_in + off, k.msg_out + off, MSG, k.normalize, k.residual ? k.residual + d->out_edge[sleg] : nullptr,
-                            lane, k.resmax, peer_m);
+    // plain: one 16x16 message, handled by epilogue warp 0; lane holds elements lane + 32 j
+    const int64_t off = d->out_off[sleg];
+    double o[8], v[8];
+    if (which == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = k.msg_in[off + lane + 32 * j];  // issued before the hand-over
     }
-  } else if (warp < 2) {
-    // S[(a', c'), (a, c)] at (a' + 4 c') + 16 (a + 4 c).  warp 0: out_2k[a', a] = sum M_2k+1[c', c] S;  warp 1: out_2k+1[c', c] = sum M_2k[a', a] S
-    const int leg = 2 * sleg + warp;
-    const double* Mo = M + (2 * sleg + (1 - warp)) * 16;  // the OTHER message of the pair
+    onchip::bar_sync(BAR_RAW_FULL16, NRAW16);
+    if (which == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = raw[lane + 32 * j];
+    }
+    onchip::bar_arrive(BAR_RAW_FREE16, NRAW16);
+    if (which != 0) return;
+    double s = 0, dot = 0, n_old = 0, n_new = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s += v[j];
+      dot += o[j] * v[j];
+      n_old += o[j] * o[j];
+      n_new += v[j] * v[j];
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, m);
+      dot += __shfl_xor_sync(0xffffffffu, dot, m);
+      n_old += __shfl_xor_sync(0xffffffffu, n_old, m);
+      n_new += __shfl_xor_sync(0xffffffffu, n_new, m);
+    }
+    const bool scale = k.normalize && s != 0.0;
+    double* peer_m = (k.peer.nranks > 1 && d->peer[sleg] >= 0) ? k.peer.peer_out[d->peer[sleg]] + off : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double x = scale ? v[j] / s : v[j];
+      k.msg_out[off + lane + 32 * j] = x;
+      if (peer_m) peer_m[lane + 32 * j] = x;
+    }
+    if (lane == 0) residual_record(k.resmax, 1.0 - dot * dot / (n_old * n_new));  // invariant under the scaling
+  } else {
+    // pair mode: S[(a', c'), (a, c)] at (a' + 4 c') + 16 (a + 4 c).
+    // warp 0: out_2k[a', a] = sum M_2k+1[c', c] S;  warp 1: out_2k+1[c', c] = sum M_2k[a', a] S
+    const int leg = 2 * sleg + which;
+    const int64_t off = d->out_off[leg];
+    const double* Mo = Mst + (2 * sleg + (1 - which)) * 16;  // the OTHER message of the pair (staged copy)
+    const double o = lane < 16 ? k.msg_in[off + lane] : 0.0;
+    double mo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mo[i] = Mo[i];
+    onchip::bar_sync(BAR_RAW_FULL16, NRAW16);
     double v = 0.0;
     if (lane < 16) {
-      const int p = lane & 3, q = lane >> 2;  // output element (p', q) of a 4x4 message
+      const int p = lane & 3, q = lane >> 2;  // output element (p, q) of a 4x4 message
 #pragma unroll
       for (int cp = 0; cp < 4; ++cp)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int row = warp == 0 ? (p + 4 * cp) : (cp + 4 * p);
-          const int col = warp == 0 ? (q + 4 * c) : (c + 4 * q);
-          v += Mo[cp + 4 * c] * raw[row + 16 * col];
+          const int row = which == 0 ? (p + 4 * cp) : (cp + 4 * p);
+          const int col = which == 0 ? (q + 4 * c) : (c + 4 * q);
+          v += mo[cp + 4 * c] * raw[row + 16 * col];
         }
     }
-    __shared__ double tiny[2][16];
-    if (lane < 16) tiny[warp][lane] = v;
-    __syncwarp();
-    const int64_t off = d->out_off[leg];
-    double* peer_m = (k.peer.nranks > 1 && d->peer[leg] >= 0) ? k.peer.peer_out[d->peer[leg]] + off : nullptr;
-    warp_epilogue<double>(tiny[warp], k.msg_in + off, k.msg_out + off, 16, k.normalize, k.residual ? k.residual + d->out_edge[leg] : nullptr, lane,
-                          k.resmax, peer_m);
+    onchip::bar_arrive(BAR_RAW_FREE16, NRAW16);
+    double s = v, dot = o * v, n_old = o * o, n_new = v * v;
+#pragma unroll
+    for (int m = 8; m > 0; m >>= 1) {  // lanes >= 16 hold zeros
+      s += __shfl_xor_sync(0xffffffffu, s, m);
+      dot += __shfl_xor_sync(0xffffffffu, dot, m);
+      n_old += __shfl_xor_sync(0xffffffffu, n_old, m);
+      n_new += __shfl_xor_sync(0xffffffffu, n_new, m);
+    }
+    if (lane < 16) {
+      const double x = (k.normalize && s != 0.0) ? v / s : v;
+      k.msg_out[off + lane] = x;
+      if (k.peer.nranks > 1 && d->peer[leg] >= 0) k.peer.peer_out[d->peer[leg]][off + lane] = x;
+    }
+    if (lane == 0) residual_record(k.resmax, 1.0 - dot * dot / (n_old * n_new));
   }
-  onchip::bar_sync(BAR_C16, NCT16);  // raw / red free again
 }
 
 __global__ void __launch_bounds__(NTHREADS16, 1) bp_update_onchip_c16(Args k) {
@@ -170,13 +221,13 @@ __global__ void __launch_bounds__(NTHREADS16, 1) bp_update_onchip_c16(Args k) {
   }
   __syncthreads();
 
-  if (warp == NCW16) {
+  if (warp == NCW16 + NEW16) {
     // ===== producer: A (one 64 KiB run) + incoming messages of item n into slot n & 1 =====
     peer_gate(k.peer, lane);
     int n = 0;
     for (int item = blockIdx.x; item < k.n_items; item += G, ++n) {
       const int sl = n & 1;
-      if (n >= 2) onchip::bar_sync(BAR_SLOT16 + sl, NCT16 + 32);
+      if (n >= 2) onchip::bar_sync(BAR_SLOT16 + sl, NRAW16 + 32);  // compute AND epilogue warps released the slot
       const ItemDesc* d = k.items + item;
       fence_proxy_async();
       if (lane == 0) mbar_expect_tx(&mbar[sl], NEL * 8 + (d->pair_mode ? 6 * 16 * 8 : 3 * MSG * 8));
@@ -188,6 +239,20 @@ __global__ void __launch_bounds__(NTHREADS16, 1) bp_update_onchip_c16(Args k) {
       } else {
         if (lane >= 8 && lane < 11) tma_bulk_g2s(Md + (lane - 8) * MSG, k.msg_in + d->in_off[lane - 8], MSG * 8, &mbar[sl]);
       }
+    }
+  } else if (warp >= NCW16) {
+    // ===== epilogue warps: tiles arrive in the order out2, out1, out0 of every item =====
+    const int which = warp - NCW16;
+    onchip::bar_arrive(BAR_RAW_FREE16, NRAW16);  // raw starts free
+    int n = 0;
+    for (int item = blockIdx.x; item < k.n_items; item += G, ++n) {
+      const ItemDesc* d = k.items + item;
+      const double* Mst = msgs + (n & 1) * 3 * MSG;  // staged incoming messages (valid until the item's slot is released)
+      if (d->pair_mode) mbar_wait(&mbar[n & 1], (n >> 1) & 1);  // pair mode reads the staged messages
+      epilogue16(raw, Mst, which, lane, k, d, 2);
+      epilogue16(raw, Mst, which, lane, k, d, 1);
+      epilogue16(raw, Mst, which, lane, k, d, 0);
+      if (item + 2 * G < k.n_items) onchip::bar_arrive(BAR_SLOT16 + (n & 1), NRAW16 + 32);
     }
   } else {
     // ===== compute warps =====
@@ -217,8 +282,8 @@ __global__ void __launch_bounds__(NTHREADS16, 1) bp_update_onchip_c16(Args k) {
           absorb_close16<L_A3, 2, 1>(Xbuf, A, pos<L_A3>(0, c), m2, g, t, accB);
         }
       }
-      finish_tile16(red, raw, accA, warp, lane, g, t, k, d, 2, M);  // includes the barrier that frees Xbuf
-      finish_tile16(red, raw, accB, warp, lane, g, t, k, d, 1, M);
+      publish16(red, raw, accA, warp, g, t);  // out2; its first barrier also frees Xbuf
+      publish16(red, raw, accB, warp, g, t);  // out1
       {
         // X' = A·M2 (columns: leg 0)  ->  out0 (absorb 1, close 0)  (columns: leg 2')
 #pragma unroll
@@ -233,9 +298,10 @@ __global__ void __launch_bounds__(NTHREADS16, 1) bp_update_onchip_c16(Args k) {
 #pragma unroll 1
         for (int c = warp; c < 16; c += NCW16) absorb_close16<L_A3, 1, 0>(Xbuf, A, pos<L_A3>(2, c), m1, g, t, accA);
       }
-      finish_tile16(red, raw, accA, warp, lane, g, t, k, d, 0, M);
-      if (item + 2 * G < k.n_items) onchip::bar_arrive(BAR_SLOT16 + sl, NCT16 + 32);
+      publish16(red, raw, accA, warp, g, t);  // out0
+      if (item + 2 * G < k.n_items) onchip::bar_arrive(BAR_SLOT16 + sl, NRAW16 + 32);
     }
+    onchip::bar_sync(BAR_RAW_FREE16, NRAW16);  // let the epilogue warps' last arrive complete
   }
   peer_post_when_last(k.peer);
 }

@@ -7,9 +7,10 @@
 
 namespace bpx {
 
-struct Mailbox {  // one per source rank, lives in the RECEIVER's memory
-  unsigned long long sweep_id;
-  double residual;
+constexpr int MAILBOX_RING = 64;  // ranks are coupled through neighbours only, so they may be several sweeps apart
+struct Mailbox {                  // one per source rank, lives in the RECEIVER's memory
+  unsigned long long sweep_id;    // latest sweep the source rank has completed and pushed
+  double residual[MAILBOX_RING];  // its local residual maxima, indexed by sweep id % MAILBOX_RING
 };
 
 struct PeerArgs {
@@ -18,6 +19,7 @@ struct PeerArgs {
   Mailbox* my_mailbox;                     // [nranks]
   Mailbox* const* peer_mailbox;            // [nranks] (own entry included)
   unsigned long long wait_id;              // posts of this sweep id must have arrived before cut messages are read (0: none)
+  unsigned long long wait_mask;            // bit p set: rank p sends this rank cut-edge messages (only those are awaited)
   unsigned long long post_id;              // id to post when this kernel's updates are complete (0: do not post)
   unsigned long long* prev_global_key;     // where CTA 0 folds the previous sweep's global residual (may be NULL)
   const unsigned long long* local_key;     // this sweep's local residual key (the kernels' resmax slot)
@@ -30,7 +32,9 @@ struct PeerArgs {
 __device__ __forceinline__ void peer_gate(const PeerArgs& pa, int lane) {
   if (pa.nranks <= 1 || pa.wait_id == 0) return;
   double v = -INFINITY;
+  const bool fold = blockIdx.x == 0 && pa.prev_global_key != nullptr;  // folding the global residual needs every rank
   for (int p = lane; p < pa.nranks; p += 32) {
+    if (!fold && !((pa.wait_mask >> p) & 1ull)) continue;
     volatile unsigned long long* flag = &pa.my_mailbox[p].sweep_id;
     const long long t0 = clock64();
     bool ok = true;
@@ -42,14 +46,14 @@ __device__ __forceinline__ void peer_gate(const PeerArgs& pa, int lane) {
       __nanosleep(100);
     }
     if (ok) {
-      const double r = *reinterpret_cast<volatile double*>(&pa.my_mailbox[p].residual);
+      const double r = *reinterpret_cast<volatile double*>(&pa.my_mailbox[p].residual[pa.wait_id % MAILBOX_RING]);
       v = (r != r || v != v) ? NAN : fmax(v, r);
     } else {
       atomicExch(pa.error_flag, 1);
     }
   }
   __threadfence_system();  // acquire: the peers' message stores precede their flag
-  if (blockIdx.x == 0 && pa.prev_global_key) {
+  if (fold) {
     bool has_nan = v != v;
     has_nan = __any_sync(0xffffffffu, has_nan);
     double m = has_nan ? -INFINITY : v;
@@ -76,7 +80,7 @@ __device__ __forceinline__ void peer_post_when_last(const PeerArgs& pa) {
     if (threadIdx.x < pa.nranks) {
       __threadfence_system();
       Mailbox* mb = pa.peer_mailbox[threadIdx.x] + pa.rank;
-      mb->residual = residual_from_key(*reinterpret_cast<const volatile unsigned long long*>(pa.local_key));
+      mb->residual[pa.post_id % MAILBOX_RING] = residual_from_key(*reinterpret_cast<const volatile unsigned long long*>(pa.local_key));
       __threadfence_system();
       *reinterpret_cast<volatile unsigned long long*>(&mb->sweep_id) = pa.post_id;
     }

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_sliced_c16(Args k) {
   } else {
   // ================================ compute warps ================================
   // (they read peer-written messages too -- the fragments below -- so they wait for the gate as well)
-  if (k.peer.nranks > 1 && warp == 0) peer_gate(PeerArgs{k.peer.nranks, k.peer.rank, k.peer.my_mailbox, k.peer.peer_mailbox, k.peer.wait_id, 0,
+  if (k.peer.nranks > 1 && warp == 0) peer_gate(PeerArgs{k.peer.nranks, k.peer.rank, k.peer.my_mailbox, k.peer.peer_mailbox, k.peer.wait_id, k.peer.wait_mask, 0,
                                                         nullptr, nullptr, nullptr, nullptr, k.peer.error_flag}, lane);
   if (k.peer.nranks > 1) onchip::bar_sync(BAR_COMPUTE, NCT);
   int it = 0;

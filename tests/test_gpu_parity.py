@@ -330,3 +330,67 @@ def test_full_path_sampled_edges_against_oracle(oracle, name, dims):
         sums = np.array([m.sum() for m in after])
         assert np.allclose(sums, 1.0, rtol=0, atol=1e-12)
         assert abs(res - oracle.iterate_diff(after, before)) < 1e-11
+
+
+# ---- hardening of the specialised kernels -------------------------------------------------------------
+@pytest.mark.parametrize("name,dims", [("cfg2", (5, 6)), ("cfg5", (4, 4)), ("cfg4", (4, 4, 4))])
+def test_fast_kernels_without_normalisation_and_multi_sweep(oracle, name, dims):
+    g = graphs.named_grid(dims, periodic=(name == "cfg4"))
+    p = problems.make_config(name, graph=g)
+    # unnormalised messages grow quickly: two sweeps are enough to exercise the branch
+    check_sweeps(oracle, p.ga, p.dtype, "norm", p.phys_dim, p.link_dim, p.tensors, p.messages, 2, normalize=False)
+
+
+def test_fast_kernel_converges_like_the_oracle(oracle):
+    g = graphs.named_grid((6, 6))
+    p = problems.make_config("cfg2", graph=g)
+    op = oracle.make_problem(p.ga, p.tensors, "norm")
+    hist_want = []
+    want, it, delta = oracle.beliefpropagation(op, p.messages, maxiter=200, tol=1e-12, history=hist_want)
+    with B.BPXContext(0) as ctx:
+        problems.upload(ctx, p)
+        assert all(b["kernel"] == _lib.BPX_KERNEL_ONCHIP for b in ctx.buckets())
+        res, done = ctx.sweep(200, 1e-12)
+        assert done == it
+        hist = ctx.residual_history()
+        assert len(hist) == done
+        assert np.allclose(hist, hist_want, rtol=1e-6, atol=1e-13)
+        assert rel_err(ctx.get_messages(), want) < 1e-9
+        # async sweeps append to the same history and keep the iterate consistent
+        ctx.sweep_async(3)
+        assert len(ctx.residual_history()) == done + 3
+        assert ctx.counters()["sweeps"] == done + 3
+
+
+def test_nan_in_a_site_tensor_propagates_to_the_residual(oracle):
+    # Julia's `maximum` propagates NaN (beliefpropagation.jl:262); so must the fused residual key
+    g = graphs.named_grid((4, 4))
+    p = problems.make_config("cfg2", graph=g)
+    t = [x.copy() for x in p.tensors]
+    t[5][0, 0, 0, 0, 0] = np.nan
+    with B.BPXContext(0) as ctx:
+        ctx.set_graph(p.ga.src, p.ga.dst, p.ga.slot, p.ga.nv)
+        ctx.set_dims(p.dtype, "norm", p.phys_dim, p.link_dim)
+        ctx.set_site_tensors(t)
+        ctx.set_messages(p.messages)
+        res, done = ctx.sweep(1)
+        assert np.isnan(res)
+
+
+def test_site_tensor_update_refreshes_private_images(oracle):
+    # bpx_set_site_tensor after a sweep must invalidate the pre-swizzled image
+    g = graphs.named_grid((4, 4))
+    p = problems.make_config("cfg2", graph=g)
+    with B.BPXContext(0) as ctx:
+        problems.upload(ctx, p)
+        ctx.sweep(1)
+        t = [x.copy() for x in p.tensors]
+        t[5] = t[5] * 2.0 + 0.01
+        flat = np.ascontiguousarray(t[5].ravel(order="F"))
+        import ctypes as C
+        ctx._check(ctx.lib.bpx_set_site_tensor(ctx.h, 5, flat.ctypes.data_as(C.c_void_p)))
+        ctx.set_messages(p.messages)
+        ctx.sweep(1)
+        got = ctx.get_messages()
+    want = oracle.sweep_jacobi(oracle.make_problem(p.ga, t, "norm"), p.messages)
+    assert rel_err(got, want) < MSG_RTOL
