@@ -293,6 +293,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     t_wall0 = time.perf_counter()
     for e0, e1 in evs:
         l2_flush.zero_()
+        if world > 1:
+            ctx.peer_barrier()  # untimed: align the ranks after their (untimed) L2 flushes, so that one rank's flush
+            #                     does not sit inside its neighbour's timed sweep
         e0.record(stream)
         ctx.sweep_async(1)
         e1.record(stream)
@@ -414,7 +417,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "dtype": "f64" if p.dtype.kind != "c" else "c128", "data": "synthetic",
             "config": {"workload": desc, "schedule": "synchronous (Jacobi) sweep, sum-normalised, residual fused",
                        "updates_per_step": n_total_updates, "updates_per_gpu": n_local_updates,
-                       "l2": "flushed between timed steps (256 MiB memset)", "timing": "CUDA events per step on the launching stream"},
+                       "l2": "flushed between timed steps (256 MiB memset)",
+                       "timing": "CUDA events per step on the launching stream" + ("; ranks aligned by a device-side barrier after each flush" if world > 1 else "")},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(counters["launches"]), "residual_after_bench": residual,
             "wall_s_timed_region": t_wall,

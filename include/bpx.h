@@ -170,6 +170,8 @@ int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32_t* owner);
 int bpx_halo_export(bpx_ctx* ctx, void* handles_3x64);
 int bpx_halo_connect(bpx_ctx* ctx, int peer_rank, const void* handles_3x64);
 int64_t bpx_num_cut_edges(const bpx_ctx* ctx);
+/* enqueue a device-side barrier over all connected ranks on the context's stream (collective: every rank calls it) */
+int bpx_peer_barrier(bpx_ctx* ctx);
 
 /* Fill the RESIDENT site tensors and messages with the synthetic benchmark recipe on the device (site tensor v =
  * randn(seed, stream v) / sqrt(n_v); message e = (I + 0.1 |randn(seed, stream nv + e)|) sum-normalised): same

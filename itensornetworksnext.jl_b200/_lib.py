@@ -89,6 +89,7 @@ def load() -> C.CDLL:
         "bpx_halo_export": (C.c_int, [vp, vp]),
         "bpx_halo_connect": (C.c_int, [vp, C.c_int, vp]),
         "bpx_num_cut_edges": (i64, [vp]),
+        "bpx_peer_barrier": (C.c_int, [vp]),
         "bpx_fill_synthetic": (C.c_int, [vp, C.c_uint64]),
         "bpx_fill_randn": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, i64, vp]),
     }

@@ -96,6 +96,7 @@ struct bpx_ctx {
   void** d_peer_mailbox = nullptr;  // [nranks] device table of mailbox arrays (own entry included)
   void* d_mailbox = nullptr;        // this rank's mailbox array: one slot per source rank
   int* d_halo_error = nullptr;
+  unsigned long long barrier_id = 0;
   unsigned long long sweep_id = 0;  // sweeps posted since bpx_set_partition (identical on all ranks)
   bool gate_pending = false, halo_connected = false;
   int gate_hist_idx = -1;

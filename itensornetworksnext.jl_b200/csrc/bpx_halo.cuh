@@ -85,6 +85,26 @@ __global__ void residual_gate_kernel(Mailbox* my_mailbox, int nranks, unsigned l
   }
 }
 
+// device-side barrier over all ranks: announce epoch `id` in every peer's mailbox, then wait for everybody's
+__global__ void peer_barrier_kernel(Mailbox* my_mailbox, Mailbox* const* peer_mailbox, int rank, int nranks, unsigned long long id,
+                                    int* error_flag) {
+  const int p = threadIdx.x;
+  if (p < nranks) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&(peer_mailbox[p] + rank)->barrier_id) = id;
+    volatile unsigned long long* flag = &my_mailbox[p].barrier_id;
+    const long long t0 = clock64();
+    while (*flag < id) {
+      if (clock64() - t0 > 8000000000ll) {
+        atomicExch(error_flag, 1);
+        break;
+      }
+      __nanosleep(100);
+    }
+    __threadfence_system();
+  }
+}
+
 inline int halo_push(bpx_ctx* ctx, void* msg_out) {
   if (ctx->nranks <= 1 || ctx->n_cut == 0) return BPX_OK;
   if (!ctx->halo_connected) {
@@ -197,6 +217,7 @@ extern "C" int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32
     BPX_CUDA(ctx, cudaMalloc((void**)&ctx->d_ticket, sizeof(unsigned int)));
     BPX_CUDA(ctx, cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
     ctx->sweep_id = 0;
+    ctx->barrier_id = 0;
   }
   return bpx::rebuild_work_lists(ctx);
 }
@@ -260,3 +281,21 @@ extern "C" int bpx_halo_connect(bpx_ctx* ctx, int peer_rank, const void* handles
 }
 
 extern "C" int64_t bpx_num_cut_edges(const bpx_ctx* ctx) { return ctx ? ctx->n_cut : -1; }
+
+// Enqueue a cross-rank barrier on the context's stream (every rank must call it the same number of times).
+extern "C" int bpx_peer_barrier(bpx_ctx* ctx) {
+  if (!ctx) return BPX_ERR_INVALID;
+  if (ctx->nranks <= 1) return BPX_OK;
+  if (!ctx->halo_connected) {
+    bpx::set_error(ctx, "bpx_peer_barrier: peers are not connected");
+    return BPX_ERR_INVALID;
+  }
+  BPX_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->barrier_id++;
+  bpx::peer_barrier_kernel<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<bpx::Mailbox*>(ctx->d_mailbox),
+                                                    reinterpret_cast<bpx::Mailbox* const*>(ctx->d_peer_mailbox), ctx->rank, ctx->nranks,
+                                                    ctx->barrier_id, ctx->d_halo_error);
+  ctx->n_launches++;
+  BPX_CUDA(ctx, cudaGetLastError());
+  return BPX_OK;
+}

@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
   bar_sync(BAR_RAW_FREE, NRAW);
   }
   // multi-GPU: every role of this CTA is done; the last CTA posts (sweep id, local residual) to all ranks
-  peer_post_when_last(k.peer);
+  peer_post_when_last(k.peer, warp >= NCW && warp < NCW + NEW);  // only the epilogue warps store messages
 }
 
 }  // namespace onchip

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS16, 1) bp_update_onchip_c16(Args k) {
     }
     onchip::bar_sync(BAR_RAW_FREE16, NRAW16);  // let the epilogue warps' last arrive complete
   }
-  peer_post_when_last(k.peer);
+  peer_post_when_last(k.peer, warp >= NCW16 && warp < NCW16 + NEW16);  // only the epilogue warps store messages
 }
 
 }  // namespace onchip16

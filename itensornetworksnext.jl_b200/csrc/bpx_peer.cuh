@@ -10,6 +10,7 @@ namespace bpx {
 constexpr int MAILBOX_RING = 64;  // ranks are coupled through neighbours only, so they may be several sweeps apart
 struct Mailbox {                  // one per source rank, lives in the RECEIVER's memory
   unsigned long long sweep_id;    // latest sweep the source rank has completed and pushed
+  unsigned long long barrier_id;  // bpx_peer_barrier epochs
   double residual[MAILBOX_RING];  // its local residual maxima, indexed by sweep id % MAILBOX_RING
 };
 
@@ -43,7 +44,7 @@ __device__ __forceinline__ void peer_gate(const PeerArgs& pa, int lane) {
         ok = false;
         break;
       }
-      __nanosleep(100);
+      __nanosleep(20);
     }
     if (ok) {
       const double r = *reinterpret_cast<volatile double*>(&pa.my_mailbox[p].residual[pa.wait_id % MAILBOX_RING]);
@@ -65,11 +66,13 @@ __device__ __forceinline__ void peer_gate(const PeerArgs& pa, int lane) {
 }
 
 // Called by every thread of every CTA when all of the CTA's global/peer stores have been issued (CTA-uniform).
-// The last CTA to arrive posts (post_id, local residual) to every rank.
-__device__ __forceinline__ void peer_post_when_last(const PeerArgs& pa) {
+// `wrote`: this thread stored messages / residual keys (only those threads need the system-scope release; a
+// membar.sys from every thread of the grid costs microseconds).  The last CTA to arrive posts (post_id, local
+// residual) to every rank.
+__device__ __forceinline__ void peer_post_when_last(const PeerArgs& pa, bool wrote = true) {
   if (pa.nranks <= 1 || pa.post_id == 0) return;
   __shared__ unsigned int s_last;
-  __threadfence_system();  // release this thread's message / residual-key stores
+  if (wrote) __threadfence_system();  // release this thread's message / residual-key stores
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(pa.ticket, 1u);

@@ -154,6 +154,10 @@ class BPXContext:
     def sweep_async(self, n_sweeps: int = 1, normalize: bool = True):
         self._check(self.lib.bpx_sweep_async(self.h, int(n_sweeps), int(bool(normalize))))
 
+    def peer_barrier(self):
+        """Device-side barrier over all connected ranks, enqueued on the context's stream (collective)."""
+        self._check(self.lib.bpx_peer_barrier(self.h))
+
     def set_profiling(self, enable: bool):
         self._check(self.lib.bpx_set_profiling(self.h, int(bool(enable))))
 
