@@ -73,6 +73,10 @@ def build_workload(name: str, world: int):
             p = problems.make_config(name, host_data=False)
             owner = [(v[1] - 1) * world // 256 for v in p.ga.vertices]
             return p, owner, f"256x256 square-lattice PEPS norm network, chi=16, d=2, Float64, {world} strips of {256 // world} rows (STRONG scaling)"
+        if name == "cfg4" and world > 1:  # BASELINE config 4 "at 1/2/4/8 B200": slabs of the periodic cube
+            p = problems.make_config(name)
+            owner = [(v[2] - 1) * world // 16 for v in p.ga.vertices]
+            return p, owner, f"16x16x16 periodic cubic PEPS norm network, chi=4, d=2, Float64, {world} slabs of {16 // world} planes (STRONG scaling)"
         p = problems.make_config(name, host_data=(name != "cfg5"))
         desc = {
             "cfg1": "4x4 square-lattice PEPS norm network, chi=2, d=2, Float64",
@@ -151,15 +155,19 @@ def cpu_reference_arm(p, seconds: float, max_steps: int = 1000, warmup: int = 1)
     from oracle.c_oracle import COracle
 
     co = COracle(p.ga, p.phys_dim, p.link_dim, p.tensors, p.dtype)
-    cores = co.num_threads()
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would silently serialise the arm)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
     flat = co.pack(p.messages)
     ne = p.ga.ne
     # probe cost on a small sample
     rng = np.random.default_rng(0)
     probe = np.sort(rng.choice(ne, size=min(ne, 4 * cores), replace=False))
-    co.sweep_jacobi(flat, edges=probe)  # cold (thread pool start-up, page faults)
+    co.sweep_jacobi(flat, edges=probe, nthreads=cores)  # cold (thread pool start-up, page faults)
     t0 = time.perf_counter()
-    co.sweep_jacobi(flat, edges=probe)
+    co.sweep_jacobi(flat, edges=probe, nthreads=cores)
     per_update = (time.perf_counter() - t0) / len(probe)
     full = per_update * ne
     if full <= seconds / 3:
@@ -169,12 +177,12 @@ def cpu_reference_arm(p, seconds: float, max_steps: int = 1000, warmup: int = 1)
         edges = np.sort(rng.choice(ne, size=min(ne, k), replace=False))
         n_upd, sample = len(edges), f"{len(edges)} randomly sampled directed edges of {ne} per step"
     for _ in range(warmup):
-        co.sweep_jacobi(flat, edges=edges)
+        co.sweep_jacobi(flat, edges=edges, nthreads=cores)
     times = []
     t_end = time.perf_counter() + seconds
     while len(times) < max_steps and (time.perf_counter() < t_end or len(times) < 2):
         t0 = time.perf_counter()
-        co.sweep_jacobi(flat, edges=edges)
+        co.sweep_jacobi(flat, edges=edges, nthreads=cores)
         times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.mean(times))
     return n_upd / (ms * 1e-3), cores, sample, ms, len(times)
