@@ -266,6 +266,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if args.kernel:
         ctx.set_kernel_policy(args.kernel)
     ctx.set_dims(p.dtype, "norm", p.phys_dim, p.link_dim)
+    if world > 1:  # partition first: site tensors are then allocated / generated for the owned vertices only
+        from itnn_b200 import partition
+
+        partition.connect(ctx, owner, rank, world)
     if p.tensors is None:  # inputs generated on the device (same recipe; the host cannot stage 63 GiB)
         ctx.fill_synthetic(123)
         flat0 = ctx.get_messages_flat()
@@ -273,10 +277,6 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         ctx.set_site_tensors(p.tensors)
         flat0 = ctx.pack_messages(p.messages)
         ctx.set_messages(flat0)
-    if world > 1:
-        from itnn_b200 import partition
-
-        partition.connect(ctx, owner, rank, world)
     n_local_updates = sum(b["edges"] for b in ctx.buckets())
     n_total_updates = p.ga.ne
 

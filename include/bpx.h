@@ -89,6 +89,9 @@ int64_t bpx_rev(const bpx_ctx* ctx, int64_t e);
 /* element (not byte) offsets / sizes in the packed host layouts; totals with v == nv / e == ne */
 int64_t bpx_site_offset(const bpx_ctx* ctx, int64_t v);
 int64_t bpx_message_offset(const bpx_ctx* ctx, int64_t e);
+/* element offset of A_v inside the DEVICE site buffer (bpx_device_site_tensors); -1 if v is not resident on this
+ * rank (partitioned contexts store only the tensors of the vertices they own) */
+int64_t bpx_site_device_offset(const bpx_ctx* ctx, int64_t v);
 
 /* kettensor(nn, v) for every v (normnetwork.jl:77), canonical layout, packed. */
 int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed);
@@ -128,6 +131,7 @@ int bpx_last_residual(bpx_ctx* ctx, double* out);
 int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* out);
 
 /* ---- beliefs (messagecache.jl:139-201), same contraction kernels with all z messages absorbed ---- */
+/* partitioned contexts fill in the vertices they own and report 0 for the others (combine across ranks on the host) */
 int bpx_vertex_scalars(bpx_ctx* ctx, void* out /* nv elements */);
 int bpx_edge_scalars(bpx_ctx* ctx, void* out /* ne/2 elements, edges with e < rev(e) in edge order */);
 /* numerator of <O_v>: vertex contraction with the d x d operator `op[s_out, s_in]` applied to the ket
@@ -162,7 +166,8 @@ int bpx_synchronize(bpx_ctx* ctx);
 /* ---- multi-GPU: vertex partition, one context per rank ------------------------
  * owner[v] = rank that updates the out-edges of v.  A rank stores all site tensors it owns and all
  * messages; per sweep it updates only its own edges and pushes the messages on cut edges straight into
- * the peers' message sets over NVLink (peer pointers from bpx_halo_export / bpx_halo_connect).       */
+ * the peers' message sets over NVLink (peer pointers from bpx_halo_export / bpx_halo_connect).  Site tensors are
+ * kept only for owned vertices (tensors uploaded earlier are preserved; later uploads skip foreign vertices). */
 int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32_t* owner);
 /* three 64-byte cudaIpcMemHandle_t: message set 0, message set 1, residual mailbox.  Exchange them between
  * the ranks by any host-side means (torch.distributed / MPI) and connect every peer; sweeps then push

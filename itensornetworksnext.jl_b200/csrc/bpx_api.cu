@@ -85,6 +85,7 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_scratch);
   F(c->d_und_edge);
   F(c->d_owned_edges);
+  F(c->d_owned_vertices);
   F(c->d_all_edges);
   F(c->d_fast_scratch);
   F(c->d_onchip_items);
@@ -244,7 +245,8 @@ extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* ph
   // packed layouts
   ctx->site_off.assign(nv + 1, 0);
   ctx->msg_off.assign(ne + 1, 0);
-  std::vector<VDesc> vdesc(nv);
+  ctx->h_vdesc.assign(nv, VDesc());
+  std::vector<VDesc>& vdesc = ctx->h_vdesc;
   int64_t max_n = 1;
   int max_out = 1;
   for (int64_t v = 0; v < nv; ++v) {
@@ -276,13 +278,11 @@ extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* ph
   ctx->max_msg_elems = max_out;
 
   int rc;
-  if ((rc = upload(ctx, &ctx->d_vdesc, vdesc))) return rc;
   if ((rc = upload(ctx, &ctx->d_src, ctx->src))) return rc;
   if ((rc = upload(ctx, &ctx->d_slot, ctx->slot))) return rc;
   if ((rc = upload(ctx, &ctx->d_rev, ctx->rev))) return rc;
   if ((rc = upload(ctx, &ctx->d_msg_off, ctx->msg_off))) return rc;
   const size_t es = ctx->esize;
-  if ((rc = dev_alloc(ctx, (char**)&ctx->d_sites, (size_t)ctx->site_off[nv] * es))) return rc;
   for (int k = 0; k < 2; ++k) {
     if ((rc = dev_alloc(ctx, (char**)&ctx->d_msg[k], (size_t)ctx->msg_off[ne] * es))) return rc;
     BPX_CUDA(ctx, cudaMemset(ctx->d_msg[k], 0, std::max<size_t>(1, (size_t)ctx->msg_off[ne] * es)));
@@ -337,8 +337,65 @@ extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* ph
   ctx->owner.clear();
   ctx->rank = 0;
   ctx->nranks = 1;
+  ctx->dev_site_off.clear();
+  ctx->dev_site_total = 0;
   ctx->dims_set = true;
+  if ((rc = relayout_sites(ctx))) return rc;
   return rebuild_work_lists(ctx);
+}
+
+// Site tensors live on the rank that owns the vertex.  (Re)build the compact device layout for the current owner
+// map, move tensors that are already resident, refresh the device descriptors.
+int bpx::relayout_sites(bpx_ctx* ctx) {
+  const int64_t nv = ctx->nv;
+  const size_t es = ctx->esize;
+  std::vector<int64_t> old_off = ctx->dev_site_off;
+  void* old = ctx->d_sites;
+  ctx->dev_site_off.assign(nv + 1, -1);
+  int64_t total = 0;
+  for (int64_t v = 0; v < nv; ++v) {
+    const bool mine = ctx->owner.empty() || ctx->owner[v] == ctx->rank;
+    if (mine) {
+      ctx->dev_site_off[v] = total;
+      total += ctx->site_off[v + 1] - ctx->site_off[v];
+    }
+    ctx->h_vdesc[v].owned = mine ? 1 : 0;
+    ctx->h_vdesc[v].site_off = mine ? ctx->dev_site_off[v] : 0;
+  }
+  ctx->dev_site_total = total;
+  ctx->d_sites = nullptr;
+  int rc = dev_alloc(ctx, (char**)&ctx->d_sites, (size_t)total * es);
+  if (rc) {
+    ctx->d_sites = old;
+    return rc;
+  }
+  if (old && !old_off.empty()) {
+    // keep what is already resident (bpx_set_partition after an upload): copy runs of consecutive vertices
+    int64_t v = 0;
+    while (v < nv) {
+      if (ctx->dev_site_off[v] < 0 || old_off[v] < 0) {
+        ++v;
+        continue;
+      }
+      int64_t w = v;
+      while (w + 1 < nv && ctx->dev_site_off[w + 1] >= 0 && old_off[w + 1] >= 0 &&
+             old_off[w + 1] - old_off[v] == ctx->dev_site_off[w + 1] - ctx->dev_site_off[v])
+        ++w;
+      const size_t bytes = (size_t)(ctx->dev_site_off[w] - ctx->dev_site_off[v] + ctx->site_off[w + 1] - ctx->site_off[w]) * es;
+      BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_sites + (size_t)ctx->dev_site_off[v] * es, (char*)old + (size_t)old_off[v] * es, bytes,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+      v = w + 1;
+    }
+    BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (old) cudaFree(old);
+  if (ctx->d_vdesc) {
+    cudaFree(ctx->d_vdesc);
+    ctx->d_vdesc = nullptr;
+  }
+  if ((rc = upload(ctx, &ctx->d_vdesc, ctx->h_vdesc))) return rc;
+  ctx->sites_dirty = true;
+  return BPX_OK;
 }
 
 // (re)derive per-bucket vertex/edge lists restricted to the vertices this rank owns
@@ -375,6 +432,15 @@ int bpx::rebuild_work_lists(bpx_ctx* ctx) {
     int rcg = upload(ctx, &ctx->d_generic_edges, ge);
     if (rcg) return rcg;
   }
+  {
+    std::vector<int32_t> ov;
+    for (int64_t v = 0; v < ctx->nv; ++v)
+      if (ctx->owner.empty() || ctx->owner[v] == ctx->rank) ov.push_back((int32_t)v);
+    F(ctx->d_owned_vertices);
+    ctx->n_owned_vertices = (int64_t)ov.size();
+    int rcv = upload(ctx, &ctx->d_owned_vertices, ov);
+    if (rcv) return rcv;
+  }
   F(ctx->d_owned_edges);
   ctx->n_owned_edges = (int64_t)owned_edges.size();
   int rc = upload(ctx, &ctx->d_owned_edges, owned_edges);
@@ -398,6 +464,9 @@ extern "C" int64_t bpx_rev(const bpx_ctx* ctx, int64_t e) {
 extern "C" int64_t bpx_site_offset(const bpx_ctx* ctx, int64_t v) {
   return (ctx && ctx->dims_set && v >= 0 && v <= ctx->nv) ? ctx->site_off[v] : -1;
 }
+extern "C" int64_t bpx_site_device_offset(const bpx_ctx* ctx, int64_t v) {
+  return (ctx && ctx->dims_set && v >= 0 && v < ctx->nv) ? ctx->dev_site_off[v] : -1;
+}
 extern "C" int64_t bpx_message_offset(const bpx_ctx* ctx, int64_t e) {
   return (ctx && ctx->dims_set && e >= 0 && e <= ctx->ne) ? ctx->msg_off[e] : -1;
 }
@@ -417,8 +486,21 @@ extern "C" int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed) {
   REQUIRE(ctx, packed || ctx->site_off[ctx->nv] == 0, "bpx_set_site_tensors: NULL data");
   // a rank only needs the tensors it owns, but uploading all keeps offsets identical everywhere
   ctx->sites_dirty = true;
-  BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sites, packed, (size_t)ctx->site_off[ctx->nv] * ctx->esize, cudaMemcpyHostToDevice,
-                                ctx->stream));
+  // runs of consecutive owned vertices are contiguous on both sides (a single rank: one copy)
+  const int64_t nv = ctx->nv;
+  int64_t v = 0;
+  while (v < nv) {
+    if (ctx->dev_site_off[v] < 0) {
+      ++v;
+      continue;
+    }
+    int64_t w = v;
+    while (w + 1 < nv && ctx->dev_site_off[w + 1] >= 0) ++w;
+    const size_t bytes = (size_t)(ctx->site_off[w + 1] - ctx->site_off[v]) * ctx->esize;
+    BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_sites + (size_t)ctx->dev_site_off[v] * ctx->esize,
+                                  (const char*)packed + (size_t)ctx->site_off[v] * ctx->esize, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    v = w + 1;
+  }
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return BPX_OK;
 }
@@ -426,7 +508,8 @@ extern "C" int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed) {
 extern "C" int bpx_set_site_tensor(bpx_ctx* ctx, int64_t v, const void* data) {
   NEED_DIMS(ctx, "bpx_set_site_tensor");
   REQUIRE(ctx, v >= 0 && v < ctx->nv && data, "bpx_set_site_tensor: bad arguments");
-  const size_t off = (size_t)ctx->site_off[v] * ctx->esize, n = (size_t)(ctx->site_off[v + 1] - ctx->site_off[v]) * ctx->esize;
+  if (ctx->dev_site_off[v] < 0) return BPX_OK;  // not resident on this rank
+  const size_t off = (size_t)ctx->dev_site_off[v] * ctx->esize, n = (size_t)(ctx->site_off[v + 1] - ctx->site_off[v]) * ctx->esize;
   ctx->sites_dirty = true;
   BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_sites + off, data, n, cudaMemcpyHostToDevice, ctx->stream));
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -884,11 +967,14 @@ static int vertex_scalars_impl(bpx_ctx* ctx, const void* ops_packed, void* out) 
     }
     cudaMemcpyAsync(d_ops, ops_packed, (size_t)op_off[nv] * ctx->esize, cudaMemcpyHostToDevice, ctx->stream);
   }
-  GenericArgs g = generic_args(ctx, ctx->d_msg[ctx->cur], nullptr, nullptr, nv, 0);
+  // partitioned contexts hold (and know the in-messages of) their own vertices only: the others are reported as 0
+  BPX_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)nv * ctx->esize, ctx->stream));
+  GenericArgs g = generic_args(ctx, ctx->d_msg[ctx->cur], nullptr, ctx->nranks > 1 ? ctx->d_owned_vertices : nullptr,
+                               ctx->nranks > 1 ? ctx->n_owned_vertices : nv, 0);
   g.ops = d_ops;
   g.op_off = d_op_off;
   g.scalars_out = d_out;
-  const int grid = (int)std::min<int64_t>(nv, ctx->gen_grid);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(g.n_work, ctx->gen_grid));
   // the scalar kernel needs no output staging, but sharing the update kernel's geometry keeps it simple
   if (ctx->dtype == BPX_F64) {
     rc = set_smem(ctx, bp_vertex_scalar_generic<double>, ctx->gen_smem_bytes);

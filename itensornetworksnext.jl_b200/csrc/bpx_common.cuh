@@ -80,6 +80,8 @@ struct VDesc {
   int64_t n;                        // elements of A_v
   int32_t z;                        // degree
   int32_t d;                        // physical dimension (1 in SINGLE mode)
+  int32_t owned;                    // tensor resident on this rank (site_off valid)
+  int32_t pad_;
   int32_t dim[BPX_MAX_DEGREE];      // link dims, slot order
   int32_t out_edge[BPX_MAX_DEGREE]; // directed edge v -> w_i
   int32_t in_edge[BPX_MAX_DEGREE];  // directed edge w_i -> v  (the message that arrives on leg i)

@@ -46,7 +46,10 @@ struct bpx_ctx {
   std::vector<int32_t> src, dst, slot, rev, deg;
   std::vector<std::vector<int32_t>> out_edge;  // per vertex, slot order
   std::vector<int32_t> link_dim, phys_dim;
-  std::vector<int64_t> site_off, msg_off;
+  std::vector<int64_t> site_off, msg_off;  // packed HOST layouts (all vertices / edges)
+  std::vector<int64_t> dev_site_off;       // device layout: owned vertices only, compacted (-1: not resident)
+  int64_t dev_site_total = 0;
+  std::vector<bpx::VDesc> h_vdesc;
   int dtype = BPX_F64, mode = BPX_MODE_NORM, esize = 8;
   int64_t max_site_elems = 1, max_msg_elems = 1;
 
@@ -86,6 +89,8 @@ struct bpx_ctx {
   // partition
   int rank = 0, nranks = 1;
   std::vector<int32_t> owner;
+  int32_t* d_owned_vertices = nullptr;
+  int64_t n_owned_vertices = 0;
   int32_t* d_owned_edges = nullptr;
   int32_t* d_all_edges = nullptr;
   int64_t n_owned_edges = 0;
@@ -124,6 +129,7 @@ void set_error(bpx_ctx* ctx, const char* fmt, ...);
   } while (0)
 
 int rebuild_work_lists(bpx_ctx* ctx);
+int relayout_sites(bpx_ctx* ctx);  // (re)allocate the site buffer for the vertices this rank owns, keeping resident data
 int launch_generic_update(bpx_ctx* ctx, const void* msg_in, void* msg_out, const int32_t* d_work, int64_t n_work,
                           int normalize, unsigned long long* resmax);
 // specialised kernels (bpx_fast.cuh)

@@ -79,7 +79,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
       for (int32_t v : b.my_vertices) {
         onchip16::ItemDesc d;
         memset(&d, 0, sizeof(d));
-        d.site_off = ctx->site_off[v];
+        d.site_off = ctx->dev_site_off[v];
         d.pair_mode = b.z == 6 ? 1 : 0;
         for (int l = 0; l < 6; ++l) d.peer[l] = -1;
         for (int l = 0; l < b.z; ++l) {
@@ -116,7 +116,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
         for (int br = 0; br < 2; ++br) {
           sliced::ItemDesc d;
           memset(&d, 0, sizeof(d));
-          d.site_off = ctx->site_off[v];
+          d.site_off = ctx->dev_site_off[v];
           d.branch = br;
           for (int l = 0; l < 4; ++l) {
             const int32_t e = ctx->out_edge[v][l];
@@ -147,7 +147,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
   if (!group.empty()) need_image = true;
   if (need_image) {
     // private pre-swizzled image of the site tensors (same offsets as the canonical buffer), refreshed lazily
-    cudaError_t e = cudaMalloc(&ctx->d_sites_swz, std::max<size_t>(16, (size_t)ctx->site_off[ctx->nv] * ctx->esize));
+    cudaError_t e = cudaMalloc(&ctx->d_sites_swz, std::max<size_t>(16, (size_t)ctx->dev_site_total * ctx->esize));
     if (e != cudaSuccess) {
       set_error(ctx, "cudaMalloc(pre-swizzled site image) failed: %s", cudaGetErrorString(e));
       cudaGetLastError();
@@ -164,7 +164,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
     for (int32_t v : b.my_vertices) {
       onchip::ItemDesc d;
       memset(&d, 0, sizeof(d));
-      d.site_off = ctx->site_off[v];
+      d.site_off = ctx->dev_site_off[v];
       d.z = b.z;
       for (int i = 0; i < b.z; ++i) {
         const int32_t e = ctx->out_edge[v][i];

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) bp_vertex_scalar_generic(GenericArgs g) {
     if (threadIdx.x == 0) {
       T s = E::zero();
       for (int i = 0; i < nwarps; ++i) s = E::add(s, red[i]);
-      reinterpret_cast<T*>(g.scalars_out)[w] = s;
+      reinterpret_cast<T*>(g.scalars_out)[v] = s;  // indexed by vertex
     }
   }
 }
@@ -306,6 +306,7 @@ __device__ __forceinline__ double randn_at_dev(unsigned long long seed, unsigned
 __global__ void fill_sites_randn(const VDesc* __restrict__ vdesc, int64_t nv, unsigned long long seed, int doubles_per_elem,
                                  double* __restrict__ sites) {
   for (int64_t v = blockIdx.y; v < nv; v += gridDim.y) {
+    if (!vdesc[v].owned) continue;
     const int64_t n = vdesc[v].n * doubles_per_elem;
     const double scale = (doubles_per_elem == 2 ? 0.70710678118654752440 : 1.0) / sqrt((double)vdesc[v].n);
     double* dst = sites + vdesc[v].site_off * doubles_per_elem;

@@ -219,6 +219,10 @@ extern "C" int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32
     ctx->sweep_id = 0;
     ctx->barrier_id = 0;
   }
+  {
+    int rc = bpx::relayout_sites(ctx);  // site tensors are stored on the owning rank only
+    if (rc) return rc;
+  }
   return bpx::rebuild_work_lists(ctx);
 }
 

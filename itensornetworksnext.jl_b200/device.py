@@ -132,8 +132,11 @@ class BPXContext:
         n = int(self.site_off[v + 1] - self.site_off[v])
         out = np.empty(n, dtype=self.dtype)
         ptr = self.lib.bpx_device_site_tensors(self.h)
+        dev_off = self.lib.bpx_site_device_offset(self.h, int(v))
+        if dev_off < 0:
+            raise KeyError(f"site tensor {v} is not resident on this rank")
         cudart = C_.CDLL("libcudart.so")
-        rc = cudart.cudaMemcpy(out.ctypes.data_as(C_.c_void_p), C_.c_void_p(ptr + int(self.site_off[v]) * self.dtype.itemsize),
+        rc = cudart.cudaMemcpy(out.ctypes.data_as(C_.c_void_p), C_.c_void_p(ptr + int(dev_off) * self.dtype.itemsize),
                                C_.c_size_t(out.nbytes), 2)
         if rc != 0:
             raise RuntimeError(f"cudaMemcpy failed ({rc})")

@@ -149,6 +149,22 @@ def _worker_gpu(rank, world, port, nsweeps, q):
     got = ctx.get_messages()
     res_tol, done_tol = ctx.sweep(50, 1e-3)  # convergence test on the GLOBAL residual
     pl = partition.plan(p.ga.src, p.ga.dst, owner, rank)
+    # site tensors live on the owning rank only; vertex scalars are reported for owned vertices
+    vs = ctx.vertex_scalars()
+    final = ctx.get_messages()
+    foreign = next(v for v in range(p.ga.nv) if owner[v] != rank)
+    try:
+        ctx.get_site_tensor(foreign)
+        resident_foreign = True
+    except KeyError:
+        resident_foreign = False
+    assert not resident_foreign
+    assert np.allclose(ctx.get_site_tensor(pl.owned_vertices[0]), p.tensors[pl.owned_vertices[0]].ravel(order="F"))
+    op = o.make_problem(p.ga, p.tensors, "norm")
+    for v in pl.owned_vertices[:6]:
+        # incoming messages of an owned vertex are valid on this rank (own edges + received cut edges)
+        assert np.isclose(vs[v], o.vertex_scalar(op, final, v), rtol=1e-10)
+    assert all(vs[v] == 0 for v in range(p.ga.nv) if owner[v] != rank)
     need = set(pl.owned_edges) | {e for es in pl.recv.values() for e in es}
     q.put((rank, {e: got[e] for e in need}, hist, (res_tol, done_tol), ctx.buckets()))
     dist.barrier()
