@@ -6,6 +6,7 @@
 #include "bpx_onchip.cuh"
 #include "bpx_sliced.cuh"
 #include "bpx_onchip16.cuh"
+#include "bpx_onchip16c.cuh"
 
 namespace bpx {
 
@@ -13,6 +14,9 @@ inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
   if (kernel == BPX_KERNEL_GENERIC) return true;
   if (ctx->mode != BPX_MODE_NORM) return false;
   if (kernel == BPX_KERNEL_ONCHIP) {
+    // ComplexF64: chi = 16, degree 1..3, any physical dimension (bpx_onchip16c.cuh)
+    if (ctx->dtype == BPX_C64)
+      return b.chi == 16 && b.z >= 1 && b.z <= 3 && b.d >= 1 && (size_t)ctx->max_smem_optin >= onchip16c::SMEM_BYTES16C;
     if (ctx->dtype != BPX_F64 || b.d != 2) return false;
     if (b.z >= 2 && b.z <= 4 && b.chi == 8) return (size_t)ctx->max_smem_optin >= onchip::SMEM_BYTES;
     // 16-wide on-chip kernel: degree 3 / chi 16, or degree 6 / chi 4 with legs paired into super-legs
@@ -46,7 +50,8 @@ inline int fast_prepare(bpx_ctx* ctx) {
   int generic_leader = -1;
   for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
     ctx->buckets[i].leader = i;
-    if (ctx->buckets[i].kernel == BPX_KERNEL_ONCHIP && ctx->buckets[i].chi == 8 && !ctx->buckets[i].my_vertices.empty()) group.push_back(i);
+    if (ctx->dtype == BPX_F64 && ctx->buckets[i].kernel == BPX_KERNEL_ONCHIP && ctx->buckets[i].chi == 8 && !ctx->buckets[i].my_vertices.empty())
+      group.push_back(i);
     if (ctx->buckets[i].kernel == BPX_KERNEL_GENERIC && !ctx->buckets[i].my_edges.empty()) {
       if (generic_leader < 0) generic_leader = i;
       ctx->buckets[i].leader = generic_leader;  // all generic buckets share one launch
@@ -67,13 +72,107 @@ inline int fast_prepare(bpx_ctx* ctx) {
     ctx->d_onchip16_items = nullptr;
   }
   ctx->n_onchip16_items = 0;
+  if (ctx->d_onchip16c_items) {
+    cudaFree(ctx->d_onchip16c_items);
+    ctx->d_onchip16c_items = nullptr;
+  }
+  ctx->n_onchip16c_slots = 0;
+  ctx->onchip16c_grid = 0;
+  if (ctx->dtype == BPX_C64) {
+    // ---- complex chi = 16 buckets (degree 1..3): one launch; items scheduled onto the CTAs here (LPT), laid out as rounds ----
+    std::vector<onchip16c::ItemDesc> its;
+    std::vector<double> cost;
+    int leader = -1;
+    for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
+      Bucket& b = ctx->buckets[i];
+      if (b.kernel != BPX_KERNEL_ONCHIP || b.my_vertices.empty()) continue;
+      if (leader < 0) leader = i;
+      b.leader = leader;
+      for (int32_t v : b.my_vertices) {
+        auto edge_of = [&](onchip16c::ItemDesc& d, int o, int l) {
+          const int32_t e = ctx->out_edge[v][l];
+          d.out_edge[o] = e;
+          d.out_off[o] = ctx->msg_off[e];
+          d.peer[o] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
+        };
+        auto in_of = [&](int l) { return ctx->msg_off[ctx->rev[ctx->out_edge[v][l]]]; };
+        onchip16c::ItemDesc d;
+        memset(&d, 0, sizeof(d));
+        d.site_off = 2 * ctx->dev_site_off[v];
+        d.canon_off = ctx->dev_site_off[v];
+        d.d = b.d;
+        d.peer[0] = d.peer[1] = -1;
+        d.first = 1;
+        if (b.z == 3) {
+          // one item per output leg; (first, second) absorbed message: out2 (M0, M1), out1 (M0, M2), out0 (M2, M1)
+          static const int first_leg[3] = {2, 0, 0}, second_leg[3] = {1, 2, 1};
+          for (int leg = 2; leg >= 0; --leg) {
+            d.kind = 0;
+            d.leg = leg;
+            d.in_off[0] = in_of(first_leg[leg]);
+            d.in_off[1] = in_of(second_leg[leg]);
+            edge_of(d, 0, leg);
+            its.push_back(d);
+            cost.push_back(16000.0 * b.d + 3000.0);
+            d.first = 0;
+          }
+        } else if (b.z == 2) {
+          d.kind = 1;
+          d.in_off[0] = in_of(0);
+          d.in_off[1] = in_of(1);
+          edge_of(d, 0, 0);
+          edge_of(d, 1, 1);
+          its.push_back(d);
+          cost.push_back(3000.0 * b.d + 3000.0);
+        } else {
+          d.kind = 2;
+          edge_of(d, 0, 0);
+          its.push_back(d);
+          cost.push_back(3000.0);
+        }
+      }
+    }
+    if (!its.empty()) {
+      const int G = std::min<int>((int)its.size(), ctx->num_sms);
+      std::vector<int> order(its.size());
+      for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+      std::vector<std::vector<int>> per_cta(G);
+      std::vector<double> load(G, 0.0);
+      for (int i : order) {  // longest processing time first onto the least loaded CTA
+        const int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        per_cta[c].push_back(i);
+        load[c] += cost[i];
+      }
+      size_t rounds = 0;
+      for (auto& l : per_cta) rounds = std::max(rounds, l.size());
+      onchip16c::ItemDesc null_item;
+      memset(&null_item, 0, sizeof(null_item));
+      null_item.kind = -1;
+      std::vector<onchip16c::ItemDesc> slots(rounds * G, null_item);
+      for (int c = 0; c < G; ++c)
+        for (size_t r = 0; r < per_cta[c].size(); ++r) slots[r * G + c] = its[per_cta[c][r]];
+      ctx->n_onchip16c_slots = (int)slots.size();
+      ctx->onchip16c_grid = G;
+      cudaError_t e = cudaMalloc((void**)&ctx->d_onchip16c_items, slots.size() * sizeof(onchip16c::ItemDesc));
+      if (e != cudaSuccess) {
+        set_error(ctx, "cudaMalloc(complex on-chip items) failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return BPX_ERR_ALLOC;
+      }
+      BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip16c_items, slots.data(), slots.size() * sizeof(onchip16c::ItemDesc), cudaMemcpyHostToDevice));
+      BPX_CUDA(ctx, cudaFuncSetAttribute(onchip16c::bp_update_onchip_c16c, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)onchip16c::SMEM_BYTES16C));
+      need_image = true;
+    }
+  }
   // ---- 16-wide ON-CHIP buckets (degree 3 / chi 16; degree 6 / chi 4 in pair mode): one launch ----
   {
     std::vector<onchip16::ItemDesc> it16;
     int leader16 = -1;
     for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
       Bucket& b = ctx->buckets[i];
-      if (b.kernel != BPX_KERNEL_ONCHIP || b.chi == 8 || b.my_vertices.empty()) continue;
+      if (ctx->dtype != BPX_F64 || b.kernel != BPX_KERNEL_ONCHIP || b.chi == 8 || b.my_vertices.empty()) continue;
       if (leader16 < 0) leader16 = i;
       b.leader = leader16;
       for (int32_t v : b.my_vertices) {
@@ -209,6 +308,12 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
   }
+  if (ctx->d_sites_swz && ctx->n_onchip16c_slots > 0) {
+    onchip16c::swizzle_sites_c16<<<std::min(ctx->n_onchip16c_slots, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
+        (const onchip16c::ItemDesc*)ctx->d_onchip16c_items, ctx->n_onchip16c_slots, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+  }
   if (ctx->d_sites_swz && ctx->n_sliced_items > 0) {
     sliced::swizzle_sites16<<<std::min(ctx->n_sliced_items, 8 * ctx->num_sms), 512, 0, ctx->stream>>>(
         (const sliced::ItemDesc*)ctx->d_sliced_items, ctx->n_sliced_items, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
@@ -220,6 +325,22 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
 }
 
 inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize) {
+  if (b.kernel == BPX_KERNEL_ONCHIP && ctx->dtype == BPX_C64) {
+    onchip16c::Args k;
+    k.items = (const onchip16c::ItemDesc*)ctx->d_onchip16c_items;
+    k.n_slots = ctx->n_onchip16c_slots;
+    k.sites = (const double*)ctx->d_sites_swz;
+    k.msg_in = (const double*)msg_in;
+    k.msg_out = (double*)msg_out;
+    k.resmax = ctx->cur_slot;
+    k.normalize = normalize;
+    k.peer = ctx->peer_args;
+    if (ctx->onchip16c_grid == 0) return BPX_OK;
+    onchip16c::bp_update_onchip_c16c<<<ctx->onchip16c_grid, onchip16c::NTHREADSC, onchip16c::SMEM_BYTES16C, ctx->stream>>>(k);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+    return BPX_OK;
+  }
   if (b.kernel == BPX_KERNEL_ONCHIP && b.chi != 8) {
     onchip16::Args k;
     k.items = (const onchip16::ItemDesc*)ctx->d_onchip16_items;

@@ -1,0 +1,377 @@
+// BPX_KERNEL_ONCHIP, ComplexF64 variant: chi = 16, degree 1..3, any physical dimension d -- BASELINE config 3
+// (heavy-hex lattice, mixed degree 2 / 3 buckets).
+//
+// A complex tensor A[s, b0, b1, b2] is processed one PHYSICAL SLICE at a time: the slice A_s[(re, im), b0, b1, b2]
+// has exactly the shape of the real kernels' [s, b0, b1, b2] tile (8192 doubles = 64 KiB, layout L_A3 of
+// bpx_sliced.cuh, the 16-byte chunk now holds (re, im) of one element instead of (s = 0, s = 1)), and the update is
+// a sum over slices:   out[b', b] = sum_s  sum_{..} conj(A_s[b', a'..]) (A_s absorbed with the incoming messages).
+// So one LDS.128 still feeds two DMMA operands; a complex MAC is four real DMMA issues
+//     Dr += Mr·Br + Mi·(-Bi),   Di += Mi·Br + Mr·Bi        (absorption)
+//     acc_r += Ar·Tr + Ai·Ti,   acc_i += Ar·Ti + (-Ai)·Tr   (closure with conj(A))
+// with the sign flips done on the integer pipe (DMMA has no negate modifier), and the register chaining of
+// bpx_onchip.cuh (accumulator fragment = operand fragment of the next GEMM) holds per real / imaginary component.
+//
+// Work items (cfg3 has 127 vertices for 148 SMs, so the sweep is ONE wave and its length is the longest item):
+//   kind 0  degree 3, ONE output leg:  X = A_s·M_first (64 KiB, shared memory) -> absorb M_second, close the out leg.
+//           Per-output items (3 GEMM units each) instead of the per-vertex leave-one-out tree (8 units): the
+//           critical path is what counts here, and 108 + 89 + 2 items fill the machine.
+//   kind 1  degree 2 vertex, both outputs: slices are 4 KiB (layout L_Z2), four warps = (output, half tile).
+//   kind 2  degree 1 vertex: out[b', b] = sum_s A[s, b] conj(A[s, b']), one element per thread.
+// The host assigns items to CTAs with a longest-processing-time schedule and lays them out as rounds
+// (slot r * grid + cta, padded with null items), so the kernel needs no atomics.
+// Slices stream through a 2-slot TMA ring (full mbarriers; the last warp to release a slot refills it).
+#pragma once
+#include "bpx_sliced.cuh"
+
+namespace bpx {
+namespace onchip16c {
+
+using namespace sliced;  // pos<>, dmma, mbarrier / TMA helpers, CHI, MSG
+
+constexpr int NCWC = 8;
+constexpr int NCTC = NCWC * 32;
+constexpr int NTHREADSC = NCTC;  // no producer warp: see the slice ring in the kernel
+constexpr int NSL3 = 8192, NSL2 = 512, NSL1 = 32;  // doubles per physical slice, by degree
+constexpr int CMSG = 2 * MSG;                      // doubles per complex 16x16 message
+
+struct ItemDesc {
+  int64_t site_off;   // DOUBLES, into the private image (slice s at + s * NSL)
+  int64_t in_off[2];  // complex elements.  kind 0: (first absorbed, second absorbed); kind 1: (M0, M1)
+  int64_t out_off[2];
+  int32_t out_edge[2];
+  int32_t peer[2];
+  int32_t kind;       // -1: null (padding of the round layout)
+  int32_t leg;        // kind 0: output leg
+  int32_t d;          // physical dimension = number of slices
+  int32_t first;      // this item swizzles the vertex's tensor (one item per vertex)
+  int64_t canon_off;  // complex elements, into the canonical site buffer
+};
+
+struct Args {
+  const ItemDesc* items;
+  int n_slots;          // rounds * grid
+  const double* sites;  // private image
+  const double* msg_in;
+  double* msg_out;
+  unsigned long long* resmax;
+  int normalize;
+  PeerArgs peer;
+};
+
+__device__ __forceinline__ double neg(double x) { return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x)); }
+
+struct CFrag {  // M[g + 8 mt, t + 4 j], real and imaginary parts
+  double r[2][4], i[2][4];
+};
+__device__ __forceinline__ CFrag load_cfrag(const double* __restrict__ M, int g, int t) {
+  CFrag f;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double2 v = *reinterpret_cast<const double2*>(M + 2 * ((g + 8 * mt) + CHI * (t + 4 * j)));
+      f.r[mt][j] = v.x;
+      f.i[mt][j] = v.y;
+    }
+  return f;
+}
+
+// dst[x', y, c] = sum_x M[x', x] src[x, y, c]  (complex; one column c of the spectator leg; dst != src)
+template <int X, int Y>
+__device__ __forceinline__ void absorb_one16c(const double* src, double* dst, uint32_t base, const CFrag& m, int g, int t) {
+  double2 b[4][2];
+  double nbi[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      b[j][h] = *reinterpret_cast<const double2*>(src + (base ^ pos<L_A3>(X, t + 4 * j) ^ pos<L_A3>(Y, g + 8 * h)));
+      nbi[j][h] = neg(b[j][h].y);
+    }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double p0 = 0, p1 = 0, q0 = 0, q1 = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dmma(p0, p1, m.r[mt][j], b[j][h].x);
+        dmma(q0, q1, m.i[mt][j], b[j][h].x);
+        dmma(p0, p1, m.i[mt][j], nbi[j][h]);
+        dmma(q0, q1, m.r[mt][j], b[j][h].y);
+      }
+      const uint32_t a = base ^ pos<L_A3>(X, g + 8 * mt);
+      *reinterpret_cast<double2*>(dst + (a ^ pos<L_A3>(Y, 2 * t + 8 * h))) = make_double2(p0, q0);
+      *reinterpret_cast<double2*>(dst + (a ^ pos<L_A3>(Y, 2 * t + 1 + 8 * h))) = make_double2(p1, q1);
+    }
+}
+
+// acc[v', v] += sum_{u'} conj(A[u', v']) * ( sum_u M[u', u] P[u, v] )   (complex; HSEL >= 0: only the v-tile HSEL)
+template <int LAY, int U, int V, int HSEL>
+__device__ __forceinline__ void absorb_close16c(const double* P, const double* A, uint32_t base, const CFrag& m, int g, int t,
+                                                double (&accr)[2][2][2], double (&acci)[2][2][2]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (HSEL >= 0 && h != HSEL) continue;
+    double2 p[4];
+    double npi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p[j] = *reinterpret_cast<const double2*>(P + (base ^ pos<LAY>(U, t + 4 * j) ^ pos<LAY>(V, g + 8 * h)));
+      npi[j] = neg(p[j].y);
+    }
+    double tr[2][2], ti[2][2];  // T[v = g + 8h, u' = 2t + i + 8 nt]
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      tr[nt][0] = tr[nt][1] = ti[nt][0] = ti[nt][1] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dmma(tr[nt][0], tr[nt][1], p[j].x, m.r[nt][j]);
+        dmma(ti[nt][0], ti[nt][1], p[j].x, m.i[nt][j]);
+        dmma(tr[nt][0], tr[nt][1], npi[j], m.i[nt][j]);
+        dmma(ti[nt][0], ti[nt][1], p[j].y, m.r[nt][j]);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double2 a = *reinterpret_cast<const double2*>(A + (base ^ pos<LAY>(U, 2 * t + i + 8 * nt) ^ pos<LAY>(V, g + 8 * mt)));
+          const double nai = neg(a.y);
+          dmma(accr[mt][h][0], accr[mt][h][1], a.x, tr[nt][i]);
+          dmma(acci[mt][h][0], acci[mt][h][1], a.x, ti[nt][i]);
+          dmma(accr[mt][h][0], accr[mt][h][1], a.y, ti[nt][i]);
+          dmma(acci[mt][h][0], acci[mt][h][1], nai, tr[nt][i]);
+        }
+  }
+}
+
+// shared memory (doubles): slot[2][NSL3] | X[NSL3] (aliased by red[NCWC][CMSG]) | raw[2][CMSG] | 2 mbarriers | 2 counters
+constexpr size_t SMEM_DOUBLES16C = (size_t)3 * NSL3 + 2 * CMSG + 4;
+constexpr size_t SMEM_BYTES16C = SMEM_DOUBLES16C * sizeof(double);
+enum { BAR_CC = 1 };
+
+// canonical A_v[s, b0..] (complex, column-major) -> private image: d slices [(re, im), b..] in L_A3 / L_Z2 / plain order
+__global__ void swizzle_sites_c16(const ItemDesc* items, int n_slots, const double* __restrict__ src, double* __restrict__ dst) {
+  for (int it = blockIdx.x; it < n_slots; it += gridDim.x) {
+    const ItemDesc d = items[it];
+    if (d.kind < 0 || !d.first) continue;
+    const int z = d.kind == 0 ? 3 : (d.kind == 1 ? 2 : 1);
+    const int nsl = d.kind == 0 ? NSL3 : (d.kind == 1 ? NSL2 : NSL1);
+    const int nb = nsl / 2;  // complex elements per slice
+    const double* s0 = src + 2 * d.canon_off;
+    double* d0 = dst + d.site_off;
+    for (int c = threadIdx.x; c < nb * d.d; c += blockDim.x) {
+      const int s = c % d.d, b = c / d.d;
+      uint32_t p;
+      if (z == 3)
+        p = pos<L_A3>(0, b & 15) ^ pos<L_A3>(1, (b >> 4) & 15) ^ pos<L_A3>(2, (b >> 8) & 15);
+      else if (z == 2)
+        p = pos<L_Z2>(0, b & 15) ^ pos<L_Z2>(1, (b >> 4) & 15);
+      else
+        p = 2 * b;
+      *reinterpret_cast<double2*>(d0 + (size_t)s * nsl + p) = *reinterpret_cast<const double2*>(s0 + 2 * (size_t)c);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_partial(double* mine, const double (&accr)[2][2][2], const double (&acci)[2][2][2], int g, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int el = (g + 8 * mt) + CHI * (2 * t + i + 8 * h);  // out[v', v] at v' + 16 v
+        *reinterpret_cast<double2*>(mine + 2 * el) = make_double2(accr[mt][h][i], acci[mt][h][i]);
+      }
+}
+
+// position of the next physical slice to load, tracked identically by every warp
+struct Cursor {
+  int idx, s;
+};
+
+__global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
+  extern __shared__ __align__(128) double smem[];
+  double* Xbuf = smem + 2 * NSL3;
+  double* red = Xbuf;  // alias: X is dead when the partial tiles are published
+  double* raw = smem + 3 * NSL3;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(raw + 2 * CMSG);  // full[2]
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(mbar + 2);  // warps that released slot 0 / 1
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int G = gridDim.x;
+
+  // ---- slice ring without a producer warp (8 warps = 2 per scheduler, so every thread may hold 255 registers):
+  // the LAST warp to release a slot refills it with the slice two units ahead ----
+  auto valid = [&](const Cursor& c) { return c.idx < k.n_slots && k.items[c.idx].kind >= 0; };
+  auto issue = [&](const Cursor& c, int sl) {  // one thread
+    const ItemDesc* d = k.items + c.idx;
+    const int nsl = d->kind == 0 ? NSL3 : (d->kind == 1 ? NSL2 : NSL1);
+    mbar_expect_tx(&mbar[sl], nsl * 8);
+    tma_bulk_g2s(smem + sl * NSL3, k.sites + d->site_off + (size_t)c.s * nsl, nsl * 8, &mbar[sl]);
+  };
+  auto advance = [&](Cursor& c) {
+    if (!valid(c)) return;
+    if (++c.s >= k.items[c.idx].d) {
+      c.s = 0;
+      c.idx += G;
+    }
+  };
+  Cursor cur{(int)blockIdx.x, 0};
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    cnt[0] = cnt[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    Cursor c = cur;
+    for (int sl = 0; sl < 2; ++sl) {
+      if (valid(c)) issue(c, sl);
+      advance(c);
+    }
+  }
+  advance(cur);
+  advance(cur);  // -> unit 2
+  // the message fragments below may have been written by peers: wait for their posts of the previous sweep
+  if (warp == 0) peer_gate(k.peer, lane);
+  __syncthreads();
+
+  auto release = [&](int sl) {  // warp-uniform; called when the warp is done with the slice in slot sl
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(&cnt[sl], 1u) == NCWC - 1) {
+        atomicExch(&cnt[sl], 0u);
+        __threadfence_block();
+        if (valid(cur)) {
+          fence_proxy_async();
+          issue(cur, sl);
+        }
+      }
+    }
+    advance(cur);
+  };
+
+  uint32_t u = 0;
+  for (int idx = blockIdx.x; idx < k.n_slots; idx += G) {
+    const ItemDesc* d = k.items + idx;
+    const int kind = d->kind;
+    if (kind < 0) break;
+    const int nd = d->d;
+    int nout = 1;
+    if (kind == 0) {
+      const int leg = d->leg;
+      const CFrag m1 = load_cfrag(k.msg_in + 2 * d->in_off[0], g, t);
+      const CFrag m2 = load_cfrag(k.msg_in + 2 * d->in_off[1], g, t);
+      double accr[2][2][2], acci[2][2][2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) accr[a][b][0] = accr[a][b][1] = acci[a][b][0] = acci[a][b][1] = 0.0;
+      for (int s = 0; s < nd; ++s, ++u) {
+        const int sl = u & 1;
+        mbar_wait(&mbar[sl], (u >> 1) & 1);
+        const double* A = smem + sl * NSL3;
+        // X = A_s · M_first (columns: a spectator leg), then absorb M_second and close the output leg
+        if (leg == 0) {
+#pragma unroll 1
+          for (int c = warp; c < 16; c += NCWC) absorb_one16c<2, 1>(A, Xbuf, pos<L_A3>(0, c), m1, g, t);
+        } else {
+#pragma unroll 1
+          for (int c = warp; c < 16; c += NCWC) absorb_one16c<0, 1>(A, Xbuf, pos<L_A3>(2, c), m1, g, t);
+        }
+        onchip::bar_sync(BAR_CC, NCTC);
+        if (leg == 0) {
+#pragma unroll 1
+          for (int c = warp; c < 16; c += NCWC) absorb_close16c<L_A3, 1, 0, -1>(Xbuf, A, pos<L_A3>(2, c), m2, g, t, accr, acci);
+        } else if (leg == 1) {
+#pragma unroll 1
+          for (int c = warp; c < 16; c += NCWC) absorb_close16c<L_A3, 2, 1, -1>(Xbuf, A, pos<L_A3>(0, c), m2, g, t, accr, acci);
+        } else {
+#pragma unroll 1
+          for (int c = warp; c < 16; c += NCWC) absorb_close16c<L_A3, 1, 2, -1>(Xbuf, A, pos<L_A3>(0, c), m2, g, t, accr, acci);
+        }
+        release(sl);
+        onchip::bar_sync(BAR_CC, NCTC);  // X is rewritten by the next slice / aliased by red
+      }
+      store_partial(red + warp * CMSG, accr, acci, g, t);
+      onchip::bar_sync(BAR_CC, NCTC);
+      {
+        const int el = threadIdx.x;
+        double sr = 0, si = 0;
+#pragma unroll
+        for (int w = 0; w < NCWC; ++w) {
+          const double2 v = *reinterpret_cast<const double2*>(red + w * CMSG + 2 * el);
+          sr += v.x;
+          si += v.y;
+        }
+        *reinterpret_cast<double2*>(raw + 2 * el) = make_double2(sr, si);
+      }
+    } else if (kind == 1) {
+      nout = 2;
+      // warps 0..3 = (output o, half tile hs): out0 absorbs leg 1 / closes leg 0 (M1), out1 absorbs leg 0 / closes leg 1 (M0)
+      const int o = warp & 1, hs = (warp >> 1) & 1;
+      double accr[2][2][2], acci[2][2][2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) accr[a][b][0] = accr[a][b][1] = acci[a][b][0] = acci[a][b][1] = 0.0;
+      CFrag m;
+      if (warp < 4) m = load_cfrag(k.msg_in + 2 * d->in_off[1 - o], g, t);
+      for (int s = 0; s < nd; ++s, ++u) {
+        const int sl = u & 1;
+        mbar_wait(&mbar[sl], (u >> 1) & 1);
+        const double* A = smem + sl * NSL3;
+        if (warp < 4) {
+          if (o == 0) {
+            if (hs == 0) absorb_close16c<L_Z2, 1, 0, 0>(A, A, 0, m, g, t, accr, acci);
+            else absorb_close16c<L_Z2, 1, 0, 1>(A, A, 0, m, g, t, accr, acci);
+          } else {
+            if (hs == 0) absorb_close16c<L_Z2, 0, 1, 0>(A, A, 0, m, g, t, accr, acci);
+            else absorb_close16c<L_Z2, 0, 1, 1>(A, A, 0, m, g, t, accr, acci);
+          }
+        }
+        release(sl);
+      }
+      if (warp < 4) store_partial(red + warp * CMSG, accr, acci, g, t);
+      onchip::bar_sync(BAR_CC, NCTC);
+      {
+        const int el = threadIdx.x;
+#pragma unroll
+        for (int oo = 0; oo < 2; ++oo) {
+          const double2 v0 = *reinterpret_cast<const double2*>(red + oo * CMSG + 2 * el);
+          const double2 v1 = *reinterpret_cast<const double2*>(red + (oo + 2) * CMSG + 2 * el);
+          *reinterpret_cast<double2*>(raw + oo * CMSG + 2 * el) = make_double2(v0.x + v1.x, v0.y + v1.y);
+        }
+      }
+    } else {
+      // degree 1: out[b', b] = sum_s A[s, b] conj(A[s, b']); thread el = b' + 16 b
+      const int bp = threadIdx.x & 15, b = threadIdx.x >> 4;
+      double sr = 0, si = 0;
+      for (int s = 0; s < nd; ++s, ++u) {
+        const int sl = u & 1;
+        mbar_wait(&mbar[sl], (u >> 1) & 1);
+        const double* A = smem + sl * NSL3;
+        const double2 x = *reinterpret_cast<const double2*>(A + 2 * b), y = *reinterpret_cast<const double2*>(A + 2 * bp);
+        sr += x.x * y.x + x.y * y.y;
+        si += x.y * y.x - x.x * y.y;
+        release(sl);
+      }
+      onchip::bar_sync(BAR_CC, NCTC);  // the previous item's epilogue is done with raw
+      *reinterpret_cast<double2*>(raw + 2 * threadIdx.x) = make_double2(sr, si);
+    }
+    onchip::bar_sync(BAR_CC, NCTC);
+    if (warp < nout) {
+      const int64_t off = d->out_off[warp];
+      c64* peer_m = (k.peer.nranks > 1 && d->peer[warp] >= 0) ? reinterpret_cast<c64*>(k.peer.peer_out[d->peer[warp]]) + off : nullptr;
+      warp_epilogue<c64>(reinterpret_cast<const c64*>(raw + warp * CMSG), reinterpret_cast<const c64*>(k.msg_in) + off,
+                         reinterpret_cast<c64*>(k.msg_out) + off, MSG, k.normalize, nullptr, lane, k.resmax, peer_m);
+    }
+  }
+  peer_post_when_last(k.peer, warp < 2);  // warps 0 and 1 run the epilogues
+}
+
+}  // namespace onchip16c
+}  // namespace bpx

@@ -59,7 +59,8 @@ __device__ __host__ __forceinline__ uint32_t global_pos(int leg, uint32_t a) {
 enum { L_A3 = 0,   // full a3-slice: global bits 0..12
        L_A0 = 1,   // full a0-slice: (a3 << 9) | global bits 0..8
        L_A0H = 2,  // a0-slice, a1[3] fixed: (a3 << 8) | global bits 0..7
-       L_A3H = 3   // a3-slice, a2[3] fixed: (a0 << 8) | (a1[3] << 7) | global bits 0..6
+       L_A3H = 3,  // a3-slice, a2[3] fixed: (a0 << 8) | (a1[3] << 7) | global bits 0..6
+       L_Z2 = 4    // two legs only (512 doubles): bit 0 | 1-3 bank group (^ a1[3] on bit 1) | 4 a1[2] | 5-8 a0
 };
 template <int LAY>
 __device__ __forceinline__ uint32_t pos(int leg, uint32_t a) {
@@ -85,12 +86,18 @@ __device__ __forceinline__ uint32_t pos(int leg, uint32_t a) {
       case 2: return g | ((a >> 1) << 5);
       default: return g;
     }
-  } else {
+  } else if (LAY == L_A3H) {
     switch (leg) {
       case 0: return g | (a << 8);
       case 1: return g | (((a >> 2) & 1u) << 4) | (((a >> 3) & 1u) << 7);
       case 2: return g | (((a >> 1) & 3u) << 5);
       default: return g;
+    }
+  } else {
+    switch (leg) {
+      case 0: return g | (a << 5);
+      case 1: return g | (((a >> 2) & 1u) << 4) | (((a >> 3) & 1u) << 1);
+      default: return 0;
     }
   }
 }

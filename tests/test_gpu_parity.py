@@ -78,6 +78,25 @@ def test_cfg5_bucket_chi16_reduced(oracle, kernel):
     check_sweeps(oracle, p.ga, p.dtype, "norm", p.phys_dim, p.link_dim, p.tensors, p.messages, 2, kernel)
 
 
+def test_complex_chi16_kernel_mixed_physical_dims(oracle):
+    # the ComplexF64 chi = 16 on-chip kernel streams one physical slice at a time: d = 1, 2, 3 and degrees 1..3 together
+    g = graphs.named_comb_tree((3, 2))
+    g.add_edge((1, 2), (2, 2))  # a loop, and degree-3 vertices
+    ga = graphs.graph_arrays(g)
+    rng = np.random.default_rng(11)
+    phys = [1 + (v % 3) for v in range(ga.nv)]
+    link_dim = [16] * ga.ne
+    tensors = []
+    for v in range(ga.nv):
+        z = ga.row_ptr[v + 1] - ga.row_ptr[v]
+        tensors.append(randn(rng, np.complex128, (phys[v], *([16] * z))) / np.sqrt(16.0**z))
+    msgs = positive_messages(ga, link_dim, np.complex128, rng)
+    buckets = check_sweeps(oracle, ga, np.complex128, "norm", phys, link_dim, tensors, msgs, 3)
+    assert {b["degree"] for b in buckets} == {1, 2, 3}
+    assert all(b["kernel"] == _lib.BPX_KERNEL_ONCHIP for b in buckets)
+    check_sweeps(oracle, ga, np.complex128, "norm", phys, link_dim, tensors, msgs, 2, normalize=False)
+
+
 # ---- edge cases ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_ragged_link_dims_and_degree_one(oracle, dtype):
