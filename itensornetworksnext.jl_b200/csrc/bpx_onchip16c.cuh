@@ -189,6 +189,63 @@ __device__ __forceinline__ void store_partial(double* mine, const double (&accr)
       }
 }
 
+// Block-wide epilogue (one element per thread and output): sum-normalise (beliefpropagation.jl:248-253), residual term
+// 1 - |<old^, new^>|^2 (beliefpropagation.jl:261-267), store (+ peer store on cut edges).  `part` = 96 doubles of shared
+// scratch.  A single warp would spend microseconds here on the eight complex divisions per lane -- on the critical path
+// of a one-wave sweep -- so all 256 threads take one element each.
+template <int NOUT>
+__device__ __forceinline__ void block_epilogue(const c64 (&v)[NOUT], const c64 (&old)[NOUT], const ItemDesc* d, const Args& k, double* part,
+                                               int warp, int lane) {
+  using E = Elem<c64>;
+  double* part1 = part;        // [NCWC][2] complex sums
+  double* part2 = part + 32;   // [NCWC][2][4] dot.re, dot.im, |old|^2, |new|^2
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+    const c64 s = warp_sum<c64>(v[o]);
+    if (lane == 0) *reinterpret_cast<double2*>(part1 + (warp * 2 + o) * 2) = make_double2(s.re, s.im);
+  }
+  onchip::bar_sync(BAR_CC, NCTC);
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+    c64 s = E::zero();
+#pragma unroll
+    for (int w = 0; w < NCWC; ++w) {
+      const double2 q = *reinterpret_cast<const double2*>(part1 + (w * 2 + o) * 2);
+      s.re += q.x;
+      s.im += q.y;
+    }
+    const bool scale = k.normalize && !E::is_zero(s);
+    const c64 x = scale ? E::div(v[o], s) : v[o];
+    const int64_t off = d->out_off[o] + threadIdx.x;
+    reinterpret_cast<c64*>(k.msg_out)[off] = x;
+    if (k.peer.nranks > 1 && d->peer[o] >= 0) reinterpret_cast<c64*>(k.peer.peer_out[d->peer[o]])[off] = x;
+    c64 dot = E::fma(E::conj(old[o]), x, E::zero());
+    dot = warp_sum<c64>(dot);
+    const double n_old = warp_sum_d(E::abs2(old[o])), n_new = warp_sum_d(E::abs2(x));
+    if (lane == 0) {
+      double* q = part2 + (warp * 2 + o) * 4;
+      q[0] = dot.re;
+      q[1] = dot.im;
+      q[2] = n_old;
+      q[3] = n_new;
+    }
+  }
+  onchip::bar_sync(BAR_CC, NCTC);
+  if (threadIdx.x < NOUT) {
+    const int o = threadIdx.x;
+    double dr = 0, di = 0, n_old = 0, n_new = 0;
+#pragma unroll
+    for (int w = 0; w < NCWC; ++w) {
+      const double* q = part2 + (w * 2 + o) * 4;
+      dr += q[0];
+      di += q[1];
+      n_old += q[2];
+      n_new += q[3];
+    }
+    residual_record(k.resmax, 1.0 - (dr * dr + di * di) / (n_old * n_new));
+  }
+}
+
 // position of the next physical slice to load, tracked identically by every warp
 struct Cursor {
   int idx, s;
@@ -260,11 +317,11 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
     const int kind = d->kind;
     if (kind < 0) break;
     const int nd = d->d;
-    int nout = 1;
     if (kind == 0) {
       const int leg = d->leg;
       const CFrag m1 = load_cfrag(k.msg_in + 2 * d->in_off[0], g, t);
       const CFrag m2 = load_cfrag(k.msg_in + 2 * d->in_off[1], g, t);
+      const c64 old[1] = {reinterpret_cast<const c64*>(k.msg_in)[d->out_off[0] + threadIdx.x]};  // early: hides the miss
       double accr[2][2][2], acci[2][2][2];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -300,17 +357,16 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
       onchip::bar_sync(BAR_CC, NCTC);
       {
         const int el = threadIdx.x;
-        double sr = 0, si = 0;
+        c64 v[1] = {make_c64(0.0, 0.0)};
 #pragma unroll
         for (int w = 0; w < NCWC; ++w) {
-          const double2 v = *reinterpret_cast<const double2*>(red + w * CMSG + 2 * el);
-          sr += v.x;
-          si += v.y;
+          const double2 q = *reinterpret_cast<const double2*>(red + w * CMSG + 2 * el);
+          v[0].re += q.x;
+          v[0].im += q.y;
         }
-        *reinterpret_cast<double2*>(raw + 2 * el) = make_double2(sr, si);
+        block_epilogue<1>(v, old, d, k, raw, warp, lane);
       }
     } else if (kind == 1) {
-      nout = 2;
       // warps 0..3 = (output o, half tile hs): out0 absorbs leg 1 / closes leg 0 (M1), out1 absorbs leg 0 / closes leg 1 (M0)
       const int o = warp & 1, hs = (warp >> 1) & 1;
       double accr[2][2][2], acci[2][2][2];
@@ -320,6 +376,8 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
         for (int b = 0; b < 2; ++b) accr[a][b][0] = accr[a][b][1] = acci[a][b][0] = acci[a][b][1] = 0.0;
       CFrag m;
       if (warp < 4) m = load_cfrag(k.msg_in + 2 * d->in_off[1 - o], g, t);
+      const c64 old[2] = {reinterpret_cast<const c64*>(k.msg_in)[d->out_off[0] + threadIdx.x],
+                          reinterpret_cast<const c64*>(k.msg_in)[d->out_off[1] + threadIdx.x]};
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;
         mbar_wait(&mbar[sl], (u >> 1) & 1);
@@ -339,16 +397,19 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
       onchip::bar_sync(BAR_CC, NCTC);
       {
         const int el = threadIdx.x;
+        c64 v[2];
 #pragma unroll
         for (int oo = 0; oo < 2; ++oo) {
           const double2 v0 = *reinterpret_cast<const double2*>(red + oo * CMSG + 2 * el);
           const double2 v1 = *reinterpret_cast<const double2*>(red + (oo + 2) * CMSG + 2 * el);
-          *reinterpret_cast<double2*>(raw + oo * CMSG + 2 * el) = make_double2(v0.x + v1.x, v0.y + v1.y);
+          v[oo] = make_c64(v0.x + v1.x, v0.y + v1.y);
         }
+        block_epilogue<2>(v, old, d, k, raw, warp, lane);
       }
     } else {
       // degree 1: out[b', b] = sum_s A[s, b] conj(A[s, b']); thread el = b' + 16 b
       const int bp = threadIdx.x & 15, b = threadIdx.x >> 4;
+      const c64 old[1] = {reinterpret_cast<const c64*>(k.msg_in)[d->out_off[0] + threadIdx.x]};
       double sr = 0, si = 0;
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;
@@ -359,18 +420,11 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
         si += x.y * y.x - x.x * y.y;
         release(sl);
       }
-      onchip::bar_sync(BAR_CC, NCTC);  // the previous item's epilogue is done with raw
-      *reinterpret_cast<double2*>(raw + 2 * threadIdx.x) = make_double2(sr, si);
-    }
-    onchip::bar_sync(BAR_CC, NCTC);
-    if (warp < nout) {
-      const int64_t off = d->out_off[warp];
-      c64* peer_m = (k.peer.nranks > 1 && d->peer[warp] >= 0) ? reinterpret_cast<c64*>(k.peer.peer_out[d->peer[warp]]) + off : nullptr;
-      warp_epilogue<c64>(reinterpret_cast<const c64*>(raw + warp * CMSG), reinterpret_cast<const c64*>(k.msg_in) + off,
-                         reinterpret_cast<c64*>(k.msg_out) + off, MSG, k.normalize, nullptr, lane, k.resmax, peer_m);
+      const c64 v[1] = {make_c64(sr, si)};
+      block_epilogue<1>(v, old, d, k, raw, warp, lane);
     }
   }
-  peer_post_when_last(k.peer, warp < 2);  // warps 0 and 1 run the epilogues
+  peer_post_when_last(k.peer, true);  // every thread stores message elements
 }
 
 }  // namespace onchip16c
