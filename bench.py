@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--flush", default="write", choices=["write", "write+read"],
+                    help="L2 flush between timed steps: 256 MiB memset, optionally followed by a read pass over the same buffer "
+                         "(leaves L2 full of clean instead of dirty lines)")
     return ap.parse_args()
 
 
@@ -302,6 +305,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     t_wall0 = time.perf_counter()
     for e0, e1 in evs:
         l2_flush.zero_()
+        if args.flush == "write+read":
+            l2_flush.view(torch.int64).sum()
         if world > 1:
             ctx.peer_barrier()  # untimed: align the ranks after their (untimed) L2 flushes, so that one rank's flush
             #                     does not sit inside its neighbour's timed sweep

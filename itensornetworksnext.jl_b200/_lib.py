@@ -10,7 +10,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbpx.so")
+LIB_PATH = os.environ.get("BPX_LIB", os.path.join(_HERE, "csrc", "libbpx.so"))  # BPX_LIB: debug builds (tools/timing_*.py)
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "include", "bpx.h"))
 
 BPX_OK = 0

@@ -335,6 +335,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.resmax = ctx->cur_slot;
     k.normalize = normalize;
     k.peer = ctx->peer_args;
+    k.timing = (long long*)ctx->d_timing;
     if (ctx->onchip16c_grid == 0) return BPX_OK;
     onchip16c::bp_update_onchip_c16c<<<ctx->onchip16c_grid, onchip16c::NTHREADSC, onchip16c::SMEM_BYTES16C, ctx->stream>>>(k);
     ctx->n_launches++;

@@ -56,7 +56,16 @@ struct Args {
   unsigned long long* resmax;
   int normalize;
   PeerArgs peer;
+  long long* timing;  // debug (BPX_ONCHIP_TIMING builds): clock64 stamps of CTA 0's first item
 };
+
+#ifdef BPX_ONCHIP_TIMING
+#define TSTAMPC(i) do { if (lane == 0 && blockIdx.x == 0 && k.timing && u < 2) k.timing[warp * 16 + (i) + 5 * (int)u] = clock64(); } while (0)
+#define TSTAMPC0(i) do { if (lane == 0 && blockIdx.x == 0 && k.timing && idx == (int)blockIdx.x) k.timing[warp * 16 + (i)] = clock64(); } while (0)
+#else
+#define TSTAMPC(i) do { } while (0)
+#define TSTAMPC0(i) do { } while (0)
+#endif
 
 __device__ __forceinline__ double neg(double x) { return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x)); }
 
@@ -268,7 +277,13 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
     const ItemDesc* d = k.items + c.idx;
     const int nsl = d->kind == 0 ? NSL3 : (d->kind == 1 ? NSL2 : NSL1);
     mbar_expect_tx(&mbar[sl], nsl * 8);
-    tma_bulk_g2s(smem + sl * NSL3, k.sites + d->site_off + (size_t)c.s * nsl, nsl * 8, &mbar[sl]);
+    const double* src = k.sites + d->site_off + (size_t)c.s * nsl;
+    if (d->kind == 0) {  // four 16 KiB copies in flight instead of one 64 KiB copy
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tma_bulk_g2s(smem + sl * NSL3 + q * 2048, src + q * 2048, 16384, &mbar[sl]);
+    } else {
+      tma_bulk_g2s(smem + sl * NSL3, src, nsl * 8, &mbar[sl]);
+    }
   };
   auto advance = [&](Cursor& c) {
     if (!valid(c)) return;
@@ -312,6 +327,15 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
   };
 
   uint32_t u = 0;
+#ifdef BPX_ONCHIP_TIMING
+  if (lane == 0 && blockIdx.x == 0 && k.timing) k.timing[warp * 16] = clock64();
+  if (threadIdx.x == 0 && k.timing) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    k.timing[2048 + 4 * blockIdx.x] = (long long)gt;
+    k.timing[2048 + 4 * blockIdx.x + 2] = clock64();
+  }
+#endif
   for (int idx = blockIdx.x; idx < k.n_slots; idx += G) {
     const ItemDesc* d = k.items + idx;
     const int kind = d->kind;
@@ -327,9 +351,11 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
       for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 2; ++b) accr[a][b][0] = accr[a][b][1] = acci[a][b][0] = acci[a][b][1] = 0.0;
+      TSTAMPC0(1);
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;
         mbar_wait(&mbar[sl], (u >> 1) & 1);
+        TSTAMPC(2);
         const double* A = smem + sl * NSL3;
         // X = A_s · M_first (columns: a spectator leg), then absorb M_second and close the output leg
         if (leg == 0) {
@@ -339,7 +365,9 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
 #pragma unroll 1
           for (int c = warp; c < 16; c += NCWC) absorb_one16c<0, 1>(A, Xbuf, pos<L_A3>(2, c), m1, g, t);
         }
+        TSTAMPC(3);
         onchip::bar_sync(BAR_CC, NCTC);
+        TSTAMPC(4);
         if (leg == 0) {
 #pragma unroll 1
           for (int c = warp; c < 16; c += NCWC) absorb_close16c<L_A3, 1, 0, -1>(Xbuf, A, pos<L_A3>(2, c), m2, g, t, accr, acci);
@@ -350,11 +378,14 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
 #pragma unroll 1
           for (int c = warp; c < 16; c += NCWC) absorb_close16c<L_A3, 1, 2, -1>(Xbuf, A, pos<L_A3>(0, c), m2, g, t, accr, acci);
         }
+        TSTAMPC(5);
         release(sl);
         onchip::bar_sync(BAR_CC, NCTC);  // X is rewritten by the next slice / aliased by red
+        TSTAMPC(6);
       }
       store_partial(red + warp * CMSG, accr, acci, g, t);
       onchip::bar_sync(BAR_CC, NCTC);
+      TSTAMPC0(12);
       {
         const int el = threadIdx.x;
         c64 v[1] = {make_c64(0.0, 0.0)};
@@ -365,6 +396,7 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
           v[0].im += q.y;
         }
         block_epilogue<1>(v, old, d, k, raw, warp, lane);
+        TSTAMPC0(13);
       }
     } else if (kind == 1) {
       // warps 0..3 = (output o, half tile hs): out0 absorbs leg 1 / closes leg 0 (M1), out1 absorbs leg 0 / closes leg 1 (M0)
@@ -424,6 +456,14 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
       block_epilogue<1>(v, old, d, k, raw, warp, lane);
     }
   }
+#ifdef BPX_ONCHIP_TIMING
+  if (threadIdx.x == 0 && k.timing) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    k.timing[2048 + 4 * blockIdx.x + 1] = (long long)gt;
+    k.timing[2048 + 4 * blockIdx.x + 3] = clock64();
+  }
+#endif
   peer_post_when_last(k.peer, true);  // every thread stores message elements
 }
 
