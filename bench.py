@@ -412,7 +412,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             e_ms = float(t.item())
         e2e = {"value": n_total_updates / (e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
                "d2h_bytes_per_step": int(nbytes + 8), "ms_per_step": e_ms / args.steps,
-               "what": "bpx_sweep_host: messages H2D (pinned) + one sweep + messages D2H + residual per step, one C-ABI call; site tensors resident"}
+               "what": "bpx_sweep_host, one C-ABI call per step with pinned host buffers: messages H2D + one sweep + messages and residual back in host "
+                       "memory; site tensors resident.  Single-launch sweeps stream: the kernel runs while the upload arrives in chunks and "
+                       "stores new messages straight into the host buffer (one CUDA-graph launch per step)"}
 
     # ---- CPU baseline (rank 0, N = 1) -----------------------------------------------------------------
     cpu = None

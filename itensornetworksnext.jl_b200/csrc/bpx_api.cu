@@ -163,6 +163,14 @@ extern "C" int bpx_destroy(bpx_ctx* ctx) {
   halo_release(ctx);
   free_problem(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  for (auto& g : ctx->io_graphs) cudaGraphExecDestroy(g.exec);
+  if (ctx->copy_stream) {
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->ev_io_start);
+    cudaEventDestroy(ctx->ev_io_done);
+    cudaFree(ctx->d_io_progress);
+    cudaFreeHost(ctx->h_io_progress);
+  }
   delete ctx;
   return BPX_OK;
 }
@@ -401,6 +409,7 @@ int bpx::relayout_sites(bpx_ctx* ctx) {
 
 // (re)derive per-bucket vertex/edge lists restricted to the vertices this rank owns
 int bpx::rebuild_work_lists(bpx_ctx* ctx) {
+  ctx->work_epoch++;  // captured steps refer to the old lists / buffers
   auto F = [](auto*& p) {
     if (p) cudaFree(p);
     p = nullptr;
@@ -533,18 +542,177 @@ extern "C" int bpx_set_messages(bpx_ctx* ctx, const void* packed) {
 
 // One reference-facing step with HOST buffers: upload the iterate, one synchronous sweep, download the new iterate
 // and the fused residual -- the per-sweep call of the Julia plugin (AI.step! + StopWhenConverged), one host sync.
+// device-accessible alias of a pinned (page-locked, mapped) host pointer, or NULL
+static void* mapped_alias(const void* host) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+// can this rank's sweep run with streamed host I/O?  (one launch of a kernel family that implements HostIO)
+static bool sweep_streams_host_io(bpx_ctx* ctx) {
+  int n = 0;
+  for (int bi = 0; bi < (int)ctx->buckets.size(); ++bi) {
+    const Bucket& b = ctx->buckets[bi];
+    if (b.my_edges.empty()) continue;
+    if (b.kernel != BPX_KERNEL_ONCHIP) return false;  // every on-chip family implements HostIO
+    if (b.leader == bi) ++n;
+  }
+  return n == 1;
+}
+
+static void io_graphs_clear(bpx_ctx* ctx) {
+  for (auto& g : ctx->io_graphs) cudaGraphExecDestroy(g.exec);
+  ctx->io_graphs.clear();
+}
+
+// Enqueue one streamed step (also the body that is captured into a CUDA graph): progress word and residual slot
+// reset, the sweep kernel (gated on the progress word, storing into the host alias), the chunked upload on the copy
+// stream, and the residual key into pinned host memory.
+// cuStreamWriteValue32 through the runtime's driver entry point (libbpx links cudart only): a stream memory op is a
+// much cheaper "chunk has landed" signal than an 8-byte copy behind every chunk.  NULL if unavailable.
+typedef int (*StreamWriteValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static StreamWriteValue32Fn stream_write_value32() {
+  static StreamWriteValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (!getenv("BPX_IO_NO_MEMOP") && cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &st) == cudaSuccess &&
+        st == cudaDriverEntryPointSuccess)
+      fn = (StreamWriteValue32Fn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+static int enqueue_streamed_step(bpx_ctx* ctx, const void* packed_in, void* out_alias, int* err_alias, int normalize, int n_chunks) {
+  const int64_t n_el = ctx->msg_off[ctx->ne];
+  std::vector<int64_t> bound(n_chunks + 1, 0);  // chunk boundaries on whole 16-byte units; cumulative element counts
+  for (int c = 1; c <= n_chunks; ++c) bound[c] = c == n_chunks ? n_el : ((n_el * c / n_chunks) & ~(int64_t)1);
+  for (int c = 0; c < n_chunks; ++c) ctx->h_io_progress[c] = bound[c + 1];
+  ctx->cur = 0;
+  ctx->history_len = 0;  // the step's residual lands in history slot 0 (a plain store by the kernel's last CTA)
+  ctx->ring_dirty = false;
+  // no memsets: the progress word, the CTA ticket and the step's private residual slot are reset by the previous
+  // step's last CTA (and zero-initialised)
+  BPX_CUDA(ctx, cudaEventRecord(ctx->ev_io_start, ctx->stream));
+  BPX_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_io_start, 0));
+  ctx->io_args.progress = ctx->d_io_progress;
+  ctx->io_args.host_out = (double*)out_alias;
+  ctx->io_args.error_flag = err_alias;
+  ctx->io_args.host_key = reinterpret_cast<unsigned long long*>(err_alias) - 1;  // pinned slot [32] (the error flag is [33])
+  ctx->io_args.local_key = reinterpret_cast<unsigned long long*>(ctx->d_io_progress + 2);
+  ctx->io_args.ring_key = ctx->d_reskeys;
+  ctx->io_args.ticket = reinterpret_cast<unsigned int*>(ctx->d_io_progress + 1);
+  ctx->slot_override = ctx->io_args.local_key;
+  int rc = sweep_once(ctx, normalize);
+  ctx->slot_override = nullptr;
+  ctx->io_args = HostIO{};
+  if (rc) return rc;
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t o = (size_t)bound[c] * ctx->esize, len = (size_t)(bound[c + 1] - bound[c]) * ctx->esize;
+    BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_msg[0] + o, (const char*)packed_in + o, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+    StreamWriteValue32Fn wv = n_el < (1ll << 32) ? stream_write_value32() : nullptr;
+    if (wv) {  // low word of the (zeroed) 64-bit progress counter
+      if (wv(ctx->copy_stream, (unsigned long long)(uintptr_t)ctx->d_io_progress, (unsigned int)bound[c + 1], 0) != 0) {
+        set_error(ctx, "bpx_sweep_host: cuStreamWriteValue32 failed");
+        return BPX_ERR_CUDA;
+      }
+    } else {
+      BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_io_progress, ctx->h_io_progress + c, sizeof(long long), cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+  }
+  BPX_CUDA(ctx, cudaEventRecord(ctx->ev_io_done, ctx->copy_stream));
+  BPX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_io_done, 0));
+  return BPX_OK;  // (the residual key arrives in pinned host memory from the kernel's last CTA)
+}
+
 extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_out, int normalize, double* residual_out) {
   NEED_DIMS(ctx, "bpx_sweep_host");
   REQUIRE(ctx, ctx->nranks == 1, "bpx_sweep_host: single-rank contexts only");
   REQUIRE(ctx, (packed_in && packed_out) || ctx->msg_off[ctx->ne] == 0, "bpx_sweep_host: NULL buffer");
   const size_t n = (size_t)ctx->msg_off[ctx->ne] * ctx->esize;
-  ctx->cur = 0;
-  BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[0], packed_in, n, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = sweep_once(ctx, normalize);
-  if (rc) return rc;
-  BPX_CUDA(ctx, cudaMemcpyAsync(packed_out, ctx->d_msg[ctx->cur], n, cudaMemcpyDeviceToHost, ctx->stream));
+  int rc;
   double res = INFINITY;
-  if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) return rc;  // synchronises the stream
+  void* out_alias = (n > 0 && sweep_streams_host_io(ctx) && mapped_alias(packed_in)) ? mapped_alias(packed_out) : nullptr;
+  if (out_alias) {
+    // ---- streamed: the kernel starts at once; the upload arrives in chunks behind a progress word the items wait
+    // for, and the epilogues store the new messages straight into the caller's buffer.  The whole step is one
+    // CUDA-graph launch (cached per buffer pair): the ~20 stream calls it replaces cost more than the sweep. ----
+    // every chunk costs ~10 us of copy-engine latency (measured): about 1 MiB per chunk, at most 16
+    int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(16, (n + (512 << 10)) >> 20));
+    if (const char* env = getenv("BPX_IO_CHUNKS")) n_chunks = std::max(1, std::min(32, atoi(env)));
+    if (!ctx->copy_stream) {
+      BPX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      BPX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_io_start, cudaEventDisableTiming));
+      BPX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_io_done, cudaEventDisableTiming));
+      BPX_CUDA(ctx, cudaMalloc((void**)&ctx->d_io_progress, 4 * sizeof(long long)));  // [0] progress, [1] CTA ticket, [2] residual key
+      BPX_CUDA(ctx, cudaMemset(ctx->d_io_progress, 0, 4 * sizeof(long long)));
+      BPX_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_io_progress, 34 * sizeof(long long), cudaHostAllocMapped));
+      ctx->h_io_progress[33] = 0;
+    }
+    if ((rc = fast_refresh_sites(ctx))) return rc;  // never part of the captured step
+    int* err_alias = (int*)mapped_alias(ctx->h_io_progress + 33);
+    const bool use_graph = !ctx->profiling && !ctx->io_graph_disabled && !getenv("BPX_IO_NO_GRAPH");
+    if (use_graph) {
+      bpx_ctx::IoGraph* g = nullptr;
+      for (auto& c : ctx->io_graphs)
+        if (c.in == packed_in && c.out == packed_out && c.normalize == normalize && c.chunks == n_chunks && c.epoch == ctx->work_epoch) g = &c;
+      const int64_t sweeps0 = ctx->n_sweeps, updates0 = ctx->n_updates, launches0 = ctx->n_launches;
+      if (!g) {
+        if (ctx->io_graphs.size() >= 8) io_graphs_clear(ctx);
+        cudaGraph_t graph = nullptr;
+        BPX_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_streamed_step(ctx, packed_in, out_alias, err_alias, normalize, n_chunks);
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc) {
+          if (graph) cudaGraphDestroy(graph);
+          return rc;
+        }
+        BPX_CUDA(ctx, ce);
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        BPX_CUDA(ctx, ce);
+        ctx->io_graphs.push_back({packed_in, packed_out, normalize, n_chunks, ctx->work_epoch, ctx->n_launches - launches0, exec});
+        g = &ctx->io_graphs.back();
+      }
+      // host-side state of "one sweep from set 0 into set 1, recorded in residual slot 0"
+      ctx->cur = 1;
+      ctx->history_len = 1;
+      ctx->n_sweeps = sweeps0 + 1;
+      ctx->n_updates = updates0 + ctx->n_owned_edges;
+      ctx->n_launches = launches0 + g->launches;
+      for (int c = 0; c < n_chunks; ++c)  // (the chunk table is read by the copy engine at run time)
+        ctx->h_io_progress[c] = c + 1 == n_chunks ? ctx->msg_off[ctx->ne] : ((ctx->msg_off[ctx->ne] * (c + 1) / n_chunks) & ~(int64_t)1);
+      BPX_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+    } else {
+      if ((rc = enqueue_streamed_step(ctx, packed_in, out_alias, err_alias, normalize, n_chunks))) return rc;
+    }
+    BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ring_dirty = true;  // slot 0 is re-used by every streamed step: other sweep entry points clear the ring first
+    unsigned long long key;
+    memcpy(&key, ctx->h_io_progress + 32, sizeof(key));
+    res = residual_from_key(key);
+    if (ctx->h_io_progress[33] != 0) {
+      ctx->h_io_progress[33] = 0;
+      cudaMemset(ctx->d_io_progress, 0, 4 * sizeof(long long));  // the self-resetting words may be stale now
+      ctx->io_graph_disabled = true;  // e.g. a runtime that serialises the graph's branches: use plain streams from now on
+      set_error(ctx, "bpx_sweep_host: timed out waiting for the streamed upload");
+      return BPX_ERR_CUDA;
+    }
+  } else {
+    ctx->cur = 0;
+    BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[0], packed_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = sweep_once(ctx, normalize))) return rc;
+    BPX_CUDA(ctx, cudaMemcpyAsync(packed_out, ctx->d_msg[ctx->cur], n, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) return rc;  // synchronises the stream
+  }
   if (residual_out) *residual_out = res;
   return BPX_OK;
 }
@@ -625,16 +793,18 @@ static int residual_ring_clear(bpx_ctx* ctx) {
   BPX_CUDA(ctx, cudaMemsetAsync(ctx->d_reskeys, 0, bytes, ctx->stream));
   BPX_CUDA(ctx, cudaMemsetAsync(ctx->d_reskeys_local, 0, bytes, ctx->stream));
   ctx->history_len = 0;
+  ctx->ring_dirty = false;
   return BPX_OK;
 }
 
 static int residual_begin_sweep(bpx_ctx* ctx) {
-  if (ctx->history_len >= ctx->history_cap) {  // ring full: start over (older history is dropped)
+  if (ctx->history_len >= ctx->history_cap || ctx->ring_dirty) {  // ring full (or slots re-used by streamed steps): start over
     int rc = halo_gate(ctx);
     if (rc) return rc;
     if ((rc = residual_ring_clear(ctx))) return rc;
   }
   ctx->cur_slot = (ctx->nranks > 1 ? ctx->d_reskeys_local : ctx->d_reskeys) + ctx->history_len;
+  if (ctx->slot_override) ctx->cur_slot = ctx->slot_override;  // streamed steps record into a private, self-resetting slot
   return BPX_OK;
 }
 

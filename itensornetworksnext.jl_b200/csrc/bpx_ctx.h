@@ -112,6 +112,26 @@ struct bpx_ctx {
   unsigned long long recv_mask = 0;  // ranks that own the tail of an edge pointing into this rank's block
   bool single_launch = false;       // the whole sweep of this rank is ONE fast launch: exchange fused into it
 
+  // streamed host I/O (bpx_sweep_host with pinned buffers)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_io_start = nullptr, ev_io_done = nullptr;
+  long long* d_io_progress = nullptr;
+  long long* h_io_progress = nullptr;  // pinned: cumulative element counts, one per chunk; [32] residual key, [33] error flag
+  bpx::HostIO io_args = {};            // what the next fast launch is told (all NULL: nothing)
+  struct IoGraph {                     // one captured step per (host buffers, normalize, chunking)
+    const void* in;
+    void* out;
+    int normalize, chunks;
+    uint64_t epoch;
+    int64_t launches;
+    cudaGraphExec_t exec;
+  };
+  std::vector<IoGraph> io_graphs;
+  uint64_t work_epoch = 0;             // bumped whenever launch lists / buffers are rebuilt (invalidates io_graphs)
+  bool io_graph_disabled = false;
+  unsigned long long* slot_override = nullptr;  // residual slot of the step being enqueued (streamed steps)
+  bool ring_dirty = false;             // residual ring slots were re-used without a clear (streamed steps)
+
   // counters
   int64_t n_launches = 0, n_updates = 0, n_sweeps = 0;
 };

@@ -93,6 +93,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
           const int32_t e = ctx->out_edge[v][l];
           d.out_edge[o] = e;
           d.out_off[o] = ctx->msg_off[e];
+          d.need = std::max<int64_t>(d.need, ctx->msg_off[e + 1]);
           d.peer[o] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
         };
         auto in_of = [&](int l) { return ctx->msg_off[ctx->rev[ctx->out_edge[v][l]]]; };
@@ -103,6 +104,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
         d.d = b.d;
         d.peer[0] = d.peer[1] = -1;
         d.first = 1;
+        for (int l = 0; l < b.z; ++l) d.need = std::max<int64_t>(d.need, ctx->msg_off[ctx->rev[ctx->out_edge[v][l]] + 1]);
         if (b.z == 3) {
           // one item per output leg; (first, second) absorbed message: out2 (M0, M1), out1 (M0, M2), out0 (M2, M1)
           static const int first_leg[3] = {2, 0, 0}, second_leg[3] = {1, 2, 1};
@@ -187,11 +189,17 @@ inline int fast_prepare(bpx_ctx* ctx) {
           d.out_off[l] = ctx->msg_off[e];
           d.in_off[l] = ctx->msg_off[ctx->rev[e]];
           d.peer[l] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
+          d.need = std::max<int64_t>(d.need, std::max(ctx->msg_off[e + 1], ctx->msg_off[ctx->rev[e] + 1]));
         }
         it16.push_back(d);
       }
     }
     if (!it16.empty()) {
+      // equal-cost items: process them in the order in which a streamed upload (bpx_sweep_host) delivers their messages
+      // (on a periodic lattice the wrap-around layers need the end of the message set and go last)
+      std::stable_sort(it16.begin(), it16.end(), [](const onchip16::ItemDesc& a, const onchip16::ItemDesc& b) {
+        return a.pair_mode != b.pair_mode ? a.pair_mode < b.pair_mode : a.need < b.need;
+      });
       ctx->n_onchip16_items = (int)it16.size();
       cudaError_t e = cudaMalloc((void**)&ctx->d_onchip16_items, it16.size() * sizeof(onchip16::ItemDesc));
       if (e != cudaSuccess) {
@@ -271,6 +279,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
         d.out_off[i] = ctx->msg_off[e];
         d.in_off[i] = ctx->msg_off[ctx->rev[e]];
         d.peer[i] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
+        d.need = std::max<int64_t>(d.need, std::max(ctx->msg_off[e + 1], ctx->msg_off[ctx->rev[e] + 1]));
       }
       for (int i = b.z; i < 4; ++i) d.peer[i] = -1;
       if (b.z == 4) {  // two half items (branch P, branch Q): finer granularity for the last wave
@@ -335,6 +344,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.resmax = ctx->cur_slot;
     k.normalize = normalize;
     k.peer = ctx->peer_args;
+    k.io = ctx->io_args;
     k.timing = (long long*)ctx->d_timing;
     if (ctx->onchip16c_grid == 0) return BPX_OK;
     onchip16c::bp_update_onchip_c16c<<<ctx->onchip16c_grid, onchip16c::NTHREADSC, onchip16c::SMEM_BYTES16C, ctx->stream>>>(k);
@@ -353,6 +363,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.resmax = ctx->cur_slot;
     k.normalize = normalize;
     k.peer = ctx->peer_args;
+    k.io = ctx->io_args;
     const int grid = std::min(k.n_items, ctx->num_sms);
     if (grid == 0) return BPX_OK;
     onchip16::bp_update_onchip_c16<<<grid, onchip16::NTHREADS16, onchip16::SMEM_BYTES16, ctx->stream>>>(k);
@@ -372,6 +383,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.resmax = ctx->cur_slot;
     k.normalize = normalize;
     k.peer = ctx->peer_args;
+    k.io = ctx->io_args;
     const int grid = std::min(k.n_items, ctx->num_sms);
     if (grid == 0) return BPX_OK;
     onchip::bp_update_onchip_c8<<<grid, onchip::NTHREADS, onchip::SMEM_BYTES, ctx->stream>>>(k);

@@ -59,6 +59,7 @@ struct ItemDesc {
   int32_t branch;  // degree 4 only: 0 = branch P (out3, out2), 1 = branch Q (out1, out0); each is its own work item
   int32_t pad[2];
   int32_t peer[4];  // rank that owns the head of out-edge i when it lives on another rank (cut edge), else -1
+  int64_t need;     // streamed host I/O: message-set prefix (elements) that holds every message this item reads
 };
 
 // ---- swizzled position (in doubles, s = 0) of element (a0,a1,a2,a3); XOR-linear in every index bit ----
@@ -229,6 +230,7 @@ struct Args {
   unsigned long long* resmax;    // this sweep's residual key (atomicMax)
   int normalize;
   PeerArgs peer;                 // multi-GPU: gate / direct peer stores / post (nranks <= 1: unused)
+  HostIO io;                     // streamed host I/O (bpx_sweep_host), all NULL otherwise
 };
 
 // shared memory (doubles): A[2][NELEM] | P[NELEM] | red[2][NCW][MSG] | raw[2][MSG] | msgs[2][4][MSG] | 2 mbarriers
@@ -277,7 +279,7 @@ __device__ __forceinline__ void publish(double* red, double* raw, int warp, int 
 // Lane holds elements lane and lane + 32.  The residual 1 - |<old^, new^>|^2 is invariant under the scaling,
 // so all four reductions run interleaved on the raw tile.
 __device__ __forceinline__ void epilogue_tile(double v0, double v1, double o0, double o1, int lane, double* new_m, int normalize,
-                                              double* residual_slot, unsigned long long* resmax, double* peer_m) {
+                                              double* residual_slot, unsigned long long* resmax, double* peer_m, double* host_m = nullptr) {
   double s = v0 + v1, dot = o0 * v0 + o1 * v1, n_old = o0 * o0 + o1 * o1, n_new = v0 * v0 + v1 * v1;
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) {
@@ -295,6 +297,10 @@ __device__ __forceinline__ void epilogue_tile(double v0, double v1, double o0, d
   if (peer_m) {  // cut edge: the owner of the head reads this message next sweep -- store it there too (NVLink)
     peer_m[lane] = v0;
     peer_m[lane + 32] = v1;
+  }
+  if (host_m) {  // streamed host I/O: the caller's host buffer (mapped), posted writes over PCIe
+    host_m[lane] = v0;
+    host_m[lane + 32] = v1;
   }
   if (lane == 0) {
     const double r = 1.0 - dot * dot / (n_old * n_new);
@@ -340,6 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
     int n = 0;
     for (int item = blockIdx.x; item < k.n_items; item += G, ++n) {
       if (n >= 2) bar_sync(BAR_SLOT_FREE + (n & 1), NCT + 32);  // compute warps are done with the slot's previous tenant
+      hostio_wait(k.io, k.items[item].need);  // streamed upload: the item's messages have arrived
       if (lane == 0) tma_item(smem + (n & 1) * NELEM, msgs + (n & 1) * 4 * MSG, &mbar[n & 1], k, k.items + item);
     }
   } else if (warp >= NCW) {
@@ -363,6 +370,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
         int e = 0;
         double* peer_m = nullptr;
         if (l >= 0) {  // old message: issued before the hand-over so its latency overlaps the compute
+          hostio_wait(k.io, d->need);
           off = d->out_off[l];
           e = d->out_edge[l];
           if (k.peer.nranks > 1 && d->peer[l] >= 0) peer_m = k.peer.peer_out[d->peer[l]] + off;
@@ -372,7 +380,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
         bar_sync(BAR_RAW_FULL, NRAW);
         const double v0 = raw[which * MSG + lane], v1 = raw[which * MSG + lane + 32];
         bar_arrive(BAR_RAW_FREE, NRAW);  // values are in registers: raw may be overwritten
-        if (l >= 0) epilogue_tile(v0, v1, o0, o1, lane, k.msg_out + off, k.normalize, k.residual ? k.residual + e : nullptr, k.resmax, peer_m);
+        if (l >= 0)
+          epilogue_tile(v0, v1, o0, o1, lane, k.msg_out + off, k.normalize, k.residual ? k.residual + e : nullptr, k.resmax, peer_m,
+                        k.io.host_out ? k.io.host_out + off : nullptr);
       }
     }
   } else {
@@ -445,6 +455,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
   }
   // multi-GPU: every role of this CTA is done; the last CTA posts (sweep id, local residual) to all ranks
   peer_post_when_last(k.peer, warp >= NCW && warp < NCW + NEW);  // only the epilogue warps store messages
+  hostio_finish(k.io);
 }
 
 }  // namespace onchip

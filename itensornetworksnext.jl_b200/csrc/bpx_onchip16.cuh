@@ -33,6 +33,7 @@ struct ItemDesc {
   int32_t peer[6];
   int32_t pair_mode;   // 0: three legs of dimension 16; 1: six legs of dimension 4 paired into super-legs
   int32_t pad;
+  int64_t need;        // streamed host I/O: message-set prefix (elements) that holds every message this item reads
 };
 
 struct Args {
@@ -45,6 +46,7 @@ struct Args {
   unsigned long long* resmax;
   int normalize;
   PeerArgs peer;
+  HostIO io;  // streamed host I/O (bpx_sweep_host), all NULL otherwise
 };
 
 // staged incoming messages: plain 3 x 256 doubles, pair mode 6 x 16 doubles; super-message element (b', b)
@@ -129,6 +131,7 @@ __device__ __forceinline__ void epilogue16(const double* raw, const double* Mst,
     const int64_t off = d->out_off[sleg];
     double o[8], v[8];
     if (which == 0) {
+      hostio_wait(k.io, d->need);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = k.msg_in[off + lane + 32 * j];  // issued before the hand-over
     }
@@ -156,11 +159,13 @@ __device__ __forceinline__ void epilogue16(const double* raw, const double* Mst,
     }
     const bool scale = k.normalize && s != 0.0;
     double* peer_m = (k.peer.nranks > 1 && d->peer[sleg] >= 0) ? k.peer.peer_out[d->peer[sleg]] + off : nullptr;
+    double* host_m = k.io.host_out ? k.io.host_out + off : nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const double x = scale ? v[j] / s : v[j];
       k.msg_out[off + lane + 32 * j] = x;
       if (peer_m) peer_m[lane + 32 * j] = x;
+      if (host_m) host_m[lane + 32 * j] = x;
     }
     if (lane == 0) residual_record(k.resmax, 1.0 - dot * dot / (n_old * n_new));  // invariant under the scaling
   } else {
@@ -169,6 +174,7 @@ __device__ __forceinline__ void epilogue16(const double* raw, const double* Mst,
     const int leg = 2 * sleg + which;
     const int64_t off = d->out_off[leg];
     const double* Mo = Mst + (2 * sleg + (1 - which)) * 16;  // the OTHER message of the pair (staged copy)
+    hostio_wait(k.io, d->need);
     const double o = lane < 16 ? k.msg_in[off + lane] : 0.0;
     double mo[16];
 #pragma unroll
@@ -199,6 +205,7 @@ __device__ __forceinline__ void epilogue16(const double* raw, const double* Mst,
       const double x = (k.normalize && s != 0.0) ? v / s : v;
       k.msg_out[off + lane] = x;
       if (k.peer.nranks > 1 && d->peer[leg] >= 0) k.peer.peer_out[d->peer[leg]][off + lane] = x;
+      if (k.io.host_out) k.io.host_out[off + lane] = x;
     }
     if (lane == 0) residual_record(k.resmax, 1.0 - dot * dot / (n_old * n_new));
   }
@@ -229,6 +236,7 @@ __global__ void __launch_bounds__(NTHREADS16, 1) bp_update_onchip_c16(Args k) {
       const int sl = n & 1;
       if (n >= 2) onchip::bar_sync(BAR_SLOT16 + sl, NRAW16 + 32);  // compute AND epilogue warps released the slot
       const ItemDesc* d = k.items + item;
+      hostio_wait(k.io, d->need);  // streamed upload: the item's messages have arrived
       fence_proxy_async();
       if (lane == 0) mbar_expect_tx(&mbar[sl], NEL * 8 + (d->pair_mode ? 6 * 16 * 8 : 3 * MSG * 8));
       __syncwarp();
@@ -304,6 +312,7 @@ __global__ void __launch_bounds__(NTHREADS16, 1) bp_update_onchip_c16(Args k) {
     onchip::bar_sync(BAR_RAW_FREE16, NRAW16);  // let the epilogue warps' last arrive complete
   }
   peer_post_when_last(k.peer, warp >= NCW16 && warp < NCW16 + NEW16);  // only the epilogue warps store messages
+  hostio_finish(k.io);
 }
 
 }  // namespace onchip16

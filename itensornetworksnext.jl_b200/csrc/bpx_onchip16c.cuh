@@ -45,6 +45,7 @@ struct ItemDesc {
   int32_t d;          // physical dimension = number of slices
   int32_t first;      // this item swizzles the vertex's tensor (one item per vertex)
   int64_t canon_off;  // complex elements, into the canonical site buffer
+  int64_t need;       // streamed host I/O: message-set prefix (elements) that holds every message this item reads
 };
 
 struct Args {
@@ -56,6 +57,7 @@ struct Args {
   unsigned long long* resmax;
   int normalize;
   PeerArgs peer;
+  HostIO io;          // streamed host I/O (bpx_sweep_host), all NULL otherwise
   long long* timing;  // debug (BPX_ONCHIP_TIMING builds): clock64 stamps of CTA 0's first item
 };
 
@@ -227,6 +229,7 @@ __device__ __forceinline__ void block_epilogue(const c64 (&v)[NOUT], const c64 (
     const c64 x = scale ? E::div(v[o], s) : v[o];
     const int64_t off = d->out_off[o] + threadIdx.x;
     reinterpret_cast<c64*>(k.msg_out)[off] = x;
+    if (k.io.host_out) reinterpret_cast<c64*>(k.io.host_out)[off] = x;
     if (k.peer.nranks > 1 && d->peer[o] >= 0) reinterpret_cast<c64*>(k.peer.peer_out[d->peer[o]])[off] = x;
     c64 dot = E::fma(E::conj(old[o]), x, E::zero());
     dot = warp_sum<c64>(dot);
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
     const int kind = d->kind;
     if (kind < 0) break;
     const int nd = d->d;
+    hostio_wait(k.io, d->need);  // streamed upload: the item's messages (fragments, old values) have arrived
     if (kind == 0) {
       const int leg = d->leg;
       const CFrag m1 = load_cfrag(k.msg_in + 2 * d->in_off[0], g, t);
@@ -465,6 +469,7 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
   }
 #endif
   peer_post_when_last(k.peer, true);  // every thread stores message elements
+  hostio_finish(k.io);
 }
 
 }  // namespace onchip16c

@@ -29,6 +29,56 @@ struct PeerArgs {
   int* error_flag;
 };
 
+// ---- streamed host I/O (bpx_sweep_host with pinned buffers): the sweep kernel runs WHILE the copy engine uploads
+// the iterate in chunks -- an item waits until the messages it reads have arrived -- and every new message is also
+// stored straight into the caller's (device-mapped) host buffer, so no download follows the kernel.
+struct HostIO {
+  long long* progress;        // elements of the message set that have arrived in msg_in so far (NULL: all resident);
+                              // reset by the kernel's last CTA for the next step
+  double* host_out;           // device-accessible alias of the host output buffer, same offsets as msg_out (NULL: none)
+  int* error_flag;
+  unsigned long long* host_key;           // where the last CTA stores the sweep's residual key (mapped host memory)
+  unsigned long long* local_key;          // the kernels' resmax slot for this step (self-resetting)
+  unsigned long long* ring_key;           // residual-history slot that receives a copy
+  unsigned int* ticket;                   // CTA completion counter (self-resetting)
+};
+// Called by every thread at the end of the kernel (CTA-uniform): the last CTA to finish hands the sweep's residual key
+// to the host, so the step needs no device-to-host copy at all.
+__device__ __forceinline__ void hostio_finish(const HostIO& io) {
+  if (!io.host_key) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(io.ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      const unsigned long long key = *reinterpret_cast<const volatile unsigned long long*>(io.local_key);
+      *reinterpret_cast<volatile unsigned long long*>(io.host_key) = key;
+      *io.ring_key = key;
+      // ready for the next step (stream-ordered): no memset nodes in front of the kernel.  Every item has passed its
+      // gate, so the upload -- and with it the last write of the progress word -- is complete.
+      *io.local_key = 0ull;
+      *io.progress = 0ll;
+      *io.ticket = 0u;
+    }
+  }
+}
+// the calling warp waits (lane 0 spins, bounded) until `need` elements have arrived
+__device__ __forceinline__ void hostio_wait(const HostIO& io, long long need) {
+  if (!io.progress) return;
+  if ((threadIdx.x & 31) == 0) {
+    const volatile long long* p = io.progress;
+    const long long t0 = clock64();
+    while (*p < need) {
+      if (clock64() - t0 > 8000000000ll) {  // ~4 s: raise the error flag instead of hanging the GPU
+        if (io.error_flag) *reinterpret_cast<volatile int*>(io.error_flag) = 2;  // (mapped host memory: plain store)
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncwarp();
+}
+
 // Called by ONE warp per CTA before it touches messages written by peers.  Lane p waits for rank p's post.
 __device__ __forceinline__ void peer_gate(const PeerArgs& pa, int lane) {
   if (pa.nranks <= 1 || pa.wait_id == 0) return;

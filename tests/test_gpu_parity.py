@@ -321,6 +321,38 @@ def test_sweep_host_single_call_step(oracle):
             a, b = b, a
 
 
+@pytest.mark.parametrize("name,dims,periodic", [("cfg2", (6, 6), False), ("cfg2", (32, 32), False), ("cfg4", (4, 4, 4), True),
+                                                ("cfg3", None, False), ("cfg5", (5, 5), False), ("cfg1", None, False)])
+def test_sweep_host_streamed_io_with_pinned_buffers(oracle, name, dims, periodic):
+    # pinned host buffers: the sweep kernel runs while the upload arrives in chunks (items gated on a progress word)
+    # and stores the new messages straight into the caller's buffer; results must equal the staged path and the oracle
+    # (cfg5 / cfg1: sweeps of several launches or generic buckets take the staged path even with pinned buffers)
+    import torch
+
+    p = problems.make_config(name, graph=graphs.named_grid(dims, periodic=periodic) if dims else None)
+    op = oracle.make_problem(p.ga, p.tensors, "norm")
+    with B.BPXContext(0) as ctx:
+        problems.upload(ctx, p)
+        flat = ctx.pack_messages(p.messages)
+        tdt = torch.complex128 if flat.dtype.kind == "c" else torch.float64
+        pa, pb = torch.empty(flat.size, dtype=tdt).pin_memory(), torch.empty(flat.size, dtype=tdt).pin_memory()
+        a, b = pa.numpy(), pb.numpy()
+        a[:] = flat
+        b[:] = np.nan
+        staged_in, staged_out = flat.copy(), np.empty_like(flat)
+        want = list(p.messages)
+        for _ in range(3):
+            prev, want = want, oracle.sweep_jacobi(op, want)
+            res = ctx.sweep_host(a, b)
+            assert np.array_equal(ctx.get_messages_flat(), b)  # the device copy of the iterate is complete too
+            res_staged = ctx.sweep_host(staged_in, staged_out)  # pageable memory: upload, sweep, download
+            assert np.array_equal(b, staged_out) and res == res_staged
+            assert rel_err(ctx.unpack_messages(b), want) < MSG_RTOL
+            assert abs(res - oracle.iterate_diff(want, prev)) < 1e-11
+            a, b = b, a
+            staged_in, staged_out = staged_out, staged_in
+
+
 @pytest.mark.parametrize("name,dims", [("cfg5", (10, 10)), ("cfg2", (32, 32))])
 def test_full_path_sampled_edges_against_oracle(oracle, name, dims):
     """Size-independent check of the production path (device-generated inputs, specialised kernels): recompute a
