@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dump-timing", action="store_true", help="debug (BPX_ONCHIP_TIMING builds): per-CTA globaltimer stamps of the last sweep")
     ap.add_argument("--flush", default="write", choices=["write", "write+read"],
                     help="L2 flush between timed steps: 256 MiB memset, optionally followed by a read pass over the same buffer "
                          "(leaves L2 full of clean instead of dirty lines)")
@@ -314,6 +315,24 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         ctx.sweep_async(1)
         e1.record(stream)
     barrier()
+    if args.dump_timing:
+        import ctypes as C_
+        buf = np.zeros(8 * 32 * 16, dtype=np.int64)
+        ctx.lib.bpx_debug_timing.argtypes = [C_.c_void_p, C_.c_void_p, C_.c_int]
+        ctx.lib.bpx_debug_timing(ctx.h, None, 0)  # allocate
+        for _ in range(3):
+            l2_flush.zero_()
+            if world > 1:
+                ctx.peer_barrier()
+            ctx.sweep_async(1)
+        barrier()
+        ctx.lib.bpx_debug_timing(ctx.h, buf.ctypes.data_as(C_.c_void_p), buf.size)
+        g = buf[2048:2048 + 8 * 148].reshape(148, 8)
+        g = g[g[:, 0] > (1 << 50)]  # (the per-phase clock64 stamps of CTA 0 share the buffer)
+        t0 = g[:, 0].min()
+        sys.stderr.write(f"[rank {rank}] CTAs {len(g)}: start spread {g[:,0].max()-t0} ns; gate done at {np.median(g[:,1]-t0):.0f} (max {(g[:,1]-t0).max()}); "
+                         f"compute end median {np.median(g[:,2]-t0):.0f} max {(g[:,2]-t0).max()}; epilogue end max {(g[:,3]-t0).max()}; "
+                         f"after post: median {np.median(g[:,4]-t0):.0f} max {(g[:,4]-t0).max()} ns\n")
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
     step_ms = np.array([a.elapsed_time(b) for a, b in evs])

@@ -152,6 +152,7 @@ __device__ __forceinline__ void warp_epilogue(const T* raw, const T* old_m, T* n
     new_m[i] = v;
     if (peer_m) peer_m[i] = v;  // cut edge: also store into the owning rank's message set (NVLink peer memory)
   }
+  if (peer_m) __threadfence_system();  // release the peer stores here, off the kernel's tail (see peer_post_when_last)
   dot = warp_sum<T>(dot);
   n_old = warp_sum_d(n_old);
   n_new = warp_sum_d(n_new);

@@ -214,6 +214,16 @@ __device__ __forceinline__ void absorb_close(const double* P, const double* A, c
 }
 
 #ifdef BPX_ONCHIP_TIMING
+__device__ __forceinline__ long long gtimer() {
+  unsigned long long gt;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+  return (long long)gt;
+}
+#define GSTAMP(i) do { if (lane == 0 && k.timing) k.timing[2048 + 8 * blockIdx.x + (i)] = gtimer(); } while (0)
+#else
+#define GSTAMP(i) do { } while (0)
+#endif
+#ifdef BPX_ONCHIP_TIMING
 #define TSTAMP(i) do { if (lane == 0 && blockIdx.x == 0 && k.timing && n_iter < 8) k.timing[(n_iter * 32 + warp) * 16 + (i)] = clock64(); } while (0)
 #else
 #define TSTAMP(i) do { } while (0)
@@ -297,6 +307,7 @@ __device__ __forceinline__ void epilogue_tile(double v0, double v1, double o0, d
   if (peer_m) {  // cut edge: the owner of the head reads this message next sweep -- store it there too (NVLink)
     peer_m[lane] = v0;
     peer_m[lane + 32] = v1;
+    __threadfence_system();  // released here, by the (otherwise idle) epilogue warp, instead of at the kernel's tail
   }
   if (host_m) {  // streamed host I/O: the caller's host buffer (mapped), posted writes over PCIe
     host_m[lane] = v0;
@@ -342,7 +353,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
 
   if (warp == NCW + NEW) {
     // ================= producer warp: TMA of item n into slot n & 1, two items ahead of the compute warps ==========
+    GSTAMP(0);
     peer_gate(k.peer, lane);  // multi-GPU: the peers' cut-edge messages of the previous sweep have landed
+    GSTAMP(1);
     int n = 0;
     for (int item = blockIdx.x; item < k.n_items; item += G, ++n) {
       if (n >= 2) bar_sync(BAR_SLOT_FREE + (n & 1), NCT + 32);  // compute warps are done with the slot's previous tenant
@@ -452,9 +465,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
   }
   // let the epilogue warps' last arrive complete
   bar_sync(BAR_RAW_FREE, NRAW);
+  if (warp == 0) GSTAMP(2);
   }
   // multi-GPU: every role of this CTA is done; the last CTA posts (sweep id, local residual) to all ranks
-  peer_post_when_last(k.peer, warp >= NCW && warp < NCW + NEW);  // only the epilogue warps store messages
+  if (warp == NCW) GSTAMP(3);  // epilogue warp 0 done
+  peer_post_when_last(k.peer, false);  // peer stores were released where they were issued
+  if (warp == 0) GSTAMP(4);
   hostio_finish(k.io);
 }
 

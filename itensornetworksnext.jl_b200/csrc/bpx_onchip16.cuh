@@ -167,6 +167,7 @@ __device__ __forceinline__ void epilogue16(const double* raw, const double* Mst,
       if (peer_m) peer_m[lane + 32 * j] = x;
       if (host_m) host_m[lane + 32 * j] = x;
     }
+    if (peer_m) __threadfence_system();  // released here instead of at the kernel's tail
     if (lane == 0) residual_record(k.resmax, 1.0 - dot * dot / (n_old * n_new));  // invariant under the scaling
   } else {
     // pair mode: S[(a', c'), (a, c)] at (a' + 4 c') + 16 (a + 4 c).
@@ -204,7 +205,10 @@ __device__ __forceinline__ void epilogue16(const double* raw, const double* Mst,
     if (lane < 16) {
       const double x = (k.normalize && s != 0.0) ? v / s : v;
       k.msg_out[off + lane] = x;
-      if (k.peer.nranks > 1 && d->peer[leg] >= 0) k.peer.peer_out[d->peer[leg]][off + lane] = x;
+      if (k.peer.nranks > 1 && d->peer[leg] >= 0) {
+        k.peer.peer_out[d->peer[leg]][off + lane] = x;
+        __threadfence_system();
+      }
       if (k.io.host_out) k.io.host_out[off + lane] = x;
     }
     if (lane == 0) residual_record(k.resmax, 1.0 - dot * dot / (n_old * n_new));
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(NTHREADS16, 1) bp_update_onchip_c16(Args k) {
     }
     onchip::bar_sync(BAR_RAW_FREE16, NRAW16);  // let the epilogue warps' last arrive complete
   }
-  peer_post_when_last(k.peer, warp >= NCW16 && warp < NCW16 + NEW16);  // only the epilogue warps store messages
+  peer_post_when_last(k.peer, false);  // peer stores were released where they were issued
   hostio_finish(k.io);
 }
 

@@ -230,7 +230,10 @@ __device__ __forceinline__ void block_epilogue(const c64 (&v)[NOUT], const c64 (
     const int64_t off = d->out_off[o] + threadIdx.x;
     reinterpret_cast<c64*>(k.msg_out)[off] = x;
     if (k.io.host_out) reinterpret_cast<c64*>(k.io.host_out)[off] = x;
-    if (k.peer.nranks > 1 && d->peer[o] >= 0) reinterpret_cast<c64*>(k.peer.peer_out[d->peer[o]])[off] = x;
+    if (k.peer.nranks > 1 && d->peer[o] >= 0) {
+      reinterpret_cast<c64*>(k.peer.peer_out[d->peer[o]])[off] = x;
+      __threadfence_system();  // released here instead of at the kernel's tail
+    }
     c64 dot = E::fma(E::conj(old[o]), x, E::zero());
     dot = warp_sum<c64>(dot);
     const double n_old = warp_sum_d(E::abs2(old[o])), n_new = warp_sum_d(E::abs2(x));
@@ -468,7 +471,7 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
     k.timing[2048 + 4 * blockIdx.x + 3] = clock64();
   }
 #endif
-  peer_post_when_last(k.peer, true);  // every thread stores message elements
+  peer_post_when_last(k.peer, false);  // peer stores were released where they were issued
   hostio_finish(k.io);
 }
 

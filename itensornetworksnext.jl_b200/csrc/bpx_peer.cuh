@@ -80,16 +80,27 @@ __device__ __forceinline__ void hostio_wait(const HostIO& io, long long need) {
 }
 
 // Called by ONE warp per CTA before it touches messages written by peers.  Lane p waits for rank p's post.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ void peer_gate(const PeerArgs& pa, int lane) {
   if (pa.nranks <= 1 || pa.wait_id == 0) return;
   double v = -INFINITY;
   const bool fold = blockIdx.x == 0 && pa.prev_global_key != nullptr;  // folding the global residual needs every rank
   for (int p = lane; p < pa.nranks; p += 32) {
     if (!fold && !((pa.wait_mask >> p) & 1ull)) continue;
-    volatile unsigned long long* flag = &pa.my_mailbox[p].sweep_id;
+    const unsigned long long* flag = &pa.my_mailbox[p].sweep_id;
     const long long t0 = clock64();
     bool ok = true;
-    while (*flag < pa.wait_id) {
+    // acquire loads instead of a trailing fence.sys (measured: ~4 us per system fence, on every CTA's critical path):
+    // the peer's message stores are ordered before its release of the flag
+    while (ld_acquire_sys(flag) < pa.wait_id) {
       if (clock64() - t0 > 8000000000ll) {  // ~4 s: raise the error flag instead of hanging the GPU
         ok = false;
         break;
@@ -103,7 +114,7 @@ __device__ __forceinline__ void peer_gate(const PeerArgs& pa, int lane) {
       atomicExch(pa.error_flag, 1);
     }
   }
-  __threadfence_system();  // acquire: the peers' message stores precede their flag
+  asm volatile("fence.proxy.async;\n" ::: "memory");  // the messages are read through TMA (async proxy) as well
   if (fold) {
     bool has_nan = v != v;
     has_nan = __any_sync(0xffffffffu, has_nan);
@@ -116,8 +127,9 @@ __device__ __forceinline__ void peer_gate(const PeerArgs& pa, int lane) {
 }
 
 // Called by every thread of every CTA when all of the CTA's global/peer stores have been issued (CTA-uniform).
-// `wrote`: this thread stored messages / residual keys (only those threads need the system-scope release; a
-// membar.sys from every thread of the grid costs microseconds).  The last CTA to arrive posts (post_id, local
+// `wrote`: this thread has peer stores that it did not release yet.  The fused kernels release (fence.sys) right
+// after the peer stores of a cut edge -- in an epilogue warp, off the critical path -- and pass false: a system fence
+// costs ~4 us (measured) and would sit on the kernel's tail here.  The last CTA to arrive posts (post_id, local
 // residual) to every rank.
 __device__ __forceinline__ void peer_post_when_last(const PeerArgs& pa, bool wrote = true) {
   if (pa.nranks <= 1 || pa.post_id == 0) return;
@@ -131,11 +143,11 @@ __device__ __forceinline__ void peer_post_when_last(const PeerArgs& pa, bool wro
   __syncthreads();
   if (s_last) {
     if (threadIdx.x < pa.nranks) {
-      __threadfence_system();
+      // every storing thread of the grid fenced (system scope) before its CTA took a ticket; the release store orders
+      // those stores and the residual before the flag -- one fence-equivalent instead of two full system fences
       Mailbox* mb = pa.peer_mailbox[threadIdx.x] + pa.rank;
       mb->residual[pa.post_id % MAILBOX_RING] = residual_from_key(*reinterpret_cast<const volatile unsigned long long*>(pa.local_key));
-      __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(&mb->sweep_id) = pa.post_id;
+      st_release_sys(&mb->sweep_id, pa.post_id);
     }
     if (threadIdx.x == 0) *pa.ticket = 0u;  // ready for the next launch (stream-ordered)
   }

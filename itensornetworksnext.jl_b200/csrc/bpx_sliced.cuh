@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_sliced_c16(Args k) {
     onchip::bar_sync(BAR_COMPUTE, NCT);  // raw / red are re-used by the next item
   }
   }
-  peer_post_when_last(k.peer, warp < 2);  // compute warps 0 and 1 run the epilogues
+  peer_post_when_last(k.peer, false);  // peer stores were released where they were issued (warp_epilogue)
 }
 
 }  // namespace sliced
