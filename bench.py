@@ -405,12 +405,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         h_in, h_out = pin_in.numpy(), pin_out.numpy()
         h_in[:] = flat0
         def e2e_step(src, dst):
-            if world == 1:
-                return ctx.sweep_host(src, dst)      # H2D (pinned) + sweep + D2H + residual, one call
-            ctx.set_messages(src)
-            ctx.sweep_async(1)
-            ctx.get_messages_flat(dst)
-            return ctx.last_residual()
+            # one C-ABI call: upload this rank's messages from pinned memory, one sweep (cut-edge messages travel between
+            # the devices), this rank's new messages + the (global) residual back in host memory
+            return ctx.sweep_host(src, dst)
 
         for _ in range(2):
             e2e_step(h_in, h_out)

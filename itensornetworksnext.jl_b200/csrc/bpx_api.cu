@@ -455,6 +455,17 @@ int bpx::rebuild_work_lists(bpx_ctx* ctx) {
   ctx->n_owned_edges = (int64_t)owned_edges.size();
   int rc = upload(ctx, &ctx->d_owned_edges, owned_edges);
   if (rc) return rc;
+  ctx->owned_runs.clear();
+  ctx->upload_end.assign(ctx->ne, 0);
+  ctx->owned_elems = 0;
+  for (int32_t e : owned_edges) {  // sorted by edge id
+    const int64_t b = ctx->msg_off[e], en = ctx->msg_off[e + 1];
+    if (en == b) continue;
+    if (!ctx->owned_runs.empty() && ctx->owned_runs.back().second == b) ctx->owned_runs.back().second = en;
+    else ctx->owned_runs.emplace_back(b, en);
+    ctx->owned_elems += en - b;
+    ctx->upload_end[e] = ctx->owned_elems;
+  }
   return fast_prepare(ctx);
 }
 
@@ -590,14 +601,36 @@ static StreamWriteValue32Fn stream_write_value32() {
   return fn;
 }
 
-static int enqueue_streamed_step(bpx_ctx* ctx, const void* packed_in, void* out_alias, int* err_alias, int normalize, int n_chunks) {
-  const int64_t n_el = ctx->msg_off[ctx->ne];
-  std::vector<int64_t> bound(n_chunks + 1, 0);  // chunk boundaries on whole 16-byte units; cumulative element counts
-  for (int c = 1; c <= n_chunks; ++c) bound[c] = c == n_chunks ? n_el : ((n_el * c / n_chunks) & ~(int64_t)1);
-  for (int c = 0; c < n_chunks; ++c) ctx->h_io_progress[c] = bound[c + 1];
-  ctx->cur = 0;
-  ctx->history_len = 0;  // the step's residual lands in history slot 0 (a plain store by the kernel's last CTA)
-  ctx->ring_dirty = false;
+// chunks of the owned runs for the streamed upload: (element begin, element end, cumulative uploaded elements)
+struct IoChunk {
+  int64_t b, e, cum;
+};
+static std::vector<IoChunk> io_chunks(bpx_ctx* ctx, int64_t chunk_elems) {
+  std::vector<IoChunk> out;
+  int64_t cum = 0;
+  for (auto& r : ctx->owned_runs)
+    for (int64_t b = r.first; b < r.second;) {
+      int64_t e = std::min(r.second, b + chunk_elems);
+      if (r.second - e < chunk_elems / 4) e = r.second;  // no tiny tail chunks
+      if (e < r.second) e &= ~(int64_t)1;                // whole 16-byte units
+      cum += e - b;
+      out.push_back({b, e, cum});
+      b = e;
+    }
+  return out;
+}
+
+// Enqueue one streamed step (also the body that is captured into a CUDA graph): the sweep kernel (gated on the
+// progress word, storing into the host alias, handing the residual key to the host) and the chunked upload on the
+// copy stream.
+static int enqueue_streamed_step(bpx_ctx* ctx, const void* packed_in, void* out_alias, int* err_alias, int normalize,
+                                 const std::vector<IoChunk>& chunks) {
+  const bool single = ctx->nranks == 1;
+  if (single) {
+    ctx->cur = 0;
+    ctx->history_len = 0;  // the step's residual lands in history slot 0 (a plain store by the kernel's last CTA)
+    ctx->ring_dirty = false;
+  }
   // no memsets: the progress word, the CTA ticket and the step's private residual slot are reset by the previous
   // step's last CTA (and zero-initialised)
   BPX_CUDA(ctx, cudaEventRecord(ctx->ev_io_start, ctx->stream));
@@ -605,45 +638,51 @@ static int enqueue_streamed_step(bpx_ctx* ctx, const void* packed_in, void* out_
   ctx->io_args.progress = ctx->d_io_progress;
   ctx->io_args.host_out = (double*)out_alias;
   ctx->io_args.error_flag = err_alias;
-  ctx->io_args.host_key = reinterpret_cast<unsigned long long*>(err_alias) - 1;  // pinned slot [32] (the error flag is [33])
-  ctx->io_args.local_key = reinterpret_cast<unsigned long long*>(ctx->d_io_progress + 2);
-  ctx->io_args.ring_key = ctx->d_reskeys;
   ctx->io_args.ticket = reinterpret_cast<unsigned int*>(ctx->d_io_progress + 1);
-  ctx->slot_override = ctx->io_args.local_key;
+  if (single) {  // partitioned runs keep the residual ring / mailbox protocol (the global maximum needs the peers' posts)
+    ctx->io_args.host_key = reinterpret_cast<unsigned long long*>(err_alias) - 1;  // pinned slot [32] (the error flag is [33])
+    ctx->io_args.local_key = reinterpret_cast<unsigned long long*>(ctx->d_io_progress + 2);
+    ctx->io_args.ring_key = ctx->d_reskeys;
+    ctx->slot_override = ctx->io_args.local_key;
+  }
+  void* const dst_set = ctx->d_msg[ctx->cur];
   int rc = sweep_once(ctx, normalize);
   ctx->slot_override = nullptr;
   ctx->io_args = HostIO{};
   if (rc) return rc;
-  for (int c = 0; c < n_chunks; ++c) {
-    const size_t o = (size_t)bound[c] * ctx->esize, len = (size_t)(bound[c + 1] - bound[c]) * ctx->esize;
-    BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_msg[0] + o, (const char*)packed_in + o, len, cudaMemcpyHostToDevice, ctx->copy_stream));
-    StreamWriteValue32Fn wv = n_el < (1ll << 32) ? stream_write_value32() : nullptr;
+  StreamWriteValue32Fn wv = ctx->owned_elems < (1ll << 32) ? stream_write_value32() : nullptr;
+  for (size_t c = 0; c < chunks.size(); ++c) {
+    const size_t o = (size_t)chunks[c].b * ctx->esize, len = (size_t)(chunks[c].e - chunks[c].b) * ctx->esize;
+    BPX_CUDA(ctx, cudaMemcpyAsync((char*)dst_set + o, (const char*)packed_in + o, len, cudaMemcpyHostToDevice, ctx->copy_stream));
     if (wv) {  // low word of the (zeroed) 64-bit progress counter
-      if (wv(ctx->copy_stream, (unsigned long long)(uintptr_t)ctx->d_io_progress, (unsigned int)bound[c + 1], 0) != 0) {
+      if (wv(ctx->copy_stream, (unsigned long long)(uintptr_t)ctx->d_io_progress, (unsigned int)chunks[c].cum, 0) != 0) {
         set_error(ctx, "bpx_sweep_host: cuStreamWriteValue32 failed");
         return BPX_ERR_CUDA;
       }
     } else {
+      ctx->h_io_progress[c] = chunks[c].cum;
       BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_io_progress, ctx->h_io_progress + c, sizeof(long long), cudaMemcpyHostToDevice, ctx->copy_stream));
     }
   }
   BPX_CUDA(ctx, cudaEventRecord(ctx->ev_io_done, ctx->copy_stream));
   BPX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_io_done, 0));
-  return BPX_OK;  // (the residual key arrives in pinned host memory from the kernel's last CTA)
+  return BPX_OK;  // (single rank: the residual key arrives in pinned host memory from the kernel's last CTA)
 }
 
 extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_out, int normalize, double* residual_out) {
   NEED_DIMS(ctx, "bpx_sweep_host");
-  REQUIRE(ctx, ctx->nranks == 1, "bpx_sweep_host: single-rank contexts only");
   REQUIRE(ctx, (packed_in && packed_out) || ctx->msg_off[ctx->ne] == 0, "bpx_sweep_host: NULL buffer");
-  const size_t n = (size_t)ctx->msg_off[ctx->ne] * ctx->esize;
+  REQUIRE(ctx, ctx->nranks == 1 || ctx->halo_connected, "bpx_sweep_host: partitioned context without connected peers");
+  const size_t n = (size_t)ctx->owned_elems * ctx->esize;
+  const bool single = ctx->nranks == 1;
   int rc;
   double res = INFINITY;
   void* out_alias = (n > 0 && sweep_streams_host_io(ctx) && mapped_alias(packed_in)) ? mapped_alias(packed_out) : nullptr;
   if (out_alias) {
     // ---- streamed: the kernel starts at once; the upload arrives in chunks behind a progress word the items wait
-    // for, and the epilogues store the new messages straight into the caller's buffer.  The whole step is one
-    // CUDA-graph launch (cached per buffer pair): the ~20 stream calls it replaces cost more than the sweep. ----
+    // for, and the epilogues store the new messages straight into the caller's buffer.  On a single rank the whole
+    // step is one CUDA-graph launch (cached per buffer pair): the ~20 stream calls it replaces cost more than the
+    // sweep.  Partitioned contexts (sweep ids in the kernel arguments) enqueue the same operations on the streams. ----
     // every chunk costs ~10 us of copy-engine latency (measured): about 1 MiB per chunk, at most 16
     int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(16, (n + (512 << 10)) >> 20));
     if (const char* env = getenv("BPX_IO_CHUNKS")) n_chunks = std::max(1, std::min(32, atoi(env)));
@@ -658,17 +697,20 @@ extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_
     }
     if ((rc = fast_refresh_sites(ctx))) return rc;  // never part of the captured step
     int* err_alias = (int*)mapped_alias(ctx->h_io_progress + 33);
-    const bool use_graph = !ctx->profiling && !ctx->io_graph_disabled && !getenv("BPX_IO_NO_GRAPH");
+    std::vector<IoChunk> chunks = io_chunks(ctx, std::max<int64_t>(2, (ctx->owned_elems + n_chunks - 1) / n_chunks));
+    if (chunks.size() > 32) chunks = io_chunks(ctx, ctx->owned_elems);  // (many runs: one chunk per run at most)
+    const bool use_graph = single && chunks.size() <= 32 && !ctx->profiling && !ctx->io_graph_disabled && !getenv("BPX_IO_NO_GRAPH");
     if (use_graph) {
       bpx_ctx::IoGraph* g = nullptr;
       for (auto& c : ctx->io_graphs)
-        if (c.in == packed_in && c.out == packed_out && c.normalize == normalize && c.chunks == n_chunks && c.epoch == ctx->work_epoch) g = &c;
+        if (c.in == packed_in && c.out == packed_out && c.normalize == normalize && c.chunks == (int)chunks.size() && c.epoch == ctx->work_epoch)
+          g = &c;
       const int64_t sweeps0 = ctx->n_sweeps, updates0 = ctx->n_updates, launches0 = ctx->n_launches;
       if (!g) {
         if (ctx->io_graphs.size() >= 8) io_graphs_clear(ctx);
         cudaGraph_t graph = nullptr;
         BPX_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        rc = enqueue_streamed_step(ctx, packed_in, out_alias, err_alias, normalize, n_chunks);
+        rc = enqueue_streamed_step(ctx, packed_in, out_alias, err_alias, normalize, chunks);
         cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
         if (rc) {
           if (graph) cudaGraphDestroy(graph);
@@ -679,7 +721,7 @@ extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_
         ce = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         BPX_CUDA(ctx, ce);
-        ctx->io_graphs.push_back({packed_in, packed_out, normalize, n_chunks, ctx->work_epoch, ctx->n_launches - launches0, exec});
+        ctx->io_graphs.push_back({packed_in, packed_out, normalize, (int)chunks.size(), ctx->work_epoch, ctx->n_launches - launches0, exec});
         g = &ctx->io_graphs.back();
       }
       // host-side state of "one sweep from set 0 into set 1, recorded in residual slot 0"
@@ -688,17 +730,21 @@ extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_
       ctx->n_sweeps = sweeps0 + 1;
       ctx->n_updates = updates0 + ctx->n_owned_edges;
       ctx->n_launches = launches0 + g->launches;
-      for (int c = 0; c < n_chunks; ++c)  // (the chunk table is read by the copy engine at run time)
-        ctx->h_io_progress[c] = c + 1 == n_chunks ? ctx->msg_off[ctx->ne] : ((ctx->msg_off[ctx->ne] * (c + 1) / n_chunks) & ~(int64_t)1);
+      for (size_t c = 0; c < chunks.size(); ++c) ctx->h_io_progress[c] = chunks[c].cum;  // (read by the copy engine at run time)
       BPX_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
     } else {
-      if ((rc = enqueue_streamed_step(ctx, packed_in, out_alias, err_alias, normalize, n_chunks))) return rc;
+      if ((rc = enqueue_streamed_step(ctx, packed_in, out_alias, err_alias, normalize, chunks))) return rc;
     }
-    BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->ring_dirty = true;  // slot 0 is re-used by every streamed step: other sweep entry points clear the ring first
-    unsigned long long key;
-    memcpy(&key, ctx->h_io_progress + 32, sizeof(key));
-    res = residual_from_key(key);
+    if (single) {
+      BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      ctx->ring_dirty = true;  // slot 0 is re-used by every streamed step: other sweep entry points clear the ring first
+      unsigned long long key;
+      memcpy(&key, ctx->h_io_progress + 32, sizeof(key));
+      res = residual_from_key(key);
+    } else {
+      if ((rc = halo_gate(ctx))) return rc;  // the global residual needs every rank's post of this sweep
+      if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) return rc;  // synchronises the stream
+    }
     if (ctx->h_io_progress[33] != 0) {
       ctx->h_io_progress[33] = 0;
       cudaMemset(ctx->d_io_progress, 0, 4 * sizeof(long long));  // the self-resetting words may be stale now
@@ -707,10 +753,19 @@ extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_
       return BPX_ERR_CUDA;
     }
   } else {
-    ctx->cur = 0;
-    BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[0], packed_in, n, cudaMemcpyHostToDevice, ctx->stream));
+    // ---- staged: upload the owned messages, sweep, download the owned messages ----
+    if (single) ctx->cur = 0;
+    if ((rc = halo_gate(ctx))) return rc;
+    for (auto& r : ctx->owned_runs) {
+      const size_t o = (size_t)r.first * ctx->esize, len = (size_t)(r.second - r.first) * ctx->esize;
+      BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_msg[ctx->cur] + o, (const char*)packed_in + o, len, cudaMemcpyHostToDevice, ctx->stream));
+    }
     if ((rc = sweep_once(ctx, normalize))) return rc;
-    BPX_CUDA(ctx, cudaMemcpyAsync(packed_out, ctx->d_msg[ctx->cur], n, cudaMemcpyDeviceToHost, ctx->stream));
+    for (auto& r : ctx->owned_runs) {
+      const size_t o = (size_t)r.first * ctx->esize, len = (size_t)(r.second - r.first) * ctx->esize;
+      BPX_CUDA(ctx, cudaMemcpyAsync((char*)packed_out + o, (const char*)ctx->d_msg[ctx->cur] + o, len, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if ((rc = halo_gate(ctx))) return rc;
     if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) return rc;  // synchronises the stream
   }
   if (residual_out) *residual_out = res;

@@ -127,6 +127,12 @@ struct bpx_ctx {
     cudaGraphExec_t exec;
   };
   std::vector<IoGraph> io_graphs;
+  // host <-> device transfers of an iterate move the messages this rank owns (all of them on a single rank): coalesced
+  // runs of owned edges in edge order; upload_end[e] = elements of the upload (in that order) up to the end of message e
+  // (0 for edges that are not uploaded -- cut edges into this rank arrive from the peers)
+  std::vector<std::pair<int64_t, int64_t>> owned_runs;  // [element begin, element end)
+  std::vector<int64_t> upload_end;
+  int64_t owned_elems = 0;
   uint64_t work_epoch = 0;             // bumped whenever launch lists / buffers are rebuilt (invalidates io_graphs)
   bool io_graph_disabled = false;
   unsigned long long* slot_override = nullptr;  // residual slot of the step being enqueued (streamed steps)

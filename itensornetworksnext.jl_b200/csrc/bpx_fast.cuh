@@ -93,7 +93,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
           const int32_t e = ctx->out_edge[v][l];
           d.out_edge[o] = e;
           d.out_off[o] = ctx->msg_off[e];
-          d.need = std::max<int64_t>(d.need, ctx->msg_off[e + 1]);
+          d.need = std::max<int64_t>(d.need, ctx->upload_end[e]);
           d.peer[o] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
         };
         auto in_of = [&](int l) { return ctx->msg_off[ctx->rev[ctx->out_edge[v][l]]]; };
@@ -104,7 +104,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
         d.d = b.d;
         d.peer[0] = d.peer[1] = -1;
         d.first = 1;
-        for (int l = 0; l < b.z; ++l) d.need = std::max<int64_t>(d.need, ctx->msg_off[ctx->rev[ctx->out_edge[v][l]] + 1]);
+        for (int l = 0; l < b.z; ++l) d.need = std::max<int64_t>(d.need, ctx->upload_end[ctx->rev[ctx->out_edge[v][l]]]);
         if (b.z == 3) {
           // one item per output leg; (first, second) absorbed message: out2 (M0, M1), out1 (M0, M2), out0 (M2, M1)
           static const int first_leg[3] = {2, 0, 0}, second_leg[3] = {1, 2, 1};
@@ -189,7 +189,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
           d.out_off[l] = ctx->msg_off[e];
           d.in_off[l] = ctx->msg_off[ctx->rev[e]];
           d.peer[l] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
-          d.need = std::max<int64_t>(d.need, std::max(ctx->msg_off[e + 1], ctx->msg_off[ctx->rev[e] + 1]));
+          d.need = std::max<int64_t>(d.need, std::max(ctx->upload_end[e], ctx->upload_end[ctx->rev[e]]));
         }
         it16.push_back(d);
       }
@@ -279,7 +279,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
         d.out_off[i] = ctx->msg_off[e];
         d.in_off[i] = ctx->msg_off[ctx->rev[e]];
         d.peer[i] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
-        d.need = std::max<int64_t>(d.need, std::max(ctx->msg_off[e + 1], ctx->msg_off[ctx->rev[e] + 1]));
+        d.need = std::max<int64_t>(d.need, std::max(ctx->upload_end[e], ctx->upload_end[ctx->rev[e]]));
       }
       for (int i = b.z; i < 4; ++i) d.peer[i] = -1;
       if (b.z == 4) {  // two half items (branch P, branch Q): finer granularity for the last wave

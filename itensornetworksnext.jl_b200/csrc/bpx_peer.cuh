@@ -45,24 +45,28 @@ struct HostIO {
 // Called by every thread at the end of the kernel (CTA-uniform): the last CTA to finish hands the sweep's residual key
 // to the host, so the step needs no device-to-host copy at all.
 __device__ __forceinline__ void hostio_finish(const HostIO& io) {
-  if (!io.host_key) return;
+  if (!io.progress) return;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(io.ticket, 1u) == gridDim.x - 1) {
       __threadfence();
-      const unsigned long long key = *reinterpret_cast<const volatile unsigned long long*>(io.local_key);
-      *reinterpret_cast<volatile unsigned long long*>(io.host_key) = key;
-      *io.ring_key = key;
+      if (io.host_key) {
+        const unsigned long long key = *reinterpret_cast<const volatile unsigned long long*>(io.local_key);
+        *reinterpret_cast<volatile unsigned long long*>(io.host_key) = key;
+        *io.ring_key = key;
+        *io.local_key = 0ull;
+      }
       // ready for the next step (stream-ordered): no memset nodes in front of the kernel.  Every item has passed its
       // gate, so the upload -- and with it the last write of the progress word -- is complete.
-      *io.local_key = 0ull;
       *io.progress = 0ll;
       *io.ticket = 0u;
     }
   }
 }
-// the calling warp waits (lane 0 spins, bounded) until `need` elements have arrived
+
+// Called by ONE warp per CTA before it touches messages written by peers.  Lane p waits for rank p's post.
+// the calling warp waits (lane 0 spins, bounded) until `need` elements of the upload have arrived
 __device__ __forceinline__ void hostio_wait(const HostIO& io, long long need) {
   if (!io.progress) return;
   if ((threadIdx.x & 31) == 0) {
@@ -79,7 +83,6 @@ __device__ __forceinline__ void hostio_wait(const HostIO& io, long long need) {
   __syncwarp();
 }
 
-// Called by ONE warp per CTA before it touches messages written by peers.  Lane p waits for rank p's post.
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -89,6 +92,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Called by ONE warp per CTA before it touches messages written by peers.  Lane p waits for rank p's post.
 __device__ __forceinline__ void peer_gate(const PeerArgs& pa, int lane) {
   if (pa.nranks <= 1 || pa.wait_id == 0) return;
   double v = -INFINITY;
