@@ -117,8 +117,20 @@ int bpx_sweep(bpx_ctx* ctx, int max_sweeps, double tol, int normalize, double* r
 int bpx_sweep_async(bpx_ctx* ctx, int n_sweeps, int normalize);
 /* One step with HOST buffers: upload the iterate (packed_in), one synchronous sweep, download the new iterate
  * (packed_out) and the fused residual; a single host synchronisation.  What the per-sweep Julia hook
- * (AI.step! specialisation + StopWhenConverged) calls when the messages live on the host. */
+ * (AI.step! specialisation + StopWhenConverged) calls when the messages live on the host.
+ *  - Partitioned contexts move only the messages of the edges this rank owns (the out-edges of its vertices): those
+ *    slices of packed_in are read, those slices of packed_out are written; messages on cut edges travel between the
+ *    devices; residual_out is the GLOBAL residual of the sweep (the call waits for every rank's post).
+ *  - If both buffers are page-locked (bpx_host_register, cudaHostAlloc, torch pin_memory) and the sweep is one
+ *    launch of an on-chip kernel, the step is STREAMED: the kernel starts at once and every work item waits until
+ *    the chunk of the upload that holds its messages has landed; new messages are stored straight into packed_out
+ *    by the kernel (no download); on a single rank the whole step is one cached CUDA-graph launch.
+ *    Results are identical to the staged path (pageable buffers, or sweeps of several launches). */
 int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_out, int normalize, double* residual_out);
+/* Page-lock (and map) a caller-owned host buffer so that bpx_sweep_host can stream through it; a thin wrapper of
+ * cudaHostRegister / cudaHostUnregister for hosts without their own CUDA binding (the Julia glue). */
+int bpx_host_register(bpx_ctx* ctx, void* ptr, size_t bytes);
+int bpx_host_unregister(bpx_ctx* ctx, void* ptr);
 /* Reference schedule: in-place (Gauss-Seidel) updates along an explicit directed-edge list
  * (beliefpropagation.jl:200-210, 255).  Runs of consecutive, mutually independent updates are batched. */
 int bpx_sweep_sequence(bpx_ctx* ctx, const int64_t* edge_seq, int64_t n_seq, int max_sweeps, double tol,

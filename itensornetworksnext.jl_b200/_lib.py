@@ -61,6 +61,8 @@ def load() -> C.CDLL:
         "bpx_site_offset": (i64, [vp, i64]),
         "bpx_message_offset": (i64, [vp, i64]),
         "bpx_site_device_offset": (i64, [vp, i64]),
+        "bpx_host_register": (C.c_int, [vp, vp, C.c_size_t]),
+        "bpx_host_unregister": (C.c_int, [vp, vp]),
         "bpx_set_site_tensors": (C.c_int, [vp, vp]),
         "bpx_set_site_tensor": (C.c_int, [vp, i64, vp]),
         "bpx_set_messages": (C.c_int, [vp, vp]),

@@ -772,6 +772,23 @@ extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_
   return BPX_OK;
 }
 
+extern "C" int bpx_host_register(bpx_ctx* ctx, void* ptr, size_t bytes) {
+  if (!ctx) return BPX_ERR_INVALID;
+  REQUIRE(ctx, ptr && bytes > 0, "bpx_host_register: bad arguments");
+  cudaSetDevice(ctx->device);
+  BPX_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+  return BPX_OK;
+}
+
+extern "C" int bpx_host_unregister(bpx_ctx* ctx, void* ptr) {
+  if (!ctx) return BPX_ERR_INVALID;
+  REQUIRE(ctx, ptr != nullptr, "bpx_host_unregister: NULL pointer");
+  cudaSetDevice(ctx->device);
+  io_graphs_clear(ctx);  // captured steps may refer to the buffer
+  BPX_CUDA(ctx, cudaHostUnregister(ptr));
+  return BPX_OK;
+}
+
 extern "C" int bpx_get_messages(bpx_ctx* ctx, void* packed) {
   NEED_DIMS(ctx, "bpx_get_messages");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }

@@ -154,6 +154,13 @@ class BPXContext:
         self._check(self.lib.bpx_sweep_host(self.h, _ptr(flat_in), _ptr(flat_out), int(bool(normalize)), C.byref(res)))
         return res.value
 
+    def host_register(self, arr: np.ndarray):
+        """Page-lock `arr` so that `sweep_host` can stream through it (cudaHostRegister)."""
+        self._check(self.lib.bpx_host_register(self.h, _ptr(arr), C.c_size_t(arr.nbytes)))
+
+    def host_unregister(self, arr: np.ndarray):
+        self._check(self.lib.bpx_host_unregister(self.h, _ptr(arr)))
+
     def sweep_async(self, n_sweeps: int = 1, normalize: bool = True):
         self._check(self.lib.bpx_sweep_async(self.h, int(n_sweeps), int(bool(normalize))))
 

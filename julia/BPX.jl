@@ -51,9 +51,24 @@ mutable struct B200MessageUpdate <: MessageUpdateAlgorithm
     bra_ket::Vector{Tuple{Any, Any}}  # per directed edge: (bra name, ket name) of the message axes
     dirty::Bool                   # host cache newer than the device copy
     last_residual::Float64
+    host_in::Vector               # page-locked packed iterates (bpx_host_register): bpx_sweep_host streams through them
+    host_out::Vector
 end
 B200MessageUpdate(; normalize = true, device = 0) =
-    B200MessageUpdate(normalize, device, C_NULL, Dict(), Dict(), Tuple{Any, Any}[], true, Inf)
+    B200MessageUpdate(normalize, device, C_NULL, Dict(), Dict(), Tuple{Any, Any}[], true, Inf, Float64[], Float64[])
+
+# Two packed host iterates, page-locked once: with such buffers `bpx_sweep_host` overlaps the upload with the sweep
+# kernel and lets the kernel store the new messages straight into `host_out` (include/bpx.h).
+function host_buffers!(alg::B200MessageUpdate, ::Type{E}) where {E}
+    total = ccall((:bpx_message_offset, libbpx), Int64, (Ptr{Cvoid}, Int64), alg.ctx, length(alg.edge_ids))
+    if length(alg.host_in) != total || eltype(alg.host_in) != E
+        alg.host_in, alg.host_out = Vector{E}(undef, total), Vector{E}(undef, total)
+        for buf in (alg.host_in, alg.host_out)
+            check(alg.ctx, ccall((:bpx_host_register, libbpx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), alg.ctx, buf, sizeof(buf)))
+        end
+    end
+    return alg
+end
 
 # ---- lowering to the canonical layout (include/bpx.h; SURVEY.md §8 b2 iv) -------------------------------
 function upload!(alg::B200MessageUpdate, nn::NormNetwork, cache::MessageCache)
@@ -106,6 +121,26 @@ function push_messages!(alg::B200MessageUpdate, cache::MessageCache, ::Type{E}) 
     return alg
 end
 
+# packed host iterate <-> MessageCache (same layout as push_messages! / pull_messages!)
+function pack_messages!(packed::Vector, alg::B200MessageUpdate, cache::MessageCache)
+    for (e, id) in alg.edge_ids
+        off = ccall((:bpx_message_offset, libbpx), Int64, (Ptr{Cvoid}, Int64), alg.ctx, id)
+        bra, ket = alg.bra_ket[id + 1]
+        m = vec(Array{eltype(packed)}(unnamed(cache[e], (bra, ket))))
+        copyto!(packed, off + 1, m, 1, length(m))
+    end
+    return packed
+end
+function unpack_messages!(cache::MessageCache, alg::B200MessageUpdate, packed::Vector)
+    for (e, id) in alg.edge_ids
+        off = ccall((:bpx_message_offset, libbpx), Int64, (Ptr{Cvoid}, Int64), alg.ctx, id)
+        bra, ket = alg.bra_ket[id + 1]
+        χ = size(unnamed(cache[e], (bra, ket)), 1)
+        cache[e] = ITensor(reshape(packed[(off + 1):(off + χ * χ)], χ, χ), (bra, ket))  # messagecache.jl:92-96
+    end
+    return cache
+end
+
 function pull_messages!(alg::B200MessageUpdate, cache::MessageCache)
     ne = length(alg.edge_ids)
     total = ccall((:bpx_message_offset, libbpx), Int64, (Ptr{Cvoid}, Int64), alg.ctx, ne)
@@ -134,13 +169,17 @@ function AI.step!(
     alg = algorithm.subalgorithm.message_update_algorithm
     cache = state.iterate
     alg.ctx == C_NULL && upload!(alg, problem.factors, cache)
-    res, done = Ref{Cdouble}(Inf), Ref{Cint}(0)
-    check(alg.ctx, ccall((:bpx_sweep, libbpx), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cint, Ref{Cdouble}, Ref{Cint}),
-        alg.ctx, 1, 0.0, alg.normalize, res, done))
+    # Variant (A) of SURVEY.md §8 b2: plain ITensor messages that live on the host, so that the stock
+    # `StopWhenConverged` (AIE.jl:84-109) keeps working: ONE `bpx_sweep_host` call per outer iteration (packed
+    # iterate in, packed iterate + fused residual out).  Use `B200Converged` with `bpx_sweep` to keep them resident.
+    E = eltype(unnamed(first(values(cache.messages)))) <: Complex ? ComplexF64 : Float64
+    host_buffers!(alg, E)
+    pack_messages!(alg.host_in, alg, cache)
+    res = Ref{Cdouble}(Inf)
+    GC.@preserve alg check(alg.ctx, ccall((:bpx_sweep_host, libbpx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{Cdouble}),
+        alg.ctx, alg.host_in, alg.host_out, alg.normalize, res))
     alg.last_residual = res[]
-    # Variant (A) of SURVEY.md §8 b2: plain ITensor messages, downloaded every sweep so that the stock
-    # `StopWhenConverged` (AIE.jl:84-109) keeps working.  Use `B200Converged` below to skip the download.
-    pull_messages!(alg, cache)
+    unpack_messages!(cache, alg, alg.host_out)
     return state
 end
 

@@ -353,6 +353,34 @@ def test_sweep_host_streamed_io_with_pinned_buffers(oracle, name, dims, periodic
             staged_in, staged_out = staged_out, staged_in
 
 
+def test_sweep_host_streams_through_registered_numpy_buffers(oracle):
+    # what the Julia glue does (no CUDA binding of its own): bpx_host_register on ordinary arrays
+    p = problems.make_config("cfg2", graph=graphs.named_grid((7, 5)))
+    op = oracle.make_problem(p.ga, p.tensors, "norm")
+    with B.BPXContext(0) as ctx:
+        problems.upload(ctx, p)
+        a = ctx.pack_messages(p.messages)
+        b = np.full_like(a, np.nan)
+        ctx.host_register(a)
+        ctx.host_register(b)
+        try:
+            want = list(p.messages)
+            for _ in range(4):  # the second use of a buffer pair replays the cached graph
+                prev, want = want, oracle.sweep_jacobi(op, want)
+                res = ctx.sweep_host(a, b)
+                assert rel_err(ctx.unpack_messages(b), want) < MSG_RTOL
+                assert abs(res - oracle.iterate_diff(want, prev)) < 1e-11
+                assert abs(ctx.last_residual() - res) < 1e-15
+                a, b = b, a
+        finally:
+            ctx.host_unregister(a)
+            ctx.host_unregister(b)
+        res, done = ctx.sweep(1, 0.0)  # ordinary sweeps after streamed steps (residual ring re-used slots)
+        prev, want = want, oracle.sweep_jacobi(op, want)
+        assert done == 1 and abs(res - oracle.iterate_diff(want, prev)) < 1e-11
+        assert rel_err(ctx.get_messages(), want) < MSG_RTOL
+
+
 @pytest.mark.parametrize("name,dims", [("cfg5", (10, 10)), ("cfg2", (32, 32))])
 def test_full_path_sampled_edges_against_oracle(oracle, name, dims):
     """Size-independent check of the production path (device-generated inputs, specialised kernels): recompute a
