@@ -92,6 +92,7 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_sliced_items);
   F(c->d_onchip16_items);
   F(c->d_onchip16c_items);
+  F(c->d_onchip8c_items);
   F(c->d_sites_swz);
   for (auto& b : c->buckets) {
     F(b.d_vertices);

@@ -76,6 +76,8 @@ struct bpx_ctx {
   int n_sliced_items = 0;
   void* d_onchip16c_items = nullptr;  // complex chi = 16 kernel: items laid out as rounds (slot r * grid + cta)
   int n_onchip16c_slots = 0, onchip16c_grid = 0;
+  void* d_onchip8c_items = nullptr;   // complex chi = 8 kernel, same round layout
+  int n_onchip8c_slots = 0, onchip8c_grid = 0;
   void* d_timing = nullptr;  // debug: per-phase clock64 stamps (BPX_ONCHIP_TIMING builds)
   void* d_onchip_items = nullptr;
   void* d_sites_swz = nullptr;  // pre-swizzled site tensors for the ONCHIP kernel (bpx_onchip.cuh)

@@ -7,6 +7,7 @@
 #include "bpx_sliced.cuh"
 #include "bpx_onchip16.cuh"
 #include "bpx_onchip16c.cuh"
+#include "bpx_onchip8c.cuh"
 
 namespace bpx {
 
@@ -15,8 +16,12 @@ inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
   if (ctx->mode != BPX_MODE_NORM) return false;
   if (kernel == BPX_KERNEL_ONCHIP) {
     // ComplexF64: chi = 16, degree 1..3, any physical dimension (bpx_onchip16c.cuh)
-    if (ctx->dtype == BPX_C64)
-      return b.chi == 16 && b.z >= 1 && b.z <= 3 && b.d >= 1 && (size_t)ctx->max_smem_optin >= onchip16c::SMEM_BYTES16C;
+    // ... and chi = 8, degree 2..4 (bpx_onchip8c.cuh)
+    if (ctx->dtype == BPX_C64) {
+      if (b.chi == 16 && b.z >= 1 && b.z <= 3 && b.d >= 1) return (size_t)ctx->max_smem_optin >= onchip16c::SMEM_BYTES16C;
+      if (b.chi == 8 && b.z >= 2 && b.z <= 4 && b.d >= 1) return (size_t)ctx->max_smem_optin >= onchip8c::SMEM_BYTES8C;
+      return false;
+    }
     if (ctx->dtype != BPX_F64 || b.d != 2) return false;
     if (b.z >= 2 && b.z <= 4 && b.chi == 8) return (size_t)ctx->max_smem_optin >= onchip::SMEM_BYTES;
     // 16-wide on-chip kernel: degree 3 / chi 16, or degree 6 / chi 4 with legs paired into super-legs
@@ -85,7 +90,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
     int leader = -1;
     for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
       Bucket& b = ctx->buckets[i];
-      if (b.kernel != BPX_KERNEL_ONCHIP || b.my_vertices.empty()) continue;
+      if (b.kernel != BPX_KERNEL_ONCHIP || b.chi != 16 || b.my_vertices.empty()) continue;
       if (leader < 0) leader = i;
       b.leader = leader;
       for (int32_t v : b.my_vertices) {
@@ -165,6 +170,105 @@ inline int fast_prepare(bpx_ctx* ctx) {
       BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip16c_items, slots.data(), slots.size() * sizeof(onchip16c::ItemDesc), cudaMemcpyHostToDevice));
       BPX_CUDA(ctx, cudaFuncSetAttribute(onchip16c::bp_update_onchip_c16c, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)onchip16c::SMEM_BYTES16C));
+      need_image = true;
+    }
+  }
+  if (ctx->d_onchip8c_items) {
+    cudaFree(ctx->d_onchip8c_items);
+    ctx->d_onchip8c_items = nullptr;
+  }
+  ctx->n_onchip8c_slots = 0;
+  ctx->onchip8c_grid = 0;
+  if (ctx->dtype == BPX_C64) {
+    // ---- complex chi = 8 buckets (degree 2..4): one launch; degree-4 vertices as two half items (branch P / Q) ----
+    std::vector<onchip8c::ItemDesc> its;
+    std::vector<double> cost;
+    int leader = -1;
+    for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
+      Bucket& b = ctx->buckets[i];
+      if (b.kernel != BPX_KERNEL_ONCHIP || b.chi != 8 || b.my_vertices.empty()) continue;
+      if (leader < 0) leader = i;
+      b.leader = leader;
+      for (int32_t v : b.my_vertices) {
+        onchip8c::ItemDesc d;
+        memset(&d, 0, sizeof(d));
+        d.site_off = 2 * ctx->dev_site_off[v];
+        d.canon_off = ctx->dev_site_off[v];
+        d.d = b.d;
+        d.first = 1;
+        for (int l = 0; l < b.z; ++l) {
+          const int32_t e = ctx->out_edge[v][l];
+          d.in_off[l] = ctx->msg_off[ctx->rev[e]];
+          d.need = std::max<int64_t>(d.need, std::max(ctx->upload_end[e], ctx->upload_end[ctx->rev[e]]));
+        }
+        auto tile = [&](int tl, int leg) {
+          const int32_t e = ctx->out_edge[v][leg];
+          d.out_edge[tl] = e;
+          d.out_off[tl] = ctx->msg_off[e];
+          d.peer[tl] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
+        };
+        for (int tl = 0; tl < onchip8c::MAXT; ++tl) d.peer[tl] = -1;
+        if (b.z == 4) {
+          d.kind = 0;  // branch P: out3, out2
+          tile(0, 3);
+          tile(1, 2);
+          its.push_back(d);
+          cost.push_back(6.0 * 4096 * b.d + 1500.0);
+          d.kind = 1;  // branch Q: out1, out0
+          d.first = 0;
+          tile(0, 1);
+          tile(1, 0);
+          its.push_back(d);
+          cost.push_back(6.0 * 4096 * b.d + 1500.0);
+        } else if (b.z == 3) {
+          d.kind = 2;
+          tile(0, 2);
+          tile(1, 1);
+          tile(2, 0);
+          its.push_back(d);
+          cost.push_back(8.0 * 512 * b.d + 1000.0 * b.d + 1500.0);
+        } else {
+          d.kind = 3;
+          tile(0, 1);
+          tile(1, 0);
+          its.push_back(d);
+          cost.push_back(2000.0);
+        }
+      }
+    }
+    if (!its.empty()) {
+      const int G = std::min<int>((int)its.size(), ctx->num_sms);
+      // longest processing time first onto the least loaded CTA; equal-cost items keep their (lattice) order, which is
+      // the order in which a streamed upload delivers their messages
+      std::vector<int> order(its.size());
+      for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+      std::vector<std::vector<int>> per_cta(G);
+      std::vector<double> load(G, 0.0);
+      for (int i : order) {
+        const int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        per_cta[c].push_back(i);
+        load[c] += cost[i];
+      }
+      size_t rounds = 0;
+      for (auto& l : per_cta) rounds = std::max(rounds, l.size());
+      onchip8c::ItemDesc null_item;
+      memset(&null_item, 0, sizeof(null_item));
+      null_item.kind = -1;
+      std::vector<onchip8c::ItemDesc> slots(rounds * G, null_item);
+      for (int c = 0; c < G; ++c)
+        for (size_t r = 0; r < per_cta[c].size(); ++r) slots[r * G + c] = its[per_cta[c][r]];
+      ctx->n_onchip8c_slots = (int)slots.size();
+      ctx->onchip8c_grid = G;
+      cudaError_t e = cudaMalloc((void**)&ctx->d_onchip8c_items, slots.size() * sizeof(onchip8c::ItemDesc));
+      if (e != cudaSuccess) {
+        set_error(ctx, "cudaMalloc(complex chi=8 items) failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return BPX_ERR_ALLOC;
+      }
+      BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip8c_items, slots.data(), slots.size() * sizeof(onchip8c::ItemDesc), cudaMemcpyHostToDevice));
+      BPX_CUDA(ctx, cudaFuncSetAttribute(onchip8c::bp_update_onchip_c8c, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)onchip8c::SMEM_BYTES8C));
       need_image = true;
     }
   }
@@ -323,6 +427,12 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
   }
+  if (ctx->d_sites_swz && ctx->n_onchip8c_slots > 0) {
+    onchip8c::swizzle_sites_c8<<<std::min(ctx->n_onchip8c_slots, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
+        (const onchip8c::ItemDesc*)ctx->d_onchip8c_items, ctx->n_onchip8c_slots, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+  }
   if (ctx->d_sites_swz && ctx->n_sliced_items > 0) {
     sliced::swizzle_sites16<<<std::min(ctx->n_sliced_items, 8 * ctx->num_sms), 512, 0, ctx->stream>>>(
         (const sliced::ItemDesc*)ctx->d_sliced_items, ctx->n_sliced_items, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
@@ -334,6 +444,23 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
 }
 
 inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize) {
+  if (b.kernel == BPX_KERNEL_ONCHIP && ctx->dtype == BPX_C64 && b.chi == 8) {
+    onchip8c::Args k;
+    k.items = (const onchip8c::ItemDesc*)ctx->d_onchip8c_items;
+    k.n_slots = ctx->n_onchip8c_slots;
+    k.sites = (const double*)ctx->d_sites_swz;
+    k.msg_in = (const double*)msg_in;
+    k.msg_out = (double*)msg_out;
+    k.resmax = ctx->cur_slot;
+    k.normalize = normalize;
+    k.peer = ctx->peer_args;
+    k.io = ctx->io_args;
+    if (ctx->onchip8c_grid == 0) return BPX_OK;
+    onchip8c::bp_update_onchip_c8c<<<ctx->onchip8c_grid, onchip8c::NT, onchip8c::SMEM_BYTES8C, ctx->stream>>>(k);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+    return BPX_OK;
+  }
   if (b.kernel == BPX_KERNEL_ONCHIP && ctx->dtype == BPX_C64) {
     onchip16c::Args k;
     k.items = (const onchip16c::ItemDesc*)ctx->d_onchip16c_items;

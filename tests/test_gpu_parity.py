@@ -97,6 +97,42 @@ def test_complex_chi16_kernel_mixed_physical_dims(oracle):
     check_sweeps(oracle, ga, np.complex128, "norm", phys, link_dim, tensors, msgs, 2, normalize=False)
 
 
+@pytest.mark.parametrize("dims,phys", [((5, 6), "uniform2"), ((4, 4), "mixed"), ((13, 13), "uniform2")])
+def test_complex_chi8_kernel_square_lattice(oracle, dims, phys):
+    # complex PEPS on a square lattice (the ComplexF64 twin of cfg2): degrees 2, 3, 4 in one launch of the complex
+    # chi = 8 kernel; (13, 13) gives 121 degree-4 vertices = 242 half items > 148 CTAs (several rounds per CTA)
+    ga = graphs.graph_arrays(graphs.named_grid(dims))
+    rng = np.random.default_rng(5)
+    physd = [2] * ga.nv if phys == "uniform2" else [1 + (v % 3) for v in range(ga.nv)]
+    link_dim = [8] * ga.ne
+    tensors = []
+    for v in range(ga.nv):
+        z = ga.row_ptr[v + 1] - ga.row_ptr[v]
+        tensors.append(randn(rng, np.complex128, (physd[v], *([8] * z))) / np.sqrt(8.0**z))
+    msgs = positive_messages(ga, link_dim, np.complex128, rng)
+    buckets = check_sweeps(oracle, ga, np.complex128, "norm", physd, link_dim, tensors, msgs, 3 if dims != (13, 13) else 2)
+    assert {b["degree"] for b in buckets} == {2, 3, 4}
+    assert all(b["kernel"] == _lib.BPX_KERNEL_ONCHIP for b in buckets)
+    if dims == (5, 6):
+        check_sweeps(oracle, ga, np.complex128, "norm", physd, link_dim, tensors, msgs, 2, normalize=False)
+        # and the streamed host step (pinned buffers) on the same kernel
+        import torch
+
+        p = oracle.make_problem(ga, tensors, "norm")
+        with make_ctx(ga, np.complex128, "norm", physd, link_dim, tensors, msgs) as ctx:
+            flat = ctx.pack_messages(msgs)
+            ta, tb = torch.empty(flat.size, dtype=torch.complex128).pin_memory(), torch.empty(flat.size, dtype=torch.complex128).pin_memory()
+            a, b = ta.numpy(), tb.numpy()
+            a[:] = flat
+            want = list(msgs)
+            for _ in range(3):
+                prev, want = want, oracle.sweep_jacobi(p, want)
+                res = ctx.sweep_host(a, b)
+                assert rel_err(ctx.unpack_messages(b), want) < MSG_RTOL
+                assert abs(res - oracle.iterate_diff(want, prev)) < 1e-11
+                a, b = b, a
+
+
 # ---- edge cases ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_ragged_link_dims_and_degree_one(oracle, dtype):
