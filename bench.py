@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "cfg5s"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "cfg5s", "cfg2c"])
     ap.add_argument("--kernel", type=int, default=0, help="force a kernel family (include/bpx.h BPX_KERNEL_*)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -92,6 +92,7 @@ def build_workload(name: str, world: int):
             "cfg3": "heavy-hex 127-site PEPS norm network, chi=16, d=2, ComplexF64",
             "cfg4": "16x16x16 periodic cubic PEPS norm network, chi=4, d=2, Float64",
             "cfg5": "256x256 square-lattice PEPS norm network, chi=16, d=2, Float64",
+            "cfg2c": "32x32 square-lattice PEPS norm network, chi=8, d=2, ComplexF64 (complex twin of config 2; not a BASELINE config)",
         }[name]
         return p, None, desc
     g = graphs.named_grid((32, 32 * world))

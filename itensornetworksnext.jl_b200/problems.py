@@ -86,6 +86,8 @@ CONFIGS = {
     "cfg3": dict(graph=heavy_hex_127, chi=16, d=2, dtype=np.complex128),
     "cfg4": dict(graph=lambda: named_grid((16, 16, 16), periodic=True), chi=4, d=2, dtype=np.float64),
     "cfg5": dict(graph=lambda: named_grid((256, 256)), chi=16, d=2, dtype=np.float64),
+    # not a BASELINE config: the ComplexF64 twin of cfg2 (complex PEPS on the square lattice)
+    "cfg2c": dict(graph=lambda: named_grid((32, 32)), chi=8, d=2, dtype=np.complex128),
 }
 
 
