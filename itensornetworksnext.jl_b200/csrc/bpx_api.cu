@@ -93,6 +93,8 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_onchip16_items);
   F(c->d_onchip16c_items);
   F(c->d_onchip8c_items);
+  F(c->d_img8c);
+  F(c->d_img16c);
   F(c->d_sites_swz);
   for (auto& b : c->buckets) {
     F(b.d_vertices);
@@ -340,6 +342,7 @@ extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* ph
       b.chi = b.z > 0 ? vdesc[v].dim[0] : 0;
       for (int i = 1; i < b.z; ++i)
         if (vdesc[v].dim[i] != b.chi) b.chi = 0;
+      for (int i = 0; i < b.z; ++i) b.max_dim = std::max<int>(b.max_dim, vdesc[v].dim[i]);
       ctx->buckets.push_back(b);
     }
     ctx->buckets[it->second].vertices.push_back((int32_t)v);
@@ -700,6 +703,9 @@ extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_
     int* err_alias = (int*)mapped_alias(ctx->h_io_progress + 33);
     std::vector<IoChunk> chunks = io_chunks(ctx, std::max<int64_t>(2, (ctx->owned_elems + n_chunks - 1) / n_chunks));
     if (chunks.size() > 32) chunks = io_chunks(ctx, ctx->owned_elems);  // (many runs: one chunk per run at most)
+    if (getenv("BPX_IO_DEBUG"))
+      fprintf(stderr, "[bpx io] owned_elems %lld chunks %zu first cum %lld last cum %lld esize %d alias %p\n", (long long)ctx->owned_elems,
+              chunks.size(), (long long)chunks.front().cum, (long long)chunks.back().cum, ctx->esize, out_alias);
     const bool use_graph = single && chunks.size() <= 32 && !ctx->profiling && !ctx->io_graph_disabled && !getenv("BPX_IO_NO_GRAPH");
     if (use_graph) {
       bpx_ctx::IoGraph* g = nullptr;

@@ -12,6 +12,7 @@ namespace bpx {
 
 struct Bucket {
   int z = 0, d = 1, chi = 0;          // chi == 0: link dims not uniform
+  int max_dim = 0;                    // largest link dimension (all vertices of a bucket share the per-leg dims)
   std::vector<int32_t> vertices;      // all vertices of the bucket
   std::vector<int32_t> my_vertices;   // ... owned by this rank
   std::vector<int32_t> my_edges;      // out-edges of my_vertices (vertex-major, slot order)
@@ -78,6 +79,7 @@ struct bpx_ctx {
   int n_onchip16c_slots = 0, onchip16c_grid = 0;
   void* d_onchip8c_items = nullptr;   // complex chi = 8 kernel, same round layout
   int n_onchip8c_slots = 0, onchip8c_grid = 0;
+  void *d_img8c = nullptr, *d_img16c = nullptr;  // zero-padded private tensor images of the complex kernels
   void* d_timing = nullptr;  // debug: per-phase clock64 stamps (BPX_ONCHIP_TIMING builds)
   void* d_onchip_items = nullptr;
   void* d_sites_swz = nullptr;  // pre-swizzled site tensors for the ONCHIP kernel (bpx_onchip.cuh)

@@ -11,6 +11,15 @@
 
 namespace bpx {
 
+// ComplexF64 on-chip families: link dims <= 8 with degree 2..4 -> 8 (bpx_onchip8c.cuh); link dims <= 16 with degree
+// 1..3 -> 16 (bpx_onchip16c.cuh); smaller / per-leg different dims are zero-padded.  0: neither.
+inline int complex_family(const Bucket& b) {
+  if (b.d < 1 || b.z < 1) return 0;
+  if (b.max_dim <= 8 && b.z >= 2 && b.z <= 4) return 8;
+  if (b.max_dim <= 16 && b.z <= 3) return 16;
+  return 0;
+}
+
 inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
   if (kernel == BPX_KERNEL_GENERIC) return true;
   if (ctx->mode != BPX_MODE_NORM) return false;
@@ -18,8 +27,9 @@ inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
     // ComplexF64: chi = 16, degree 1..3, any physical dimension (bpx_onchip16c.cuh)
     // ... and chi = 8, degree 2..4 (bpx_onchip8c.cuh)
     if (ctx->dtype == BPX_C64) {
-      if (b.chi == 16 && b.z >= 1 && b.z <= 3 && b.d >= 1) return (size_t)ctx->max_smem_optin >= onchip16c::SMEM_BYTES16C;
-      if (b.chi == 8 && b.z >= 2 && b.z <= 4 && b.d >= 1) return (size_t)ctx->max_smem_optin >= onchip8c::SMEM_BYTES8C;
+      const int fam = complex_family(b);
+      if (fam == 16) return (size_t)ctx->max_smem_optin >= onchip16c::SMEM_BYTES16C;
+      if (fam == 8) return (size_t)ctx->max_smem_optin >= onchip8c::SMEM_BYTES8C;
       return false;
     }
     if (ctx->dtype != BPX_F64 || b.d != 2) return false;
@@ -88,9 +98,10 @@ inline int fast_prepare(bpx_ctx* ctx) {
     std::vector<onchip16c::ItemDesc> its;
     std::vector<double> cost;
     int leader = -1;
+    int64_t img_total = 0;  // doubles of the zero-padded image
     for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
       Bucket& b = ctx->buckets[i];
-      if (b.kernel != BPX_KERNEL_ONCHIP || b.chi != 16 || b.my_vertices.empty()) continue;
+      if (b.kernel != BPX_KERNEL_ONCHIP || complex_family(b) != 16 || b.my_vertices.empty()) continue;
       if (leader < 0) leader = i;
       b.leader = leader;
       for (int32_t v : b.my_vertices) {
@@ -98,17 +109,20 @@ inline int fast_prepare(bpx_ctx* ctx) {
           const int32_t e = ctx->out_edge[v][l];
           d.out_edge[o] = e;
           d.out_off[o] = ctx->msg_off[e];
+          d.out_dim[o] = ctx->h_vdesc[v].dim[l];
           d.need = std::max<int64_t>(d.need, ctx->upload_end[e]);
           d.peer[o] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
         };
         auto in_of = [&](int l) { return ctx->msg_off[ctx->rev[ctx->out_edge[v][l]]]; };
         onchip16c::ItemDesc d;
         memset(&d, 0, sizeof(d));
-        d.site_off = 2 * ctx->dev_site_off[v];
+        d.site_off = img_total;
+        img_total += (int64_t)b.d * (b.z == 3 ? onchip16c::NSL3 : (b.z == 2 ? onchip16c::NSL2 : onchip16c::NSL1));
         d.canon_off = ctx->dev_site_off[v];
         d.d = b.d;
         d.peer[0] = d.peer[1] = -1;
         d.first = 1;
+        for (int l = 0; l < 3; ++l) d.dim[l] = l < b.z ? ctx->h_vdesc[v].dim[l] : 1;
         for (int l = 0; l < b.z; ++l) d.need = std::max<int64_t>(d.need, ctx->upload_end[ctx->rev[ctx->out_edge[v][l]]]);
         if (b.z == 3) {
           // one item per output leg; (first, second) absorbed message: out2 (M0, M1), out1 (M0, M2), out0 (M2, M1)
@@ -118,6 +132,8 @@ inline int fast_prepare(bpx_ctx* ctx) {
             d.leg = leg;
             d.in_off[0] = in_of(first_leg[leg]);
             d.in_off[1] = in_of(second_leg[leg]);
+            d.in_dim[0] = d.dim[first_leg[leg]];
+            d.in_dim[1] = d.dim[second_leg[leg]];
             edge_of(d, 0, leg);
             its.push_back(d);
             cost.push_back(16000.0 * b.d + 3000.0);
@@ -127,6 +143,8 @@ inline int fast_prepare(bpx_ctx* ctx) {
           d.kind = 1;
           d.in_off[0] = in_of(0);
           d.in_off[1] = in_of(1);
+          d.in_dim[0] = d.dim[0];
+          d.in_dim[1] = d.dim[1];
           edge_of(d, 0, 0);
           edge_of(d, 1, 1);
           its.push_back(d);
@@ -161,6 +179,12 @@ inline int fast_prepare(bpx_ctx* ctx) {
         for (size_t r = 0; r < per_cta[c].size(); ++r) slots[r * G + c] = its[per_cta[c][r]];
       ctx->n_onchip16c_slots = (int)slots.size();
       ctx->onchip16c_grid = G;
+      if (getenv("BPX_IO_DEBUG")) {
+        int64_t mx = 0;
+        for (auto& it : its) mx = std::max(mx, it.need);
+        fprintf(stderr, "[bpx c16c] items %zu slots %zu grid %d max need %lld img doubles %lld\n", its.size(), slots.size(), G, (long long)mx,
+                (long long)img_total);
+      }
       cudaError_t e = cudaMalloc((void**)&ctx->d_onchip16c_items, slots.size() * sizeof(onchip16c::ItemDesc));
       if (e != cudaSuccess) {
         set_error(ctx, "cudaMalloc(complex on-chip items) failed: %s", cudaGetErrorString(e));
@@ -170,7 +194,15 @@ inline int fast_prepare(bpx_ctx* ctx) {
       BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip16c_items, slots.data(), slots.size() * sizeof(onchip16c::ItemDesc), cudaMemcpyHostToDevice));
       BPX_CUDA(ctx, cudaFuncSetAttribute(onchip16c::bp_update_onchip_c16c, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)onchip16c::SMEM_BYTES16C));
-      need_image = true;
+      if (ctx->d_img16c) cudaFree(ctx->d_img16c);
+      ctx->d_img16c = nullptr;
+      e = cudaMalloc(&ctx->d_img16c, std::max<size_t>(16, (size_t)img_total * sizeof(double)));
+      if (e != cudaSuccess) {
+        set_error(ctx, "cudaMalloc(complex 16-wide tensor image) failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return BPX_ERR_ALLOC;
+      }
+      ctx->sites_dirty = true;
     }
   }
   if (ctx->d_onchip8c_items) {
@@ -184,18 +216,21 @@ inline int fast_prepare(bpx_ctx* ctx) {
     std::vector<onchip8c::ItemDesc> its;
     std::vector<double> cost;
     int leader = -1;
+    int64_t img_total = 0;  // doubles of the zero-padded image
     for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
       Bucket& b = ctx->buckets[i];
-      if (b.kernel != BPX_KERNEL_ONCHIP || b.chi != 8 || b.my_vertices.empty()) continue;
+      if (b.kernel != BPX_KERNEL_ONCHIP || complex_family(b) != 8 || b.my_vertices.empty()) continue;
       if (leader < 0) leader = i;
       b.leader = leader;
       for (int32_t v : b.my_vertices) {
         onchip8c::ItemDesc d;
         memset(&d, 0, sizeof(d));
-        d.site_off = 2 * ctx->dev_site_off[v];
+        d.site_off = img_total;
+        img_total += (int64_t)b.d * (onchip::NELEM >> (3 * (4 - b.z)));
         d.canon_off = ctx->dev_site_off[v];
         d.d = b.d;
         d.first = 1;
+        for (int l = 0; l < 4; ++l) d.dim[l] = l < b.z ? ctx->h_vdesc[v].dim[l] : 1;
         for (int l = 0; l < b.z; ++l) {
           const int32_t e = ctx->out_edge[v][l];
           d.in_off[l] = ctx->msg_off[ctx->rev[e]];
@@ -205,6 +240,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
           const int32_t e = ctx->out_edge[v][leg];
           d.out_edge[tl] = e;
           d.out_off[tl] = ctx->msg_off[e];
+          d.out_dim[tl] = d.dim[leg];
           d.peer[tl] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
         };
         for (int tl = 0; tl < onchip8c::MAXT; ++tl) d.peer[tl] = -1;
@@ -269,7 +305,15 @@ inline int fast_prepare(bpx_ctx* ctx) {
       BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip8c_items, slots.data(), slots.size() * sizeof(onchip8c::ItemDesc), cudaMemcpyHostToDevice));
       BPX_CUDA(ctx, cudaFuncSetAttribute(onchip8c::bp_update_onchip_c8c, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)onchip8c::SMEM_BYTES8C));
-      need_image = true;
+      if (ctx->d_img8c) cudaFree(ctx->d_img8c);
+      ctx->d_img8c = nullptr;
+      e = cudaMalloc(&ctx->d_img8c, std::max<size_t>(16, (size_t)img_total * sizeof(double)));
+      if (e != cudaSuccess) {
+        set_error(ctx, "cudaMalloc(complex 8-wide tensor image) failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return BPX_ERR_ALLOC;
+      }
+      ctx->sites_dirty = true;
     }
   }
   // ---- 16-wide ON-CHIP buckets (degree 3 / chi 16; degree 6 / chi 4 in pair mode): one launch ----
@@ -421,15 +465,15 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
   }
-  if (ctx->d_sites_swz && ctx->n_onchip16c_slots > 0) {
+  if (ctx->d_img16c && ctx->n_onchip16c_slots > 0) {
     onchip16c::swizzle_sites_c16<<<std::min(ctx->n_onchip16c_slots, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
-        (const onchip16c::ItemDesc*)ctx->d_onchip16c_items, ctx->n_onchip16c_slots, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
+        (const onchip16c::ItemDesc*)ctx->d_onchip16c_items, ctx->n_onchip16c_slots, (const double*)ctx->d_sites, (double*)ctx->d_img16c);
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
   }
-  if (ctx->d_sites_swz && ctx->n_onchip8c_slots > 0) {
+  if (ctx->d_img8c && ctx->n_onchip8c_slots > 0) {
     onchip8c::swizzle_sites_c8<<<std::min(ctx->n_onchip8c_slots, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
-        (const onchip8c::ItemDesc*)ctx->d_onchip8c_items, ctx->n_onchip8c_slots, (const double*)ctx->d_sites, (double*)ctx->d_sites_swz);
+        (const onchip8c::ItemDesc*)ctx->d_onchip8c_items, ctx->n_onchip8c_slots, (const double*)ctx->d_sites, (double*)ctx->d_img8c);
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
   }
@@ -444,11 +488,11 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
 }
 
 inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize) {
-  if (b.kernel == BPX_KERNEL_ONCHIP && ctx->dtype == BPX_C64 && b.chi == 8) {
+  if (b.kernel == BPX_KERNEL_ONCHIP && ctx->dtype == BPX_C64 && complex_family(b) == 8) {
     onchip8c::Args k;
     k.items = (const onchip8c::ItemDesc*)ctx->d_onchip8c_items;
     k.n_slots = ctx->n_onchip8c_slots;
-    k.sites = (const double*)ctx->d_sites_swz;
+    k.sites = (const double*)ctx->d_img8c;
     k.msg_in = (const double*)msg_in;
     k.msg_out = (double*)msg_out;
     k.resmax = ctx->cur_slot;
@@ -465,7 +509,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     onchip16c::Args k;
     k.items = (const onchip16c::ItemDesc*)ctx->d_onchip16c_items;
     k.n_slots = ctx->n_onchip16c_slots;
-    k.sites = (const double*)ctx->d_sites_swz;
+    k.sites = (const double*)ctx->d_img16c;
     k.msg_in = (const double*)msg_in;
     k.msg_out = (double*)msg_out;
     k.resmax = ctx->cur_slot;

@@ -1,5 +1,7 @@
-// BPX_KERNEL_ONCHIP, ComplexF64 variant: chi = 16, degree 1..3, any physical dimension d -- BASELINE config 3
-// (heavy-hex lattice, mixed degree 2 / 3 buckets).
+// BPX_KERNEL_ONCHIP, ComplexF64 variant: link dimensions <= 16, degree 1..3, any physical dimension d -- BASELINE
+// config 3 (heavy-hex lattice, chi = 16, mixed degree 2 / 3 buckets).  Smaller (also per-leg different) link dimensions
+// are ZERO-PADDED to 16 in the private tensor image; message fragments, old values and stores are masked to the true
+// dimensions -- exact, because every padded tensor entry is zero.
 //
 // A complex tensor A[s, b0, b1, b2] is processed one PHYSICAL SLICE at a time: the slice A_s[(re, im), b0, b1, b2]
 // has exactly the shape of the real kernels' [s, b0, b1, b2] tile (8192 doubles = 64 KiB, layout L_A3 of
@@ -46,6 +48,10 @@ struct ItemDesc {
   int32_t first;      // this item swizzles the vertex's tensor (one item per vertex)
   int64_t canon_off;  // complex elements, into the canonical site buffer
   int64_t need;       // streamed host I/O: message-set prefix (elements) that holds every message this item reads
+  int32_t dim[3];     // true link dimension per leg (<= 16; absent legs: 1)
+  int32_t in_dim[2];  // dimension of the messages at in_off[0..1]
+  int32_t out_dim[2]; // dimension of the messages at out_off[0..1]
+  int32_t pad2;
 };
 
 struct Args {
@@ -74,13 +80,15 @@ __device__ __forceinline__ double neg(double x) { return __hiloint2double(__doub
 struct CFrag {  // M[g + 8 mt, t + 4 j], real and imaginary parts
   double r[2][4], i[2][4];
 };
-__device__ __forceinline__ CFrag load_cfrag(const double* __restrict__ M, int g, int t) {
+// M is chi x chi (chi <= 16), column-major; entries beyond chi read as zero
+__device__ __forceinline__ CFrag load_cfrag(const double* __restrict__ M, int g, int t, int chi) {
   CFrag f;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const double2 v = *reinterpret_cast<const double2*>(M + 2 * ((g + 8 * mt) + CHI * (t + 4 * j)));
+      const int row = g + 8 * mt, col = t + 4 * j;
+      const double2 v = (row < chi && col < chi) ? *reinterpret_cast<const double2*>(M + 2 * (row + chi * col)) : make_double2(0.0, 0.0);
       f.r[mt][j] = v.x;
       f.i[mt][j] = v.y;
     }
@@ -164,26 +172,33 @@ constexpr size_t SMEM_DOUBLES16C = (size_t)3 * NSL3 + 2 * CMSG + 4;
 constexpr size_t SMEM_BYTES16C = SMEM_DOUBLES16C * sizeof(double);
 enum { BAR_CC = 1 };
 
-// canonical A_v[s, b0..] (complex, column-major) -> private image: d slices [(re, im), b..] in L_A3 / L_Z2 / plain order
+// canonical A_v[s, b0..] (complex, column-major, true dims) -> private image: d slices [(re, im), b..] in L_A3 / L_Z2 /
+// plain order, every leg zero-padded to 16
 __global__ void swizzle_sites_c16(const ItemDesc* items, int n_slots, const double* __restrict__ src, double* __restrict__ dst) {
   for (int it = blockIdx.x; it < n_slots; it += gridDim.x) {
     const ItemDesc d = items[it];
     if (d.kind < 0 || !d.first) continue;
     const int z = d.kind == 0 ? 3 : (d.kind == 1 ? 2 : 1);
     const int nsl = d.kind == 0 ? NSL3 : (d.kind == 1 ? NSL2 : NSL1);
-    const int nb = nsl / 2;  // complex elements per slice
+    const int nb = nsl / 2;  // padded complex elements per slice
     const double* s0 = src + 2 * d.canon_off;
     double* d0 = dst + d.site_off;
     for (int c = threadIdx.x; c < nb * d.d; c += blockDim.x) {
       const int s = c % d.d, b = c / d.d;
+      const int b0 = b & 15, b1 = (b >> 4) & 15, b2 = (b >> 8) & 15;
       uint32_t p;
       if (z == 3)
-        p = pos<L_A3>(0, b & 15) ^ pos<L_A3>(1, (b >> 4) & 15) ^ pos<L_A3>(2, (b >> 8) & 15);
+        p = pos<L_A3>(0, b0) ^ pos<L_A3>(1, b1) ^ pos<L_A3>(2, b2);
       else if (z == 2)
-        p = pos<L_Z2>(0, b & 15) ^ pos<L_Z2>(1, (b >> 4) & 15);
+        p = pos<L_Z2>(0, b0) ^ pos<L_Z2>(1, b1);
       else
         p = 2 * b;
-      *reinterpret_cast<double2*>(d0 + (size_t)s * nsl + p) = *reinterpret_cast<const double2*>(s0 + 2 * (size_t)c);
+      double2 v = make_double2(0.0, 0.0);
+      if (b0 < d.dim[0] && b1 < d.dim[1] && b2 < d.dim[2]) {
+        const size_t ci = (size_t)s + (size_t)d.d * (b0 + (size_t)d.dim[0] * (b1 + (size_t)d.dim[1] * b2));
+        v = *reinterpret_cast<const double2*>(s0 + 2 * ci);
+      }
+      *reinterpret_cast<double2*>(d0 + (size_t)s * nsl + p) = v;
     }
   }
 }
@@ -200,6 +215,16 @@ __device__ __forceinline__ void store_partial(double* mine, const double (&accr)
       }
 }
 
+// thread el = b' + 16 b of a 16x16 tile -> offset inside the true chi x chi message, or -1 outside
+__device__ __forceinline__ int msg_elem_off(int chi) {
+  const int bp = threadIdx.x & 15, b = threadIdx.x >> 4;
+  return (bp < chi && b < chi) ? bp + chi * b : -1;
+}
+__device__ __forceinline__ c64 load_old(const Args& k, const ItemDesc* d, int o) {
+  const int eo = msg_elem_off(d->out_dim[o]);
+  return eo >= 0 ? reinterpret_cast<const c64*>(k.msg_in)[d->out_off[o] + eo] : make_c64(0.0, 0.0);
+}
+
 // Block-wide epilogue (one element per thread and output): sum-normalise (beliefpropagation.jl:248-253), residual term
 // 1 - |<old^, new^>|^2 (beliefpropagation.jl:261-267), store (+ peer store on cut edges).  `part` = 96 doubles of shared
 // scratch.  A single warp would spend microseconds here on the eight complex divisions per lane -- on the critical path
@@ -211,8 +236,11 @@ __device__ __forceinline__ void block_epilogue(const c64 (&v)[NOUT], const c64 (
   double* part1 = part;        // [NCWC][2] complex sums
   double* part2 = part + 32;   // [NCWC][2][4] dot.re, dot.im, |old|^2, |new|^2
 #pragma unroll
+  int eo[NOUT];
+#pragma unroll
   for (int o = 0; o < NOUT; ++o) {
-    const c64 s = warp_sum<c64>(v[o]);
+    eo[o] = msg_elem_off(d->out_dim[o]);
+    const c64 s = warp_sum<c64>(eo[o] >= 0 ? v[o] : E::zero());
     if (lane == 0) *reinterpret_cast<double2*>(part1 + (warp * 2 + o) * 2) = make_double2(s.re, s.im);
   }
   onchip::bar_sync(BAR_CC, NCTC);
@@ -226,13 +254,16 @@ __device__ __forceinline__ void block_epilogue(const c64 (&v)[NOUT], const c64 (
       s.im += q.y;
     }
     const bool scale = k.normalize && !E::is_zero(s);
-    const c64 x = scale ? E::div(v[o], s) : v[o];
-    const int64_t off = d->out_off[o] + threadIdx.x;
-    reinterpret_cast<c64*>(k.msg_out)[off] = x;
-    if (k.io.host_out) reinterpret_cast<c64*>(k.io.host_out)[off] = x;
-    if (k.peer.nranks > 1 && d->peer[o] >= 0) {
-      reinterpret_cast<c64*>(k.peer.peer_out[d->peer[o]])[off] = x;
-      __threadfence_system();  // released here instead of at the kernel's tail
+    c64 x = E::zero();
+    if (eo[o] >= 0) {
+      x = scale ? E::div(v[o], s) : v[o];
+      const int64_t off = d->out_off[o] + eo[o];
+      reinterpret_cast<c64*>(k.msg_out)[off] = x;
+      if (k.io.host_out) reinterpret_cast<c64*>(k.io.host_out)[off] = x;
+      if (k.peer.nranks > 1 && d->peer[o] >= 0) {
+        reinterpret_cast<c64*>(k.peer.peer_out[d->peer[o]])[off] = x;
+        __threadfence_system();  // released here instead of at the kernel's tail
+      }
     }
     c64 dot = E::fma(E::conj(old[o]), x, E::zero());
     dot = warp_sum<c64>(dot);
@@ -347,12 +378,15 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
     const int kind = d->kind;
     if (kind < 0) break;
     const int nd = d->d;
-    hostio_wait(k.io, d->need);  // streamed upload: the item's messages (fragments, old values) have arrived
+    if (k.io.progress) {  // streamed upload: the item's messages (fragments, old values) have arrived -- ONE warp polls
+      if (warp == 0) hostio_wait(k.io, d->need);
+      onchip::bar_sync(BAR_CC, NCTC);
+    }
     if (kind == 0) {
       const int leg = d->leg;
-      const CFrag m1 = load_cfrag(k.msg_in + 2 * d->in_off[0], g, t);
-      const CFrag m2 = load_cfrag(k.msg_in + 2 * d->in_off[1], g, t);
-      const c64 old[1] = {reinterpret_cast<const c64*>(k.msg_in)[d->out_off[0] + threadIdx.x]};  // early: hides the miss
+      const CFrag m1 = load_cfrag(k.msg_in + 2 * d->in_off[0], g, t, d->in_dim[0]);
+      const CFrag m2 = load_cfrag(k.msg_in + 2 * d->in_off[1], g, t, d->in_dim[1]);
+      const c64 old[1] = {load_old(k, d, 0)};  // early: hides the miss
       double accr[2][2][2], acci[2][2][2];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -414,9 +448,8 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
 #pragma unroll
         for (int b = 0; b < 2; ++b) accr[a][b][0] = accr[a][b][1] = acci[a][b][0] = acci[a][b][1] = 0.0;
       CFrag m;
-      if (warp < 4) m = load_cfrag(k.msg_in + 2 * d->in_off[1 - o], g, t);
-      const c64 old[2] = {reinterpret_cast<const c64*>(k.msg_in)[d->out_off[0] + threadIdx.x],
-                          reinterpret_cast<const c64*>(k.msg_in)[d->out_off[1] + threadIdx.x]};
+      if (warp < 4) m = load_cfrag(k.msg_in + 2 * d->in_off[1 - o], g, t, d->in_dim[1 - o]);
+      const c64 old[2] = {load_old(k, d, 0), load_old(k, d, 1)};
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;
         mbar_wait(&mbar[sl], (u >> 1) & 1);
@@ -448,7 +481,7 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16c(Args k) {
     } else {
       // degree 1: out[b', b] = sum_s A[s, b] conj(A[s, b']); thread el = b' + 16 b
       const int bp = threadIdx.x & 15, b = threadIdx.x >> 4;
-      const c64 old[1] = {reinterpret_cast<const c64*>(k.msg_in)[d->out_off[0] + threadIdx.x]};
+      const c64 old[1] = {load_old(k, d, 0)};
       double sr = 0, si = 0;
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;

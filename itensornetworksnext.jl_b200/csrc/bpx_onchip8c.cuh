@@ -1,5 +1,7 @@
-// BPX_KERNEL_ONCHIP, ComplexF64 variant for chi = 8, degree 2..4, any physical dimension d (complex PEPS on a square
-// lattice: the complex twin of BASELINE config 2).
+// BPX_KERNEL_ONCHIP, ComplexF64 variant for link dimensions <= 8, degree 2..4, any physical dimension d (complex PEPS on
+// a square lattice: the complex twin of BASELINE config 2).  Link dimensions below 8 (also different ones per leg) are
+// ZERO-PADDED to 8 in the kernel's private tensor image; message fragments, old values and stores are masked to the
+// true dimensions -- exact, because every padded tensor entry is zero.
 //
 // Same idea as bpx_onchip16c.cuh: a complex tensor is processed one PHYSICAL SLICE at a time.  The slice
 // A_s[(re, im), a0, a1, a2, a3] has exactly the shape and the XOR-swizzled layout (leg_pos) of the real kernel's
@@ -50,6 +52,9 @@ struct ItemDesc {
   int32_t first;        // this item swizzles the vertex's tensor
   int32_t pad;
   int64_t need;         // streamed host I/O: prefix of the upload that holds every message this item reads
+  int32_t dim[4];       // true link dimension per leg (<= 8; absent legs: 1)
+  int32_t out_dim[MAXT];  // link dimension of each output tile's message
+  int32_t pad2;
 };
 
 struct Args {
@@ -71,12 +76,15 @@ struct CMsgFrag {
   double mar[2], mai[2];  // M[g, t + 4j]  : A operand of "absorb first leg", B operand of the T-GEMM
   double mbr[2], mbi[2];  // M[g, 2t + i]  : B operand of "absorb second leg" (register-chained)
 };
-__device__ __forceinline__ CMsgFrag load_cfrag8(const double* __restrict__ M, int g, int t) {
+// M is chi x chi (chi <= 8), column-major; entries beyond chi read as zero
+__device__ __forceinline__ CMsgFrag load_cfrag8(const double* __restrict__ M, int g, int t, int chi) {
   CMsgFrag f;
+  const double2 zero = make_double2(0.0, 0.0);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const double2 a = *reinterpret_cast<const double2*>(M + 2 * (g + CHI * (t + 4 * j)));
-    const double2 b = *reinterpret_cast<const double2*>(M + 2 * (g + CHI * (2 * t + j)));
+    const int ca = t + 4 * j, cb = 2 * t + j;
+    const double2 a = (g < chi && ca < chi) ? *reinterpret_cast<const double2*>(M + 2 * (g + chi * ca)) : zero;
+    const double2 b = (g < chi && cb < chi) ? *reinterpret_cast<const double2*>(M + 2 * (g + chi * cb)) : zero;
     f.mar[j] = a.x;
     f.mai[j] = a.y;
     f.mbr[j] = b.x;
@@ -188,7 +196,8 @@ constexpr size_t SMEM_DOUBLES8C = (size_t)3 * NELEM + NW * MAXT * CMSG8 + 128 + 
 constexpr size_t SMEM_BYTES8C = SMEM_DOUBLES8C * sizeof(double);
 enum { BAR_C8 = 1 };
 
-// canonical A_v[s, a0..] (complex, column-major) -> private image: d slices [(re, im), a0..] in leg_pos order
+// canonical A_v[s, a0..] (complex, column-major, true dims) -> private image: d slices [(re, im), a0..] in leg_pos order,
+// every leg zero-padded to 8
 __global__ void swizzle_sites_c8(const ItemDesc* items, int n_slots, const double* __restrict__ src, double* __restrict__ dst) {
   for (int it = blockIdx.x; it < n_slots; it += gridDim.x) {
     const ItemDesc d = items[it];
@@ -198,8 +207,14 @@ __global__ void swizzle_sites_c8(const ItemDesc* items, int n_slots, const doubl
     double* d0 = dst + d.site_off;
     for (int c = threadIdx.x; c < nb * d.d; c += blockDim.x) {
       const int s = c % d.d, b = c / d.d;
-      const uint32_t p = leg_pos(0, b & 7) ^ leg_pos(1, (b >> 3) & 7) ^ leg_pos(2, (b >> 6) & 7) ^ leg_pos(3, (b >> 9) & 7);
-      *reinterpret_cast<double2*>(d0 + (size_t)s * nsl + p) = *reinterpret_cast<const double2*>(s0 + 2 * (size_t)c);
+      const int a0 = b & 7, a1 = (b >> 3) & 7, a2 = (b >> 6) & 7, a3 = (b >> 9) & 7;
+      const uint32_t p = leg_pos(0, a0) ^ leg_pos(1, a1) ^ leg_pos(2, a2) ^ leg_pos(3, a3);
+      double2 v = make_double2(0.0, 0.0);
+      if (a0 < d.dim[0] && a1 < d.dim[1] && a2 < d.dim[2] && a3 < d.dim[3]) {
+        const size_t ci = (size_t)s + (size_t)d.d * (a0 + (size_t)d.dim[0] * (a1 + (size_t)d.dim[1] * (a2 + (size_t)d.dim[2] * a3)));
+        v = *reinterpret_cast<const double2*>(s0 + 2 * ci);
+      }
+      *reinterpret_cast<double2*>(d0 + (size_t)s * nsl + p) = v;
     }
   }
 }
@@ -281,20 +296,26 @@ __global__ void __launch_bounds__(NT, 1) bp_update_onchip_c8c(Args k) {
     const int kind = d->kind;
     if (kind < 0) break;
     const int nd = d->d, ntile = n_tiles(kind);
-    hostio_wait(k.io, d->need);  // streamed upload: the item's messages (fragments, old values) have arrived
+    if (k.io.progress) {  // streamed upload: the item's messages (fragments, old values) have arrived -- ONE warp polls
+      if (warp == 0) hostio_wait(k.io, d->need);
+      bar_sync(BAR_C8, NT);
+    }
     // old value of the output element this thread finalises: tile = thread / 64, element = thread % 64 (issued early)
     const int my_tile = threadIdx.x >> 6, my_el = threadIdx.x & 63;
+    const int chi_o = my_tile < ntile ? d->out_dim[my_tile] : 0;
+    const bool my_valid = (my_el & 7) < chi_o && (my_el >> 3) < chi_o;  // inside the true chi_o x chi_o message
+    const int64_t my_off = my_valid ? d->out_off[my_tile] + (my_el & 7) + chi_o * (my_el >> 3) : 0;
     c64 old = make_c64(0.0, 0.0);
-    if (my_tile < ntile) old = reinterpret_cast<const c64*>(k.msg_in)[d->out_off[my_tile] + my_el];
+    if (my_valid) old = reinterpret_cast<const c64*>(k.msg_in)[my_off];
     CAcc acc[MAXT];
 #pragma unroll
     for (int i = 0; i < MAXT; ++i) cacc_zero(acc[i]);
     const c64* min_c = reinterpret_cast<const c64*>(k.msg_in);
     if (kind <= 1) {
-      const CMsgFrag m0 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[0]), g, t);
-      const CMsgFrag m1 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[1]), g, t);
-      const CMsgFrag m2 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[2]), g, t);
-      const CMsgFrag m3 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[3]), g, t);
+      const CMsgFrag m0 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[0]), g, t, d->dim[0]);
+      const CMsgFrag m1 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[1]), g, t, d->dim[1]);
+      const CMsgFrag m2 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[2]), g, t, d->dim[2]);
+      const CMsgFrag m3 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[3]), g, t, d->dim[3]);
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;
         mbar_wait(&mbar[sl], (u >> 1) & 1);
@@ -314,9 +335,9 @@ __global__ void __launch_bounds__(NT, 1) bp_update_onchip_c8c(Args k) {
         bar_sync(BAR_C8, NT);  // P is rewritten by the next slice
       }
     } else if (kind == 2) {
-      const CMsgFrag m0 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[0]), g, t);
-      const CMsgFrag m1 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[1]), g, t);
-      const CMsgFrag m2 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[2]), g, t);
+      const CMsgFrag m0 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[0]), g, t, d->dim[0]);
+      const CMsgFrag m1 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[1]), g, t, d->dim[1]);
+      const CMsgFrag m2 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[2]), g, t, d->dim[2]);
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;
         mbar_wait(&mbar[sl], (u >> 1) & 1);
@@ -334,8 +355,8 @@ __global__ void __launch_bounds__(NT, 1) bp_update_onchip_c8c(Args k) {
         bar_sync(BAR_C8, NT);
       }
     } else {  // degree 2: out1 (absorb 0, close 1), out0 (absorb 1, close 0) straight from A
-      const CMsgFrag m0 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[0]), g, t);
-      const CMsgFrag m1 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[1]), g, t);
+      const CMsgFrag m0 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[0]), g, t, d->dim[0]);
+      const CMsgFrag m1 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[1]), g, t, d->dim[1]);
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;
         mbar_wait(&mbar[sl], (u >> 1) & 1);
@@ -353,7 +374,7 @@ __global__ void __launch_bounds__(NT, 1) bp_update_onchip_c8c(Args k) {
     {
       using E = Elem<c64>;
       c64 v = E::zero();
-      if (my_tile < ntile) {
+      if (my_valid) {
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
           const double2 q = *reinterpret_cast<const double2*>(red + (w * MAXT + my_tile) * CMSG8 + 2 * my_el);
@@ -369,9 +390,9 @@ __global__ void __launch_bounds__(NT, 1) bp_update_onchip_c8c(Args k) {
       const double2 q0 = *reinterpret_cast<const double2*>(part1 + 2 * (warp & ~1)), q1 = *reinterpret_cast<const double2*>(part1 + 2 * (warp | 1));
       const c64 s = make_c64(q0.x + q1.x, q0.y + q1.y);
       c64 x = v;
-      if (my_tile < ntile) {
+      if (my_valid) {
         if (k.normalize && !E::is_zero(s)) x = E::div(v, s);
-        const int64_t off = d->out_off[my_tile] + my_el;
+        const int64_t off = my_off;
         reinterpret_cast<c64*>(k.msg_out)[off] = x;
         if (k.io.host_out) reinterpret_cast<c64*>(k.io.host_out)[off] = x;
         if (k.peer.nranks > 1 && d->peer[my_tile] >= 0) {
@@ -380,7 +401,7 @@ __global__ void __launch_bounds__(NT, 1) bp_update_onchip_c8c(Args k) {
         }
       }
       c64 dot = warp_sum<c64>(E::fma(E::conj(old), x, E::zero()));
-      const double n_old = warp_sum_d(E::abs2(old)), n_new = warp_sum_d(my_tile < ntile ? E::abs2(x) : 0.0);
+      const double n_old = warp_sum_d(E::abs2(old)), n_new = warp_sum_d(my_valid ? E::abs2(x) : 0.0);
       if (lane == 0) {
         double* q = part2 + 4 * warp;
         q[0] = dot.re;

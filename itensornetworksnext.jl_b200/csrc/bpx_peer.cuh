@@ -66,18 +66,22 @@ __device__ __forceinline__ void hostio_finish(const HostIO& io) {
 }
 
 // Called by ONE warp per CTA before it touches messages written by peers.  Lane p waits for rank p's post.
-// the calling warp waits (lane 0 spins, bounded) until `need` elements of the upload have arrived
+// the calling warp waits (lane 0 spins, bounded, with back-off) until `need` elements of the upload have arrived.
+// Keep the number of polling warps small: a thousand lanes hammering the one L2 line starve the copy engine's write of
+// the progress word itself (observed: a sweep whose every item needs the whole upload never saw it arrive).
 __device__ __forceinline__ void hostio_wait(const HostIO& io, long long need) {
   if (!io.progress) return;
   if ((threadIdx.x & 31) == 0) {
     const volatile long long* p = io.progress;
     const long long t0 = clock64();
+    unsigned ns = 200;
     while (*p < need) {
       if (clock64() - t0 > 8000000000ll) {  // ~4 s: raise the error flag instead of hanging the GPU
         if (io.error_flag) *reinterpret_cast<volatile int*>(io.error_flag) = 2;  // (mapped host memory: plain store)
         break;
       }
-      __nanosleep(100);
+      __nanosleep(ns);
+      if (ns < 2000) ns += ns;
     }
   }
   __syncwarp();
