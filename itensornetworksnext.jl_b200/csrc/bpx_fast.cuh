@@ -20,6 +20,16 @@ inline int complex_family(const Bucket& b) {
   return 0;
 }
 
+// Float64 buckets for the hand-tuned kernels: exact shapes only
+inline bool real_tuned_c8(const Bucket& b) { return b.d == 2 && b.z >= 2 && b.z <= 4 && b.chi == 8; }
+inline bool real_tuned_c16(const Bucket& b) { return b.d == 2 && ((b.z == 3 && b.chi == 16) || (b.z == 6 && b.chi == 4)); }
+// buckets served by the templated slice kernel of bpx_onchip8c.cuh: ComplexF64 family 8, and every Float64 bucket with
+// degree 2..4 and link dims <= 8 (any d, per-leg dims) that the tuned kernels do not take
+inline bool uses_c8x(const bpx_ctx* ctx, const Bucket& b) {
+  if (ctx->dtype == BPX_C64) return complex_family(b) == 8;
+  return b.d >= 1 && b.z >= 2 && b.z <= 4 && b.max_dim <= 8 && !real_tuned_c8(b);
+}
+
 inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
   if (kernel == BPX_KERNEL_GENERIC) return true;
   if (ctx->mode != BPX_MODE_NORM) return false;
@@ -32,10 +42,11 @@ inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
       if (fam == 8) return (size_t)ctx->max_smem_optin >= onchip8c::SMEM_BYTES8C;
       return false;
     }
-    if (ctx->dtype != BPX_F64 || b.d != 2) return false;
-    if (b.z >= 2 && b.z <= 4 && b.chi == 8) return (size_t)ctx->max_smem_optin >= onchip::SMEM_BYTES;
+    if (ctx->dtype != BPX_F64) return false;
+    if (real_tuned_c8(b)) return (size_t)ctx->max_smem_optin >= onchip::SMEM_BYTES;
     // 16-wide on-chip kernel: degree 3 / chi 16, or degree 6 / chi 4 with legs paired into super-legs
-    if ((b.z == 3 && b.chi == 16) || (b.z == 6 && b.chi == 4)) return (size_t)ctx->max_smem_optin >= onchip16::SMEM_BYTES16;
+    if (real_tuned_c16(b)) return (size_t)ctx->max_smem_optin >= onchip16::SMEM_BYTES16;
+    if (uses_c8x(ctx, b)) return (size_t)ctx->max_smem_optin >= onchip8c::SMEM_BYTES8C;
     return false;
   }
   if (kernel == BPX_KERNEL_SLICED)
@@ -65,7 +76,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
   int generic_leader = -1;
   for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
     ctx->buckets[i].leader = i;
-    if (ctx->dtype == BPX_F64 && ctx->buckets[i].kernel == BPX_KERNEL_ONCHIP && ctx->buckets[i].chi == 8 && !ctx->buckets[i].my_vertices.empty())
+    if (ctx->dtype == BPX_F64 && ctx->buckets[i].kernel == BPX_KERNEL_ONCHIP && real_tuned_c8(ctx->buckets[i]) && !ctx->buckets[i].my_vertices.empty())
       group.push_back(i);
     if (ctx->buckets[i].kernel == BPX_KERNEL_GENERIC && !ctx->buckets[i].my_edges.empty()) {
       if (generic_leader < 0) generic_leader = i;
@@ -211,24 +222,27 @@ inline int fast_prepare(bpx_ctx* ctx) {
   }
   ctx->n_onchip8c_slots = 0;
   ctx->onchip8c_grid = 0;
-  if (ctx->dtype == BPX_C64) {
-    // ---- complex chi = 8 buckets (degree 2..4): one launch; degree-4 vertices as two half items (branch P / Q) ----
+  {
+    // ---- slice-kernel buckets (complex family 8 / general real, degree 2..4): one launch; degree-4 vertices as two half
+    // items (branch P / Q) ----
+    const bool cplx = ctx->dtype == BPX_C64;
     std::vector<onchip8c::ItemDesc> its;
     std::vector<double> cost;
     int leader = -1;
     int64_t img_total = 0;  // doubles of the zero-padded image
     for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
       Bucket& b = ctx->buckets[i];
-      if (b.kernel != BPX_KERNEL_ONCHIP || complex_family(b) != 8 || b.my_vertices.empty()) continue;
+      if (b.kernel != BPX_KERNEL_ONCHIP || !uses_c8x(ctx, b) || b.my_vertices.empty()) continue;
       if (leader < 0) leader = i;
       b.leader = leader;
       for (int32_t v : b.my_vertices) {
         onchip8c::ItemDesc d;
         memset(&d, 0, sizeof(d));
         d.site_off = img_total;
-        img_total += (int64_t)b.d * (onchip::NELEM >> (3 * (4 - b.z)));
+        d.phys = b.d;
+        d.d = cplx ? b.d : (b.d + 1) / 2;  // slices: physical values (complex) or physical pairs (real)
+        img_total += (int64_t)d.d * (onchip::NELEM >> (3 * (4 - b.z)));
         d.canon_off = ctx->dev_site_off[v];
-        d.d = b.d;
         d.first = 1;
         for (int l = 0; l < 4; ++l) d.dim[l] = l < b.z ? ctx->h_vdesc[v].dim[l] : 1;
         for (int l = 0; l < b.z; ++l) {
@@ -249,20 +263,20 @@ inline int fast_prepare(bpx_ctx* ctx) {
           tile(0, 3);
           tile(1, 2);
           its.push_back(d);
-          cost.push_back(6.0 * 4096 * b.d + 1500.0);
+          cost.push_back((cplx ? 6.0 * 4096 : 6.0 * 1024) * d.d + 1500.0);
           d.kind = 1;  // branch Q: out1, out0
           d.first = 0;
           tile(0, 1);
           tile(1, 0);
           its.push_back(d);
-          cost.push_back(6.0 * 4096 * b.d + 1500.0);
+          cost.push_back((cplx ? 6.0 * 4096 : 6.0 * 1024) * d.d + 1500.0);
         } else if (b.z == 3) {
           d.kind = 2;
           tile(0, 2);
           tile(1, 1);
           tile(2, 0);
           its.push_back(d);
-          cost.push_back(8.0 * 512 * b.d + 1000.0 * b.d + 1500.0);
+          cost.push_back((cplx ? 8.0 * 512 : 8.0 * 128) * d.d + 1000.0 * d.d + 1500.0);
         } else {
           d.kind = 3;
           tile(0, 1);
@@ -303,7 +317,9 @@ inline int fast_prepare(bpx_ctx* ctx) {
         return BPX_ERR_ALLOC;
       }
       BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip8c_items, slots.data(), slots.size() * sizeof(onchip8c::ItemDesc), cudaMemcpyHostToDevice));
-      BPX_CUDA(ctx, cudaFuncSetAttribute(onchip8c::bp_update_onchip_c8c, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      BPX_CUDA(ctx, cudaFuncSetAttribute(onchip8c::bp_update_onchip_c8x<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)onchip8c::SMEM_BYTES8C));
+      BPX_CUDA(ctx, cudaFuncSetAttribute(onchip8c::bp_update_onchip_c8x<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)onchip8c::SMEM_BYTES8C));
       if (ctx->d_img8c) cudaFree(ctx->d_img8c);
       ctx->d_img8c = nullptr;
@@ -322,7 +338,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
     int leader16 = -1;
     for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
       Bucket& b = ctx->buckets[i];
-      if (ctx->dtype != BPX_F64 || b.kernel != BPX_KERNEL_ONCHIP || b.chi == 8 || b.my_vertices.empty()) continue;
+      if (ctx->dtype != BPX_F64 || b.kernel != BPX_KERNEL_ONCHIP || !real_tuned_c16(b) || b.my_vertices.empty()) continue;
       if (leader16 < 0) leader16 = i;
       b.leader = leader16;
       for (int32_t v : b.my_vertices) {
@@ -472,8 +488,12 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
     BPX_CUDA(ctx, cudaGetLastError());
   }
   if (ctx->d_img8c && ctx->n_onchip8c_slots > 0) {
-    onchip8c::swizzle_sites_c8<<<std::min(ctx->n_onchip8c_slots, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
-        (const onchip8c::ItemDesc*)ctx->d_onchip8c_items, ctx->n_onchip8c_slots, (const double*)ctx->d_sites, (double*)ctx->d_img8c);
+    if (ctx->dtype == BPX_C64)
+      onchip8c::swizzle_sites_c8<true><<<std::min(ctx->n_onchip8c_slots, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
+          (const onchip8c::ItemDesc*)ctx->d_onchip8c_items, ctx->n_onchip8c_slots, (const double*)ctx->d_sites, (double*)ctx->d_img8c);
+    else
+      onchip8c::swizzle_sites_c8<false><<<std::min(ctx->n_onchip8c_slots, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
+          (const onchip8c::ItemDesc*)ctx->d_onchip8c_items, ctx->n_onchip8c_slots, (const double*)ctx->d_sites, (double*)ctx->d_img8c);
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
   }
@@ -488,7 +508,7 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
 }
 
 inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize) {
-  if (b.kernel == BPX_KERNEL_ONCHIP && ctx->dtype == BPX_C64 && complex_family(b) == 8) {
+  if (b.kernel == BPX_KERNEL_ONCHIP && uses_c8x(ctx, b)) {
     onchip8c::Args k;
     k.items = (const onchip8c::ItemDesc*)ctx->d_onchip8c_items;
     k.n_slots = ctx->n_onchip8c_slots;
@@ -500,7 +520,10 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.peer = ctx->peer_args;
     k.io = ctx->io_args;
     if (ctx->onchip8c_grid == 0) return BPX_OK;
-    onchip8c::bp_update_onchip_c8c<<<ctx->onchip8c_grid, onchip8c::NT, onchip8c::SMEM_BYTES8C, ctx->stream>>>(k);
+    if (ctx->dtype == BPX_C64)
+      onchip8c::bp_update_onchip_c8x<true><<<ctx->onchip8c_grid, onchip8c::NT, onchip8c::SMEM_BYTES8C, ctx->stream>>>(k);
+    else
+      onchip8c::bp_update_onchip_c8x<false><<<ctx->onchip8c_grid, onchip8c::NT, onchip8c::SMEM_BYTES8C, ctx->stream>>>(k);
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
     return BPX_OK;
@@ -523,7 +546,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     BPX_CUDA(ctx, cudaGetLastError());
     return BPX_OK;
   }
-  if (b.kernel == BPX_KERNEL_ONCHIP && b.chi != 8) {
+  if (b.kernel == BPX_KERNEL_ONCHIP && ctx->dtype == BPX_F64 && real_tuned_c16(b)) {
     onchip16::Args k;
     k.items = (const onchip16::ItemDesc*)ctx->d_onchip16_items;
     k.n_items = ctx->n_onchip16_items;

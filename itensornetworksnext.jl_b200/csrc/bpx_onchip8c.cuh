@@ -3,6 +3,11 @@
 // ZERO-PADDED to 8 in the kernel's private tensor image; message fragments, old values and stores are masked to the
 // true dimensions -- exact, because every padded tensor entry is zero.
 //
+// The kernel is a template over the element type.  CPLX = false is the general REAL variant -- any physical dimension (the
+// 16-byte chunk holds the physical pair (s = 2q, s = 2q + 1), one slice per pair, odd d padded with a zero), link
+// dimensions <= 8, also per-leg different -- for the Float64 buckets the hand-tuned (chi = 8, d = 2) kernel of
+// bpx_onchip.cuh does not cover (BASELINE config 1: chi = 2).  Two DMMA chains per operand pair instead of four.
+//
 // Same idea as bpx_onchip16c.cuh: a complex tensor is processed one PHYSICAL SLICE at a time.  The slice
 // A_s[(re, im), a0, a1, a2, a3] has exactly the shape and the XOR-swizzled layout (leg_pos) of the real kernel's
 // [s, a0..a3] tile (8192 doubles = 64 KiB; degree 3: 1024, degree 2: 128), one LDS.128 feeds the real and the imaginary
@@ -48,9 +53,9 @@ struct ItemDesc {
   int32_t out_edge[MAXT];
   int32_t peer[MAXT];
   int32_t kind;         // -1 null | 0 degree 4 branch P (out3, out2) | 1 degree 4 branch Q (out1, out0) | 2 degree 3 | 3 degree 2
-  int32_t d;            // physical dimension = number of slices
+  int32_t d;            // number of slices: complex: physical dimension; real: physical PAIRS, (phys + 1) / 2
   int32_t first;        // this item swizzles the vertex's tensor
-  int32_t pad;
+  int32_t phys;         // physical dimension
   int64_t need;         // streamed host I/O: prefix of the upload that holds every message this item reads
   int32_t dim[4];       // true link dimension per leg (<= 8; absent legs: 1)
   int32_t out_dim[MAXT];  // link dimension of each output tile's message
@@ -72,19 +77,35 @@ struct Args {
 __device__ __forceinline__ int slice_doubles(int kind) { return kind <= 1 ? NELEM : (kind == 2 ? NELEM / 8 : NELEM / 64); }
 __device__ __forceinline__ int n_tiles(int kind) { return kind == 2 ? 3 : 2; }
 
+template <bool CPLX>
+struct Tr;
+template <>
+struct Tr<true> {
+  using T = c64;
+  __device__ static __forceinline__ double2 pack(c64 a) { return make_double2(a.re, a.im); }
+  __device__ static __forceinline__ c64 unpack(double2 q) { return make_c64(q.x, q.y); }
+};
+template <>
+struct Tr<false> {
+  using T = double;
+  __device__ static __forceinline__ double2 pack(double a) { return make_double2(a, 0.0); }
+  __device__ static __forceinline__ double unpack(double2 q) { return q.x; }
+};
+
 struct CMsgFrag {
   double mar[2], mai[2];  // M[g, t + 4j]  : A operand of "absorb first leg", B operand of the T-GEMM
   double mbr[2], mbi[2];  // M[g, 2t + i]  : B operand of "absorb second leg" (register-chained)
 };
 // M is chi x chi (chi <= 8), column-major; entries beyond chi read as zero
-__device__ __forceinline__ CMsgFrag load_cfrag8(const double* __restrict__ M, int g, int t, int chi) {
+template <bool CPLX>
+__device__ __forceinline__ CMsgFrag load_cfrag8(const typename Tr<CPLX>::T* __restrict__ M, int g, int t, int chi) {
   CMsgFrag f;
-  const double2 zero = make_double2(0.0, 0.0);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int ca = t + 4 * j, cb = 2 * t + j;
-    const double2 a = (g < chi && ca < chi) ? *reinterpret_cast<const double2*>(M + 2 * (g + chi * ca)) : zero;
-    const double2 b = (g < chi && cb < chi) ? *reinterpret_cast<const double2*>(M + 2 * (g + chi * cb)) : zero;
+    double2 a = make_double2(0.0, 0.0), b = a;
+    if (g < chi && ca < chi) a = Tr<CPLX>::pack(M[g + chi * ca]);
+    if (g < chi && cb < chi) b = Tr<CPLX>::pack(M[g + chi * cb]);
     f.mar[j] = a.x;
     f.mai[j] = a.y;
     f.mbr[j] = b.x;
@@ -93,21 +114,30 @@ __device__ __forceinline__ CMsgFrag load_cfrag8(const double* __restrict__ M, in
   return f;
 }
 
-// D[x' = g, y = 2t + i] = sum_x M[x', x] src[x, y]   (complex; accumulators start at zero)
+// D[x' = g, y = 2t + i] = sum_x M[x', x] src[x, y]   (accumulators start at zero).  Complex: (xr, xi) = real / imaginary
+// part.  Real: xr / xi are the two physical values of the chunk, each its own chain.
+template <bool CPLX>
 __device__ __forceinline__ void cabsorb(const CMsgFrag& m, const double2& b0, const double2& b1, double (&xr)[2], double (&xi)[2]) {
   xr[0] = xr[1] = xi[0] = xi[1] = 0.0;
-  dmma(xr[0], xr[1], m.mar[0], b0.x);
-  dmma(xi[0], xi[1], m.mai[0], b0.x);
-  dmma(xr[0], xr[1], m.mai[0], neg(b0.y));
-  dmma(xi[0], xi[1], m.mar[0], b0.y);
-  dmma(xr[0], xr[1], m.mar[1], b1.x);
-  dmma(xi[0], xi[1], m.mai[1], b1.x);
-  dmma(xr[0], xr[1], m.mai[1], neg(b1.y));
-  dmma(xi[0], xi[1], m.mar[1], b1.y);
+  if (CPLX) {
+    dmma(xr[0], xr[1], m.mar[0], b0.x);
+    dmma(xi[0], xi[1], m.mai[0], b0.x);
+    dmma(xr[0], xr[1], m.mai[0], neg(b0.y));
+    dmma(xi[0], xi[1], m.mar[0], b0.y);
+    dmma(xr[0], xr[1], m.mar[1], b1.x);
+    dmma(xi[0], xi[1], m.mai[1], b1.x);
+    dmma(xr[0], xr[1], m.mai[1], neg(b1.y));
+    dmma(xi[0], xi[1], m.mar[1], b1.y);
+  } else {
+    dmma(xr[0], xr[1], m.mar[0], b0.x);
+    dmma(xi[0], xi[1], m.mar[0], b0.y);
+    dmma(xr[0], xr[1], m.mar[1], b1.x);
+    dmma(xi[0], xi[1], m.mar[1], b1.y);
+  }
 }
 
 // dst[.., x', y', ..] = sum_{x,y} MX[x', x] MY[y', y] src[.., x, y, ..]   (legs X then Y absorbed; dst != src)
-template <int X, int Y, int C0, int C1>
+template <bool CPLX, int X, int Y, int C0, int C1>
 __device__ __forceinline__ void absorb_pair_c(const double* src, double* dst, const CMsgFrag& mx, const CMsgFrag& my, int warp, int g, int t) {
   const uint32_t ld0 = leg_pos(X, t) ^ leg_pos(Y, g), ld1 = leg_pos(X, t + 4) ^ leg_pos(Y, g);
   const uint32_t st0 = leg_pos(X, g) ^ leg_pos(Y, 2 * t), st1 = leg_pos(X, g) ^ leg_pos(Y, 2 * t + 1);
@@ -117,15 +147,20 @@ __device__ __forceinline__ void absorb_pair_c(const double* src, double* dst, co
     const double2 b0 = *reinterpret_cast<const double2*>(src + (base ^ ld0));
     const double2 b1 = *reinterpret_cast<const double2*>(src + (base ^ ld1));
     double xr[2], xi[2];
-    cabsorb(mx, b0, b1, xr, xi);
+    cabsorb<CPLX>(mx, b0, b1, xr, xi);
     // absorb Y from registers: D2[x' = g, y' = 2t + i'] = sum_{y = 2t + i} D1[x', y] MY[y', y]
     double pr0 = 0, pr1 = 0, pi0 = 0, pi1 = 0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      dmma(pr0, pr1, xr[i], my.mbr[i]);
-      dmma(pi0, pi1, xr[i], my.mbi[i]);
-      dmma(pr0, pr1, neg(xi[i]), my.mbi[i]);
-      dmma(pi0, pi1, xi[i], my.mbr[i]);
+      if (CPLX) {
+        dmma(pr0, pr1, xr[i], my.mbr[i]);
+        dmma(pi0, pi1, xr[i], my.mbi[i]);
+        dmma(pr0, pr1, neg(xi[i]), my.mbi[i]);
+        dmma(pi0, pi1, xi[i], my.mbr[i]);
+      } else {
+        dmma(pr0, pr1, xr[i], my.mbr[i]);
+        dmma(pi0, pi1, xi[i], my.mbr[i]);
+      }
     }
     *reinterpret_cast<double2*>(dst + (base ^ st0)) = make_double2(pr0, pi0);
     *reinterpret_cast<double2*>(dst + (base ^ st1)) = make_double2(pr1, pi1);
@@ -133,7 +168,7 @@ __device__ __forceinline__ void absorb_pair_c(const double* src, double* dst, co
 }
 
 // dst[.., x', y, ..] = sum_x MX[x', x] src[.., x, y, ..]   (single absorption; Y is a passive tile leg)
-template <int X, int Y, int C0, int C1>
+template <bool CPLX, int X, int Y, int C0, int C1>
 __device__ __forceinline__ void absorb_one_c(const double* src, double* dst, const CMsgFrag& mx, int warp, int g, int t) {
   const uint32_t ld0 = leg_pos(X, t) ^ leg_pos(Y, g), ld1 = leg_pos(X, t + 4) ^ leg_pos(Y, g);
   const uint32_t st0 = leg_pos(X, g) ^ leg_pos(Y, 2 * t), st1 = leg_pos(X, g) ^ leg_pos(Y, 2 * t + 1);
@@ -142,7 +177,7 @@ __device__ __forceinline__ void absorb_one_c(const double* src, double* dst, con
     const double2 b0 = *reinterpret_cast<const double2*>(src + (base ^ ld0));
     const double2 b1 = *reinterpret_cast<const double2*>(src + (base ^ ld1));
     double xr[2], xi[2];
-    cabsorb(mx, b0, b1, xr, xi);
+    cabsorb<CPLX>(mx, b0, b1, xr, xi);
     *reinterpret_cast<double2*>(dst + (base ^ st0)) = make_double2(xr[0], xi[0]);
     *reinterpret_cast<double2*>(dst + (base ^ st1)) = make_double2(xr[1], xi[1]);
   }
@@ -158,7 +193,7 @@ __device__ __forceinline__ void cacc_zero(CAcc& a) {
 }
 
 // acc[v', v] += sum_{cols, u'} conj(A[.., u', v']) * ( sum_u MU[u', u] P[.., u, v] )   (leg U absorbed on the fly, V open)
-template <int U, int V, int C0, int C1>
+template <bool CPLX, int U, int V, int C0, int C1>
 __device__ __forceinline__ void absorb_close_c(const double* P, const double* A, const CMsgFrag& mu, int warp, int g, int t, CAcc& acc) {
   const uint32_t lp0 = leg_pos(U, t) ^ leg_pos(V, g), lp1 = leg_pos(U, t + 4) ^ leg_pos(V, g);
   const uint32_t la0 = leg_pos(U, 2 * t) ^ leg_pos(V, g), la1 = leg_pos(U, 2 * t + 1) ^ leg_pos(V, g);
@@ -171,23 +206,34 @@ __device__ __forceinline__ void absorb_close_c(const double* P, const double* A,
     const double2 a1 = *reinterpret_cast<const double2*>(A + (base ^ la1));
     // T[v = g, u' = 2t + i] = sum_u P[u, v] MU[u', u]
     double tr0 = 0, tr1 = 0, ti0 = 0, ti1 = 0;
-    dmma(tr0, tr1, p0.x, mu.mar[0]);
-    dmma(ti0, ti1, p0.x, mu.mai[0]);
-    dmma(tr0, tr1, neg(p0.y), mu.mai[0]);
-    dmma(ti0, ti1, p0.y, mu.mar[0]);
-    dmma(tr0, tr1, p1.x, mu.mar[1]);
-    dmma(ti0, ti1, p1.x, mu.mai[1]);
-    dmma(tr0, tr1, neg(p1.y), mu.mai[1]);
-    dmma(ti0, ti1, p1.y, mu.mar[1]);
-    // out[v' = g, v] += sum_{u' = 2t + i} conj(A[u', v']) T[v, u']
-    dmma(acc.r[0][0], acc.r[0][1], a0.x, tr0);
-    dmma(acc.i[0][0], acc.i[0][1], a0.x, ti0);
-    dmma(acc.r[1][0], acc.r[1][1], a1.x, tr1);
-    dmma(acc.i[1][0], acc.i[1][1], a1.x, ti1);
-    dmma(acc.r[0][0], acc.r[0][1], a0.y, ti0);
-    dmma(acc.i[0][0], acc.i[0][1], neg(a0.y), tr0);
-    dmma(acc.r[1][0], acc.r[1][1], a1.y, ti1);
-    dmma(acc.i[1][0], acc.i[1][1], neg(a1.y), tr1);
+    if (CPLX) {
+      dmma(tr0, tr1, p0.x, mu.mar[0]);
+      dmma(ti0, ti1, p0.x, mu.mai[0]);
+      dmma(tr0, tr1, neg(p0.y), mu.mai[0]);
+      dmma(ti0, ti1, p0.y, mu.mar[0]);
+      dmma(tr0, tr1, p1.x, mu.mar[1]);
+      dmma(ti0, ti1, p1.x, mu.mai[1]);
+      dmma(tr0, tr1, neg(p1.y), mu.mai[1]);
+      dmma(ti0, ti1, p1.y, mu.mar[1]);
+      // out[v' = g, v] += sum_{u' = 2t + i} conj(A[u', v']) T[v, u']
+      dmma(acc.r[0][0], acc.r[0][1], a0.x, tr0);
+      dmma(acc.i[0][0], acc.i[0][1], a0.x, ti0);
+      dmma(acc.r[1][0], acc.r[1][1], a1.x, tr1);
+      dmma(acc.i[1][0], acc.i[1][1], a1.x, ti1);
+      dmma(acc.r[0][0], acc.r[0][1], a0.y, ti0);
+      dmma(acc.i[0][0], acc.i[0][1], neg(a0.y), tr0);
+      dmma(acc.r[1][0], acc.r[1][1], a1.y, ti1);
+      dmma(acc.i[1][0], acc.i[1][1], neg(a1.y), tr1);
+    } else {  // (tr, ti) and (acc.r, acc.i): the two physical values of the chunk; summed when the tile is stored
+      dmma(tr0, tr1, p0.x, mu.mar[0]);
+      dmma(ti0, ti1, p0.y, mu.mar[0]);
+      dmma(tr0, tr1, p1.x, mu.mar[1]);
+      dmma(ti0, ti1, p1.y, mu.mar[1]);
+      dmma(acc.r[0][0], acc.r[0][1], a0.x, tr0);
+      dmma(acc.i[0][0], acc.i[0][1], a0.y, ti0);
+      dmma(acc.r[1][0], acc.r[1][1], a1.x, tr1);
+      dmma(acc.i[1][0], acc.i[1][1], a1.y, ti1);
+    }
   }
 }
 
@@ -196,14 +242,15 @@ constexpr size_t SMEM_DOUBLES8C = (size_t)3 * NELEM + NW * MAXT * CMSG8 + 128 + 
 constexpr size_t SMEM_BYTES8C = SMEM_DOUBLES8C * sizeof(double);
 enum { BAR_C8 = 1 };
 
-// canonical A_v[s, a0..] (complex, column-major, true dims) -> private image: d slices [(re, im), a0..] in leg_pos order,
-// every leg zero-padded to 8
+// canonical A_v[s, a0..] (column-major, true dims) -> private image: slices [chunk, a0..] in leg_pos order, every leg
+// zero-padded to 8; chunk = (re, im) of physical value s (complex) or the physical pair (2s, 2s + 1) (real)
+template <bool CPLX>
 __global__ void swizzle_sites_c8(const ItemDesc* items, int n_slots, const double* __restrict__ src, double* __restrict__ dst) {
   for (int it = blockIdx.x; it < n_slots; it += gridDim.x) {
     const ItemDesc d = items[it];
     if (d.kind < 0 || !d.first) continue;
     const int nsl = slice_doubles(d.kind), nb = nsl / 2;
-    const double* s0 = src + 2 * d.canon_off;
+    const double* s0 = src + (CPLX ? 2 : 1) * d.canon_off;
     double* d0 = dst + d.site_off;
     for (int c = threadIdx.x; c < nb * d.d; c += blockDim.x) {
       const int s = c % d.d, b = c / d.d;
@@ -211,23 +258,33 @@ __global__ void swizzle_sites_c8(const ItemDesc* items, int n_slots, const doubl
       const uint32_t p = leg_pos(0, a0) ^ leg_pos(1, a1) ^ leg_pos(2, a2) ^ leg_pos(3, a3);
       double2 v = make_double2(0.0, 0.0);
       if (a0 < d.dim[0] && a1 < d.dim[1] && a2 < d.dim[2] && a3 < d.dim[3]) {
-        const size_t ci = (size_t)s + (size_t)d.d * (a0 + (size_t)d.dim[0] * (a1 + (size_t)d.dim[1] * (a2 + (size_t)d.dim[2] * a3)));
-        v = *reinterpret_cast<const double2*>(s0 + 2 * ci);
+        const size_t lin = (size_t)d.phys * (a0 + (size_t)d.dim[0] * (a1 + (size_t)d.dim[1] * (a2 + (size_t)d.dim[2] * a3)));
+        if (CPLX) {
+          v = *reinterpret_cast<const double2*>(s0 + 2 * (lin + s));
+        } else {
+          v.x = s0[lin + 2 * s];
+          if (2 * s + 1 < d.phys) v.y = s0[lin + 2 * s + 1];
+        }
       }
       *reinterpret_cast<double2*>(d0 + (size_t)s * nsl + p) = v;
     }
   }
 }
 
+template <bool CPLX>
 __device__ __forceinline__ void store_tile(double* mine, const CAcc& a, int g, int t) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const int el = g + CHI * (2 * t + c);  // out[v', v] at v' + 8 v
-    *reinterpret_cast<double2*>(mine + 2 * el) = make_double2(a.r[0][c] + a.r[1][c], a.i[0][c] + a.i[1][c]);
+    const double re = a.r[0][c] + a.r[1][c], im = a.i[0][c] + a.i[1][c];
+    *reinterpret_cast<double2*>(mine + 2 * el) = CPLX ? make_double2(re, im) : make_double2(re + im, 0.0);
   }
 }
 
-__global__ void __launch_bounds__(NT, 1) bp_update_onchip_c8c(Args k) {
+template <bool CPLX>
+__global__ void __launch_bounds__(NT, 1) bp_update_onchip_c8x(Args k) {
+  using T = typename Tr<CPLX>::T;
+  using E = Elem<T>;
   extern __shared__ __align__(128) double smem[];
   double* Pbuf = smem + 2 * NELEM;
   double* red = smem + 3 * NELEM;
@@ -305,107 +362,107 @@ __global__ void __launch_bounds__(NT, 1) bp_update_onchip_c8c(Args k) {
     const int chi_o = my_tile < ntile ? d->out_dim[my_tile] : 0;
     const bool my_valid = (my_el & 7) < chi_o && (my_el >> 3) < chi_o;  // inside the true chi_o x chi_o message
     const int64_t my_off = my_valid ? d->out_off[my_tile] + (my_el & 7) + chi_o * (my_el >> 3) : 0;
-    c64 old = make_c64(0.0, 0.0);
-    if (my_valid) old = reinterpret_cast<const c64*>(k.msg_in)[my_off];
+    T old = E::zero();
+    if (my_valid) old = reinterpret_cast<const T*>(k.msg_in)[my_off];
     CAcc acc[MAXT];
 #pragma unroll
     for (int i = 0; i < MAXT; ++i) cacc_zero(acc[i]);
-    const c64* min_c = reinterpret_cast<const c64*>(k.msg_in);
+    const T* min_c = reinterpret_cast<const T*>(k.msg_in);
     if (kind <= 1) {
-      const CMsgFrag m0 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[0]), g, t, d->dim[0]);
-      const CMsgFrag m1 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[1]), g, t, d->dim[1]);
-      const CMsgFrag m2 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[2]), g, t, d->dim[2]);
-      const CMsgFrag m3 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[3]), g, t, d->dim[3]);
+      const CMsgFrag m0 = load_cfrag8<CPLX>(min_c + d->in_off[0], g, t, d->dim[0]);
+      const CMsgFrag m1 = load_cfrag8<CPLX>(min_c + d->in_off[1], g, t, d->dim[1]);
+      const CMsgFrag m2 = load_cfrag8<CPLX>(min_c + d->in_off[2], g, t, d->dim[2]);
+      const CMsgFrag m3 = load_cfrag8<CPLX>(min_c + d->in_off[3], g, t, d->dim[3]);
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;
         mbar_wait(&mbar[sl], (u >> 1) & 1);
         const double* A = smem + sl * NELEM;
         if (kind == 0) {  // P = A·M0·M1 -> out3 (absorb 2, close 3), out2 (absorb 3, close 2)
-          absorb_pair_c<0, 1, 2, 3>(A, Pbuf, m0, m1, warp, g, t);
+          absorb_pair_c<CPLX, 0, 1, 2, 3>(A, Pbuf, m0, m1, warp, g, t);
           bar_sync(BAR_C8, NT);
-          absorb_close_c<2, 3, 0, 1>(Pbuf, A, m2, warp, g, t, acc[0]);
-          absorb_close_c<3, 2, 0, 1>(Pbuf, A, m3, warp, g, t, acc[1]);
+          absorb_close_c<CPLX, 2, 3, 0, 1>(Pbuf, A, m2, warp, g, t, acc[0]);
+          absorb_close_c<CPLX, 3, 2, 0, 1>(Pbuf, A, m3, warp, g, t, acc[1]);
         } else {          // Q = A·M2·M3 -> out1 (absorb 0, close 1), out0 (absorb 1, close 0)
-          absorb_pair_c<2, 3, 0, 1>(A, Pbuf, m2, m3, warp, g, t);
+          absorb_pair_c<CPLX, 2, 3, 0, 1>(A, Pbuf, m2, m3, warp, g, t);
           bar_sync(BAR_C8, NT);
-          absorb_close_c<0, 1, 2, 3>(Pbuf, A, m0, warp, g, t, acc[0]);
-          absorb_close_c<1, 0, 2, 3>(Pbuf, A, m1, warp, g, t, acc[1]);
+          absorb_close_c<CPLX, 0, 1, 2, 3>(Pbuf, A, m0, warp, g, t, acc[0]);
+          absorb_close_c<CPLX, 1, 0, 2, 3>(Pbuf, A, m1, warp, g, t, acc[1]);
         }
         release(sl);
         bar_sync(BAR_C8, NT);  // P is rewritten by the next slice
       }
     } else if (kind == 2) {
-      const CMsgFrag m0 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[0]), g, t, d->dim[0]);
-      const CMsgFrag m1 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[1]), g, t, d->dim[1]);
-      const CMsgFrag m2 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[2]), g, t, d->dim[2]);
+      const CMsgFrag m0 = load_cfrag8<CPLX>(min_c + d->in_off[0], g, t, d->dim[0]);
+      const CMsgFrag m1 = load_cfrag8<CPLX>(min_c + d->in_off[1], g, t, d->dim[1]);
+      const CMsgFrag m2 = load_cfrag8<CPLX>(min_c + d->in_off[2], g, t, d->dim[2]);
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;
         mbar_wait(&mbar[sl], (u >> 1) & 1);
         const double* A = smem + sl * NELEM;
         // X = A·M0 -> out2 (absorb 1, close 2), out1 (absorb 2, close 1);  X' = A·M2 -> out0 (absorb 1, close 0)
-        absorb_one_c<0, 1, 2, -1>(A, Pbuf, m0, warp, g, t);
+        absorb_one_c<CPLX, 0, 1, 2, -1>(A, Pbuf, m0, warp, g, t);
         bar_sync(BAR_C8, NT);
-        absorb_close_c<1, 2, 0, -1>(Pbuf, A, m1, warp, g, t, acc[0]);
-        absorb_close_c<2, 1, 0, -1>(Pbuf, A, m2, warp, g, t, acc[1]);
+        absorb_close_c<CPLX, 1, 2, 0, -1>(Pbuf, A, m1, warp, g, t, acc[0]);
+        absorb_close_c<CPLX, 2, 1, 0, -1>(Pbuf, A, m2, warp, g, t, acc[1]);
         bar_sync(BAR_C8, NT);
-        absorb_one_c<2, 1, 0, -1>(A, Pbuf, m2, warp, g, t);
+        absorb_one_c<CPLX, 2, 1, 0, -1>(A, Pbuf, m2, warp, g, t);
         bar_sync(BAR_C8, NT);
-        absorb_close_c<1, 0, 2, -1>(Pbuf, A, m1, warp, g, t, acc[2]);
+        absorb_close_c<CPLX, 1, 0, 2, -1>(Pbuf, A, m1, warp, g, t, acc[2]);
         release(sl);
         bar_sync(BAR_C8, NT);
       }
     } else {  // degree 2: out1 (absorb 0, close 1), out0 (absorb 1, close 0) straight from A
-      const CMsgFrag m0 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[0]), g, t, d->dim[0]);
-      const CMsgFrag m1 = load_cfrag8(reinterpret_cast<const double*>(min_c + d->in_off[1]), g, t, d->dim[1]);
+      const CMsgFrag m0 = load_cfrag8<CPLX>(min_c + d->in_off[0], g, t, d->dim[0]);
+      const CMsgFrag m1 = load_cfrag8<CPLX>(min_c + d->in_off[1], g, t, d->dim[1]);
       for (int s = 0; s < nd; ++s, ++u) {
         const int sl = u & 1;
         mbar_wait(&mbar[sl], (u >> 1) & 1);
         const double* A = smem + sl * NELEM;
-        absorb_close_c<0, 1, -1, -1>(A, A, m0, warp, g, t, acc[0]);
-        absorb_close_c<1, 0, -1, -1>(A, A, m1, warp, g, t, acc[1]);
+        absorb_close_c<CPLX, 0, 1, -1, -1>(A, A, m0, warp, g, t, acc[0]);
+        absorb_close_c<CPLX, 1, 0, -1, -1>(A, A, m1, warp, g, t, acc[1]);
         release(sl);
       }
     }
     // ---- cross-warp reduction + block-wide epilogue: two warps per output tile, one element per thread ----
 #pragma unroll
     for (int i = 0; i < MAXT; ++i)
-      if (i < ntile) store_tile(red + (warp * MAXT + i) * CMSG8, acc[i], g, t);
+      if (i < ntile) store_tile<CPLX>(red + (warp * MAXT + i) * CMSG8, acc[i], g, t);
     bar_sync(BAR_C8, NT);
     {
-      using E = Elem<c64>;
-      c64 v = E::zero();
+      double2 vsum = make_double2(0.0, 0.0);
       if (my_valid) {
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
           const double2 q = *reinterpret_cast<const double2*>(red + (w * MAXT + my_tile) * CMSG8 + 2 * my_el);
-          v.re += q.x;
-          v.im += q.y;
+          vsum.x += q.x;
+          vsum.y += q.y;
         }
       }
-      double* part1 = part;       // [NW] complex sums
+      const T v = Tr<CPLX>::unpack(vsum);
+      double* part1 = part;       // [NW] (complex) sums
       double* part2 = part + 32;  // [NW][4]
-      const c64 sw = warp_sum<c64>(v);
-      if (lane == 0) *reinterpret_cast<double2*>(part1 + 2 * warp) = make_double2(sw.re, sw.im);
+      const T sw = warp_sum<T>(v);
+      if (lane == 0) *reinterpret_cast<double2*>(part1 + 2 * warp) = Tr<CPLX>::pack(sw);
       bar_sync(BAR_C8, NT);
       const double2 q0 = *reinterpret_cast<const double2*>(part1 + 2 * (warp & ~1)), q1 = *reinterpret_cast<const double2*>(part1 + 2 * (warp | 1));
-      const c64 s = make_c64(q0.x + q1.x, q0.y + q1.y);
-      c64 x = v;
+      const T s = Tr<CPLX>::unpack(make_double2(q0.x + q1.x, q0.y + q1.y));
+      T x = v;
       if (my_valid) {
         if (k.normalize && !E::is_zero(s)) x = E::div(v, s);
         const int64_t off = my_off;
-        reinterpret_cast<c64*>(k.msg_out)[off] = x;
-        if (k.io.host_out) reinterpret_cast<c64*>(k.io.host_out)[off] = x;
+        reinterpret_cast<T*>(k.msg_out)[off] = x;
+        if (k.io.host_out) reinterpret_cast<T*>(k.io.host_out)[off] = x;
         if (k.peer.nranks > 1 && d->peer[my_tile] >= 0) {
-          reinterpret_cast<c64*>(k.peer.peer_out[d->peer[my_tile]])[off] = x;
+          reinterpret_cast<T*>(k.peer.peer_out[d->peer[my_tile]])[off] = x;
           __threadfence_system();  // released here instead of at the kernel's tail
         }
       }
-      c64 dot = warp_sum<c64>(E::fma(E::conj(old), x, E::zero()));
+      const double2 dot = Tr<CPLX>::pack(warp_sum<T>(E::fma(E::conj(old), x, E::zero())));
       const double n_old = warp_sum_d(E::abs2(old)), n_new = warp_sum_d(my_valid ? E::abs2(x) : 0.0);
       if (lane == 0) {
         double* q = part2 + 4 * warp;
-        q[0] = dot.re;
-        q[1] = dot.im;
+        q[0] = dot.x;
+        q[1] = dot.y;
         q[2] = n_old;
         q[3] = n_new;
       }

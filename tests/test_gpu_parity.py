@@ -133,6 +133,21 @@ def test_complex_chi8_kernel_square_lattice(oracle, dims, phys):
                 a, b = b, a
 
 
+@pytest.mark.parametrize("chi,d,dims", [(2, 2, (4, 4)), (5, 3, (4, 5)), (7, 1, (3, 4)), (8, 3, (3, 3))])
+def test_real_slice_kernel_small_and_odd_shapes(oracle, chi, d, dims):
+    # Float64 buckets outside the hand-tuned (chi = 8, d = 2) shape -- cfg1's chi = 2, odd d, chi = 5 / 7 -- run on the
+    # templated slice kernel (zero-padded image, physical pairs): degrees 2, 3, 4 in one launch
+    ga = graphs.graph_arrays(graphs.named_grid(dims))
+    rng = np.random.default_rng(chi * 10 + d)
+    link_dim = [chi] * ga.ne
+    tensors = peps_tensors(ga, chi, d, np.float64, rng)
+    msgs = positive_messages(ga, link_dim, np.float64, rng)
+    buckets = check_sweeps(oracle, ga, np.float64, "norm", [d] * ga.nv, link_dim, tensors, msgs, 3)
+    assert {b["degree"] for b in buckets} == {2, 3, 4}
+    assert all(b["kernel"] == _lib.BPX_KERNEL_ONCHIP for b in buckets), buckets
+    check_sweeps(oracle, ga, np.float64, "norm", [d] * ga.nv, link_dim, tensors, msgs, 2, normalize=False)
+
+
 # ---- edge cases ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_ragged_link_dims_and_degree_one(oracle, dtype):
