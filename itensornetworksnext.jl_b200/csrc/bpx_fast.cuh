@@ -30,6 +30,13 @@ inline bool uses_c8x(const bpx_ctx* ctx, const Bucket& b) {
   return b.d >= 1 && b.z >= 2 && b.z <= 4 && b.max_dim <= 8 && !real_tuned_c8(b);
 }
 
+// ... and by the 16-wide slice kernel of bpx_onchip16c.cuh: ComplexF64 family 16, and the remaining Float64 buckets with
+// degree 1..3 and link dims <= 16
+inline bool uses_c16x(const bpx_ctx* ctx, const Bucket& b) {
+  if (ctx->dtype == BPX_C64) return complex_family(b) == 16;
+  return b.d >= 1 && b.z >= 1 && b.z <= 3 && b.max_dim <= 16 && !real_tuned_c8(b) && !real_tuned_c16(b) && !uses_c8x(ctx, b);
+}
+
 inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
   if (kernel == BPX_KERNEL_GENERIC) return true;
   if (ctx->mode != BPX_MODE_NORM) return false;
@@ -47,6 +54,7 @@ inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
     // 16-wide on-chip kernel: degree 3 / chi 16, or degree 6 / chi 4 with legs paired into super-legs
     if (real_tuned_c16(b)) return (size_t)ctx->max_smem_optin >= onchip16::SMEM_BYTES16;
     if (uses_c8x(ctx, b)) return (size_t)ctx->max_smem_optin >= onchip8c::SMEM_BYTES8C;
+    if (uses_c16x(ctx, b)) return (size_t)ctx->max_smem_optin >= onchip16c::SMEM_BYTES16C;
     return false;
   }
   if (kernel == BPX_KERNEL_SLICED)
@@ -104,15 +112,17 @@ inline int fast_prepare(bpx_ctx* ctx) {
   }
   ctx->n_onchip16c_slots = 0;
   ctx->onchip16c_grid = 0;
-  if (ctx->dtype == BPX_C64) {
-    // ---- complex chi = 16 buckets (degree 1..3): one launch; items scheduled onto the CTAs here (LPT), laid out as rounds ----
+  {
+    // ---- 16-wide slice-kernel buckets (complex family 16 / general real, degree 1..3): one launch; items scheduled onto
+    // the CTAs here (LPT), laid out as rounds ----
+    const bool cplx = ctx->dtype == BPX_C64;
     std::vector<onchip16c::ItemDesc> its;
     std::vector<double> cost;
     int leader = -1;
     int64_t img_total = 0;  // doubles of the zero-padded image
     for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
       Bucket& b = ctx->buckets[i];
-      if (b.kernel != BPX_KERNEL_ONCHIP || complex_family(b) != 16 || b.my_vertices.empty()) continue;
+      if (b.kernel != BPX_KERNEL_ONCHIP || !uses_c16x(ctx, b) || b.my_vertices.empty()) continue;
       if (leader < 0) leader = i;
       b.leader = leader;
       for (int32_t v : b.my_vertices) {
@@ -128,9 +138,10 @@ inline int fast_prepare(bpx_ctx* ctx) {
         onchip16c::ItemDesc d;
         memset(&d, 0, sizeof(d));
         d.site_off = img_total;
-        img_total += (int64_t)b.d * (b.z == 3 ? onchip16c::NSL3 : (b.z == 2 ? onchip16c::NSL2 : onchip16c::NSL1));
+        d.phys = b.d;
+        d.d = cplx ? b.d : (b.d + 1) / 2;  // slices: physical values (complex) or physical pairs (real)
+        img_total += (int64_t)d.d * (b.z == 3 ? onchip16c::NSL3 : (b.z == 2 ? onchip16c::NSL2 : onchip16c::NSL1));
         d.canon_off = ctx->dev_site_off[v];
-        d.d = b.d;
         d.peer[0] = d.peer[1] = -1;
         d.first = 1;
         for (int l = 0; l < 3; ++l) d.dim[l] = l < b.z ? ctx->h_vdesc[v].dim[l] : 1;
@@ -147,7 +158,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
             d.in_dim[1] = d.dim[second_leg[leg]];
             edge_of(d, 0, leg);
             its.push_back(d);
-            cost.push_back(16000.0 * b.d + 3000.0);
+            cost.push_back((cplx ? 16000.0 : 4000.0) * d.d + 3000.0);
             d.first = 0;
           }
         } else if (b.z == 2) {
@@ -159,7 +170,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
           edge_of(d, 0, 0);
           edge_of(d, 1, 1);
           its.push_back(d);
-          cost.push_back(3000.0 * b.d + 3000.0);
+          cost.push_back((cplx ? 3000.0 : 1000.0) * d.d + 3000.0);
         } else {
           d.kind = 2;
           edge_of(d, 0, 0);
@@ -203,7 +214,9 @@ inline int fast_prepare(bpx_ctx* ctx) {
         return BPX_ERR_ALLOC;
       }
       BPX_CUDA(ctx, cudaMemcpy(ctx->d_onchip16c_items, slots.data(), slots.size() * sizeof(onchip16c::ItemDesc), cudaMemcpyHostToDevice));
-      BPX_CUDA(ctx, cudaFuncSetAttribute(onchip16c::bp_update_onchip_c16c, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      BPX_CUDA(ctx, cudaFuncSetAttribute(onchip16c::bp_update_onchip_c16x<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)onchip16c::SMEM_BYTES16C));
+      BPX_CUDA(ctx, cudaFuncSetAttribute(onchip16c::bp_update_onchip_c16x<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)onchip16c::SMEM_BYTES16C));
       if (ctx->d_img16c) cudaFree(ctx->d_img16c);
       ctx->d_img16c = nullptr;
@@ -482,8 +495,12 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
     BPX_CUDA(ctx, cudaGetLastError());
   }
   if (ctx->d_img16c && ctx->n_onchip16c_slots > 0) {
-    onchip16c::swizzle_sites_c16<<<std::min(ctx->n_onchip16c_slots, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
-        (const onchip16c::ItemDesc*)ctx->d_onchip16c_items, ctx->n_onchip16c_slots, (const double*)ctx->d_sites, (double*)ctx->d_img16c);
+    if (ctx->dtype == BPX_C64)
+      onchip16c::swizzle_sites_c16<true><<<std::min(ctx->n_onchip16c_slots, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
+          (const onchip16c::ItemDesc*)ctx->d_onchip16c_items, ctx->n_onchip16c_slots, (const double*)ctx->d_sites, (double*)ctx->d_img16c);
+    else
+      onchip16c::swizzle_sites_c16<false><<<std::min(ctx->n_onchip16c_slots, 8 * ctx->num_sms), 256, 0, ctx->stream>>>(
+          (const onchip16c::ItemDesc*)ctx->d_onchip16c_items, ctx->n_onchip16c_slots, (const double*)ctx->d_sites, (double*)ctx->d_img16c);
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
   }
@@ -528,7 +545,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     BPX_CUDA(ctx, cudaGetLastError());
     return BPX_OK;
   }
-  if (b.kernel == BPX_KERNEL_ONCHIP && ctx->dtype == BPX_C64) {
+  if (b.kernel == BPX_KERNEL_ONCHIP && uses_c16x(ctx, b)) {
     onchip16c::Args k;
     k.items = (const onchip16c::ItemDesc*)ctx->d_onchip16c_items;
     k.n_slots = ctx->n_onchip16c_slots;
@@ -541,7 +558,10 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.io = ctx->io_args;
     k.timing = (long long*)ctx->d_timing;
     if (ctx->onchip16c_grid == 0) return BPX_OK;
-    onchip16c::bp_update_onchip_c16c<<<ctx->onchip16c_grid, onchip16c::NTHREADSC, onchip16c::SMEM_BYTES16C, ctx->stream>>>(k);
+    if (ctx->dtype == BPX_C64)
+      onchip16c::bp_update_onchip_c16x<true><<<ctx->onchip16c_grid, onchip16c::NTHREADSC, onchip16c::SMEM_BYTES16C, ctx->stream>>>(k);
+    else
+      onchip16c::bp_update_onchip_c16x<false><<<ctx->onchip16c_grid, onchip16c::NTHREADSC, onchip16c::SMEM_BYTES16C, ctx->stream>>>(k);
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
     return BPX_OK;

@@ -38,6 +38,7 @@ using onchip::mbar_wait;
 using onchip::n_cols;
 using onchip::tma_bulk_g2s;
 using onchip16c::Cursor;
+using onchip16c::Tr;
 using onchip16c::neg;
 
 constexpr int NW = 8;
@@ -76,21 +77,6 @@ struct Args {
 
 __device__ __forceinline__ int slice_doubles(int kind) { return kind <= 1 ? NELEM : (kind == 2 ? NELEM / 8 : NELEM / 64); }
 __device__ __forceinline__ int n_tiles(int kind) { return kind == 2 ? 3 : 2; }
-
-template <bool CPLX>
-struct Tr;
-template <>
-struct Tr<true> {
-  using T = c64;
-  __device__ static __forceinline__ double2 pack(c64 a) { return make_double2(a.re, a.im); }
-  __device__ static __forceinline__ c64 unpack(double2 q) { return make_c64(q.x, q.y); }
-};
-template <>
-struct Tr<false> {
-  using T = double;
-  __device__ static __forceinline__ double2 pack(double a) { return make_double2(a, 0.0); }
-  __device__ static __forceinline__ double unpack(double2 q) { return q.x; }
-};
 
 struct CMsgFrag {
   double mar[2], mai[2];  // M[g, t + 4j]  : A operand of "absorb first leg", B operand of the T-GEMM

@@ -148,6 +148,22 @@ def test_real_slice_kernel_small_and_odd_shapes(oracle, chi, d, dims):
     check_sweeps(oracle, ga, np.float64, "norm", [d] * ga.nv, link_dim, tensors, msgs, 2, normalize=False)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("chi,d", [(12, 3), (16, 1), (9, 2)])
+def test_wide_slice_kernel_dims_up_to_16(oracle, dtype, chi, d):
+    # degree 1..3 with link dims 9..16 (and chi = 16 outside the tuned d = 2 shape): the 16-wide slice kernel, both dtypes
+    g = graphs.named_comb_tree((3, 2))
+    g.add_edge((1, 2), (2, 2))
+    ga = graphs.graph_arrays(g)
+    rng = np.random.default_rng(chi + d)
+    link_dim = [chi] * ga.ne
+    tensors = peps_tensors(ga, chi, d, dtype, rng)
+    msgs = positive_messages(ga, link_dim, dtype, rng)
+    buckets = check_sweeps(oracle, ga, dtype, "norm", [d] * ga.nv, link_dim, tensors, msgs, 3)
+    assert {b["degree"] for b in buckets} == {1, 2, 3}
+    assert all(b["kernel"] == _lib.BPX_KERNEL_ONCHIP for b in buckets), buckets
+
+
 # ---- edge cases ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_ragged_link_dims_and_degree_one(oracle, dtype):
@@ -165,10 +181,9 @@ def test_ragged_link_dims_and_degree_one(oracle, dtype):
         tensors.append(randn(rng, dtype, (phys[v], *dims)))
     msgs = positive_messages(ga, link_dim, dtype, rng)
     buckets = check_sweeps(oracle, ga, dtype, "norm", phys, link_dim, tensors, msgs, 3)
-    if np.dtype(dtype).kind == "c":
-        # ComplexF64: link dims 1..4, different per leg, d = 1..3 run on the on-chip kernels (zero-padded private images)
-        assert all(b["kernel"] == _lib.BPX_KERNEL_ONCHIP for b in buckets), buckets
-        check_sweeps(oracle, ga, dtype, "norm", phys, link_dim, tensors, msgs, 2, kernel=_lib.BPX_KERNEL_GENERIC)
+    # link dims 1..4, different per leg, d = 1..3, degrees 1..3: all on the slice kernels (zero-padded private images)
+    assert all(b["kernel"] == _lib.BPX_KERNEL_ONCHIP for b in buckets), buckets
+    check_sweeps(oracle, ga, dtype, "norm", phys, link_dim, tensors, msgs, 2, kernel=_lib.BPX_KERNEL_GENERIC)
 
 
 def test_isolated_vertex_and_empty_graph(oracle):
