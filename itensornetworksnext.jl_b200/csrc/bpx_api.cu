@@ -567,16 +567,16 @@ static void* mapped_alias(const void* host) {
   return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
-// can this rank's sweep run with streamed host I/O?  (one launch of a kernel family that implements HostIO)
+// can this rank's sweep run with streamed host I/O?  (every launch is a kernel family that implements HostIO)
 static bool sweep_streams_host_io(bpx_ctx* ctx) {
   int n = 0;
   for (int bi = 0; bi < (int)ctx->buckets.size(); ++bi) {
     const Bucket& b = ctx->buckets[bi];
     if (b.my_edges.empty()) continue;
-    if (b.kernel != BPX_KERNEL_ONCHIP) return false;  // every on-chip family implements HostIO
+    if (b.kernel != BPX_KERNEL_ONCHIP && b.kernel != BPX_KERNEL_SLICED) return false;
     if (b.leader == bi) ++n;
   }
-  return n == 1;
+  return n >= 1;
 }
 
 static void io_graphs_clear(bpx_ctx* ctx) {
@@ -909,17 +909,27 @@ static int sweep_once(bpx_ctx* ctx, int normalize) {
   const void* in = ctx->d_msg[ctx->cur];
   void* out = ctx->d_msg[ctx->cur ^ 1];
   int rc;
-  // Partitioned runs.  If this rank's whole sweep is one fast launch, that kernel itself waits for the peers' posts
-  // (producer-warp prologue), stores cut-edge messages into the peers from its epilogue and lets its last CTA post:
-  // no gate / halo / post launches.  Otherwise the exchange runs as separate small kernels.
+  // Partitioned runs.  If every launch of this rank's sweep is a specialised kernel, the exchange is fused into them:
+  // the FIRST launch waits for the peers' posts (prologue), every launch stores its cut-edge messages into the peers
+  // from its epilogue, and the last CTA of the LAST launch posts: no gate / halo / post launches.  Otherwise the
+  // exchange runs as separate small kernels.
   int n_fast = 0, n_generic = 0;
+  std::vector<std::pair<int64_t, int>> order;  // (-edges of the launch group, leader bucket): largest launch first, so
+  //                                              that a streamed upload overlaps with it; generic launch last
   for (int bi = 0; bi < (int)ctx->buckets.size(); ++bi) {
     const Bucket& b = ctx->buckets[bi];
     if (b.my_edges.empty()) continue;
     if (b.kernel == BPX_KERNEL_GENERIC) ++n_generic;
     else if (b.leader == bi) ++n_fast;
+    if (b.leader == bi) {
+      int64_t edges = 0;
+      for (const Bucket& o : ctx->buckets)
+        if (o.leader == bi && o.kernel == b.kernel) edges += (int64_t)o.my_edges.size();
+      order.emplace_back(b.kernel == BPX_KERNEL_GENERIC ? 1 : -edges, bi);
+    }
   }
-  const bool fused = ctx->nranks > 1 && ctx->halo_connected && n_fast == 1 && n_generic == 0 && !ctx->sites_dirty;
+  std::stable_sort(order.begin(), order.end(), [](const std::pair<int64_t, int>& a, const std::pair<int64_t, int>& b) { return a.first < b.first; });
+  const bool fused = ctx->nranks > 1 && ctx->halo_connected && n_fast >= 1 && n_generic == 0 && !ctx->sites_dirty;
   ctx->peer_args = PeerArgs{};
   if (!fused && (rc = halo_gate(ctx))) return rc;
   if ((rc = fast_refresh_sites(ctx))) return rc;
@@ -930,18 +940,26 @@ static int sweep_once(bpx_ctx* ctx, int normalize) {
     pa.rank = ctx->rank;
     pa.my_mailbox = reinterpret_cast<Mailbox*>(ctx->d_mailbox);
     pa.peer_mailbox = reinterpret_cast<Mailbox* const*>(ctx->d_peer_mailbox);
-    pa.wait_id = ctx->gate_pending ? ctx->sweep_id : 0;
+    pa.wait_id = 0;                 // set per launch below: the first launch gates, the last one posts
+    pa.post_id = 0;
     pa.wait_mask = ctx->recv_mask;  // only the ranks that feed this rank are awaited inside the kernel;
     pa.prev_global_key = nullptr;   // the global residual is folded by the explicit gate when the host asks for it
-    pa.post_id = ++ctx->sweep_id;
     pa.local_key = ctx->cur_slot;
     pa.peer_out = reinterpret_cast<double* const*>(ctx->d_peer_msg) + (size_t)(ctx->cur ^ 1) * ctx->nranks;
     pa.ticket = ctx->d_ticket;
     pa.error_flag = ctx->d_halo_error;
   }
-  for (int bi = 0; bi < (int)ctx->buckets.size(); ++bi) {
-    Bucket& b = ctx->buckets[bi];
-    if (b.my_edges.empty() || b.leader != bi) continue;  // merged into its group leader's launch
+  const unsigned long long fused_wait = fused && ctx->gate_pending ? ctx->sweep_id : 0;
+  const unsigned long long fused_post = fused ? ++ctx->sweep_id : 0;
+  unsigned int* const io_ticket = ctx->io_args.ticket;
+  for (size_t li = 0; li < order.size(); ++li) {
+    const int bi = order[li].second;
+    Bucket& b = ctx->buckets[bi];  // (buckets merged into a launch group run in their leader's launch)
+    if (fused) {
+      ctx->peer_args.wait_id = li == 0 ? fused_wait : 0;
+      ctx->peer_args.post_id = li + 1 == order.size() ? fused_post : 0;
+    }
+    ctx->io_args.ticket = li + 1 == order.size() ? io_ticket : nullptr;  // streamed host I/O: the last launch finishes the step
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->profiling && b.timing.size() < 8192) {
       BPX_CUDA(ctx, cudaEventCreate(&ev0));

@@ -134,7 +134,7 @@ __device__ __forceinline__ void residual_record(unsigned long long* slot, double
 template <typename T>
 __device__ __forceinline__ void warp_epilogue(const T* raw, const T* old_m, T* new_m, int nelem, int normalize,
                                               double* residual_slot, int lane, unsigned long long* resmax = nullptr,
-                                              T* peer_m = nullptr) {
+                                              T* peer_m = nullptr, T* host_m = nullptr) {
   using E = Elem<T>;
   T s = E::zero();
   for (int i = lane; i < nelem; i += 32) s = E::add(s, raw[i]);
@@ -151,6 +151,7 @@ __device__ __forceinline__ void warp_epilogue(const T* raw, const T* old_m, T* n
     n_new += E::abs2(v);
     new_m[i] = v;
     if (peer_m) peer_m[i] = v;  // cut edge: also store into the owning rank's message set (NVLink peer memory)
+    if (host_m) host_m[i] = v;  // streamed host I/O: the caller's mapped host buffer
   }
   if (peer_m) __threadfence_system();  // release the peer stores here, off the kernel's tail (see peer_post_when_last)
   dot = warp_sum<T>(dot);

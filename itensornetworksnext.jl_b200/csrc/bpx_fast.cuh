@@ -408,6 +408,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
             d.out_off[l] = ctx->msg_off[e];
             d.in_off[l] = ctx->msg_off[ctx->rev[e]];
             d.peer[l] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
+            d.need = std::max<int64_t>(d.need, std::max(ctx->upload_end[e], ctx->upload_end[ctx->rev[e]]));
           }
           sit.push_back(d);
         }
@@ -617,6 +618,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.resmax = ctx->cur_slot;
     k.normalize = normalize;
     k.peer = ctx->peer_args;
+    k.io = ctx->io_args;
     const int grid = std::min(k.n_items, ctx->num_sms);
     if (grid == 0) return BPX_OK;
     sliced::bp_update_sliced_c16<<<grid, sliced::NTHREADS, sliced::SMEM_BYTES, ctx->stream>>>(k);

@@ -45,7 +45,7 @@ struct HostIO {
 // Called by every thread at the end of the kernel (CTA-uniform): the last CTA to finish hands the sweep's residual key
 // to the host, so the step needs no device-to-host copy at all.
 __device__ __forceinline__ void hostio_finish(const HostIO& io) {
-  if (!io.progress) return;
+  if (!io.progress || !io.ticket) return;  // (only the LAST launch of a sweep is given the ticket)
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();

@@ -110,6 +110,7 @@ struct ItemDesc {
   int32_t branch;      // 0: P (out3, out2), 1: Q (out1, out0)
   int32_t pad[3];
   int32_t peer[4];     // rank owning the head of out-edge i if it lives elsewhere (cut edge), else -1
+  int64_t need;        // streamed host I/O: prefix of the upload that holds every message this item reads
 };
 
 struct Args {
@@ -123,6 +124,7 @@ struct Args {
   unsigned long long* resmax;  // this sweep's residual key (atomicMax)
   int normalize;
   PeerArgs peer;               // multi-GPU: gate / direct peer stores / post (nranks <= 1: unused)
+  HostIO io;                   // streamed host I/O (bpx_sweep_host), all NULL otherwise
 };
 
 // message fragments for 16-wide legs
@@ -362,6 +364,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_sliced_c16(Args k) {
   for (int item = blockIdx.x; item < k.n_items; item += G, ++it) {
     const ItemDesc* d = k.items + item;
     const int br = d->branch;
+    if (k.io.progress) {  // streamed upload: the item's messages (fragments, old values) have arrived -- ONE warp polls
+      if (warp == 0) hostio_wait(k.io, d->need);
+      onchip::bar_sync(BAR_COMPUTE, NCT);
+    }
     const int lx = br == 0 ? 0 : 2, ly = br == 0 ? 1 : 3;  // pair absorbed in phase 1
     const int lu = br == 0 ? 2 : 0, lv = br == 0 ? 3 : 1;  // pair closed in phase 2
     {
@@ -438,12 +444,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_sliced_c16(Args k) {
       const int64_t off = d->out_off[leg];
       double* peer_m = (k.peer.nranks > 1 && d->peer[leg] >= 0) ? k.peer.peer_out[d->peer[leg]] + off : nullptr;
       warp_epilogue<double>(raw + warp * MSG, k.msg_in + off, k.msg_out + off, MSG, k.normalize,
-                            k.residual ? k.residual + d->out_edge[leg] : nullptr, lane, k.resmax, peer_m);
+                            k.residual ? k.residual + d->out_edge[leg] : nullptr, lane, k.resmax, peer_m,
+                            k.io.host_out ? k.io.host_out + off : nullptr);
     }
     onchip::bar_sync(BAR_COMPUTE, NCT);  // raw / red are re-used by the next item
   }
   }
   peer_post_when_last(k.peer, false);  // peer stores were released where they were issued (warp_epilogue)
+  hostio_finish(k.io);
 }
 
 }  // namespace sliced

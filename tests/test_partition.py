@@ -277,3 +277,77 @@ def test_two_rank_sweep_host_moves_owned_messages_only():
                 assert np.abs(m - want[e]).max() / np.abs(want[e]).max() < 1e-10, (rank, mode, e)
         seen |= set(out["pinned"][0])
     assert seen == set(range(p.ga.ne))  # the ranks' owned slices tile the iterate
+
+
+# ---------------------------------------------------------------------------------------------------
+def _worker_gpu_multi_launch(rank, world, port, nsweeps, q):
+    """chi = 16 lattice: degree 4 (sliced kernel), degree 3 (tuned 16-wide kernel) and degree 2 (16-wide slice kernel) are
+    three launches per sweep; the exchange is fused into them (first launch gates, last launch posts)."""
+    pkg, o = _setup(rank, world, port, "gloo")
+    from itnn_b200 import partition, problems
+
+    torch.cuda.set_device(rank)
+    g, p = _problem(pkg, dims=(4, 6), chi=16)
+    owner = partition.strip_owner(p.ga.vertices, world, axis=1)
+    pl = partition.plan(p.ga.src, p.ga.dst, owner, rank)
+    ctx = pkg.BPXContext(rank)
+    problems.upload(ctx, p)
+    partition.connect(ctx, owner, rank, world)
+    hist = []
+    for _ in range(nsweeps):
+        res, done = ctx.sweep(1, 0.0)
+        hist.append(res)
+    got = ctx.get_messages()
+    launches = ctx.counters()["launches"]
+    # and the streamed host step over the same three launches (pinned buffers)
+    flat = ctx.pack_messages(p.messages)
+    ta, tb = torch.empty(flat.size, dtype=torch.float64).pin_memory(), torch.empty(flat.size, dtype=torch.float64).pin_memory()
+    a, b = ta.numpy(), tb.numpy()
+    a[:] = flat
+    ctx.set_messages(flat)
+    hist_host = []
+    for _ in range(nsweeps):
+        hist_host.append(ctx.sweep_host(a, b))
+        a, b = b, a
+    host_msgs = ctx.unpack_messages(a)
+    need = set(pl.owned_edges) | {e for es in pl.recv.values() for e in es}
+    q.put((rank, {e: got[e] for e in need}, hist, {e: host_msgs[e] for e in pl.owned_edges}, hist_host, ctx.buckets(), launches))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_rank_multi_launch_sweep_fuses_the_exchange():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, nsweeps = 2, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_gpu_multi_launch, args=(r, world, port, nsweeps, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+
+    pkg, o = entry.import_package(), entry.import_oracle()
+    g, p = _problem(pkg, dims=(4, 6), chi=16)
+    op = o.make_problem(p.ga, p.tensors, "norm")
+    want = list(p.messages)
+    hist = []
+    for _ in range(nsweeps):
+        prev, want = want, o.sweep_jacobi(op, want)
+        hist.append(o.iterate_diff(want, prev))
+    for rank, msgs, h, host_msgs, h_host, buckets, launches in results:
+        assert sorted(b["kernel"] for b in buckets if b["edges"]) == [2, 2, 3], buckets  # on-chip x2 + sliced, no generic launch
+        assert np.allclose(h, hist, rtol=0, atol=1e-12)
+        assert np.allclose(h_host, hist, rtol=0, atol=1e-12)
+        for e, m in msgs.items():
+            assert np.abs(m - want[e]).max() / np.abs(want[e]).max() < 1e-10
+        for e, m in host_msgs.items():
+            assert np.abs(m - want[e]).max() / np.abs(want[e]).max() < 1e-10
