@@ -658,6 +658,7 @@ static int enqueue_streamed_step(bpx_ctx* ctx, const void* packed_in, void* out_
   for (size_t c = 0; c < chunks.size(); ++c) {
     const size_t o = (size_t)chunks[c].b * ctx->esize, len = (size_t)(chunks[c].e - chunks[c].b) * ctx->esize;
     BPX_CUDA(ctx, cudaMemcpyAsync((char*)dst_set + o, (const char*)packed_in + o, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (getenv("BPX_IO_TEST_STALL")) continue;  // (tests: the upload never reports progress -> the kernel gives up)
     if (wv) {  // low word of the (zeroed) 64-bit progress counter
       if (wv(ctx->copy_stream, (unsigned long long)(uintptr_t)ctx->d_io_progress, (unsigned int)chunks[c].cum, 0) != 0) {
         set_error(ctx, "bpx_sweep_host: cuStreamWriteValue32 failed");
@@ -681,7 +682,11 @@ extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_
   const bool single = ctx->nranks == 1;
   int rc;
   double res = INFINITY;
-  void* out_alias = (n > 0 && sweep_streams_host_io(ctx) && mapped_alias(packed_in)) ? mapped_alias(packed_out) : nullptr;
+  void* out_alias =
+      (n > 0 && !ctx->io_stream_disabled && packed_in != packed_out && sweep_streams_host_io(ctx) && mapped_alias(packed_in))
+          ? mapped_alias(packed_out)
+          : nullptr;
+  const int cur0 = ctx->cur;
   if (out_alias) {
     // ---- streamed: the kernel starts at once; the upload arrives in chunks behind a progress word the items wait
     // for, and the epilogues store the new messages straight into the caller's buffer.  On a single rank the whole
@@ -753,13 +758,22 @@ extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_
       if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) return rc;  // synchronises the stream
     }
     if (ctx->h_io_progress[33] != 0) {
+      // The kernel gave up waiting for the upload: something serialises kernel and copies (a profiler replaying
+      // kernels, a runtime that does not overlap the graph's branches).  The upload itself has completed by now; the
+      // results of this attempt are discarded and the step is repeated staged -- as every later step of this context.
       ctx->h_io_progress[33] = 0;
-      cudaMemset(ctx->d_io_progress, 0, 4 * sizeof(long long));  // the self-resetting words may be stale now
-      ctx->io_graph_disabled = true;  // e.g. a runtime that serialises the graph's branches: use plain streams from now on
-      set_error(ctx, "bpx_sweep_host: timed out waiting for the streamed upload");
-      return BPX_ERR_CUDA;
+      BPX_CUDA(ctx, cudaMemset(ctx->d_io_progress, 0, 4 * sizeof(long long)));  // the self-resetting words are stale
+      ctx->io_stream_disabled = true;
+      if (single) ctx->ring_dirty = true;
+      else {
+        set_error(ctx, "bpx_sweep_host: timed out waiting for the streamed upload on a partitioned context");
+        return BPX_ERR_CUDA;  // (the peers have seen this sweep's pushes: it cannot be repeated locally)
+      }
+      ctx->cur = cur0;
+      out_alias = nullptr;
     }
-  } else {
+  }
+  if (!out_alias) {
     // ---- staged: upload the owned messages, sweep, download the owned messages ----
     if (single) ctx->cur = 0;
     if ((rc = halo_gate(ctx))) return rc;

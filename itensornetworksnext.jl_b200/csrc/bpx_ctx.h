@@ -139,6 +139,7 @@ struct bpx_ctx {
   int64_t owned_elems = 0;
   uint64_t work_epoch = 0;             // bumped whenever launch lists / buffers are rebuilt (invalidates io_graphs)
   bool io_graph_disabled = false;
+  bool io_stream_disabled = false;     // a streamed step timed out once: this context stages its host steps from now on
   unsigned long long* slot_override = nullptr;  // residual slot of the step being enqueued (streamed steps)
   bool ring_dirty = false;             // residual ring slots were re-used without a clear (streamed steps)
 

@@ -72,12 +72,13 @@ __device__ __forceinline__ void hostio_finish(const HostIO& io) {
 __device__ __forceinline__ void hostio_wait(const HostIO& io, long long need) {
   if (!io.progress) return;
   if ((threadIdx.x & 31) == 0) {
-    const volatile long long* p = io.progress;
+    const volatile long long* p = io.progress;  // p[0] progress, p[3] abort (same L2 line)
     const long long t0 = clock64();
     unsigned ns = 200;
-    while (*p < need) {
-      if (clock64() - t0 > 8000000000ll) {  // ~4 s: raise the error flag instead of hanging the GPU
-        if (io.error_flag) *reinterpret_cast<volatile int*>(io.error_flag) = 2;  // (mapped host memory: plain store)
+    while (*p < need && p[3] == 0) {
+      if (clock64() - t0 > 8000000000ll) {  // ~4 s: give up once for the whole grid instead of hanging the GPU; the host
+        io.progress[3] = 1;                 // then repeats the step with a staged upload (e.g. under a profiler that
+        if (io.error_flag) *reinterpret_cast<volatile int*>(io.error_flag) = 2;  // serialises kernel and copies)
         break;
       }
       __nanosleep(ns);

@@ -451,6 +451,31 @@ def test_sweep_host_streams_through_registered_numpy_buffers(oracle):
         assert rel_err(ctx.get_messages(), want) < MSG_RTOL
 
 
+def test_streamed_step_falls_back_to_the_staged_path_when_the_upload_stalls(oracle, monkeypatch):
+    # something serialises kernel and copies (a profiler replaying kernels): the kernel gives up waiting after ~4 s, the
+    # step is repeated staged -- same results -- and the context stops streaming
+    import torch
+
+    p = problems.make_config("cfg2", graph=graphs.named_grid((5, 5)))
+    op = oracle.make_problem(p.ga, p.tensors, "norm")
+    with B.BPXContext(0) as ctx:
+        problems.upload(ctx, p)
+        flat = ctx.pack_messages(p.messages)
+        ta, tb = torch.empty(flat.size, dtype=torch.float64).pin_memory(), torch.empty(flat.size, dtype=torch.float64).pin_memory()
+        a, b = ta.numpy(), tb.numpy()
+        a[:] = flat
+        want = oracle.sweep_jacobi(op, p.messages)
+        monkeypatch.setenv("BPX_IO_TEST_STALL", "1")  # the upload never reports progress
+        res = ctx.sweep_host(a, b)
+        monkeypatch.delenv("BPX_IO_TEST_STALL")
+        assert rel_err(ctx.unpack_messages(b), want) < MSG_RTOL
+        assert abs(res - oracle.iterate_diff(want, p.messages)) < 1e-11
+        prev, want = want, oracle.sweep_jacobi(op, want)
+        res = ctx.sweep_host(b, a)  # staged from now on
+        assert rel_err(ctx.unpack_messages(a), want) < MSG_RTOL
+        assert abs(res - oracle.iterate_diff(want, prev)) < 1e-11
+
+
 @pytest.mark.parametrize("name,dims", [("cfg5", (10, 10)), ("cfg2", (32, 32))])
 def test_full_path_sampled_edges_against_oracle(oracle, name, dims):
     """Size-independent check of the production path (device-generated inputs, specialised kernels): recompute a
