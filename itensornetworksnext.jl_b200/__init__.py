@@ -14,6 +14,7 @@ from .beliefpropagation import (
     vertex_scalar, vertex_scalars,
 )
 from .device import BPXContext, fill_randn
+from .generators import delta, delta_network, diagonaltensor, ising_network, sqrt_ising_bond
 from .graphs import (
     NamedEdge, NamedGraph, forest_cover_edge_sequence, graph_arrays, heavy_hex_127, named_comb_tree,
     named_cycle_graph, named_grid, named_path_graph,
