@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "cfg5s", "cfg2c"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "cfg5s", "cfg2c", "ising"])
     ap.add_argument("--kernel", type=int, default=0, help="force a kernel family (include/bpx.h BPX_KERNEL_*)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -72,6 +72,11 @@ def build_workload(name: str, world: int):
     """-> (SyntheticProblem, owner list or None, description)."""
     from itnn_b200 import graphs, problems
 
+    if name == "ising":  # not a BASELINE config: the HBM-bound single-layer bucket of the path (SURVEY.md §8 f1)
+        if world > 1:
+            raise SystemExit("--workload ising is a single-GPU workload")
+        return (problems.make_config("ising"), None,
+                "1024x1024 periodic square-lattice Ising partition-function network (ising_network recipe, beta=0.3), single layer, chi=2, Float64")
     if name == "cfg5s":  # cfg5's buckets on a lattice the default run can generate quickly
         g = graphs.named_grid((24, 24))
         p = problems.make_config("cfg5", graph=g)
@@ -197,11 +202,47 @@ def cpu_reference_arm(p, seconds: float, max_steps: int = 1000, warmup: int = 1)
     return n_upd / (ms * 1e-3), cores, sample, ms, len(times)
 
 
+def cpu_reference_arm_single(seconds: float, max_steps: int = 1000, dims=(64, 64)):
+    """Single-layer workloads: the numpy oracle's synchronous sweep (one thread, per-edge contractions like the reference)
+    on a `dims` sub-lattice of the workload.  -> (updates/s, cores, sample, ms/step, steps)"""
+    from itnn_b200 import problems
+
+    o = entry.import_oracle()
+    q = problems.synthetic_ising(dims)
+    tensors, msgs = problems.unpacked(q)
+    op = o.make_problem(q.ga, tensors, "single")
+    o.sweep_jacobi(op, msgs)
+    times = []
+    t_end = time.perf_counter() + seconds
+    while len(times) < max_steps and (time.perf_counter() < t_end or len(times) < 2):
+        t0 = time.perf_counter()
+        msgs = o.sweep_jacobi(op, msgs)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    sample = f"{dims[0]}x{dims[1]} periodic sub-lattice of the workload ({q.ga.ne} directed edges per step), numpy oracle, one thread"
+    return q.ga.ne / (ms * 1e-3), 1, sample, ms, len(times)
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     entry.import_package()
     p, _, desc = build_workload(args.workload, 1)
+    if p.mode == "single":
+        budget = max(10.0, min(120.0, 4.0 * args.steps))
+        val, cores, sample, ms, steps = cpu_reference_arm_single(budget, max_steps=args.steps)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "schedule": "synchronous", "note": "reference CPU path restated in numpy (oracle/bp_oracle.py); "
+                       "the Julia reference itself cannot run in this image"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
     if p.tensors is None:  # cfg5: the host cannot stage 63 GiB; same buckets on an 8x8 sub-lattice
         from itnn_b200 import graphs, problems
 
@@ -276,7 +317,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     ctx.set_graph(p.ga.src, p.ga.dst, p.ga.slot, p.ga.nv)
     if args.kernel:
         ctx.set_kernel_policy(args.kernel)
-    ctx.set_dims(p.dtype, "norm", p.phys_dim, p.link_dim)
+    ctx.set_dims(p.dtype, p.mode, p.phys_dim if p.mode == "norm" else None, p.link_dim)
     if world > 1:  # partition first: site tensors are then allocated / generated for the owned vertices only
         from itnn_b200 import partition
 
@@ -368,6 +409,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     flops_per_launch = bytes_per_launch = 0.0
     merged = [b for b in all_buckets if b["leader"] == dom["leader"]]
     for b in merged:
+        if p.mode == "single":  # vector messages; the factor shrinks by chi with every absorbed message
+            flops_per_launch += b["edges"] * problems.single_layer_update_flops(b["degree"], b["chi"]) * cplx
+            bytes_per_launch += b["vertices"] * float(b["chi"]) ** b["degree"] * w + 3.0 * b["edges"] * b["chi"] * w
+            continue
         flops_per_launch += b["edges"] * 2.0 * b["degree"] * b["phys"] * float(b["chi"]) ** (b["degree"] + 1) * cplx
         bytes_per_launch += b["vertices"] * b["phys"] * float(b["chi"]) ** b["degree"] * w + 3.0 * b["edges"] * b["chi"] ** 2 * w
     avg_ms = dom_ms / max(dom_n, 1)
@@ -393,7 +438,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     elif dom["kernel"] == 3 and world == 1:
         roof["traffic"] = SLICED_TRAFFIC_PER_VERTEX * dom["vertices"]
         roof["traffic_source"] = "profiles/r1c_sliced_c16_ncu_summary.csv (per-vertex DRAM bytes x degree-4 vertices of this workload)"
-    roof["kernel"] = {1: "bp_update_generic", 2: "bp_update_onchip", 3: "bp_update_sliced"}.get(dom["kernel"], "?")
+    roof["kernel"] = {1: "bp_update_generic", 2: "bp_update_onchip", 3: "bp_update_sliced", 4: "bp_update_single_vertex"}.get(dom["kernel"], "?")
     roof["bucket"] = {"degree": z, "chi": chi, "phys": d, "updates_per_launch": sum(b["edges"] for b in merged),
                       "degrees_in_launch": sorted(b["degree"] for b in merged)}
     roof["avg_launch_ms"] = avg_ms
@@ -442,11 +487,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pc, note = p, ""
-        if p.tensors is None:  # cfg5: time the CPU on an 8x8 sub-lattice of the same buckets
-            from itnn_b200 import graphs
-            pc, note = problems.make_config("cfg5", graph=graphs.named_grid((8, 8))), "8x8 sub-lattice of the workload; "
-        v, cores, sample, ms, steps = cpu_reference_arm(pc, args.cpu_seconds)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{note}{sample}; {steps} steps of {ms:.1f} ms"}
+        if p.mode == "single":
+            v, cores, sample, ms, steps = cpu_reference_arm_single(args.cpu_seconds)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{sample}; {steps} steps of {ms:.1f} ms"}
+        else:
+            if p.tensors is None:  # cfg5: time the CPU on an 8x8 sub-lattice of the same buckets
+                from itnn_b200 import graphs
+                pc, note = problems.make_config("cfg5", graph=graphs.named_grid((8, 8))), "8x8 sub-lattice of the workload; "
+            v, cores, sample, ms, steps = cpu_reference_arm(pc, args.cpu_seconds)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{note}{sample}; {steps} steps of {ms:.1f} ms"}
 
     # ---- optional: BP to convergence (the north star's end-to-end statement) --------------------------------
     conv = None

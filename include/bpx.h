@@ -62,7 +62,8 @@ enum {
   BPX_KERNEL_AUTO = 0,
   BPX_KERNEL_GENERIC = 1, /* edge-centric, any shape, strided loops            */
   BPX_KERNEL_ONCHIP = 2,  /* vertex-centric, site tensor resident in shared memory, FP64 DMMA chain */
-  BPX_KERNEL_SLICED = 3   /* vertex-centric, site tensor streamed in leg slices, FP64 DMMA chain    */
+  BPX_KERNEL_SLICED = 3,  /* vertex-centric, site tensor streamed in leg slices, FP64 DMMA chain    */
+  BPX_KERNEL_VERTEX = 4   /* SINGLE mode, small uniform link dims: one thread per vertex, factor in registers (HBM bound) */
 };
 
 int bpx_version(void);

@@ -16,7 +16,7 @@ HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "include", "bpx.h"))
 BPX_OK = 0
 BPX_F64, BPX_C64 = 0, 1
 BPX_MODE_NORM, BPX_MODE_SINGLE = 0, 1
-BPX_KERNEL_AUTO, BPX_KERNEL_GENERIC, BPX_KERNEL_ONCHIP, BPX_KERNEL_SLICED = 0, 1, 2, 3
+BPX_KERNEL_AUTO, BPX_KERNEL_GENERIC, BPX_KERNEL_ONCHIP, BPX_KERNEL_SLICED, BPX_KERNEL_VERTEX = 0, 1, 2, 3, 4
 BPX_MAX_DEGREE = 12
 
 _lib = None

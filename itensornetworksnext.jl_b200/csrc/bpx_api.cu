@@ -99,6 +99,8 @@ static void free_problem(bpx_ctx* c) {
   for (auto& b : c->buckets) {
     F(b.d_vertices);
     F(b.d_edges);
+    F(b.d_vx_site);
+    F(b.d_vx_moff);
     for (auto& ev : b.timing) {
       cudaEventDestroy(ev.first);
       cudaEventDestroy(ev.second);
@@ -933,7 +935,7 @@ static int sweep_once(bpx_ctx* ctx, int normalize) {
   for (int bi = 0; bi < (int)ctx->buckets.size(); ++bi) {
     const Bucket& b = ctx->buckets[bi];
     if (b.my_edges.empty()) continue;
-    if (b.kernel == BPX_KERNEL_GENERIC) ++n_generic;
+    if (plain_family(b.kernel)) ++n_generic;
     else if (b.leader == bi) ++n_fast;
     if (b.leader == bi) {
       int64_t edges = 0;
@@ -983,6 +985,8 @@ static int sweep_once(bpx_ctx* ctx, int normalize) {
     }
     if (b.kernel == BPX_KERNEL_GENERIC)  // ONE launch for all generic buckets (the kernel takes any mix of edges)
       rc = launch_generic_update(ctx, in, out, ctx->d_generic_edges, ctx->n_generic_edges, normalize, ctx->cur_slot);
+    else if (b.kernel == BPX_KERNEL_VERTEX)
+      rc = launch_vertex_update(ctx, b, in, out, normalize);
     else
       rc = launch_fast_update(ctx, b, in, out, normalize);
     if (rc) return rc;
@@ -1338,7 +1342,7 @@ extern "C" int bpx_bucket_info(const bpx_ctx* ctx, int bucket, int64_t info[8]) 
 
 extern "C" int bpx_set_kernel_policy(bpx_ctx* ctx, int kernel) {
   if (!ctx) return BPX_ERR_INVALID;
-  REQUIRE(ctx, kernel >= BPX_KERNEL_AUTO && kernel <= BPX_KERNEL_SLICED, "bpx_set_kernel_policy: unknown kernel %d", kernel);
+  REQUIRE(ctx, kernel >= BPX_KERNEL_AUTO && kernel <= BPX_KERNEL_VERTEX, "bpx_set_kernel_policy: unknown kernel %d", kernel);
   ctx->kernel_policy = kernel;
   if (ctx->dims_set) {
     BPX_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -18,6 +18,8 @@ struct Bucket {
   std::vector<int32_t> my_edges;      // out-edges of my_vertices (vertex-major, slot order)
   int32_t* d_vertices = nullptr;
   int32_t* d_edges = nullptr;
+  int64_t* d_vx_site = nullptr;       // VERTEX kernel descriptors (bpx_vertex.cuh): site offsets [n] ...
+  int32_t* d_vx_moff = nullptr;       // ... and message offsets [2 z][n], n = my_vertices.size()
   int kernel = BPX_KERNEL_GENERIC;
   int leader = 0;  // bucket index whose launch covers this bucket (launch groups, bpx_fast.cuh)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // profiling: one event pair per timed launch
@@ -171,6 +173,10 @@ bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel);
 int fast_prepare(bpx_ctx* ctx);
 int fast_refresh_sites(bpx_ctx* ctx);
 int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize);
+int launch_vertex_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize);
+// kernel families that do not implement the fused multi-GPU exchange / streamed host I/O hooks (the sweep runs the
+// exchange as separate small kernels and stages host iterates for them)
+inline bool plain_family(int kernel) { return kernel == BPX_KERNEL_GENERIC || kernel == BPX_KERNEL_VERTEX; }
 // multi-GPU (bpx_halo.cuh)
 int halo_push(bpx_ctx* ctx, void* msg_out);
 int halo_post_residual(bpx_ctx* ctx);

@@ -8,6 +8,7 @@
 #include "bpx_onchip16.cuh"
 #include "bpx_onchip16c.cuh"
 #include "bpx_onchip8c.cuh"
+#include "bpx_vertex.cuh"
 
 namespace bpx {
 
@@ -39,6 +40,9 @@ inline bool uses_c16x(const bpx_ctx* ctx, const Bucket& b) {
 
 inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
   if (kernel == BPX_KERNEL_GENERIC) return true;
+  if (kernel == BPX_KERNEL_VERTEX)  // single-layer networks, uniform link dim 2..4, factor of <= 64 doubles (bpx_vertex.cuh)
+    return ctx->mode == BPX_MODE_SINGLE && b.chi >= 2 && vertexk::shape_supported(ctx->dtype == BPX_C64, b.z, b.chi) &&
+           ctx->msg_off[ctx->ne] < (1ll << 31);
   if (ctx->mode != BPX_MODE_NORM) return false;
   if (kernel == BPX_KERNEL_ONCHIP) {
     // ComplexF64: chi = 16, degree 1..3, any physical dimension (bpx_onchip16c.cuh)
@@ -65,6 +69,7 @@ inline bool fast_kernel_supported(bpx_ctx* ctx, const Bucket& b, int kernel) {
 inline int fast_kernel_for(bpx_ctx* ctx, const Bucket& b) {
   if (fast_kernel_supported(ctx, b, BPX_KERNEL_ONCHIP)) return BPX_KERNEL_ONCHIP;
   if (fast_kernel_supported(ctx, b, BPX_KERNEL_SLICED)) return BPX_KERNEL_SLICED;
+  if (fast_kernel_supported(ctx, b, BPX_KERNEL_VERTEX)) return BPX_KERNEL_VERTEX;
   return BPX_KERNEL_GENERIC;
 }
 
@@ -90,6 +95,35 @@ inline int fast_prepare(bpx_ctx* ctx) {
       if (generic_leader < 0) generic_leader = i;
       ctx->buckets[i].leader = generic_leader;  // all generic buckets share one launch
     }
+  }
+  // ---- VERTEX buckets (single-layer, thread per vertex): structure-of-arrays descriptors, one launch per bucket ----
+  for (Bucket& b : ctx->buckets) {
+    if (b.d_vx_site) cudaFree(b.d_vx_site);
+    if (b.d_vx_moff) cudaFree(b.d_vx_moff);
+    b.d_vx_site = nullptr;
+    b.d_vx_moff = nullptr;
+    if (b.kernel != BPX_KERNEL_VERTEX || b.my_vertices.empty()) continue;
+    const size_t n = b.my_vertices.size();
+    std::vector<int64_t> site(n);
+    std::vector<int32_t> moff(2 * (size_t)b.z * n);
+    for (size_t i = 0; i < n; ++i) {
+      const int32_t v = b.my_vertices[i];
+      site[i] = ctx->dev_site_off[v];
+      for (int k = 0; k < b.z; ++k) {
+        const int32_t e = ctx->out_edge[v][k];
+        moff[(size_t)k * n + i] = (int32_t)ctx->msg_off[ctx->rev[e]];      // message arriving on leg k
+        moff[(size_t)(b.z + k) * n + i] = (int32_t)ctx->msg_off[e];        // message leaving on leg k
+      }
+    }
+    cudaError_t e = cudaMalloc((void**)&b.d_vx_site, n * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b.d_vx_moff, moff.size() * sizeof(int32_t));
+    if (e != cudaSuccess) {
+      set_error(ctx, "cudaMalloc(vertex-kernel descriptors) failed: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return BPX_ERR_ALLOC;
+    }
+    BPX_CUDA(ctx, cudaMemcpy(b.d_vx_site, site.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    BPX_CUDA(ctx, cudaMemcpy(b.d_vx_moff, moff.data(), moff.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
   if (ctx->d_sliced_items) {
     cudaFree(ctx->d_sliced_items);
@@ -522,6 +556,26 @@ inline int fast_refresh_sites(bpx_ctx* ctx) {
     BPX_CUDA(ctx, cudaGetLastError());
   }
   ctx->sites_dirty = false;
+  return BPX_OK;
+}
+
+// SINGLE-mode buckets on the thread-per-vertex register kernel (bpx_vertex.cuh)
+inline int launch_vertex_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void* msg_out, int normalize) {
+  vertexk::Args k;
+  k.site = b.d_vx_site;
+  k.moff = b.d_vx_moff;
+  k.sites = ctx->d_sites;
+  k.msg_in = msg_in;
+  k.msg_out = msg_out;
+  k.resmax = ctx->cur_slot;
+  k.n = (int64_t)b.my_vertices.size();
+  k.normalize = normalize;
+  if (k.n == 0) return BPX_OK;
+  const int grid = (int)std::min<int64_t>((k.n + vertexk::NT - 1) / vertexk::NT, (int64_t)ctx->num_sms * 32);
+  const cudaError_t e = ctx->dtype == BPX_C64 ? vertexk::launch<c64>(k, b.z, b.chi, grid, ctx->stream)
+                                              : vertexk::launch<double>(k, b.z, b.chi, grid, ctx->stream);
+  ctx->n_launches++;
+  BPX_CUDA(ctx, e);
   return BPX_OK;
 }
 

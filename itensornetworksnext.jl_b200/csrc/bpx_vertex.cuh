@@ -1,0 +1,230 @@
+// Vertex-centric register kernel for SINGLE-layer networks with small uniform link dimensions: the HBM-bound bucket
+// family of the path (Ising / spin-ice / delta networks of src/ITensorNetworkGenerators, chi = 2).
+//
+// One update on a single-layer network (beliefpropagation.jl:242-257 with plain ITensorNetwork factors):
+//     m~_{u->v_j}[b] = sum_{l : l_j = b} T_u[l_0..l_{z-1}] prod_{k != j} m_{w_k->u}[l_k]
+// followed by the sum-normalisation (:248-253) and the per-edge term of iterate_diff (:261-267).
+//
+// Arithmetic intensity is O(z) flop per byte of T_u (a chi = 2, degree-4 factor is 128 B and costs ~160 flops for all
+// four out-messages), far below the FP64 ridge, so the kernel is organised around memory traffic only:
+//   * ONE THREAD PER VERTEX.  The factor is read once (16-byte loads, one full 128 B line per thread at chi = 2,
+//     z = 4) and ALL z leave-one-out contractions are formed from it in registers (prefix products over the legs,
+//     fully unrolled: every index of the loops below is a compile-time constant), so T_u is read once per sweep
+//     instead of z times and no intermediate touches shared or global memory.
+//   * Descriptors are a structure of arrays indexed by the position in the bucket (site offset, z in-message offsets,
+//     z out-message offsets: 8 + 8 z bytes per vertex), read fully coalesced -- the generic kernel's 176-byte VDesc per
+//     update would cost more traffic than the factor itself.
+//   * The residual maximum is reduced per thread -> warp (shuffles) -> CTA (shared memory) and leaves the CTA as ONE
+//     atomicMax on the sweep's order-preserving key (bpx_common.cuh); a per-message atomic on one address would
+//     serialise millions of updates.
+// Algorithmic bytes per vertex: chi^z w (factor) + 3 z chi w (message in, old, out) -- the roofline `bench.py
+// --workload ising` reports against (plus the 8 + 8 z descriptor bytes, which are real traffic but not algorithmic).
+#pragma once
+#include "bpx_common.cuh"
+
+namespace bpx {
+namespace vertexk {
+
+constexpr int NT = 128;  // threads per CTA
+
+struct Args {
+  const int64_t* site;     // [n]      element offset of T_v in the device site buffer
+  const int32_t* moff;     // [2 z][n] element offsets of the z incoming messages, then of the z outgoing messages
+  const void* sites;
+  const void* msg_in;
+  void* msg_out;
+  unsigned long long* resmax;  // the sweep's residual key (may be NULL)
+  int64_t n;               // vertices in this launch
+  int normalize;
+};
+
+__host__ __device__ constexpr int ipow(int b, int e) { return e <= 0 ? 1 : b * ipow(b, e - 1); }
+
+// shapes that stay in registers: chi^z values of at most 64 doubles (complex counts twice)
+template <typename T, int Z, int N>
+__host__ __device__ constexpr bool supported() {
+  return Z >= 1 && Z <= 6 && N >= 2 && N <= 4 && ipow(N, Z) * (int)(sizeof(T) / 8) <= 64;
+}
+inline bool shape_supported(bool is_complex, int z, int n) {
+  if (z < 1 || z > 6 || n < 2 || n > 4) return false;
+  int64_t e = 1;
+  for (int i = 0; i < z; ++i) e *= n;
+  return e * (is_complex ? 2 : 1) <= 64;
+}
+
+// COUNT elements from global memory into registers; 16-byte loads when the run is 16-byte aligned
+template <typename T, int COUNT>
+__device__ __forceinline__ void load_run(const T* __restrict__ p, T (&dst)[COUNT]) {
+  if constexpr (sizeof(T) == 16) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int i = 0; i < COUNT; ++i) {
+      const double2 v = __ldg(q + i);
+      dst[i] = make_c64(v.x, v.y);
+    }
+  } else {
+    if constexpr (COUNT % 2 == 0) {
+      if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+        for (int i = 0; i < COUNT / 2; ++i) {
+          const double2 v = __ldg(q + i);
+          dst[2 * i] = v.x;
+          dst[2 * i + 1] = v.y;
+        }
+        return;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < COUNT; ++i) dst[i] = __ldg(p + i);
+  }
+}
+
+template <typename T, int COUNT>
+__device__ __forceinline__ void store_run(T* __restrict__ p, const T (&src)[COUNT]) {
+  if constexpr (sizeof(T) == 16) {
+    double2* q = reinterpret_cast<double2*>(p);
+#pragma unroll
+    for (int i = 0; i < COUNT; ++i) q[i] = make_double2(src[i].re, src[i].im);
+  } else {
+    if constexpr (COUNT % 2 == 0) {
+      if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        double2* q = reinterpret_cast<double2*>(p);
+#pragma unroll
+        for (int i = 0; i < COUNT / 2; ++i) q[i] = make_double2(src[2 * i], src[2 * i + 1]);
+        return;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < COUNT; ++i) p[i] = src[i];
+  }
+}
+
+template <typename T, int Z, int N>
+__global__ void __launch_bounds__(NT) bp_update_single_vertex(Args a) {
+  using E = Elem<T>;
+  constexpr int NE = ipow(N, Z);
+  const T* __restrict__ sites = reinterpret_cast<const T*>(a.sites);
+  const T* __restrict__ msg_in = reinterpret_cast<const T*>(a.msg_in);
+  T* __restrict__ msg_out = reinterpret_cast<T*>(a.msg_out);
+  unsigned long long key = 0ull;  // 0 = nothing recorded (residual_key never returns 0)
+
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * NT) {
+    T t[NE];
+    load_run<T, NE>(sites + a.site[i], t);
+    T m[Z][N];
+#pragma unroll
+    for (int k = 0; k < Z; ++k) load_run<T, N>(msg_in + a.moff[(int64_t)k * a.n + i], m[k]);
+
+    // all z leave-one-out contractions in one pass over the factor:
+    //   pre_j = T[l] prod_{k < j} m_k[l_k],  suf_j = prod_{k > j} m_k[l_k],  raw_j[l_j] += pre_j suf_j
+    T raw[Z][N];
+#pragma unroll
+    for (int j = 0; j < Z; ++j)
+#pragma unroll
+      for (int b = 0; b < N; ++b) raw[j][b] = E::zero();
+#pragma unroll
+    for (int x = 0; x < NE; ++x) {
+      int dig[Z];  // l_k of element x: constants once the loop is unrolled
+      {
+        int r = x;
+#pragma unroll
+        for (int k = 0; k < Z; ++k) {
+          dig[k] = r % N;
+          r /= N;
+        }
+      }
+      T pre[Z];
+      pre[0] = t[x];
+#pragma unroll
+      for (int k = 1; k < Z; ++k) pre[k] = E::mul(pre[k - 1], m[k - 1][dig[k - 1]]);
+      // j = Z - 1: empty suffix
+      raw[Z - 1][dig[Z - 1]] = E::add(raw[Z - 1][dig[Z - 1]], pre[Z - 1]);
+      if constexpr (Z >= 2) {
+        T suf = m[Z - 1][dig[Z - 1]];
+#pragma unroll
+        for (int j = Z - 2; j >= 0; --j) {
+          raw[j][dig[j]] = E::fma(pre[j], suf, raw[j][dig[j]]);
+          if (j > 0) suf = E::mul(suf, m[j][dig[j]]);
+        }
+      }
+    }
+
+    // epilogue per out-message: sum-normalise, residual term against the previous message on that edge, store
+#pragma unroll
+    for (int j = 0; j < Z; ++j) {
+      const int64_t off = a.moff[(int64_t)(Z + j) * a.n + i];
+      T old_m[N];
+      load_run<T, N>(msg_in + off, old_m);
+      T s = E::zero();
+#pragma unroll
+      for (int b = 0; b < N; ++b) s = E::add(s, raw[j][b]);
+      const bool scale = a.normalize && !E::is_zero(s);
+      T dot = E::zero();
+      double n_old = 0.0, n_new = 0.0;
+      T v[N];
+#pragma unroll
+      for (int b = 0; b < N; ++b) {
+        v[b] = scale ? E::div(raw[j][b], s) : raw[j][b];
+        dot = E::fma(E::conj(old_m[b]), v[b], dot);
+        n_old += E::abs2(old_m[b]);
+        n_new += E::abs2(v[b]);
+      }
+      store_run<T, N>(msg_out + off, v);
+      const unsigned long long kj = residual_key(1.0 - E::abs2(dot) / (n_old * n_new));
+      key = kj > key ? kj : key;
+    }
+  }
+
+  // thread -> warp -> CTA -> one atomicMax
+  if (a.resmax == nullptr) return;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, s);
+    key = o > key ? o : key;
+  }
+  __shared__ unsigned long long wkey[NT / 32];
+  if ((threadIdx.x & 31) == 0) wkey[threadIdx.x >> 5] = key;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) key = wkey[w] > key ? wkey[w] : key;
+    if (key != 0ull) atomicMax(a.resmax, key);
+  }
+}
+
+template <typename T, int Z, int N>
+inline cudaError_t launch_zn(const Args& a, int grid, cudaStream_t stream) {
+  if constexpr (supported<T, Z, N>()) {
+    bp_update_single_vertex<T, Z, N><<<grid, NT, 0, stream>>>(a);
+    return cudaGetLastError();
+  } else {
+    return cudaErrorInvalidValue;
+  }
+}
+
+template <typename T, int N>
+inline cudaError_t launch_n(const Args& a, int z, int grid, cudaStream_t stream) {
+  switch (z) {
+    case 1: return launch_zn<T, 1, N>(a, grid, stream);
+    case 2: return launch_zn<T, 2, N>(a, grid, stream);
+    case 3: return launch_zn<T, 3, N>(a, grid, stream);
+    case 4: return launch_zn<T, 4, N>(a, grid, stream);
+    case 5: return launch_zn<T, 5, N>(a, grid, stream);
+    case 6: return launch_zn<T, 6, N>(a, grid, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <typename T>
+inline cudaError_t launch(const Args& a, int z, int n, int grid, cudaStream_t stream) {
+  switch (n) {
+    case 2: return launch_n<T, 2>(a, z, grid, stream);
+    case 3: return launch_n<T, 3>(a, z, grid, stream);
+    case 4: return launch_n<T, 4>(a, z, grid, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace vertexk
+}  // namespace bpx

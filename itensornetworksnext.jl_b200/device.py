@@ -60,6 +60,7 @@ class BPXContext:
         slot = np.ascontiguousarray(slot, dtype=np.int32)
         self._check(self.lib.bpx_set_graph(self.h, int(nv), len(src), _ptr(src), _ptr(dst), _ptr(slot)))
         self.nv, self.ne = int(nv), len(src)
+        self._src = src
 
     def set_dims(self, dtype, mode: str, phys_dim: Optional[Sequence[int]], link_dim: Sequence[int]):
         self.dtype = np.dtype(dtype)
@@ -71,8 +72,17 @@ class BPXContext:
         pd = None if phys_dim is None else np.ascontiguousarray(phys_dim, dtype=np.int32)
         ld = np.ascontiguousarray(link_dim, dtype=np.int32)
         self._check(self.lib.bpx_set_dims(self.h, code, m, _ptr(pd), _ptr(ld)))
-        self.site_off = np.array([self.lib.bpx_site_offset(self.h, v) for v in range(self.nv + 1)], dtype=np.int64)
-        self.msg_off = np.array([self.lib.bpx_message_offset(self.h, e) for e in range(self.ne + 1)], dtype=np.int64)
+        # packed host layouts (the library's bpx_site_offset / bpx_message_offset, computed here in bulk: one ctypes call
+        # per vertex and edge takes seconds on lattices of millions of vertices); the totals are checked against the library
+        n_site = np.ones(self.nv, dtype=np.int64) if pd is None or mode == "single" else pd.astype(np.int64)
+        np.multiply.at(n_site, self._src, ld.astype(np.int64))
+        self.site_off = np.concatenate([[0], np.cumsum(n_site)]).astype(np.int64)
+        n_msg = ld.astype(np.int64) ** 2 if mode == "norm" else ld.astype(np.int64)
+        self.msg_off = np.concatenate([[0], np.cumsum(n_msg)]).astype(np.int64)
+        if (self.site_off[-1] != self.lib.bpx_site_offset(self.h, self.nv) or self.msg_off[-1] != self.lib.bpx_message_offset(self.h, self.ne)
+                or (self.nv and self.site_off[self.nv // 2] != self.lib.bpx_site_offset(self.h, self.nv // 2))
+                or (self.ne and self.msg_off[self.ne // 2] != self.lib.bpx_message_offset(self.h, self.ne // 2))):
+            raise RuntimeError("packed layout mismatch between the host mirror and libbpx")
         self.link_dim = ld
 
     # -- data --------------------------------------------------------------------------------------
@@ -86,6 +96,10 @@ class BPXContext:
         return out
 
     def pack_messages(self, msgs: Sequence[np.ndarray]) -> np.ndarray:
+        if isinstance(msgs, np.ndarray) and msgs.ndim == 1:  # already packed
+            if msgs.size != int(self.msg_off[-1]):
+                raise ValueError(f"packed messages have {msgs.size} elements, expected {int(self.msg_off[-1])}")
+            return np.ascontiguousarray(msgs, dtype=self.dtype)
         out = np.empty(int(self.msg_off[-1]), dtype=self.dtype)
         for e, m in enumerate(msgs):
             n = int(self.msg_off[e + 1] - self.msg_off[e])

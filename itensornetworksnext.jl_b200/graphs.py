@@ -314,3 +314,39 @@ def graph_arrays(g: NamedGraph) -> GraphArrays:
         row_ptr.append(len(src))
     rev = [edge_index[(d, s)] for s, d in zip(src, dst)]
     return GraphArrays(verts, vindex, src, dst, rev, slot, row_ptr, edge_index)
+
+
+def grid_graph_arrays(dims: Sequence[int], periodic: bool = False) -> GraphArrays:
+    """Hypercubic lattice straight to the integer arrays of the C ABI, vectorised (numpy): for lattices of millions of
+    vertices, where building a `NamedGraph` of Python tuples first would take minutes.
+
+    Vertex ids run with the first coordinate fastest (like `named_grid`); the link legs of a vertex are ordered
+    (-axis0, +axis0, -axis1, +axis1, ...), existing neighbours only -- NOT the insertion order `named_grid` produces, so
+    site tensors must be authored for this leg order.  Periodic wrap links only along axes longer than 2.  `vertices`
+    is a `range`, and the name-based lookups (`vindex`, `edge_index`, `edge_id`) are not populated."""
+    import numpy as np
+
+    dims = tuple(int(d) for d in dims)
+    nd = len(dims)
+    nv = int(np.prod(dims))
+    idx = np.arange(nv, dtype=np.int64)
+    coords = np.unravel_index(idx, dims, order="F")
+    nbr = np.full((nv, 2 * nd), -1, dtype=np.int64)
+    stride = 1
+    for ax, n in enumerate(dims):
+        c = coords[ax]
+        wrap = periodic and n > 2
+        nbr[:, 2 * ax] = np.where(c > 0, idx - stride, idx + (n - 1) * stride if wrap else -1)
+        nbr[:, 2 * ax + 1] = np.where(c < n - 1, idx + stride, idx - (n - 1) * stride if wrap else -1)
+        stride *= n
+    valid = nbr >= 0
+    deg = valid.sum(axis=1)
+    row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    pos = np.cumsum(valid, axis=1) - 1            # position of direction k among the existing legs of a vertex
+    src = np.repeat(idx, deg)
+    dst = nbr[valid]
+    slot = pos[valid]
+    direction = np.broadcast_to(np.arange(2 * nd), nbr.shape)[valid]
+    rev = row_ptr[dst] + pos[dst, direction ^ 1]  # the same link seen from the other end: opposite direction there
+    return GraphArrays(range(nv), {}, src, dst, rev, slot.astype(np.int64), row_ptr, {})
+
