@@ -20,6 +20,7 @@ struct Bucket {
   int32_t* d_edges = nullptr;
   int64_t* d_vx_site = nullptr;       // VERTEX kernel descriptors (bpx_vertex.cuh): site offsets [n] ...
   int32_t* d_vx_moff = nullptr;       // ... and message offsets [2 z][n], n = my_vertices.size()
+  int vx_out_contig = 0;              // every vertex's out-messages are adjacent in the packed layout (slot order)
   int kernel = BPX_KERNEL_GENERIC;
   int leader = 0;  // bucket index whose launch covers this bucket (launch groups, bpx_fast.cuh)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // profiling: one event pair per timed launch

@@ -106,6 +106,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
     const size_t n = b.my_vertices.size();
     std::vector<int64_t> site(n);
     std::vector<int32_t> moff(2 * (size_t)b.z * n);
+    b.vx_out_contig = 1;
     for (size_t i = 0; i < n; ++i) {
       const int32_t v = b.my_vertices[i];
       site[i] = ctx->dev_site_off[v];
@@ -113,6 +114,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
         const int32_t e = ctx->out_edge[v][k];
         moff[(size_t)k * n + i] = (int32_t)ctx->msg_off[ctx->rev[e]];      // message arriving on leg k
         moff[(size_t)(b.z + k) * n + i] = (int32_t)ctx->msg_off[e];        // message leaving on leg k
+        if (ctx->msg_off[e] != ctx->msg_off[ctx->out_edge[v][0]] + (int64_t)k * b.chi) b.vx_out_contig = 0;
       }
     }
     cudaError_t e = cudaMalloc((void**)&b.d_vx_site, n * sizeof(int64_t));
@@ -570,6 +572,7 @@ inline int launch_vertex_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, voi
   k.resmax = ctx->cur_slot;
   k.n = (int64_t)b.my_vertices.size();
   k.normalize = normalize;
+  k.out_contig = b.vx_out_contig;
   if (k.n == 0) return BPX_OK;
   const int grid = (int)std::min<int64_t>((k.n + vertexk::NT - 1) / vertexk::NT, (int64_t)ctx->num_sms * 32);
   const cudaError_t e = ctx->dtype == BPX_C64 ? vertexk::launch<c64>(k, b.z, b.chi, grid, ctx->stream)

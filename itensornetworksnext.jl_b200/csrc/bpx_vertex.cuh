@@ -36,6 +36,7 @@ struct Args {
   unsigned long long* resmax;  // the sweep's residual key (may be NULL)
   int64_t n;               // vertices in this launch
   int normalize;
+  int out_contig;          // the z out-messages of every vertex are adjacent in the packed message layout, slot order
 };
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e <= 0 ? 1 : b * ipow(b, e - 1); }
@@ -100,79 +101,221 @@ __device__ __forceinline__ void store_run(T* __restrict__ p, const T (&src)[COUN
   }
 }
 
+// geometry of the staged (warp-cooperative) path: a warp's 32 factors (and its 32 runs of z out-messages) are contiguous
+// in HBM when the bucket's vertices are consecutive, so the warp moves them with fully coalesced 16-byte accesses and
+// transposes through shared memory (row = one vertex; odd row stride in 16-byte units: conflict-free LDS/STS.128)
+template <typename T, int Z, int N>
+struct Shape {
+  static constexpr int NE = ipow(N, Z);
+  static constexpr int RB = NE * (int)sizeof(T);       // bytes of one factor
+  static constexpr int OB = Z * N * (int)sizeof(T);    // bytes of the z out-messages of one vertex
+  static constexpr bool STAGED = (RB % 16 == 0) && (OB % 16 == 0);
+  static constexpr int RC = RB / 16, RS = RC + ((RC & 1) ? 2 : 1);
+  static constexpr int OC = OB / 16, OS = OC + ((OC & 1) ? 2 : 1);
+  static constexpr int WARP_UNITS = STAGED ? 32 * (RS + OS) : 0;  // 16-byte units of shared memory per warp
+  static constexpr int SMEM_BYTES = (NT / 32) * WARP_UNITS * 16;
+};
+
+// all z leave-one-out contractions in one pass over the factor:
+//   pre_j = T[l] prod_{k < j} m_k[l_k],  suf_j = prod_{k > j} m_k[l_k],  raw_j[l_j] += pre_j suf_j
+template <typename T, int Z, int N>
+__device__ __forceinline__ void leave_one_out(const T (&t)[Shape<T, Z, N>::NE], const T (&m)[Z][N], T (&raw)[Z][N]) {
+  using E = Elem<T>;
+  constexpr int NE = Shape<T, Z, N>::NE;
+#pragma unroll
+  for (int j = 0; j < Z; ++j)
+#pragma unroll
+    for (int b = 0; b < N; ++b) raw[j][b] = E::zero();
+#pragma unroll
+  for (int x = 0; x < NE; ++x) {
+    int dig[Z];  // l_k of element x: constants once the loop is unrolled
+    {
+      int r = x;
+#pragma unroll
+      for (int k = 0; k < Z; ++k) {
+        dig[k] = r % N;
+        r /= N;
+      }
+    }
+    T pre[Z];
+    pre[0] = t[x];
+#pragma unroll
+    for (int k = 1; k < Z; ++k) pre[k] = E::mul(pre[k - 1], m[k - 1][dig[k - 1]]);
+    // j = Z - 1: empty suffix
+    raw[Z - 1][dig[Z - 1]] = E::add(raw[Z - 1][dig[Z - 1]], pre[Z - 1]);
+    if constexpr (Z >= 2) {
+      T suf = m[Z - 1][dig[Z - 1]];
+#pragma unroll
+      for (int j = Z - 2; j >= 0; --j) {
+        raw[j][dig[j]] = E::fma(pre[j], suf, raw[j][dig[j]]);
+        if (j > 0) suf = E::mul(suf, m[j][dig[j]]);
+      }
+    }
+  }
+}
+
+// epilogue of one out-message: sum-normalise (beliefpropagation.jl:248-253), residual term against the previous message
+// on that edge (:261-267).  Returns the order-preserving key of the residual.
+template <typename T, int N>
+__device__ __forceinline__ unsigned long long finish_message(const T* raw, const T* old_m, int normalize, T* v) {
+  using E = Elem<T>;
+  T s = E::zero();
+#pragma unroll
+  for (int b = 0; b < N; ++b) s = E::add(s, raw[b]);
+  const bool scale = normalize && !E::is_zero(s);
+  T dot = E::zero();
+  double n_old = 0.0, n_new = 0.0;
+#pragma unroll
+  for (int b = 0; b < N; ++b) {
+    v[b] = scale ? E::div(raw[b], s) : raw[b];
+    dot = E::fma(E::conj(old_m[b]), v[b], dot);
+    n_old += E::abs2(old_m[b]);
+    n_new += E::abs2(v[b]);
+  }
+  return residual_key(1.0 - E::abs2(dot) / (n_old * n_new));
+}
+
+// 16 bytes global -> shared without a register round trip (LDGSTS, L2 only)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// a shared-memory row of 16-byte units <-> COUNT elements in registers (COUNT * sizeof(T) is a multiple of 16)
+template <typename T, int COUNT>
+__device__ __forceinline__ void row_load(const double2* row, T* dst) {
+  if constexpr (sizeof(T) == 16) {
+#pragma unroll
+    for (int e = 0; e < COUNT; ++e) {
+      const double2 x = row[e];
+      dst[e] = make_c64(x.x, x.y);
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < COUNT / 2; ++u) {
+      const double2 x = row[u];
+      reinterpret_cast<double*>(dst)[2 * u] = x.x;
+      reinterpret_cast<double*>(dst)[2 * u + 1] = x.y;
+    }
+  }
+}
+template <typename T, int COUNT>
+__device__ __forceinline__ void row_store(double2* row, const T* src) {
+  if constexpr (sizeof(T) == 16) {
+#pragma unroll
+    for (int e = 0; e < COUNT; ++e) row[e] = make_double2(src[e].re, src[e].im);
+  } else {
+#pragma unroll
+    for (int u = 0; u < COUNT / 2; ++u)
+      row[u] = make_double2(reinterpret_cast<const double*>(src)[2 * u], reinterpret_cast<const double*>(src)[2 * u + 1]);
+  }
+}
+
 template <typename T, int Z, int N>
 __global__ void __launch_bounds__(NT) bp_update_single_vertex(Args a) {
-  using E = Elem<T>;
-  constexpr int NE = ipow(N, Z);
+  using S = Shape<T, Z, N>;
+  constexpr int NE = S::NE;
+  extern __shared__ __align__(16) unsigned char vx_smem[];
   const T* __restrict__ sites = reinterpret_cast<const T*>(a.sites);
   const T* __restrict__ msg_in = reinterpret_cast<const T*>(a.msg_in);
   T* __restrict__ msg_out = reinterpret_cast<T*>(a.msg_out);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long key = 0ull;  // 0 = nothing recorded (residual_key never returns 0)
 
-  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * NT) {
-    T t[NE];
-    load_run<T, NE>(sites + a.site[i], t);
-    T m[Z][N];
+  // one warp = 32 consecutive vertices of the bucket per iteration (all lanes stay in the loop: warp collectives inside)
+  for (int64_t w0 = ((int64_t)blockIdx.x * (NT / 32) + warp) * 32; w0 < a.n; w0 += (int64_t)gridDim.x * NT) {
+    const int64_t i = w0 + lane;
+    const bool valid = i < a.n;
+    // descriptors first (independent, coalesced): everything below depends on them only
+    int64_t site = 0;
+    int32_t in_off[Z], out_off[Z];
+    if (valid) {
+      site = a.site[i];
 #pragma unroll
-    for (int k = 0; k < Z; ++k) load_run<T, N>(msg_in + a.moff[(int64_t)k * a.n + i], m[k]);
-
-    // all z leave-one-out contractions in one pass over the factor:
-    //   pre_j = T[l] prod_{k < j} m_k[l_k],  suf_j = prod_{k > j} m_k[l_k],  raw_j[l_j] += pre_j suf_j
-    T raw[Z][N];
+      for (int k = 0; k < Z; ++k) in_off[k] = a.moff[(int64_t)k * a.n + i];
+      out_off[0] = a.moff[(int64_t)Z * a.n + i];
+    } else {
 #pragma unroll
-    for (int j = 0; j < Z; ++j)
-#pragma unroll
-      for (int b = 0; b < N; ++b) raw[j][b] = E::zero();
-#pragma unroll
-    for (int x = 0; x < NE; ++x) {
-      int dig[Z];  // l_k of element x: constants once the loop is unrolled
-      {
-        int r = x;
-#pragma unroll
-        for (int k = 0; k < Z; ++k) {
-          dig[k] = r % N;
-          r /= N;
-        }
-      }
-      T pre[Z];
-      pre[0] = t[x];
-#pragma unroll
-      for (int k = 1; k < Z; ++k) pre[k] = E::mul(pre[k - 1], m[k - 1][dig[k - 1]]);
-      // j = Z - 1: empty suffix
-      raw[Z - 1][dig[Z - 1]] = E::add(raw[Z - 1][dig[Z - 1]], pre[Z - 1]);
-      if constexpr (Z >= 2) {
-        T suf = m[Z - 1][dig[Z - 1]];
-#pragma unroll
-        for (int j = Z - 2; j >= 0; --j) {
-          raw[j][dig[j]] = E::fma(pre[j], suf, raw[j][dig[j]]);
-          if (j > 0) suf = E::mul(suf, m[j][dig[j]]);
-        }
-      }
+      for (int k = 0; k < Z; ++k) in_off[k] = 0;
+      out_off[0] = 0;
     }
-
-    // epilogue per out-message: sum-normalise, residual term against the previous message on that edge, store
+    bool staged = false;
+    int64_t site0 = 0;
+    int32_t out0 = 0;
+    if constexpr (S::STAGED) {
+      site0 = __shfl_sync(0xffffffffu, site, 0);
+      out0 = __shfl_sync(0xffffffffu, out_off[0], 0);
+      const bool mine = valid && site == site0 + (int64_t)lane * NE && out_off[0] == out0 + lane * (Z * N);
+      staged = a.out_contig && __all_sync(0xffffffffu, mine) && ((reinterpret_cast<uintptr_t>(sites + site0) & 15) == 0) &&
+               ((reinterpret_cast<uintptr_t>(msg_in + out0) & 15) == 0) && ((reinterpret_cast<uintptr_t>(msg_out + out0) & 15) == 0);
+    }
+    if (staged) {
+      if constexpr (S::STAGED) {
+        double2* wt = reinterpret_cast<double2*>(vx_smem) + (size_t)warp * S::WARP_UNITS;  // 32 factor rows
+        double2* wo = wt + 32 * S::RS;                                                     // 32 rows of z out-messages
+        const double2* gt = reinterpret_cast<const double2*>(sites + site0);
+        const double2* go = reinterpret_cast<const double2*>(msg_in + out0);
+        // every global read of the iteration is issued here, back to back: the factor rows and the old out-messages go
+        // straight from HBM into their transposed shared-memory slots (cp.async, 16 bytes per lane and request: each
+        // request covers 512 contiguous bytes), the z gathered in-messages into registers
 #pragma unroll
-    for (int j = 0; j < Z; ++j) {
-      const int64_t off = a.moff[(int64_t)(Z + j) * a.n + i];
-      T old_m[N];
-      load_run<T, N>(msg_in + off, old_m);
-      T s = E::zero();
+        for (int q = 0; q < S::RC; ++q) {
+          const int c = q * 32 + lane;
+          cp_async16(wt + (c / S::RC) * S::RS + (c % S::RC), gt + c);
+        }
 #pragma unroll
-      for (int b = 0; b < N; ++b) s = E::add(s, raw[j][b]);
-      const bool scale = a.normalize && !E::is_zero(s);
-      T dot = E::zero();
-      double n_old = 0.0, n_new = 0.0;
-      T v[N];
+        for (int q = 0; q < S::OC; ++q) {
+          const int c = q * 32 + lane;
+          cp_async16(wo + (c / S::OC) * S::OS + (c % S::OC), go + c);
+        }
+        T m[Z][N];
 #pragma unroll
-      for (int b = 0; b < N; ++b) {
-        v[b] = scale ? E::div(raw[j][b], s) : raw[j][b];
-        dot = E::fma(E::conj(old_m[b]), v[b], dot);
-        n_old += E::abs2(old_m[b]);
-        n_new += E::abs2(v[b]);
+        for (int k = 0; k < Z; ++k) load_run<T, N>(msg_in + in_off[k], m[k]);
+        cp_async_wait_all();
+        __syncwarp();
+        T t[NE], old_m[Z * N];
+        row_load<T, NE>(wt + lane * S::RS, t);
+        row_load<T, Z * N>(wo + lane * S::OS, old_m);
+        T raw[Z][N], v[Z * N];
+        leave_one_out<T, Z, N>(t, m, raw);
+#pragma unroll
+        for (int j = 0; j < Z; ++j) {
+          const unsigned long long kj = finish_message<T, N>(raw[j], old_m + j * N, a.normalize, v + j * N);
+          key = kj > key ? kj : key;
+        }
+        row_store<T, Z * N>(wo + lane * S::OS, v);  // (only this lane touched its row since the barrier above)
+        __syncwarp();
+        double2* gout = reinterpret_cast<double2*>(msg_out + out0);
+#pragma unroll
+        for (int q = 0; q < S::OC; ++q) {
+          const int c = q * 32 + lane;
+          gout[c] = wo[(c / S::OC) * S::OS + (c % S::OC)];
+        }
+        __syncwarp();  // rows are re-filled by other lanes in the next iteration
       }
-      store_run<T, N>(msg_out + off, v);
-      const unsigned long long kj = residual_key(1.0 - E::abs2(dot) / (n_old * n_new));
-      key = kj > key ? kj : key;
+    } else if (valid) {
+      // per-thread path: a tail warp, a bucket whose vertices are not consecutive in memory, or an odd row size
+#pragma unroll
+      for (int j = 1; j < Z; ++j) out_off[j] = a.moff[(int64_t)(Z + j) * a.n + i];
+      T t[NE];
+      load_run<T, NE>(sites + site, t);
+      T m[Z][N], old_m[Z][N];
+#pragma unroll
+      for (int k = 0; k < Z; ++k) load_run<T, N>(msg_in + in_off[k], m[k]);
+#pragma unroll
+      for (int j = 0; j < Z; ++j) load_run<T, N>(msg_in + out_off[j], old_m[j]);
+      T raw[Z][N];
+      leave_one_out<T, Z, N>(t, m, raw);
+#pragma unroll
+      for (int j = 0; j < Z; ++j) {
+        T v[N];
+        const unsigned long long kj = finish_message<T, N>(raw[j], old_m[j], a.normalize, v);
+        key = kj > key ? kj : key;
+        store_run<T, N>(msg_out + out_off[j], v);
+      }
     }
   }
 
@@ -184,7 +327,7 @@ __global__ void __launch_bounds__(NT) bp_update_single_vertex(Args a) {
     key = o > key ? o : key;
   }
   __shared__ unsigned long long wkey[NT / 32];
-  if ((threadIdx.x & 31) == 0) wkey[threadIdx.x >> 5] = key;
+  if (lane == 0) wkey[warp] = key;
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -196,7 +339,12 @@ __global__ void __launch_bounds__(NT) bp_update_single_vertex(Args a) {
 template <typename T, int Z, int N>
 inline cudaError_t launch_zn(const Args& a, int grid, cudaStream_t stream) {
   if constexpr (supported<T, Z, N>()) {
-    bp_update_single_vertex<T, Z, N><<<grid, NT, 0, stream>>>(a);
+    constexpr int smem = Shape<T, Z, N>::SMEM_BYTES;
+    if (smem > 48 * 1024) {
+      const cudaError_t e = cudaFuncSetAttribute(bp_update_single_vertex<T, Z, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+    }
+    bp_update_single_vertex<T, Z, N><<<grid, NT, smem, stream>>>(a);
     return cudaGetLastError();
   } else {
     return cudaErrorInvalidValue;
