@@ -574,9 +574,8 @@ inline int launch_vertex_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, voi
   k.normalize = normalize;
   k.out_contig = b.vx_out_contig;
   if (k.n == 0) return BPX_OK;
-  const int grid = (int)std::min<int64_t>((k.n + vertexk::NT - 1) / vertexk::NT, (int64_t)ctx->num_sms * 32);
-  const cudaError_t e = ctx->dtype == BPX_C64 ? vertexk::launch<c64>(k, b.z, b.chi, grid, ctx->stream)
-                                              : vertexk::launch<double>(k, b.z, b.chi, grid, ctx->stream);
+  const cudaError_t e = ctx->dtype == BPX_C64 ? vertexk::launch<c64>(k, b.z, b.chi, ctx->num_sms, ctx->stream)
+                                              : vertexk::launch<double>(k, b.z, b.chi, ctx->num_sms, ctx->stream);
   ctx->n_launches++;
   BPX_CUDA(ctx, e);
   return BPX_OK;

@@ -20,12 +20,17 @@
 // Algorithmic bytes per vertex: chi^z w (factor) + 3 z chi w (message in, old, out) -- the roofline `bench.py
 // --workload ising` reports against (plus the 8 + 8 z descriptor bytes, which are real traffic but not algorithmic).
 #pragma once
+#include <stdlib.h>
+
 #include "bpx_common.cuh"
 
 namespace bpx {
 namespace vertexk {
 
 constexpr int NT = 128;  // threads per CTA
+#ifndef BPX_VERTEX_MIN_CTAS
+#define BPX_VERTEX_MIN_CTAS 6  // resident CTAs per SM the small Float64 shapes are compiled for (register cap 80; 5 -> 96 measured 2 % slower)
+#endif
 
 struct Args {
   const int64_t* site;     // [n]      element offset of T_v in the device site buffer
@@ -114,6 +119,9 @@ struct Shape {
   static constexpr int OC = OB / 16, OS = OC + ((OC & 1) ? 2 : 1);
   static constexpr int WARP_UNITS = STAGED ? 32 * (RS + OS) : 0;  // 16-byte units of shared memory per warp
   static constexpr int SMEM_BYTES = (NT / 32) * WARP_UNITS * 16;
+  // small factors: cap the registers at 96 (register files are allocated in units of 256 per warp: 100 registers would
+  // cost a fifth resident CTA)
+  static constexpr int MIN_CTAS = (NE * (int)(sizeof(T) / 8) <= 16) ? (sizeof(T) == 8 ? BPX_VERTEX_MIN_CTAS : 5) : 1;
 };
 
 // all z leave-one-out contractions in one pass over the factor:
@@ -215,7 +223,7 @@ __device__ __forceinline__ void row_store(double2* row, const T* src) {
 }
 
 template <typename T, int Z, int N>
-__global__ void __launch_bounds__(NT) bp_update_single_vertex(Args a) {
+__global__ void __launch_bounds__(NT, Shape<T, Z, N>::MIN_CTAS) bp_update_single_vertex(Args a) {
   using S = Shape<T, Z, N>;
   constexpr int NE = S::NE;
   extern __shared__ __align__(16) unsigned char vx_smem[];
@@ -225,22 +233,34 @@ __global__ void __launch_bounds__(NT) bp_update_single_vertex(Args a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long key = 0ull;  // 0 = nothing recorded (residual_key never returns 0)
 
-  // one warp = 32 consecutive vertices of the bucket per iteration (all lanes stay in the loop: warp collectives inside)
-  for (int64_t w0 = ((int64_t)blockIdx.x * (NT / 32) + warp) * 32; w0 < a.n; w0 += (int64_t)gridDim.x * NT) {
+  // one warp = 32 consecutive vertices of the bucket per iteration (all lanes stay in the loop: warp collectives inside).
+  // The grid is persistent (resident CTAs only), so a warp runs many iterations and the descriptors of iteration k + 1
+  // are fetched while iteration k computes: one exposed memory latency per iteration instead of two.
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  int64_t w0 = ((int64_t)blockIdx.x * (NT / 32) + warp) * 32;
+  int64_t nx_site = 0;
+  int32_t nx_in[Z], nx_out0 = 0;
+#pragma unroll
+  for (int k = 0; k < Z; ++k) nx_in[k] = 0;
+  if (w0 + lane < a.n) {
+    nx_site = a.site[w0 + lane];
+#pragma unroll
+    for (int k = 0; k < Z; ++k) nx_in[k] = a.moff[(int64_t)k * a.n + w0 + lane];
+    nx_out0 = a.moff[(int64_t)Z * a.n + w0 + lane];
+  }
+  for (; w0 < a.n; w0 += stride) {
     const int64_t i = w0 + lane;
     const bool valid = i < a.n;
-    // descriptors first (independent, coalesced): everything below depends on them only
-    int64_t site = 0;
+    const int64_t site = nx_site;
     int32_t in_off[Z], out_off[Z];
-    if (valid) {
-      site = a.site[i];
 #pragma unroll
-      for (int k = 0; k < Z; ++k) in_off[k] = a.moff[(int64_t)k * a.n + i];
-      out_off[0] = a.moff[(int64_t)Z * a.n + i];
-    } else {
+    for (int k = 0; k < Z; ++k) in_off[k] = nx_in[k];
+    out_off[0] = nx_out0;
+    if (i + stride < a.n) {  // prefetch the next iteration's descriptors (consumed after this iteration's stores)
+      nx_site = a.site[i + stride];
 #pragma unroll
-      for (int k = 0; k < Z; ++k) in_off[k] = 0;
-      out_off[0] = 0;
+      for (int k = 0; k < Z; ++k) nx_in[k] = a.moff[(int64_t)k * a.n + i + stride];
+      nx_out0 = a.moff[(int64_t)Z * a.n + i + stride];
     }
     bool staged = false;
     int64_t site0 = 0;
@@ -336,14 +356,28 @@ __global__ void __launch_bounds__(NT) bp_update_single_vertex(Args a) {
   }
 }
 
+// `ctas_per_sm` > 0: launch a persistent grid of num_sms * min(ctas_per_sm, occupancy) CTAs (at most one CTA per NT vertices)
 template <typename T, int Z, int N>
-inline cudaError_t launch_zn(const Args& a, int grid, cudaStream_t stream) {
+inline cudaError_t launch_zn(const Args& a, int num_sms, cudaStream_t stream) {
   if constexpr (supported<T, Z, N>()) {
     constexpr int smem = Shape<T, Z, N>::SMEM_BYTES;
-    if (smem > 48 * 1024) {
-      const cudaError_t e = cudaFuncSetAttribute(bp_update_single_vertex<T, Z, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static int resident = 0;  // CTAs per SM of this instantiation (queried once)
+    if (resident == 0) {
+      if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(bp_update_single_vertex<T, Z, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+      }
+      int occ = 0;
+      const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bp_update_single_vertex<T, Z, N>, NT, smem);
       if (e != cudaSuccess) return e;
+      resident = occ > 0 ? occ : 1;
+      if (const char* env = getenv("BPX_VERTEX_CTAS_PER_SM")) {  // tuning knob: CTAs per SM of the launch (> occupancy: not persistent)
+        const int v = atoi(env);
+        if (v > 0) resident = v;
+      }
     }
+    const int64_t want = (a.n + NT - 1) / NT, cap = (int64_t)num_sms * resident;
+    const int grid = (int)(want < cap ? want : cap);
     bp_update_single_vertex<T, Z, N><<<grid, NT, smem, stream>>>(a);
     return cudaGetLastError();
   } else {
@@ -352,24 +386,24 @@ inline cudaError_t launch_zn(const Args& a, int grid, cudaStream_t stream) {
 }
 
 template <typename T, int N>
-inline cudaError_t launch_n(const Args& a, int z, int grid, cudaStream_t stream) {
+inline cudaError_t launch_n(const Args& a, int z, int num_sms, cudaStream_t stream) {
   switch (z) {
-    case 1: return launch_zn<T, 1, N>(a, grid, stream);
-    case 2: return launch_zn<T, 2, N>(a, grid, stream);
-    case 3: return launch_zn<T, 3, N>(a, grid, stream);
-    case 4: return launch_zn<T, 4, N>(a, grid, stream);
-    case 5: return launch_zn<T, 5, N>(a, grid, stream);
-    case 6: return launch_zn<T, 6, N>(a, grid, stream);
+    case 1: return launch_zn<T, 1, N>(a, num_sms, stream);
+    case 2: return launch_zn<T, 2, N>(a, num_sms, stream);
+    case 3: return launch_zn<T, 3, N>(a, num_sms, stream);
+    case 4: return launch_zn<T, 4, N>(a, num_sms, stream);
+    case 5: return launch_zn<T, 5, N>(a, num_sms, stream);
+    case 6: return launch_zn<T, 6, N>(a, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
 template <typename T>
-inline cudaError_t launch(const Args& a, int z, int n, int grid, cudaStream_t stream) {
+inline cudaError_t launch(const Args& a, int z, int n, int num_sms, cudaStream_t stream) {
   switch (n) {
-    case 2: return launch_n<T, 2>(a, z, grid, stream);
-    case 3: return launch_n<T, 3>(a, z, grid, stream);
-    case 4: return launch_n<T, 4>(a, z, grid, stream);
+    case 2: return launch_n<T, 2>(a, z, num_sms, stream);
+    case 3: return launch_n<T, 3>(a, z, num_sms, stream);
+    case 4: return launch_n<T, 4>(a, z, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -5,19 +5,16 @@ set -u
 O=gpurun_out
 mkdir -p $O
 T0=$(date +%s)
-timeout 200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > $O/r1j_pytest_gpu.txt
-echo "pytest done at $(( $(date +%s) - T0 )) s" >> $O/r1j_pytest_gpu.txt
-timeout 80 python bench.py --steps 10 --warmup 3 --cpu-seconds 3 > $O/r1j_bench_cfg2_n1.json 2> $O/r1j_bench_cfg2_n1.err
-timeout 120 python bench.py --workload ising --steps 20 --warmup 3 --cpu-seconds 5 > $O/r1j_bench_ising_n1.json 2> $O/r1j_bench_ising_n1.err
-timeout 100 ncu --set full --clock-control none --import-source on -k regex:bp_update_single_vertex --launch-skip 2 -c 1 -f \
-  -o $O/r1j_vertex_ising python tools/profile_sweep.py ising 5 > $O/r1j_ncu.log 2>&1
-timeout 60 python -c "import __graft_entry__ as e; e.smoke()" > $O/r1j_smoke.txt 2>&1
-echo "all done at $(( $(date +%s) - T0 )) s" >> $O/r1j_pytest_gpu.txt
-cat $O/r1j_pytest_gpu.txt
-tail -c 600 $O/r1j_bench_ising_n1.err
-head -c 900 $O/r1j_bench_ising_n1.json
+timeout 200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > $O/r1m_pytest_gpu.txt
+echo "pytest done at $(( $(date +%s) - T0 )) s" >> $O/r1m_pytest_gpu.txt
+timeout 80 python bench.py --steps 10 --warmup 3 --cpu-seconds 3 > $O/r1m_bench_cfg2_n1.json 2> $O/r1m_bench_cfg2_n1.err
+timeout 120 python bench.py --workload ising --steps 20 --warmup 3 --cpu-seconds 5 > $O/r1m_bench_ising_n1.json 2> $O/r1m_bench_ising_n1.err
+timeout 60 python -c "import __graft_entry__ as e; e.smoke()" > $O/r1m_smoke.txt 2>&1
+echo "all done at $(( $(date +%s) - T0 )) s" >> $O/r1m_pytest_gpu.txt
+cat $O/r1m_pytest_gpu.txt
+tail -c 600 $O/r1m_bench_ising_n1.err
+head -c 900 $O/r1m_bench_ising_n1.json
 echo
-head -c 400 $O/r1j_bench_cfg2_n1.json
+head -c 400 $O/r1m_bench_cfg2_n1.json
 echo
-tail -3 $O/r1j_ncu.log
-cat $O/r1j_smoke.txt | tail -2
+cat $O/r1m_smoke.txt | tail -2
