@@ -36,6 +36,8 @@ PROFILED_TRAFFIC = {
     ("cfg2", 1): (62.28e6 + 0.59e6, "profiles/r1d_onchip_c8_final_ncu_summary.csv"),
     ("cfg4", 1): (272.88e6 + 9.31e6, "profiles/r1e_onchip_c16_cfg4_ncu_summary.csv"),
     ("cfg3", 1): (6.72e6 + 0.0, "profiles/r1f_onchip_c16c_cfg3_ncu_summary.csv (the 1.2 MB of new messages stay in L2)"),
+    ("ising", 1): (230.85e6 + 48.74e6, "profiles/r1k_vertex_ising_v3_ncu_summary.csv (each message is read twice, as input and as the old "
+                   "value, but comes from DRAM once; + 29 MB of descriptors; part of the output stays in L2)"),
 }
 # sliced chi=16 kernel: 926.9 MB read + 415.0 MB written for 196 degree-4 vertices (profiles/r1c_sliced_c16_ncu_summary.csv)
 SLICED_TRAFFIC_PER_VERTEX = (926.93e6 + 415.05e6) / 196.0

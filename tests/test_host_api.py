@@ -130,3 +130,37 @@ def test_canonical_arrays_permutes_by_name():
     # vertex 2: neighbours in leg order (b -> 3, a -> 1)
     assert [cp.ga.vertices[cp.ga.dst[e]] for e in range(cp.ga.row_ptr[1], cp.ga.row_ptr[2])] == [3, 1]
     assert np.array_equal(cp.tensors[1], np.transpose(t2.data, (1, 0, 2)))
+
+
+def test_grid_graph_arrays_matches_named_grid():
+    """The vectorised lattice builder (millions of vertices) describes the same graph as named_grid + graph_arrays."""
+    for dims, periodic in [((4, 4), False), ((4, 4), True), ((3, 2), True), ((3, 3, 3), True), ((5,), True), ((2, 2), True), ((1, 4), False)]:
+        ga = graphs.grid_graph_arrays(dims, periodic)
+        gb = graphs.graph_arrays(graphs.named_grid(dims, periodic))
+        assert ga.nv == gb.nv and ga.ne == gb.ne
+        assert set(zip(ga.src.tolist(), ga.dst.tolist())) == set(zip(gb.src, gb.dst))  # same vertex numbering
+        assert np.all(ga.src[ga.rev] == ga.dst) and np.all(ga.rev[ga.rev] == np.arange(ga.ne))
+        assert np.all(ga.slot == np.arange(ga.ne) - ga.row_ptr[ga.src]) and np.all(np.diff(ga.src) >= 0)
+    big = graphs.grid_graph_arrays((1024, 1024), True)
+    assert big.nv == 1 << 20 and big.ne == 1 << 22 and np.all(np.diff(big.row_ptr) == 4)
+
+
+def test_synthetic_ising_workload_is_the_generator_network(oracle):
+    """bench.py --workload ising builds its factors in bulk; on a small lattice they contract to the same partition
+    function as the `ising_network` generator's network, and the work model of the roofline is the documented one."""
+    from itnn_b200 import generators, problems
+    from itnn_b200.tensornetwork import Index, canonical_arrays
+
+    for dims, periodic in [((4, 4), True), ((4, 3), False)]:
+        q = problems.synthetic_ising(dims, 0.3, periodic)
+        tensors, msgs = problems.unpacked(q)
+        z1 = oracle.contract_all_sequential(oracle.make_problem(q.ga, tensors, "single"))
+        g = graphs.named_grid(dims, periodic)
+        ld = {frozenset((e.src, e.dst)): Index(2) for e in g.edges()}
+        cp = canonical_arrays(generators.ising_network(lambda e: ld[frozenset((e.src, e.dst))], 0.3, g))
+        z2 = oracle.contract_all_sequential(oracle.make_problem(cp.ga, cp.tensors, "single"))
+        assert np.isclose(z1, z2, rtol=1e-12)
+        assert all(abs(m.sum() - 1) < 1e-12 and (m > 0).all() for m in msgs)
+    q = problems.synthetic_ising((8, 8))
+    assert q.mode == "single" and q.bytes_per_sweep() == 64 * 16 * 8 + 3 * 256 * 2 * 8   # factors + 3 x messages
+    assert q.flops_per_sweep() == 256 * 2 * (16 + 8 + 4)                                # absorb 3 legs: 16 + 8 + 4 MACs
