@@ -152,6 +152,33 @@ int bpx_edge_scalars(bpx_ctx* ctx, void* out /* ne/2 elements, edges with e < re
  * the reference has no `expect`. */
 int bpx_vertex_expect_numerators(bpx_ctx* ctx, const void* ops_packed, void* out /* nv elements */);
 
+/* ---- the consumer of the messages: BP simple-update gate application ------------------------------------
+ * Replaces `apply_gate_bp!` (src/apply/apply_operators.jl:213-283, the default `BPApplyGate` strategy of
+ * `apply_operator`, :190-211) for a BATCH of vertex-disjoint gates, e.g. one layer of a Trotter circuit: the
+ * reference applies one gate per call on the host; here one CTA owns one gate and one launch covers the layer.
+ * Site tensors (the ket layer) and the current message set are updated IN PLACE on the device
+ * (the reference copies state and env first, `initialize_output`, :204-208 -- the Julia glue copies if it must).
+ *
+ * Two-site gates (:246-283): edges[g] = a directed edge v1 -> v2 of the graph; ops_packed holds for every gate the
+ *   operator `op[o1, o2, i1, i2]` (column-major, d1*d2*d1*d2 elements; 1 = src, 2 = dst of the edge; outputs first
+ *   like ITensorBase `operator`s, test/test_apply_operator.jl:19-27), packed in gate order.  Per gate: gauges
+ *   from the incoming boundary messages (gram_eigh_full_with_pinv) -> QR -> gate -> truncated SVD -> sqrt(S) split ->
+ *   inverse gauges; the messages of BOTH directions of the gate edge become diag(S) (:273-277).
+ *   max_rank: `trunc` rank; 0 = keep the bond dimension.  The link leg keeps its dimension chi_e: the kept rank is
+ *   k = min(max_rank, chi_e, rank bound of the bond matrix) and tensors / messages are zero-padded from k to chi_e
+ *   (the reference would shrink or grow the leg; to grow a bond re-declare the dims with bpx_set_dims).
+ *   normalize != 0: S <- S / |S| (:262-264).
+ *   singular_values_out (may be NULL): link_dim[edges[g]] doubles per gate, packed in gate order (kept values, then 0).
+ * One-site gates (:226-244): vertices[g]; ops_packed holds `op[o, i]` (d_v*d_v elements) per gate; normalize != 0
+ *   divides the new tensor by the norm of its gauged version (all incoming messages).
+ * BPX_ERR_INVALID if two gates of one call share a vertex; BPX_ERR_UNSUPPORTED on partitioned contexts. */
+int bpx_apply_two_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* edges, const void* ops_packed,
+                             int max_rank, int normalize, double* singular_values_out);
+int bpx_apply_one_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* vertices, const void* ops_packed,
+                             int normalize);
+/* download one site tensor (canonical layout) -- `state[v]` after gates were applied */
+int bpx_get_site_tensor(bpx_ctx* ctx, int64_t v, void* data);
+
 /* ---- introspection --------------------------------------------------------------------------------- */
 int bpx_num_buckets(const bpx_ctx* ctx);
 /* info[0]=degree, [1]=chi (0 if non-uniform), [2]=phys dim, [3]=#vertices, [4]=#directed edges,

@@ -13,6 +13,9 @@ from .beliefpropagation import (
     region_scalar, select_algorithm, select_beliefpropagation_stopping_criterion, similar_message_environment,
     vertex_scalar, vertex_scalars,
 )
+from .apply import (
+    ApplyOperatorAlgorithm, BPApplyGate, NoApplyOperatorEnvironmentPreparation, Operator, apply_operator, apply_operators,
+)
 from .device import BPXContext, fill_randn
 from .generators import delta, delta_network, diagonaltensor, ising_network, sqrt_ising_bond
 from .graphs import (

@@ -80,6 +80,9 @@ def load() -> C.CDLL:
         "bpx_vertex_scalars": (C.c_int, [vp, vp]),
         "bpx_edge_scalars": (C.c_int, [vp, vp]),
         "bpx_vertex_expect_numerators": (C.c_int, [vp, vp, vp]),
+        "bpx_apply_two_site_gates": (C.c_int, [vp, i64, vp, vp, C.c_int, C.c_int, vp]),
+        "bpx_apply_one_site_gates": (C.c_int, [vp, i64, vp, vp, C.c_int]),
+        "bpx_get_site_tensor": (C.c_int, [vp, i64, vp]),
         "bpx_num_buckets": (C.c_int, [vp]),
         "bpx_bucket_info": (C.c_int, [vp, C.c_int, P(i64)]),
         "bpx_set_kernel_policy": (C.c_int, [vp, C.c_int]),

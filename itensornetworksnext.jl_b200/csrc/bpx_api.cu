@@ -14,6 +14,7 @@
 #include "bpx_ctx.h"
 #include "bpx_fast.cuh"
 #include "bpx_halo.cuh"
+#include "bpx_apply.cuh"
 
 using namespace bpx;
 
@@ -1368,6 +1369,182 @@ extern "C" int bpx_set_stream(bpx_ctx* ctx, void* cuda_stream) {
   cudaStreamSynchronize(ctx->stream);
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return BPX_OK;
+}
+
+// ---- the consumer of the messages: BP simple-update gate application (bpx_apply.cuh) ---------------------------
+extern "C" int bpx_get_site_tensor(bpx_ctx* ctx, int64_t v, void* data) {
+  NEED_DIMS(ctx, "bpx_get_site_tensor");
+  REQUIRE(ctx, v >= 0 && v < ctx->nv && data, "bpx_get_site_tensor: bad arguments");
+  REQUIRE(ctx, ctx->dev_site_off[v] >= 0, "bpx_get_site_tensor: vertex %lld is not resident on this rank", (long long)v);
+  const size_t off = (size_t)ctx->dev_site_off[v] * ctx->esize, n = (size_t)(ctx->site_off[v + 1] - ctx->site_off[v]) * ctx->esize;
+  BPX_CUDA(ctx, cudaMemcpyAsync(data, (char*)ctx->d_sites + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPX_OK;
+}
+
+static void apply_fill_side(bpx_ctx* ctx, applyk::Side& s, int64_t v, int bond_slot, int chi_b) {
+  const VDesc& vd = ctx->h_vdesc[v];
+  s.site_off = ctx->dev_site_off[v];
+  s.z = vd.z;
+  s.d = vd.d;
+  s.bond_slot = bond_slot;
+  for (int i = 0; i < vd.z; ++i) {
+    s.dim[i] = vd.dim[i];
+    s.in_msg[i] = ctx->msg_off[vd.in_edge[i]];
+  }
+  applyk::finish_side(s, chi_b);
+}
+
+// gates: descriptors with ws_off still unset.  Runs them in chunks bounded by the work-space budget.
+static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const void* ops_packed, size_t ops_elems,
+                     int normalize, double* sv_dev, int64_t sv_stride, bool needs_ws = true) {
+  const int64_t ng = (int64_t)gates.size();
+  if (ng == 0) return BPX_OK;
+  // chunks: consecutive gates whose work space fits the budget (at least one gate per chunk)
+  size_t free_b = 0, total_b = 0;
+  BPX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  const int64_t budget = (int64_t)std::max<size_t>(std::min<size_t>(free_b / 2, (size_t)8 << 30), (size_t)1 << 20) / ctx->esize;
+  std::vector<int64_t> chunk_begin{0};
+  int64_t cur_total = 0, max_total = 0;
+  for (int64_t g = 0; g < ng; ++g) {
+    const int64_t need = needs_ws ? applyk::layout_of(gates[g]).total + 2 : 2;  // plain one-site gates work in place
+    if (cur_total > 0 && cur_total + need > budget) {
+      chunk_begin.push_back(g);
+      cur_total = 0;
+    }
+    gates[g].ws_off = cur_total;
+    cur_total += need;
+    max_total = std::max(max_total, cur_total);
+  }
+  chunk_begin.push_back(ng);
+  applyk::GateDesc* d_gates = nullptr;
+  char* d_ws = nullptr;
+  char* d_ops = nullptr;
+  int rc = upload(ctx, &d_gates, gates);
+  if (!rc) rc = dev_alloc(ctx, &d_ws, (size_t)max_total * ctx->esize);
+  if (!rc) rc = dev_alloc(ctx, &d_ops, ops_elems * ctx->esize);
+  cudaError_t ce = cudaSuccess;
+  if (!rc) {
+    ce = cudaMemcpyAsync(d_ops, ops_packed, ops_elems * ctx->esize, cudaMemcpyHostToDevice, ctx->stream);
+    for (size_t c = 0; c + 1 < chunk_begin.size() && ce == cudaSuccess; ++c) {
+      applyk::ApplyArgs a;
+      a.gates = d_gates + chunk_begin[c];
+      a.n_gates = chunk_begin[c + 1] - chunk_begin[c];
+      a.sites = ctx->d_sites;
+      a.msgs = ctx->d_msg[ctx->cur];
+      a.ops = d_ops;
+      a.ws = d_ws;
+      a.sv_out = sv_dev ? sv_dev + chunk_begin[c] * sv_stride : nullptr;
+      a.sv_stride = sv_stride;
+      a.normalize = normalize;
+      const int grid = (int)std::min<int64_t>(a.n_gates, (int64_t)ctx->num_sms * 8);
+      if (ctx->dtype == BPX_F64)
+        applyk::bp_apply_gates<double><<<grid, applyk::NT, 0, ctx->stream>>>(a);
+      else
+        applyk::bp_apply_gates<c64><<<grid, applyk::NT, 0, ctx->stream>>>(a);
+      ctx->n_launches++;
+      ce = cudaGetLastError();
+    }
+  }
+  const cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_gates);
+  cudaFree(d_ws);
+  cudaFree(d_ops);
+  if (rc) return rc;
+  BPX_CUDA(ctx, ce);
+  BPX_CUDA(ctx, ce2);
+  ctx->sites_dirty = true;  // the private tensor images of the update kernels are stale now
+  return BPX_OK;
+}
+
+static int apply_common_checks(bpx_ctx* ctx, const char* name) {
+  REQUIRE(ctx, ctx->mode == BPX_MODE_NORM, "%s: NORM mode only (the state is the ket layer of a norm network)", name);
+  if (ctx->nranks > 1) {
+    set_error(ctx, "%s: partitioned contexts are not supported yet (apply gates before bpx_set_partition)", name);
+    return BPX_ERR_UNSUPPORTED;
+  }
+  return BPX_OK;
+}
+
+extern "C" int bpx_apply_two_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* edges, const void* ops_packed,
+                                        int max_rank, int normalize, double* singular_values_out) {
+  NEED_DIMS(ctx, "bpx_apply_two_site_gates");
+  int rc = apply_common_checks(ctx, "bpx_apply_two_site_gates");
+  if (rc) return rc;
+  REQUIRE(ctx, n_gates >= 0 && max_rank >= 0, "bpx_apply_two_site_gates: bad arguments");
+  if (n_gates == 0) return BPX_OK;
+  REQUIRE(ctx, edges && ops_packed, "bpx_apply_two_site_gates: NULL edges / operators");
+  std::vector<applyk::GateDesc> gates((size_t)n_gates);
+  std::vector<char> used((size_t)ctx->nv, 0);
+  int64_t op_off = 0, sv_stride = 1;
+  for (int64_t g = 0; g < n_gates; ++g) {
+    const int64_t e = edges[g];
+    REQUIRE(ctx, e >= 0 && e < ctx->ne, "bpx_apply_two_site_gates: gate %lld: edge %lld out of range", (long long)g, (long long)e);
+    const int64_t v1 = ctx->src[e], v2 = ctx->dst[e], r = ctx->rev[e];
+    REQUIRE(ctx, !used[v1] && !used[v2],
+            "bpx_apply_two_site_gates: gate %lld shares a vertex with an earlier gate of the batch (gates of one call "
+            "must be vertex-disjoint; apply overlapping gates in successive calls)", (long long)g);
+    used[v1] = used[v2] = 1;
+    applyk::GateDesc& gd = gates[g];
+    memset(&gd, 0, sizeof(gd));
+    gd.nsides = 2;
+    gd.chi_b = ctx->link_dim[e];
+    apply_fill_side(ctx, gd.s[0], v1, ctx->slot[e], gd.chi_b);
+    apply_fill_side(ctx, gd.s[1], v2, ctx->slot[r], gd.chi_b);
+    REQUIRE(ctx, gd.s[0].d <= 16 && gd.s[1].d <= 16, "bpx_apply_two_site_gates: physical dimension > 16");
+    const int m = gd.s[0].nref * gd.s[0].d, n = gd.s[1].nref * gd.s[1].d;
+    int k = max_rank > 0 ? std::min(max_rank, gd.chi_b) : gd.chi_b;
+    gd.k = std::min(k, std::min(m, n));
+    gd.msg12 = ctx->msg_off[e];
+    gd.msg21 = ctx->msg_off[r];
+    gd.op_off = op_off;
+    const int64_t dd = (int64_t)gd.s[0].d * gd.s[1].d;
+    op_off += dd * dd;
+    sv_stride = std::max<int64_t>(sv_stride, gd.chi_b);
+  }
+  double* d_sv = nullptr;
+  if (singular_values_out && (rc = dev_alloc(ctx, &d_sv, (size_t)(n_gates * sv_stride)))) return rc;
+  rc = apply_run(ctx, gates, ops_packed, (size_t)op_off, normalize, d_sv, sv_stride);
+  if (!rc && d_sv) {
+    std::vector<double> h((size_t)(n_gates * sv_stride));
+    cudaError_t ce = cudaMemcpy(h.data(), d_sv, h.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) {
+      cudaFree(d_sv);
+      BPX_CUDA(ctx, ce);
+    }
+    int64_t o = 0;  // packed: link_dim[edges[g]] values per gate, gate order
+    for (int64_t g = 0; g < n_gates; ++g)
+      for (int i = 0; i < gates[g].chi_b; ++i) singular_values_out[o++] = h[(size_t)(g * sv_stride + i)];
+  }
+  cudaFree(d_sv);
+  return rc;
+}
+
+extern "C" int bpx_apply_one_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* vertices, const void* ops_packed,
+                                        int normalize) {
+  NEED_DIMS(ctx, "bpx_apply_one_site_gates");
+  int rc = apply_common_checks(ctx, "bpx_apply_one_site_gates");
+  if (rc) return rc;
+  REQUIRE(ctx, n_gates >= 0, "bpx_apply_one_site_gates: bad arguments");
+  if (n_gates == 0) return BPX_OK;
+  REQUIRE(ctx, vertices && ops_packed, "bpx_apply_one_site_gates: NULL vertices / operators");
+  std::vector<applyk::GateDesc> gates((size_t)n_gates);
+  std::vector<char> used((size_t)ctx->nv, 0);
+  int64_t op_off = 0;
+  for (int64_t g = 0; g < n_gates; ++g) {
+    const int64_t v = vertices[g];
+    REQUIRE(ctx, v >= 0 && v < ctx->nv, "bpx_apply_one_site_gates: gate %lld: vertex %lld out of range", (long long)g, (long long)v);
+    REQUIRE(ctx, !used[v], "bpx_apply_one_site_gates: vertex %lld appears twice in the batch", (long long)v);
+    used[v] = 1;
+    applyk::GateDesc& gd = gates[g];
+    memset(&gd, 0, sizeof(gd));
+    gd.nsides = 1;
+    apply_fill_side(ctx, gd.s[0], v, -1, 0);
+    REQUIRE(ctx, gd.s[0].d <= 16, "bpx_apply_one_site_gates: physical dimension > 16");
+    gd.op_off = op_off;
+    op_off += (int64_t)gd.s[0].d * gd.s[0].d;
+  }
+  return apply_run(ctx, gates, ops_packed, (size_t)op_off, normalize, nullptr, 0, normalize != 0);
 }
 
 extern "C" void* bpx_device_messages(bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? ctx->d_msg[ctx->cur] : nullptr; }

@@ -140,21 +140,37 @@ class BPXContext:
         self._check(self.lib.bpx_fill_synthetic(self.h, int(seed)))
 
     def get_site_tensor(self, v: int) -> np.ndarray:
-        """Debug/test helper: download one canonical site tensor (flat, column-major)."""
-        import ctypes as C_
-
-        n = int(self.site_off[v + 1] - self.site_off[v])
-        out = np.empty(n, dtype=self.dtype)
-        ptr = self.lib.bpx_device_site_tensors(self.h)
-        dev_off = self.lib.bpx_site_device_offset(self.h, int(v))
-        if dev_off < 0:
+        """Download one canonical site tensor (flat, column-major): `state[v]` after gates were applied."""
+        if self.lib.bpx_site_device_offset(self.h, int(v)) < 0:
             raise KeyError(f"site tensor {v} is not resident on this rank")
-        cudart = C_.CDLL("libcudart.so")
-        rc = cudart.cudaMemcpy(out.ctypes.data_as(C_.c_void_p), C_.c_void_p(ptr + int(dev_off) * self.dtype.itemsize),
-                               C_.c_size_t(out.nbytes), 2)
-        if rc != 0:
-            raise RuntimeError(f"cudaMemcpy failed ({rc})")
+        out = np.empty(int(self.site_off[v + 1] - self.site_off[v]), dtype=self.dtype)
+        self._check(self.lib.bpx_get_site_tensor(self.h, int(v), _ptr(out)))
         return out
+
+    # -- gate application (src/apply/apply_operators.jl:213-283) ------------------------------------
+    def apply_two_site_gates(self, edges: Sequence[int], ops: Sequence[np.ndarray], max_rank: int = 0,
+                             normalize: bool = False) -> List[np.ndarray]:
+        """A batch of vertex-disjoint two-site gates, in place on the device.  ops[g][o1, o2, i1, i2] with 1 = src and
+        2 = dst of directed edge edges[g].  Returns the kept singular values per gate (zero-padded to the link dim)."""
+        e = np.ascontiguousarray(edges, dtype=np.int64)
+        flat = (np.concatenate([np.asarray(o, dtype=self.dtype).ravel(order="F") for o in ops]) if len(ops)
+                else np.empty(0, self.dtype))
+        dims = [int(self.link_dim[i]) for i in e]
+        sv = np.zeros(max(1, sum(dims)), dtype=np.float64)
+        self._check(self.lib.bpx_apply_two_site_gates(self.h, len(e), _ptr(e), _ptr(np.ascontiguousarray(flat)), int(max_rank),
+                                                      int(bool(normalize)), _ptr(sv)))
+        out, o = [], 0
+        for c in dims:
+            out.append(sv[o:o + c].copy())
+            o += c
+        return out
+
+    def apply_one_site_gates(self, vertices: Sequence[int], ops: Sequence[np.ndarray], normalize: bool = False):
+        v = np.ascontiguousarray(vertices, dtype=np.int64)
+        flat = (np.concatenate([np.asarray(o, dtype=self.dtype).ravel(order="F") for o in ops]) if len(ops)
+                else np.empty(0, self.dtype))
+        self._check(self.lib.bpx_apply_one_site_gates(self.h, len(v), _ptr(v), _ptr(np.ascontiguousarray(flat)),
+                                                      int(bool(normalize))))
 
     # -- hot path ----------------------------------------------------------------------------------
     def sweep(self, max_sweeps: int = 1, tol: float = 0.0, normalize: bool = True):

@@ -1,0 +1,83 @@
+"""TEST INFRASTRUCTURE: a stand-in for `BPXContext` that runs the gate-application DEVICE CODE on the host through
+tests/native/apply_host.cu (csrc/bpx_apply.cuh compiled for the host), so that the Python lowering of
+itensornetworksnext.jl_b200/apply.py (names -> canonical layout, bond padding / slicing, layer batching) can be checked
+against the reference's known answers without a GPU.  Only `-m "not gpu"` tests monkeypatch it in; the product always
+talks to libbpx.so (CUDA)."""
+import ctypes
+
+import numpy as np
+
+P = ctypes.c_void_p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(P)
+
+
+class HostHarnessContext:
+    def __init__(self, hostlib, device=0):
+        self.lib = hostlib
+        self.calls = []  # (kind, number of gates) per device call -- lets tests see the batching
+
+    def set_graph(self, src, dst, slot, nv):
+        self.src, self.dst, self.slot, self.nv = list(src), list(dst), list(slot), int(nv)
+        self.ne = len(self.src)
+        index = {(s, d): e for e, (s, d) in enumerate(zip(self.src, self.dst))}
+        self.rev = [index[(d, s)] for s, d in zip(self.src, self.dst)]
+        self.out = [[] for _ in range(self.nv)]
+        for e, s in enumerate(self.src):
+            self.out[s].append(e)
+        for v in range(self.nv):
+            self.out[v].sort(key=lambda e: self.slot[e])
+
+    def set_dims(self, dtype, mode, phys_dim, link_dim):
+        assert mode == "norm"
+        self.dtype = np.dtype(dtype)
+        self.phys, self.link_dim = list(phys_dim), [int(c) for c in link_dim]
+
+    def set_site_tensors(self, tensors):
+        self.sites = [np.asarray(t, dtype=self.dtype).ravel(order="F").copy() for t in tensors]
+
+    def set_messages(self, msgs):
+        self.msgs = [np.asarray(m, dtype=self.dtype).ravel(order="F").copy() for m in msgs]
+
+    def _side(self, v):
+        dims = np.array([self.link_dim[e] for e in self.out[v]], dtype=np.int32)
+        incoming = [self.msgs[self.rev[e]] for e in self.out[v]]
+        msgs = np.concatenate(incoming) if incoming else np.zeros(0, self.dtype)
+        return len(self.out[v]), self.phys[v], dims, np.ascontiguousarray(msgs)
+
+    def apply_two_site_gates(self, edges, ops, max_rank=0, normalize=False):
+        self.calls.append(("two", len(edges)))
+        code = 1 if self.dtype.kind == "c" else 0
+        used, out = set(), []
+        for e, op in zip(edges, ops):
+            v1, v2, r = self.src[e], self.dst[e], self.rev[e]
+            assert not ({v1, v2} & used), "gates of one call must be vertex-disjoint"
+            used |= {v1, v2}
+            z1, d1, dims1, m1 = self._side(v1)
+            z2, d2, dims2, m2 = self._side(v2)
+            chi = self.link_dim[e]
+            o = np.asarray(op, dtype=self.dtype).ravel(order="F").copy()
+            msg_out, sv = np.zeros(chi * chi, dtype=self.dtype), np.zeros(chi)
+            rc = self.lib.apply_host_two_site(code, z1, d1, self.slot[e], _ptr(dims1), _ptr(self.sites[v1]), _ptr(m1), z2, d2,
+                                              self.slot[r], _ptr(dims2), _ptr(self.sites[v2]), _ptr(m2), _ptr(o),
+                                              int(max_rank), int(bool(normalize)), _ptr(msg_out), sv.ctypes.data_as(P))
+            assert rc == 0
+            self.msgs[e], self.msgs[r] = msg_out, msg_out.copy()
+            out.append(sv)
+        return out
+
+    def apply_one_site_gates(self, vertices, ops, normalize=False):
+        self.calls.append(("one", len(vertices)))
+        code = 1 if self.dtype.kind == "c" else 0
+        for v, op in zip(vertices, ops):
+            z, d, dims, m = self._side(v)
+            o = np.asarray(op, dtype=self.dtype).ravel(order="F").copy()
+            self.lib.apply_host_one_site(code, z, d, _ptr(dims), _ptr(self.sites[v]), _ptr(m), _ptr(o), int(bool(normalize)))
+
+    def get_site_tensor(self, v):
+        return self.sites[v].copy()
+
+    def close(self):
+        pass

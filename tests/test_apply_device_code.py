@@ -1,0 +1,276 @@
+"""The gate-application device code (csrc/bpx_apply.cuh) checked WITHOUT a GPU: tests/native/apply_host.cu
+compiles the same `__host__ __device__` routines for the host (a CUDA block collapses to one sequential lane), and
+every stage -- one-sided Jacobi, Householder QR, gauges from messages, the whole one- and two-site gate -- is compared
+with numpy / the apply_operator oracle (oracle/apply_oracle.py, which restates src/apply/apply_operators.jl:213-283).
+The CUDA launch of the same code is covered by the `gpu` tests in test_zz_gpu_apply.py."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import randn
+from oracle import apply_oracle as A
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "native", "apply_host.cu")
+HDR = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_apply.cuh")
+OUT = os.path.join(HERE, "native", "_build", "libapply_host.so")
+DTYPES = [np.float64, np.complex128]
+P = ctypes.c_void_p
+
+
+@pytest.fixture(scope="module")
+def hostlib():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    stale = not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in (SRC, HDR))
+    if stale:
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+                        "-shared", "-o", OUT, SRC], check=True)
+    return ctypes.CDLL(OUT)
+
+
+def ptr(a):
+    return a.ctypes.data_as(P)
+
+
+def code(dtype):
+    return 1 if np.dtype(dtype).kind == "c" else 0
+
+
+def fcopy(a):
+    return np.array(a, order="F", copy=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stages
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(6, 6), (9, 4), (4, 9), (12, 7), (1, 3), (5, 1), (32, 32)])
+def test_jacobi_svd(hostlib, dtype, shape):
+    rng = np.random.default_rng(11)
+    m, n = shape
+    a = randn(rng, dtype, (m, n))
+    if m >= 6 and n >= 4:
+        a[:, 1] = 0.5 * a[:, 0]  # a rank-deficient pair
+    b, v = fcopy(a), np.zeros((n, n), dtype=dtype, order="F")
+    hostlib.apply_host_jacobi(code(dtype), ptr(b), m, n, ptr(v))
+    assert np.allclose(v.conj().T @ v, np.eye(n), atol=1e-13)          # V unitary
+    assert np.allclose(a @ v, b, atol=1e-12 * np.abs(a).max())          # A V = B
+    gram = b.conj().T @ b
+    off = gram - np.diag(np.diag(gram))
+    assert np.abs(off).max() <= 1e-13 * np.abs(gram).max()              # orthogonal columns
+    got = np.sort(np.sqrt(np.diag(gram).real))[::-1][:min(m, n)]
+    want = np.linalg.svd(a, compute_uv=False)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-13 * want.max())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(20, 6), (6, 6), (4, 6), (1, 4), (2, 5), (64, 8)])
+def test_householder_qr(hostlib, dtype, shape):
+    rng = np.random.default_rng(5)
+    rows, cols = shape
+    a = randn(rng, dtype, (rows, cols))
+    if rows > 4:
+        a[:, 2] = a[:, 0] - 2 * a[:, 1]  # rank deficient
+    p, tau = fcopy(a), np.zeros(cols, dtype=dtype)
+    nref = min(rows, cols)
+    ncols = 3
+    y0 = np.zeros((rows, ncols), dtype=dtype, order="F")
+    y0[:nref] = randn(rng, dtype, (nref, ncols))
+    y = fcopy(y0)
+    hostlib.apply_host_qr(code(dtype), ptr(p), ctypes.c_int64(rows), cols, ptr(tau), ptr(y), ncols)
+    r = np.triu(p[:nref, :])
+    # Q from applying the reflectors to the identity
+    eye = np.zeros((rows, nref), dtype=dtype, order="F")
+    eye[:nref, :nref] = np.eye(nref)
+    p2, tau2 = fcopy(a), np.zeros(cols, dtype=dtype)
+    hostlib.apply_host_qr(code(dtype), ptr(p2), ctypes.c_int64(rows), cols, ptr(tau2), ptr(eye), nref)
+    q = eye
+    assert np.allclose(q.conj().T @ q, np.eye(nref), atol=1e-13)
+    assert np.allclose(q @ r, a, atol=1e-13 * max(1.0, np.abs(a).max()) * rows)
+    assert np.allclose(y, q @ y0[:nref], atol=1e-13 * rows)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("chi,rank", [(1, 1), (3, 3), (8, 8), (8, 5), (16, 16)])
+def test_gauge_from_message(hostlib, dtype, chi, rank):
+    rng = np.random.default_rng(chi * 10 + rank)
+    f = randn(rng, dtype, (rank, chi))
+    g = f.conj().T @ f                                   # Hermitian PSD of the given rank
+    msg = fcopy(g + 1e-17 * randn(rng, dtype, (chi, chi)))  # not exactly Hermitian, like a BP message
+    x = np.zeros((chi, chi), dtype=dtype, order="F")
+    xinv = np.zeros_like(x)
+    ev = np.zeros(chi)
+    hostlib.apply_host_gauge(code(dtype), ptr(msg), chi, ptr(x), ptr(xinv), ev.ctypes.data_as(P))
+    scale = np.abs(g).max()
+    assert np.allclose(x.conj().T @ x, g, atol=1e-13 * scale)
+    want_ev = np.linalg.eigvalsh(g)
+    assert np.allclose(np.sort(ev), want_ev, atol=1e-13 * scale)
+    proj = x @ xinv                                      # projector on the kept eigenvectors
+    assert np.allclose(proj, np.diag(np.diag(proj)), atol=1e-10)
+    assert int(round(np.trace(proj).real)) == rank
+    # same gauge-invariant content as the oracle's factorisation
+    xo, xinvo = A.gram_eigh_full_with_pinv(g)
+    assert np.allclose(xinv @ x, xinvo @ xo, atol=1e-9)  # projector on the support, as an operator on the ket leg
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole gates against the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def random_network(rng, dtype, adjacency, dims, d):
+    """adjacency: {v: [neighbours in slot order]}, dims: {frozenset(v, w): chi}.  -> oracle state + PSD environment."""
+    link = lambda v, w: ("l",) + tuple(sorted((v, w)))
+    state, env = {}, {}
+    for v, nb in adjacency.items():
+        shape = (d[v],) + tuple(dims[frozenset((v, w))] for w in nb)
+        names = (("s", v),) + tuple(link(v, w) for w in nb)
+        state[v] = (randn(rng, dtype, shape), names)
+        for w in nb:
+            c = dims[frozenset((v, w))]
+            f = randn(rng, dtype, (c, c)) + 1.5 * np.eye(c)
+            m = f.conj().T @ f
+            env[(w, v)] = (m / np.trace(m).real).astype(dtype)
+    return state, env
+
+
+def side_args(state, env, adjacency, v, other):
+    x, names = state[v]
+    nb = adjacency[v]
+    dims = np.array(x.shape[1:], dtype=np.int32)
+    slot = nb.index(other) if other is not None else -1
+    msgs = np.concatenate([fcopy(env[(w, v)]).ravel(order="F") for w in nb]) if nb else np.zeros(0, x.dtype)
+    return len(nb), x.shape[0], slot, dims, fcopy(x).ravel(order="F").copy(), np.ascontiguousarray(msgs)
+
+
+def bond_product(state, v1, v2):
+    """Gauge-invariant content of the pair: the two tensors contracted over their bond."""
+    t = A.contract(state[v1], state[v2])
+    names = sorted(t[1], key=repr)
+    return A.permute(t, names)
+
+
+GRID = {  # 2 x 3 grid, vertex -> neighbours in slot order
+    0: [1, 3], 1: [0, 2, 4], 2: [1, 5], 3: [0, 4], 4: [3, 1, 5], 5: [4, 2],
+}
+
+
+def grid_dims(chi_bond, chi_other):
+    dims = {}
+    for v, nb in GRID.items():
+        for w in nb:
+            dims[frozenset((v, w))] = chi_other
+    dims[frozenset((1, 4))] = chi_bond
+    dims[frozenset((0, 1))] = max(1, chi_other - 1)  # ragged external legs
+    return dims
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("chi_bond,chi_other,max_rank,normalize", [
+    (3, 2, 0, False), (3, 2, 2, False), (4, 3, 3, True), (2, 3, 1, True), (4, 1, 0, False), (1, 2, 0, False),
+])
+def test_two_site_gate_matches_oracle(hostlib, dtype, chi_bond, chi_other, max_rank, normalize):
+    rng = np.random.default_rng(100 * chi_bond + 10 * chi_other + max_rank)
+    d = {v: 2 for v in GRID}
+    d[4] = 3  # different physical dims on the two sides
+    state, env = random_network(rng, dtype, GRID, grid_dims(chi_bond, chi_other), d)
+    v1, v2 = 1, 4
+    o = randn(rng, dtype, (d[v1], d[v2], d[v1], d[v2]))
+    names = (("s", v1), ("s", v2))
+    # the device keeps the leg's dimension: max_rank = 0 means "truncate to chi_bond" (the fixed-chi simple update)
+    want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=max_rank or chi_bond, normalize=normalize)
+
+    z1, d1, s1, dims1, site1, msgs1 = side_args(state, env, GRID, v1, v2)
+    z2, d2, s2, dims2, site2, msgs2 = side_args(state, env, GRID, v2, v1)
+    op = fcopy(o).ravel(order="F").copy()
+    msg_out = np.zeros(chi_bond * chi_bond, dtype=dtype)
+    sv = np.zeros(chi_bond)
+    rc = hostlib.apply_host_two_site(code(dtype), z1, d1, s1, ptr(dims1), ptr(site1), ptr(msgs1), z2, d2, s2, ptr(dims2),
+                                     ptr(site2), ptr(msgs2), ptr(op), max_rank, int(normalize), ptr(msg_out),
+                                     sv.ctypes.data_as(P))
+    assert rc == 0
+    k = want_env[(v1, v2)].shape[0]
+    s_want = np.diag(want_env[(v1, v2)]).real
+    assert np.allclose(sv[:k], s_want, rtol=1e-10, atol=1e-13) and np.all(sv[k:] == 0)
+    m = msg_out.reshape(chi_bond, chi_bond, order="F")
+    assert np.allclose(m[:k, :k], want_env[(v1, v2)], rtol=1e-10, atol=1e-13)
+    assert np.all(m[k:, :] == 0) and np.all(m[:, k:] == 0)
+
+    got_state = dict(state)
+    got_state[v1] = (site1.reshape(state[v1][0].shape, order="F"), state[v1][1])
+    got_state[v2] = (site2.reshape(state[v2][0].shape, order="F"), state[v2][1])
+    # the kept rank is zero-padded up to the leg's dimension
+    b1 = got_state[v1][0].take(range(k, chi_bond), axis=1 + s1)
+    assert b1.size == 0 or np.all(b1 == 0)
+    got = bond_product(got_state, v1, v2)
+    want = bond_product(want_state, v1, v2)
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_two_site_gate_on_a_leaf_pair(hostlib, dtype):
+    """Both vertices have no external legs (a 2-site chain): rows = 1, no reflectors, no gauges."""
+    rng = np.random.default_rng(2)
+    adj = {0: [1], 1: [0]}
+    state, env = random_network(rng, dtype, adj, {frozenset((0, 1)): 3}, {0: 2, 1: 2})
+    o = randn(rng, dtype, (2, 2, 2, 2))
+    names = (("s", 0), ("s", 1))
+    want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=3)
+    a1, a2 = side_args(state, env, adj, 0, 1), side_args(state, env, adj, 1, 0)
+    msg_out, sv = np.zeros(9, dtype=dtype), np.zeros(3)
+    op = fcopy(o).ravel(order="F").copy()
+    hostlib.apply_host_two_site(code(dtype), a1[0], a1[1], a1[2], ptr(a1[3]), ptr(a1[4]), ptr(a1[5]), a2[0], a2[1], a2[2],
+                                ptr(a2[3]), ptr(a2[4]), ptr(a2[5]), ptr(op), 0, 0, ptr(msg_out), sv.ctypes.data_as(P))
+    got_state = {0: (a1[4].reshape(2, 3, order="F"), state[0][1]), 1: (a2[4].reshape(2, 3, order="F"), state[1][1])}
+    k = want_env[(0, 1)].shape[0]                      # min(chi, m, n) = 1: rank of a 1 x d by d x 1 ... bond matrix
+    assert np.allclose(sv[:k], np.diag(want_env[(0, 1)]).real, rtol=1e-12)
+    assert np.abs(bond_product(got_state, 0, 1) - bond_product(want_state, 0, 1)).max() < 1e-12
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("normalize", [False, True])
+def test_one_site_gate_matches_oracle(hostlib, dtype, normalize):
+    rng = np.random.default_rng(9)
+    d = {v: 3 for v in GRID}
+    state, env = random_network(rng, dtype, GRID, grid_dims(3, 2), d)
+    v = 4
+    o = randn(rng, dtype, (3, 3))
+    names = (("s", v),)
+    want_state, _ = A.apply_operator((o, names, names), state, env, normalize=normalize)
+    z, dv, _, dims, site, msgs = side_args(state, env, GRID, v, None)
+    op = fcopy(o).ravel(order="F").copy()
+    hostlib.apply_host_one_site(code(dtype), z, dv, ptr(dims), ptr(site), ptr(msgs), ptr(op), int(normalize))
+    got = site.reshape(state[v][0].shape, order="F")
+    want = A.permute(want_state[v], state[v][1])
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_two_site_gate_cfg5_shape(hostlib, dtype):
+    """The shape of BASELINE config 5's bulk (degree 4, chi = 16 would be 1 MiB per tensor: chi = 6 keeps the CPU test
+    quick) with a rank-deficient incoming message."""
+    rng = np.random.default_rng(77)
+    adj = {0: [1, 2, 3, 4], 1: [0, 5, 6, 7]}
+    for w in range(2, 8):
+        adj[w] = [0 if w < 5 else 1]
+    dims = {frozenset((v, w)): 6 for v, nb in adj.items() for w in nb}
+    d = {v: 2 for v in adj}
+    state, env = random_network(rng, dtype, adj, dims, d)
+    f = randn(rng, dtype, (4, 6))
+    env[(2, 0)] = (f.conj().T @ f).astype(dtype)       # rank 4 of 6: two gauge directions are dropped by the pinv
+    o = randn(rng, dtype, (2, 2, 2, 2))
+    names = (("s", 0), ("s", 1))
+    want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=6, normalize=True)
+    a1, a2 = side_args(state, env, adj, 0, 1), side_args(state, env, adj, 1, 0)
+    msg_out, sv = np.zeros(36, dtype=dtype), np.zeros(6)
+    op = fcopy(o).ravel(order="F").copy()
+    hostlib.apply_host_two_site(code(dtype), a1[0], a1[1], a1[2], ptr(a1[3]), ptr(a1[4]), ptr(a1[5]), a2[0], a2[1], a2[2],
+                                ptr(a2[3]), ptr(a2[4]), ptr(a2[5]), ptr(op), 6, 1, ptr(msg_out), sv.ctypes.data_as(P))
+    assert np.allclose(sv, np.diag(want_env[(0, 1)]).real, rtol=1e-9)
+    got_state = dict(state)
+    got_state[0] = (a1[4].reshape(state[0][0].shape, order="F"), state[0][1])
+    got_state[1] = (a2[4].reshape(state[1][0].shape, order="F"), state[1][1])
+    got, want = bond_product(got_state, 0, 1), bond_product(want_state, 0, 1)
+    assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
