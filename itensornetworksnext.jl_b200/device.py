@@ -155,7 +155,7 @@ class BPXContext:
         e = np.ascontiguousarray(edges, dtype=np.int64)
         flat = (np.concatenate([np.asarray(o, dtype=self.dtype).ravel(order="F") for o in ops]) if len(ops)
                 else np.empty(0, self.dtype))
-        dims = [int(self.link_dim[i]) for i in e]
+        dims = [int(self.link_dim[i]) if 0 <= i < self.ne else 0 for i in e]  # bad ids are reported by the library
         sv = np.zeros(max(1, sum(dims)), dtype=np.float64)
         self._check(self.lib.bpx_apply_two_site_gates(self.h, len(e), _ptr(e), _ptr(np.ascontiguousarray(flat)), int(max_rank),
                                                       int(bool(normalize)), _ptr(sv)))
