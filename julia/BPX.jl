@@ -232,6 +232,70 @@ function edge_scalars(alg::B200MessageUpdate, ::Type{E} = Float64) where {E}
     return out
 end
 
+# ---- gate application on the device (src/apply/apply_operators.jl:150-283) ---------------------------------------
+# Plug-in point: "abstract type ApplyOperatorAlgorithm" (:150) with `apply_operator!(algorithm, dest, operator, state, env)`
+# (:185-194) and `initialize_output` (:204-208); an instance passed as `apply_operator(op, state, env; alg = X)` reaches
+# `apply_operator(algorithm::ApplyOperatorAlgorithm, ...)` (:173-176) untouched (select_algorithm.jl:41-48).
+import ITensorNetworksNext: apply_operator!, initialize_output
+using ITensorNetworksNext: ApplyOperatorAlgorithm, normnetwork
+using ITensorBase: domainnames
+
+"""
+    B200ApplyGate(; trunc = nothing, normalize = false, bp = B200MessageUpdate())
+
+BP simple-update gate application (`BPApplyGate`, apply_operators.jl:180-283) on the B200 that `bp` is bound to: state
+and environment are uploaded once (`upload!`), every gate -- or, through `apply_layer!`, every layer of vertex-disjoint
+gates -- is one `ccall`, and tensors / messages are pulled back when the caller asks for them.
+"""
+Base.@kwdef struct B200ApplyGate <: ApplyOperatorAlgorithm
+    trunc::Union{Nothing, Int} = nothing
+    normalize::Bool = false
+    bp::B200MessageUpdate = B200MessageUpdate()
+end
+
+initialize_output(::typeof(apply_operator!), ::B200ApplyGate, operator, state, env) = copy(state), copy(env)
+
+# operator -> [o1, o2, i1, i2] (column-major; 1 = src, 2 = dst of the gate edge), outputs first like ITensorBase operators
+function lowered_operator(op, state, vs, ::Type{E}) where {E}
+    ins = [only(intersect(domainnames(op), sitenames(state, v))) for v in vs]
+    outs = [n for n in dimnames(op) if !(n in domainnames(op))]   # codomain names, same order as the domain
+    return vec(Array{E}(unnamed(op, (outs..., ins...))))
+end
+
+function apply_operator!(alg::B200ApplyGate, dest, op, state, env)
+    bp = alg.bp
+    bp.ctx == C_NULL && upload!(bp, normnetwork(state), env)      # state + env resident from here on
+    E = eltype(unnamed(first(values(env.messages)))) <: Complex ? ComplexF64 : Float64
+    vs = [v for v in vertices(state) if !isempty(intersect(domainnames(op), sitenames(state, v)))]
+    isempty(vs) && throw(ArgumentError("operator shares no indices with the tensor network"))
+    packed = lowered_operator(op, state, vs, E)
+    if length(vs) == 1
+        ids = Int64[bp.vertex_ids[only(vs)]]
+        GC.@preserve ids packed check(bp.ctx, ccall((:bpx_apply_one_site_gates, libbpx), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Cvoid}, Cint), bp.ctx, 1, ids, packed, alg.normalize))
+    elseif length(vs) == 2
+        ids = Int64[bp.edge_ids[NamedEdge(vs[1] => vs[2])]]
+        sv = zeros(Float64, 4096)
+        GC.@preserve ids packed sv check(bp.ctx, ccall((:bpx_apply_two_site_gates, libbpx), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}),
+            bp.ctx, 1, ids, packed, something(alg.trunc, 0), alg.normalize, sv))
+        pull_messages!(bp, env)                                    # the two diag(S) messages of the gate edge (:273-277)
+    else
+        throw(ArgumentError("$(length(vs))-site gate decomposition not implemented"))
+    end
+    for v in vs                                                    # `dest[v] = ...` (:243, :270-271)
+        old = state[v]
+        names = (sitenames(state, v)..., (only(linknames(state, NamedEdge(v => w))) for w in neighbors(state, v))...)
+        buf = Vector{E}(undef, length(unnamed(old)))
+        GC.@preserve buf check(bp.ctx, ccall((:bpx_get_site_tensor, libbpx), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+            bp.ctx, bp.vertex_ids[v], buf))
+        dest[v] = ITensor(reshape(buf, size(unnamed(old, names))), names)
+    end
+    return dest
+end
+# A whole circuit layer (vertex-disjoint gates) is ONE call: pass all edge ids / packed operators at once
+# (`bpx_apply_two_site_gates(ctx, n_gates, edges, ops, ...)`); see itensornetworksnext.jl_b200/apply.py `_apply_batch`.
+
 function Base.close(alg::B200MessageUpdate)
     alg.ctx == C_NULL || ccall((:bpx_destroy, libbpx), Cint, (Ptr{Cvoid},), alg.ctx)
     alg.ctx = C_NULL
