@@ -81,6 +81,54 @@ def main():
     save("ising_4x4_torus_jacobi", sites=q.tensors, messages0=q.messages, messages=np.stack(per_sweep), residual=np.array(res),
          log_z_exact=np.log(o.contract_all_sequential(p)))
 
+    apply_case()
+
+
+def apply_case():
+    """BP simple-update gate layer (src/apply/apply_operators.jl:246-283): a 3x3 ComplexF64 PEPS (chi = 3, d = 2) with the
+    messages of four synchronous BP sweeps as environment, one layer of three disjoint two-site gates truncated to rank 2
+    with S normalised, then one one-site gate.  Stored: inputs, kept singular values, and per gate the GAUGE-INVARIANT
+    content of the result (the two new tensors contracted over their bond, axes sorted by name) -- the tensors
+    themselves are only defined up to the phases of the singular vectors."""
+    from oracle import apply_oracle as A
+
+    p = problems.synthetic_peps(graphs.named_grid((3, 3)), 3, 2, np.complex128, seed=11, name="apply33")
+    ga = p.ga
+    op = o.make_problem(ga, p.tensors, "norm")
+    msgs = list(p.messages)
+    for _ in range(4):
+        msgs = o.sweep_jacobi(op, msgs)
+    state, env = apply_state(ga, p.tensors, msgs)
+    from itnn_b200.device import fill_randn
+    edges = [ga.edge_index[(0, 1)], ga.edge_index[(5, 4)], ga.edge_index[(6, 7)]]
+    ops = [fill_randn(11, 1000 + i, np.complex128, 16).reshape((2, 2, 2, 2), order="F") for i in range(len(edges))]
+    svs, pairs = [], []
+    for e, g_ in zip(edges, ops):
+        v1, v2 = ga.src[e], ga.dst[e]
+        names = (("s", v1), ("s", v2))
+        new_state, new_env = A.apply_operator((g_, names, names), state, env, trunc=2, normalize=True)
+        svs.append(np.diag(new_env[(v1, v2)]).real)
+        t = A.contract(new_state[v1], new_state[v2])
+        pairs.append(A.permute(t, sorted(t[1], key=repr)).ravel(order="F"))
+    one = fill_randn(11, 2000, np.complex128, 4).reshape((2, 2), order="F")
+    names = (("s", 8),)
+    one_state, _ = A.apply_operator((one, names, names), state, env, normalize=True)
+    save("apply_grid33_c128", sites=stack(p.tensors), messages=stack(msgs), edges=np.array(edges), ops=np.stack(ops),
+         max_rank=2, normalize=1, singular_values=np.stack(svs), pair_products=np.concatenate(pairs),
+         pair_sizes=np.array([len(x) for x in pairs]), one_site_vertex=8, one_site_op=one,
+         one_site_result=A.permute(one_state[8], state[8][1]).ravel(order="F"), chi=3, d=2, seed=11)
+
+
+def apply_state(ga, tensors, msgs):
+    """Canonical arrays -> the apply oracle's named state / environment (site name ("s", v), link name ("l", lo, hi))."""
+    link = lambda v, w: ("l", min(v, w), max(v, w))
+    state = {}
+    for v in range(ga.nv):
+        nb = [ga.dst[e] for e in range(ga.row_ptr[v], ga.row_ptr[v + 1])]
+        state[v] = (np.asarray(tensors[v]), (("s", v),) + tuple(link(v, w) for w in nb))
+    env = {(ga.src[e], ga.dst[e]): np.asarray(msgs[e]) for e in range(ga.ne)}
+    return state, env
+
 
 if __name__ == "__main__":
     main()

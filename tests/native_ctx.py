@@ -4,10 +4,27 @@ itensornetworksnext.jl_b200/apply.py (names -> canonical layout, bond padding / 
 against the reference's known answers without a GPU.  Only `-m "not gpu"` tests monkeypatch it in; the product always
 talks to libbpx.so (CUDA)."""
 import ctypes
+import os
+import subprocess
 
 import numpy as np
 
 P = ctypes.c_void_p
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "native", "apply_host.cu")
+HDR = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_apply.cuh")
+OUT = os.path.join(HERE, "native", "_build", "libapply_host.so")
+
+
+def build_hostlib() -> ctypes.CDLL:
+    """Compile tests/native/apply_host.cu (the device code of csrc/bpx_apply.cuh for the host) if stale; load it."""
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    stale = not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in (SRC, HDR))
+    if stale:
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+                        "-shared", "-o", OUT, SRC], check=True)
+    return ctypes.CDLL(OUT)
 
 
 def _ptr(a):

@@ -4,32 +4,21 @@ every stage -- one-sided Jacobi, Householder QR, gauges from messages, the whole
 with numpy / the apply_operator oracle (oracle/apply_oracle.py, which restates src/apply/apply_operators.jl:213-283).
 The CUDA launch of the same code is covered by the `gpu` tests in test_zz_gpu_apply.py."""
 import ctypes
-import os
-import subprocess
 
 import numpy as np
 import pytest
 
 from helpers import randn
+from native_ctx import build_hostlib
 from oracle import apply_oracle as A
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "native", "apply_host.cu")
-HDR = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_apply.cuh")
-OUT = os.path.join(HERE, "native", "_build", "libapply_host.so")
 DTYPES = [np.float64, np.complex128]
 P = ctypes.c_void_p
 
 
 @pytest.fixture(scope="module")
 def hostlib():
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    stale = not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in (SRC, HDR))
-    if stale:
-        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
-                        "-shared", "-o", OUT, SRC], check=True)
-    return ctypes.CDLL(OUT)
+    return build_hostlib()
 
 
 def ptr(a):

@@ -124,3 +124,94 @@ def test_gpu_reproduces_single_layer_fixtures():
                 res, _ = ctx.sweep(1)
                 assert rel(ctx.get_messages_flat(), f["messages"][k]) < TOL
                 assert abs(res - f["residual"][k]) < 1e-11
+
+
+# ---- gate application (src/apply/apply_operators.jl:246-283): fixture apply_grid33_c128 ----------------------
+def _apply_fixture():
+    from golden.make_golden import apply_state  # the committed generating script also defines the naming
+
+    f = load("apply_grid33_c128")
+    ga = graphs.graph_arrays(graphs.named_grid((3, 3)))
+    chi, d = int(f["chi"]), int(f["d"])
+    deg = np.diff(ga.row_ptr)
+    off = np.concatenate([[0], np.cumsum(d * chi ** deg)])
+    tensors = [f["sites"][off[v]:off[v + 1]].reshape((d,) + (chi,) * int(deg[v]), order="F") for v in range(ga.nv)]
+    msgs = [f["messages"][chi * chi * e:chi * chi * (e + 1)].reshape((chi, chi), order="F") for e in range(ga.ne)]
+    return f, ga, tensors, msgs, apply_state
+
+
+def _check_apply_result(f, ga, apply_state, new_tensors, new_msgs, svs):
+    from oracle import apply_oracle as A
+
+    k = int(f["max_rank"])
+    state, _ = apply_state(ga, new_tensors, new_msgs)
+    pair_off = np.concatenate([[0], np.cumsum(f["pair_sizes"])])
+    for i, e in enumerate(f["edges"]):
+        v1, v2 = ga.src[e], ga.dst[e]
+        assert np.allclose(svs[i][:k], f["singular_values"][i], rtol=1e-10) and np.all(svs[i][k:] == 0)
+        t = A.contract(state[v1], state[v2])
+        got = A.permute(t, sorted(t[1], key=repr)).ravel(order="F")
+        assert rel(got, f["pair_products"][pair_off[i]:pair_off[i + 1]]) < 1e-9
+        for ee in (int(e), ga.rev[e]):
+            assert np.allclose(np.diag(new_msgs[ee])[:k], f["singular_values"][i], rtol=1e-10)
+
+
+def test_host_compiled_device_code_reproduces_apply_fixture():
+    from native_ctx import HostHarnessContext, build_hostlib
+
+    f, ga, tensors, msgs, apply_state = _apply_fixture()
+    ctx = HostHarnessContext(build_hostlib())
+    ctx.set_graph(ga.src, ga.dst, ga.slot, ga.nv)
+    ctx.set_dims(np.complex128, "norm", [2] * ga.nv, [3] * ga.ne)
+    ctx.set_site_tensors(tensors)
+    ctx.set_messages(msgs)
+    svs = ctx.apply_two_site_gates([int(e) for e in f["edges"]], list(f["ops"]), max_rank=int(f["max_rank"]), normalize=True)
+    shapes = [t.shape for t in tensors]
+    new_tensors = [ctx.get_site_tensor(v).reshape(shapes[v], order="F") for v in range(ga.nv)]
+    new_msgs = [m.reshape((3, 3), order="F") for m in ctx.msgs]
+    _check_apply_result(f, ga, apply_state, new_tensors, new_msgs, svs)
+    ctx.set_site_tensors(tensors)
+    ctx.set_messages(msgs)
+    v = int(f["one_site_vertex"])
+    ctx.apply_one_site_gates([v], [f["one_site_op"]], normalize=True)
+    assert rel(ctx.get_site_tensor(v), f["one_site_result"]) < 1e-12
+
+
+def test_oracle_reproduces_apply_fixture(oracle):
+    """The fixture's environment is what four oracle sweeps give, and the apply oracle regenerates its outputs."""
+    from oracle import apply_oracle as A
+
+    f, ga, tensors, msgs, apply_state = _apply_fixture()
+    q = problems.synthetic_peps(graphs.named_grid((3, 3)), 3, 2, np.complex128, seed=int(f["seed"]))
+    assert np.array_equal(np.concatenate([t.ravel(order="F") for t in q.tensors]), f["sites"])
+    p = oracle.make_problem(ga, q.tensors, "norm")
+    m = list(q.messages)
+    for _ in range(4):
+        m = oracle.sweep_jacobi(p, m)
+    assert rel(np.concatenate([x.ravel(order="F") for x in m]), f["messages"]) < 1e-13
+    state, env = apply_state(ga, tensors, msgs)
+    for i, e in enumerate(f["edges"]):
+        names = (("s", ga.src[e]), ("s", ga.dst[e]))
+        _, new_env = A.apply_operator((f["ops"][i], names, names), state, env, trunc=int(f["max_rank"]), normalize=True)
+        assert np.allclose(np.diag(new_env[(ga.src[e], ga.dst[e])]).real, f["singular_values"][i], rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_apply_fixture():
+    f, ga, tensors, msgs, apply_state = _apply_fixture()
+    with B.BPXContext(0) as ctx:
+        ctx.set_graph(ga.src, ga.dst, ga.slot, ga.nv)
+        ctx.set_dims(np.complex128, "norm", [2] * ga.nv, [3] * ga.ne)
+        ctx.set_site_tensors(tensors)
+        ctx.set_messages(msgs)
+        svs = ctx.apply_two_site_gates([int(e) for e in f["edges"]], list(f["ops"]), max_rank=int(f["max_rank"]), normalize=True)
+        shapes = [t.shape for t in tensors]
+        new_tensors = [ctx.get_site_tensor(v).reshape(shapes[v], order="F") for v in range(ga.nv)]
+        new_msgs = ctx.get_messages()
+        _check_apply_result(f, ga, apply_state, new_tensors, new_msgs, svs)
+        # the one-site gate of the fixture on the ORIGINAL state
+        ctx.set_site_tensors(tensors)
+        ctx.set_messages(msgs)
+        v = int(f["one_site_vertex"])
+        ctx.apply_one_site_gates([v], [f["one_site_op"]], normalize=True)
+        assert rel(ctx.get_site_tensor(v), f["one_site_result"]) < 1e-10
