@@ -22,6 +22,7 @@ from .graphs import (
     NamedEdge, NamedGraph, forest_cover_edge_sequence, graph_arrays, heavy_hex_127, named_comb_tree,
     named_cycle_graph, named_grid, named_path_graph,
 )
+from .resident import ResidentState
 from .tensornetwork import (
     BraView, Index, ITensor, ITensorNetwork, KetView, NormNetwork, canonical_arrays, normnetwork, random_state,
     randn_itensor, tensornetwork, uniquename,

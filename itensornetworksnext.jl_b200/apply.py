@@ -114,7 +114,7 @@ def _lowered_operator(op: Operator, state: ITensorNetwork, vs: Sequence, dtype) 
 class _ApplySession:
     """state + env resident on one GPU in the canonical layout (optionally with one bond zero-padded)."""
 
-    def __init__(self, state: ITensorNetwork, env: MessageCache, device: int, pad: Optional[Tuple[int, int]] = None):
+    def __init__(self, state: ITensorNetwork, env: Optional[MessageCache], device: int, pad: Optional[Tuple[int, int]] = None):
         self.state = state
         self.nn = NormNetwork(state, {n: ("bra", n) for n, vs in state.dimname_vertices.items() if len(vs) == 2})
         cp = canonical_arrays(self.nn)
@@ -122,6 +122,9 @@ class _ApplySession:
         msgs = []
         for e in range(ga.ne):
             ne_ = ga.named_edge(e)
+            if env is None:  # all-ones messages (test/test_apply_operator.jl:72)
+                msgs.append(np.ones((cp.link_dim[e], cp.link_dim[e]), dtype=cp.dtype))
+                continue
             if ne_ not in env:
                 raise KeyError(f"no message on edge {ne_!r}")
             msgs.append(self._message_array(env[ne_], cp.ket_names[e], cp.dtype))

@@ -98,3 +98,67 @@ class HostHarnessContext:
 
     def close(self):
         pass
+
+    # -- everything below is NOT device code: BP sweeps and beliefs come from the numpy oracle, so that host-side
+    #    drivers that interleave gates and sweeps (ResidentState) can be exercised without a GPU --------------------
+    def _oracle_problem(self):
+        import __graft_entry__ as entry
+        from itnn_b200.graphs import GraphArrays
+
+        o = entry.import_oracle()
+        row_ptr = [0]
+        for v in range(self.nv):
+            row_ptr.append(row_ptr[-1] + len(self.out[v]))
+        ga = GraphArrays(vertices=list(range(self.nv)), vindex={v: v for v in range(self.nv)}, src=self.src, dst=self.dst,
+                         rev=self.rev, slot=self.slot, row_ptr=row_ptr,
+                         edge_index={(s, d): e for e, (s, d) in enumerate(zip(self.src, self.dst))})
+        shapes = [(self.phys[v],) + tuple(self.link_dim[e] for e in self.out[v]) for v in range(self.nv)]
+        tensors = [self.sites[v].reshape(shapes[v], order="F") for v in range(self.nv)]
+        return o, o.make_problem(ga, tensors, "norm")
+
+    def get_messages(self):
+        return [m.reshape((c, c), order="F").copy() for m, c in zip(self.msgs, self.link_dim)]
+
+    def _set(self, msgs):
+        self.msgs = [np.asarray(m, dtype=self.dtype).ravel(order="F").copy() for m in msgs]
+
+    def sweep(self, max_sweeps=1, tol=0.0, normalize=True):
+        o, p = self._oracle_problem()
+        msgs, res, done, self._history = self.get_messages(), float("inf"), 0, []
+        for _ in range(max_sweeps):
+            prev, msgs = msgs, o.sweep_jacobi(p, msgs, normalize)
+            res, done = o.iterate_diff(msgs, prev), done + 1
+            self._history.append(res)
+            if tol > 0 and res < tol:
+                break
+        self._set(msgs)
+        return res, done
+
+    def sweep_sequence(self, edge_seq, max_sweeps=1, tol=0.0, normalize=True):
+        o, p = self._oracle_problem()
+        msgs, res, done, self._history = self.get_messages(), float("inf"), 0, []
+        for _ in range(max_sweeps):
+            prev = [m.copy() for m in msgs]
+            msgs = o.sweep_sequential(p, msgs, list(edge_seq), normalize)
+            res, done = o.iterate_diff(msgs, prev), done + 1
+            self._history.append(res)
+            if tol > 0 and res < tol:
+                break
+        self._set(msgs)
+        return res, done
+
+    def residual_history(self, n=4096):
+        return np.array(getattr(self, "_history", []))
+
+    def vertex_scalars(self):
+        o, p = self._oracle_problem()
+        return np.array(o.vertex_scalars(p, self.get_messages()))
+
+    def edge_scalars(self):
+        o, p = self._oracle_problem()
+        return np.array(o.edge_scalars(p, self.get_messages()))
+
+    def vertex_expect_numerators(self, ops):
+        o, p = self._oracle_problem()
+        msgs = self.get_messages()
+        return np.array([o.vertex_scalar(p, msgs, v, np.asarray(ops[v])) for v in range(self.nv)])
