@@ -36,3 +36,29 @@ def test_shared_rng_is_deterministic_and_normal(pkg):
     assert abs((abs(z) ** 2).mean() - 1) < 0.03
     # prefix property: out[i] depends only on (seed, stream, i)
     assert np.array_equal(pkg.fill_randn(123, 7, np.float64, 10), a[:10])
+
+
+def _build_demo(tmp_path):
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "itensornetworksnext.jl_b200", "csrc")
+    exe = str(tmp_path / "bpx_demo")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-O2", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "bpx_demo.c"), "-o", exe, "-L" + libdir, "-lbpx", "-Wl,-rpath," + libdir, "-lm"],
+                   check=True)
+    return subprocess.run([exe], capture_output=True, text=True, timeout=300)
+
+
+def test_header_is_plain_c_and_a_c_client_links(pkg, tmp_path):
+    """include/bpx.h compiles as strict C99 (no C++ or torch types at the boundary); a C client links against libbpx.so
+    and, without a GPU, is told loudly that there is no CPU fallback."""
+    import torch
+
+    pkg._lib.load()
+    r = _build_demo(tmp_path)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr

@@ -194,24 +194,3 @@ def test_oracle_reproduces_apply_fixture(oracle):
         names = (("s", ga.src[e]), ("s", ga.dst[e]))
         _, new_env = A.apply_operator((f["ops"][i], names, names), state, env, trunc=int(f["max_rank"]), normalize=True)
         assert np.allclose(np.diag(new_env[(ga.src[e], ga.dst[e])]).real, f["singular_values"][i], rtol=1e-12)
-
-
-@pytest.mark.gpu
-def test_gpu_reproduces_apply_fixture():
-    f, ga, tensors, msgs, apply_state = _apply_fixture()
-    with B.BPXContext(0) as ctx:
-        ctx.set_graph(ga.src, ga.dst, ga.slot, ga.nv)
-        ctx.set_dims(np.complex128, "norm", [2] * ga.nv, [3] * ga.ne)
-        ctx.set_site_tensors(tensors)
-        ctx.set_messages(msgs)
-        svs = ctx.apply_two_site_gates([int(e) for e in f["edges"]], list(f["ops"]), max_rank=int(f["max_rank"]), normalize=True)
-        shapes = [t.shape for t in tensors]
-        new_tensors = [ctx.get_site_tensor(v).reshape(shapes[v], order="F") for v in range(ga.nv)]
-        new_msgs = ctx.get_messages()
-        _check_apply_result(f, ga, apply_state, new_tensors, new_msgs, svs)
-        # the one-site gate of the fixture on the ORIGINAL state
-        ctx.set_site_tensors(tensors)
-        ctx.set_messages(msgs)
-        v = int(f["one_site_vertex"])
-        ctx.apply_one_site_gates([v], [f["one_site_op"]], normalize=True)
-        assert rel(ctx.get_site_tensor(v), f["one_site_result"]) < 1e-10
