@@ -5,7 +5,12 @@ lowering to the C ABI of csrc/libbpx.so (include/bpx.h).  All arithmetic runs in
 """
 from . import _lib
 from ._lib import BPXError
+from . import algorithmsinterface as AI
+from . import algorithmsinterface as AIE  # the reference splits the same protocol over two modules
+from .algorithmsinterface import MethodError, StopWhenAny, StoppingCriterion
 from .beliefpropagation import (
+    BeliefPropagationAlgorithm, BeliefPropagationProblem, BeliefPropagationState, BeliefPropagationSweepAlgorithm,
+    BeliefPropagationSweepProblem, BeliefPropagationSweepState, DeviceMessageCache, device_iterate,
     ArgumentError, B200MessageUpdate, BeliefPropagationResult, MessageCache, MessageUpdateAlgorithm,
     SimpleMessageUpdate, StopAfterIteration, StopWhenConverged, beliefpropagation, bethe_free_energy,
     default_algorithm, default_beliefpropagation_edges, edge_scalar, edge_scalars, expect, identity_message,

@@ -25,6 +25,8 @@ from typing import Callable, Dict, Hashable, Iterable, List, Optional, Sequence
 import numpy as np
 
 from . import _lib
+from . import algorithmsinterface as AI
+from .algorithmsinterface import MethodError, StopAfterIteration, StopWhenAny, StopWhenConverged, StoppingCriterion
 from .device import BPXContext
 from .graphs import NamedEdge, forest_cover_edge_sequence, to_edge
 from .tensornetwork import CanonicalProblem, Index, ITensor, ITensorNetwork, NormNetwork, canonical_arrays
@@ -35,34 +37,8 @@ class ArgumentError(ValueError):
 
 
 # ---------------------------------------------------------------------------------------------------
-# stopping criteria (AlgorithmsInterface.StopAfterIteration, AIE.StopWhenConverged, `|`)
+# stopping criteria (AlgorithmsInterface.StopAfterIteration, AIE.StopWhenConverged, `|`): algorithmsinterface.py
 # ---------------------------------------------------------------------------------------------------
-class StoppingCriterion:
-    def __or__(self, other: "StoppingCriterion") -> "StopWhenAny":
-        return StopWhenAny([self, other])
-
-
-@dataclass
-class StopAfterIteration(StoppingCriterion):
-    maxiter: int
-
-
-@dataclass
-class StopWhenConverged(StoppingCriterion):
-    tol: float
-
-    def __post_init__(self):
-        self.tol = float(self.tol)  # `tol::Float64` (AIE.jl:63-65)
-
-
-@dataclass
-class StopWhenAny(StoppingCriterion):
-    criteria: List[StoppingCriterion]
-
-    def __or__(self, other):
-        return StopWhenAny(self.criteria + [other])
-
-
 def select_beliefpropagation_stopping_criterion(c=None, **kwargs) -> StoppingCriterion:
     """beliefpropagation.jl:16-55."""
     if isinstance(c, StoppingCriterion):
@@ -93,6 +69,10 @@ def select_beliefpropagation_stopping_criterion(c=None, **kwargs) -> StoppingCri
     return crit
 
 
+class _NotFlat(Exception):
+    """The criterion is not an OR of StopAfterIteration / StopWhenConverged: run the generic AI loop."""
+
+
 def _flatten_criterion(c: StoppingCriterion):
     """-> (maxiter or None, tol or None) of an OR-combination."""
     maxiter = tol = None
@@ -105,7 +85,7 @@ def _flatten_criterion(c: StoppingCriterion):
         elif isinstance(it, StopWhenConverged):
             m, t = None, it.tol
         else:
-            raise ArgumentError(f"unsupported stopping criterion {it!r}")
+            raise _NotFlat()
         if m is not None:
             maxiter = m if maxiter is None else min(maxiter, m)
         if t is not None:
@@ -246,6 +226,10 @@ class MessageCache:
         vs = set(vertices)
         return MessageCache({e: m for e, m in self._m.items() if e.src in vs and e.dst in vs})
 
+    def iterate_diff(self, other) -> float:
+        """`AIE.iterate_diff(::MessageCache, ::MessageCache)` (beliefpropagation.jl:261-267), on the device."""
+        return iterate_diff(self, other)
+
 
 def messagecache(f_or_pairs, edges=None) -> MessageCache:
     if edges is None:
@@ -374,9 +358,23 @@ def beliefpropagation(factors, messages, *, edges=None, stopping_criterion=None,
     cache = messages if isinstance(messages, MessageCache) else MessageCache(messages)
     alg = select_algorithm(message_update, message_update_algorithm, (cache, factors, None))
     criterion = select_beliefpropagation_stopping_criterion(stopping_criterion)
-    maxiter, tol = _flatten_criterion(criterion)
     if not isinstance(alg, (SimpleMessageUpdate, B200MessageUpdate)):
         raise TypeError(f"unsupported message update algorithm {type(alg).__name__}")
+    try:
+        maxiter, tol = _flatten_criterion(criterion)
+    except _NotFlat:
+        # a user-defined criterion: the reference's own construction (beliefpropagation.jl:75-91) over a device iterate,
+        # one C-ABI call per sweep, the criterion evaluated on the host before every sweep
+        if alg.schedule == "synchronous" and edges is not None:
+            raise ArgumentError("`edges` selects the sequential schedule; the synchronous sweep updates every edge")
+        if alg.schedule == "sequential" and edges is None:
+            edges = default_beliefpropagation_edges(factors)
+        n_steps = len(edges) if edges is not None else len(cache)
+        sub = BeliefPropagationSweepAlgorithm(StopAfterIteration(n_steps), alg)
+        algorithm = BeliefPropagationAlgorithm(edges, sub, criterion)
+        session = _Session(factors, alg.device, getattr(alg, "kernel", _lib.BPX_KERNEL_AUTO))
+        session.upload_messages(cache)
+        return AI.solve(BeliefPropagationProblem(factors), algorithm, iterate=DeviceMessageCache(session, cache))
     if maxiter is None:
         maxiter = 2 ** 31 - 1
     session = _Session(factors, alg.device, getattr(alg, "kernel", _lib.BPX_KERNEL_AUTO))
@@ -398,6 +396,167 @@ def beliefpropagation(factors, messages, *, edges=None, stopping_criterion=None,
         info.residual_history = list(session.ctx.residual_history())
         info.at_iteration = done if (tol is not None and done > 0 and res < tol) else -1
     return session.download_messages(cache)
+
+
+# ---------------------------------------------------------------------------------------------------
+# The AlgorithmsInterface layer of BP (beliefpropagation.jl:94-210): problem / algorithm / state types, so that a
+# caller can drive BP sweep by sweep with its own stopping criterion exactly as with the reference
+# (`AI.solve(problem, algorithm; iterate = cache)`, `AI.step!`, `AI.is_finished!`).
+# ---------------------------------------------------------------------------------------------------
+class BeliefPropagationProblem(AI.Problem):
+    def __init__(self, factors):
+        self.factors = factors
+
+
+class BeliefPropagationSweepProblem(AI.Problem):
+    def __init__(self, factors, edges):
+        self.factors = factors
+        self.edges = edges
+
+
+class BeliefPropagationSweepState(AI.State):
+    def __init__(self, iterate, iteration: int = 0, stopping_criterion_state=None):
+        self.iterate = iterate
+        self.iteration = iteration
+        self.stopping_criterion_state = stopping_criterion_state
+
+
+class BeliefPropagationSweepAlgorithm(AI.Algorithm):
+    """One sweep = `length(edges)` steps, each a `message_update!` of `edges[iteration]` (beliefpropagation.jl:160-210)."""
+
+    def __init__(self, stopping_criterion: StoppingCriterion, message_update_algorithm=None):
+        self.message_update_algorithm = SimpleMessageUpdate() if message_update_algorithm is None else message_update_algorithm
+        self.stopping_criterion = stopping_criterion
+
+    def initialize_state(self, problem, *, iterate, iteration: int = 0):
+        scs = self.stopping_criterion.initialize_state(problem, self, iterate=iterate)
+        return BeliefPropagationSweepState(iterate, iteration, scs)
+
+    def step_(self, problem, state):
+        edge = problem.edges[state.iteration - 1]  # Julia: problem.edges[state.iteration], 1-based
+        message_update(state.iterate, problem.factors, edge, self.message_update_algorithm)
+        return state
+
+
+class BeliefPropagationState(AI.NestedState):
+    def __init__(self, substate, iteration: int = 0, stopping_criterion_state=None):
+        self.substate = substate
+        self.iteration = iteration
+        self.stopping_criterion_state = stopping_criterion_state
+
+
+class BeliefPropagationAlgorithm(AI.NestedAlgorithm):
+    """Outer loop: one step = one sweep (beliefpropagation.jl:100-151).
+
+    The generic nested step runs the sweep edge by edge (one C-ABI call per `message_update!`).  When the iterate is a
+    `DeviceMessageCache` the whole sweep is ONE call instead -- the Python twin of the `AI.step!` specialisation in
+    julia/BPX.jl (INTEGRATION.md, "Why the dispatch hook sits one level above `message_update!`")."""
+
+    def __init__(self, edges, subalgorithm: BeliefPropagationSweepAlgorithm, stopping_criterion: StoppingCriterion):
+        self.edges = edges
+        self.subalgorithm = subalgorithm
+        self.stopping_criterion = stopping_criterion
+
+    def initialize_state(self, problem, *, iterate, iteration: int = 0):
+        subproblem = BeliefPropagationSweepProblem(problem.factors, self.edges)
+        substate = self.subalgorithm.initialize_state(subproblem, iterate=iterate)
+        scs = self.stopping_criterion.initialize_state(problem, self, iterate=iterate)
+        return BeliefPropagationState(substate, iteration, scs)
+
+    def initialize_subsolve(self, problem, state):
+        return BeliefPropagationSweepProblem(problem.factors, self.edges), self.subalgorithm, state.substate
+
+    def step_(self, problem, state):
+        it = state.iterate
+        if isinstance(it, DeviceMessageCache):
+            it.sweep(self.edges, self.subalgorithm.message_update_algorithm)
+            return state
+        return super().step_(problem, state)
+
+    def finalize_state_(self, problem, state):
+        it = state.iterate
+        return it.materialize() if isinstance(it, DeviceMessageCache) else it
+
+
+class _DeviceSnapshot:
+    """`copy(iterate)` of a device-resident iterate (StopWhenConverged copies it every outer iteration, AIE.jl:74, 96):
+    a marker, not data -- the difference to the next iterate is the residual fused into the sweep kernels."""
+
+    def __init__(self, owner: "DeviceMessageCache", version: int):
+        self.owner = owner
+        self.version = version
+
+    def copy(self):
+        return _DeviceSnapshot(self.owner, self.version)
+
+
+class DeviceMessageCache(MessageCache):
+    """A MessageCache whose messages live on the GPU between sweeps (SURVEY.md §8 b2 iii, variant B).
+
+    `sweep` runs one sweep in one C-ABI call; `copy()` hands out a marker; `iterate_diff(previous)` returns the residual
+    the update kernels fused into their epilogue (no second pass over the messages, no download).  Reading a message
+    (`cache[edge]`, `items()`, ...) downloads the set once per version; `materialize()` gives an ordinary MessageCache."""
+
+    def __init__(self, session: "_Session", like: MessageCache):
+        self._session = session
+        self._like = like
+        self._version = 0
+        self._host_version = -1
+        self._host: Dict[NamedEdge, object] = {}
+        self._last_residual = 0.0
+
+    # the base class reads and writes `self._m`
+    @property
+    def _m(self):
+        if self._host_version != self._version:
+            self._host = dict(self._session.download_messages(self._like)._m)
+            self._host_version = self._version
+        return self._host
+
+    @_m.setter
+    def _m(self, value):
+        self._host = value
+
+    def __setitem__(self, e, m):
+        raise ArgumentError("a DeviceMessageCache is updated by sweeps; use materialize() for a host copy to edit")
+
+    def sweep(self, edges, alg) -> float:
+        ctx, ga = self._session.ctx, self._session.cp.ga
+        schedule = getattr(alg, "schedule", "sequential")
+        if schedule == "synchronous":
+            res, _ = ctx.sweep(1, 0.0, alg.normalize)
+        else:
+            seq = [ga.edge_id(e) for e in (edges if edges is not None else default_beliefpropagation_edges(self._session.factors))]
+            res, _ = ctx.sweep_sequence(seq, 1, 0.0, alg.normalize)
+        self._version += 1
+        self._last_residual = res
+        return res
+
+    def copy(self):
+        return _DeviceSnapshot(self, self._version)
+
+    def iterate_diff(self, other) -> float:
+        if isinstance(other, _DeviceSnapshot) and other.owner is self:
+            if other.version == self._version:
+                return 0.0
+            if other.version == self._version - 1:
+                return self._last_residual
+            raise ArgumentError("only the residual of the LAST sweep is kept on the device")
+        ga = self._session.cp.ga
+        return self._session.ctx.iterate_diff([self._session._msg_array(e, other[ga.named_edge(e)]) for e in range(ga.ne)])
+
+    def materialize(self) -> MessageCache:
+        c = self._session.download_messages(self._like)
+        return c
+
+
+def device_iterate(factors, messages, message_update_algorithm=None) -> DeviceMessageCache:
+    """Upload factors and messages once and return the device-resident iterate to pass as `AI.solve(...; iterate=)`."""
+    cache = messages if isinstance(messages, MessageCache) else MessageCache(messages)
+    alg = select_algorithm(message_update, message_update_algorithm, (cache, factors, None))
+    session = _Session(factors, alg.device, getattr(alg, "kernel", _lib.BPX_KERNEL_AUTO))
+    session.upload_messages(cache)
+    return DeviceMessageCache(session, cache)
 
 
 def message_update(cache: MessageCache, factors, edge, alg=None, **kwargs) -> MessageCache:

@@ -162,3 +162,13 @@ class HostHarnessContext:
         o, p = self._oracle_problem()
         msgs = self.get_messages()
         return np.array([o.vertex_scalar(p, msgs, v, np.asarray(ops[v])) for v in range(self.nv)])
+
+    def iterate_diff(self, other):
+        o, _ = self._oracle_problem()
+        other = [np.asarray(m, dtype=self.dtype).reshape((c, c), order="F") for m, c in zip(other, self.link_dim)] \
+            if not isinstance(other, np.ndarray) or other.ndim != 1 else \
+            [other[sum(k * k for k in self.link_dim[:e]):][: c * c].reshape((c, c), order="F") for e, c in enumerate(self.link_dim)]
+        return o.iterate_diff(self.get_messages(), other)
+
+    def set_kernel_policy(self, kernel):
+        pass

@@ -35,3 +35,11 @@ def test_c_client_runs_on_the_gpu(pkg, tmp_path):
     r = _build_demo(tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "BP:" in r.stdout and "kept singular values" in r.stdout and "vertex scalar" in r.stdout
+
+
+@pytest.mark.parametrize("schedule", ["synchronous", "sequential"])
+def test_bp_ai_layer_gpu(schedule):
+    """AI.solve / manual stepping / user-defined criteria over a device-resident iterate (tests/test_algorithmsinterface.py)."""
+    from test_algorithmsinterface import check_bp_ai_layer
+
+    check_bp_ai_layer(schedule)
