@@ -27,7 +27,7 @@ from typing import Dict, Hashable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .beliefpropagation import AbstractAlgorithm, ArgumentError, MessageCache, select_algorithm as _select
+from .beliefpropagation import AbstractAlgorithm, ArgumentError, MessageCache
 from .device import BPXContext
 from .graphs import NamedEdge
 from .tensornetwork import Index, ITensor, ITensorNetwork, NormNetwork, canonical_arrays

@@ -17,7 +17,6 @@ back to the CPU, and the oracle under oracle/ is never imported.
 """
 from __future__ import annotations
 
-import cmath
 import math
 from dataclasses import dataclass, field
 from typing import Callable, Dict, Hashable, Iterable, List, Optional, Sequence
@@ -26,7 +25,7 @@ import numpy as np
 
 from . import _lib
 from . import algorithmsinterface as AI
-from .algorithmsinterface import MethodError, StopAfterIteration, StopWhenAny, StopWhenConverged, StoppingCriterion
+from .algorithmsinterface import StopAfterIteration, StopWhenAny, StopWhenConverged, StoppingCriterion
 from .device import BPXContext
 from .graphs import NamedEdge, forest_cover_edge_sequence, to_edge
 from .tensornetwork import CanonicalProblem, Index, ITensor, ITensorNetwork, NormNetwork, canonical_arrays
