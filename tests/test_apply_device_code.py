@@ -263,3 +263,44 @@ def test_two_site_gate_cfg5_shape(hostlib, dtype):
     got_state[1] = (a2[4].reshape(state[1][0].shape, order="F"), state[1][1])
     got, want = bond_product(got_state, 0, 1), bond_product(want_state, 0, 1)
     assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+
+
+def test_identity_gate_at_the_true_cfg5_shape(hostlib):
+    """BASELINE config 5's bulk shape for real: degree 4, chi = 16, d = 2 (1 MiB per tensor, 4096 x 32 matrix view).  The
+    identity gate with the full rank kept must leave the pair invariant (checked through random probes on the external
+    legs -- the full pair product would be 0.5 GB) and return the singular values of the gauged bond."""
+    rng = np.random.default_rng(16)
+    chi, d, z = 16, 2, 4
+    dims = np.full(z, chi, dtype=np.int32)
+    sites = [randn(rng, np.float64, (d,) + (chi,) * z) / 64.0 for _ in range(2)]
+    msgs = []
+    for _ in range(2):
+        ms = []
+        for _ in range(z):
+            f = randn(rng, np.float64, (chi, chi)) + 4.0 * np.eye(chi)
+            m = f.T @ f
+            ms.append((m / np.trace(m)).ravel(order="F"))
+        msgs.append(np.concatenate(ms))
+    flat = [fcopy(s).ravel(order="F").copy() for s in sites]
+    op = np.eye(d * d).reshape(d, d, d, d).ravel(order="F").copy()
+    msg_out, sv = np.zeros(chi * chi), np.zeros(chi)
+    slot1, slot2 = 1, 2
+    rc = hostlib.apply_host_two_site(0, z, d, slot1, ptr(dims), ptr(flat[0]), ptr(msgs[0]), z, d, slot2, ptr(dims), ptr(flat[1]),
+                                     ptr(msgs[1]), ptr(op), 0, 0, ptr(msg_out), sv.ctypes.data_as(P))
+    assert rc == 0 and np.all(sv > 0) and np.all(np.diff(sv) <= 0)
+    new = [f.reshape((d,) + (chi,) * z, order="F") for f in flat]
+
+    def probe(t, slot, vecs):
+        """Contract every external leg with a probe vector -> [s, bond]."""
+        out = t
+        for leg in reversed(range(z)):
+            if leg != slot:
+                out = np.tensordot(out, vecs[leg], axes=([1 + leg], [0]))
+        return out
+
+    v1 = [rng.standard_normal(chi) for _ in range(z)]
+    v2 = [rng.standard_normal(chi) for _ in range(z)]
+    before = probe(sites[0], slot1, v1) @ probe(sites[1], slot2, v2).T
+    after = probe(new[0], slot1, v1) @ probe(new[1], slot2, v2).T
+    assert np.abs(after - before).max() <= 1e-9 * np.abs(before).max()
+    assert np.allclose(np.diag(msg_out.reshape(chi, chi, order="F")), sv)
