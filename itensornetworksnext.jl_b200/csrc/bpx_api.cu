@@ -15,6 +15,7 @@
 #include "bpx_fast.cuh"
 #include "bpx_halo.cuh"
 #include "bpx_apply.cuh"
+#include "bpx_apply2.cuh"
 
 using namespace bpx;
 
@@ -1404,10 +1405,19 @@ static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const v
   size_t free_b = 0, total_b = 0;
   BPX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   const int64_t budget = (int64_t)std::max<size_t>(std::min<size_t>(free_b / 2, (size_t)8 << 30), (size_t)1 << 20) / ctx->esize;
+  // OPT-IN version 2 of the two-site kernel (bpx_apply2.cuh: gauging and TSQR staged through shared memory); the
+  // default stays version 1 until version 2 has been run and measured on a B200
+  const char* v2env = getenv("BPX_APPLY_V2");
+  bool v2 = v2env && atoi(v2env) != 0 && needs_ws;
+  const int64_t smem_elems = ((int64_t)ctx->max_smem_optin - 2048) / ctx->esize;
+  for (int64_t g = 0; v2 && g < ng; ++g)
+    v2 = gates[g].nsides == 2 && applyk2::block_rows(gates[g].s[0], smem_elems) > 0 &&
+         applyk2::block_rows(gates[g].s[1], smem_elems) > 0;
   std::vector<int64_t> chunk_begin{0};
   int64_t cur_total = 0, max_total = 0;
   for (int64_t g = 0; g < ng; ++g) {
-    const int64_t need = needs_ws ? applyk::layout_of(gates[g]).total + 2 : 2;  // plain one-site gates work in place
+    // plain one-site gates work in place
+    const int64_t need = !needs_ws ? 2 : (v2 ? applyk2::layout2_of(gates[g], smem_elems).total : applyk::layout_of(gates[g]).total) + 2;
     if (cur_total > 0 && cur_total + need > budget) {
       chunk_begin.push_back(g);
       cur_total = 0;
@@ -1438,7 +1448,19 @@ static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const v
       a.sv_stride = sv_stride;
       a.normalize = normalize;
       const int grid = (int)std::min<int64_t>(a.n_gates, (int64_t)ctx->num_sms * 8);
-      if (ctx->dtype == BPX_F64)
+      if (v2) {
+        applyk2::ApplyArgs2 a2;
+        a2.base = a;
+        a2.smem_elems = smem_elems;
+        const int bytes = (int)(smem_elems * ctx->esize);
+        if (ctx->dtype == BPX_F64) {
+          if ((rc = set_smem(ctx, applyk2::bp_apply_gates_v2<double>, bytes))) break;
+          applyk2::bp_apply_gates_v2<double><<<grid, applyk::NT, bytes, ctx->stream>>>(a2);
+        } else {
+          if ((rc = set_smem(ctx, applyk2::bp_apply_gates_v2<c64>, bytes))) break;
+          applyk2::bp_apply_gates_v2<c64><<<grid, applyk::NT, bytes, ctx->stream>>>(a2);
+        }
+      } else if (ctx->dtype == BPX_F64)
         applyk::bp_apply_gates<double><<<grid, applyk::NT, 0, ctx->stream>>>(a);
       else
         applyk::bp_apply_gates<c64><<<grid, applyk::NT, 0, ctx->stream>>>(a);

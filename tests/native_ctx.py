@@ -13,13 +13,14 @@ P = ctypes.c_void_p
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "native", "apply_host.cu")
 HDR = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_apply.cuh")
+HDR2 = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_apply2.cuh")
 OUT = os.path.join(HERE, "native", "_build", "libapply_host.so")
 
 
 def build_hostlib() -> ctypes.CDLL:
     """Compile tests/native/apply_host.cu (the device code of csrc/bpx_apply.cuh for the host) if stale; load it."""
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    stale = not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in (SRC, HDR))
+    stale = not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in (SRC, HDR, HDR2))
     if stale:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
@@ -32,9 +33,10 @@ def _ptr(a):
 
 
 class HostHarnessContext:
-    def __init__(self, hostlib, device=0):
+    def __init__(self, hostlib, device=0, v2_block_rows=None):
         self.lib = hostlib
         self.calls = []  # (kind, number of gates) per device call -- lets tests see the batching
+        self.v2_block_rows = v2_block_rows  # None: csrc/bpx_apply.cuh; an int: csrc/bpx_apply2.cuh with TSQR blocks of that many rows
 
     def set_graph(self, src, dst, slot, nv):
         self.src, self.dst, self.slot, self.nv = list(src), list(dst), list(slot), int(nv)
@@ -77,9 +79,18 @@ class HostHarnessContext:
             chi = self.link_dim[e]
             o = np.asarray(op, dtype=self.dtype).ravel(order="F").copy()
             msg_out, sv = np.zeros(chi * chi, dtype=self.dtype), np.zeros(chi)
-            rc = self.lib.apply_host_two_site(code, z1, d1, self.slot[e], _ptr(dims1), _ptr(self.sites[v1]), _ptr(m1), z2, d2,
-                                              self.slot[r], _ptr(dims2), _ptr(self.sites[v2]), _ptr(m2), _ptr(o),
-                                              int(max_rank), int(bool(normalize)), _ptr(msg_out), sv.ctypes.data_as(P))
+            args = (code, z1, d1, self.slot[e], _ptr(dims1), _ptr(self.sites[v1]), _ptr(m1), z2, d2, self.slot[r], _ptr(dims2),
+                    _ptr(self.sites[v2]), _ptr(m2), _ptr(o), int(max_rank), int(bool(normalize)), _ptr(msg_out),
+                    sv.ctypes.data_as(P))
+            if self.v2_block_rows is None:
+                rc = self.lib.apply_host_two_site(*args)
+            else:
+                need = 0
+                for dims, slot, d in ((dims1, self.slot[e], d1), (dims2, self.slot[r], d2)):
+                    rows = int(np.prod([dims[i] for i in range(len(dims)) if i != slot], dtype=np.int64))
+                    cols = d * int(dims[slot])
+                    need = max(need, 2 * rows, cols * cols + 2 * cols * (cols + self.v2_block_rows))
+                rc = self.lib.apply_host_two_site_v2(*args, ctypes.c_int64(need))
             assert rc == 0
             self.msgs[e], self.msgs[r] = msg_out, msg_out.copy()
             out.append(sv)

@@ -106,6 +106,29 @@ def test_gauge_from_message(hostlib, dtype, chi, rank):
     assert np.allclose(xinv @ x, xinvo @ xo, atol=1e-9)  # projector on the support, as an operator on the ket leg
 
 
+def smem_for(sides, rb):
+    """Emulated shared-memory budget (elements) that gives version 2 TSQR row blocks of `rb` (None: version 1)."""
+    need = 0
+    for z, d, slot, dims in sides:
+        rows = int(np.prod([dims[i] for i in range(z) if i != slot], dtype=np.int64))
+        cols = d * int(dims[slot])
+        need = max(need, 2 * rows, cols * cols + 2 * cols * (cols + rb))
+    return need
+
+
+def two_site(hostlib, variant, dtype, a1, a2, op, max_rank, normalize, msg_out, sv):
+    """variant: "v1" (csrc/bpx_apply.cuh) or ("v2", rb) (csrc/bpx_apply2.cuh with row blocks of rb)."""
+    args = (code(dtype), a1[0], a1[1], a1[2], ptr(a1[3]), ptr(a1[4]), ptr(a1[5]), a2[0], a2[1], a2[2], ptr(a2[3]), ptr(a2[4]),
+            ptr(a2[5]), ptr(op), int(max_rank), int(normalize), ptr(msg_out), sv.ctypes.data_as(P))
+    if variant == "v1":
+        return hostlib.apply_host_two_site(*args)
+    smem = smem_for([(a[0], a[1], a[2], a[3]) for a in (a1, a2)], variant[1])
+    return hostlib.apply_host_two_site_v2(*args, ctypes.c_int64(smem))
+
+
+VARIANTS = ["v1", ("v2", 1), ("v2", 3), ("v2", 8), ("v2", 4096)]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # whole gates against the oracle
 # ---------------------------------------------------------------------------------------------------------------
@@ -156,11 +179,12 @@ def grid_dims(chi_bond, chi_other):
     return dims
 
 
+@pytest.mark.parametrize("variant", VARIANTS, ids=str)
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("chi_bond,chi_other,max_rank,normalize", [
     (3, 2, 0, False), (3, 2, 2, False), (4, 3, 3, True), (2, 3, 1, True), (4, 1, 0, False), (1, 2, 0, False),
 ])
-def test_two_site_gate_matches_oracle(hostlib, dtype, chi_bond, chi_other, max_rank, normalize):
+def test_two_site_gate_matches_oracle(hostlib, variant, dtype, chi_bond, chi_other, max_rank, normalize):
     rng = np.random.default_rng(100 * chi_bond + 10 * chi_other + max_rank)
     d = {v: 2 for v in GRID}
     d[4] = 3  # different physical dims on the two sides
@@ -171,14 +195,13 @@ def test_two_site_gate_matches_oracle(hostlib, dtype, chi_bond, chi_other, max_r
     # the device keeps the leg's dimension: max_rank = 0 means "truncate to chi_bond" (the fixed-chi simple update)
     want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=max_rank or chi_bond, normalize=normalize)
 
-    z1, d1, s1, dims1, site1, msgs1 = side_args(state, env, GRID, v1, v2)
-    z2, d2, s2, dims2, site2, msgs2 = side_args(state, env, GRID, v2, v1)
+    a1 = side_args(state, env, GRID, v1, v2)
+    a2 = side_args(state, env, GRID, v2, v1)
+    (z1, d1, s1, dims1, site1, msgs1), (z2, d2, s2, dims2, site2, msgs2) = a1, a2
     op = fcopy(o).ravel(order="F").copy()
     msg_out = np.zeros(chi_bond * chi_bond, dtype=dtype)
     sv = np.zeros(chi_bond)
-    rc = hostlib.apply_host_two_site(code(dtype), z1, d1, s1, ptr(dims1), ptr(site1), ptr(msgs1), z2, d2, s2, ptr(dims2),
-                                     ptr(site2), ptr(msgs2), ptr(op), max_rank, int(normalize), ptr(msg_out),
-                                     sv.ctypes.data_as(P))
+    rc = two_site(hostlib, variant, dtype, a1, a2, op, max_rank, normalize, msg_out, sv)
     assert rc == 0
     k = want_env[(v1, v2)].shape[0]
     s_want = np.diag(want_env[(v1, v2)]).real
@@ -198,8 +221,9 @@ def test_two_site_gate_matches_oracle(hostlib, dtype, chi_bond, chi_other, max_r
     assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("variant", ["v1", ("v2", 1), ("v2", 64)], ids=str)
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_two_site_gate_on_a_leaf_pair(hostlib, dtype):
+def test_two_site_gate_on_a_leaf_pair(hostlib, variant, dtype):
     """Both vertices have no external legs (a 2-site chain): rows = 1, no reflectors, no gauges."""
     rng = np.random.default_rng(2)
     adj = {0: [1], 1: [0]}
@@ -210,8 +234,7 @@ def test_two_site_gate_on_a_leaf_pair(hostlib, dtype):
     a1, a2 = side_args(state, env, adj, 0, 1), side_args(state, env, adj, 1, 0)
     msg_out, sv = np.zeros(9, dtype=dtype), np.zeros(3)
     op = fcopy(o).ravel(order="F").copy()
-    hostlib.apply_host_two_site(code(dtype), a1[0], a1[1], a1[2], ptr(a1[3]), ptr(a1[4]), ptr(a1[5]), a2[0], a2[1], a2[2],
-                                ptr(a2[3]), ptr(a2[4]), ptr(a2[5]), ptr(op), 0, 0, ptr(msg_out), sv.ctypes.data_as(P))
+    assert two_site(hostlib, variant, dtype, a1, a2, op, 0, 0, msg_out, sv) == 0
     got_state = {0: (a1[4].reshape(2, 3, order="F"), state[0][1]), 1: (a2[4].reshape(2, 3, order="F"), state[1][1])}
     k = want_env[(0, 1)].shape[0]                      # min(chi, m, n) = 1: rank of a 1 x d by d x 1 ... bond matrix
     assert np.allclose(sv[:k], np.diag(want_env[(0, 1)]).real, rtol=1e-12)
@@ -236,8 +259,9 @@ def test_one_site_gate_matches_oracle(hostlib, dtype, normalize):
     assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("variant", ["v1", ("v2", 5), ("v2", 32), ("v2", 100000)], ids=str)
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_two_site_gate_cfg5_shape(hostlib, dtype):
+def test_two_site_gate_cfg5_shape(hostlib, variant, dtype):
     """The shape of BASELINE config 5's bulk (degree 4, chi = 16 would be 1 MiB per tensor: chi = 6 keeps the CPU test
     quick) with a rank-deficient incoming message."""
     rng = np.random.default_rng(77)
@@ -255,8 +279,7 @@ def test_two_site_gate_cfg5_shape(hostlib, dtype):
     a1, a2 = side_args(state, env, adj, 0, 1), side_args(state, env, adj, 1, 0)
     msg_out, sv = np.zeros(36, dtype=dtype), np.zeros(6)
     op = fcopy(o).ravel(order="F").copy()
-    hostlib.apply_host_two_site(code(dtype), a1[0], a1[1], a1[2], ptr(a1[3]), ptr(a1[4]), ptr(a1[5]), a2[0], a2[1], a2[2],
-                                ptr(a2[3]), ptr(a2[4]), ptr(a2[5]), ptr(op), 6, 1, ptr(msg_out), sv.ctypes.data_as(P))
+    assert two_site(hostlib, variant, dtype, a1, a2, op, 6, 1, msg_out, sv) == 0
     assert np.allclose(sv, np.diag(want_env[(0, 1)]).real, rtol=1e-9)
     got_state = dict(state)
     got_state[0] = (a1[4].reshape(state[0][0].shape, order="F"), state[0][1])
@@ -265,7 +288,8 @@ def test_two_site_gate_cfg5_shape(hostlib, dtype):
     assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
 
 
-def test_identity_gate_at_the_true_cfg5_shape(hostlib):
+@pytest.mark.parametrize("variant", ["v1", ("v2", 224), ("v2", 96)], ids=str)
+def test_identity_gate_at_the_true_cfg5_shape(hostlib, variant):
     """BASELINE config 5's bulk shape for real: degree 4, chi = 16, d = 2 (1 MiB per tensor, 4096 x 32 matrix view).  The
     identity gate with the full rank kept must leave the pair invariant (checked through random probes on the external
     legs -- the full pair product would be 0.5 GB) and return the singular values of the gauged bond."""
@@ -285,8 +309,9 @@ def test_identity_gate_at_the_true_cfg5_shape(hostlib):
     op = np.eye(d * d).reshape(d, d, d, d).ravel(order="F").copy()
     msg_out, sv = np.zeros(chi * chi), np.zeros(chi)
     slot1, slot2 = 1, 2
-    rc = hostlib.apply_host_two_site(0, z, d, slot1, ptr(dims), ptr(flat[0]), ptr(msgs[0]), z, d, slot2, ptr(dims), ptr(flat[1]),
-                                     ptr(msgs[1]), ptr(op), 0, 0, ptr(msg_out), sv.ctypes.data_as(P))
+    a1 = (z, d, slot1, dims, flat[0], msgs[0])
+    a2 = (z, d, slot2, dims, flat[1], msgs[1])
+    rc = two_site(hostlib, variant, np.float64, a1, a2, op, 0, 0, msg_out, sv)
     assert rc == 0 and np.all(sv > 0) and np.all(np.diff(sv) <= 0)
     new = [f.reshape((d,) + (chi,) * z, order="F") for f in flat]
 

@@ -55,12 +55,12 @@ def mirror_apply_operators(ops, state, env, **kwargs):
     return from_network(new_net), from_cache(new_net, new_cache)
 
 
-@pytest.fixture
-def host_ctx(monkeypatch, hostlib):  # noqa: F811
+@pytest.fixture(params=[None, 2, 64], ids=["v1", "v2-rb2", "v2-rb64"])
+def host_ctx(monkeypatch, hostlib, request):  # noqa: F811
     made = []
 
     def factory(device=0):
-        c = HostHarnessContext(hostlib, device)
+        c = HostHarnessContext(hostlib, device, v2_block_rows=request.param)
         made.append(c)
         return c
 
