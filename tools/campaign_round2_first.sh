@@ -14,6 +14,9 @@ timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $O/r2a_bench
 timeout 300 python tools/bench_apply.py --lattice 32 32 --chi 8 --layers 8 > $O/r2a_apply_32x32_chi8.json 2> $O/r2a_apply_32x32_chi8.err
 timeout 300 python tools/bench_apply.py --lattice 32 32 --chi 8 --dtype c128 --layers 8 > $O/r2a_apply_32x32_chi8_c128.json 2> $O/r2a_apply_32x32_chi8_c128.err
 timeout 600 python tools/bench_apply.py --lattice 16 16 --chi 16 --layers 4 --oracle-gates 2 > $O/r2a_apply_16x16_chi16.json 2> $O/r2a_apply_16x16_chi16.err
+# 3b. the opt-in version 2 of the kernel (bpx_apply2.cuh), same workloads
+BPX_APPLY_V2=1 timeout 300 python tools/bench_apply.py --lattice 32 32 --chi 8 --layers 8 --oracle-gates 0 > $O/r2a_apply_v2_32x32_chi8.json 2> $O/r2a_apply_v2_32x32_chi8.err
+BPX_APPLY_V2=1 timeout 600 python tools/bench_apply.py --lattice 16 16 --chi 16 --layers 4 --oracle-gates 0 > $O/r2a_apply_v2_16x16_chi16.json 2> $O/r2a_apply_v2_16x16_chi16.err
 # 4. launch list + one full ncu capture of bp_apply_gates on the cfg2-shaped layer
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/r2a_launches_apply.csv \
   python tools/bench_apply.py --lattice 32 32 --chi 8 --layers 2 --oracle-gates 0 > $O/r2a_apply_under_ncu.log 2>&1
@@ -24,3 +27,5 @@ python tools/ncu_summary.py $O/r2a_apply_gates_chi8.raw.csv $O/r2a_apply_gates_c
 cat $O/r2a_pytest_gpu.txt
 tail -c 600 $O/r2a_apply_32x32_chi8.json; echo
 tail -c 600 $O/r2a_apply_16x16_chi16.json; echo
+tail -c 400 $O/r2a_apply_v2_32x32_chi8.json; echo
+tail -c 400 $O/r2a_apply_v2_16x16_chi16.json; echo
