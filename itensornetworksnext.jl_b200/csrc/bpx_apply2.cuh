@@ -90,6 +90,58 @@ __host__ __device__ __forceinline__ int64_t join_index(const Side& sd, int64_t r
   return s + sd.d * idx;
 }
 
+// jacobi_cols with B (m x n) and V (n x n) staged through shared memory when they fit: every rotation step of the
+// round-robin schedule is a dependent round trip to its operands, a few hundred ns in global memory, tens in shared
+template <typename T>
+__host__ __device__ void jacobi_cols_staged(const Team& tm, T* B, int m, int n, T* V, int* flag, T* smem, int64_t smem_elems) {
+  const int64_t nb = (int64_t)m * n, nv = (int64_t)n * n;
+  if (nb + nv > smem_elems) {
+    jacobi_cols<T>(tm, B, m, n, V, flag);
+    return;
+  }
+  T* sb = smem;
+  T* sv = smem + nb;
+  for (int64_t i = tm.tid(); i < nb; i += tm.nt()) sb[i] = B[i];
+  tm.sync();
+  jacobi_cols<T>(tm, sb, m, n, sv, flag);
+  for (int64_t i = tm.tid(); i < nb; i += tm.nt()) B[i] = sb[i];
+  for (int64_t i = tm.tid(); i < nv; i += tm.nt()) V[i] = sv[i];
+  tm.sync();
+}
+
+// gauge_from_message of version 1 with the eigen-decomposition staged through shared memory (same arithmetic)
+template <typename T>
+__host__ __device__ void gauge_from_message_staged(const Team& tm, const T* msg, int chi, T* bx, T* vx, double* ev, int* flag,
+                                                   T* smem, int64_t smem_elems) {
+  using E = Elem<T>;
+  for (int i = tm.tid(); i < chi * chi; i += tm.nt()) {
+    const int r = i % chi, c = i / chi;
+    bx[i] = scal(E::add(msg[r + c * chi], E::conj(msg[c + r * chi])), 0.5);  // Hermitian part
+  }
+  tm.sync();
+  jacobi_cols_staged<T>(tm, bx, chi, chi, vx, flag, smem, smem_elems);
+  for (int j = tm.tid(); j < chi; j += tm.nt()) {
+    T acc = E::zero();
+    for (int r = 0; r < chi; ++r) acc = E::fma(E::conj(vx[r + j * chi]), bx[r + j * chi], acc);
+    ev[j] = real_of(acc);
+  }
+  tm.sync();
+  double dmax = 0.0;
+  for (int j = 0; j < chi; ++j) dmax = ev[j] > dmax ? ev[j] : dmax;
+  const double cut = EPS * chi * dmax;
+  for (int i = tm.tid(); i < chi * chi; i += tm.nt()) {
+    const int g = i % chi, l = i / chi;
+    const double d = ev[g];
+    bx[i] = d > cut ? scal(E::conj(vx[l + g * chi]), sqrt(d)) : E::zero();
+  }
+  tm.sync();
+  for (int i = tm.tid(); i < chi * chi; i += tm.nt()) {
+    const double d = ev[i / chi];
+    vx[i] = d > cut ? scal(vx[i], 1.0 / sqrt(d)) : E::zero();
+  }
+  tm.sync();
+}
+
 // every external leg of one column multiplied by its gauge matrix, in a shared-memory ping-pong; `which` = 0: X, 1: X^-1.
 // Returns the buffer (c0 or c1) that holds the result.
 template <typename T>
@@ -112,13 +164,13 @@ __host__ __device__ T* gauge_column(const Team& tm, const Side& sd, T* c0, T* c1
 // Phase 1: gauges from the messages, then P[:, c] = (X_1 x X_2 x ...) A[:, c] column by column
 template <typename T>
 __host__ __device__ void gauged_matrix(const Team& tm, const Side& sd, const T* a, const T* msgs, T* P, T* gz, T* smem,
-                                       int* flag) {
+                                       int64_t smem_elems, int* flag) {
   T* g = gz;
   for (int i = 0; i < sd.z; ++i) {
     if (i == sd.bond_slot) continue;
     const int chi = sd.dim[i];
-    gauge_from_message<T>(tm, msgs + sd.in_msg[i], chi, g, g + (int64_t)chi * chi,
-                          reinterpret_cast<double*>(g + 2 * (int64_t)chi * chi), flag);
+    gauge_from_message_staged<T>(tm, msgs + sd.in_msg[i], chi, g, g + (int64_t)chi * chi,
+                                 reinterpret_cast<double*>(g + 2 * (int64_t)chi * chi), flag, smem, smem_elems);
     g += 2 * (int64_t)chi * chi + chi;
   }
   T* c0 = smem;
@@ -239,7 +291,7 @@ __host__ __device__ void run_two_site_v2(const Team& tm, const GateDesc& gd, T* 
   T* w = ws + gd.ws_off;
   for (int a = 0; a < 2; ++a) {
     const Side& sd = gd.s[a];
-    gauged_matrix<T>(tm, sd, sites + sd.site_off, msgs, w + L.py[a], w + L.gauge[a], smem, flag);
+    gauged_matrix<T>(tm, sd, sites + sd.site_off, msgs, w + L.py[a], w + L.gauge[a], smem, smem_elems, flag);
     tsqr_factor<T>(tm, sd, w + L.py[a], L.rb[a], w + L.v[a], w + L.tau[a], w + L.r[a], smem);
   }
   // ---- the bond problem: identical to version 1 (theta, gate, Jacobi SVD, order, normalisation) ------------------
@@ -274,7 +326,7 @@ __host__ __device__ void run_two_site_v2(const Team& tm, const GateDesc& gd, T* 
   T* Vs = w + L.vs;
   double* sig = reinterpret_cast<double*>(w + L.sig);
   int32_t* order = reinterpret_cast<int32_t*>(w + L.order);
-  jacobi_cols<T>(tm, th1, m, n, Vs, flag);
+  jacobi_cols_staged<T>(tm, th1, m, n, Vs, flag, smem, smem_elems);
   for (int j = tm.tid(); j < n; j += tm.nt()) {
     double a = 0.0;
     for (int r = 0; r < m; ++r) a += E::abs2(th1[r + m * j]);
