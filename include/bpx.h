@@ -171,7 +171,9 @@ int bpx_vertex_expect_numerators(bpx_ctx* ctx, const void* ops_packed, void* out
  *   singular_values_out (may be NULL): link_dim[edges[g]] doubles per gate, packed in gate order (kept values, then 0).
  * One-site gates (:226-244): vertices[g]; ops_packed holds `op[o, i]` (d_v*d_v elements) per gate; normalize != 0
  *   divides the new tensor by the norm of its gauged version (all incoming messages).
- * BPX_ERR_INVALID if two gates of one call share a vertex; BPX_ERR_UNSUPPORTED on partitioned contexts. */
+ * BPX_ERR_INVALID if two gates of one call share a vertex.  Partitioned contexts: every rank passes the gates that lie
+ * inside its own block (all vertices owned by the rank; the call first waits for the cut-edge messages of the last
+ * sweep); a gate that touches a foreign vertex -- a gate across a cut edge -- is BPX_ERR_UNSUPPORTED. */
 int bpx_apply_two_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* edges, const void* ops_packed,
                              int max_rank, int normalize, double* singular_values_out);
 int bpx_apply_one_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* vertices, const void* ops_packed,

@@ -1481,8 +1481,18 @@ static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const v
 
 static int apply_common_checks(bpx_ctx* ctx, const char* name) {
   REQUIRE(ctx, ctx->mode == BPX_MODE_NORM, "%s: NORM mode only (the state is the ket layer of a norm network)", name);
-  if (ctx->nranks > 1) {
-    set_error(ctx, "%s: partitioned contexts are not supported yet (apply gates before bpx_set_partition)", name);
+  // partitioned contexts: every rank applies the gates that lie inside its own block (apply_owned_check); the incoming
+  // boundary messages of its vertices include cut-edge messages pushed by the peers during the last sweep
+  if (ctx->nranks > 1) return halo_gate(ctx);
+  return BPX_OK;
+}
+
+// a gate can run on this rank if all its vertices are resident here (gates across a cut edge need the peer's tensor)
+static int apply_owned_check(bpx_ctx* ctx, const char* name, int64_t g, int64_t v) {
+  if (ctx->nranks > 1 && ctx->owner[v] != ctx->rank) {
+    set_error(ctx, "%s: gate %lld touches vertex %lld, which rank %d owns: on a partitioned context every rank applies the "
+              "gates inside its own block; gates across a cut edge are not supported yet", name, (long long)g, (long long)v,
+              (int)ctx->owner[v]);
     return BPX_ERR_UNSUPPORTED;
   }
   return BPX_OK;
@@ -1507,6 +1517,7 @@ extern "C" int bpx_apply_two_site_gates(bpx_ctx* ctx, int64_t n_gates, const int
             "bpx_apply_two_site_gates: gate %lld shares a vertex with an earlier gate of the batch (gates of one call "
             "must be vertex-disjoint; apply overlapping gates in successive calls)", (long long)g);
     used[v1] = used[v2] = 1;
+    if ((rc = apply_owned_check(ctx, "bpx_apply_two_site_gates", g, v1)) || (rc = apply_owned_check(ctx, "bpx_apply_two_site_gates", g, v2))) return rc;
     applyk::GateDesc& gd = gates[g];
     memset(&gd, 0, sizeof(gd));
     gd.nsides = 2;
@@ -1558,6 +1569,7 @@ extern "C" int bpx_apply_one_site_gates(bpx_ctx* ctx, int64_t n_gates, const int
     REQUIRE(ctx, v >= 0 && v < ctx->nv, "bpx_apply_one_site_gates: gate %lld: vertex %lld out of range", (long long)g, (long long)v);
     REQUIRE(ctx, !used[v], "bpx_apply_one_site_gates: vertex %lld appears twice in the batch", (long long)v);
     used[v] = 1;
+    if ((rc = apply_owned_check(ctx, "bpx_apply_one_site_gates", g, v))) return rc;
     applyk::GateDesc& gd = gates[g];
     memset(&gd, 0, sizeof(gd));
     gd.nsides = 1;
