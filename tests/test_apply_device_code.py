@@ -183,6 +183,7 @@ def grid_dims(chi_bond, chi_other):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("chi_bond,chi_other,max_rank,normalize", [
     (3, 2, 0, False), (3, 2, 2, False), (4, 3, 3, True), (2, 3, 1, True), (4, 1, 0, False), (1, 2, 0, False),
+    (2, 4, 2, True), (2, 8, 2, False),
 ])
 def test_two_site_gate_matches_oracle(hostlib, variant, dtype, chi_bond, chi_other, max_rank, normalize):
     rng = np.random.default_rng(100 * chi_bond + 10 * chi_other + max_rank)
