@@ -156,7 +156,7 @@ __host__ __device__ __forceinline__ void mode_fibres_fixed(const Team& tm, const
     T v[CHI];
 #pragma unroll
     for (int l = 0; l < CHI; ++l) v[l] = in[base + l * st];
-#pragma unroll
+#pragma unroll 1  // unrolling g as well hoists CHI^2 loads of x: 10 KB of spills per thread at CHI = 16 complex
     for (int g = 0; g < CHI; ++g) {
       T acc = E::zero();
 #pragma unroll
