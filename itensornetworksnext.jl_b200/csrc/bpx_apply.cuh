@@ -35,6 +35,12 @@ constexpr int MAX_JACOBI_SWEEPS = 60;
 constexpr int NT = 256;  // threads per CTA on the device
 
 // ---- the team: a CTA on the device, one sequential lane on the host -----------------------------------------
+#ifndef BPX_HOST_TEAM_SYNC
+#define BPX_HOST_TEAM_SYNC()
+#endif
+#ifndef BPX_FLAG_SET
+#define BPX_FLAG_SET(p) (*(p) = 1)  // the race-check harness makes this a relaxed atomic store for ThreadSanitizer
+#endif
 struct Team {
   int lane, wid, nw;  // lane in the warp, warp in the team, warps in the team
   __host__ __device__ __forceinline__ int lanes() const {
@@ -49,6 +55,8 @@ struct Team {
   __host__ __device__ __forceinline__ void sync() const {
 #ifdef __CUDA_ARCH__
     __syncthreads();
+#else
+    BPX_HOST_TEAM_SYNC();  // empty unless a host test harness runs several "warps" as threads (tests/native/apply_race_check.cu)
 #endif
   }
   // warp-wide sums (every lane gets the result)
@@ -237,7 +245,7 @@ __host__ __device__ void jacobi_cols(const Team& tm, T* B, int m, int n, T* V, i
           vp[r] = sub(scal(x, c), scal(y, s));
           vq[r] = E::add(scal(x, s), scal(y, c));
         }
-        if (tm.lane == 0) *flag = 1;
+        if (tm.lane == 0) BPX_FLAG_SET(flag);  // several warps may store the same 1: benign
       }
       tm.sync();
     }

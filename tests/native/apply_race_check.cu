@@ -1,0 +1,167 @@
+// TEST INFRASTRUCTURE: the gate-application device code (csrc/bpx_apply.cuh, csrc/bpx_apply2.cuh) run on the host with one
+// THREAD PER WARP and a real barrier behind Team::sync(), under ThreadSanitizer.  What the single-lane host harness
+// (apply_host.cu) cannot see -- a missing barrier between phases executed by different warps -- shows up here as a data
+// race report or as a result that differs from the sequential run.  (Lanes inside a warp are not modelled: every
+// "warp" has one lane; intra-warp hazards are covered by __syncwarp() in the two places lanes exchange data.)
+//
+//   nvcc -O1 -g -std=c++17 -Xcompiler -fsanitize=thread -Xcompiler -pthread -o apply_race_check apply_race_check.cu
+//   ./apply_race_check        (exit 0: no race, multi-warp == sequential; TSAN reports make it exit 66)
+#include <pthread.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+static thread_local pthread_barrier_t* g_barrier = nullptr;
+static inline void host_team_barrier() {
+  if (g_barrier) pthread_barrier_wait(g_barrier);
+}
+#define BPX_HOST_TEAM_SYNC() host_team_barrier()
+#define BPX_FLAG_SET(p) __atomic_store_n((p), 1, __ATOMIC_RELAXED)
+
+#include "../../itensornetworksnext.jl_b200/csrc/bpx_apply2.cuh"
+
+using namespace bpx;
+using namespace bpx::applyk;
+
+static double urand(uint64_t& s) {
+  s = s * 6364136223846793005ull + 1442695040888963407ull;
+  return (double)((s >> 11) & ((1ull << 53) - 1)) / (double)(1ull << 53) - 0.5;
+}
+
+template <typename T>
+static T rnd(uint64_t& s);
+template <>
+double rnd<double>(uint64_t& s) { return urand(s); }
+template <>
+c64 rnd<c64>(uint64_t& s) { return make_c64(urand(s), urand(s)); }
+
+template <typename T>
+struct Problem {
+  GateDesc g;
+  std::vector<T> sites, msgs, op;
+};
+
+// two vertices of degree z with link dims chi (external) and chi_b (bond), Hermitian PSD messages
+template <typename T>
+static Problem<T> make_problem(int z, int chi, int chi_b, int d, uint64_t seed) {
+  Problem<T> p;
+  memset(&p.g, 0, sizeof(p.g));
+  p.g.nsides = 2;
+  p.g.chi_b = chi_b;
+  uint64_t s = seed;
+  for (int a = 0; a < 2; ++a) {
+    Side& sd = p.g.s[a];
+    sd.z = z;
+    sd.d = d;
+    sd.bond_slot = a == 0 ? 1 % z : 0;
+    for (int i = 0; i < z; ++i) {
+      sd.dim[i] = i == sd.bond_slot ? chi_b : chi;
+      sd.in_msg[i] = (int64_t)p.msgs.size();
+      const int c = sd.dim[i];
+      std::vector<T> f((size_t)c * c);
+      for (auto& x : f) x = rnd<T>(s);
+      for (int r = 0; r < c; ++r) f[r + c * r] = Elem<T>::add(f[r + c * r], from_real<T>(1.5));
+      for (int r = 0; r < c; ++r)       // M = F^H F
+        for (int q = 0; q < c; ++q) {
+          T acc = Elem<T>::zero();
+          for (int k = 0; k < c; ++k) acc = Elem<T>::fma(Elem<T>::conj(f[k + c * r]), f[k + c * q], acc);
+          p.msgs.push_back(acc);
+        }
+    }
+    finish_side(sd, chi_b);
+    sd.site_off = (int64_t)p.sites.size();
+    for (int64_t i = 0; i < sd.n; ++i) p.sites.push_back(rnd<T>(s));
+  }
+  p.g.msg12 = (int64_t)p.msgs.size();
+  p.g.msg21 = p.g.msg12 + (int64_t)chi_b * chi_b;
+  p.msgs.resize(p.msgs.size() + 2 * (size_t)chi_b * chi_b);
+  const int m = p.g.s[0].nref * d, n = p.g.s[1].nref * d;
+  p.g.k = chi_b < m ? (chi_b < n ? chi_b : n) : (m < n ? m : n);
+  for (int i = 0; i < d * d * d * d; ++i) p.op.push_back(rnd<T>(s));
+  return p;
+}
+
+// run one gate with `nw` warps (threads); version 2 when smem_elems > 0
+template <typename T>
+static void run(Problem<T> p, int nw, int64_t smem_elems, std::vector<T>& sites_out, std::vector<double>& sv) {
+  sv.assign(p.g.chi_b, 0.0);
+  const int64_t total = smem_elems > 0 ? applyk2::layout2_of(p.g, smem_elems).total : layout_of(p.g).total;
+  std::vector<T> ws((size_t)total + 2), smem((size_t)(smem_elems > 0 ? smem_elems : 1));
+  int flag = 0;
+  double ssum = 0.0;
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, nw);
+  auto body = [&](int w) {
+    g_barrier = nw > 1 ? &bar : nullptr;
+    Team tm;
+    tm.lane = 0;
+    tm.wid = w;
+    tm.nw = nw;
+    if (smem_elems > 0)
+      applyk2::run_two_site_v2<T>(tm, p.g, p.sites.data(), p.msgs.data(), p.op.data(), ws.data(), sv.data(), 1, &flag, smem.data(),
+                                  smem_elems);
+    else
+      run_gate<T>(tm, p.g, p.sites.data(), p.msgs.data(), p.op.data(), ws.data(), sv.data(), 1, &flag, &ssum);
+  };
+  std::vector<std::thread> th;
+  for (int w = 1; w < nw; ++w) th.emplace_back(body, w);
+  body(0);
+  for (auto& t : th) t.join();
+  pthread_barrier_destroy(&bar);
+  sites_out = p.sites;
+}
+
+template <typename T>
+static int check(const char* name, int z, int chi, int chi_b, int d, int64_t rb) {
+  Problem<T> p = make_problem<T>(z, chi, chi_b, d, 12345 + z * 100 + chi);
+  int64_t smem = 0;
+  if (rb > 0) {
+    for (int a = 0; a < 2; ++a) {
+      const int64_t c = p.g.s[a].cols, need = c * c + 2 * c * (c + rb), need2 = 2 * p.g.s[a].rows;
+      smem = smem > need ? smem : need;
+      smem = smem > need2 ? smem : need2;
+    }
+    if (applyk2::block_rows(p.g.s[0], smem) == 0 || applyk2::block_rows(p.g.s[1], smem) == 0) {
+      printf("%s: shapes do not fit version 2\n", name);
+      return 1;
+    }
+  }
+  std::vector<T> ref, got;
+  std::vector<double> sv_ref, sv_got;
+  run<T>(p, 1, smem, ref, sv_ref);
+  int bad = 0;
+  for (int nw : {2, 5, 8}) {
+    run<T>(p, nw, smem, got, sv_got);
+    double err = 0.0, scale = 0.0;
+    for (size_t i = 0; i < ref.size(); ++i) {
+      err = fmax(err, sqrt(Elem<T>::abs2(sub(ref[i], got[i]))));
+      scale = fmax(scale, sqrt(Elem<T>::abs2(ref[i])));
+    }
+    double sverr = 0.0;
+    for (size_t i = 0; i < sv_ref.size(); ++i) sverr = fmax(sverr, fabs(sv_ref[i] - sv_got[i]));
+    // one lane per warp: the arithmetic is the same in every schedule, so the results must agree to rounding of the
+    // (order-independent) operations -- in practice bit for bit
+    const bool ok = err <= 1e-12 * scale && sverr <= 1e-12;
+    printf("%-34s nw=%d  max |diff| = %.2e (scale %.2e), sv diff %.2e  %s\n", name, nw, err, scale, sverr, ok ? "ok" : "MISMATCH");
+    bad += !ok;
+  }
+  return bad;
+}
+
+int main() {
+  int bad = 0;
+  bad += check<double>("v1 f64  z=4 chi=3 bond=4 d=2", 4, 3, 4, 2, 0);
+  bad += check<c64>("v1 c128 z=3 chi=4 bond=3 d=2", 3, 4, 3, 2, 0);
+  bad += check<double>("v1 f64  z=1 (leaf pair) bond=3", 1, 3, 3, 2, 0);
+  bad += check<double>("v2 f64  z=4 chi=3 bond=4 d=2 rb=5", 4, 3, 4, 2, 5);
+  bad += check<double>("v2 f64  z=4 chi=4 bond=4 d=2 rb=64", 4, 4, 4, 2, 64);
+  bad += check<c64>("v2 c128 z=3 chi=4 bond=3 d=2 rb=3", 3, 4, 3, 2, 3);
+  bad += check<c64>("v2 c128 z=3 chi=8 bond=2 d=3 rb=16", 3, 8, 2, 3, 16);
+  bad += check<double>("v2 f64  z=1 (leaf pair) bond=3 rb=1", 1, 3, 3, 2, 1);
+  printf(bad ? "FAILED: %d mismatches\n" : "all schedules agree\n", bad);
+  return bad ? 1 : 0;
+}
