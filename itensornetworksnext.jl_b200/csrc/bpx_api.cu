@@ -1404,7 +1404,8 @@ static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const v
   // chunks: consecutive gates whose work space fits the budget (at least one gate per chunk)
   size_t free_b = 0, total_b = 0;
   BPX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-  const int64_t budget = (int64_t)std::max<size_t>(std::min<size_t>(free_b / 2, (size_t)8 << 30), (size_t)1 << 20) / ctx->esize;
+  int64_t budget = (int64_t)std::max<size_t>(std::min<size_t>(free_b / 2, (size_t)8 << 30), (size_t)1 << 20) / ctx->esize;
+  if (const char* e = getenv("BPX_APPLY_WS_BYTES")) budget = std::max<int64_t>(1, atoll(e) / ctx->esize);  // tests: force several chunks
   // OPT-IN version 2 of the two-site kernel (bpx_apply2.cuh: gauging and TSQR staged through shared memory); the
   // default stays version 1 until version 2 has been run and measured on a B200
   const char* v2env = getenv("BPX_APPLY_V2");

@@ -82,3 +82,31 @@ def test_v2_matches_v1(monkeypatch, dtype, lattice, chi, max_rank, normalize):
         x, y = bond_invariant(s1, v, w), bond_invariant(s2, v, w)
         assert np.abs(x - y).max() <= 1e-9 * np.abs(x).max()
     assert all(np.allclose(a, b, rtol=1e-10, atol=1e-14) for a, b in zip(m1, m2))
+
+
+@pytest.mark.parametrize("v2", ["0", "1"])
+def test_chunked_layers_equal_one_launch(monkeypatch, v2):
+    """A work-space budget of 64 KiB splits the layer into several launches (the path cfg5-sized layers take when their
+    work space exceeds half the free HBM): results must equal the single-launch run bit for bit."""
+    rng = np.random.default_rng(2)
+    p = problems.synthetic_peps(graphs.named_grid((4, 6)), 4, 2, np.float64, init="positive")
+    edges = matching(p.ga, rng)
+    ops = [randn(rng, np.float64, (2, 2, 2, 2)) for _ in edges]
+    monkeypatch.setenv("BPX_APPLY_V2", v2)
+    out = []
+    for budget in (None, str(64 * 1024)):
+        if budget is None:
+            monkeypatch.delenv("BPX_APPLY_WS_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("BPX_APPLY_WS_BYTES", budget)
+        with B.BPXContext(0) as ctx:
+            problems.upload(ctx, p)
+            ctx.sweep(4, 0.0, True)
+            before = ctx.counters()["launches"]
+            svs = ctx.apply_two_site_gates(edges, ops, max_rank=3, normalize=True)
+            out.append((svs, device_tensors(ctx, p), ctx.get_messages(), ctx.counters()["launches"] - before))
+    (sv_a, t_a, m_a, n_a), (sv_b, t_b, m_b, n_b) = out
+    assert n_a == 1 and n_b > 1
+    assert all(np.array_equal(x, y) for x, y in zip(sv_a, sv_b))
+    assert all(np.array_equal(x, y) for x, y in zip(t_a, t_b))
+    assert all(np.array_equal(x, y) for x, y in zip(m_a, m_b))
