@@ -38,6 +38,12 @@ constexpr int NT = 256;  // threads per CTA on the device
 #ifndef BPX_HOST_TEAM_SYNC
 #define BPX_HOST_TEAM_SYNC()
 #endif
+#ifndef BPX_HOST_LANES  // the race-check harness can also run several lanes per warp as threads
+#define BPX_HOST_LANES 1
+#define BPX_HOST_WARP_SUM(team, x) (x)
+#define BPX_HOST_SYNCWARP(team)
+#define BPX_HOST_ATOMIC_ADD(p, v) (*(p) += (v))
+#endif
 #ifndef BPX_FLAG_SET
 #define BPX_FLAG_SET(p) (*(p) = 1)  // the race-check harness makes this a relaxed atomic store for ThreadSanitizer
 #endif
@@ -47,7 +53,7 @@ struct Team {
 #ifdef __CUDA_ARCH__
     return 32;
 #else
-    return 1;
+    return BPX_HOST_LANES;
 #endif
   }
   __host__ __device__ __forceinline__ int tid() const { return wid * lanes() + lane; }
@@ -63,6 +69,8 @@ struct Team {
   __host__ __device__ __forceinline__ double sum(double x) const {
 #ifdef __CUDA_ARCH__
     x = warp_sum_d(x);
+#else
+    x = BPX_HOST_WARP_SUM(*this, x);
 #endif
     return x;
   }
@@ -70,6 +78,8 @@ struct Team {
   __host__ __device__ __forceinline__ T sum_t(T x) const {
 #ifdef __CUDA_ARCH__
     x = warp_sum<T>(x);
+#else
+    x = BPX_HOST_WARP_SUM(*this, x);
 #endif
     return x;
   }
@@ -375,6 +385,8 @@ __host__ __device__ int householder_qr(const Team& tm, T* P, int64_t rows, int c
         const T f = E::mul(ctau, w);
 #ifdef __CUDA_ARCH__
         __syncwarp();  // every lane has read cc[j] before lane 0 overwrites it
+#else
+        BPX_HOST_SYNCWARP(tm);
 #endif
         for (int64_t r = j + 1 + tm.lane; r < rows; r += L) cc[r] = sub(cc[r], E::mul(f, E::mul(cj[r], scale)));
         if (tm.lane == 0) cc[j] = sub(cc[j], f);
@@ -409,11 +421,15 @@ __host__ __device__ void apply_q(const Team& tm, const T* P, int64_t rows, int n
       const T f = E::mul(tj, w);
 #ifdef __CUDA_ARCH__
       __syncwarp();
+#else
+      BPX_HOST_SYNCWARP(tm);
 #endif
       for (int64_t r = j + 1 + tm.lane; r < rows; r += L) y[r] = sub(y[r], E::mul(f, v[r]));
       if (tm.lane == 0) y[j] = sub(y[j], f);
 #ifdef __CUDA_ARCH__
       __syncwarp();
+#else
+      BPX_HOST_SYNCWARP(tm);
 #endif
     }
   }
@@ -637,7 +653,7 @@ __host__ __device__ void run_one_site(const Team& tm, const GateDesc& gd, T* sit
 #ifdef __CUDA_ARCH__
   if (tm.lane == 0) atomicAdd(scratch_sum, part);
 #else
-  *scratch_sum += part;
+  if (tm.lane == 0) BPX_HOST_ATOMIC_ADD(scratch_sum, part);
 #endif
   tm.sync();
   const double nrm = sqrt(*scratch_sum);

@@ -1,6 +1,7 @@
 """Inter-warp synchronisation of the gate-application kernels (csrc/bpx_apply.cuh, csrc/bpx_apply2.cuh) checked WITHOUT a
-GPU: tests/native/apply_race_check.cu runs the same `__host__ __device__` code with one thread per warp and a real barrier
-behind `Team::sync()`, under ThreadSanitizer.  A missing barrier between two phases executed by different warps is a
+GPU: tests/native/apply_race_check.cu runs the same `__host__ __device__` code with one thread per warp -- or per LANE,
+with warp barriers standing in for `__syncwarp()` and the shuffle reductions -- and a real barrier behind `Team::sync()`,
+under ThreadSanitizer.  A missing barrier between two phases executed by different warps is a
 data-race report (or a result that differs from the sequential schedule); with the barriers removed TSAN reports
 thousands of races on this very program, so the check has teeth."""
 import os
@@ -27,4 +28,4 @@ def test_gate_kernels_are_race_free_across_warps():
         pytest.skip("ThreadSanitizer cannot run in this environment: " + out.strip().splitlines()[0])
     assert "ThreadSanitizer: data race" not in out, out[-3000:]
     assert r.returncode == 0 and "all schedules agree" in out, out[-3000:]
-    assert out.count(" ok") >= 24 and "MISMATCH" not in out
+    assert out.count(" ok") >= 40 and "MISMATCH" not in out  # 8 problems x 5 schedules (warps x lanes)
