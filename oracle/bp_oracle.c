@@ -122,7 +122,7 @@ static int update_edge(int is_complex, int64_t e, const int64_t* src, const int6
                        void* work0, void* work1) {
   const int64_t u = src[e];
   const int z = (int)(row_ptr[u + 1] - row_ptr[u]);
-  int32_t dim[MAXZ];
+  int32_t dim[MAXZ] = {0};
   const void* in[MAXZ];
   const size_t w = is_complex ? 16 : 8;
   for (int i = 0; i < z; ++i) {
