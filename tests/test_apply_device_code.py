@@ -330,3 +330,104 @@ def test_identity_gate_at_the_true_cfg5_shape(hostlib, variant):
     after = probe(new[0], slot1, v1) @ probe(new[1], slot2, v2).T
     assert np.abs(after - before).max() <= 1e-9 * np.abs(before).max()
     assert np.allclose(np.diag(msg_out.reshape(chi, chi, order="F")), sv)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the other BASELINE shapes and numerically hard inputs
+# ---------------------------------------------------------------------------------------------------------------
+def star_pair(rng, dtype, z, chi, d, chi_bond=None, msg=None):
+    """Two degree-z vertices joined by one bond, every other leg ending in a leaf; returns (adj, state, env)."""
+    chi_bond = chi if chi_bond is None else chi_bond
+    adj = {0: [1] + [2 + i for i in range(z - 1)], 1: [0] + [2 + (z - 1) + i for i in range(z - 1)]}
+    for w in range(2, 2 * z):
+        adj[w] = [0 if w < 2 + (z - 1) else 1]
+    dims = {frozenset((v, w)): chi for v, nb in adj.items() for w in nb}
+    dims[frozenset((0, 1))] = chi_bond
+    state, env = random_network(rng, dtype, adj, dims, {v: d for v in adj})
+    if msg is not None:
+        for key in list(env):
+            if key[1] in (0, 1) and key[0] not in (0, 1):
+                env[key] = msg(rng, env[key].shape[0]).astype(dtype)
+    return adj, state, env
+
+
+def run_pair(hostlib, variant, dtype, adj, state, env, o, max_rank, normalize):
+    a1, a2 = side_args(state, env, adj, 0, 1), side_args(state, env, adj, 1, 0)
+    chi_b = int(a1[3][a1[2]])
+    msg_out, sv = np.zeros(chi_b * chi_b, dtype=dtype), np.zeros(chi_b)
+    op = fcopy(o).ravel(order="F").copy()
+    assert two_site(hostlib, variant, dtype, a1, a2, op, max_rank, normalize, msg_out, sv) == 0
+    got = dict(state)
+    got[0] = (a1[4].reshape(state[0][0].shape, order="F"), state[0][1])
+    got[1] = (a2[4].reshape(state[1][0].shape, order="F"), state[1][1])
+    return got, sv
+
+
+@pytest.mark.parametrize("variant", ["v1", ("v2", 32), ("v2", 100000)], ids=str)
+@pytest.mark.parametrize("dtype,z,chi,d", [(np.float64, 6, 4, 2), (np.complex128, 3, 16, 2), (np.float64, 4, 8, 2),
+                                          (np.complex128, 4, 8, 2)], ids=["cfg4", "cfg3", "cfg2", "cfg2c"])
+def test_two_site_gate_baseline_shapes(hostlib, variant, dtype, z, chi, d):
+    """The bulk shapes of BASELINE configs 2, 2c, 3 and 4 (config 5 and config 1 are covered above)."""
+    rng = np.random.default_rng(z * 100 + chi)
+    adj, state, env = star_pair(rng, dtype, z, chi, d)
+    o = randn(rng, dtype, (d, d, d, d))
+    names = (("s", 0), ("s", 1))
+    want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=chi, normalize=True)
+    got, sv = run_pair(hostlib, variant, dtype, adj, state, env, o, chi, True)
+    assert np.allclose(sv, np.diag(want_env[(0, 1)]).real, rtol=1e-9, atol=1e-13)
+    x, y = bond_product(got, 0, 1), bond_product(want_state, 0, 1)
+    assert np.abs(x - y).max() <= 1e-9 * np.abs(y).max()
+
+
+def graded_message(decades):
+    def make(rng, c):
+        q, _ = np.linalg.qr(rng.standard_normal((c, c)) + 1j * rng.standard_normal((c, c)))
+        ev = np.logspace(0, -decades, c)
+        return (q * ev) @ q.conj().T
+    return make
+
+
+@pytest.mark.parametrize("variant", ["v1", ("v2", 16)], ids=str)
+@pytest.mark.parametrize("decades", [6, 10, 13])
+def test_two_site_gate_with_ill_conditioned_environments(hostlib, variant, decades):
+    """Message spectra spanning 6, 10 and 13 decades (a strongly entangled bond next to a nearly product one): the gauges
+    X = sqrt(D) V^H and their inverses amplify rounding by sqrt(cond).  Yardstick: the IDENTITY gate with the full rank
+    kept must leave the pair invariant.  The device path (one-sided Jacobi: small eigenvalues of a PSD matrix to high
+    relative accuracy) is at least as accurate as the oracle's LAPACK eigh there (measured: 1.6e-7 against 9.5e-4 at 13
+    decades), and on a random gate the two agree to within their own errors; the singular values agree to 1e-8."""
+    rng = np.random.default_rng(decades)
+    dtype = np.complex128
+    adj, state, env = star_pair(rng, dtype, 3, 4, 2, msg=graded_message(decades))
+    names = (("s", 0), ("s", 1))
+    ident = np.eye(4).reshape(2, 2, 2, 2).astype(dtype)
+    y0 = bond_product(state, 0, 1)
+    oracle_state, _ = A.apply_operator((ident, names, names), state, env, trunc=4)
+    device_state, _ = run_pair(hostlib, variant, dtype, adj, state, env, ident, 4, False)
+    err_oracle = np.abs(bond_product(oracle_state, 0, 1) - y0).max() / np.abs(y0).max()
+    err_device = np.abs(bond_product(device_state, 0, 1) - y0).max() / np.abs(y0).max()
+    assert err_device <= max(2 * err_oracle, 1e-10), (err_device, err_oracle)
+    assert err_device <= {6: 1e-9, 10: 1e-5, 13: 1e-5}[decades]
+    o = randn(rng, dtype, (2, 2, 2, 2))
+    want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=4, normalize=True)
+    got, sv = run_pair(hostlib, variant, dtype, adj, state, env, o, 4, True)
+    assert np.allclose(sv, np.diag(want_env[(0, 1)]).real, rtol=1e-8, atol=1e-12)
+    x, y = bond_product(got, 0, 1), bond_product(want_state, 0, 1)
+    assert np.abs(x - y).max() <= (20 * (err_oracle + err_device) + 1e-9) * np.abs(y).max()
+
+
+@pytest.mark.parametrize("variant", ["v1", ("v2", 16)], ids=str)
+def test_two_site_gate_with_degenerate_singular_values(hostlib, variant):
+    """A gate that leaves an exactly degenerate spectrum on the bond (identity on a product state of Bell-like pairs):
+    any basis of the degenerate subspace is a valid answer; the pair product and S are unique."""
+    rng = np.random.default_rng(1)
+    dtype = np.float64
+    adj = {0: [1], 1: [0]}
+    state = {0: (np.eye(2)[:, :] / np.sqrt(2), (("s", 0), ("l", 0, 1))), 1: (np.eye(2) / np.sqrt(2) * np.sqrt(2), (("s", 1), ("l", 0, 1)))}
+    env = {(0, 1): np.eye(2) / 2, (1, 0): np.eye(2) / 2}
+    o = np.eye(4).reshape(2, 2, 2, 2)
+    names = (("s", 0), ("s", 1))
+    want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=2)
+    got, sv = run_pair(hostlib, variant, dtype, adj, state, env, o, 2, False)
+    assert np.allclose(sv, np.diag(want_env[(0, 1)]).real, rtol=1e-12) and abs(sv[0] - sv[1]) < 1e-14
+    x, y = bond_product(got, 0, 1), bond_product(want_state, 0, 1)
+    assert np.abs(x - y).max() <= 1e-13
