@@ -189,7 +189,10 @@ inline void finish_side(Side& s, int chi_b) {
 // (n x n, initialised to the identity here): on return B_in V = B_out with mutually orthogonal columns.
 // Round-robin schedule: n' = n rounded up to even players, n' - 1 steps of n'/2 disjoint pairs per sweep, one warp
 // per pair (lanes stride the rows).  `flag` is one int visible to the whole team (shared memory on the device).
-template <typename T>
+// STABLE_PHASE: use the rotation [[c, s ph], [-s conj(ph), c]], which tends to the identity as s -> 0; the default
+// (version 1, verified on the B200) multiplies column q by conj(ph) -- equally valid, but near convergence ph is the phase
+// of rounding noise, so the phases of the singular vectors (a bond gauge) depend on the order of the reductions.
+template <typename T, bool STABLE_PHASE = false>
 __host__ __device__ void jacobi_cols(const Team& tm, T* B, int m, int n, T* V, int* flag) {
   using E = Elem<T>;
   const int L = tm.lanes();
@@ -242,18 +245,33 @@ __host__ __device__ void jacobi_cols(const Team& tm, T* B, int m, int n, T* V, i
         const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
         const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
         const T cph = E::conj(ph);
-        // [p', q'] = [p, q] J,  J = [[c, s], [-s conj(ph), c conj(ph)]]  (unitary)
-        for (int r = tm.lane; r < m; r += L) {
-          const T x = bp[r], y = E::mul(bq[r], cph);
-          bp[r] = sub(scal(x, c), scal(y, s));
-          bq[r] = E::add(scal(x, s), scal(y, c));
-        }
         T* vp = V + (int64_t)p * n;
         T* vq = V + (int64_t)q * n;
-        for (int r = tm.lane; r < n; r += L) {
-          const T x = vp[r], y = E::mul(vq[r], cph);
-          vp[r] = sub(scal(x, c), scal(y, s));
-          vq[r] = E::add(scal(x, s), scal(y, c));
+        if constexpr (STABLE_PHASE) {
+          // [p', q'] = [p, q] J,  J = [[c, s ph], [-s conj(ph), c]]  (unitary, -> 1 as s -> 0)
+          const T sph = scal(ph, s), scph = scal(cph, s);
+          for (int r = tm.lane; r < m; r += L) {
+            const T x = bp[r], y = bq[r];
+            bp[r] = sub(scal(x, c), E::mul(y, scph));
+            bq[r] = E::add(E::mul(x, sph), scal(y, c));
+          }
+          for (int r = tm.lane; r < n; r += L) {
+            const T x = vp[r], y = vq[r];
+            vp[r] = sub(scal(x, c), E::mul(y, scph));
+            vq[r] = E::add(E::mul(x, sph), scal(y, c));
+          }
+        } else {
+          // [p', q'] = [p, q] J,  J = [[c, s], [-s conj(ph), c conj(ph)]]  (unitary)
+          for (int r = tm.lane; r < m; r += L) {
+            const T x = bp[r], y = E::mul(bq[r], cph);
+            bp[r] = sub(scal(x, c), scal(y, s));
+            bq[r] = E::add(scal(x, s), scal(y, c));
+          }
+          for (int r = tm.lane; r < n; r += L) {
+            const T x = vp[r], y = E::mul(vq[r], cph);
+            vp[r] = sub(scal(x, c), scal(y, s));
+            vq[r] = E::add(scal(x, s), scal(y, c));
+          }
         }
         if (tm.lane == 0) BPX_FLAG_SET(flag);  // several warps may store the same 1: benign
       }

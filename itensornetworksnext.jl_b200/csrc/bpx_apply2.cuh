@@ -96,14 +96,14 @@ template <typename T>
 __host__ __device__ void jacobi_cols_staged(const Team& tm, T* B, int m, int n, T* V, int* flag, T* smem, int64_t smem_elems) {
   const int64_t nb = (int64_t)m * n, nv = (int64_t)n * n;
   if (nb + nv > smem_elems) {
-    jacobi_cols<T>(tm, B, m, n, V, flag);
+    jacobi_cols<T, true>(tm, B, m, n, V, flag);
     return;
   }
   T* sb = smem;
   T* sv = smem + nb;
   for (int64_t i = tm.tid(); i < nb; i += tm.nt()) sb[i] = B[i];
   tm.sync();
-  jacobi_cols<T>(tm, sb, m, n, sv, flag);
+  jacobi_cols<T, true>(tm, sb, m, n, sv, flag);  // phase-stable rotation (see jacobi_cols)
   for (int64_t i = tm.tid(); i < nb; i += tm.nt()) B[i] = sb[i];
   for (int64_t i = tm.tid(); i < nv; i += tm.nt()) V[i] = sv[i];
   tm.sync();

@@ -213,12 +213,15 @@ static int check(const char* name, int z, int chi, int chi_b, int d, int64_t rb)
   std::vector<T> ref, got;
   std::vector<double> sv_ref, sv_got;
   run<T>(p, 1, 1, smem, ref, sv_ref);
+  const std::vector<T> ref_raw = ref;
   int bad = 0;
   const int sched[5][2] = {{2, 1}, {5, 1}, {8, 1}, {3, 4}, {2, 7}};  // (warps, lanes per warp); lanes = 1 first (raw tensors)
   for (const auto& sc : sched) {
     const int nw = sc[0], lanes = sc[1];
     run<T>(p, nw, lanes, smem, got, sv_got);
+    double raw = 0.0;
     if (lanes > 1) {  // a different order of the warp-wide sums: compare what is physical
+      for (size_t i = 0; i < got.size(); ++i) raw = fmax(raw, sqrt(Elem<T>::abs2(sub(ref_raw[i], got[i]))));
       got = pair_product<T>(p.g, got);
       if (ref.size() != got.size()) ref = pair_product<T>(p.g, ref);
     }
@@ -234,8 +237,8 @@ static int check(const char* name, int z, int chi, int chi_b, int d, int64_t rb)
     // (with several lanes the order of the warp-wide sums differs from the sequential run: agreement to rounding)
     const double tol = lanes == 1 ? 1e-12 : 1e-9;
     const bool ok = err <= tol * scale && sverr <= tol;
-    printf("%-34s warps=%d lanes=%d  max |diff| = %.2e (scale %.2e), sv diff %.2e  %s\n", name, nw, lanes, err, scale, sverr,
-           ok ? "ok" : "MISMATCH");
+    printf("%-34s warps=%d lanes=%d  max |diff| = %.2e (scale %.2e), sv diff %.2e, raw tensors %.1e  %s\n", name, nw, lanes, err,
+           scale, sverr, raw, ok ? "ok" : "MISMATCH");
     bad += !ok;
   }
   return bad;
