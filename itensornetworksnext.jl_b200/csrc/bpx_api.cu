@@ -1410,7 +1410,9 @@ static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const v
   // default stays version 1 until version 2 has been run and measured on a B200
   const char* v2env = getenv("BPX_APPLY_V2");
   bool v2 = v2env && atoi(v2env) != 0 && needs_ws;
-  const int64_t smem_elems = ((int64_t)ctx->max_smem_optin - 2048) / ctx->esize;
+  int64_t smem_elems = ((int64_t)ctx->max_smem_optin - 2048) / ctx->esize;
+  if (const char* e = getenv("BPX_APPLY_V2_SMEM_KB"))  // tuning knob: smaller panels, more resident CTAs per SM
+    smem_elems = std::max<int64_t>(64, std::min<int64_t>(smem_elems, atoll(e) * 1024 / ctx->esize));
   for (int64_t g = 0; v2 && g < ng; ++g)
     v2 = gates[g].nsides == 2 && applyk2::block_rows(gates[g].s[0], smem_elems) > 0 &&
          applyk2::block_rows(gates[g].s[1], smem_elems) > 0;
