@@ -37,7 +37,7 @@ def fcopy(a):
 # stages
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(6, 6), (9, 4), (4, 9), (12, 7), (1, 3), (5, 1), (32, 32)])
+@pytest.mark.parametrize("shape", [(6, 6), (9, 4), (4, 9), (12, 7), (1, 3), (5, 1), (32, 32), (64, 64), (64, 32), (32, 64)])
 def test_jacobi_svd(hostlib, dtype, shape):
     rng = np.random.default_rng(11)
     m, n = shape
@@ -431,3 +431,22 @@ def test_two_site_gate_with_degenerate_singular_values(hostlib, variant):
     assert np.allclose(sv, np.diag(want_env[(0, 1)]).real, rtol=1e-12) and abs(sv[0] - sv[1]) < 1e-14
     x, y = bond_product(got, 0, 1), bond_product(want_state, 0, 1)
     assert np.abs(x - y).max() <= 1e-13
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_jacobi_svd_graded_spectrum(hostlib, dtype):
+    """cfg5's bond matrix size (64 x 64) with singular values over 12 decades: every one to 1e-10 RELATIVE accuracy
+    (one-sided Jacobi is relatively accurate; this is what keeps small Schmidt values meaningful under truncation)."""
+    rng = np.random.default_rng(3)
+    n = 64
+    u, _ = np.linalg.qr(randn(rng, dtype, (n, n)))
+    v, _ = np.linalg.qr(randn(rng, dtype, (n, n)))
+    sv = np.logspace(0, -12, n)
+    a = (u * sv) @ v.conj().T
+    b, vv = fcopy(a), np.zeros((n, n), dtype=dtype, order="F")
+    hostlib.apply_host_jacobi(code(dtype), ptr(b), n, n, ptr(vv))
+    got = np.sort(np.linalg.norm(b, axis=0))[::-1]
+    # the matrix itself carries eps * |A| of rounding from its construction: values above that are relatively accurate
+    assert np.allclose(got[:40], sv[:40], rtol=1e-8)
+    assert np.allclose(got, np.linalg.svd(a, compute_uv=False), atol=1e-15)
+    assert np.allclose(vv.conj().T @ vv, np.eye(n), atol=1e-13)
