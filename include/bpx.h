@@ -181,6 +181,15 @@ int bpx_apply_one_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* verti
 /* download one site tensor (canonical layout) -- `state[v]` after gates were applied */
 int bpx_get_site_tensor(bpx_ctx* ctx, int64_t v, void* data);
 
+/* Two-site expectation values in the BP environment, the quantity a simple-update evolution monitors (bond energies):
+ * for every listed directed edge e = v1 -> v2, both norm-network factors contracted with every incoming message except
+ * the two on the shared link, `op[o1, o2, i1, i2]` (column-major, d1*d2*d1*d2 elements per edge, packed in list order)
+ * applied to the two ket site legs.  num_out[g] / den_out[g] = <O_e>; den is the same contraction with the identity.
+ * Build-defined extension like bpx_vertex_expect_numerators: the two-vertex analogue of `vertex_scalar`
+ * (messagecache.jl:139-143); the reference has no `expect`.  Read-only: edges may share vertices. */
+int bpx_edge_expect(bpx_ctx* ctx, int64_t n_edges, const int64_t* edges, const void* ops_packed, void* num_out,
+                    void* den_out);
+
 /* ---- introspection --------------------------------------------------------------------------------- */
 int bpx_num_buckets(const bpx_ctx* ctx);
 /* info[0]=degree, [1]=chi (0 if non-uniform), [2]=phys dim, [3]=#vertices, [4]=#directed edges,

@@ -83,6 +83,7 @@ def load() -> C.CDLL:
         "bpx_apply_two_site_gates": (C.c_int, [vp, i64, vp, vp, C.c_int, C.c_int, vp]),
         "bpx_apply_one_site_gates": (C.c_int, [vp, i64, vp, vp, C.c_int]),
         "bpx_get_site_tensor": (C.c_int, [vp, i64, vp]),
+        "bpx_edge_expect": (C.c_int, [vp, i64, vp, vp, vp, vp]),
         "bpx_num_buckets": (C.c_int, [vp]),
         "bpx_bucket_info": (C.c_int, [vp, C.c_int, P(i64)]),
         "bpx_set_kernel_policy": (C.c_int, [vp, C.c_int]),

@@ -16,6 +16,7 @@
 #include "bpx_halo.cuh"
 #include "bpx_apply.cuh"
 #include "bpx_apply2.cuh"
+#include "bpx_expect2.cuh"
 
 using namespace bpx;
 
@@ -1582,6 +1583,92 @@ extern "C" int bpx_apply_one_site_gates(bpx_ctx* ctx, int64_t n_gates, const int
     op_off += (int64_t)gd.s[0].d * gd.s[0].d;
   }
   return apply_run(ctx, gates, ops_packed, (size_t)op_off, normalize, nullptr, 0, normalize != 0);
+}
+
+// ---- two-site expectation values in the BP environment (bpx_expect2.cuh) ------------------------------------
+extern "C" int bpx_edge_expect(bpx_ctx* ctx, int64_t n_edges, const int64_t* edges, const void* ops_packed, void* num_out,
+                               void* den_out) {
+  NEED_DIMS(ctx, "bpx_edge_expect");
+  REQUIRE(ctx, ctx->mode == BPX_MODE_NORM, "bpx_edge_expect: NORM mode only");
+  REQUIRE(ctx, n_edges >= 0, "bpx_edge_expect: bad arguments");
+  if (n_edges == 0) return BPX_OK;
+  REQUIRE(ctx, edges && ops_packed && num_out && den_out, "bpx_edge_expect: NULL argument");
+  int rc = halo_gate(ctx);
+  if (rc) return rc;
+  std::vector<expect2::EdgeDesc> desc((size_t)n_edges);
+  int64_t op_off = 0;
+  for (int64_t g = 0; g < n_edges; ++g) {
+    const int64_t e = edges[g];
+    REQUIRE(ctx, e >= 0 && e < ctx->ne, "bpx_edge_expect: entry %lld: edge %lld out of range", (long long)g, (long long)e);
+    const int64_t v1 = ctx->src[e], v2 = ctx->dst[e], r = ctx->rev[e];
+    if ((rc = apply_owned_check(ctx, "bpx_edge_expect", g, v1)) || (rc = apply_owned_check(ctx, "bpx_edge_expect", g, v2))) return rc;
+    expect2::EdgeDesc& d = desc[g];
+    memset(&d, 0, sizeof(d));
+    d.chi_b = ctx->link_dim[e];
+    apply_fill_side(ctx, d.s[0], v1, ctx->slot[e], d.chi_b);
+    apply_fill_side(ctx, d.s[1], v2, ctx->slot[r], d.chi_b);
+    d.op_off = op_off;
+    const int64_t dd = (int64_t)d.s[0].d * d.s[1].d;
+    op_off += dd * dd;
+  }
+  // chunks bounded by the work-space budget, like the gate layers
+  size_t free_b = 0, total_b = 0;
+  BPX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  int64_t budget = (int64_t)std::max<size_t>(std::min<size_t>(free_b / 2, (size_t)8 << 30), (size_t)1 << 20) / ctx->esize;
+  if (const char* e = getenv("BPX_APPLY_WS_BYTES")) budget = std::max<int64_t>(1, atoll(e) / ctx->esize);
+  std::vector<int64_t> chunk_begin{0};
+  int64_t cur_total = 0, max_total = 0;
+  for (int64_t g = 0; g < n_edges; ++g) {
+    const int64_t need = expect2::layout_of(desc[g]).total + 2;
+    if (cur_total > 0 && cur_total + need > budget) {
+      chunk_begin.push_back(g);
+      cur_total = 0;
+    }
+    desc[g].ws_off = cur_total;
+    cur_total += need;
+    max_total = std::max(max_total, cur_total);
+  }
+  chunk_begin.push_back(n_edges);
+  expect2::EdgeDesc* d_desc = nullptr;
+  char *d_ws = nullptr, *d_ops = nullptr, *d_out = nullptr;
+  rc = upload(ctx, &d_desc, desc);
+  if (!rc) rc = dev_alloc(ctx, &d_ws, (size_t)max_total * ctx->esize);
+  if (!rc) rc = dev_alloc(ctx, &d_ops, (size_t)op_off * ctx->esize);
+  if (!rc) rc = dev_alloc(ctx, &d_out, (size_t)(2 * n_edges) * ctx->esize);
+  cudaError_t ce = cudaSuccess;
+  if (!rc) {
+    ce = cudaMemcpyAsync(d_ops, ops_packed, (size_t)op_off * ctx->esize, cudaMemcpyHostToDevice, ctx->stream);
+    for (size_t c = 0; c + 1 < chunk_begin.size() && ce == cudaSuccess; ++c) {
+      expect2::ExpectArgs a;
+      a.edges = d_desc + chunk_begin[c];
+      a.n_edges = chunk_begin[c + 1] - chunk_begin[c];
+      a.sites = ctx->d_sites;
+      a.msgs = ctx->d_msg[ctx->cur];
+      a.ops = d_ops;
+      a.ws = d_ws;
+      a.num_out = d_out + (size_t)chunk_begin[c] * ctx->esize;
+      a.den_out = d_out + (size_t)(n_edges + chunk_begin[c]) * ctx->esize;
+      const int grid = (int)std::min<int64_t>(a.n_edges, (int64_t)ctx->num_sms * 8);
+      if (ctx->dtype == BPX_F64)
+        expect2::bp_edge_expect<double><<<grid, applyk::NT, 0, ctx->stream>>>(a);
+      else
+        expect2::bp_edge_expect<c64><<<grid, applyk::NT, 0, ctx->stream>>>(a);
+      ctx->n_launches++;
+      ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(num_out, d_out, (size_t)n_edges * ctx->esize, cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(den_out, d_out + (size_t)n_edges * ctx->esize, (size_t)n_edges * ctx->esize, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  const cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_desc);
+  cudaFree(d_ws);
+  cudaFree(d_ops);
+  cudaFree(d_out);
+  if (rc) return rc;
+  BPX_CUDA(ctx, ce);
+  BPX_CUDA(ctx, ce2);
+  return BPX_OK;
 }
 
 extern "C" void* bpx_device_messages(bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? ctx->d_msg[ctx->cur] : nullptr; }

@@ -172,6 +172,16 @@ class BPXContext:
         self._check(self.lib.bpx_apply_one_site_gates(self.h, len(v), _ptr(v), _ptr(np.ascontiguousarray(flat)),
                                                       int(bool(normalize))))
 
+    def edge_expect(self, edges: Sequence[int], ops: Sequence[np.ndarray]):
+        """Two-site expectation values in the BP environment: (numerators, denominators) per listed directed edge;
+        ops[g][o1, o2, i1, i2] with 1 = src and 2 = dst of edges[g].  Read-only (edges may share vertices)."""
+        e = np.ascontiguousarray(edges, dtype=np.int64)
+        flat = (np.concatenate([np.asarray(o, dtype=self.dtype).ravel(order="F") for o in ops]) if len(ops)
+                else np.empty(0, self.dtype))
+        num, den = np.zeros(max(1, len(e)), dtype=self.dtype), np.zeros(max(1, len(e)), dtype=self.dtype)
+        self._check(self.lib.bpx_edge_expect(self.h, len(e), _ptr(e), _ptr(np.ascontiguousarray(flat)), _ptr(num), _ptr(den)))
+        return num[:len(e)], den[:len(e)]
+
     # -- hot path ----------------------------------------------------------------------------------
     def sweep(self, max_sweeps: int = 1, tol: float = 0.0, normalize: bool = True):
         res, done = C.c_double(), C.c_int()

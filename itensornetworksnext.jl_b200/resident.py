@@ -125,6 +125,21 @@ class ResidentState:
             return list(vals)
         return [vals[cp.ga.vindex[v]] for v in vertices]
 
+    def expect_two_site(self, operators: Sequence[Operator]):
+        """<O> for two-site operators on neighbouring vertices in the BP environment (bond energies of a simple-update
+        evolution); read-only, so the operators may overlap.  Build-defined like `expect`."""
+        operators = list(operators)
+        cp = self._s.cp
+        edges, lowered = [], []
+        for op in operators:
+            vs = _touched_vertices(op, self.names)
+            if len(vs) != 2 or vs[1] not in self.names.graph.neighbors(vs[0]):
+                raise ArgumentError("expect_two_site takes operators on two neighbouring vertices")
+            edges.append(cp.ga.edge_id(NamedEdge(vs[0], vs[1])))
+            lowered.append(_lowered_operator(op, self.names, vs, cp.dtype))
+        num, den = self._s.ctx.edge_expect(edges, lowered)
+        return list(num / den)
+
     # -- back to the host ------------------------------------------------------------------------------------------
     def state(self) -> ITensorNetwork:
         return ITensorNetwork({v: self._s.site_itensor(v) for v in self.names.vertices()})

@@ -302,6 +302,35 @@ def local_expect(p: Problem, msgs: Sequence[np.ndarray], v: int, op: np.ndarray)
     return vertex_scalar(p, msgs, v, op) / vertex_scalar(p, msgs, v)
 
 
+def edge_density(p: Problem, msgs: Sequence[np.ndarray], e: int) -> np.ndarray:
+    """BP two-site reduced density matrix (unnormalised) of the vertices of directed edge e, rho[s1, s2, s1', s2'] (ket
+    indices first): both norm-network factors (normnetwork.jl:49-54) with every incoming message except the two on the
+    shared link -- the two-vertex analogue of `vertex_scalar` (messagecache.jl:139-143).  Build-defined, like
+    `local_expect` (the reference has no `expect`)."""
+    assert p.mode == "norm"
+
+    def half(vtx, slot):
+        A = p.tensors[vtx]
+        z = A.ndim - 1
+        ins = [msgs[int(p.rev[f])] for f in p.out_edges(vtx)]
+        T = A
+        for i in range(z):
+            if i != slot:
+                T = np.moveaxis(np.tensordot(ins[i], T, axes=([1], [i + 1])), 0, i + 1)  # M[bra, ket] on the ket leg
+        ext = [i + 1 for i in range(z) if i != slot]
+        return np.tensordot(T, A.conj(), axes=(ext, ext))  # N[s, b, s', b']
+
+    n1 = half(int(p.src[e]), int(p.slot[e]))
+    n2 = half(int(p.dst[e]), int(p.slot[int(p.rev[e])]))
+    return np.einsum("abcd,ebfd->aecf", n1, n2)
+
+
+def two_site_expect(p: Problem, msgs: Sequence[np.ndarray], e: int, op: np.ndarray):
+    """(numerator, denominator) of <O_e>, op[o1, o2, i1, i2] with 1 = src(e), 2 = dst(e)."""
+    rho = edge_density(p, msgs, e)
+    return np.einsum("cdab,abcd->", op, rho), np.einsum("abab->", rho)
+
+
 # ---------------------------------------------------------------------------------------------------
 # brute force (for known-answer tests only)
 # ---------------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../itensornetworksnext.jl_b200/csrc/bpx_apply2.cuh"
+#include "../../itensornetworksnext.jl_b200/csrc/bpx_expect2.cuh"
 
 using namespace bpx;
 using namespace bpx::applyk;
@@ -101,7 +102,54 @@ static void one_site(int z, int d, const int32_t* dims, T* site, const T* msgs_i
   run_gate<T>(host_team(), g, site, msgs.data(), op, ws.data(), nullptr, normalize, &flag, &ssum);
 }
 
+template <typename T>
+static void edge_expect(int z1, int d1, int slot1, const int32_t* dims1, const T* site1, const T* msgs1, int z2, int d2,
+                        int slot2, const int32_t* dims2, const T* site2, const T* msgs2, const T* op, T* num, T* den) {
+  expect2::EdgeDesc g;
+  memset(&g, 0, sizeof(g));
+  const int chi = dims1[slot1];
+  g.chi_b = chi;
+  std::vector<T> sites, msgs;
+  const int zs[2] = {z1, z2}, ds[2] = {d1, d2}, slots[2] = {slot1, slot2};
+  const int32_t* dims[2] = {dims1, dims2};
+  const T* site_in[2] = {site1, site2};
+  const T* msg_in[2] = {msgs1, msgs2};
+  for (int a = 0; a < 2; ++a) {
+    Side& s = g.s[a];
+    s.z = zs[a];
+    s.d = ds[a];
+    s.bond_slot = slots[a];
+    int64_t moff = 0;
+    for (int i = 0; i < s.z; ++i) {
+      s.dim[i] = dims[a][i];
+      s.in_msg[i] = (int64_t)msgs.size() + moff;
+      moff += (int64_t)s.dim[i] * s.dim[i];
+    }
+    msgs.insert(msgs.end(), msg_in[a], msg_in[a] + moff);
+    finish_side(s, chi);
+    s.site_off = (int64_t)sites.size();
+    sites.insert(sites.end(), site_in[a], site_in[a] + s.n);
+  }
+  std::vector<T> ws((size_t)expect2::layout_of(g).total + 1);
+  double accum[4];
+  expect2::run_edge<T>(host_team(), g, sites.data(), msgs.data(), op, ws.data(), num, den, accum);
+}
+
 extern "C" {
+
+// two-site expectation value in the BP environment (csrc/bpx_expect2.cuh): numerator and denominator of <O_e>
+int apply_host_edge_expect(int dtype, int z1, int d1, int slot1, const int32_t* dims1, const void* site1, const void* msgs1, int z2,
+                           int d2, int slot2, const int32_t* dims2, const void* site2, const void* msgs2, const void* op,
+                           void* num, void* den) {
+  if (dims1[slot1] != dims2[slot2]) return -1;
+  if (dtype == 0)
+    edge_expect<double>(z1, d1, slot1, dims1, (const double*)site1, (const double*)msgs1, z2, d2, slot2, dims2,
+                        (const double*)site2, (const double*)msgs2, (const double*)op, (double*)num, (double*)den);
+  else
+    edge_expect<c64>(z1, d1, slot1, dims1, (const c64*)site1, (const c64*)msgs1, z2, d2, slot2, dims2, (const c64*)site2,
+                     (const c64*)msgs2, (const c64*)op, (c64*)num, (c64*)den);
+  return 0;
+}
 
 // dtype: 0 = Float64, 1 = ComplexF64 (interleaved).  msgsN: the z_N incoming messages of vertex N packed in slot order
 // (chi_i^2 each, [bra, ket] column-major; the entry of the bond slot is ignored).  Sites are updated in place.

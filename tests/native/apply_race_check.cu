@@ -57,6 +57,7 @@ namespace bpx { struct c64; }
 static inline bpx::c64 host_warp_sum(int lane, bpx::c64 x);
 
 #include "../../itensornetworksnext.jl_b200/csrc/bpx_apply2.cuh"
+#include "../../itensornetworksnext.jl_b200/csrc/bpx_expect2.cuh"
 
 using namespace bpx;
 using namespace bpx::applyk;
@@ -244,8 +245,63 @@ static int check(const char* name, int z, int chi, int chi_b, int d, int64_t rb)
   return bad;
 }
 
+// two-site expectation kernel (csrc/bpx_expect2.cuh) under the same schedules
+template <typename T>
+static int check_expect(const char* name, int z, int chi, int chi_b, int d) {
+  Problem<T> p = make_problem<T>(z, chi, chi_b, d, 777 + z * 10 + chi);
+  expect2::EdgeDesc g;
+  memset(&g, 0, sizeof(g));
+  g.s[0] = p.g.s[0];
+  g.s[1] = p.g.s[1];
+  g.chi_b = chi_b;
+  const int64_t total = expect2::layout_of(g).total;
+  const int sched[6][2] = {{1, 1}, {2, 1}, {5, 1}, {8, 1}, {3, 4}, {2, 7}};
+  T ref_num = Elem<T>::zero(), ref_den = Elem<T>::zero();
+  int bad = 0;
+  for (const auto& sc : sched) {
+    const int nw = sc[0], lanes = sc[1];
+    g_lanes = lanes;
+    std::vector<WarpShared> warps(nw);
+    for (auto& w : warps) pthread_barrier_init(&w.bar, nullptr, lanes);
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, nullptr, nw * lanes);
+    std::vector<T> ws((size_t)total + 2);
+    double accum[4] = {0, 0, 0, 0};
+    T num = Elem<T>::zero(), den = Elem<T>::zero();
+    auto body = [&](int t) {
+      g_barrier = nw * lanes > 1 ? &bar : nullptr;
+      g_warp = lanes > 1 ? &warps[t / lanes] : nullptr;
+      Team tm;
+      tm.lane = t % lanes;
+      tm.wid = t / lanes;
+      tm.nw = nw;
+      expect2::run_edge<T>(tm, g, p.sites.data(), p.msgs.data(), p.op.data(), ws.data(), &num, &den, accum);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nw * lanes; ++t) th.emplace_back(body, t);
+    body(0);
+    for (auto& t : th) t.join();
+    pthread_barrier_destroy(&bar);
+    for (auto& w : warps) pthread_barrier_destroy(&w.bar);
+    g_lanes = 1;
+    if (nw * lanes == 1) {
+      ref_num = num;
+      ref_den = den;
+      continue;
+    }
+    const double err = sqrt(Elem<T>::abs2(sub(num, ref_num))) + sqrt(Elem<T>::abs2(sub(den, ref_den)));
+    const double scale = sqrt(Elem<T>::abs2(ref_num)) + sqrt(Elem<T>::abs2(ref_den));
+    const bool ok = err <= 1e-12 * scale;
+    printf("%-34s warps=%d lanes=%d  |diff| = %.2e (scale %.2e)  %s\n", name, nw, lanes, err, scale, ok ? "ok" : "MISMATCH");
+    bad += !ok;
+  }
+  return bad;
+}
+
 int main() {
   int bad = 0;
+  bad += check_expect<double>("expect2 f64  z=4 chi=3 bond=4 d=2", 4, 3, 4, 2);
+  bad += check_expect<c64>("expect2 c128 z=3 chi=4 bond=3 d=2", 3, 4, 3, 2);
   bad += check<double>("v1 f64  z=4 chi=3 bond=4 d=2", 4, 3, 4, 2, 0);
   bad += check<c64>("v1 c128 z=3 chi=4 bond=3 d=2", 3, 4, 3, 2, 0);
   bad += check<double>("v1 f64  z=1 (leaf pair) bond=3", 1, 3, 3, 2, 0);

@@ -14,13 +14,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "native", "apply_host.cu")
 HDR = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_apply.cuh")
 HDR2 = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_apply2.cuh")
+HDR3 = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_expect2.cuh")
 OUT = os.path.join(HERE, "native", "_build", "libapply_host.so")
 
 
 def build_hostlib() -> ctypes.CDLL:
     """Compile tests/native/apply_host.cu (the device code of csrc/bpx_apply.cuh for the host) if stale; load it."""
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    stale = not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in (SRC, HDR, HDR2))
+    stale = not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in (SRC, HDR, HDR2, HDR3))
     if stale:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
@@ -103,6 +104,23 @@ class HostHarnessContext:
             z, d, dims, m = self._side(v)
             o = np.asarray(op, dtype=self.dtype).ravel(order="F").copy()
             self.lib.apply_host_one_site(code, z, d, _ptr(dims), _ptr(self.sites[v]), _ptr(m), _ptr(o), int(bool(normalize)))
+
+    def edge_expect(self, edges, ops):
+        """Two-site expectation values (csrc/bpx_expect2.cuh on the host): (numerators, denominators)."""
+        self.calls.append(("expect2", len(edges)))
+        code = 1 if self.dtype.kind == "c" else 0
+        num, den = np.zeros(len(edges), dtype=self.dtype), np.zeros(len(edges), dtype=self.dtype)
+        for i, (e, op) in enumerate(zip(edges, ops)):
+            v1, v2, r = self.src[e], self.dst[e], self.rev[e]
+            z1, d1, dims1, m1 = self._side(v1)
+            z2, d2, dims2, m2 = self._side(v2)
+            o = np.asarray(op, dtype=self.dtype).ravel(order="F").copy()
+            a, b = np.zeros(1, dtype=self.dtype), np.zeros(1, dtype=self.dtype)
+            rc = self.lib.apply_host_edge_expect(code, z1, d1, self.slot[e], _ptr(dims1), _ptr(self.sites[v1]), _ptr(m1), z2, d2,
+                                                 self.slot[r], _ptr(dims2), _ptr(self.sites[v2]), _ptr(m2), _ptr(o), _ptr(a), _ptr(b))
+            assert rc == 0
+            num[i], den[i] = a[0], b[0]
+        return num, den
 
     def get_site_tensor(self, v):
         return self.sites[v].copy()

@@ -450,3 +450,72 @@ def test_jacobi_svd_graded_spectrum(hostlib, dtype):
     assert np.allclose(got[:40], sv[:40], rtol=1e-8)
     assert np.allclose(got, np.linalg.svd(a, compute_uv=False), atol=1e-15)
     assert np.allclose(vv.conj().T @ vv, np.eye(n), atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# two-site expectation values (csrc/bpx_expect2.cuh)
+# ---------------------------------------------------------------------------------------------------------------
+def oracle_problem_from_state(oracle, adjacency, state):
+    """Oracle `Problem` (bp_oracle.py) for a named state: vertices in dict order, legs already in slot order."""
+    from itnn_b200.graphs import GraphArrays
+
+    verts = list(adjacency)
+    vi = {v: i for i, v in enumerate(verts)}
+    src, dst, slot, row_ptr = [], [], [], [0]
+    for v in verts:
+        for k, w in enumerate(adjacency[v]):
+            src.append(vi[v]); dst.append(vi[w]); slot.append(k)
+        row_ptr.append(len(src))
+    index = {(s, d): e for e, (s, d) in enumerate(zip(src, dst))}
+    rev = [index[(d, s)] for s, d in zip(src, dst)]
+    ga = GraphArrays(vertices=verts, vindex=vi, src=src, dst=dst, rev=rev, slot=slot, row_ptr=row_ptr, edge_index=index)
+    return ga, oracle.make_problem(ga, [state[v][0] for v in verts], "norm")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("chi_bond,chi_other", [(3, 2), (2, 4), (1, 3), (4, 1)])
+def test_edge_expect_matches_oracle(oracle, hostlib, dtype, chi_bond, chi_other):
+    rng = np.random.default_rng(chi_bond * 10 + chi_other)
+    d = {v: 2 for v in GRID}
+    d[4] = 3
+    state, env = random_network(rng, dtype, GRID, grid_dims(chi_bond, chi_other), d)
+    ga, p = oracle_problem_from_state(oracle, GRID, state)
+    msgs = [env[(ga.vertices[ga.src[e]], ga.vertices[ga.dst[e]])] for e in range(ga.ne)]
+    v1, v2 = 1, 4
+    o = randn(rng, dtype, (d[v1], d[v2], d[v1], d[v2]))
+    want_num, want_den = oracle.two_site_expect(p, msgs, ga.edge_index[(ga.vindex[v1], ga.vindex[v2])], o)
+    a1, a2 = side_args(state, env, GRID, v1, v2), side_args(state, env, GRID, v2, v1)
+    num, den = np.zeros(1, dtype=dtype), np.zeros(1, dtype=dtype)
+    op = fcopy(o).ravel(order="F").copy()
+    rc = hostlib.apply_host_edge_expect(code(dtype), a1[0], a1[1], a1[2], ptr(a1[3]), ptr(a1[4]), ptr(a1[5]), a2[0], a2[1], a2[2],
+                                        ptr(a2[3]), ptr(a2[4]), ptr(a2[5]), ptr(op), ptr(num), ptr(den))
+    assert rc == 0
+    assert np.isclose(num[0], want_num, rtol=1e-11, atol=1e-14 * abs(want_den))
+    assert np.isclose(den[0], want_den, rtol=1e-11) and abs(np.imag(den[0])) <= 1e-12 * abs(den[0])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_edge_expect_is_exact_on_a_tree(oracle, hostlib, dtype):
+    """Known answer: on a tree with converged BP messages the two-site expectation value is the exact one."""
+    rng = np.random.default_rng(8)
+    adj = {0: [1], 1: [0, 2, 3], 2: [1], 3: [1, 4], 4: [3]}
+    dims = {frozenset((v, w)): 3 for v, nb in adj.items() for w in nb}
+    state, _ = random_network(rng, dtype, adj, dims, {v: 2 for v in adj})
+    ga, p = oracle_problem_from_state(oracle, adj, state)
+    msgs = [np.ones((3, 3), dtype=dtype) for _ in range(ga.ne)]
+    for _ in range(6):  # diameter 3: the synchronous schedule has converged
+        msgs = oracle.sweep_jacobi(p, msgs)
+    env = {(ga.vertices[ga.src[e]], ga.vertices[ga.dst[e]]): msgs[e] for e in range(ga.ne)}
+    psi = A.permute(A.prod(state), [("s", v) for v in adj]).reshape(-1)
+    for v1, v2 in ((1, 3), (3, 4), (0, 1)):
+        o = randn(rng, dtype, (2, 2, 2, 2))
+        a1, a2 = side_args(state, env, adj, v1, v2), side_args(state, env, adj, v2, v1)
+        num, den = np.zeros(1, dtype=dtype), np.zeros(1, dtype=dtype)
+        op = fcopy(o).ravel(order="F").copy()
+        hostlib.apply_host_edge_expect(code(dtype), a1[0], a1[1], a1[2], ptr(a1[3]), ptr(a1[4]), ptr(a1[5]), a2[0], a2[1], a2[2],
+                                       ptr(a2[3]), ptr(a2[4]), ptr(a2[5]), ptr(op), ptr(num), ptr(den))
+        full = psi.reshape((2,) * 5)
+        moved = np.moveaxis(full, (v1, v2), (0, 1))
+        opsi = np.tensordot(o, moved, axes=([2, 3], [0, 1]))
+        exact = np.vdot(moved.ravel(), opsi.ravel()) / np.vdot(psi, psi)
+        assert np.isclose(num[0] / den[0], exact, rtol=1e-10, atol=1e-12)

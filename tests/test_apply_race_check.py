@@ -12,7 +12,8 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "native", "apply_race_check.cu")
 EXE = os.path.join(HERE, "native", "_build", "apply_race_check")
-HDRS = [os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", f) for f in ("bpx_apply.cuh", "bpx_apply2.cuh", "bpx_common.cuh")]
+HDRS = [os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", f)
+        for f in ("bpx_apply.cuh", "bpx_apply2.cuh", "bpx_expect2.cuh", "bpx_common.cuh")]
 
 
 def test_gate_kernels_are_race_free_across_warps():
@@ -28,4 +29,4 @@ def test_gate_kernels_are_race_free_across_warps():
         pytest.skip("ThreadSanitizer cannot run in this environment: " + out.strip().splitlines()[0])
     assert "ThreadSanitizer: data race" not in out, out[-3000:]
     assert r.returncode == 0 and "all schedules agree" in out, out[-3000:]
-    assert out.count(" ok") >= 40 and "MISMATCH" not in out  # 8 problems x 5 schedules (warps x lanes)
+    assert out.count(" ok") >= 50 and "MISMATCH" not in out  # (8 gate problems + 2 expectation problems) x 5 schedules

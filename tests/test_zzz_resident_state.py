@@ -118,6 +118,38 @@ def evolve_and_check(g, chi, h=1.0, steps=(60, 60, 60), dts=(0.1, 0.03, 0.01)):
     assert np.all(ex > 0.3)  # h = 1: strongly polarised along X, no symmetry breaking
 
 
+def bond_hamiltonians(g, h):
+    """h_e = -Z Z - (h / z_v) X 1 - (h / z_w) 1 X as two-site operators: sum_e h_e = H."""
+    ops = []
+    for e in g.edges():
+        zv, zw = g.degree(e.src), g.degree(e.dst)
+        hb = -np.kron(Z, Z) - (h / zv) * np.kron(X, I2) - (h / zw) * np.kron(I2, X)
+        names = (("s", e.src), ("s", e.dst))
+        ops.append(B.Operator(hb.reshape(2, 2, 2, 2), names, names))
+    return ops
+
+
+def check_energy_from_two_site_expectations(g, chi=4, h=1.0):
+    """sum_e <h_e> from the device (bpx_edge_expect in the BP environment) == <H> by brute force on the downloaded
+    tensors: exact on a tree.  A short evolution makes the state entangled and the environments non-trivial."""
+    ham, e0, _ = exact_ground_state(g, h)
+    with B.ResidentState(product_state(g, chi)) as rs:
+        rs.beliefpropagation(dict(maxiter=50, tol=1e-14), schedule="sequential")
+        gates = bond_gates(g, h, 0.1)
+        for _ in range(15):
+            rs.apply_operators(gates, trunc=chi, normalize=True)
+        info = rs.beliefpropagation(dict(maxiter=50, tol=1e-14), schedule="sequential")
+        assert info.delta < 1e-12
+        bond_energies = np.array(rs.expect_two_site(bond_hamiltonians(g, h)))
+        net = rs.state()
+    psi = dense_vector(net, g)
+    psi = psi / np.linalg.norm(psi)
+    energy = psi @ ham @ psi
+    assert np.abs(bond_energies.imag).max() < 1e-12 if np.iscomplexobj(bond_energies) else True
+    assert abs(bond_energies.real.sum() - energy) < 1e-9 * abs(energy)
+    assert e0 - 1e-10 <= energy < 0.9 * e0  # variational, and already close to the ground state after 15 steps
+
+
 @pytest.fixture
 def host_ctx(monkeypatch):
     lib = build_hostlib()
@@ -170,3 +202,8 @@ def test_tfi_comb_tree_ground_state_gpu():
 
 def test_tfi_comb_tree_ground_state_host_harness(host_ctx):
     evolve_and_check(graphs.named_comb_tree((3, 2)), chi=4, steps=(30, 30, 40))
+
+
+@pytest.mark.parametrize("graph", ["chain", "comb"])
+def test_energy_from_two_site_expectations_host_harness(host_ctx, graph):
+    check_energy_from_two_site_expectations(graphs.named_path_graph(5) if graph == "chain" else graphs.named_comb_tree((3, 2)))

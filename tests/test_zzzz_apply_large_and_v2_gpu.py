@@ -110,3 +110,37 @@ def test_chunked_layers_equal_one_launch(monkeypatch, v2):
     assert all(np.array_equal(x, y) for x, y in zip(sv_a, sv_b))
     assert all(np.array_equal(x, y) for x, y in zip(t_a, t_b))
     assert all(np.array_equal(x, y) for x, y in zip(m_a, m_b))
+
+
+# ---- two-site expectation values (csrc/bpx_expect2.cuh), never run on a GPU yet ------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_edge_expect_matches_oracle_gpu(oracle, dtype):
+    """bpx_edge_expect on every directed edge of a 4 x 4 PEPS (chi = 4) after a few sweeps, against
+    oracle.two_site_expect; the two orientations of an edge with the operator transposed accordingly agree."""
+    rng = np.random.default_rng(4)
+    p = problems.synthetic_peps(graphs.named_grid((4, 4)), 4, 2, dtype, init="positive")
+    ga = p.ga
+    edges = list(range(ga.ne))
+    ops = [randn(rng, dtype, (2, 2, 2, 2)) for _ in edges]
+    with B.BPXContext(0) as ctx:
+        problems.upload(ctx, p)
+        ctx.sweep(5, 0.0, True)
+        msgs = ctx.get_messages()
+        num, den = ctx.edge_expect(edges, ops)
+        swapped = [np.transpose(ops[e], (1, 0, 3, 2)) for e in edges]
+        num_r, den_r = ctx.edge_expect([ga.rev[e] for e in edges], swapped)
+        with pytest.raises(B.BPXError, match="out of range"):
+            ctx.edge_expect([ga.ne], [ops[0]])
+    op_ = oracle.make_problem(ga, p.tensors, "norm")
+    for e in edges:
+        want_num, want_den = oracle.two_site_expect(op_, msgs, e, ops[e])
+        assert np.isclose(num[e], want_num, rtol=1e-10, atol=1e-13 * abs(want_den))
+        assert np.isclose(den[e], want_den, rtol=1e-10)
+    assert np.allclose(num_r, num, rtol=1e-10, atol=1e-13 * np.abs(den).max()) and np.allclose(den_r, den, rtol=1e-10)
+
+
+@pytest.mark.parametrize("graph", ["chain", "comb"])
+def test_energy_from_two_site_expectations_gpu(graph):
+    from test_zzz_resident_state import check_energy_from_two_site_expectations
+
+    check_energy_from_two_site_expectations(graphs.named_path_graph(5) if graph == "chain" else graphs.named_comb_tree((3, 2)))
