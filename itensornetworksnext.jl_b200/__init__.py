@@ -20,6 +20,7 @@ from .beliefpropagation import (
 )
 from .apply import (
     ApplyOperatorAlgorithm, BPApplyGate, NoApplyOperatorEnvironmentPreparation, Operator, apply_operator, apply_operators,
+    expect_two_site,
 )
 from .device import BPXContext, fill_randn
 from .generators import delta, delta_network, diagonaltensor, ising_network, sqrt_ising_bond

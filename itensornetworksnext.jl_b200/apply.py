@@ -315,3 +315,25 @@ def _changes_bond(state: ITensorNetwork, vs: Sequence, trunc: Optional[int]) -> 
         bound.append(min(rows, d * chi) * d)
     k = min(bound) if trunc is None else min(int(trunc), min(bound))
     return k != chi
+
+
+def expect_two_site(operators: Sequence[Operator], state: ITensorNetwork, env, device: int = 0) -> List:
+    """<O> of two-site operators on neighbouring vertices of `state` in the BP environment `env` (bpx_edge_expect).
+    Build-defined like `expect` (the reference has neither); read-only, the operators may overlap."""
+    env = env if isinstance(env, MessageCache) else MessageCache(env)
+    operators = list(operators)
+    if not operators:
+        return []
+    s = _ApplySession(state, env, device)
+    try:
+        edges, lowered = [], []
+        for op in operators:
+            vs = _touched_vertices(op, state)
+            if len(vs) != 2 or vs[1] not in state.graph.neighbors(vs[0]):
+                raise ArgumentError("expect_two_site takes operators on two neighbouring vertices")
+            edges.append(s.cp.ga.edge_id(NamedEdge(vs[0], vs[1])))
+            lowered.append(_lowered_operator(op, state, vs, s.cp.dtype))
+        num, den = s.ctx.edge_expect(edges, lowered)
+        return list(num / den)
+    finally:
+        s.close()

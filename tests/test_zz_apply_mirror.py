@@ -142,6 +142,40 @@ def check_errors():
     assert out_net is not net and all(np.array_equal(out_net[v].data, net[v].data) for v in net.vertices())
 
 
+def check_expect_two_site(oracle, dtype):
+    """`expect_two_site` of the mirror (names -> canonical layout -> bpx_edge_expect) against the oracle on a 3 x 3 PEPS
+    whose site legs are NOT the first axis of the stored tensors."""
+    rng = np.random.default_rng(12)
+    g = graphs.named_grid((3, 3))
+    net, _, sites = B.random_state(dtype, g, d=2, chi=2, rng=rng)
+    # store every tensor with its site leg last: the lowering must permute by name
+    net = B.ITensorNetwork({v: B.ITensor(np.moveaxis(net[v].data, 0, -1), net[v].inds[1:] + net[v].inds[:1]) for v in net.vertices()})
+    nn = B.normnetwork(net)
+    cp = B.canonical_arrays(nn)
+    env_arrays = []
+    for e in range(cp.ga.ne):
+        f = randn(rng, dtype, (2, 2)) + 1.5 * np.eye(2)
+        env_arrays.append((f.conj().T @ f).astype(dtype))
+    cache = B.MessageCache({cp.ga.named_edge(e): B.ITensor(env_arrays[e], (B.Index(2, ("bra", cp.ket_names[e])), B.Index(2, cp.ket_names[e])))
+                            for e in range(cp.ga.ne)})
+    pairs = [((1, 1), (2, 1)), ((2, 2), (2, 3)), ((2, 3), (2, 2)), ((3, 3), (3, 2))]
+    ops = []
+    for v, w in pairs:
+        names = (sites[v].name, sites[w].name)
+        ops.append(B.Operator(randn(rng, dtype, (2, 2, 2, 2)), names, names))
+    got = B.expect_two_site(ops, net, cache)
+    p = oracle.make_problem(cp.ga, cp.tensors, "norm")
+    for (v, w), op, val in zip(pairs, ops, got):
+        # the lowering orders the two vertices as they appear in `vertices(state)`
+        first, second = (v, w) if cp.ga.vindex[v] < cp.ga.vindex[w] else (w, v)
+        o = op.data if (first, second) == (v, w) else np.transpose(op.data, (1, 0, 3, 2))
+        num, den = oracle.two_site_expect(p, env_arrays, cp.ga.edge_id(B.NamedEdge(first, second)), o)
+        assert np.isclose(val, num / den, rtol=1e-10, atol=1e-13)
+    with pytest.raises(B.ArgumentError, match="neighbouring"):
+        names = (sites[(1, 1)].name, sites[(3, 3)].name)
+        B.expect_two_site([B.Operator(np.zeros((2, 2, 2, 2)), names, names)], net, cache)
+
+
 # ---- CPU: lowering + device code on the host -----------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_mirror_known_answers_host_harness(oracle, host_ctx, dtype):
@@ -159,6 +193,11 @@ def test_mirror_matches_oracle_on_a_grid_host_harness(host_ctx, dtype):
 
 def test_mirror_errors_host_harness(host_ctx):
     check_errors()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_mirror_expect_two_site_host_harness(oracle, host_ctx, dtype):
+    check_expect_two_site(oracle, dtype)
 
 
 # ---- GPU: BP messages and gate application on the B200 ----------------------------------------------------------------

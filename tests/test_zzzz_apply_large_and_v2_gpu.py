@@ -144,3 +144,10 @@ def test_energy_from_two_site_expectations_gpu(graph):
     from test_zzz_resident_state import check_energy_from_two_site_expectations
 
     check_energy_from_two_site_expectations(graphs.named_path_graph(5) if graph == "chain" else graphs.named_comb_tree((3, 2)))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_mirror_expect_two_site_gpu(oracle, dtype):
+    from test_zz_apply_mirror import check_expect_two_site
+
+    check_expect_two_site(oracle, dtype)
