@@ -17,6 +17,8 @@ timeout 600 python tools/bench_apply.py --lattice 16 16 --chi 16 --layers 4 --or
 # 3b. the opt-in version 2 of the kernel (bpx_apply2.cuh), same workloads
 BPX_APPLY_V2=1 timeout 300 python tools/bench_apply.py --lattice 32 32 --chi 8 --layers 8 --oracle-gates 0 > $O/r2a_apply_v2_32x32_chi8.json 2> $O/r2a_apply_v2_32x32_chi8.err
 BPX_APPLY_V2=1 timeout 600 python tools/bench_apply.py --lattice 16 16 --chi 16 --layers 4 --oracle-gates 0 > $O/r2a_apply_v2_16x16_chi16.json 2> $O/r2a_apply_v2_16x16_chi16.err
+# 3c. a whole simple-update step (gate layers + BP sweeps + bond energies) on one context
+timeout 300 python tools/bench_simple_update.py --lattice 32 32 --chi 8 --steps 5 > $O/r2a_simple_update_32x32_chi8.json 2> $O/r2a_simple_update_32x32_chi8.err
 # 4. launch list + one full ncu capture of bp_apply_gates on the cfg2-shaped layer
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/r2a_launches_apply.csv \
   python tools/bench_apply.py --lattice 32 32 --chi 8 --layers 2 --oracle-gates 0 > $O/r2a_apply_under_ncu.log 2>&1
