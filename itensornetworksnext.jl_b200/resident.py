@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from .apply import (Operator, _ApplySession, _lowered_operator, _reference_rank, _touched_vertices)
-from .beliefpropagation import (ArgumentError, BeliefPropagationResult, MessageCache, _flatten_criterion,
+from .beliefpropagation import (ArgumentError, BeliefPropagationResult, MessageCache, _flatten_criterion, _NotFlat,
                                 select_beliefpropagation_stopping_criterion)
 from .graphs import NamedEdge, forest_cover_edge_sequence
 from .tensornetwork import Index, ITensor, ITensorNetwork
@@ -95,7 +95,11 @@ class ResidentState:
     # -- belief propagation on the norm network of the resident state (beliefpropagation.jl:69-92) -------------------
     def beliefpropagation(self, stopping_criterion=None, schedule: str = "synchronous", normalize: bool = True,
                           edges=None) -> BeliefPropagationResult:
-        maxiter, tol = _flatten_criterion(select_beliefpropagation_stopping_criterion(stopping_criterion))
+        try:
+            maxiter, tol = _flatten_criterion(select_beliefpropagation_stopping_criterion(stopping_criterion))
+        except _NotFlat:
+            raise ArgumentError("ResidentState.beliefpropagation takes StopAfterIteration / StopWhenConverged criteria "
+                                "(maxiter, tol); drive custom criteria through AI.solve with a DeviceMessageCache") from None
         maxiter = 2 ** 31 - 1 if maxiter is None else maxiter
         ctx, ga = self._s.ctx, self._s.cp.ga
         if schedule == "synchronous":
