@@ -541,3 +541,23 @@ def test_two_site_gate_fuzz(hostlib):
             worst = max(worst, np.abs(sv[:len(s_want)] - s_want).max() / s_want.max(),
                         np.abs(bond_product(got, 0, 1) - y).max() / np.abs(y).max())
     assert worst < 1e-9, worst
+
+
+def test_edge_expect_fuzz(oracle, hostlib):
+    """60 random shapes (degree 1-4, link dims 1-4, bond 1-5, d 1-3, both dtypes) against oracle.two_site_expect."""
+    rng = np.random.default_rng(77)
+    for it in range(60):
+        dtype = DTYPES[it % 2]
+        z, chi, chib, d = int(rng.integers(1, 5)), int(rng.integers(1, 5)), int(rng.integers(1, 6)), int(rng.integers(1, 4))
+        adj, state, env = star_pair(rng, dtype, z, chi, d, chi_bond=chib)
+        ga, p = oracle_problem_from_state(oracle, adj, state)
+        msgs = [env[(ga.vertices[ga.src[e]], ga.vertices[ga.dst[e]])] for e in range(ga.ne)]
+        o = randn(rng, dtype, (d, d, d, d))
+        want_num, want_den = oracle.two_site_expect(p, msgs, ga.edge_index[(0, 1)], o)
+        a1, a2 = side_args(state, env, adj, 0, 1), side_args(state, env, adj, 1, 0)
+        num, den = np.zeros(1, dtype=dtype), np.zeros(1, dtype=dtype)
+        op = fcopy(o).ravel(order="F").copy()
+        hostlib.apply_host_edge_expect(code(dtype), a1[0], a1[1], a1[2], ptr(a1[3]), ptr(a1[4]), ptr(a1[5]), a2[0], a2[1], a2[2],
+                                       ptr(a2[3]), ptr(a2[4]), ptr(a2[5]), ptr(op), ptr(num), ptr(den))
+        assert np.isclose(den[0], want_den, rtol=1e-11)
+        assert np.isclose(num[0], want_num, rtol=1e-10, atol=1e-13 * abs(want_den))
