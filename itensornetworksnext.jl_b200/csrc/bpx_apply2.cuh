@@ -1,6 +1,7 @@
 // Two-site gate application, version 2 (OPT-IN: BPX_APPLY_V2=1; bp_apply_gates of bpx_apply.cuh stays the default until
-// this one has been run and measured on a B200 -- it was written after round 1's GPU budget had ended and has so far
-// only been verified on the host through tests/native/apply_host.cu, like every routine of bpx_apply.cuh).
+// this one has been MEASURED on a B200).  Developed on the host (tests/native: host-compiled device code, ThreadSanitizer
+// schedules) when round 1's GPU budget was all but spent; its first GPU run matched version 1 in all six cases of
+// tests/test_zzzz_apply_large_and_v2_gpu.py::test_v2_matches_v1 (profiles/r1o_late_pytest_gpu.txt).
 //
 // Same algorithm and same building blocks as version 1 (apply_operators.jl:246-283; jacobi_cols, gauge_from_message,
 // householder_qr, apply_q, mode_product), reorganised around MEMORY TRAFFIC.  Version 1 keeps the rows x cols matrix
