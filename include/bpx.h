@@ -15,8 +15,9 @@
  *     a context is available from bpx_last_error().  No C++ exception crosses this boundary.
  *   - plain pointers and sizes only.  Host buffers are owned by the caller and are only touched during
  *     the call (all calls are synchronous w.r.t. the host buffers they read or write).
- *   - the library owns all device memory.  A context is bound to ONE CUDA device (one process per GPU;
- *     multi-GPU runs create one context per rank and connect them with bpx_halo_*).
+ *   - the library owns all device memory.  A context made by bpx_create is bound to ONE CUDA device; multi-GPU runs
+ *     either use ONE context over a device list (bpx_create_multi: single process, what a `beliefpropagation()` call
+ *     needs) or one context per rank/process connected with bpx_halo_* (what torchrun / MPI launchers need).
  *   - a context is not thread-safe; several contexts may coexist.
  *   - there is no CPU fallback: every compute entry point fails with BPX_ERR_CUDA if no sm_100 device
  *     is usable.
@@ -70,6 +71,23 @@ int bpx_version(void);
 
 /* ---- context ------------------------------------------------------------------------------------ */
 int bpx_create(int device, bpx_ctx** out);
+/* Single-process multi-GPU (the reference is one call tree on one task, beliefpropagation.jl:69-92): ONE context over
+ * `ndev` devices.  Every entry point of this header works on it unchanged: the problem is described once, the library
+ * partitions the vertices over the devices (balanced contiguous blocks of the vertex order; bpx_set_owner overrides), each
+ * device stores the site tensors it owns and updates the out-edges of its vertices, cut-edge messages are stored
+ * straight into the owning device's message set over NVLink and the residual is max-reduced through peer mailboxes inside
+ * the sweep kernels (cudaDeviceEnablePeerAccess + plain pointers; no IPC handles, no process group, no NCCL).  All
+ * launches are asynchronous and issued from the calling thread.  Results do not depend on the number of devices for the
+ * on-chip kernel families (same per-vertex arithmetic); see DESIGN.md for the sliced kernel.
+ * Not available on such a context: bpx_set_stream (one internal stream per device), bpx_device_* pointers, the per-rank
+ * halo calls, bpx_sweep_sequence / bpx_iterate_diff (single device only), gates and two-site expectation values across
+ * a cut edge (BPX_ERR_UNSUPPORTED, as on per-rank contexts). */
+int bpx_create_multi(const int* devices, int ndev, bpx_ctx** out);
+int bpx_num_devices(const bpx_ctx* ctx);
+/* multi-device contexts: owner[v] = index into `devices` of the device that updates the out-edges of v (after
+ * bpx_set_dims; site tensors already uploaded stay where they are needed).  bpx_get_owner reads the partition in use. */
+int bpx_set_owner(bpx_ctx* ctx, const int32_t* owner);
+int bpx_get_owner(const bpx_ctx* ctx, int32_t* owner_out /* nv */);
 int bpx_destroy(bpx_ctx* ctx);
 /* ctx may be NULL: returns the message of the last failed bpx_create on this thread. */
 const char* bpx_last_error(const bpx_ctx* ctx);
@@ -106,10 +124,13 @@ int bpx_get_message(bpx_ctx* ctx, int64_t e, void* data);
  * bpx_sweep: up to `max_sweeps` SYNCHRONOUS sweeps.  One sweep performs, for every directed edge,
  * `message_update!(::SimpleMessageUpdate, cache, factors, edge)` (beliefpropagation.jl:242-257) from the
  * previous sweep's messages, with the sum-normalisation (:248-253, `normalize` != 0) and the per-edge
- * term of `iterate_diff` (:261-267) fused into the kernel epilogue.  After each sweep the maximum
- * residual is compared with `tol` on the device: the loop stops after the first sweep whose residual
- * is < tol (StopWhenConverged, AlgorithmsInterfaceExtensions.jl:84-119) or after max_sweeps
- * (StopAfterIteration).  tol <= 0 disables the convergence test.
+ * term of `iterate_diff` (:261-267) fused into the kernel epilogue.  The loop stops after the first sweep
+ * whose maximum residual is < tol (StopWhenConverged, AlgorithmsInterfaceExtensions.jl:84-119) or after
+ * max_sweeps (StopAfterIteration); tol <= 0 disables the convergence test.  On a single device the test runs ON
+ * THE DEVICE: sweeps are enqueued in batches (4, 8, 16, ...) ahead of the host and every launch of a sweep first
+ * checks the previous sweep's residual key, turning into a no-op once it is below tol -- the iterate is exactly
+ * the one after the first converged sweep, and the host synchronises once per batch instead of once per sweep.
+ * Partitioned / multi-device contexts check the GLOBAL residual on the host after every sweep.
  * residual_out: residual of the last executed sweep; sweeps_done: number executed (either may be NULL). */
 int bpx_sweep(bpx_ctx* ctx, int max_sweeps, double tol, int normalize, double* residual_out,
               int* sweeps_done);

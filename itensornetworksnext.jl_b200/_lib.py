@@ -51,6 +51,10 @@ def load() -> C.CDLL:
     sig = {
         "bpx_version": (C.c_int, []),
         "bpx_create": (C.c_int, [C.c_int, P(vp)]),
+        "bpx_create_multi": (C.c_int, [vp, C.c_int, P(vp)]),
+        "bpx_num_devices": (C.c_int, [vp]),
+        "bpx_set_owner": (C.c_int, [vp, vp]),
+        "bpx_get_owner": (C.c_int, [vp, vp]),
         "bpx_destroy": (C.c_int, [vp]),
         "bpx_last_error": (C.c_char_p, [vp]),
         "bpx_set_graph": (C.c_int, [vp, i64, i64, vp, vp, vp]),

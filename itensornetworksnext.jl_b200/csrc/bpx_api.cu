@@ -42,6 +42,18 @@ void bpx::set_error(bpx_ctx* ctx, const char* fmt, ...) {
     }                                     \
   } while (0)
 
+static int sweep_once(bpx_ctx* ctx, int normalize);
+static int residual_read(bpx_ctx* ctx, int idx, double* out);
+static int residual_ring_clear(bpx_ctx* ctx);
+static int sweep_host_staged_enqueue(bpx_ctx* ctx, const void* packed_in, void* packed_out, int normalize);
+static int sweep_host_staged_finish(bpx_ctx* ctx, double* residual_out);
+#include "bpx_multi.cuh"  // single-process multi-GPU: a parent context fans every entry point out to one child per device
+#define MULTI(ctx, expr)                                   \
+  do {                                                     \
+    if ((ctx) && !(ctx)->children.empty()) return (expr);  \
+  } while (0)
+#define MULTI0(ctx) ((ctx)->children[0])
+
 template <typename T>
 static int dev_alloc(bpx_ctx* ctx, T** p, size_t count) {
   *p = nullptr;
@@ -93,6 +105,11 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_fast_scratch);
   F(c->d_onchip_items);
   F(c->d_sliced_items);
+  F(c->d_sliced2_items);
+  F(c->d_sliced2_group_ptr);
+  F(c->d_sliced2_partials);
+  F(c->d_sliced2_gsync);
+  c->n_sliced2_groups = c->n_sliced2_items = 0;
   F(c->d_onchip16_items);
   F(c->d_onchip16c_items);
   F(c->d_onchip8c_items);
@@ -165,6 +182,7 @@ extern "C" int bpx_create(int device, bpx_ctx** out) {
 }
 
 extern "C" int bpx_destroy(bpx_ctx* ctx) {
+  MULTI(ctx, bpx::multi::destroy(ctx));
   if (!ctx) return BPX_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -188,6 +206,7 @@ extern "C" const char* bpx_last_error(const bpx_ctx* ctx) { return ctx ? ctx->er
 // ---- problem description -----------------------------------------------------------------------
 extern "C" int bpx_set_graph(bpx_ctx* ctx, int64_t nv, int64_t ne, const int64_t* src, const int64_t* dst,
                              const int32_t* slot) {
+  MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_set_graph(c, nv, ne, src, dst, slot); }));
   if (!ctx) return BPX_ERR_INVALID;
   REQUIRE(ctx, nv >= 0 && ne >= 0 && (ne == 0 || (src && dst && slot)), "bpx_set_graph: bad arguments");
   REQUIRE(ctx, nv < (1ll << 31) && ne < (1ll << 31), "bpx_set_graph: more than 2^31 vertices/edges");
@@ -235,6 +254,7 @@ extern "C" int bpx_set_graph(bpx_ctx* ctx, int64_t nv, int64_t ne, const int64_t
 static int pick_kernel(bpx_ctx* ctx, const Bucket& b);
 
 extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* phys_dim, const int32_t* link_dim) {
+  MULTI(ctx, bpx::multi::set_dims(ctx, dtype, mode, phys_dim, link_dim));
   if (!ctx) return BPX_ERR_INVALID;
   REQUIRE(ctx, ctx->graph_set, "bpx_set_dims: call bpx_set_graph first");
   REQUIRE(ctx, dtype == BPX_F64 || dtype == BPX_C64, "bpx_set_dims: unknown dtype %d", dtype);
@@ -486,18 +506,22 @@ static int pick_kernel(bpx_ctx* ctx, const Bucket& b) {
   return fast_kernel_supported(ctx, b, want) ? want : BPX_KERNEL_GENERIC;
 }
 
-extern "C" int64_t bpx_num_vertices(const bpx_ctx* ctx) { return ctx ? ctx->nv : -1; }
-extern "C" int64_t bpx_num_edges(const bpx_ctx* ctx) { return ctx ? ctx->ne : -1; }
+extern "C" int64_t bpx_num_vertices(const bpx_ctx* ctx) { return !ctx ? -1 : (ctx->children.empty() ? ctx->nv : ctx->children[0]->nv); }
+extern "C" int64_t bpx_num_edges(const bpx_ctx* ctx) { return !ctx ? -1 : (ctx->children.empty() ? ctx->ne : ctx->children[0]->ne); }
 extern "C" int64_t bpx_rev(const bpx_ctx* ctx, int64_t e) {
+  if (ctx && !ctx->children.empty()) return bpx_rev(ctx->children[0], e);
   return (ctx && ctx->graph_set && e >= 0 && e < ctx->ne) ? ctx->rev[e] : -1;
 }
 extern "C" int64_t bpx_site_offset(const bpx_ctx* ctx, int64_t v) {
+  if (ctx && !ctx->children.empty()) return bpx_site_offset(ctx->children[0], v);
   return (ctx && ctx->dims_set && v >= 0 && v <= ctx->nv) ? ctx->site_off[v] : -1;
 }
 extern "C" int64_t bpx_site_device_offset(const bpx_ctx* ctx, int64_t v) {
+  if (ctx && !ctx->children.empty()) return (v < 0 || v >= ctx->nv) ? -1 : bpx_site_device_offset(ctx->children[ctx->multi_owner.empty() ? 0 : ctx->multi_owner[v]], v);
   return (ctx && ctx->dims_set && v >= 0 && v < ctx->nv) ? ctx->dev_site_off[v] : -1;
 }
 extern "C" int64_t bpx_message_offset(const bpx_ctx* ctx, int64_t e) {
+  if (ctx && !ctx->children.empty()) return bpx_message_offset(ctx->children[0], e);
   return (ctx && ctx->dims_set && e >= 0 && e <= ctx->ne) ? ctx->msg_off[e] : -1;
 }
 
@@ -508,10 +532,8 @@ extern "C" int64_t bpx_message_offset(const bpx_ctx* ctx, int64_t e) {
     BPX_CUDA(ctx, cudaSetDevice(ctx->device));                   \
   } while (0)
 
-static int sweep_once(bpx_ctx* ctx, int normalize);
-static int residual_read(bpx_ctx* ctx, int idx, double* out);
-
 extern "C" int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed) {
+  MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_set_site_tensors(c, packed); }));
   NEED_DIMS(ctx, "bpx_set_site_tensors");
   REQUIRE(ctx, packed || ctx->site_off[ctx->nv] == 0, "bpx_set_site_tensors: NULL data");
   // a rank only needs the tensors it owns, but uploading all keeps offsets identical everywhere
@@ -536,6 +558,7 @@ extern "C" int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed) {
 }
 
 extern "C" int bpx_set_site_tensor(bpx_ctx* ctx, int64_t v, const void* data) {
+  MULTI(ctx, (v < 0 || v >= ctx->nv) ? (int)BPX_ERR_INVALID : bpx::multi::fail(ctx, bpx::multi::owner_of(ctx, v), bpx_set_site_tensor(bpx::multi::owner_of(ctx, v), v, data)));
   NEED_DIMS(ctx, "bpx_set_site_tensor");
   REQUIRE(ctx, v >= 0 && v < ctx->nv && data, "bpx_set_site_tensor: bad arguments");
   if (ctx->dev_site_off[v] < 0) return BPX_OK;  // not resident on this rank
@@ -547,6 +570,7 @@ extern "C" int bpx_set_site_tensor(bpx_ctx* ctx, int64_t v, const void* data) {
 }
 
 extern "C" int bpx_set_messages(bpx_ctx* ctx, const void* packed) {
+  MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_set_messages(c, packed); }));
   NEED_DIMS(ctx, "bpx_set_messages");
   REQUIRE(ctx, packed || ctx->msg_off[ctx->ne] == 0, "bpx_set_messages: NULL data");
   const size_t n = (size_t)ctx->msg_off[ctx->ne] * ctx->esize;
@@ -679,7 +703,32 @@ static int enqueue_streamed_step(bpx_ctx* ctx, const void* packed_in, void* out_
   return BPX_OK;  // (single rank: the residual key arrives in pinned host memory from the kernel's last CTA)
 }
 
+// staged host step, first half: everything is enqueued, nothing waits (a multi-device context enqueues all its devices
+// before the first of them waits for its peers)
+static int sweep_host_staged_enqueue(bpx_ctx* ctx, const void* packed_in, void* packed_out, int normalize) {
+  int rc;
+  if (ctx->nranks == 1) ctx->cur = 0;
+  if ((rc = halo_gate(ctx))) return rc;
+  for (auto& r : ctx->owned_runs) {
+    const size_t o = (size_t)r.first * ctx->esize, len = (size_t)(r.second - r.first) * ctx->esize;
+    BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_msg[ctx->cur] + o, (const char*)packed_in + o, len, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if ((rc = sweep_once(ctx, normalize))) return rc;
+  for (auto& r : ctx->owned_runs) {
+    const size_t o = (size_t)r.first * ctx->esize, len = (size_t)(r.second - r.first) * ctx->esize;
+    BPX_CUDA(ctx, cudaMemcpyAsync((char*)packed_out + o, (const char*)ctx->d_msg[ctx->cur] + o, len, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return BPX_OK;
+}
+// ... second half: the (global) residual; synchronises the stream
+static int sweep_host_staged_finish(bpx_ctx* ctx, double* residual_out) {
+  int rc;
+  if ((rc = halo_gate(ctx))) return rc;
+  return residual_read(ctx, ctx->history_len - 1, residual_out);
+}
+
 extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_out, int normalize, double* residual_out) {
+  MULTI(ctx, bpx::multi::sweep_host(ctx, packed_in, packed_out, normalize, residual_out));
   NEED_DIMS(ctx, "bpx_sweep_host");
   REQUIRE(ctx, (packed_in && packed_out) || ctx->msg_off[ctx->ne] == 0, "bpx_sweep_host: NULL buffer");
   REQUIRE(ctx, ctx->nranks == 1 || ctx->halo_connected, "bpx_sweep_host: partitioned context without connected peers");
@@ -780,25 +829,15 @@ extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_
   }
   if (!out_alias) {
     // ---- staged: upload the owned messages, sweep, download the owned messages ----
-    if (single) ctx->cur = 0;
-    if ((rc = halo_gate(ctx))) return rc;
-    for (auto& r : ctx->owned_runs) {
-      const size_t o = (size_t)r.first * ctx->esize, len = (size_t)(r.second - r.first) * ctx->esize;
-      BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_msg[ctx->cur] + o, (const char*)packed_in + o, len, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    if ((rc = sweep_once(ctx, normalize))) return rc;
-    for (auto& r : ctx->owned_runs) {
-      const size_t o = (size_t)r.first * ctx->esize, len = (size_t)(r.second - r.first) * ctx->esize;
-      BPX_CUDA(ctx, cudaMemcpyAsync((char*)packed_out + o, (const char*)ctx->d_msg[ctx->cur] + o, len, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    if ((rc = halo_gate(ctx))) return rc;
-    if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) return rc;  // synchronises the stream
+    if ((rc = sweep_host_staged_enqueue(ctx, packed_in, packed_out, normalize))) return rc;
+    if ((rc = sweep_host_staged_finish(ctx, &res))) return rc;
   }
   if (residual_out) *residual_out = res;
   return BPX_OK;
 }
 
 extern "C" int bpx_host_register(bpx_ctx* ctx, void* ptr, size_t bytes) {
+  MULTI(ctx, bpx::multi::fail(ctx, MULTI0(ctx), bpx_host_register(MULTI0(ctx), ptr, bytes)));
   if (!ctx) return BPX_ERR_INVALID;
   REQUIRE(ctx, ptr && bytes > 0, "bpx_host_register: bad arguments");
   cudaSetDevice(ctx->device);
@@ -807,6 +846,7 @@ extern "C" int bpx_host_register(bpx_ctx* ctx, void* ptr, size_t bytes) {
 }
 
 extern "C" int bpx_host_unregister(bpx_ctx* ctx, void* ptr) {
+  MULTI(ctx, bpx::multi::fail(ctx, MULTI0(ctx), bpx_host_unregister(MULTI0(ctx), ptr)));
   if (!ctx) return BPX_ERR_INVALID;
   REQUIRE(ctx, ptr != nullptr, "bpx_host_unregister: NULL pointer");
   cudaSetDevice(ctx->device);
@@ -816,6 +856,7 @@ extern "C" int bpx_host_unregister(bpx_ctx* ctx, void* ptr) {
 }
 
 extern "C" int bpx_get_messages(bpx_ctx* ctx, void* packed) {
+  MULTI(ctx, bpx::multi::get_messages(ctx, packed));
   NEED_DIMS(ctx, "bpx_get_messages");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, packed || ctx->msg_off[ctx->ne] == 0, "bpx_get_messages: NULL data");
@@ -826,6 +867,7 @@ extern "C" int bpx_get_messages(bpx_ctx* ctx, void* packed) {
 }
 
 extern "C" int bpx_get_message(bpx_ctx* ctx, int64_t e, void* data) {
+  MULTI(ctx, (e < 0 || e >= ctx->ne) ? (int)BPX_ERR_INVALID : bpx::multi::fail(ctx, bpx::multi::owner_of(ctx, MULTI0(ctx)->src[e]), bpx_get_message(bpx::multi::owner_of(ctx, MULTI0(ctx)->src[e]), e, data)));
   NEED_DIMS(ctx, "bpx_get_message");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, e >= 0 && e < ctx->ne && data, "bpx_get_message: bad arguments");
@@ -869,6 +911,7 @@ int bpx::launch_generic_update(bpx_ctx* ctx, const void* msg_in, void* msg_out, 
   if (n_work == 0) return BPX_OK;
   GenericArgs g = generic_args(ctx, msg_in, msg_out, d_work, n_work, normalize);
   g.resmax = resmax;
+  g.stop_key = resmax ? ctx->stop_key : 0ull;
   const int grid = (int)std::min<int64_t>(n_work, ctx->gen_grid);
   int rc;
   if (ctx->dtype == BPX_F64) {
@@ -1013,17 +1056,65 @@ static int sweep_once(bpx_ctx* ctx, int normalize) {
 }
 
 extern "C" int bpx_sweep(bpx_ctx* ctx, int max_sweeps, double tol, int normalize, double* residual_out, int* sweeps_done) {
+  MULTI(ctx, bpx::multi::sweep(ctx, max_sweeps, tol, normalize, residual_out, sweeps_done));
   NEED_DIMS(ctx, "bpx_sweep");
   REQUIRE(ctx, max_sweeps >= 0, "bpx_sweep: max_sweeps < 0");
   int done = 0, rc;
   double res = INFINITY;
   if ((rc = halo_gate(ctx))) return rc;
   if ((rc = residual_ring_clear(ctx))) return rc;
+  if (tol > 0.0 && ctx->nranks == 1 && !getenv("BPX_HOST_STOP")) {
+    // StopWhenConverged ON THE DEVICE (AlgorithmsInterfaceExtensions.jl:84-119): sweeps are enqueued in batches ahead of
+    // the host; every launch of a sweep first looks at the previous sweep's final residual key and turns into a no-op
+    // once it is below the tolerance (sweep_already_converged), so the iterate is exactly the one after the first
+    // converged sweep however many sweeps were enqueued.  The host synchronises once per BATCH (4, 8, 16, 16, ...) to
+    // read the keys and stop enqueuing -- not once per sweep.
+    const unsigned long long tol_key = residual_key(tol);
+    const int cur0 = ctx->cur;
+    const int64_t sweeps0 = ctx->n_sweeps, updates0 = ctx->n_updates;
+    int batch = 4;
+    bool converged = false;
+    std::vector<unsigned long long> keys;
+    while (done < max_sweeps && !converged) {
+      if (ctx->history_len >= ctx->history_cap && (rc = residual_ring_clear(ctx))) return rc;  // (host is in sync here)
+      const int first = ctx->history_len;
+      const int nb = std::min(std::min(batch, max_sweeps - done), ctx->history_cap - first);
+      for (int b = 0; b < nb; ++b) {
+        ctx->stop_key = ctx->history_len > first || first > 0 ? tol_key : 0ull;  // slot[-1] exists and belongs to this call
+        rc = sweep_once(ctx, normalize);
+        ctx->stop_key = 0ull;
+        if (rc) return rc;
+      }
+      keys.resize(nb);
+      BPX_CUDA(ctx, cudaMemcpyAsync(keys.data(), ctx->d_reskeys + first, nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+      BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      int ran = nb;
+      for (int b = 0; b < nb; ++b) {
+        res = residual_from_key(keys[b]);
+        if (res < tol) {
+          converged = true;
+          ran = b + 1;  // sweeps b+1 .. nb-1 of the batch were no-ops
+          break;
+        }
+      }
+      done += ran;
+      ctx->history_len = first + ran;
+      batch = std::min(16, batch * 2);
+    }
+    // host-side bookkeeping of the sweeps that really ran
+    ctx->cur = cur0 ^ (done & 1);
+    ctx->n_sweeps = sweeps0 + done;
+    ctx->n_updates = updates0 + (int64_t)done * ctx->n_owned_edges;
+    if (residual_out) *residual_out = res;
+    if (sweeps_done) *sweeps_done = done;
+    return BPX_OK;
+  }
   for (int it = 0; it < max_sweeps; ++it) {
     if ((rc = sweep_once(ctx, normalize))) return rc;
     ++done;
     if (tol > 0.0) {
-      // StopWhenConverged: stop after the first sweep whose (global) residual is below tol
+      // StopWhenConverged: stop after the first sweep whose (global) residual is below tol; partitioned contexts need
+      // every rank's post of the sweep, so the host checks after each one
       if ((rc = halo_gate(ctx))) return rc;
       if ((rc = residual_read(ctx, ctx->history_len - 1, &res))) return rc;
       if (res < tol) break;
@@ -1048,6 +1139,7 @@ extern "C" int bpx_sweep(bpx_ctx* ctx, int max_sweeps, double tol, int normalize
 }
 
 extern "C" int bpx_sweep_async(bpx_ctx* ctx, int n_sweeps, int normalize) {
+  MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_sweep_async(c, n_sweeps, normalize); }));
   NEED_DIMS(ctx, "bpx_sweep_async");
   REQUIRE(ctx, n_sweeps >= 0, "bpx_sweep_async: n_sweeps < 0");
   for (int it = 0; it < n_sweeps; ++it) {
@@ -1058,6 +1150,7 @@ extern "C" int bpx_sweep_async(bpx_ctx* ctx, int n_sweeps, int normalize) {
 }
 
 extern "C" int bpx_set_profiling(bpx_ctx* ctx, int enable) {
+  MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_set_profiling(c, enable); }));
   NEED_DIMS(ctx, "bpx_set_profiling");
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (auto& b : ctx->buckets) {
@@ -1074,6 +1167,7 @@ extern "C" int bpx_set_profiling(bpx_ctx* ctx, int enable) {
 }
 
 extern "C" int bpx_bucket_time(bpx_ctx* ctx, int bucket, double* total_ms, int64_t* launches) {
+  MULTI(ctx, bpx::multi::fail(ctx, MULTI0(ctx), bpx_bucket_time(MULTI0(ctx), bucket, total_ms, launches)));
   NEED_DIMS(ctx, "bpx_bucket_time");
   REQUIRE(ctx, bucket >= 0 && bucket < (int)ctx->buckets.size(), "bpx_bucket_time: bucket out of range");
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1094,6 +1188,7 @@ extern "C" int bpx_bucket_time(bpx_ctx* ctx, int bucket, double* total_ms, int64
 
 extern "C" int bpx_sweep_sequence(bpx_ctx* ctx, const int64_t* edge_seq, int64_t n_seq, int max_sweeps, double tol,
                                   int normalize, double* residual_out, int* sweeps_done) {
+  MULTI(ctx, bpx::multi::fail(ctx, MULTI0(ctx), bpx_sweep_sequence(MULTI0(ctx), edge_seq, n_seq, max_sweeps, tol, normalize, residual_out, sweeps_done)));
   NEED_DIMS(ctx, "bpx_sweep_sequence");
   REQUIRE(ctx, ctx->nranks == 1, "bpx_sweep_sequence: the sequential schedule is single-GPU only");
   REQUIRE(ctx, max_sweeps >= 0 && n_seq >= 0 && (n_seq == 0 || edge_seq), "bpx_sweep_sequence: bad arguments");
@@ -1181,6 +1276,7 @@ extern "C" int bpx_sweep_sequence(bpx_ctx* ctx, const int64_t* edge_seq, int64_t
 }
 
 extern "C" int bpx_residual_history(bpx_ctx* ctx, double* out, int n, int* n_out) {
+  MULTI(ctx, bpx::multi::fail(ctx, MULTI0(ctx), bpx_residual_history(MULTI0(ctx), out, n, n_out)));
   NEED_DIMS(ctx, "bpx_residual_history");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   const int k = std::max(0, std::min(n, ctx->history_len));
@@ -1196,6 +1292,7 @@ extern "C" int bpx_residual_history(bpx_ctx* ctx, double* out, int n, int* n_out
 }
 
 extern "C" int bpx_last_residual(bpx_ctx* ctx, double* out) {
+  MULTI(ctx, bpx::multi::fail(ctx, MULTI0(ctx), bpx_last_residual(MULTI0(ctx), out)));
   NEED_DIMS(ctx, "bpx_last_residual");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, out, "bpx_last_residual: out is NULL");
@@ -1207,6 +1304,7 @@ extern "C" int bpx_last_residual(bpx_ctx* ctx, double* out) {
 }
 
 extern "C" int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* out) {
+  MULTI(ctx, bpx::multi::fail(ctx, MULTI0(ctx), bpx_iterate_diff(MULTI0(ctx), other_packed, out)));
   NEED_DIMS(ctx, "bpx_iterate_diff");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, out && (other_packed || ctx->ne == 0), "bpx_iterate_diff: bad arguments");
@@ -1286,12 +1384,14 @@ static int vertex_scalars_impl(bpx_ctx* ctx, const void* ops_packed, void* out) 
 }
 
 extern "C" int bpx_vertex_scalars(bpx_ctx* ctx, void* out) {
+  MULTI(ctx, bpx::multi::merge_vertex(ctx, out, [&](bpx_ctx* c, void* o) -> int { return bpx_vertex_scalars(c, o); }));
   NEED_DIMS(ctx, "bpx_vertex_scalars");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   return vertex_scalars_impl(ctx, nullptr, out);
 }
 
 extern "C" int bpx_vertex_expect_numerators(bpx_ctx* ctx, const void* ops_packed, void* out) {
+  MULTI(ctx, bpx::multi::merge_vertex(ctx, out, [&](bpx_ctx* c, void* o) -> int { return bpx_vertex_expect_numerators(c, ops_packed, o); }));
   NEED_DIMS(ctx, "bpx_vertex_expect_numerators");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   REQUIRE(ctx, ctx->mode == BPX_MODE_NORM, "bpx_vertex_expect_numerators: NORM mode only");
@@ -1300,6 +1400,7 @@ extern "C" int bpx_vertex_expect_numerators(bpx_ctx* ctx, const void* ops_packed
 }
 
 extern "C" int bpx_edge_scalars(bpx_ctx* ctx, void* out) {
+  MULTI(ctx, bpx::multi::edge_scalars(ctx, out));
   NEED_DIMS(ctx, "bpx_edge_scalars");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
   const int64_t n = ctx->n_und;
@@ -1327,9 +1428,22 @@ extern "C" int bpx_edge_scalars(bpx_ctx* ctx, void* out) {
 }
 
 // ---- introspection ------------------------------------------------------------------------------
-extern "C" int bpx_num_buckets(const bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? (int)ctx->buckets.size() : -1; }
+extern "C" int bpx_num_buckets(const bpx_ctx* ctx) {
+  if (ctx && !ctx->children.empty()) return bpx_num_buckets(ctx->children[0]);
+  return (ctx && ctx->dims_set) ? (int)ctx->buckets.size() : -1;
+}
 
 extern "C" int bpx_bucket_info(const bpx_ctx* ctx, int bucket, int64_t info[8]) {
+  if (ctx && !ctx->children.empty()) {  // a child's view, with the vertex / edge counts summed over the devices
+    int rc = bpx_bucket_info(ctx->children[0], bucket, info);
+    for (size_t k = 1; k < ctx->children.size() && rc == BPX_OK; ++k) {
+      int64_t t[8];
+      rc = bpx_bucket_info(ctx->children[k], bucket, t);
+      info[3] += t[3];
+      info[4] += t[4];
+    }
+    return rc;
+  }
   if (!ctx || !ctx->dims_set || bucket < 0 || bucket >= (int)ctx->buckets.size() || !info) return BPX_ERR_INVALID;
   const Bucket& b = ctx->buckets[bucket];
   info[0] = b.z;
@@ -1344,6 +1458,7 @@ extern "C" int bpx_bucket_info(const bpx_ctx* ctx, int bucket, int64_t info[8]) 
 }
 
 extern "C" int bpx_set_kernel_policy(bpx_ctx* ctx, int kernel) {
+  MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_set_kernel_policy(c, kernel); }));
   if (!ctx) return BPX_ERR_INVALID;
   REQUIRE(ctx, kernel >= BPX_KERNEL_AUTO && kernel <= BPX_KERNEL_VERTEX, "bpx_set_kernel_policy: unknown kernel %d", kernel);
   ctx->kernel_policy = kernel;
@@ -1355,6 +1470,7 @@ extern "C" int bpx_set_kernel_policy(bpx_ctx* ctx, int kernel) {
 }
 
 extern "C" int bpx_counters(bpx_ctx* ctx, int64_t out[3], int reset) {
+  MULTI(ctx, bpx::multi::counters(ctx, out, reset));
   if (!ctx) return BPX_ERR_INVALID;
   if (out) {
     out[0] = ctx->n_launches;
@@ -1366,6 +1482,7 @@ extern "C" int bpx_counters(bpx_ctx* ctx, int64_t out[3], int reset) {
 }
 
 extern "C" int bpx_set_stream(bpx_ctx* ctx, void* cuda_stream) {
+  MULTI(ctx, bpx::multi::set_stream(ctx, cuda_stream));
   if (!ctx) return BPX_ERR_INVALID;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -1375,6 +1492,7 @@ extern "C" int bpx_set_stream(bpx_ctx* ctx, void* cuda_stream) {
 
 // ---- the consumer of the messages: BP simple-update gate application (bpx_apply.cuh) ---------------------------
 extern "C" int bpx_get_site_tensor(bpx_ctx* ctx, int64_t v, void* data) {
+  MULTI(ctx, (v < 0 || v >= ctx->nv) ? (int)BPX_ERR_INVALID : bpx::multi::fail(ctx, bpx::multi::owner_of(ctx, v), bpx_get_site_tensor(bpx::multi::owner_of(ctx, v), v, data)));
   NEED_DIMS(ctx, "bpx_get_site_tensor");
   REQUIRE(ctx, v >= 0 && v < ctx->nv && data, "bpx_get_site_tensor: bad arguments");
   REQUIRE(ctx, ctx->dev_site_off[v] >= 0, "bpx_get_site_tensor: vertex %lld is not resident on this rank", (long long)v);
@@ -1504,6 +1622,7 @@ static int apply_owned_check(bpx_ctx* ctx, const char* name, int64_t g, int64_t 
 
 extern "C" int bpx_apply_two_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* edges, const void* ops_packed,
                                         int max_rank, int normalize, double* singular_values_out) {
+  MULTI(ctx, bpx::multi::apply_two(ctx, n_gates, edges, ops_packed, max_rank, normalize, singular_values_out));
   NEED_DIMS(ctx, "bpx_apply_two_site_gates");
   int rc = apply_common_checks(ctx, "bpx_apply_two_site_gates");
   if (rc) return rc;
@@ -1559,6 +1678,7 @@ extern "C" int bpx_apply_two_site_gates(bpx_ctx* ctx, int64_t n_gates, const int
 
 extern "C" int bpx_apply_one_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* vertices, const void* ops_packed,
                                         int normalize) {
+  MULTI(ctx, bpx::multi::apply_one(ctx, n_gates, vertices, ops_packed, normalize));
   NEED_DIMS(ctx, "bpx_apply_one_site_gates");
   int rc = apply_common_checks(ctx, "bpx_apply_one_site_gates");
   if (rc) return rc;
@@ -1588,6 +1708,7 @@ extern "C" int bpx_apply_one_site_gates(bpx_ctx* ctx, int64_t n_gates, const int
 // ---- two-site expectation values in the BP environment (bpx_expect2.cuh) ------------------------------------
 extern "C" int bpx_edge_expect(bpx_ctx* ctx, int64_t n_edges, const int64_t* edges, const void* ops_packed, void* num_out,
                                void* den_out) {
+  MULTI(ctx, bpx::multi::edge_expect(ctx, n_edges, edges, ops_packed, num_out, den_out));
   NEED_DIMS(ctx, "bpx_edge_expect");
   REQUIRE(ctx, ctx->mode == BPX_MODE_NORM, "bpx_edge_expect: NORM mode only");
   REQUIRE(ctx, n_edges >= 0, "bpx_edge_expect: bad arguments");
@@ -1671,10 +1792,17 @@ extern "C" int bpx_edge_expect(bpx_ctx* ctx, int64_t n_edges, const int64_t* edg
   return BPX_OK;
 }
 
-extern "C" void* bpx_device_messages(bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? ctx->d_msg[ctx->cur] : nullptr; }
-extern "C" void* bpx_device_site_tensors(bpx_ctx* ctx) { return (ctx && ctx->dims_set) ? ctx->d_sites : nullptr; }
+extern "C" void* bpx_device_messages(bpx_ctx* ctx) {
+  if (ctx && !ctx->children.empty()) return ctx->children.size() == 1 ? bpx_device_messages(ctx->children[0]) : nullptr;
+  return (ctx && ctx->dims_set) ? ctx->d_msg[ctx->cur] : nullptr;
+}
+extern "C" void* bpx_device_site_tensors(bpx_ctx* ctx) {
+  if (ctx && !ctx->children.empty()) return ctx->children.size() == 1 ? bpx_device_site_tensors(ctx->children[0]) : nullptr;
+  return (ctx && ctx->dims_set) ? ctx->d_sites : nullptr;
+}
 
 extern "C" int bpx_synchronize(bpx_ctx* ctx) {
+  MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_synchronize(c); }));
   if (!ctx) return BPX_ERR_INVALID;
   BPX_CUDA(ctx, cudaSetDevice(ctx->device));
   if (ctx->dims_set) {
@@ -1687,6 +1815,7 @@ extern "C" int bpx_synchronize(bpx_ctx* ctx) {
 
 // ---- device-side synthetic inputs (benchmarks at sizes the host cannot stage) ----------------------------------
 extern "C" int bpx_fill_synthetic(bpx_ctx* ctx, uint64_t seed) {
+  MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_fill_synthetic(c, seed); }));
   NEED_DIMS(ctx, "bpx_fill_synthetic");
   REQUIRE(ctx, ctx->mode == BPX_MODE_NORM, "bpx_fill_synthetic: NORM mode only");
   const int dpe = ctx->esize / 8;
@@ -1748,6 +1877,7 @@ extern "C" int bpx_fill_randn(uint64_t seed, uint64_t stream, int dtype, int64_t
 
 // debug only (not part of include/bpx.h): per-phase timestamps of CTA 0 in BPX_ONCHIP_TIMING builds
 extern "C" int bpx_debug_timing(bpx_ctx* ctx, long long* out, int n) {
+  MULTI(ctx, bpx_debug_timing(MULTI0(ctx), out, n));
   if (!ctx) return BPX_ERR_INVALID;
   cudaSetDevice(ctx->device);
   if (!ctx->d_timing) {

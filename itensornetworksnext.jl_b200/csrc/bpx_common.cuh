@@ -128,6 +128,19 @@ __device__ __forceinline__ void residual_record(unsigned long long* slot, double
   if (slot) atomicMax(slot, residual_key(r));
 }
 
+// Device-side StopWhenConverged (AlgorithmsInterfaceExtensions.jl:84-119) for sweeps that are enqueued ahead of the host:
+// `slot` is this sweep's entry of the residual-key ring, so slot[-1] is the previous sweep's final key (stream order).  If
+// that residual is already below the tolerance (key < stop_key; NaN has the largest key and never stops), the sweep must
+// not happen: every CTA of every launch of the sweep returns at once, and the key is handed on (slot[0] = slot[-1]) so
+// that all later pre-enqueued sweeps stop as well.  stop_key == 0: no test (first sweep of a call, tol <= 0).
+__device__ __forceinline__ bool sweep_already_converged(unsigned long long* slot, unsigned long long stop_key) {
+  if (stop_key == 0ull || slot == nullptr) return false;
+  const unsigned long long prev = *reinterpret_cast<const volatile unsigned long long*>(slot - 1);
+  if (prev == 0ull || prev >= stop_key) return false;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(slot) = prev;
+  return true;
+}
+
 // Epilogue shared by every update kernel: sum-normalise (beliefpropagation.jl:248-253), residual term
 // 1 - |<old^, new^>|^2 (beliefpropagation.jl:261-267), store.  Executed by ONE warp; `raw` holds the
 // unnormalised message (nelem entries, any address space), `old_m` / `new_m` the global slots.

@@ -30,8 +30,9 @@ struct Bucket {
 
 struct Peer {
   int rank = -1;
-  void* msg[2] = {nullptr, nullptr};  // peer's two message sets (cudaIpcOpenMemHandle)
+  void* msg[2] = {nullptr, nullptr};  // peer's two message sets (cudaIpcOpenMemHandle, or plain pointers: same process)
   void* mailbox = nullptr;            // peer's mailbox array
+  bool ipc = true;                    // opened from IPC handles (closed on release); false: bpx_create_multi siblings
 };
 
 }  // namespace bpx
@@ -78,6 +79,13 @@ struct bpx_ctx {
   int n_onchip16_items = 0;
   void* d_sliced_items = nullptr;
   int n_sliced_items = 0;
+  // group-cooperative version of the sliced kernel (bpx_sliced2.cuh): vertices grouped per CTA group
+  void* d_sliced2_items = nullptr;
+  int32_t* d_sliced2_group_ptr = nullptr;
+  int n_sliced2_items = 0, n_sliced2_groups = 0, sliced2_G = 0, sliced2_grid = 0;
+  void* d_sliced2_partials = nullptr;
+  unsigned int* d_sliced2_gsync = nullptr;
+  alignas(64) unsigned char sliced2_tmaps[4 * 128];  // sliced2::TensorMaps (four CUtensorMap), rebuilt with the buffers
   void* d_onchip16c_items = nullptr;  // complex chi = 16 kernel: items laid out as rounds (slot r * grid + cta)
   int n_onchip16c_slots = 0, onchip16c_grid = 0;
   void* d_onchip8c_items = nullptr;   // complex chi = 8 kernel, same round layout
@@ -117,6 +125,7 @@ struct bpx_ctx {
   bpx::PeerArgs peer_args = {};     // what the next fast launch is told about the exchange (nranks 0: nothing)
   unsigned int* d_ticket = nullptr;
   unsigned long long recv_mask = 0;  // ranks that own the tail of an edge pointing into this rank's block
+  unsigned long long stop_key = 0;  // device-side convergence test of the sweep being enqueued (0: none)
   bool single_launch = false;       // the whole sweep of this rank is ONE fast launch: exchange fused into it
 
   // streamed host I/O (bpx_sweep_host with pinned buffers)
@@ -148,6 +157,12 @@ struct bpx_ctx {
 
   // counters
   int64_t n_launches = 0, n_updates = 0, n_sweeps = 0;
+
+  // single-process multi-GPU (bpx_create_multi, bpx_multi.cuh): the parent owns one partitioned child per device and holds
+  // no device memory itself
+  std::vector<bpx_ctx*> children;
+  std::vector<int32_t> multi_owner;  // owner[v] = index of the child that updates the out-edges of v
+  bool is_child = false;
 };
 
 namespace bpx {
@@ -183,5 +198,6 @@ int halo_push(bpx_ctx* ctx, void* msg_out);
 int halo_post_residual(bpx_ctx* ctx);
 int halo_gate(bpx_ctx* ctx);
 void halo_release(bpx_ctx* ctx);
+int halo_finalize(bpx_ctx* ctx);  // all peers known: build the device-side tables of peer message sets / mailboxes
 
 }  // namespace bpx

@@ -5,6 +5,7 @@
 #include "bpx_ctx.h"
 #include "bpx_onchip.cuh"
 #include "bpx_sliced.cuh"
+#include "bpx_sliced2.cuh"
 #include "bpx_onchip16.cuh"
 #include "bpx_onchip16c.cuh"
 #include "bpx_onchip8c.cuh"
@@ -71,6 +72,56 @@ inline int fast_kernel_for(bpx_ctx* ctx, const Bucket& b) {
   if (fast_kernel_supported(ctx, b, BPX_KERNEL_SLICED)) return BPX_KERNEL_SLICED;
   if (fast_kernel_supported(ctx, b, BPX_KERNEL_VERTEX)) return BPX_KERNEL_VERTEX;
   return BPX_KERNEL_GENERIC;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libbpx links cudart only)
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TensorMapEncodeTiledFn tensor_map_encoder() {
+  static TensorMapEncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+      fn = (TensorMapEncodeTiledFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+// the two strided views of a buffer of `n` doubles that the sliced kernel's half slices use (bpx_sliced2.cuh)
+inline int sliced2_encode_views(bpx_ctx* ctx, void* base, size_t n, CUtensorMap* a0h, CUtensorMap* a3h) {
+  TensorMapEncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) {
+    set_error(ctx, "cuTensorMapEncodeTiled is not available from this driver");
+    return BPX_ERR_CUDA;
+  }
+  const cuuint32_t ones[3] = {1, 1, 1};
+  {
+    const cuuint64_t dims[3] = {256, 32, (n + 8191) / 8192};
+    const cuuint64_t strides[2] = {256 * 8, 8192 * 8};
+    const cuuint32_t box[3] = {256, 1, 16};
+    const CUresult r = enc(a0h, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error(ctx, "cuTensorMapEncodeTiled(a0-half-slice view) failed: %d", (int)r);
+      return BPX_ERR_CUDA;
+    }
+  }
+  {
+    const cuuint64_t dims[3] = {128, 2, (n + 255) / 256};
+    const cuuint64_t strides[2] = {128 * 8, 256 * 8};
+    const cuuint32_t box[3] = {128, 1, 32};
+    const CUresult r = enc(a3h, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error(ctx, "cuTensorMapEncodeTiled(a3-half-slice view) failed: %d", (int)r);
+      return BPX_ERR_CUDA;
+    }
+  }
+  return BPX_OK;
 }
 
 // Build the launch groups: all ONCHIP buckets share ONE persistent launch over a cost-sorted item list
@@ -426,13 +477,29 @@ inline int fast_prepare(bpx_ctx* ctx) {
       need_image = true;
     }
   }
-  // ---- SLICED buckets (chi = 16): two half items per vertex ----
+  // ---- SLICED buckets (chi = 16, degree 4) ----
+  // version 2 (bpx_sliced2.cuh, default): groups of G CTAs share one vertex; version 1 (BPX_SLICED_V1=1, or message
+  // offsets that are not 16-byte aligned): two independent half items per vertex
   {
+    auto F = [](auto*& p) {
+      if (p) cudaFree(p);
+      p = nullptr;
+    };
+    F(ctx->d_sliced2_items);
+    F(ctx->d_sliced2_group_ptr);
+    F(ctx->d_sliced2_partials);
+    F(ctx->d_sliced2_gsync);
+    ctx->n_sliced2_items = ctx->n_sliced2_groups = ctx->sliced2_G = ctx->sliced2_grid = 0;
     std::vector<sliced::ItemDesc> sit;
+    std::vector<sliced2::VItem> vit;
+    bool aligned = true;
     for (int i = 0; i < (int)ctx->buckets.size(); ++i) {
       Bucket& b = ctx->buckets[i];
       if (b.kernel != BPX_KERNEL_SLICED) continue;
-      for (int32_t v : b.my_vertices)
+      for (int32_t v : b.my_vertices) {
+        sliced2::VItem w;
+        memset(&w, 0, sizeof(w));
+        w.site_off = ctx->dev_site_off[v];
         for (int br = 0; br < 2; ++br) {
           sliced::ItemDesc d;
           memset(&d, 0, sizeof(d));
@@ -445,15 +512,52 @@ inline int fast_prepare(bpx_ctx* ctx) {
             d.in_off[l] = ctx->msg_off[ctx->rev[e]];
             d.peer[l] = (!ctx->owner.empty() && ctx->owner[ctx->dst[e]] != ctx->rank) ? ctx->owner[ctx->dst[e]] : -1;
             d.need = std::max<int64_t>(d.need, std::max(ctx->upload_end[e], ctx->upload_end[ctx->rev[e]]));
+            w.out_edge[l] = d.out_edge[l];
+            w.out_off[l] = d.out_off[l];
+            w.in_off[l] = d.in_off[l];
+            w.peer[l] = d.peer[l];
+            if (d.in_off[l] & 1) aligned = false;  // the staged message copies are TMA bulk loads (16-byte granules)
           }
+          w.need = d.need;
           sit.push_back(d);
         }
+        vit.push_back(w);
+      }
     }
     if (!sit.empty()) {
       ctx->n_sliced_items = (int)sit.size();
+      const bool v2 = aligned && !getenv("BPX_SLICED_V1") && ctx->num_sms >= 4;
+      size_t scratch_doubles = (size_t)std::min(ctx->n_sliced_items, ctx->num_sms) * sliced::NTENSOR;
+      std::vector<sliced2::VItem> grouped;
+      std::vector<int32_t> group_ptr;
+      if (v2) {
+        int G = 8;
+        if (const char* env = getenv("BPX_SLICED_G")) G = atoi(env) == 4 ? 4 : 8;
+        if (ctx->num_sms < 8) G = 4;
+        // capacity units of 4 CTAs: a group of 8 owns two units, a trailing group of 4 one; vertex i -> unit i % n_units
+        // (vertices stay in lattice order inside a group: the order in which a streamed upload delivers their messages)
+        const int n_units = ctx->num_sms / 4;
+        const int upg = G / 4;
+        const int n_groups = (n_units + upg - 1) / upg;
+        std::vector<std::vector<int>> per_group(n_groups);
+        for (size_t i = 0; i < vit.size(); ++i) per_group[(int)(i % n_units) / upg].push_back((int)i);
+        group_ptr.push_back(0);
+        for (auto& l : per_group) {
+          for (int i : l) grouped.push_back(vit[i]);
+          group_ptr.push_back((int32_t)grouped.size());
+        }
+        ctx->n_sliced2_items = (int)grouped.size();
+        ctx->n_sliced2_groups = n_groups;
+        ctx->sliced2_G = G;
+        ctx->sliced2_grid = n_units * 4;
+        scratch_doubles = (size_t)n_groups * 2 * sliced::NTENSOR;
+      }
       cudaError_t e = cudaMalloc((void**)&ctx->d_sliced_items, sit.size() * sizeof(sliced::ItemDesc));
-      if (e == cudaSuccess)
-        e = cudaMalloc(&ctx->d_fast_scratch, (size_t)std::min(ctx->n_sliced_items, ctx->num_sms) * sliced::NTENSOR * sizeof(double));
+      if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fast_scratch, scratch_doubles * sizeof(double));
+      if (e == cudaSuccess && v2) e = cudaMalloc((void**)&ctx->d_sliced2_items, grouped.size() * sizeof(sliced2::VItem));
+      if (e == cudaSuccess && v2) e = cudaMalloc((void**)&ctx->d_sliced2_group_ptr, group_ptr.size() * sizeof(int32_t));
+      if (e == cudaSuccess && v2) e = cudaMalloc(&ctx->d_sliced2_partials, (size_t)ctx->n_sliced2_groups * sliced2::PART_PER_GROUP * sizeof(double));
+      if (e == cudaSuccess && v2) e = cudaMalloc((void**)&ctx->d_sliced2_gsync, (size_t)ctx->n_sliced2_groups * sliced2::GS_STRIDE * sizeof(unsigned int));
       if (e != cudaSuccess) {
         set_error(ctx, "cudaMalloc(sliced kernel items/scratch) failed: %s", cudaGetErrorString(e));
         cudaGetLastError();
@@ -462,6 +566,12 @@ inline int fast_prepare(bpx_ctx* ctx) {
       BPX_CUDA(ctx, cudaMemcpy(ctx->d_sliced_items, sit.data(), sit.size() * sizeof(sliced::ItemDesc), cudaMemcpyHostToDevice));
       BPX_CUDA(ctx, cudaFuncSetAttribute(sliced::bp_update_sliced_c16, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sliced::SMEM_BYTES));
+      if (v2) {
+        BPX_CUDA(ctx, cudaMemcpy(ctx->d_sliced2_items, grouped.data(), grouped.size() * sizeof(sliced2::VItem), cudaMemcpyHostToDevice));
+        BPX_CUDA(ctx, cudaMemcpy(ctx->d_sliced2_group_ptr, group_ptr.data(), group_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        BPX_CUDA(ctx, cudaFuncSetAttribute(sliced2::bp_update_sliced_c16g, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sliced2::SMEM2_BYTES));
+      }
       need_image = true;
     }
   }
@@ -475,6 +585,13 @@ inline int fast_prepare(bpx_ctx* ctx) {
       return BPX_ERR_ALLOC;
     }
     ctx->sites_dirty = true;
+  }
+  if (ctx->n_sliced2_groups > 0) {
+    // tensor-map views of the tensor image and of the groups' scratch images (both buffers exist now)
+    sliced2::TensorMaps* tm = reinterpret_cast<sliced2::TensorMaps*>(ctx->sliced2_tmaps);
+    int rc = sliced2_encode_views(ctx, ctx->d_sites_swz, (size_t)ctx->dev_site_total, &tm->a0h_sites, &tm->a3h_sites);
+    if (!rc) rc = sliced2_encode_views(ctx, ctx->d_fast_scratch, (size_t)ctx->n_sliced2_groups * 2 * sliced::NTENSOR, &tm->a0h_scratch, &tm->a3h_scratch);
+    if (rc) return rc;
   }
   if (group.empty()) return BPX_OK;
   std::sort(group.begin(), group.end(), [&](int a, int b) { return ctx->buckets[a].z > ctx->buckets[b].z; });
@@ -573,6 +690,7 @@ inline int launch_vertex_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, voi
   k.n = (int64_t)b.my_vertices.size();
   k.normalize = normalize;
   k.out_contig = b.vx_out_contig;
+  k.stop_key = ctx->stop_key;
   if (k.n == 0) return BPX_OK;
   const cudaError_t e = ctx->dtype == BPX_C64 ? vertexk::launch<c64>(k, b.z, b.chi, ctx->num_sms, ctx->stream)
                                               : vertexk::launch<double>(k, b.z, b.chi, ctx->num_sms, ctx->stream);
@@ -593,6 +711,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.normalize = normalize;
     k.peer = ctx->peer_args;
     k.io = ctx->io_args;
+    k.stop_key = ctx->stop_key;
     if (ctx->onchip8c_grid == 0) return BPX_OK;
     if (ctx->dtype == BPX_C64)
       onchip8c::bp_update_onchip_c8x<true><<<ctx->onchip8c_grid, onchip8c::NT, onchip8c::SMEM_BYTES8C, ctx->stream>>>(k);
@@ -613,6 +732,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.normalize = normalize;
     k.peer = ctx->peer_args;
     k.io = ctx->io_args;
+    k.stop_key = ctx->stop_key;
     k.timing = (long long*)ctx->d_timing;
     if (ctx->onchip16c_grid == 0) return BPX_OK;
     if (ctx->dtype == BPX_C64)
@@ -635,6 +755,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.normalize = normalize;
     k.peer = ctx->peer_args;
     k.io = ctx->io_args;
+    k.stop_key = ctx->stop_key;
     const int grid = std::min(k.n_items, ctx->num_sms);
     if (grid == 0) return BPX_OK;
     onchip16::bp_update_onchip_c16<<<grid, onchip16::NTHREADS16, onchip16::SMEM_BYTES16, ctx->stream>>>(k);
@@ -655,9 +776,38 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.normalize = normalize;
     k.peer = ctx->peer_args;
     k.io = ctx->io_args;
+    k.stop_key = ctx->stop_key;
     const int grid = std::min(k.n_items, ctx->num_sms);
     if (grid == 0) return BPX_OK;
     onchip::bp_update_onchip_c8<<<grid, onchip::NTHREADS, onchip::SMEM_BYTES, ctx->stream>>>(k);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+    return BPX_OK;
+  }
+  if (b.kernel == BPX_KERNEL_SLICED && ctx->n_sliced2_groups > 0) {
+    sliced2::Args k;
+    k.items = (const sliced2::VItem*)ctx->d_sliced2_items;
+    k.group_ptr = ctx->d_sliced2_group_ptr;
+    k.n_groups = ctx->n_sliced2_groups;
+    k.G = ctx->sliced2_G;
+    k.sites = (const double*)ctx->d_sites_swz;
+    k.scratch = (double*)ctx->d_fast_scratch;
+    k.partials = (double*)ctx->d_sliced2_partials;
+    k.gsync = ctx->d_sliced2_gsync;
+    k.timing = (long long*)ctx->d_timing;
+    k.msg_in = (const double*)msg_in;
+    k.msg_out = (double*)msg_out;
+    k.residual = nullptr;
+    k.resmax = ctx->cur_slot;
+    k.normalize = normalize;
+    k.peer = ctx->peer_args;
+    k.io = ctx->io_args;
+    k.stop_key = ctx->stop_key;
+    if (ctx->n_sliced2_items == 0) return BPX_OK;
+    // the group counters start every launch at zero (a memset node when the step is captured into a CUDA graph)
+    BPX_CUDA(ctx, cudaMemsetAsync(ctx->d_sliced2_gsync, 0, (size_t)ctx->n_sliced2_groups * sliced2::GS_STRIDE * sizeof(unsigned int), ctx->stream));
+    sliced2::bp_update_sliced_c16g<<<ctx->sliced2_grid, sliced2::NTHREADS2, sliced2::SMEM2_BYTES, ctx->stream>>>(
+        k, *reinterpret_cast<const sliced2::TensorMaps*>(ctx->sliced2_tmaps));
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());
     return BPX_OK;
@@ -675,6 +825,7 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.normalize = normalize;
     k.peer = ctx->peer_args;
     k.io = ctx->io_args;
+    k.stop_key = ctx->stop_key;
     const int grid = std::min(k.n_items, ctx->num_sms);
     if (grid == 0) return BPX_OK;
     sliced::bp_update_sliced_c16<<<grid, sliced::NTHREADS, sliced::SMEM_BYTES, ctx->stream>>>(k);

@@ -32,6 +32,7 @@ struct GenericArgs {
   const void* ops;         // scalars: optional per-vertex d x d operators (packed), else NULL
   const int64_t* op_off;   // per-vertex element offsets into ops
   void* scalars_out;       // scalars: per work item
+  unsigned long long stop_key;  // device-side convergence test (sweep_already_converged), 0: none
 };
 
 // out[l, a', r] = sum_a M[a' + chi_out * a] * cur[l + L * (a + chi * r)]
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) bp_update_generic(GenericArgs g) {
   __shared__ int64_t cur_dim[BPX_MAX_DEGREE + 1];  // dims of the running tensor: [d, l_0..l_{z-1}]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const bool norm_mode = (g.mode == BPX_MODE_NORM);
+  if (sweep_already_converged(g.resmax, g.stop_key)) return;
 
   T* buf[2];
   T* out_s;  // raw output message staged in shared memory (chi_s^2 or chi_s entries)

@@ -144,8 +144,31 @@ inline int halo_gate(bpx_ctx* ctx) {
   return BPX_OK;
 }
 
+inline int halo_finalize(bpx_ctx* ctx) {
+  if ((int)ctx->peers.size() != ctx->nranks - 1) {
+    set_error(ctx, "halo: %d of %d peers connected", (int)ctx->peers.size(), ctx->nranks - 1);
+    return BPX_ERR_INVALID;
+  }
+  std::vector<void*> msg(2 * ctx->nranks, nullptr), mb(ctx->nranks, nullptr);
+  msg[ctx->rank] = ctx->d_msg[0];
+  msg[ctx->nranks + ctx->rank] = ctx->d_msg[1];
+  mb[ctx->rank] = ctx->d_mailbox;
+  for (auto& q : ctx->peers) {
+    msg[q.rank] = q.msg[0];
+    msg[ctx->nranks + q.rank] = q.msg[1];
+    mb[q.rank] = q.mailbox;
+  }
+  BPX_CUDA(ctx, cudaMalloc((void**)&ctx->d_peer_msg, msg.size() * sizeof(void*)));
+  BPX_CUDA(ctx, cudaMemcpy(ctx->d_peer_msg, msg.data(), msg.size() * sizeof(void*), cudaMemcpyHostToDevice));
+  BPX_CUDA(ctx, cudaMalloc((void**)&ctx->d_peer_mailbox, mb.size() * sizeof(void*)));
+  BPX_CUDA(ctx, cudaMemcpy(ctx->d_peer_mailbox, mb.data(), mb.size() * sizeof(void*), cudaMemcpyHostToDevice));
+  ctx->halo_connected = true;
+  return BPX_OK;
+}
+
 inline void halo_release(bpx_ctx* ctx) {
   for (auto& p : ctx->peers) {
+    if (!p.ipc) continue;  // siblings of a multi-device context: plain pointers owned by the sibling
     for (int k = 0; k < 2; ++k)
       if (p.msg[k] && p.rank != ctx->rank) cudaIpcCloseMemHandle(p.msg[k]);
     if (p.mailbox && p.rank != ctx->rank) cudaIpcCloseMemHandle(p.mailbox);
@@ -171,6 +194,10 @@ inline void halo_release(bpx_ctx* ctx) {
 
 extern "C" int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32_t* owner) {
   if (!ctx) return BPX_ERR_INVALID;
+  if (!ctx->children.empty()) {
+    bpx::set_error(ctx, "multi-device contexts partition themselves (bpx_set_owner); the per-rank halo calls do not apply");
+    return BPX_ERR_INVALID;
+  }
   if (!ctx->dims_set) {
     bpx::set_error(ctx, "bpx_set_partition: call bpx_set_dims first");
     return BPX_ERR_INVALID;
@@ -229,6 +256,10 @@ extern "C" int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32
 // handles: [0..63] message set 0, [64..127] message set 1, [128..191] mailbox
 extern "C" int bpx_halo_export(bpx_ctx* ctx, void* handles_3x64) {
   if (!ctx || !handles_3x64) return BPX_ERR_INVALID;
+  if (!ctx->children.empty()) {
+    bpx::set_error(ctx, "multi-device contexts partition themselves (bpx_set_owner); the per-rank halo calls do not apply");
+    return BPX_ERR_INVALID;
+  }
   if (!ctx->dims_set || ctx->nranks <= 1) {
     bpx::set_error(ctx, "bpx_halo_export: call bpx_set_partition (nranks > 1) first");
     return BPX_ERR_INVALID;
@@ -247,6 +278,10 @@ extern "C" int bpx_halo_export(bpx_ctx* ctx, void* handles_3x64) {
 // the last call finalises the device-side peer tables.
 extern "C" int bpx_halo_connect(bpx_ctx* ctx, int peer_rank, const void* handles_3x64) {
   if (!ctx || !handles_3x64) return BPX_ERR_INVALID;
+  if (!ctx->children.empty()) {
+    bpx::set_error(ctx, "multi-device contexts partition themselves (bpx_set_owner); the per-rank halo calls do not apply");
+    return BPX_ERR_INVALID;
+  }
   if (!ctx->dims_set || ctx->nranks <= 1 || peer_rank < 0 || peer_rank >= ctx->nranks || peer_rank == ctx->rank) {
     bpx::set_error(ctx, "bpx_halo_connect: bad peer rank %d", peer_rank);
     return BPX_ERR_INVALID;
@@ -265,30 +300,32 @@ extern "C" int bpx_halo_connect(bpx_ctx* ctx, int peer_rank, const void* handles
   BPX_CUDA(ctx, cudaIpcOpenMemHandle(&p.msg[1], h[1], cudaIpcMemLazyEnablePeerAccess));
   BPX_CUDA(ctx, cudaIpcOpenMemHandle(&p.mailbox, h[2], cudaIpcMemLazyEnablePeerAccess));
   ctx->peers.push_back(p);
-  if ((int)ctx->peers.size() == ctx->nranks - 1) {
-    std::vector<void*> msg(2 * ctx->nranks, nullptr), mb(ctx->nranks, nullptr);
-    msg[ctx->rank] = ctx->d_msg[0];
-    msg[ctx->nranks + ctx->rank] = ctx->d_msg[1];
-    mb[ctx->rank] = ctx->d_mailbox;
-    for (auto& q : ctx->peers) {
-      msg[q.rank] = q.msg[0];
-      msg[ctx->nranks + q.rank] = q.msg[1];
-      mb[q.rank] = q.mailbox;
-    }
-    BPX_CUDA(ctx, cudaMalloc((void**)&ctx->d_peer_msg, msg.size() * sizeof(void*)));
-    BPX_CUDA(ctx, cudaMemcpy(ctx->d_peer_msg, msg.data(), msg.size() * sizeof(void*), cudaMemcpyHostToDevice));
-    BPX_CUDA(ctx, cudaMalloc((void**)&ctx->d_peer_mailbox, mb.size() * sizeof(void*)));
-    BPX_CUDA(ctx, cudaMemcpy(ctx->d_peer_mailbox, mb.data(), mb.size() * sizeof(void*), cudaMemcpyHostToDevice));
-    ctx->halo_connected = true;
-  }
+  if ((int)ctx->peers.size() == ctx->nranks - 1) return bpx::halo_finalize(ctx);
   return BPX_OK;
 }
 
-extern "C" int64_t bpx_num_cut_edges(const bpx_ctx* ctx) { return ctx ? ctx->n_cut : -1; }
+extern "C" int64_t bpx_num_cut_edges(const bpx_ctx* ctx) {
+  if (ctx && !ctx->children.empty()) {
+    int64_t n = 0;
+    for (const bpx_ctx* c : ctx->children) n += c->n_cut;
+    return n;
+  }
+  return ctx ? ctx->n_cut : -1;
+}
 
 // Enqueue a cross-rank barrier on the context's stream (every rank must call it the same number of times).
 extern "C" int bpx_peer_barrier(bpx_ctx* ctx) {
   if (!ctx) return BPX_ERR_INVALID;
+  if (!ctx->children.empty()) {
+    for (bpx_ctx* c : ctx->children) {
+      const int rc = bpx_peer_barrier(c);
+      if (rc) {
+        ctx->err = c->err;
+        return rc;
+      }
+    }
+    return BPX_OK;
+  }
   if (ctx->nranks <= 1) return BPX_OK;
   if (!ctx->halo_connected) {
     bpx::set_error(ctx, "bpx_peer_barrier: peers are not connected");

@@ -241,6 +241,7 @@ struct Args {
   int normalize;
   PeerArgs peer;                 // multi-GPU: gate / direct peer stores / post (nranks <= 1: unused)
   HostIO io;                     // streamed host I/O (bpx_sweep_host), all NULL otherwise
+  unsigned long long stop_key;   // device-side convergence test (sweep_already_converged), 0: none
 };
 
 // shared memory (doubles): A[2][NELEM] | P[NELEM] | red[2][NCW][MSG] | raw[2][MSG] | msgs[2][4][MSG] | 2 mbarriers
@@ -342,6 +343,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_onchip_c8(Args k) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(msgs + 2 * 4 * MSG);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int G = gridDim.x;
+  if (sweep_already_converged(k.resmax, k.stop_key)) return;
   if ((int)blockIdx.x >= k.n_items) return;
 
   if (threadIdx.x == 0) {

@@ -47,6 +47,7 @@ struct Args {
   int normalize;
   PeerArgs peer;
   HostIO io;  // streamed host I/O (bpx_sweep_host), all NULL otherwise
+  unsigned long long stop_key;  // device-side convergence test (sweep_already_converged), 0: none
 };
 
 // staged incoming messages: plain 3 x 256 doubles, pair mode 6 x 16 doubles; super-message element (b', b)
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(NTHREADS16, 1) bp_update_onchip_c16(Args k) {
   double* msgs = raw + MSG;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(msgs + 2 * 3 * MSG);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  if (sweep_already_converged(k.resmax, k.stop_key)) return;
   const int G = gridDim.x;
   if ((int)blockIdx.x >= k.n_items) return;
   if (threadIdx.x == 0) {

@@ -69,6 +69,7 @@ struct Args {
   PeerArgs peer;
   HostIO io;          // streamed host I/O (bpx_sweep_host), all NULL otherwise
   long long* timing;  // debug (BPX_ONCHIP_TIMING builds): clock64 stamps of CTA 0's first item
+  unsigned long long stop_key;  // device-side convergence test (sweep_already_converged), 0: none
 };
 
 #ifdef BPX_ONCHIP_TIMING
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(NTHREADSC, 1) bp_update_onchip_c16x(Args k) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(raw + 2 * CMSG);  // full[2]
   unsigned int* cnt = reinterpret_cast<unsigned int*>(mbar + 2);  // warps that released slot 0 / 1
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  if (sweep_already_converged(k.resmax, k.stop_key)) return;
   const int G = gridDim.x;
 
   // ---- slice ring without a producer warp (8 warps = 2 per scheduler, so every thread may hold 255 registers):

@@ -73,6 +73,7 @@ struct Args {
   int normalize;
   PeerArgs peer;
   HostIO io;
+  unsigned long long stop_key;  // device-side convergence test (sweep_already_converged), 0: none
 };
 
 __device__ __forceinline__ int slice_doubles(int kind) { return kind <= 1 ? NELEM : (kind == 2 ? NELEM / 8 : NELEM / 64); }
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(NT, 1) bp_update_onchip_c8x(Args k) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(part + 128);  // full[2]
   unsigned int* cnt = reinterpret_cast<unsigned int*>(mbar + 2);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  if (sweep_already_converged(k.resmax, k.stop_key)) return;
   const int G = gridDim.x;
 
   auto valid = [&](const Cursor& c) { return c.idx < k.n_slots && k.items[c.idx].kind >= 0; };

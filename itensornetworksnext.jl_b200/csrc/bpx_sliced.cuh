@@ -125,6 +125,7 @@ struct Args {
   int normalize;
   PeerArgs peer;               // multi-GPU: gate / direct peer stores / post (nranks <= 1: unused)
   HostIO io;                   // streamed host I/O (bpx_sweep_host), all NULL otherwise
+  unsigned long long stop_key; // device-side convergence test (sweep_already_converged), 0: none
 };
 
 // message fragments for 16-wide legs
@@ -161,6 +162,7 @@ __device__ __forceinline__ void absorb_pair16(double* buf, uint32_t base, const 
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int h = 0; h < 2; ++h) b[j][h] = *reinterpret_cast<const double2*>(buf + (base ^ pos<LAY>(X, t + 4 * j) ^ pos<LAY>(Y, g + 8 * h)));
+  __syncwarp();  // the column is overwritten below: every lane has read it first (mma.sync converges the warp anyway)
   // absorb X: D1[x' = g + 8 mt, y = 2t + i + 8h]
   double d1[2][2][2][2];  // [mt][h][s][i]
 #pragma unroll
@@ -268,6 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bp_update_sliced_c16(Args k) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(raw + 2 * MSG);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int G = gridDim.x;
+  if (sweep_already_converged(k.resmax, k.stop_key)) return;
   if ((int)blockIdx.x >= k.n_items) return;
   double* scratch = k.scratch + (size_t)blockIdx.x * NTENSOR;
 

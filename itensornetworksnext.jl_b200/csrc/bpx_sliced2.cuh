@@ -1,0 +1,559 @@
+// BPX_KERNEL_SLICED, version 2: (degree 4, chi = 16, d = 2, Float64) -- BASELINE config 5 -- with the working set of the
+// vertices in flight kept INSIDE the 126 MB L2.
+//
+// Version 1 (bpx_sliced.cuh) gives every CTA its own (vertex, branch) item: 148 x (1 MiB tensor + 1 MiB scratch) does not
+// fit the L2, the tensor is streamed four times and the intermediate round-trips through DRAM: 6.85 MB of DRAM traffic
+// per vertex against 1.07 MB algorithmic, 3.7 TB/s at full speed -- the memory system, not the tensor pipe, was the limit.
+//
+// Here a GROUP of G CTAs (8, or 4) shares ONE vertex, so that only 148/G vertices are in flight (G = 8: 19 groups x
+// (2 tensors + 2 scratch images) = 76 MiB), and the three passes over the tensor are software-pipelined ACROSS vertices so
+// that no CTA ever waits at a group barrier:
+//
+//   S1(v): a3-slices            A[.., a3 = r]  --absorb M0, M1 in place-->  P[.., a3 = r]              -> scratch[v & 1]
+//   S2(v): a0-half-slices       P, A           --absorb 2 / close 3, absorb 3 / close 2-->  out3, out2 partial sums
+//                               A (same slice) --absorb M2, M3 in place-->  Q[a0 = r, ..]  OVER P in scratch[v & 1]
+//   S3(v): a3-half-slices       Q, A           --absorb 0 / close 1, absorb 1 / close 0-->  out1, out0 partial sums
+//
+// (branch Q's first pass rides on the tensor slices that branch P's second pass has in shared memory anyway: the tensor is
+// read three times instead of four, and Q overwrites P slice by slice).  Every CTA runs the stage sequence
+//   S1(0) S2(0) | S1(1) S3(0) S2(1) | S1(2) S3(1) S2(2) | ... | S3(n-1)
+// on its share of the slices (member j of a group owns a3 / a0 values j, j + G, ...): between the end of a stage and the
+// first load of the stage that depends on ALL members' stores there is always a whole stage of independent work, so the
+// group barriers (monotone counters in global memory, release / acquire at gpu scope) cost nothing.  The compute warps
+// never synchronise with each other or with anything global: every warp stores its partial 16x16 output tiles straight
+// into an L2-resident buffer and bumps a shared-memory event counter; a COMMUNICATION warp turns those events (and the
+// producer's "stage stored" events) into gpu-scope fences + arrivals on the group counters, and an EPILOGUE warp of the
+// member that owns an output sums the 8 x G partial tiles in a fixed order and finishes the message (sum-normalisation,
+// residual, stores, cut-edge peer stores) -- all off the tensor pipe's critical path.
+//
+// Warp roles (352 threads, 1 CTA / SM): 8 compute warps (DMMA), 1 producer warp (TMA loads / stores, L2 prefetch),
+// 1 communication warp, 1 epilogue warp.  Same private tensor image, shared-memory layouts and DMMA micro-kernels as
+// version 1.
+#pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libbpx links cudart only)
+
+#include "bpx_sliced.cuh"
+
+namespace bpx {
+namespace sliced2 {
+
+using namespace sliced;
+
+constexpr int NTHREADS2 = NCT + 96;  // 8 compute warps + producer + communication + epilogue
+constexpr int WARP_PRODUCER = NCW, WARP_COMM = NCW + 1, WARP_EPILOGUE = NCW + 2;
+constexpr int PART_GEN = 3;  // generations of partial tiles in flight (vertex v uses v % 3): the epilogue of v may lag two vertices
+constexpr size_t PART_PER_GROUP = (size_t)PART_GEN * 8 * NCW * 4 * MSG;  // doubles: [v % 3][member][warp][output leg][256]
+
+struct VItem {  // one (degree 4, chi 16) vertex
+  int64_t site_off;   // elements, into the private image buffer
+  int64_t in_off[4];
+  int64_t out_off[4];
+  int32_t out_edge[4];
+  int32_t peer[4];    // rank owning the head of out-edge i if it lives elsewhere (cut edge), else -1
+  int64_t need;       // streamed host I/O: prefix of the upload that holds every message this vertex reads
+};
+
+enum { GS_B1 = 0, GS_B2 = 1, GS_B3A = 2, GS_B3B = 3, GS_STRIDE = 4 };  // per-group counters
+
+struct Args {
+  const VItem* items;        // grouped: group g owns items[group_ptr[g] .. group_ptr[g + 1])
+  const int32_t* group_ptr;  // [n_groups + 1]
+  int n_groups;
+  int G;                     // CTAs per group (8 or 4); the last group may have fewer (>= 4, a divisor of 16)
+  const double* sites;       // private swizzled image
+  double* scratch;           // per group: 2 x NTENSOR doubles
+  double* partials;          // per group: PART_PER_GROUP doubles (per-warp partial output tiles, fragment order)
+  unsigned int* gsync;       // per group: GS_STRIDE counters, zeroed before the launch
+  const double* msg_in;
+  double* msg_out;
+  double* residual;
+  unsigned long long* resmax;  // this sweep's residual key (atomicMax)
+  int normalize;
+  PeerArgs peer;               // multi-GPU: gate / direct peer stores / post (nranks <= 1: unused)
+  HostIO io;                   // streamed host I/O (bpx_sweep_host), all NULL otherwise
+  unsigned long long stop_key; // device-side convergence test (sweep_already_converged), 0: none
+  long long* timing;           // debug (BPX_SLICED_TIMING builds): per-CTA cycle counters, 16 per CTA
+};
+
+#ifdef BPX_SLICED_TIMING
+#define TCLK() clock64()
+#define TACC(slot, t0) do { if (lane == 0 && k.timing) k.timing[blockIdx.x * 16 + (slot)] += clock64() - (t0); } while (0)
+#else
+#define TCLK() 0ll
+#define TACC(slot, t0) do { (void)(t0); } while (0)
+#endif
+
+// shared memory: ring 3 x 64 KiB | staged messages 2 x 4 x 2 KiB | raw 2 KiB | mbarriers + event counters
+constexpr size_t SMEM2_DOUBLES = (size_t)3 * SLICE + 8 * MSG + MSG + 16;
+constexpr size_t SMEM2_BYTES = SMEM2_DOUBLES * sizeof(double);
+enum { M2_FULL = 0 /*3*/, M2_DONE = 3 /*3*/, M2_MSG = 6 /*2*/, M2_EV = 8 /* 8 plain 32-bit event counters */ };
+enum { EV_B1 = 0, EV_B2 = 1, EV_DUMP = 2, EV_EPI = 3 };  // S1 / S2 stages stored, warp dumps written, epilogues finished
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu(unsigned int* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_once(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// one lane waits until a group counter has reached `target` (bounded: a group member that never arrives is a bug or a
+// grid that is not co-resident -- trap instead of hanging the GPU)
+__device__ __forceinline__ void group_wait(const unsigned int* ctr, unsigned int target) {
+  if (ld_acquire_gpu(ctr) >= target) return;
+  const long long t0 = clock64();
+  unsigned ns = 32;
+  while (ld_acquire_gpu(ctr) < target) {
+    __nanosleep(ns);
+    if (ns < 512) ns += ns;
+    if (clock64() - t0 > 20000000000ll) __trap();
+  }
+}
+
+// Strided half slices move as ONE TMA tensor copy each (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG) instead of 16-32 plain
+// bulk copies of 1-2 KiB: measured, a CTA's TMA unit retires one small bulk copy per ~120 clk, which made the a3-half
+// slices (64 x 1 KiB per step) the bottleneck of the whole kernel.  Two views of a buffer of doubles:
+//   view A0H: dims {256, 32, ceil(N / 8192)}, strides {256, 8192} doubles, box {256, 1, 16}:
+//             the a0-half slice (a0 = r, a1[3] = hh) of a tensor at element offset o starts at s = o + (r << 9) + (hh << 8)
+//             -> coordinates (0, (s >> 8) & 31, s >> 13)          [16 rows (a3) of 2 KiB]
+//   view A3H: dims {128, 2, ceil(N / 256)}, strides {128, 256} doubles, box {128, 1, 32}:
+//             the a3-half slice (a3 = r, a2[3] = hh) starts at s = o + (r << 13) + (hh << 7)
+//             -> coordinates (0, (s >> 7) & 1, s >> 8)            [32 rows (a0, a1[3]) of 1 KiB]
+// Both land densely in shared memory in row order: exactly the layouts L_A0H / L_A3H.
+struct TensorMaps {
+  CUtensorMap a0h_sites, a3h_sites, a0h_scratch, a3h_scratch;
+};
+__device__ __forceinline__ void tma_tensor3_g2s(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_tensor3_s2g(const CUtensorMap* tm, int c0, int c1, int c2, const void* src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];\n" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2),
+               "r"(smem_u32(src))
+               : "memory");
+}
+
+enum { K_S1 = 0, K_S2 = 1, K_S3 = 2 };
+struct Step {
+  int kind, v, q;
+};
+// step t of a member's sequence  S1(0) S2(0) | S1(1) S3(0) S2(1) | ... | S3(n-1)
+__device__ __forceinline__ Step decode_step(int t, int n, int nS1, int nS2) {
+  Step s;
+  if (t < nS1) {
+    s.kind = K_S1; s.v = 0; s.q = t;
+    return s;
+  }
+  const int per = nS1 + 2 * nS2;
+  const int u = t + nS2, v = u / per, w = u - v * per;
+  if (v == n) { s.kind = K_S3; s.v = n - 1; s.q = w; }
+  else if (w < nS1) { s.kind = K_S1; s.v = v; s.q = w; }
+  else if (w < nS1 + nS2) { s.kind = K_S3; s.v = v - 1; s.q = w - nS1; }
+  else { s.kind = K_S2; s.v = v; s.q = w - nS1 - nS2; }
+  return s;
+}
+
+// canonical A_v[s, a0..a3] -> private image (run once per upload)
+__global__ void swizzle_sites16v(const VItem* items, int n_items, const double* __restrict__ src, double* __restrict__ dst) {
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int64_t off = items[item].site_off;
+    for (int c = threadIdx.x; c < NTENSOR / 2; c += blockDim.x) {
+      const uint32_t p = global_pos(0, c & 15) ^ global_pos(1, (c >> 4) & 15) ^ global_pos(2, (c >> 8) & 15) ^ global_pos(3, c >> 12);
+      *reinterpret_cast<double2*>(dst + off + p) = *reinterpret_cast<const double2*>(src + off + 2 * c);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, const __grid_constant__ TensorMaps tm) {
+  extern __shared__ __align__(128) double smem[];
+  double* ring = smem;
+  double* msgs = smem + 3 * SLICE;   // [2][4][256]
+  double* raw = msgs + 8 * MSG;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(raw + MSG);
+  volatile unsigned int* ev = reinterpret_cast<volatile unsigned int*>(&mbar[M2_EV]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+  if (sweep_already_converged(k.resmax, k.stop_key)) return;
+
+  // ---- who am I: group, member, members of my group ----
+  const int grp = blockIdx.x / k.G, j = blockIdx.x - grp * k.G;
+  const int Gm = min(k.G, (int)gridDim.x - grp * k.G);
+  const bool active = grp < k.n_groups;
+  const int base_item = active ? k.group_ptr[grp] : 0;
+  const int n = active ? k.group_ptr[grp + 1] - base_item : 0;
+  const int nS1 = 16 / Gm, nS2 = 32 / Gm;  // steps per stage (S3 like S2)
+  const int T = n * (nS1 + 2 * nS2);
+  double* const scratch0 = k.scratch + (size_t)grp * 2 * NTENSOR;
+  double* const part0 = k.partials + (size_t)grp * PART_PER_GROUP;
+  unsigned int* const gs = k.gsync + (size_t)grp * GS_STRIDE;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&mbar[M2_FULL + i], 1);
+      mbar_init(&mbar[M2_DONE + i], NCW);
+    }
+    mbar_init(&mbar[M2_MSG + 0], 1);
+    mbar_init(&mbar[M2_MSG + 1], 1);
+    for (int i = 0; i < 8; ++i) ev[i] = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (n > 0) {
+  if (warp == WARP_PRODUCER) {
+    // ================================ producer warp ================================
+    const long long tp0 = TCLK();
+    peer_gate(k.peer, lane);  // multi-GPU: the peers' cut-edge messages of the previous sweep have landed
+    int L = 0;                 // next step to load
+    unsigned int myB1 = 0, myB2 = 0;
+    int pending_post = -1;     // stage kind whose stores were committed with the previous step; post once they completed
+    auto post = [&](int kind) {
+      // all lanes have waited for their own bulk groups: the stage's stores are complete.  Hand the arrival on the group
+      // counter to the communication warp (a gpu-scope fence under load costs microseconds: not on this warp's clock)
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        if (kind == K_S1) ev[EV_B1] = myB1 + 1u;
+        else ev[EV_B2] = myB2 + 1u;
+      }
+      if (kind == K_S1) ++myB1;
+      else ++myB2;
+      __syncwarp();
+    };
+    // may the load of step `s` go out?  The first step of S2(v) / S3(v) needs EVERY member's stores of S1(v) / S2(v):
+    // my own must have been posted (else waiting would dead-lock), and the group counter must have reached its target --
+    // checked without blocking, so that this warp keeps retiring steps (stores, posts) of the stage in flight meanwhile
+    auto can_load = [&](const Step& s) {
+      if (s.q != 0 || s.kind == K_S1) return true;
+      if ((s.kind == K_S2 ? myB1 : myB2) < (unsigned)s.v + 1u) return false;
+      unsigned int c = 0;
+      if (lane == 0) c = ld_acquire_gpu(gs + (s.kind == K_S2 ? GS_B1 : GS_B2));
+      c = __shfl_sync(0xffffffffu, c, 0);
+      return c >= (unsigned)Gm * (unsigned)(s.v + 1);
+    };
+    auto issue_load = [&](int t, const Step& s) {
+      const VItem* d = k.items + base_item + s.v;
+      const int b = t % 3;
+      double* dst = ring + b * SLICE;
+      const double* Aimg = k.sites + d->site_off;
+      const double* scr = scratch0 + (size_t)(s.v & 1) * NTENSOR;
+      if (s.q == 0) {
+        if (s.kind == K_S1) {
+          // the vertex's four incoming messages -> staged copy (slot v & 1)
+          if (k.io.progress) {
+            hostio_wait(k.io, d->need);
+            asm volatile("fence.proxy.async;\n" ::: "memory");
+          }
+          uint64_t* mb = &mbar[M2_MSG + (s.v & 1)];
+          if (lane == 0) mbar_expect_tx(mb, 4 * MSG * 8);
+          __syncwarp();
+          if (lane < 4) tma_bulk_g2s(msgs + ((s.v & 1) * 4 + lane) * MSG, k.msg_in + d->in_off[lane], MSG * 8, mb);
+        } else {
+          // (can_load has seen every member's stores of the producing stage complete, with acquire semantics)
+          if (s.kind == K_S2 && s.v + 1 < n) {
+            // this member's tensor slices of the NEXT vertex: start them on their way from DRAM into the L2 now
+            const double* An = k.sites + k.items[base_item + s.v + 1].site_off;
+            for (int q = lane >> 2; q < nS1; q += 8)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(An + ((size_t)(j + q * Gm) << 13) + (lane & 3) * 2048), "r"(16384) : "memory");
+          }
+        }
+      }
+      fence_proxy_async();  // generic-proxy accesses of the slot's previous tenant happen-before the async-proxy writes
+      if (lane == 0) mbar_expect_tx(&mbar[M2_FULL + b], SLICE * 8);
+      __syncwarp();
+      if (s.kind == K_S1) {
+        const int r = j + s.q * Gm;  // a3-slice: one contiguous 64 KiB run
+        if (lane < 4) tma_bulk_g2s(dst + lane * 2048, Aimg + ((size_t)r << 13) + lane * 2048, 16384, &mbar[M2_FULL + b]);
+      } else if (s.kind == K_S2) {
+        const int r = j + (s.q >> 1) * Gm, hh = s.q & 1;  // a0-half slice (a0 = r, a1[3] = hh): 16 rows (a3) of 2 KiB
+        const size_t go = ((size_t)r << 9) + ((size_t)hh << 8);
+        const size_t sp = (size_t)(scr - k.scratch) + go, sa = (size_t)d->site_off + go;
+        if (lane == 0) tma_tensor3_g2s(dst, &tm.a0h_scratch, 0, (int)((sp >> 8) & 31), (int)(sp >> 13), &mbar[M2_FULL + b]);
+        if (lane == 1) tma_tensor3_g2s(dst + HALF, &tm.a0h_sites, 0, (int)((sa >> 8) & 31), (int)(sa >> 13), &mbar[M2_FULL + b]);
+      } else {
+        const int r = j + (s.q >> 1) * Gm, hh = s.q & 1;  // a3-half slice (a3 = r, a2[3] = hh): 32 rows (a0, a1[3]) of 1 KiB
+        const size_t go = ((size_t)r << 13) + ((size_t)hh << 7);
+        const size_t sp = (size_t)(scr - k.scratch) + go, sa = (size_t)d->site_off + go;
+        if (lane == 0) tma_tensor3_g2s(dst, &tm.a3h_scratch, 0, (int)((sp >> 7) & 1), (int)(sp >> 8), &mbar[M2_FULL + b]);
+        if (lane == 1) tma_tensor3_g2s(dst + HALF, &tm.a3h_sites, 0, (int)((sa >> 7) & 1), (int)(sa >> 8), &mbar[M2_FULL + b]);
+      }
+    };
+    auto pump = [&](int r) {  // issue every load that may go out now: at most two steps ahead of the retired one
+      while (L < T && L <= r + 2) {
+        const Step s = decode_step(L, n, nS1, nS2);
+        if (!can_load(s)) break;
+        issue_load(L, s);
+        ++L;
+      }
+    };
+    pump(-1);
+    for (int r = 0; r < T; ++r) {
+      const Step s = decode_step(r, n, nS1, nS2);
+      const int b = r % 3;
+      const long long td = TCLK();
+      {  // compute warps finished step r?  Meanwhile keep trying a load that waits for the group
+        const long long t0w = clock64();
+        while (!__any_sync(0xffffffffu, mbar_try_once(&mbar[M2_DONE + b], (uint32_t)(r / 3) & 1u))) {
+          if (L < T && L <= r + 1) pump(r - 1);
+          if (clock64() - t0w > 40000000000ll) __trap();
+        }
+        mbar_wait(&mbar[M2_DONE + b], (uint32_t)(r / 3) & 1u);  // (every lane observes the completed phase itself)
+      }
+      TACC(8, td);
+      const double* src = ring + b * SLICE;
+      double* scr = scratch0 + (size_t)(s.v & 1) * NTENSOR;
+      // every lane that stores owns its bulk group: lanes issue, commit and wait symmetrically (one group per step)
+      if (s.kind == K_S1) {
+        const int rr = j + s.q * Gm;
+        if (lane < 4) tma_bulk_s2g(scr + ((size_t)rr << 13) + lane * 2048, src + lane * 2048, 16384);
+      } else if (s.kind == K_S2) {
+        const int rr = j + (s.q >> 1) * Gm, hh = s.q & 1;  // the A half of the slot now holds Q[a0 = rr, a1[3] = hh, ..]
+        const size_t sp = (size_t)(scr - k.scratch) + ((size_t)rr << 9) + ((size_t)hh << 8);
+        if (lane == 0) tma_tensor3_s2g(&tm.a0h_scratch, 0, (int)((sp >> 8) & 31), (int)(sp >> 13), src + HALF);
+      }
+      bulk_commit();
+      const bool stage_end = (s.kind == K_S1 && s.q == nS1 - 1) || (s.kind == K_S2 && s.q == nS2 - 1);
+      // the stage that needs this stage's stores follows immediately (first vertex, last vertex): nothing to overlap with
+      bool adjacent = false;
+      if (stage_end) {
+        if (r + 1 >= T) adjacent = true;
+        else {
+          const Step nx = decode_step(r + 1, n, nS1, nS2);
+          adjacent = (s.kind == K_S1 && nx.kind == K_S2 && nx.v == s.v) || (s.kind == K_S2 && nx.kind == K_S3 && nx.v == s.v);
+        }
+      }
+      (void)adjacent;
+      (void)pending_post;
+      const long long tb = TCLK();
+      bulk_wait_read<1>();  // the store of step r-1 has drained its slot, which step r+2 re-uses
+      __syncwarp();
+      pump(r);
+      if (stage_end) {
+        // post the stage as early as possible: the compute warps have just started step r+1, this warp has nothing else to
+        // do until they finish it -- wait for the stage's last store to complete here, then hand the arrival on
+        bulk_wait<0>();
+        post(s.kind);
+        pump(r);  // (first vertex / last vertex: the dependent stage follows immediately)
+      }
+      TACC(9, tb);
+    }
+    bulk_wait<0>();
+    __syncwarp();
+    TACC(10, tp0);
+  } else if (warp == WARP_COMM) {
+    // ================================ communication warp ================================
+    // shared-memory events -> arrivals on the group's global counters.  One lane, a non-blocking service loop: every
+    // pending event is forwarded as soon as it is seen (the fences this takes run here, next to nothing else).
+    if (lane == 0) {
+      unsigned sent_b1 = 0, sent_b2 = 0, sent_d = 0;
+      const unsigned un = (unsigned)n;
+      const long long t0 = clock64();
+      while (sent_b1 < un || sent_b2 < un || sent_d < 2u * un) {
+        bool progress = false;
+        // B1(v): before anybody may overwrite the partial tiles of vertex v - 3 (S2(v) dumps into the same generation), my
+        // epilogue warp must have finished with them
+        if (sent_b1 < ev[EV_B1] && (sent_b1 < (unsigned)PART_GEN || ev[EV_EPI] + (unsigned)PART_GEN > sent_b1)) {
+          red_release_gpu(gs + GS_B1);  // (release at gpu scope: the fence is part of it)
+          ++sent_b1;
+          progress = true;
+        }
+        if (sent_b2 < ev[EV_B2]) {
+          red_release_gpu(gs + GS_B2);
+          ++sent_b2;
+          progress = true;
+        }
+        if (ev[EV_DUMP] >= (unsigned)NCW * (sent_d + 1u)) {  // dump d: even = S2 (out3, out2), odd = S3 (out1, out0)
+          red_release_gpu(gs + ((sent_d & 1u) ? GS_B3B : GS_B3A));
+          ++sent_d;
+          progress = true;
+        }
+        if (!progress) {
+          __nanosleep(100);
+          if (clock64() - t0 > 40000000000ll) __trap();
+        }
+      }
+    }
+  } else if (warp == WARP_EPILOGUE) {
+    // ================================ epilogue warp ================================
+    const long long te0 = TCLK();
+    for (int i = 0; i < n; ++i) {
+      const VItem* d = k.items + base_item + i;
+      const long long tw = TCLK();
+      if (lane == 0) {
+        group_wait(gs + GS_B3A, (unsigned)Gm * (unsigned)(i + 1));
+        group_wait(gs + GS_B3B, (unsigned)Gm * (unsigned)(i + 1));
+      }
+      __syncwarp();
+      TACC(11, tw);
+      if (k.io.progress) hostio_wait(k.io, d->need);
+      const double* part = part0 + (size_t)(i % PART_GEN) * 8 * NCW * 4 * MSG;
+#pragma unroll 1
+      for (int leg = 0; leg < 4; ++leg) {
+        if ((i + leg) % Gm != j) continue;  // this member finishes out-edge `leg` of vertex i
+        // sum the Gm x 8 partial tiles (fragment order: double2 (i2 = 0, 1) at [(mt * 2 + h) * 32 + lane]) in a fixed order
+        double2 acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = make_double2(0.0, 0.0);
+        for (int m = 0; m < Gm; ++m) {
+          const double2* src = reinterpret_cast<const double2*>(part + (((size_t)m * NCW) * 4 + leg) * MSG) + lane;
+          double2 v[NCW][4];
+#pragma unroll
+          for (int w = 0; w < NCW; ++w)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[w][q] = __ldcg(src + (size_t)w * 4 * (MSG / 2) + q * 32);
+#pragma unroll
+          for (int w = 0; w < NCW; ++w)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc[q].x += v[w][q].x;
+              acc[q].y += v[w][q].y;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int mt = q >> 1, h = q & 1;
+          const int el = (g + 8 * mt) + CHI * (2 * t4 + 8 * h);  // out[v', v] at v' + 16 v
+          raw[el] = acc[q].x;
+          raw[el + CHI] = acc[q].y;
+        }
+        __syncwarp();
+        const int64_t off = d->out_off[leg];
+        double* peer_m = (k.peer.nranks > 1 && d->peer[leg] >= 0) ? k.peer.peer_out[d->peer[leg]] + off : nullptr;
+        warp_epilogue<double>(raw, k.msg_in + off, k.msg_out + off, MSG, k.normalize,
+                              k.residual ? k.residual + d->out_edge[leg] : nullptr, lane, k.resmax, peer_m,
+                              k.io.host_out ? k.io.host_out + off : nullptr);
+        __syncwarp();
+      }
+      if (lane == 0) ev[EV_EPI] = (unsigned)(i + 1);
+    }
+    TACC(13, te0);
+  } else {
+    // ================================ compute warps ================================
+    int t = 0;  // running step index (slot = t % 3, mbarrier parity = (t / 3) & 1)
+    const long long tc0 = TCLK();
+    auto dump = [&](int i, int leg_a, int leg_b, const double (&accA)[2][2][2], const double (&accB)[2][2][2]) {
+      // this warp's two partial output tiles -> its slots of the group's partial buffer (L2), fragment order, coalesced
+      const long long tdump = TCLK();
+      double* part = part0 + ((((size_t)(i % PART_GEN) * 8 + j) * NCW + warp) * 4) * MSG;
+      double2* pa = reinterpret_cast<double2*>(part + (size_t)leg_a * MSG) + lane;
+      double2* pb = reinterpret_cast<double2*>(part + (size_t)leg_b * MSG) + lane;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          __stcg(pa + (mt * 2 + h) * 32, make_double2(accA[mt][h][0], accA[mt][h][1]));
+          __stcg(pb + (mt * 2 + h) * 32, make_double2(accB[mt][h][0], accB[mt][h][1]));
+        }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        atomicAdd_block(const_cast<unsigned int*>(&ev[EV_DUMP]), 1u);
+      }
+      if (warp == 0) TACC(4, tdump);
+    };
+    for (int v = 0; v <= n; ++v) {
+      if (v < n) {
+        // ---- S1(v): absorb the pair (0, 1) in place, a3-slices ----
+        const long long tm = TCLK();
+        mbar_wait(&mbar[M2_MSG + (v & 1)], (uint32_t)(v >> 1) & 1u);
+        if (warp == 0) TACC(5, tm);
+        const double* mm = msgs + (v & 1) * 4 * MSG;
+        const FragA mx = load_fragA(mm + 0 * MSG, g, t4);
+        const FragB my = load_fragB(mm + 1 * MSG, g, t4);
+        for (int q = 0; q < nS1; ++q, ++t) {
+          const int b = t % 3, r = j + q * Gm;
+          const long long tf1 = TCLK();
+          mbar_wait(&mbar[M2_FULL + b], (uint32_t)(t / 3) & 1u);
+          if (warp == 0) TACC(1, tf1);
+          double* buf = ring + b * SLICE;
+#pragma unroll 1
+          for (int c = warp; c < 16; c += NCW) absorb_pair16<L_A3, 0, 1>(buf, pos<L_A3>(2, c) ^ pos<L_A3>(3, r), mx, my, g, t4);
+          fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
+        }
+      }
+      if (v >= 1) {
+        // ---- S3(v-1): a3-half slices of Q and A; absorb 0 / close 1 -> out1, absorb 1 / close 0 -> out0 ----
+        const int i = v - 1;
+        const double* mm = msgs + (i & 1) * 4 * MSG;
+        const FragA mu = load_fragA(mm + 0 * MSG, g, t4);
+        const FragA mv = load_fragA(mm + 1 * MSG, g, t4);
+        double accA[2][2][2], accB[2][2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b2 = 0; b2 < 2; ++b2) accA[a][b2][0] = accA[a][b2][1] = accB[a][b2][0] = accB[a][b2][1] = 0.0;
+        for (int q = 0; q < nS2; ++q, ++t) {
+          const int b = t % 3, r = j + (q >> 1) * Gm, hh = q & 1;
+          const long long tf3 = TCLK();
+          mbar_wait(&mbar[M2_FULL + b], (uint32_t)(t / 3) & 1u);
+          if (warp == 0) TACC(3, tf3);
+          if (warp == 0 && q == 0) TACC(12, tf3);
+          const double* Pb = ring + b * SLICE;
+          const double* Ab = Pb + HALF;
+          const int c = warp + 8 * hh;  // column a2'
+          const uint32_t base = pos<L_A3H>(2, c) ^ pos<L_A3H>(3, r);
+          absorb_close16<L_A3H, 0, 1>(Pb, Ab, base, mu, g, t4, accA);
+          absorb_close16<L_A3H, 1, 0>(Pb, Ab, base, mv, g, t4, accB);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
+        }
+        dump(i, 1, 0, accA, accB);
+      }
+      if (v < n) {
+        // ---- S2(v): a0-half slices of P and A; absorb 2 / close 3 -> out3, absorb 3 / close 2 -> out2;
+        //      then the SAME tensor columns absorb (2, 3) in place: Q's first pass ----
+        const double* mm = msgs + (v & 1) * 4 * MSG;
+        const FragA mu = load_fragA(mm + 2 * MSG, g, t4);
+        const FragA mv = load_fragA(mm + 3 * MSG, g, t4);
+        const FragB my3 = load_fragB(mm + 3 * MSG, g, t4);
+        double accA[2][2][2], accB[2][2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b2 = 0; b2 < 2; ++b2) accA[a][b2][0] = accA[a][b2][1] = accB[a][b2][0] = accB[a][b2][1] = 0.0;
+        for (int q = 0; q < nS2; ++q, ++t) {
+          const int b = t % 3, r = j + (q >> 1) * Gm, hh = q & 1;
+          const long long tf2 = TCLK();
+          mbar_wait(&mbar[M2_FULL + b], (uint32_t)(t / 3) & 1u);
+          if (warp == 0) TACC(2, tf2);
+          double* Pb = ring + b * SLICE;
+          double* Ab = Pb + HALF;
+          const int c = warp + 8 * hh;  // column a1'
+          const uint32_t base = pos<L_A0H>(1, c) ^ pos<L_A0H>(0, r);
+          absorb_close16<L_A0H, 2, 3>(Pb, Ab, base, mu, g, t4, accA);
+          absorb_close16<L_A0H, 3, 2>(Pb, Ab, base, mv, g, t4, accB);
+          __syncwarp();  // every lane has read the column before it is overwritten (only this warp touches column c)
+          absorb_pair16<L_A0H, 2, 3>(Ab, base, mu, my3, g, t4);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
+        }
+        dump(v, 3, 2, accA, accB);
+      }
+    }
+    if (warp == 0) TACC(0, tc0);
+  }
+  }
+  __syncthreads();
+  peer_post_when_last(k.peer, false);  // peer stores were released where they were issued (warp_epilogue)
+  hostio_finish(k.io);
+}
+
+}  // namespace sliced2
+}  // namespace bpx

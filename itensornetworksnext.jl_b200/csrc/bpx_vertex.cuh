@@ -42,6 +42,7 @@ struct Args {
   int64_t n;               // vertices in this launch
   int normalize;
   int out_contig;          // the z out-messages of every vertex are adjacent in the packed message layout, slot order
+  unsigned long long stop_key;  // device-side convergence test (sweep_already_converged), 0: none
 };
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e <= 0 ? 1 : b * ipow(b, e - 1); }
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(NT, Shape<T, Z, N>::MIN_CTAS) bp_update_single
   const T* __restrict__ msg_in = reinterpret_cast<const T*>(a.msg_in);
   T* __restrict__ msg_out = reinterpret_cast<T*>(a.msg_out);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (sweep_already_converged(a.resmax, a.stop_key)) return;
   unsigned long long key = 0ull;  // 0 = nothing recorded (residual_key never returns 0)
 
   // one warp = 32 consecutive vertices of the bucket per iteration (all lanes stay in the loop: warp collectives inside).

@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-OUT = os.path.join(HERE, "libbpx.so")
+OUT = os.environ.get("BPX_BUILD_OUT", os.path.join(HERE, "libbpx.so"))  # BPX_BUILD_OUT: debug builds next to the product
 SOURCES = ["bpx_api.cu"]
 DEPS = [f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".h"))] + [os.path.join("..", "..", "include", "bpx.h")]
 

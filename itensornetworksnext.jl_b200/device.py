@@ -19,14 +19,23 @@ def _ptr(a: Optional[np.ndarray]):
 
 
 class BPXContext:
-    def __init__(self, device: int = 0):
+    """`BPXContext(0)`: one device.  `BPXContext(devices=[0, 1, ...])`: ONE context over several devices of this process
+    (bpx_create_multi): same methods, the library partitions the vertices and exchanges cut-edge messages over NVLink."""
+
+    def __init__(self, device: int = 0, devices: Optional[Sequence[int]] = None):
         self.lib = _lib.load()
         h = C.c_void_p()
-        rc = self.lib.bpx_create(int(device), C.byref(h))
+        if devices is not None:
+            devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+            rc = self.lib.bpx_create_multi(_ptr(devs), len(devs), C.byref(h))
+            device = int(devs[0]) if len(devs) else 0
+        else:
+            rc = self.lib.bpx_create(int(device), C.byref(h))
         if rc != 0:
             raise BPXError(rc, self.lib.bpx_last_error(None).decode())
         self.h = h
         self.device = device
+        self.devices = [int(d) for d in devices] if devices is not None else [int(device)]
         self.dtype = None
         self.mode = None
         self.nv = self.ne = 0
@@ -85,6 +94,16 @@ class BPXContext:
             raise RuntimeError("packed layout mismatch between the host mirror and libbpx")
         self.link_dim = ld
 
+    def set_owner(self, owner: Sequence[int]):
+        """Multi-device contexts: owner[v] = index of the device that updates the out-edges of v (after set_dims)."""
+        own = np.ascontiguousarray(owner, dtype=np.int32)
+        self._check(self.lib.bpx_set_owner(self.h, _ptr(own)))
+
+    def get_owner(self) -> np.ndarray:
+        out = np.zeros(self.nv, dtype=np.int32)
+        self._check(self.lib.bpx_get_owner(self.h, _ptr(out)))
+        return out
+
     # -- data --------------------------------------------------------------------------------------
     def pack_sites(self, tensors: Sequence[np.ndarray]) -> np.ndarray:
         out = np.empty(int(self.site_off[-1]), dtype=self.dtype)
@@ -141,7 +160,7 @@ class BPXContext:
 
     def get_site_tensor(self, v: int) -> np.ndarray:
         """Download one canonical site tensor (flat, column-major): `state[v]` after gates were applied."""
-        if self.lib.bpx_site_device_offset(self.h, int(v)) < 0:
+        if len(self.devices) == 1 and self.lib.bpx_site_device_offset(self.h, int(v)) < 0:
             raise KeyError(f"site tensor {v} is not resident on this rank")
         out = np.empty(int(self.site_off[v + 1] - self.site_off[v]), dtype=self.dtype)
         self._check(self.lib.bpx_get_site_tensor(self.h, int(v), _ptr(out)))
