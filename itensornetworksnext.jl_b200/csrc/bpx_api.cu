@@ -108,6 +108,7 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_sliced2_items);
   F(c->d_sliced2_group_ptr);
   F(c->d_sliced2_partials);
+  F(c->d_sliced2_part1);
   F(c->d_sliced2_gsync);
   c->n_sliced2_groups = c->n_sliced2_items = 0;
   F(c->d_onchip16_items);

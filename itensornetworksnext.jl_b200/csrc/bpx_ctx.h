@@ -84,6 +84,7 @@ struct bpx_ctx {
   int32_t* d_sliced2_group_ptr = nullptr;
   int n_sliced2_items = 0, n_sliced2_groups = 0, sliced2_G = 0, sliced2_grid = 0;
   void* d_sliced2_partials = nullptr;
+  void* d_sliced2_part1 = nullptr;
   unsigned int* d_sliced2_gsync = nullptr;
   alignas(64) unsigned char sliced2_tmaps[4 * 128];  // sliced2::TensorMaps (four CUtensorMap), rebuilt with the buffers
   void* d_onchip16c_items = nullptr;  // complex chi = 16 kernel: items laid out as rounds (slot r * grid + cta)

@@ -104,7 +104,7 @@ inline int sliced2_encode_views(bpx_ctx* ctx, void* base, size_t n, CUtensorMap*
     const cuuint64_t strides[2] = {256 * 8, 8192 * 8};
     const cuuint32_t box[3] = {256, 1, 16};
     const CUresult r = enc(a0h, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_SWIZZLE_NONE, getenv("BPX_TMAP_NOPROMO") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error(ctx, "cuTensorMapEncodeTiled(a0-half-slice view) failed: %d", (int)r);
       return BPX_ERR_CUDA;
@@ -115,7 +115,7 @@ inline int sliced2_encode_views(bpx_ctx* ctx, void* base, size_t n, CUtensorMap*
     const cuuint64_t strides[2] = {128 * 8, 256 * 8};
     const cuuint32_t box[3] = {128, 1, 32};
     const CUresult r = enc(a3h, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_SWIZZLE_NONE, getenv("BPX_TMAP_NOPROMO") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error(ctx, "cuTensorMapEncodeTiled(a3-half-slice view) failed: %d", (int)r);
       return BPX_ERR_CUDA;
@@ -488,6 +488,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
     F(ctx->d_sliced2_items);
     F(ctx->d_sliced2_group_ptr);
     F(ctx->d_sliced2_partials);
+    F(ctx->d_sliced2_part1);
     F(ctx->d_sliced2_gsync);
     ctx->n_sliced2_items = ctx->n_sliced2_groups = ctx->sliced2_G = ctx->sliced2_grid = 0;
     std::vector<sliced::ItemDesc> sit;
@@ -557,6 +558,7 @@ inline int fast_prepare(bpx_ctx* ctx) {
       if (e == cudaSuccess && v2) e = cudaMalloc((void**)&ctx->d_sliced2_items, grouped.size() * sizeof(sliced2::VItem));
       if (e == cudaSuccess && v2) e = cudaMalloc((void**)&ctx->d_sliced2_group_ptr, group_ptr.size() * sizeof(int32_t));
       if (e == cudaSuccess && v2) e = cudaMalloc(&ctx->d_sliced2_partials, (size_t)ctx->n_sliced2_groups * sliced2::PART_PER_GROUP * sizeof(double));
+      if (e == cudaSuccess && v2) e = cudaMalloc(&ctx->d_sliced2_part1, (size_t)ctx->sliced2_grid * sliced2::PART1_PER_CTA * sizeof(double));
       if (e == cudaSuccess && v2) e = cudaMalloc((void**)&ctx->d_sliced2_gsync, (size_t)ctx->n_sliced2_groups * sliced2::GS_STRIDE * sizeof(unsigned int));
       if (e != cudaSuccess) {
         set_error(ctx, "cudaMalloc(sliced kernel items/scratch) failed: %s", cudaGetErrorString(e));
@@ -793,8 +795,10 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     k.sites = (const double*)ctx->d_sites_swz;
     k.scratch = (double*)ctx->d_fast_scratch;
     k.partials = (double*)ctx->d_sliced2_partials;
+    k.part1 = (double*)ctx->d_sliced2_part1;
     k.gsync = ctx->d_sliced2_gsync;
     k.timing = (long long*)ctx->d_timing;
+    k.flags = getenv("BPX_SLICED_FLAGS") ? atoi(getenv("BPX_SLICED_FLAGS")) : 0;
     k.msg_in = (const double*)msg_in;
     k.msg_out = (double*)msg_out;
     k.residual = nullptr;

@@ -39,10 +39,11 @@ namespace sliced2 {
 
 using namespace sliced;
 
-constexpr int NTHREADS2 = NCT + 96;  // 8 compute warps + producer + communication + epilogue
-constexpr int WARP_PRODUCER = NCW, WARP_COMM = NCW + 1, WARP_EPILOGUE = NCW + 2;
+constexpr int NTHREADS2 = NCT + 128;  // 8 compute warps + producer + communication + reducer + epilogue
+constexpr int WARP_PRODUCER = NCW, WARP_COMM = NCW + 1, WARP_REDUCER = NCW + 2, WARP_EPILOGUE = NCW + 3;
 constexpr int PART_GEN = 3;  // generations of partial tiles in flight (vertex v uses v % 3): the epilogue of v may lag two vertices
-constexpr size_t PART_PER_GROUP = (size_t)PART_GEN * 8 * NCW * 4 * MSG;  // doubles: [v % 3][member][warp][output leg][256]
+constexpr size_t PART_PER_GROUP = (size_t)PART_GEN * 8 * 4 * MSG;  // doubles: [v % 3][member][output leg][256], fragment order
+constexpr size_t PART1_PER_CTA = (size_t)2 * NCW * 2 * MSG;        // doubles: [dump parity][warp][tile][256], fragment order
 
 struct VItem {  // one (degree 4, chi 16) vertex
   int64_t site_off;   // elements, into the private image buffer
@@ -62,7 +63,8 @@ struct Args {
   int G;                     // CTAs per group (8 or 4); the last group may have fewer (>= 4, a divisor of 16)
   const double* sites;       // private swizzled image
   double* scratch;           // per group: 2 x NTENSOR doubles
-  double* partials;          // per group: PART_PER_GROUP doubles (per-warp partial output tiles, fragment order)
+  double* partials;          // per group: PART_PER_GROUP doubles (one partial tile per member and output leg)
+  double* part1;             // per CTA: PART1_PER_CTA doubles (per-warp partial tiles of the last two dumps, L2 resident)
   unsigned int* gsync;       // per group: GS_STRIDE counters, zeroed before the launch
   const double* msg_in;
   double* msg_out;
@@ -73,6 +75,8 @@ struct Args {
   HostIO io;                   // streamed host I/O (bpx_sweep_host), all NULL otherwise
   unsigned long long stop_key; // device-side convergence test (sweep_already_converged), 0: none
   long long* timing;           // debug (BPX_SLICED_TIMING builds): per-CTA cycle counters, 16 per CTA
+  int flags;                   // tuning experiments (BPX_SLICED_FLAGS): 1 = no L2 eviction hints, 2 = L2 prefetch of the next vertex's
+                               // tensor slices (measured: +0.8 MB of DRAM traffic per vertex for no gain in time: off)
 };
 
 #ifdef BPX_SLICED_TIMING
@@ -87,7 +91,8 @@ struct Args {
 constexpr size_t SMEM2_DOUBLES = (size_t)3 * SLICE + 8 * MSG + MSG + 16;
 constexpr size_t SMEM2_BYTES = SMEM2_DOUBLES * sizeof(double);
 enum { M2_FULL = 0 /*3*/, M2_DONE = 3 /*3*/, M2_MSG = 6 /*2*/, M2_EV = 8 /* 8 plain 32-bit event counters */ };
-enum { EV_B1 = 0, EV_B2 = 1, EV_DUMP = 2, EV_EPI = 3 };  // S1 / S2 stages stored, warp dumps written, epilogues finished
+enum { EV_B1 = 0, EV_B2 = 1, EV_DUMP = 2, EV_EPI = 3, EV_RED = 4 };  // S1 / S2 stages stored, warp dumps written, epilogues
+                                                                      // finished, dumps reduced
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
@@ -148,6 +153,36 @@ __device__ __forceinline__ void tma_tensor3_s2g(const CUtensorMap* tm, int c0, i
                : "memory");
 }
 
+// L2 eviction priorities: the scratch images (P / Q) are written and re-read by the whole group within one vertex period and
+// must not be written back to DRAM in between (evict_last); the tensor's last pass will not be needed again (evict_first)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_tensor3_g2s_hint(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;\n" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_tensor3_s2g_hint(const CUtensorMap* tm, int c0, int c1, int c2, const void* src, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;\n" ::"l"(tm), "r"(c0),
+               "r"(c1), "r"(c2), "r"(smem_u32(src)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_s2g_hint(void* gdst, const void* ssrc, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes),
+               "l"(pol)
+               : "memory");
+}
+
 enum { K_S1 = 0, K_S2 = 1, K_S3 = 2 };
 struct Step {
   int kind, v, q;
@@ -199,6 +234,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
   const int T = n * (nS1 + 2 * nS2);
   double* const scratch0 = k.scratch + (size_t)grp * 2 * NTENSOR;
   double* const part0 = k.partials + (size_t)grp * PART_PER_GROUP;
+  double* const part1 = k.part1 + (size_t)blockIdx.x * PART1_PER_CTA;
   unsigned int* const gs = k.gsync + (size_t)grp * GS_STRIDE;
 
   if (threadIdx.x == 0) {
@@ -218,6 +254,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
     // ================================ producer warp ================================
     const long long tp0 = TCLK();
     peer_gate(k.peer, lane);  // multi-GPU: the peers' cut-edge messages of the previous sweep have landed
+    const bool hints = !(k.flags & 1);
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_done = l2_policy_evict_first();
     int L = 0;                 // next step to load
     unsigned int myB1 = 0, myB2 = 0;
     int pending_post = -1;     // stage kind whose stores were committed with the previous step; post once they completed
@@ -264,7 +302,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
           if (lane < 4) tma_bulk_g2s(msgs + ((s.v & 1) * 4 + lane) * MSG, k.msg_in + d->in_off[lane], MSG * 8, mb);
         } else {
           // (can_load has seen every member's stores of the producing stage complete, with acquire semantics)
-          if (s.kind == K_S2 && s.v + 1 < n) {
+          if (s.kind == K_S2 && s.v + 1 < n && (k.flags & 2)) {
             // this member's tensor slices of the NEXT vertex: start them on their way from DRAM into the L2 now
             const double* An = k.sites + k.items[base_item + s.v + 1].site_off;
             for (int q = lane >> 2; q < nS1; q += 8)
@@ -282,14 +320,23 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
         const int r = j + (s.q >> 1) * Gm, hh = s.q & 1;  // a0-half slice (a0 = r, a1[3] = hh): 16 rows (a3) of 2 KiB
         const size_t go = ((size_t)r << 9) + ((size_t)hh << 8);
         const size_t sp = (size_t)(scr - k.scratch) + go, sa = (size_t)d->site_off + go;
-        if (lane == 0) tma_tensor3_g2s(dst, &tm.a0h_scratch, 0, (int)((sp >> 8) & 31), (int)(sp >> 13), &mbar[M2_FULL + b]);
+        if (lane == 0) {
+          if (hints) tma_tensor3_g2s_hint(dst, &tm.a0h_scratch, 0, (int)((sp >> 8) & 31), (int)(sp >> 13), &mbar[M2_FULL + b], pol_keep);
+          else tma_tensor3_g2s(dst, &tm.a0h_scratch, 0, (int)((sp >> 8) & 31), (int)(sp >> 13), &mbar[M2_FULL + b]);
+        }
         if (lane == 1) tma_tensor3_g2s(dst + HALF, &tm.a0h_sites, 0, (int)((sa >> 8) & 31), (int)(sa >> 13), &mbar[M2_FULL + b]);
       } else {
         const int r = j + (s.q >> 1) * Gm, hh = s.q & 1;  // a3-half slice (a3 = r, a2[3] = hh): 32 rows (a0, a1[3]) of 1 KiB
         const size_t go = ((size_t)r << 13) + ((size_t)hh << 7);
         const size_t sp = (size_t)(scr - k.scratch) + go, sa = (size_t)d->site_off + go;
-        if (lane == 0) tma_tensor3_g2s(dst, &tm.a3h_scratch, 0, (int)((sp >> 7) & 1), (int)(sp >> 8), &mbar[M2_FULL + b]);
-        if (lane == 1) tma_tensor3_g2s(dst + HALF, &tm.a3h_sites, 0, (int)((sa >> 7) & 1), (int)(sa >> 8), &mbar[M2_FULL + b]);
+        if (lane == 0) {
+          if (hints) tma_tensor3_g2s_hint(dst, &tm.a3h_scratch, 0, (int)((sp >> 7) & 1), (int)(sp >> 8), &mbar[M2_FULL + b], pol_keep);
+          else tma_tensor3_g2s(dst, &tm.a3h_scratch, 0, (int)((sp >> 7) & 1), (int)(sp >> 8), &mbar[M2_FULL + b]);
+        }
+        if (lane == 1) {
+          if (hints) tma_tensor3_g2s_hint(dst + HALF, &tm.a3h_sites, 0, (int)((sa >> 7) & 1), (int)(sa >> 8), &mbar[M2_FULL + b], pol_done);
+          else tma_tensor3_g2s(dst + HALF, &tm.a3h_sites, 0, (int)((sa >> 7) & 1), (int)(sa >> 8), &mbar[M2_FULL + b]);
+        }
       }
     };
     auto pump = [&](int r) {  // issue every load that may go out now: at most two steps ahead of the retired one
@@ -319,11 +366,17 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
       // every lane that stores owns its bulk group: lanes issue, commit and wait symmetrically (one group per step)
       if (s.kind == K_S1) {
         const int rr = j + s.q * Gm;
-        if (lane < 4) tma_bulk_s2g(scr + ((size_t)rr << 13) + lane * 2048, src + lane * 2048, 16384);
+        if (lane < 4) {
+          if (hints) tma_bulk_s2g_hint(scr + ((size_t)rr << 13) + lane * 2048, src + lane * 2048, 16384, pol_keep);
+          else tma_bulk_s2g(scr + ((size_t)rr << 13) + lane * 2048, src + lane * 2048, 16384);
+        }
       } else if (s.kind == K_S2) {
         const int rr = j + (s.q >> 1) * Gm, hh = s.q & 1;  // the A half of the slot now holds Q[a0 = rr, a1[3] = hh, ..]
         const size_t sp = (size_t)(scr - k.scratch) + ((size_t)rr << 9) + ((size_t)hh << 8);
-        if (lane == 0) tma_tensor3_s2g(&tm.a0h_scratch, 0, (int)((sp >> 8) & 31), (int)(sp >> 13), src + HALF);
+        if (lane == 0) {
+          if (hints) tma_tensor3_s2g_hint(&tm.a0h_scratch, 0, (int)((sp >> 8) & 31), (int)(sp >> 13), src + HALF, pol_keep);
+          else tma_tensor3_s2g(&tm.a0h_scratch, 0, (int)((sp >> 8) & 31), (int)(sp >> 13), src + HALF);
+        }
       }
       bulk_commit();
       const bool stage_end = (s.kind == K_S1 && s.q == nS1 - 1) || (s.kind == K_S2 && s.q == nS2 - 1);
@@ -359,10 +412,10 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
     // shared-memory events -> arrivals on the group's global counters.  One lane, a non-blocking service loop: every
     // pending event is forwarded as soon as it is seen (the fences this takes run here, next to nothing else).
     if (lane == 0) {
-      unsigned sent_b1 = 0, sent_b2 = 0, sent_d = 0;
+      unsigned sent_b1 = 0, sent_b2 = 0;
       const unsigned un = (unsigned)n;
       const long long t0 = clock64();
-      while (sent_b1 < un || sent_b2 < un || sent_d < 2u * un) {
+      while (sent_b1 < un || sent_b2 < un) {
         bool progress = false;
         // B1(v): before anybody may overwrite the partial tiles of vertex v - 3 (S2(v) dumps into the same generation), my
         // epilogue warp must have finished with them
@@ -376,15 +429,54 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
           ++sent_b2;
           progress = true;
         }
-        if (ev[EV_DUMP] >= (unsigned)NCW * (sent_d + 1u)) {  // dump d: even = S2 (out3, out2), odd = S3 (out1, out0)
-          red_release_gpu(gs + ((sent_d & 1u) ? GS_B3B : GS_B3A));
-          ++sent_d;
-          progress = true;
-        }
         if (!progress) {
           __nanosleep(100);
           if (clock64() - t0 > 40000000000ll) __trap();
         }
+      }
+    }
+  } else if (warp == WARP_REDUCER) {
+    // ================================ reducer warp ================================
+    // dump d (even: S2(d / 2) -> out3, out2; odd: S3(d / 2) -> out1, out0): sum the eight warps' partial tiles (written to
+    // this CTA's L2-resident slots a moment ago) in warp order -> this member's tile of the group's partial buffer; arrive
+    for (int dmp = 0; dmp < 2 * n; ++dmp) {
+      if (lane == 0) {
+        const long long t0 = clock64();
+        while (ev[EV_DUMP] < (unsigned)NCW * (unsigned)(dmp + 1)) {
+          __nanosleep(100);
+          if (clock64() - t0 > 40000000000ll) __trap();
+        }
+      }
+      __syncwarp();
+      __threadfence_block();
+      const int i = dmp >> 1;
+      const int legs[2] = {(dmp & 1) ? 1 : 3, (dmp & 1) ? 0 : 2};
+      const double2* src = reinterpret_cast<const double2*>(part1 + (size_t)(dmp & 1) * NCW * 2 * MSG) + lane;
+      double* dstg = part0 + ((size_t)(i % PART_GEN) * 8 + j) * 4 * MSG;
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        double2 v[NCW][4];
+#pragma unroll
+        for (int w = 0; w < NCW; ++w)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[w][q] = __ldcg(src + ((size_t)w * 2 + tile) * (MSG / 2) + q * 32);
+        double2* out = reinterpret_cast<double2*>(dstg + (size_t)legs[tile] * MSG) + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          double2 a = v[0][q];
+#pragma unroll
+          for (int w = 1; w < NCW; ++w) {
+            a.x += v[w][q].x;
+            a.y += v[w][q].y;
+          }
+          __stcg(out + q * 32, a);
+        }
+      }
+      __threadfence();  // every lane's stores, before lane 0's arrival
+      __syncwarp();
+      if (lane == 0) {
+        red_release_gpu(gs + ((dmp & 1) ? GS_B3B : GS_B3A));
+        ev[EV_RED] = (unsigned)(dmp + 1);
       }
     }
   } else if (warp == WARP_EPILOGUE) {
@@ -400,28 +492,22 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
       __syncwarp();
       TACC(11, tw);
       if (k.io.progress) hostio_wait(k.io, d->need);
-      const double* part = part0 + (size_t)(i % PART_GEN) * 8 * NCW * 4 * MSG;
+      const double* part = part0 + (size_t)(i % PART_GEN) * 8 * 4 * MSG;
 #pragma unroll 1
       for (int leg = 0; leg < 4; ++leg) {
         if ((i + leg) % Gm != j) continue;  // this member finishes out-edge `leg` of vertex i
-        // sum the Gm x 8 partial tiles (fragment order: double2 (i2 = 0, 1) at [(mt * 2 + h) * 32 + lane]) in a fixed order
+        // sum the Gm members' partial tiles (fragment order: double2 (i2 = 0, 1) at [(mt * 2 + h) * 32 + lane]) in member order
         double2 acc[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[q] = make_double2(0.0, 0.0);
         for (int m = 0; m < Gm; ++m) {
-          const double2* src = reinterpret_cast<const double2*>(part + (((size_t)m * NCW) * 4 + leg) * MSG) + lane;
-          double2 v[NCW][4];
+          const double2* src = reinterpret_cast<const double2*>(part + ((size_t)m * 4 + leg) * MSG) + lane;
 #pragma unroll
-          for (int w = 0; w < NCW; ++w)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[w][q] = __ldcg(src + (size_t)w * 4 * (MSG / 2) + q * 32);
-#pragma unroll
-          for (int w = 0; w < NCW; ++w)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              acc[q].x += v[w][q].x;
-              acc[q].y += v[w][q].y;
-            }
+          for (int q = 0; q < 4; ++q) {
+            const double2 v = __ldcg(src + q * 32);
+            acc[q].x += v.x;
+            acc[q].y += v.y;
+          }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -445,12 +531,17 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
     // ================================ compute warps ================================
     int t = 0;  // running step index (slot = t % 3, mbarrier parity = (t / 3) & 1)
     const long long tc0 = TCLK();
-    auto dump = [&](int i, int leg_a, int leg_b, const double (&accA)[2][2][2], const double (&accB)[2][2][2]) {
-      // this warp's two partial output tiles -> its slots of the group's partial buffer (L2), fragment order, coalesced
+    int n_dump = 0;  // dumps so far (S2(0), S3(0), S2(1), S3(1), ...)
+    auto dump = [&](const double (&accA)[2][2][2], const double (&accB)[2][2][2]) {
+      // this warp's two partial output tiles -> its slots of the CTA's two-deep dump buffer (L2), fragment order, coalesced
       const long long tdump = TCLK();
-      double* part = part0 + ((((size_t)(i % PART_GEN) * 8 + j) * NCW + warp) * 4) * MSG;
-      double2* pa = reinterpret_cast<double2*>(part + (size_t)leg_a * MSG) + lane;
-      double2* pb = reinterpret_cast<double2*>(part + (size_t)leg_b * MSG) + lane;
+      if (n_dump >= 2) {  // the reducer has finished with the dump before last (in practice: long ago)
+        if (lane == 0)
+          while (ev[EV_RED] + 2u <= (unsigned)n_dump) __nanosleep(64);
+        __syncwarp();
+      }
+      double2* pa = reinterpret_cast<double2*>(part1 + (((size_t)(n_dump & 1) * NCW + warp) * 2) * MSG) + lane;
+      double2* pb = pa + MSG / 2;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -463,6 +554,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
         __threadfence_block();
         atomicAdd_block(const_cast<unsigned int*>(&ev[EV_DUMP]), 1u);
       }
+      ++n_dump;
       if (warp == 0) TACC(4, tdump);
     };
     for (int v = 0; v <= n; ++v) {
@@ -513,7 +605,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
           __syncwarp();
           if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
         }
-        dump(i, 1, 0, accA, accB);
+        dump(accA, accB);  // tile 0 -> out1, tile 1 -> out0
       }
       if (v < n) {
         // ---- S2(v): a0-half slices of P and A; absorb 2 / close 3 -> out3, absorb 3 / close 2 -> out2;
@@ -544,7 +636,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
           __syncwarp();
           if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
         }
-        dump(v, 3, 2, accA, accB);
+        dump(accA, accB);  // tile 0 -> out3, tile 1 -> out2
       }
     }
     if (warp == 0) TACC(0, tc0);
