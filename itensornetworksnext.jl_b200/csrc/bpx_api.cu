@@ -714,6 +714,10 @@ static int sweep_host_staged_enqueue(bpx_ctx* ctx, const void* packed_in, void* 
     const size_t o = (size_t)r.first * ctx->esize, len = (size_t)(r.second - r.first) * ctx->esize;
     BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_msg[ctx->cur] + o, (const char*)packed_in + o, len, cudaMemcpyHostToDevice, ctx->stream));
   }
+  for (auto& r : ctx->halo_in_runs) {  // (children of a multi-device context: the peers' cut-edge messages, from the host too)
+    const size_t o = (size_t)r.first * ctx->esize, len = (size_t)(r.second - r.first) * ctx->esize;
+    BPX_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_msg[ctx->cur] + o, (const char*)packed_in + o, len, cudaMemcpyHostToDevice, ctx->stream));
+  }
   if ((rc = sweep_once(ctx, normalize))) return rc;
   for (auto& r : ctx->owned_runs) {
     const size_t o = (size_t)r.first * ctx->esize, len = (size_t)(r.second - r.first) * ctx->esize;

@@ -164,6 +164,9 @@ struct bpx_ctx {
   std::vector<bpx_ctx*> children;
   std::vector<int32_t> multi_owner;  // owner[v] = index of the child that updates the out-edges of v
   bool is_child = false;
+  // children only: element runs of the messages on cut edges that point INTO this device's block; a host iterate
+  // (bpx_sweep_host) uploads them too, so that one call depends on its host buffer alone
+  std::vector<std::pair<int64_t, int64_t>> halo_in_runs;
 };
 
 namespace bpx {

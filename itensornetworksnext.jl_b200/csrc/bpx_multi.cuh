@@ -75,6 +75,7 @@ static int partition(bpx_ctx* m, const int32_t* owner_or_null) {
       return BPX_ERR_INVALID;
     }
   m->multi_owner = owner;
+  for (bpx_ctx* c : m->children) c->halo_in_runs.clear();
   if (n == 1) return BPX_OK;
   int rank = 0;
   for (bpx_ctx* c : m->children) {
@@ -85,6 +86,13 @@ static int partition(bpx_ctx* m, const int32_t* owner_or_null) {
   for (int a = 0; a < n; ++a) {
     bpx_ctx* ca = m->children[a];
     cudaSetDevice(ca->device);
+    ca->halo_in_runs.clear();
+    for (int64_t e = 0; e < c0->ne; ++e)
+      if (owner[c0->dst[e]] == a && owner[c0->src[e]] != a) {
+        const int64_t b0 = c0->msg_off[e], b1 = c0->msg_off[e + 1];
+        if (!ca->halo_in_runs.empty() && ca->halo_in_runs.back().second == b0) ca->halo_in_runs.back().second = b1;
+        else ca->halo_in_runs.emplace_back(b0, b1);
+      }
     for (int b = 0; b < n; ++b)
       if (b != a) connect_direct(ca, m->children[b], b);
     const int rc = bpx::halo_finalize(ca);

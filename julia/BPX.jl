@@ -19,7 +19,7 @@ using ITensorNetworksNext.AlgorithmsInterfaceExtensions: AlgorithmsInterfaceExte
 import AlgorithmsInterface as AI
 using Graphs: vertices, src, dst, neighbors
 using NamedGraphs: NamedEdge
-using ITensorBase: ITensor, dimnames, unnamed
+using ITensorBase: ITensorBase, ITensor, dimnames, unnamed
 
 const libbpx = get(ENV, "LIBBPX", "libbpx.so")
 const BPX_F64, BPX_C64 = Cint(0), Cint(1)
@@ -36,15 +36,26 @@ function check(ctx::Ptr{Cvoid}, rc::Cint)
 end
 
 """
-    B200MessageUpdate(; normalize = true, device = 0)
+    B200MessageUpdate(; normalize = true, devices = [0])
 
-Message-update strategy that runs whole synchronous BP sweeps on one B200 through libbpx.  Pass it as
-`beliefpropagation(nn, messages; message_update_algorithm = B200MessageUpdate(), stopping_criterion = ...)`.
-The device context is created lazily on the first sweep and kept in the (mutable) strategy object.
+Message-update strategy that runs whole synchronous BP sweeps on one or several B200s of this process through libbpx.
+Pass it as `beliefpropagation(nn, messages; message_update_algorithm = B200MessageUpdate(devices = 0:7), ...)`: ONE
+context over the device list (`bpx_create_multi`), the library partitions the vertices and exchanges cut-edge messages
+over NVLink inside the sweep kernels -- no MPI, no second Julia process.  The context is created lazily on the first
+sweep and kept in the (mutable) strategy object.
+
+Two ways to hold the iterate (SURVEY.md 8 b2):
+  (A) ordinary ITensor messages on the host: works with the stock `StopWhenConverged`; every outer iteration is one
+      `bpx_sweep_host` call (packed iterate in, packed iterate + fused residual out);
+  (B) `device_iterate(alg, nn, messages)`: the messages handed to `beliefpropagation` are `DeviceMessageRef`s (edge id +
+      context).  `copy(iterate)` copies refs, `AIE.iterate_diff` returns the residual fused into the last sweep's kernels,
+      a sweep is one `bpx_sweep` call without any message traffic, and `materialize(cache)` / `ITensor(ref)` download on
+      demand.  `solve_resident!(alg, nn, messages; maxiter, tol)` runs the whole `(; maxiter, tol)` loop in ONE call with
+      the convergence test on the device.
 """
 mutable struct B200MessageUpdate <: MessageUpdateAlgorithm
     normalize::Bool
-    device::Int
+    devices::Vector{Cint}
     ctx::Ptr{Cvoid}
     edge_ids::Dict{Any, Int}      # NamedEdge -> directed edge id of the C ABI
     vertex_ids::Dict{Any, Int}
@@ -54,8 +65,8 @@ mutable struct B200MessageUpdate <: MessageUpdateAlgorithm
     host_in::Vector               # page-locked packed iterates (bpx_host_register): bpx_sweep_host streams through them
     host_out::Vector
 end
-B200MessageUpdate(; normalize = true, device = 0) =
-    B200MessageUpdate(normalize, device, C_NULL, Dict(), Dict(), Tuple{Any, Any}[], true, Inf, Float64[], Float64[])
+B200MessageUpdate(; normalize = true, devices = [0]) =
+    B200MessageUpdate(normalize, Cint.(collect(devices)), C_NULL, Dict(), Dict(), Tuple{Any, Any}[], true, Inf, Float64[], Float64[])
 
 # Two packed host iterates, page-locked once: with such buffers `bpx_sweep_host` overlaps the upload with the sweep
 # kernel and lets the kernel store the new messages straight into `host_out` (include/bpx.h).
@@ -80,7 +91,8 @@ function upload!(alg::B200MessageUpdate, nn::NormNetwork, cache::MessageCache)
         push!(srcs, alg.vertex_ids[v]); push!(dsts, alg.vertex_ids[w]); push!(slots, k - 1)
     end
     ctxref = Ref{Ptr{Cvoid}}(C_NULL)
-    rc = ccall((:bpx_create, libbpx), Cint, (Cint, Ref{Ptr{Cvoid}}), alg.device, ctxref)
+    # one context over the whole device list (a single device is the list of one)
+    rc = ccall((:bpx_create_multi, libbpx), Cint, (Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}), alg.devices, length(alg.devices), ctxref)
     rc == 0 || throw(BPXError(rc, unsafe_string(ccall((:bpx_last_error, libbpx), Cstring, (Ptr{Cvoid},), C_NULL))))
     ctx = alg.ctx = ctxref[]
     check(ctx, ccall((:bpx_set_graph, libbpx), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}),
@@ -183,6 +195,80 @@ function AI.step!(
     return state
 end
 
+# ---- variant (B): device-resident iterate --------------------------------------------------------------------
+"""A message that lives on the device: what `MessageCache` holds when the iterate is resident (valtype of the messages
+handed to `beliefpropagation`, messagecache.jl:33-49)."""
+struct DeviceMessageRef
+    alg::B200MessageUpdate
+    edge_id::Int
+end
+
+"download one message as an ordinary ITensor (axes (bra, ket) like messagecache.jl:211-218)"
+function ITensorBase.ITensor(r::DeviceMessageRef)
+    ctx = r.alg.ctx
+    n = ccall((:bpx_message_offset, libbpx), Int64, (Ptr{Cvoid}, Int64), ctx, r.edge_id + 1) -
+        ccall((:bpx_message_offset, libbpx), Int64, (Ptr{Cvoid}, Int64), ctx, r.edge_id)
+    E = r.alg.host_in isa Vector{ComplexF64} ? ComplexF64 : Float64
+    buf = Vector{E}(undef, n)
+    GC.@preserve buf check(ctx, ccall((:bpx_get_message, libbpx), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}), ctx, r.edge_id, buf))
+    χ = isqrt(n)
+    return ITensor(reshape(buf, χ, χ), r.alg.bra_ket[r.edge_id + 1])
+end
+
+"""
+    device_iterate(alg, nn, messages) -> messages of `DeviceMessageRef`
+
+Upload the network and the initial messages once and return the resident iterate to pass to `beliefpropagation`.
+"""
+function device_iterate(alg::B200MessageUpdate, nn::NormNetwork, messages)
+    cache = MessageCache(messages)
+    alg.ctx == C_NULL ? upload!(alg, nn, cache) : push_messages!(alg, cache, eltype(alg.host_in) <: Complex ? ComplexF64 : Float64)
+    return Dict(e => DeviceMessageRef(alg, id) for (e, id) in alg.edge_ids)
+end
+
+# `copy(iterate)` runs every outer iteration (AIE.jl:74, 96): refs are immutable handles, the cache itself is the copy
+Base.copy(c::MessageCache{DeviceMessageRef}) = c
+# ... and the comparison of two iterates is the residual the sweep kernels fused into their epilogues (bp.jl:261-267)
+function AIE.iterate_diff(a::MessageCache{DeviceMessageRef}, ::MessageCache{DeviceMessageRef})
+    return first(values(a.messages)).alg.last_residual
+end
+
+"all messages as ordinary ITensors: one `bpx_get_messages`"
+function materialize(c::MessageCache{DeviceMessageRef})
+    alg = first(values(c.messages)).alg
+    return MessageCache(Dict(e => ITensor(r) for (e, r) in pairs(c.messages)))   # (bulk variant: pull_messages!)
+end
+
+# one outer iteration on a resident iterate: one sweep, no message traffic; the residual comes back with the call
+function AI.step!(
+        problem::BeliefPropagationProblem,
+        algorithm::BeliefPropagationAlgorithm{<:Any, <:BeliefPropagationSweepAlgorithm{<:B200MessageUpdate}},
+        state::AI.State{<:MessageCache{DeviceMessageRef}}
+    )
+    alg = algorithm.subalgorithm.message_update_algorithm
+    res, done = Ref{Cdouble}(Inf), Ref{Cint}(0)
+    check(alg.ctx, ccall((:bpx_sweep, libbpx), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cint, Ref{Cdouble}, Ref{Cint}),
+        alg.ctx, 1, 0.0, alg.normalize, res, done))
+    alg.last_residual = res[]
+    return state
+end
+
+"""
+    solve_resident!(alg, nn, messages; maxiter, tol) -> (cache, sweeps, residual)
+
+The `(; maxiter, tol)` form of `beliefpropagation` (beliefpropagation.jl:46-54) in ONE call: `StopAfterIteration(maxiter) |
+StopWhenConverged(tol)` is evaluated on the device (sweeps are enqueued in batches, a converged run turns the remaining
+launches into no-ops), so the host neither copies nor compares iterates.
+"""
+function solve_resident!(alg::B200MessageUpdate, nn::NormNetwork, messages; maxiter::Int, tol::Float64)
+    refs = device_iterate(alg, nn, messages)
+    res, done = Ref{Cdouble}(Inf), Ref{Cint}(0)
+    check(alg.ctx, ccall((:bpx_sweep, libbpx), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cint, Ref{Cdouble}, Ref{Cint}),
+        alg.ctx, maxiter, tol, alg.normalize, res, done))
+    alg.last_residual = res[]
+    return materialize(MessageCache(refs)), Int(done[]), res[]
+end
+
 # Per-edge entry kept for API completeness (`message_update!(alg, cache, factors, edge)`, beliefpropagation.jl:242):
 # a one-edge sequential "sweep" on the device.
 function message_update!(alg::B200MessageUpdate, cache, factors, edge)
@@ -247,10 +333,11 @@ BP simple-update gate application (`BPApplyGate`, apply_operators.jl:180-283) on
 and environment are uploaded once (`upload!`), every gate -- or, through `apply_layer!`, every layer of vertex-disjoint
 gates -- is one `ccall`, and tensors / messages are pulled back when the caller asks for them.
 """
-Base.@kwdef struct B200ApplyGate <: ApplyOperatorAlgorithm
+Base.@kwdef mutable struct B200ApplyGate <: ApplyOperatorAlgorithm
     trunc::Union{Nothing, Int} = nothing
     normalize::Bool = false
     bp::B200MessageUpdate = B200MessageUpdate()
+    resident::Tuple{UInt, UInt} = (UInt(0), UInt(0))   # objectid of the (state, env) the device copy mirrors
 end
 
 initialize_output(::typeof(apply_operator!), ::B200ApplyGate, operator, state, env) = copy(state), copy(env)
@@ -264,7 +351,13 @@ end
 
 function apply_operator!(alg::B200ApplyGate, dest, op, state, env)
     bp = alg.bp
-    bp.ctx == C_NULL && upload!(bp, normnetwork(state), env)      # state + env resident from here on
+    # state + env resident from here on -- for THESE objects: a different (or host-modified, hence re-created) state / env
+    # is uploaded again instead of silently acting on the stale device copy
+    if bp.ctx == C_NULL || alg.resident != (objectid(state), objectid(env))
+        bp.ctx == C_NULL || close(bp)
+        upload!(bp, normnetwork(state), env)
+        alg.resident = (objectid(state), objectid(env))
+    end
     E = eltype(unnamed(first(values(env.messages)))) <: Complex ? ComplexF64 : Float64
     vs = [v for v in vertices(state) if !isempty(intersect(domainnames(op), sitenames(state, v)))]
     isempty(vs) && throw(ArgumentError("operator shares no indices with the tensor network"))
@@ -275,7 +368,13 @@ function apply_operator!(alg::B200ApplyGate, dest, op, state, env)
             (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Cvoid}, Cint), bp.ctx, 1, ids, packed, alg.normalize))
     elseif length(vs) == 2
         ids = Int64[bp.edge_ids[NamedEdge(vs[1] => vs[2])]]
-        sv = zeros(Float64, 4096)
+        χe = size(unnamed(env[NamedEdge(vs[1] => vs[2])]), 1)       # the C ABI keeps the link dimension (include/bpx.h)
+        rank_bound = min(prod(size(unnamed(state[vs[1]]))), prod(size(unnamed(state[vs[2]])))) ÷ χe
+        if something(alg.trunc, rank_bound) > χe && rank_bound > χe
+            throw(ArgumentError("this gate would grow the bond from $χe (reference: up to $(something(alg.trunc, rank_bound))): " *
+                "re-declare the link dimension (zero-padded tensors + bpx_set_dims) before the call, as apply.py `_apply_batch` does"))
+        end
+        sv = zeros(Float64, χe)
         GC.@preserve ids packed sv check(bp.ctx, ccall((:bpx_apply_two_site_gates, libbpx), Cint,
             (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}),
             bp.ctx, 1, ids, packed, something(alg.trunc, 0), alg.normalize, sv))
