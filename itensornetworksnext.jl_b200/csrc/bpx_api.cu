@@ -99,6 +99,7 @@ static void free_problem(bpx_ctx* c) {
   F(c->d_generic_edges);
   F(c->d_scratch);
   F(c->d_und_edge);
+  F(c->d_first_out_edge);
   F(c->d_owned_edges);
   F(c->d_owned_vertices);
   F(c->d_all_edges);
@@ -1340,6 +1341,59 @@ extern "C" int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* 
 }
 
 // ---- beliefs --------------------------------------------------------------------------------------
+// vertex_scalar(s) (messagecache.jl:139-151) on the UPDATE kernels: one sweep of every bucket's kernel with normalize = 0
+// from the current message set into the idle one -- no exchange, no residual, no flip -- and one dot product per vertex
+// (bp_vertex_belief).  Every bucket family, single-layer networks included, serves beliefs at sweep speed this way; only
+// isolated vertices (no out-edge) are left to the generic scalar kernel.
+static int belief_sweep(bpx_ctx* ctx, char* d_out /* nv elements, zero-initialised */) {
+  int rc;
+  if ((rc = fast_refresh_sites(ctx))) return rc;
+  const void* in = ctx->d_msg[ctx->cur];
+  void* tmp = ctx->d_msg[ctx->cur ^ 1];
+  const PeerArgs peer0 = ctx->peer_args;
+  const HostIO io0 = ctx->io_args;
+  unsigned long long* const slot0 = ctx->cur_slot;
+  const unsigned long long stop0 = ctx->stop_key;
+  ctx->peer_args = PeerArgs{};
+  ctx->io_args = HostIO{};
+  ctx->stop_key = 0ull;
+  ctx->cur_slot = ctx->d_reskeys + ctx->history_cap;  // spare entry behind the ring: the residual of this pass is discarded
+  rc = BPX_OK;
+  for (int bi = 0; bi < (int)ctx->buckets.size() && rc == BPX_OK; ++bi) {
+    Bucket& b = ctx->buckets[bi];
+    if (b.my_edges.empty() || b.leader != bi) continue;
+    if (b.kernel == BPX_KERNEL_GENERIC) rc = launch_generic_update(ctx, in, tmp, ctx->d_generic_edges, ctx->n_generic_edges, 0, ctx->cur_slot);
+    else if (b.kernel == BPX_KERNEL_VERTEX) rc = launch_vertex_update(ctx, b, in, tmp, 0);
+    else rc = launch_fast_update(ctx, b, in, tmp, 0);
+  }
+  ctx->peer_args = peer0;
+  ctx->io_args = io0;
+  ctx->cur_slot = slot0;
+  ctx->stop_key = stop0;
+  if (rc) return rc;
+  if (!ctx->d_first_out_edge) {
+    std::vector<int32_t> first(ctx->nv, -1);
+    for (int64_t v = 0; v < ctx->nv; ++v)
+      if (!ctx->out_edge[v].empty()) first[v] = ctx->out_edge[v][0];
+    if ((rc = upload(ctx, &ctx->d_first_out_edge, first))) return rc;
+  }
+  const int64_t n_work = ctx->nranks > 1 ? ctx->n_owned_vertices : ctx->nv;
+  if (n_work > 0) {
+    const int threads = 256;
+    const int64_t blocks = (n_work * 32 + threads - 1) / threads;
+    const int32_t* list = ctx->nranks > 1 ? ctx->d_owned_vertices : nullptr;
+    if (ctx->dtype == BPX_F64)
+      bp_vertex_belief<double><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const double*)tmp, (const double*)in, ctx->d_msg_off, ctx->d_rev,
+                                                                             ctx->d_first_out_edge, list, n_work, (double*)d_out);
+    else
+      bp_vertex_belief<c64><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const c64*)tmp, (const c64*)in, ctx->d_msg_off, ctx->d_rev,
+                                                                          ctx->d_first_out_edge, list, n_work, (c64*)d_out);
+    ctx->n_launches++;
+    BPX_CUDA(ctx, cudaGetLastError());
+  }
+  return BPX_OK;
+}
+
 static int vertex_scalars_impl(bpx_ctx* ctx, const void* ops_packed, void* out) {
   const int64_t nv = ctx->nv;
   if (nv == 0) return BPX_OK;
@@ -1361,27 +1415,51 @@ static int vertex_scalars_impl(bpx_ctx* ctx, const void* ops_packed, void* out) 
   }
   // partitioned contexts hold (and know the in-messages of) their own vertices only: the others are reported as 0
   BPX_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)nv * ctx->esize, ctx->stream));
-  GenericArgs g = generic_args(ctx, ctx->d_msg[ctx->cur], nullptr, ctx->nranks > 1 ? ctx->d_owned_vertices : nullptr,
-                               ctx->nranks > 1 ? ctx->n_owned_vertices : nv, 0);
+  int32_t* d_isolated = nullptr;
+  int64_t n_isolated = 0;
+  const bool on_update_kernels = !ops_packed && !getenv("BPX_BELIEFS_GENERIC");
+  if (on_update_kernels) {
+    // plain vertex scalars: at sweep speed on the buckets' own (tensor-pipe) kernels; the generic scalar kernel below then
+    // only visits vertices without a link (their scalar is the plain norm of the tensor)
+    if ((rc = belief_sweep(ctx, d_out))) {
+      cudaFree(d_out);
+      return rc;
+    }
+    std::vector<int32_t> iso;
+    for (int64_t v = 0; v < nv; ++v)
+      if (ctx->out_edge[v].empty() && (ctx->owner.empty() || ctx->owner[v] == ctx->rank)) iso.push_back((int32_t)v);
+    n_isolated = (int64_t)iso.size();
+    if (n_isolated > 0 && (rc = upload(ctx, &d_isolated, iso))) {
+      cudaFree(d_out);
+      return rc;
+    }
+  }
+  GenericArgs g = on_update_kernels
+                      ? generic_args(ctx, ctx->d_msg[ctx->cur], nullptr, d_isolated, n_isolated, 0)
+                      : generic_args(ctx, ctx->d_msg[ctx->cur], nullptr, ctx->nranks > 1 ? ctx->d_owned_vertices : nullptr,
+                                     ctx->nranks > 1 ? ctx->n_owned_vertices : nv, 0);
   g.ops = d_ops;
   g.op_off = d_op_off;
   g.scalars_out = d_out;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(g.n_work, ctx->gen_grid));
   // the scalar kernel needs no output staging, but sharing the update kernel's geometry keeps it simple
-  if (ctx->dtype == BPX_F64) {
-    rc = set_smem(ctx, bp_vertex_scalar_generic<double>, ctx->gen_smem_bytes);
-    if (!rc) bp_vertex_scalar_generic<double><<<grid, 256, ctx->gen_smem_bytes, ctx->stream>>>(g);
-  } else {
-    rc = set_smem(ctx, bp_vertex_scalar_generic<c64>, ctx->gen_smem_bytes);
-    if (!rc) bp_vertex_scalar_generic<c64><<<grid, 256, ctx->gen_smem_bytes, ctx->stream>>>(g);
+  if (g.n_work > 0) {
+    if (ctx->dtype == BPX_F64) {
+      rc = set_smem(ctx, bp_vertex_scalar_generic<double>, ctx->gen_smem_bytes);
+      if (!rc) bp_vertex_scalar_generic<double><<<grid, 256, ctx->gen_smem_bytes, ctx->stream>>>(g);
+    } else {
+      rc = set_smem(ctx, bp_vertex_scalar_generic<c64>, ctx->gen_smem_bytes);
+      if (!rc) bp_vertex_scalar_generic<c64><<<grid, 256, ctx->gen_smem_bytes, ctx->stream>>>(g);
+    }
+    ctx->n_launches++;
   }
-  ctx->n_launches++;
   cudaError_t ce = cudaGetLastError();
   if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_out, (size_t)nv * ctx->esize, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
   cudaFree(d_out);
   cudaFree(d_ops);
   cudaFree(d_op_off);
+  cudaFree(d_isolated);
   if (rc) return rc;
   BPX_CUDA(ctx, ce);
   BPX_CUDA(ctx, ce2);

@@ -61,6 +61,7 @@ struct bpx_ctx {
   // device
   bpx::VDesc* d_vdesc = nullptr;
   int32_t *d_src = nullptr, *d_slot = nullptr, *d_rev = nullptr, *d_und_edge = nullptr;
+  int32_t* d_first_out_edge = nullptr;  // per vertex: its first out-edge (-1: none), built on the first belief pass
   int64_t* d_msg_off = nullptr;
   void* d_sites = nullptr;
   void* d_msg[2] = {nullptr, nullptr};

@@ -225,6 +225,31 @@ __global__ void bp_edge_scalar(const T* __restrict__ msgs, const int64_t* __rest
   if (lane == 0) out[w] = acc;
 }
 
+// vertex_scalar through the update kernels (messagecache.jl:139-143): the factor of v contracted with ALL its incoming
+// messages equals  sum_i Mtilde_{v->w}[i] * M_{w->v}[i]  for any neighbour w, where Mtilde is the UNNORMALISED update output
+// on the out-edge (everything but M_{w->v} absorbed) -- so one sweep of the bucket kernels with normalize = 0 into the idle
+// message set plus this dot product gives every vertex scalar.  One warp per vertex: its first out-edge.
+template <typename T>
+__global__ void bp_vertex_belief(const T* __restrict__ unnormalised_out, const T* __restrict__ msgs_in, const int64_t* __restrict__ msg_off,
+                                 const int32_t* __restrict__ rev, const int32_t* __restrict__ first_out_edge /* per vertex, -1: none */,
+                                 const int32_t* __restrict__ vertices /* work list or NULL */, int64_t n_work, T* __restrict__ out) {
+  using E = Elem<T>;
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_work) return;
+  const int64_t v = vertices ? vertices[w] : w;
+  const int e = first_out_edge[v];
+  if (e < 0) return;  // isolated vertex: left to the generic scalar kernel
+  const int r = rev[e];
+  const int64_t n = msg_off[e + 1] - msg_off[e];
+  const T* a = unnormalised_out + msg_off[e];
+  const T* b = msgs_in + msg_off[r];
+  T acc = E::zero();
+  for (int64_t i = lane; i < n; i += 32) acc = E::fma(a[i], b[i], acc);
+  acc = warp_sum<T>(acc);
+  if (lane == 0) out[v] = acc;
+}
+
 // Per-edge term of iterate_diff (beliefpropagation.jl:261-267) between two message sets.
 template <typename T>
 __global__ void bp_edge_residual(const T* __restrict__ m1, const T* __restrict__ m2, const int64_t* __restrict__ msg_off,
