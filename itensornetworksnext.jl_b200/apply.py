@@ -28,7 +28,7 @@ from typing import Dict, Hashable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from .beliefpropagation import AbstractAlgorithm, ArgumentError, MessageCache
-from .device import BPXContext
+from .device import BPXContext, cast_to
 from .graphs import NamedEdge
 from .tensornetwork import Index, ITensor, ITensorNetwork, NormNetwork, canonical_arrays
 
@@ -108,7 +108,20 @@ def _lowered_operator(op: Operator, state: ITensorNetwork, vs: Sequence, dtype) 
     axes = [out_of[n] for n in flat] + [len(flat) + op.in_names.index(n) for n in flat]
     arr = np.transpose(op.data, axes)
     dims = [int(np.prod([state[v].data.shape[state[v].dimnames().index(n)] for n in s], dtype=np.int64)) for v, s in zip(vs, sites)]
-    return np.ascontiguousarray(arr).reshape(dims + dims).astype(dtype)
+    return cast_to(np.ascontiguousarray(arr).reshape(dims + dims), dtype, "operator")
+
+
+def _promoted(state: ITensorNetwork, ops: Sequence[Operator], env) -> ITensorNetwork:
+    """ITensorBase.apply promotes: a complex gate (exp(-i dt H)) or complex messages on a Float64 state give a ComplexF64
+    state.  The device session takes its dtype from the state, so promote the state here instead of truncating the gate."""
+    if np.dtype(state.dtype).kind == "c":
+        return state
+    need = any(np.iscomplexobj(op.data) for op in ops)
+    if not need and env is not None:
+        need = any(np.iscomplexobj(m.data if isinstance(m, ITensor) else m) for m in env.values())
+    if not need:
+        return state
+    return ITensorNetwork({v: ITensor(t.data.astype(np.complex128), t.inds) for v, t in state.tensors.items()})
 
 
 class _ApplySession:
@@ -155,8 +168,8 @@ class _ApplySession:
             if len(names) != 2 or ket_name not in names:
                 raise ArgumentError(f"message {names} is not an operator on link {ket_name!r}")
             bra = names[0] if names[1] == ket_name else names[1]
-            return np.asarray(m.array(bra, ket_name), dtype=dtype)
-        return np.asarray(m, dtype=dtype)
+            return cast_to(m.array(bra, ket_name), dtype, "message")
+        return cast_to(m, dtype, "message")
 
     def site_itensor(self, v, keep: Optional[Dict[int, int]] = None) -> ITensor:
         """Download vertex `v` and name its axes like the input state (site legs un-fused; `keep`: slot -> kept dim)."""
@@ -208,6 +221,7 @@ def _diag_message(old, s: np.ndarray, ket_name, dtype) -> ITensor:
 def _apply_batch(alg: BPApplyGate, ops: Sequence[Operator], touched: Sequence[Sequence], state: ITensorNetwork,
                  env: MessageCache):
     """A run of vertex-disjoint gates of one kind (all one-site or all two-site) in one device call."""
+    state = _promoted(state, ops, env)
     tensors = dict(state.tensors)
     new_env = env.copy()
     two = len(touched[0]) == 2
@@ -324,6 +338,7 @@ def expect_two_site(operators: Sequence[Operator], state: ITensorNetwork, env, d
     operators = list(operators)
     if not operators:
         return []
+    state = _promoted(state, operators, env)
     s = _ApplySession(state, env, device)
     try:
         edges, lowered = [], []

@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib
 from . import algorithmsinterface as AI
 from .algorithmsinterface import StopAfterIteration, StopWhenAny, StopWhenConverged, StoppingCriterion
-from .device import BPXContext
+from .device import BPXContext, cast_to
 from .graphs import NamedEdge, forest_cover_edge_sequence, to_edge
 from .tensornetwork import CanonicalProblem, Index, ITensor, ITensorNetwork, NormNetwork, canonical_arrays
 
@@ -645,7 +645,7 @@ def expect(factors: NormNetwork, messages: MessageCache, op: np.ndarray, vertice
     Build-defined extension (the reference has no `expect`); BASELINE.json's parity target
     names converged local expectation values."""
     s = _session_for(factors, messages)
-    ops = [np.asarray(op, dtype=s.cp.dtype)] * s.cp.ga.nv
+    ops = [cast_to(op, s.cp.dtype, "operator")] * s.cp.ga.nv
     num = s.ctx.vertex_expect_numerators(ops)
     den = s.ctx.vertex_scalars()
     vals = num / den

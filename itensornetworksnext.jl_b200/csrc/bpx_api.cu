@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost one pointer test unless a profiler is attached
+
 #include "bpx_common.cuh"
 #include "bpx_generic.cuh"
 #include "bpx_ctx.h"
@@ -973,7 +975,13 @@ static int residual_read(bpx_ctx* ctx, int idx, double* out) {
 }
 
 // one synchronous sweep: every owned directed edge, bucket by bucket, from d_msg[cur] into d_msg[cur^1]
+struct NvtxScope {  // RAII range: every return path of the function closes it
+  explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+  ~NvtxScope() { nvtxRangePop(); }
+};
+
 static int sweep_once(bpx_ctx* ctx, int normalize) {
+  NvtxScope nvtx_sweep("bpx:sweep");
   const void* in = ctx->d_msg[ctx->cur];
   void* out = ctx->d_msg[ctx->cur ^ 1];
   int rc;
@@ -1035,12 +1043,21 @@ static int sweep_once(bpx_ctx* ctx, int normalize) {
       b.timing.emplace_back(ev0, ev1);
       BPX_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
     }
+    {
+      // NVTX range per bucket launch: "bpx:bucket z=<degree> chi=<dim> d=<phys> kernel=<family>"
+      static const char* const fam[] = {"auto", "generic", "onchip", "sliced", "vertex"};
+      char label[96];
+      snprintf(label, sizeof(label), "bpx:bucket z=%d chi=%d d=%d kernel=%s edges=%lld", b.z, b.chi, b.d, fam[b.kernel & 7 ? (b.kernel <= 4 ? b.kernel : 0) : 0],
+               (long long)b.my_edges.size());
+      nvtxRangePushA(label);
+    }
     if (b.kernel == BPX_KERNEL_GENERIC)  // ONE launch for all generic buckets (the kernel takes any mix of edges)
       rc = launch_generic_update(ctx, in, out, ctx->d_generic_edges, ctx->n_generic_edges, normalize, ctx->cur_slot);
     else if (b.kernel == BPX_KERNEL_VERTEX)
       rc = launch_vertex_update(ctx, b, in, out, normalize);
     else
       rc = launch_fast_update(ctx, b, in, out, normalize);
+    nvtxRangePop();
     if (rc) return rc;
     if (ev1) BPX_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
   }
@@ -1346,6 +1363,7 @@ extern "C" int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* 
 // (bp_vertex_belief).  Every bucket family, single-layer networks included, serves beliefs at sweep speed this way; only
 // isolated vertices (no out-edge) are left to the generic scalar kernel.
 static int belief_sweep(bpx_ctx* ctx, char* d_out /* nv elements, zero-initialised */) {
+  NvtxScope nvtx_beliefs("bpx:beliefs");
   int rc;
   if ((rc = fast_refresh_sites(ctx))) return rc;
   const void* in = ctx->d_msg[ctx->cur];

@@ -39,11 +39,12 @@ namespace sliced2 {
 
 using namespace sliced;
 
-constexpr int NTHREADS2 = NCT + 128;  // 8 compute warps + producer + communication + reducer + epilogue
-constexpr int WARP_PRODUCER = NCW, WARP_COMM = NCW + 1, WARP_REDUCER = NCW + 2, WARP_EPILOGUE = NCW + 3;
+// CW compute warps + producer + communication + post-processing (reduce partial tiles, finish messages)
+template <int CW>
+constexpr int nthreads2() { return (CW + 3) * 32; }
 constexpr int PART_GEN = 3;  // generations of partial tiles in flight (vertex v uses v % 3): the epilogue of v may lag two vertices
 constexpr size_t PART_PER_GROUP = (size_t)PART_GEN * 8 * 4 * MSG;  // doubles: [v % 3][member][output leg][256], fragment order
-constexpr size_t PART1_PER_CTA = (size_t)2 * NCW * 2 * MSG;        // doubles: [dump parity][warp][tile][256], fragment order
+constexpr size_t PART1_PER_CTA = (size_t)2 * 2 * 8 * MSG;          // doubles: [dump parity][output][contributor][256], fragment order
 
 struct VItem {  // one (degree 4, chi 16) vertex
   int64_t site_off;   // elements, into the private image buffer
@@ -183,6 +184,44 @@ __device__ __forceinline__ void tma_bulk_s2g_hint(void* gdst, const void* ssrc, 
                : "memory");
 }
 
+// In-place pair absorption split by output rows (16-warp variant: lower register footprint, and two warps can share one
+// column): load the whole column once, then produce the rows x' = g + 8 mt of  buf[x', y'] = sum MX[x', x] MY[y', y] buf[x, y]
+template <int LAY, int X, int Y>
+__device__ __forceinline__ void load_col16(const double* buf, uint32_t base, int g, int t, double2 (&b)[4][2]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) b[j][h] = *reinterpret_cast<const double2*>(buf + (base ^ pos<LAY>(X, t + 4 * j) ^ pos<LAY>(Y, g + 8 * h)));
+}
+template <int LAY, int X, int Y>
+__device__ __forceinline__ void absorb_pair16_rows(double* buf, uint32_t base, const double2 (&b)[4][2], const double (&mxr)[4], const FragB& my,
+                                                   int mt, int g, int t) {
+  double d1[2][2][2];  // [h][s][i]: D1[x' = g + 8 mt, y = 2t + i + 8h]
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    d1[h][0][0] = d1[h][0][1] = d1[h][1][0] = d1[h][1][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dmma(d1[h][0][0], d1[h][0][1], mxr[j], b[j][h].x);
+      dmma(d1[h][1][0], d1[h][1][1], mxr[j], b[j][h].y);
+    }
+  }
+  const uint32_t a = base ^ pos<LAY>(X, g + 8 * mt);
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    double p0 = 0, p1 = 0, q0 = 0, q1 = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        dmma(p0, p1, d1[h][0][i], my.v[nt][h][i]);
+        dmma(q0, q1, d1[h][1][i], my.v[nt][h][i]);
+      }
+    *reinterpret_cast<double2*>(buf + (a ^ pos<LAY>(Y, 2 * t + 8 * nt))) = make_double2(p0, q0);
+    *reinterpret_cast<double2*>(buf + (a ^ pos<LAY>(Y, 2 * t + 1 + 8 * nt))) = make_double2(p1, q1);
+  }
+}
+
 enum { K_S1 = 0, K_S2 = 1, K_S3 = 2 };
 struct Step {
   int kind, v, q;
@@ -214,7 +253,9 @@ __global__ void swizzle_sites16v(const VItem* items, int n_items, const double* 
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, const __grid_constant__ TensorMaps tm) {
+template <int CW>  // compute warps: 8 (a column per warp: both products of a step) or 16 (two warps per column: one product each)
+__global__ void __launch_bounds__(nthreads2<CW>(), 1) bp_update_sliced_c16g(Args k, const __grid_constant__ TensorMaps tm) {
+  constexpr int WARP_PRODUCER = CW, WARP_COMM = CW + 1, WARP_POST = CW + 2;
   extern __shared__ __align__(128) double smem[];
   double* ring = smem;
   double* msgs = smem + 3 * SLICE;   // [2][4][256]
@@ -240,7 +281,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) {
       mbar_init(&mbar[M2_FULL + i], 1);
-      mbar_init(&mbar[M2_DONE + i], NCW);
+      mbar_init(&mbar[M2_DONE + i], CW);
     }
     mbar_init(&mbar[M2_MSG + 0], 1);
     mbar_init(&mbar[M2_MSG + 1], 1);
@@ -414,7 +455,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
     if (lane == 0) {
       unsigned sent_b1 = 0, sent_b2 = 0;
       const unsigned un = (unsigned)n;
-      const long long t0 = clock64();
+      long long t0 = clock64();
       while (sent_b1 < un || sent_b2 < un) {
         bool progress = false;
         // B1(v): before anybody may overwrite the partial tiles of vertex v - 3 (S2(v) dumps into the same generation), my
@@ -431,100 +472,120 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
         }
         if (!progress) {
           __nanosleep(100);
-          if (clock64() - t0 > 40000000000ll) __trap();
+          if (clock64() - t0 > 40000000000ll) __trap();  // ~20 s without any event: a member of the group is gone
+        } else {
+          t0 = clock64();
         }
       }
     }
-  } else if (warp == WARP_REDUCER) {
-    // ================================ reducer warp ================================
-    // dump d (even: S2(d / 2) -> out3, out2; odd: S3(d / 2) -> out1, out0): sum the eight warps' partial tiles (written to
-    // this CTA's L2-resident slots a moment ago) in warp order -> this member's tile of the group's partial buffer; arrive
-    for (int dmp = 0; dmp < 2 * n; ++dmp) {
-      if (lane == 0) {
-        const long long t0 = clock64();
-        while (ev[EV_DUMP] < (unsigned)NCW * (unsigned)(dmp + 1)) {
-          __nanosleep(100);
-          if (clock64() - t0 > 40000000000ll) __trap();
-        }
-      }
-      __syncwarp();
-      __threadfence_block();
-      const int i = dmp >> 1;
-      const int legs[2] = {(dmp & 1) ? 1 : 3, (dmp & 1) ? 0 : 2};
-      const double2* src = reinterpret_cast<const double2*>(part1 + (size_t)(dmp & 1) * NCW * 2 * MSG) + lane;
-      double* dstg = part0 + ((size_t)(i % PART_GEN) * 8 + j) * 4 * MSG;
-#pragma unroll
-      for (int tile = 0; tile < 2; ++tile) {
-        double2 v[NCW][4];
-#pragma unroll
-        for (int w = 0; w < NCW; ++w)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) v[w][q] = __ldcg(src + ((size_t)w * 2 + tile) * (MSG / 2) + q * 32);
-        double2* out = reinterpret_cast<double2*>(dstg + (size_t)legs[tile] * MSG) + lane;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          double2 a = v[0][q];
-#pragma unroll
-          for (int w = 1; w < NCW; ++w) {
-            a.x += v[w][q].x;
-            a.y += v[w][q].y;
-          }
-          __stcg(out + q * 32, a);
-        }
-      }
-      __threadfence();  // every lane's stores, before lane 0's arrival
-      __syncwarp();
-      if (lane == 0) {
-        red_release_gpu(gs + ((dmp & 1) ? GS_B3B : GS_B3A));
-        ev[EV_RED] = (unsigned)(dmp + 1);
-      }
-    }
-  } else if (warp == WARP_EPILOGUE) {
-    // ================================ epilogue warp ================================
+  } else if (warp == WARP_POST) {
+    // ================================ post-processing warp ================================
+    // (a) dump d (even: S2(d / 2) -> out3, out2; odd: S3(d / 2) -> out1, out0): sum the eight contributors' partial tiles
+    //     (written to this CTA's L2-resident dump slots a moment ago) in a fixed order -> this member's tile of the
+    //     group's partial buffer, arrive on the group counter;
+    // (b) vertex i complete in the whole group: sum the members' tiles of the out-edges this member owns and finish the
+    //     messages (sum-normalisation, residual, stores, cut-edge peer stores).
+    // A non-blocking service loop: a late group never holds up the reduction of this CTA's own dumps.
     const long long te0 = TCLK();
-    for (int i = 0; i < n; ++i) {
-      const VItem* d = k.items + base_item + i;
-      const long long tw = TCLK();
-      if (lane == 0) {
-        group_wait(gs + GS_B3A, (unsigned)Gm * (unsigned)(i + 1));
-        group_wait(gs + GS_B3B, (unsigned)Gm * (unsigned)(i + 1));
-      }
-      __syncwarp();
-      TACC(11, tw);
-      if (k.io.progress) hostio_wait(k.io, d->need);
-      const double* part = part0 + (size_t)(i % PART_GEN) * 8 * 4 * MSG;
+    int dmp = 0, epi = 0;
+    long long t0 = clock64();
+    while (dmp < 2 * n || epi < n) {
+      bool progress = false;
+      unsigned have = 0;
+      if (lane == 0) have = ev[EV_DUMP];
+      have = __shfl_sync(0xffffffffu, have, 0);
+      if (dmp < 2 * n && have >= (unsigned)CW * (unsigned)(dmp + 1)) {
+        __threadfence_block();
+        const int i = dmp >> 1;
+        const int legs[2] = {(dmp & 1) ? 1 : 3, (dmp & 1) ? 0 : 2};
+        const double2* src = reinterpret_cast<const double2*>(part1 + (size_t)(dmp & 1) * 2 * 8 * MSG) + lane;
+        double* dstg = part0 + ((size_t)(i % PART_GEN) * 8 + j) * 4 * MSG;
 #pragma unroll 1
-      for (int leg = 0; leg < 4; ++leg) {
-        if ((i + leg) % Gm != j) continue;  // this member finishes out-edge `leg` of vertex i
-        // sum the Gm members' partial tiles (fragment order: double2 (i2 = 0, 1) at [(mt * 2 + h) * 32 + lane]) in member order
-        double2 acc[4];
+        for (int tile = 0; tile < 2; ++tile) {
+          double2 acc[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] = make_double2(0.0, 0.0);
-        for (int m = 0; m < Gm; ++m) {
-          const double2* src = reinterpret_cast<const double2*>(part + ((size_t)m * 4 + leg) * MSG) + lane;
+          for (int half = 0; half < 2; ++half) {
+            double2 v[4][4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double2 v = __ldcg(src + q * 32);
-            acc[q].x += v.x;
-            acc[q].y += v.y;
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[w][q] = __ldcg(src + ((size_t)tile * 8 + half * 4 + w) * (MSG / 2) + q * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              double2 a = half == 0 ? v[0][q] : make_double2(acc[q].x + v[0][q].x, acc[q].y + v[0][q].y);
+#pragma unroll
+              for (int w = 1; w < 4; ++w) {
+                a.x += v[w][q].x;
+                a.y += v[w][q].y;
+              }
+              acc[q] = a;
+            }
           }
-        }
+          double2* out = reinterpret_cast<double2*>(dstg + (size_t)legs[tile] * MSG) + lane;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int mt = q >> 1, h = q & 1;
-          const int el = (g + 8 * mt) + CHI * (2 * t4 + 8 * h);  // out[v', v] at v' + 16 v
-          raw[el] = acc[q].x;
-          raw[el + CHI] = acc[q].y;
+          for (int q = 0; q < 4; ++q) __stcg(out + q * 32, acc[q]);
         }
+        __threadfence();  // every lane's stores, before lane 0's arrival
         __syncwarp();
-        const int64_t off = d->out_off[leg];
-        double* peer_m = (k.peer.nranks > 1 && d->peer[leg] >= 0) ? k.peer.peer_out[d->peer[leg]] + off : nullptr;
-        warp_epilogue<double>(raw, k.msg_in + off, k.msg_out + off, MSG, k.normalize,
-                              k.residual ? k.residual + d->out_edge[leg] : nullptr, lane, k.resmax, peer_m,
-                              k.io.host_out ? k.io.host_out + off : nullptr);
-        __syncwarp();
+        ++dmp;
+        if (lane == 0) {
+          red_release_gpu(gs + (((dmp - 1) & 1) ? GS_B3B : GS_B3A));
+          ev[EV_RED] = (unsigned)dmp;
+        }
+        progress = true;
       }
-      if (lane == 0) ev[EV_EPI] = (unsigned)(i + 1);
+      if (epi < n && dmp >= min(2 * n, 2 * epi + 2)) {
+        unsigned ok = 0;
+        if (lane == 0)
+          ok = (ld_acquire_gpu(gs + GS_B3A) >= (unsigned)Gm * (unsigned)(epi + 1) && ld_acquire_gpu(gs + GS_B3B) >= (unsigned)Gm * (unsigned)(epi + 1)) ? 1u : 0u;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) {
+          const int i = epi;
+          const VItem* d = k.items + base_item + i;
+          if (k.io.progress) hostio_wait(k.io, d->need);
+          const double* part = part0 + (size_t)(i % PART_GEN) * 8 * 4 * MSG;
+#pragma unroll 1
+          for (int leg = 0; leg < 4; ++leg) {
+            if ((i + leg) % Gm != j) continue;  // this member finishes out-edge `leg` of vertex i
+            // sum the Gm members' tiles (fragment order: double2 (i2 = 0, 1) at [(mt * 2 + h) * 32 + lane]) in member order
+            double2 acc[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = make_double2(0.0, 0.0);
+            for (int m = 0; m < Gm; ++m) {
+              const double2* src = reinterpret_cast<const double2*>(part + ((size_t)m * 4 + leg) * MSG) + lane;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const double2 v = __ldcg(src + q * 32);
+                acc[q].x += v.x;
+                acc[q].y += v.y;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int mt = q >> 1, h = q & 1;
+              const int el = (g + 8 * mt) + CHI * (2 * t4 + 8 * h);  // out[v', v] at v' + 16 v
+              raw[el] = acc[q].x;
+              raw[el + CHI] = acc[q].y;
+            }
+            __syncwarp();
+            const int64_t off = d->out_off[leg];
+            double* peer_m = (k.peer.nranks > 1 && d->peer[leg] >= 0) ? k.peer.peer_out[d->peer[leg]] + off : nullptr;
+            warp_epilogue<double>(raw, k.msg_in + off, k.msg_out + off, MSG, k.normalize,
+                                  k.residual ? k.residual + d->out_edge[leg] : nullptr, lane, k.resmax, peer_m,
+                                  k.io.host_out ? k.io.host_out + off : nullptr);
+            __syncwarp();
+          }
+          ++epi;
+          if (lane == 0) ev[EV_EPI] = (unsigned)epi;
+          progress = true;
+        }
+      }
+      if (!progress) {
+        __nanosleep(100);
+        if (clock64() - t0 > 40000000000ll) __trap();
+      } else {
+        t0 = clock64();
+      }
     }
     TACC(13, te0);
   } else {
@@ -532,30 +593,29 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
     int t = 0;  // running step index (slot = t % 3, mbarrier parity = (t / 3) & 1)
     const long long tc0 = TCLK();
     int n_dump = 0;  // dumps so far (S2(0), S3(0), S2(1), S3(1), ...)
-    auto dump = [&](const double (&accA)[2][2][2], const double (&accB)[2][2][2]) {
-      // this warp's two partial output tiles -> its slots of the CTA's two-deep dump buffer (L2), fragment order, coalesced
-      const long long tdump = TCLK();
-      if (n_dump >= 2) {  // the reducer has finished with the dump before last (in practice: long ago)
+    // one partial 16x16 output tile of this warp -> slot [output][contributor] of the CTA's two-deep dump buffer (L2),
+    // fragment order, coalesced
+    auto dump_tile = [&](int out, int contributor, const double (&acc)[2][2][2]) {
+      double2* pa = reinterpret_cast<double2*>(part1 + ((((size_t)(n_dump & 1) * 2 + out) * 8 + contributor)) * MSG) + lane;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) __stcg(pa + (mt * 2 + h) * 32, make_double2(acc[mt][h][0], acc[mt][h][1]));
+    };
+    auto dump_begin = [&]() {
+      if (n_dump >= 2) {  // the post-processing warp has finished with the dump before last (in practice: long ago)
         if (lane == 0)
           while (ev[EV_RED] + 2u <= (unsigned)n_dump) __nanosleep(64);
         __syncwarp();
       }
-      double2* pa = reinterpret_cast<double2*>(part1 + (((size_t)(n_dump & 1) * NCW + warp) * 2) * MSG) + lane;
-      double2* pb = pa + MSG / 2;
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          __stcg(pa + (mt * 2 + h) * 32, make_double2(accA[mt][h][0], accA[mt][h][1]));
-          __stcg(pb + (mt * 2 + h) * 32, make_double2(accB[mt][h][0], accB[mt][h][1]));
-        }
+    };
+    auto dump_end = [&]() {
       __syncwarp();
       if (lane == 0) {
         __threadfence_block();
         atomicAdd_block(const_cast<unsigned int*>(&ev[EV_DUMP]), 1u);
       }
       ++n_dump;
-      if (warp == 0) TACC(4, tdump);
     };
     for (int v = 0; v <= n; ++v) {
       if (v < n) {
@@ -572,8 +632,17 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
           mbar_wait(&mbar[M2_FULL + b], (uint32_t)(t / 3) & 1u);
           if (warp == 0) TACC(1, tf1);
           double* buf = ring + b * SLICE;
+          if constexpr (CW == 8) {
 #pragma unroll 1
-          for (int c = warp; c < 16; c += NCW) absorb_pair16<L_A3, 0, 1>(buf, pos<L_A3>(2, c) ^ pos<L_A3>(3, r), mx, my, g, t4);
+            for (int c = warp; c < 16; c += 8) absorb_pair16<L_A3, 0, 1>(buf, pos<L_A3>(2, c) ^ pos<L_A3>(3, r), mx, my, g, t4);
+          } else {  // one column per warp, rows in two passes
+            const uint32_t base = pos<L_A3>(2, warp) ^ pos<L_A3>(3, r);
+            double2 bc[4][2];
+            load_col16<L_A3, 0, 1>(buf, base, g, t4, bc);
+            __syncwarp();  // the column is overwritten below: every lane has read it first
+            absorb_pair16_rows<L_A3, 0, 1>(buf, base, bc, mx.v[0], my, 0, g, t4);
+            absorb_pair16_rows<L_A3, 0, 1>(buf, base, bc, mx.v[1], my, 1, g, t4);
+          }
           fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
           __syncwarp();
           if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
@@ -583,60 +652,138 @@ __global__ void __launch_bounds__(NTHREADS2, 1) bp_update_sliced_c16g(Args k, co
         // ---- S3(v-1): a3-half slices of Q and A; absorb 0 / close 1 -> out1, absorb 1 / close 0 -> out0 ----
         const int i = v - 1;
         const double* mm = msgs + (i & 1) * 4 * MSG;
-        const FragA mu = load_fragA(mm + 0 * MSG, g, t4);
-        const FragA mv = load_fragA(mm + 1 * MSG, g, t4);
-        double accA[2][2][2], accB[2][2][2];
+        if constexpr (CW == 8) {
+          const FragA mu = load_fragA(mm + 0 * MSG, g, t4);
+          const FragA mv = load_fragA(mm + 1 * MSG, g, t4);
+          double accA[2][2][2], accB[2][2][2];
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+          for (int a = 0; a < 2; ++a)
 #pragma unroll
-          for (int b2 = 0; b2 < 2; ++b2) accA[a][b2][0] = accA[a][b2][1] = accB[a][b2][0] = accB[a][b2][1] = 0.0;
-        for (int q = 0; q < nS2; ++q, ++t) {
-          const int b = t % 3, r = j + (q >> 1) * Gm, hh = q & 1;
-          const long long tf3 = TCLK();
-          mbar_wait(&mbar[M2_FULL + b], (uint32_t)(t / 3) & 1u);
-          if (warp == 0) TACC(3, tf3);
-          if (warp == 0 && q == 0) TACC(12, tf3);
-          const double* Pb = ring + b * SLICE;
-          const double* Ab = Pb + HALF;
-          const int c = warp + 8 * hh;  // column a2'
-          const uint32_t base = pos<L_A3H>(2, c) ^ pos<L_A3H>(3, r);
-          absorb_close16<L_A3H, 0, 1>(Pb, Ab, base, mu, g, t4, accA);
-          absorb_close16<L_A3H, 1, 0>(Pb, Ab, base, mv, g, t4, accB);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
+            for (int b2 = 0; b2 < 2; ++b2) accA[a][b2][0] = accA[a][b2][1] = accB[a][b2][0] = accB[a][b2][1] = 0.0;
+          for (int q = 0; q < nS2; ++q, ++t) {
+            const int b = t % 3, r = j + (q >> 1) * Gm, hh = q & 1;
+            const long long tf3 = TCLK();
+            mbar_wait(&mbar[M2_FULL + b], (uint32_t)(t / 3) & 1u);
+            if (warp == 0) TACC(3, tf3);
+            if (warp == 0 && q == 0) TACC(12, tf3);
+            const double* Pb = ring + b * SLICE;
+            const double* Ab = Pb + HALF;
+            const int c = warp + 8 * hh;  // column a2'
+            const uint32_t base = pos<L_A3H>(2, c) ^ pos<L_A3H>(3, r);
+            absorb_close16<L_A3H, 0, 1>(Pb, Ab, base, mu, g, t4, accA);
+            absorb_close16<L_A3H, 1, 0>(Pb, Ab, base, mv, g, t4, accB);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
+          }
+          const long long tdump = TCLK();
+          dump_begin();
+          dump_tile(0, warp, accA);  // -> out1
+          dump_tile(1, warp, accB);  // -> out0
+          dump_end();
+          if (warp == 0) TACC(4, tdump);
+        } else {
+          const int c8 = warp >> 1, role = warp & 1;  // role 0: absorb 0 / close 1 -> out1; role 1: absorb 1 / close 0 -> out0
+          const FragA mu = load_fragA(mm + role * MSG, g, t4);
+          double acc[2][2][2];
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) acc[a][b2][0] = acc[a][b2][1] = 0.0;
+          for (int q = 0; q < nS2; ++q, ++t) {
+            const int b = t % 3, r = j + (q >> 1) * Gm, hh = q & 1;
+            const long long tf3 = TCLK();
+            mbar_wait(&mbar[M2_FULL + b], (uint32_t)(t / 3) & 1u);
+            if (warp == 0) TACC(3, tf3);
+            if (warp == 0 && q == 0) TACC(12, tf3);
+            const double* Pb = ring + b * SLICE;
+            const double* Ab = Pb + HALF;
+            const uint32_t base = pos<L_A3H>(2, c8 + 8 * hh) ^ pos<L_A3H>(3, r);
+            if (role == 0) absorb_close16<L_A3H, 0, 1>(Pb, Ab, base, mu, g, t4, acc);
+            else absorb_close16<L_A3H, 1, 0>(Pb, Ab, base, mu, g, t4, acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
+          }
+          const long long tdump = TCLK();
+          dump_begin();
+          dump_tile(role, c8, acc);
+          dump_end();
+          if (warp == 0) TACC(4, tdump);
         }
-        dump(accA, accB);  // tile 0 -> out1, tile 1 -> out0
       }
       if (v < n) {
         // ---- S2(v): a0-half slices of P and A; absorb 2 / close 3 -> out3, absorb 3 / close 2 -> out2;
         //      then the SAME tensor columns absorb (2, 3) in place: Q's first pass ----
         const double* mm = msgs + (v & 1) * 4 * MSG;
-        const FragA mu = load_fragA(mm + 2 * MSG, g, t4);
-        const FragA mv = load_fragA(mm + 3 * MSG, g, t4);
-        const FragB my3 = load_fragB(mm + 3 * MSG, g, t4);
-        double accA[2][2][2], accB[2][2][2];
+        if constexpr (CW == 8) {
+          const FragA mu = load_fragA(mm + 2 * MSG, g, t4);
+          const FragA mv = load_fragA(mm + 3 * MSG, g, t4);
+          const FragB my3 = load_fragB(mm + 3 * MSG, g, t4);
+          double accA[2][2][2], accB[2][2][2];
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+          for (int a = 0; a < 2; ++a)
 #pragma unroll
-          for (int b2 = 0; b2 < 2; ++b2) accA[a][b2][0] = accA[a][b2][1] = accB[a][b2][0] = accB[a][b2][1] = 0.0;
-        for (int q = 0; q < nS2; ++q, ++t) {
-          const int b = t % 3, r = j + (q >> 1) * Gm, hh = q & 1;
-          const long long tf2 = TCLK();
-          mbar_wait(&mbar[M2_FULL + b], (uint32_t)(t / 3) & 1u);
-          if (warp == 0) TACC(2, tf2);
-          double* Pb = ring + b * SLICE;
-          double* Ab = Pb + HALF;
-          const int c = warp + 8 * hh;  // column a1'
-          const uint32_t base = pos<L_A0H>(1, c) ^ pos<L_A0H>(0, r);
-          absorb_close16<L_A0H, 2, 3>(Pb, Ab, base, mu, g, t4, accA);
-          absorb_close16<L_A0H, 3, 2>(Pb, Ab, base, mv, g, t4, accB);
-          __syncwarp();  // every lane has read the column before it is overwritten (only this warp touches column c)
-          absorb_pair16<L_A0H, 2, 3>(Ab, base, mu, my3, g, t4);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
+            for (int b2 = 0; b2 < 2; ++b2) accA[a][b2][0] = accA[a][b2][1] = accB[a][b2][0] = accB[a][b2][1] = 0.0;
+          for (int q = 0; q < nS2; ++q, ++t) {
+            const int b = t % 3, r = j + (q >> 1) * Gm, hh = q & 1;
+            const long long tf2 = TCLK();
+            mbar_wait(&mbar[M2_FULL + b], (uint32_t)(t / 3) & 1u);
+            if (warp == 0) TACC(2, tf2);
+            double* Pb = ring + b * SLICE;
+            double* Ab = Pb + HALF;
+            const int c = warp + 8 * hh;  // column a1'
+            const uint32_t base = pos<L_A0H>(1, c) ^ pos<L_A0H>(0, r);
+            absorb_close16<L_A0H, 2, 3>(Pb, Ab, base, mu, g, t4, accA);
+            absorb_close16<L_A0H, 3, 2>(Pb, Ab, base, mv, g, t4, accB);
+            __syncwarp();  // every lane has read the column before it is overwritten (only this warp touches column c)
+            absorb_pair16<L_A0H, 2, 3>(Ab, base, mu, my3, g, t4);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
+          }
+          const long long tdump = TCLK();
+          dump_begin();
+          dump_tile(0, warp, accA);  // -> out3
+          dump_tile(1, warp, accB);  // -> out2
+          dump_end();
+          if (warp == 0) TACC(4, tdump);
+        } else {
+          const int c8 = warp >> 1, role = warp & 1;  // role 0: absorb 2 / close 3 -> out3; role 1: absorb 3 / close 2 -> out2
+          const FragA mu = load_fragA(mm + (2 + role) * MSG, g, t4);
+          double acc[2][2][2];
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) acc[a][b2][0] = acc[a][b2][1] = 0.0;
+          for (int q = 0; q < nS2; ++q, ++t) {
+            const int b = t % 3, r = j + (q >> 1) * Gm, hh = q & 1;
+            const long long tf2 = TCLK();
+            mbar_wait(&mbar[M2_FULL + b], (uint32_t)(t / 3) & 1u);
+            if (warp == 0) TACC(2, tf2);
+            double* Pb = ring + b * SLICE;
+            double* Ab = Pb + HALF;
+            const uint32_t base = pos<L_A0H>(1, c8 + 8 * hh) ^ pos<L_A0H>(0, r);
+            if (role == 0) absorb_close16<L_A0H, 2, 3>(Pb, Ab, base, mu, g, t4, acc);
+            else absorb_close16<L_A0H, 3, 2>(Pb, Ab, base, mu, g, t4, acc);
+            // Q's first pass on the same tensor column, rows split between the two warps of the column: both read the whole
+            // column first (after their products), meet at the pair's named barrier, then write their own rows
+            double2 bc[4][2];
+            load_col16<L_A0H, 2, 3>(Ab, base, g, t4, bc);
+            double mxr[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) mxr[jj] = mm[2 * MSG + (g + 8 * role) + CHI * (t4 + 4 * jj)];  // M2[g + 8 mt, t + 4 j], mt = role
+            const FragB my3 = load_fragB(mm + 3 * MSG, g, t4);
+            onchip::bar_sync(1 + c8, 64);
+            absorb_pair16_rows<L_A0H, 2, 3>(Ab, base, bc, mxr, my3, role, g, t4);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mbar[M2_DONE + b]);
+          }
+          const long long tdump = TCLK();
+          dump_begin();
+          dump_tile(role, c8, acc);
+          dump_end();
+          if (warp == 0) TACC(4, tdump);
         }
-        dump(accA, accB);  // tile 0 -> out3, tile 1 -> out2
       }
     }
     if (warp == 0) TACC(0, tc0);

@@ -18,6 +18,17 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def cast_to(a, dtype, what: str = "array") -> np.ndarray:
+    """`np.asarray(a, dtype)` that refuses to throw an imaginary part away: a complex operator / message / tensor handed to
+    a Float64 context is an error (the reference promotes to ComplexF64, ITensorBase.apply), not a silent truncation."""
+    a = np.asarray(a)
+    dtype = np.dtype(dtype)
+    if a.dtype.kind == "c" and dtype.kind != "c" and a.size and np.any(a.imag != 0):
+        raise TypeError(f"complex {what} for a Float64 context would lose its imaginary part: promote the state / iterate "
+                        "to ComplexF64 first")
+    return a.real.astype(dtype) if (a.dtype.kind == "c" and dtype.kind != "c") else a.astype(dtype, copy=False)
+
+
 class BPXContext:
     """`BPXContext(0)`: one device.  `BPXContext(devices=[0, 1, ...])`: ONE context over several devices of this process
     (bpx_create_multi): same methods, the library partitions the vertices and exchanges cut-edge messages over NVLink."""
@@ -111,20 +122,20 @@ class BPXContext:
             n = int(self.site_off[v + 1] - self.site_off[v])
             if t.size != n:
                 raise ValueError(f"site tensor {v} has {t.size} elements, expected {n}")
-            out[self.site_off[v]:self.site_off[v + 1]] = np.asarray(t, dtype=self.dtype).ravel(order="F")
+            out[self.site_off[v]:self.site_off[v + 1]] = cast_to(t, self.dtype, "site tensor").ravel(order="F")
         return out
 
     def pack_messages(self, msgs: Sequence[np.ndarray]) -> np.ndarray:
         if isinstance(msgs, np.ndarray) and msgs.ndim == 1:  # already packed
             if msgs.size != int(self.msg_off[-1]):
                 raise ValueError(f"packed messages have {msgs.size} elements, expected {int(self.msg_off[-1])}")
-            return np.ascontiguousarray(msgs, dtype=self.dtype)
+            return np.ascontiguousarray(cast_to(msgs, self.dtype, "message set"))
         out = np.empty(int(self.msg_off[-1]), dtype=self.dtype)
         for e, m in enumerate(msgs):
             n = int(self.msg_off[e + 1] - self.msg_off[e])
             if m.size != n:
                 raise ValueError(f"message {e} has {m.size} elements, expected {n}")
-            out[self.msg_off[e]:self.msg_off[e + 1]] = np.asarray(m, dtype=self.dtype).ravel(order="F")
+            out[self.msg_off[e]:self.msg_off[e + 1]] = cast_to(m, self.dtype, "message").ravel(order="F")
         return out
 
     def unpack_messages(self, flat: np.ndarray) -> List[np.ndarray]:
@@ -172,7 +183,7 @@ class BPXContext:
         """A batch of vertex-disjoint two-site gates, in place on the device.  ops[g][o1, o2, i1, i2] with 1 = src and
         2 = dst of directed edge edges[g].  Returns the kept singular values per gate (zero-padded to the link dim)."""
         e = np.ascontiguousarray(edges, dtype=np.int64)
-        flat = (np.concatenate([np.asarray(o, dtype=self.dtype).ravel(order="F") for o in ops]) if len(ops)
+        flat = (np.concatenate([cast_to(o, self.dtype, "operator").ravel(order="F") for o in ops]) if len(ops)
                 else np.empty(0, self.dtype))
         dims = [int(self.link_dim[i]) if 0 <= i < self.ne else 0 for i in e]  # bad ids are reported by the library
         sv = np.zeros(max(1, sum(dims)), dtype=np.float64)
@@ -186,7 +197,7 @@ class BPXContext:
 
     def apply_one_site_gates(self, vertices: Sequence[int], ops: Sequence[np.ndarray], normalize: bool = False):
         v = np.ascontiguousarray(vertices, dtype=np.int64)
-        flat = (np.concatenate([np.asarray(o, dtype=self.dtype).ravel(order="F") for o in ops]) if len(ops)
+        flat = (np.concatenate([cast_to(o, self.dtype, "operator").ravel(order="F") for o in ops]) if len(ops)
                 else np.empty(0, self.dtype))
         self._check(self.lib.bpx_apply_one_site_gates(self.h, len(v), _ptr(v), _ptr(np.ascontiguousarray(flat)),
                                                       int(bool(normalize))))
@@ -195,7 +206,7 @@ class BPXContext:
         """Two-site expectation values in the BP environment: (numerators, denominators) per listed directed edge;
         ops[g][o1, o2, i1, i2] with 1 = src and 2 = dst of edges[g].  Read-only (edges may share vertices)."""
         e = np.ascontiguousarray(edges, dtype=np.int64)
-        flat = (np.concatenate([np.asarray(o, dtype=self.dtype).ravel(order="F") for o in ops]) if len(ops)
+        flat = (np.concatenate([cast_to(o, self.dtype, "operator").ravel(order="F") for o in ops]) if len(ops)
                 else np.empty(0, self.dtype))
         num, den = np.zeros(max(1, len(e)), dtype=self.dtype), np.zeros(max(1, len(e)), dtype=self.dtype)
         self._check(self.lib.bpx_edge_expect(self.h, len(e), _ptr(e), _ptr(np.ascontiguousarray(flat)), _ptr(num), _ptr(den)))
@@ -273,7 +284,7 @@ class BPXContext:
         return out
 
     def vertex_expect_numerators(self, ops: Sequence[np.ndarray]) -> np.ndarray:
-        flat = np.concatenate([np.asarray(o, dtype=self.dtype).ravel(order="F") for o in ops]) if len(ops) else np.empty(0, self.dtype)
+        flat = np.concatenate([cast_to(o, self.dtype, "operator").ravel(order="F") for o in ops]) if len(ops) else np.empty(0, self.dtype)
         out = np.empty(self.nv, dtype=self.dtype)
         self._check(self.lib.bpx_vertex_expect_numerators(self.h, _ptr(np.ascontiguousarray(flat)), _ptr(out)))
         return out

@@ -16,6 +16,8 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
+from .device import cast_to
+
 from .apply import (Operator, _ApplySession, _lowered_operator, _reference_rank, _touched_vertices)
 from .beliefpropagation import (ArgumentError, BeliefPropagationResult, MessageCache, _flatten_criterion, _NotFlat,
                                 select_beliefpropagation_stopping_criterion)
@@ -123,7 +125,7 @@ class ResidentState:
 
     def expect(self, op: np.ndarray, vertices=None):
         cp = self._s.cp
-        ops = [np.asarray(op, dtype=cp.dtype)] * cp.ga.nv
+        ops = [cast_to(op, cp.dtype, "operator")] * cp.ga.nv
         vals = self._s.ctx.vertex_expect_numerators(ops) / self._s.ctx.vertex_scalars()
         if vertices is None:
             return list(vals)

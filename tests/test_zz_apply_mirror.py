@@ -222,3 +222,38 @@ def test_mirror_matches_oracle_on_a_grid_gpu(dtype):
 @pytest.mark.gpu
 def test_mirror_errors_gpu():
     check_errors()
+
+
+# ---- dtype promotion: a complex gate on a real state must not lose its imaginary part -------------
+def test_complex_gate_on_a_float64_state_promotes_host_harness(host_ctx):
+    rng = np.random.default_rng(11)
+    g = graphs.named_path_graph(3)
+    net, _, sites = B.random_state(np.float64, g, d=2, chi=2, rng=rng)
+    cache = B.MessageCache(B.message_environment(B.ones_message, B.normnetwork(net)))
+    names = (sites[1].name, sites[2].name)
+    h = rng.standard_normal((4, 4))
+    h = h + h.T
+    w, v = np.linalg.eigh(h)
+    u = (v * np.exp(-0.3j * w)) @ v.conj().T                     # exp(-i dt H): a genuinely complex two-site gate
+    op = B.Operator(u.reshape(2, 2, 2, 2), names, names)
+    got_net, got_env = B.apply_operator(op, net, cache)
+    assert all(np.iscomplexobj(got_net[x].data) for x in (1, 2))
+    # same gate on the explicitly promoted state
+    cnet = B.ITensorNetwork({x: B.ITensor(net[x].data.astype(np.complex128), net[x].inds) for x in net.vertices()})
+    want_net, want_env = B.apply_operator(op, cnet, cache)
+    for x in net.vertices():
+        assert np.allclose(got_net[x].data, want_net[x].data, rtol=0, atol=1e-13)
+    assert np.abs(np.asarray(got_net[1].data).imag).max() > 1e-3    # the imaginary part is really there
+    # one-site gate, same story
+    op1 = B.Operator(np.array([[1.0, 0.0], [0.0, 1.0j]]), (sites[1].name,), (sites[1].name,))
+    n1, _ = B.apply_operator(op1, net, cache)
+    assert np.iscomplexobj(n1[1].data) and np.abs(n1[1].data.imag).max() > 0
+
+
+def test_context_refuses_to_drop_an_imaginary_part():
+    from itnn_b200.device import cast_to
+
+    assert cast_to(np.array([1.0 + 0.0j, 2.0]), np.float64, "operator").dtype == np.float64   # harmless: imaginary part is zero
+    with pytest.raises(TypeError, match="imaginary part"):
+        cast_to(np.array([1.0 + 1.0j]), np.float64, "operator")
+    assert cast_to(np.array([1.0, 2.0]), np.complex128, "message").dtype == np.complex128
