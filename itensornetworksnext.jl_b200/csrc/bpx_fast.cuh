@@ -812,14 +812,15 @@ inline int launch_fast_update(bpx_ctx* ctx, Bucket& b, const void* msg_in, void*
     if (ctx->n_sliced2_items == 0) return BPX_OK;
     // the group counters start every launch at zero (a memset node when the step is captured into a CUDA graph)
     BPX_CUDA(ctx, cudaMemsetAsync(ctx->d_sliced2_gsync, 0, (size_t)ctx->n_sliced2_groups * sliced2::GS_STRIDE * sizeof(unsigned int), ctx->stream));
-    // 16 compute warps (4 per scheduler): a warp may issue one DMMA every ~32 clk, the pipe takes one per 16 clk per
-    // scheduler, so two warps per scheduler cannot keep it busy through any hiccup (BPX_SLICED_CW=8: the older split)
-    static const bool cw8 = getenv("BPX_SLICED_CW") && atoi(getenv("BPX_SLICED_CW")) == 8;
-    if (cw8)
-      sliced2::bp_update_sliced_c16g<8><<<ctx->sliced2_grid, sliced2::nthreads2<8>(), sliced2::SMEM2_BYTES, ctx->stream>>>(
+    // 8 compute warps (a column per warp and step, both products) is the default; BPX_SLICED_CW=16 selects the variant with
+    // two warps per column (one product each, 96 registers): measured 9 % SLOWER at cfg5 -- the FP64 pipe, not the number of
+    // warps that feed it, limits the compute phases
+    const char* cw_env = getenv("BPX_SLICED_CW");
+    if (cw_env && atoi(cw_env) == 16)
+      sliced2::bp_update_sliced_c16g<16><<<ctx->sliced2_grid, sliced2::nthreads2<16>(), sliced2::SMEM2_BYTES, ctx->stream>>>(
           k, *reinterpret_cast<const sliced2::TensorMaps*>(ctx->sliced2_tmaps));
     else
-      sliced2::bp_update_sliced_c16g<16><<<ctx->sliced2_grid, sliced2::nthreads2<16>(), sliced2::SMEM2_BYTES, ctx->stream>>>(
+      sliced2::bp_update_sliced_c16g<8><<<ctx->sliced2_grid, sliced2::nthreads2<8>(), sliced2::SMEM2_BYTES, ctx->stream>>>(
           k, *reinterpret_cast<const sliced2::TensorMaps*>(ctx->sliced2_tmaps));
     ctx->n_launches++;
     BPX_CUDA(ctx, cudaGetLastError());

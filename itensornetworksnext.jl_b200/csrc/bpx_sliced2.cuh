@@ -55,7 +55,12 @@ struct VItem {  // one (degree 4, chi 16) vertex
   int64_t need;       // streamed host I/O: prefix of the upload that holds every message this vertex reads
 };
 
-enum { GS_B1 = 0, GS_B2 = 1, GS_B3A = 2, GS_B3B = 3, GS_STRIDE = 4 };  // per-group counters
+// per-group counters.  B1 / B2: monotone over the vertices (a member can only arrive for vertex v + 1 after it has passed
+// the barrier of vertex v, so "count >= G (v + 1)" is exact).  B3: one counter per GENERATION of partial tiles (vertex
+// v uses v % PART_GEN), both dumps of a vertex counted: a member's post-processing warp may lag its compute warps, so a
+// single monotone counter could reach its target with one member counted twice and another missing; per generation the
+// arrivals for vertex v + PART_GEN cannot start before every member has finished the epilogue of vertex v.
+enum { GS_B1 = 0, GS_B2 = 1, GS_B3 = 2 /* .. 4 */, GS_STRIDE = 8 };
 
 struct Args {
   const VItem* items;        // grouped: group g owns items[group_ptr[g] .. group_ptr[g + 1])
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(nthreads2<CW>(), 1) bp_update_sliced_c16g(Args
         __syncwarp();
         ++dmp;
         if (lane == 0) {
-          red_release_gpu(gs + (((dmp - 1) & 1) ? GS_B3B : GS_B3A));
+          red_release_gpu(gs + GS_B3 + ((dmp - 1) >> 1) % PART_GEN);
           ev[EV_RED] = (unsigned)dmp;
         }
         progress = true;
@@ -537,7 +542,7 @@ __global__ void __launch_bounds__(nthreads2<CW>(), 1) bp_update_sliced_c16g(Args
       if (epi < n && dmp >= min(2 * n, 2 * epi + 2)) {
         unsigned ok = 0;
         if (lane == 0)
-          ok = (ld_acquire_gpu(gs + GS_B3A) >= (unsigned)Gm * (unsigned)(epi + 1) && ld_acquire_gpu(gs + GS_B3B) >= (unsigned)Gm * (unsigned)(epi + 1)) ? 1u : 0u;
+          ok = ld_acquire_gpu(gs + GS_B3 + epi % PART_GEN) >= 2u * (unsigned)Gm * (unsigned)(epi / PART_GEN + 1) ? 1u : 0u;
         ok = __shfl_sync(0xffffffffu, ok, 0);
         if (ok) {
           const int i = epi;

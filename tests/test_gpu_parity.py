@@ -568,3 +568,35 @@ def test_site_tensor_update_refreshes_private_images(oracle):
         got = ctx.get_messages()
     want = oracle.sweep_jacobi(oracle.make_problem(p.ga, t, "norm"), p.messages)
     assert rel_err(got, want) < MSG_RTOL
+
+
+@pytest.mark.parametrize("variant", [{}, {"BPX_SLICED_CW": "16"}, {"BPX_SLICED_G": "4"}], ids=["g8-cw8", "g8-cw16", "g4-cw8"])
+def test_group_cooperative_sliced_kernel_equals_the_independent_kernel_at_scale(monkeypatch, variant):
+    """The group-cooperative chi = 16 kernel (bpx_sliced2.cuh) hands partial tiles between warps, CTAs and vertices through
+    counters; a protocol hole shows up as a handful of wrong messages only when every group processes MANY vertices (a
+    first version passed every small-lattice test and failed here).  48 x 48: 111 vertices per group; six sweeps must equal
+    version 1 (one CTA per half vertex, no cross-CTA protocol) to rounding, and the run must converge like it."""
+    g = graphs.named_grid((48, 48))
+    q = problems.make_config("cfg5", graph=g, host_data=False)
+
+    def run(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = []
+        with B.BPXContext(0) as ctx:
+            problems.upload(ctx, q)
+            assert {b["degree"]: b["kernel"] for b in ctx.buckets()}[4] == _lib.BPX_KERNEL_SLICED
+            for _ in range(6):
+                res, _ = ctx.sweep(1)
+                out.append((res, ctx.get_messages_flat()))
+            res, done = ctx.sweep(200, 1e-10)
+        for k in env:
+            monkeypatch.delenv(k)
+        return out, (res, done)
+
+    want, conv_want = run({"BPX_SLICED_V1": "1"})
+    got, conv_got = run(variant)
+    for (ra, ma), (rb, mb) in zip(want, got):
+        assert np.abs(ma - mb).max() < 1e-13
+        assert abs(ra - rb) < 1e-12
+    assert conv_got[1] == conv_want[1] and conv_got[0] < 1e-10
