@@ -805,6 +805,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             if par is not None and not par.get("ok", True):
                 sys.stderr.write(f"bench.py: PARITY FAILURE on {nm}: {json.dumps(par)}\n")
                 ok = False
+            # the synthetic BASELINE workloads converge in tens of sweeps: a run that hits maxiter has a handful of wrong
+            # messages somewhere that a 64-edge sample can miss (this caught a protocol race in round 2)
+            cv = res.get("convergence") if isinstance(res, dict) else None
+            if cv is not None and not cv.get("converged", True):
+                sys.stderr.write(f"bench.py: BP DID NOT CONVERGE on {nm} within maxiter: {json.dumps(cv)}\n")
+                ok = False
     if world > 1:
         D.dist.destroy_process_group()
     if not ok:
