@@ -168,6 +168,16 @@ int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* out);
 /* partitioned contexts fill in the vertices they own and report 0 for the others (combine across ranks on the host) */
 int bpx_vertex_scalars(bpx_ctx* ctx, void* out /* nv elements */);
 int bpx_edge_scalars(bpx_ctx* ctx, void* out /* ne/2 elements, edges with e < rev(e) in edge order */);
+/* `bethe_free_energy(factors, messages)` (messagecache.jl:185-201) without leaving the device: vertex scalars on the
+ * update kernels, edge scalars, then ONE reduction kernel forms sum(log.(numerators)) - sum(log.(denominators)); 7 doubles
+ * come back.  out = (re, im); *promoted (may be NULL) = 1 when the reference's result is Complex (complex element type, or a
+ * term with negative real part, :189-194 -- then im carries the phases, a multiple of pi for real networks), 0 when it is
+ * a real number (im = 0).  A zero edge scalar gives (-inf, 0) like :196-198. */
+int bpx_bethe_free_energy(bpx_ctx* ctx, double out[2], int* promoted);
+/* the same reduction, raw, for process-per-GPU contexts (each rank reports the vertices it owns and the undirected edges
+ * whose first orientation starts there; add [0..3] and OR [4..6] across ranks): parts = { sum log|num|, sum arg(num),
+ * sum log|den|, sum arg(den), any real(num) < 0, any real(den) < 0, any den == 0 } */
+int bpx_bethe_free_energy_parts(bpx_ctx* ctx, double parts[7]);
 /* numerator of <O_v>: vertex contraction with the d x d operator `op[s_out, s_in]` applied to the ket
  * site leg, for every vertex (ops packed per vertex, d_v*d_v elements each).  Build-defined extension:
  * the reference has no `expect`. */

@@ -625,19 +625,10 @@ def region_scalar(factors, messages: MessageCache, region):
 
 
 def bethe_free_energy(factors, messages: MessageCache):
-    """sum(log.(vertex scalars)) - sum(log.(edge scalars)) with the reference's complex promotion and
-    -Inf rules (messagecache.jl:185-201).  The scalars come from the device; the handful of logs are
-    host-side bookkeeping."""
+    """sum(log.(vertex scalars)) - sum(log.(edge scalars)) with the reference's complex promotion and -Inf rules
+    (messagecache.jl:185-201), reduced on the device (`bpx_bethe_free_energy`): only the result crosses the bus."""
     s = _session_for(factors, messages)
-    num = np.asarray(s.ctx.vertex_scalars())
-    den = np.asarray(s.ctx.edge_scalars())
-    if np.any(num.real < 0):
-        num = num.astype(np.complex128)
-    if np.any(den.real < 0):
-        den = den.astype(np.complex128)
-    if np.any(den == 0):
-        return -math.inf
-    return np.sum(np.log(num)) - np.sum(np.log(den))
+    return s.ctx.bethe_free_energy()
 
 
 def expect(factors: NormNetwork, messages: MessageCache, op: np.ndarray, vertices=None):

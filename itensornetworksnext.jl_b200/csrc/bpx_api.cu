@@ -77,6 +77,64 @@ static int upload(bpx_ctx* ctx, T** dptr, const std::vector<T>& h) {
   return BPX_OK;
 }
 
+// Context-cached work space: returns a buffer of at least `bytes` for role `slot`, growing it when needed.
+static const size_t WS_KEEP_BYTES = (size_t)1 << 30;
+template <typename T>
+static int ws_get(bpx_ctx* ctx, int slot, size_t bytes, T** out) {
+  if (bytes == 0) bytes = 8;
+  if (ctx->ws_bytes[slot] < bytes) {
+    if (ctx->ws[slot]) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(ctx->ws[slot]);
+      ctx->ws[slot] = nullptr;
+      ctx->ws_bytes[slot] = 0;
+    }
+    const size_t want = bytes <= WS_KEEP_BYTES ? std::max(bytes + bytes / 4, (size_t)4096) : bytes;
+    cudaError_t e = cudaMalloc(&ctx->ws[slot], want);
+    size_t got = want;
+    if (e != cudaSuccess && want > bytes) {
+      cudaGetLastError();
+      e = cudaMalloc(&ctx->ws[slot], bytes);
+      got = bytes;
+    }
+    if (e != cudaSuccess) {
+      ctx->ws[slot] = nullptr;
+      set_error(ctx, "cudaMalloc(%zu bytes of work space) failed: %s", bytes, cudaGetErrorString(e));
+      cudaGetLastError();
+      return BPX_ERR_ALLOC;
+    }
+    ctx->ws_bytes[slot] = got;
+  }
+  *out = (T*)ctx->ws[slot];
+  return BPX_OK;
+}
+// end of a call: give back the buffers that are too large to keep (the stream has been synchronised)
+static void ws_trim(bpx_ctx* ctx) {
+  for (int i = 0; i < bpx_ctx::WS_COUNT; ++i)
+    if (ctx->ws_bytes[i] > WS_KEEP_BYTES) {
+      cudaFree(ctx->ws[i]);
+      ctx->ws[i] = nullptr;
+      ctx->ws_bytes[i] = 0;
+    }
+}
+static void ws_release(bpx_ctx* ctx) {
+  for (int i = 0; i < bpx_ctx::WS_COUNT; ++i) {
+    if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+    ctx->ws[i] = nullptr;
+    ctx->ws_bytes[i] = 0;
+  }
+  if (ctx->h_logsum) cudaFreeHost(ctx->h_logsum);
+  ctx->h_logsum = nullptr;
+}
+template <typename T>
+static int ws_upload(bpx_ctx* ctx, int slot, const std::vector<T>& h, T** dptr) {
+  int rc = ws_get(ctx, slot, h.size() * sizeof(T), dptr);
+  if (rc) return rc;
+  // pageable source: the copy has returned from the host buffer's point of view when the call returns
+  if (!h.empty()) BPX_CUDA(ctx, cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return BPX_OK;
+}
+
 static void free_problem(bpx_ctx* c) {
   halo_release(c);
   c->rank = 0;
@@ -192,6 +250,7 @@ extern "C" int bpx_destroy(bpx_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   halo_release(ctx);
   free_problem(ctx);
+  ws_release(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   for (auto& g : ctx->io_graphs) cudaGraphExecDestroy(g.exec);
   if (ctx->copy_stream) {
@@ -1412,24 +1471,22 @@ static int belief_sweep(bpx_ctx* ctx, char* d_out /* nv elements, zero-initialis
   return BPX_OK;
 }
 
-static int vertex_scalars_impl(bpx_ctx* ctx, const void* ops_packed, void* out) {
+// Enqueues the vertex scalars (or expectation-value numerators) into the context's WS_SCALARS buffer; nothing leaves the device.
+static int vertex_scalars_enqueue(bpx_ctx* ctx, const void* ops_packed, char** d_out_p) {
   const int64_t nv = ctx->nv;
-  if (nv == 0) return BPX_OK;
-  REQUIRE(ctx, out, "vertex scalars: out is NULL");
   char* d_out = nullptr;
   char* d_ops = nullptr;
   int64_t* d_op_off = nullptr;
-  int rc = dev_alloc(ctx, &d_out, (size_t)nv * ctx->esize);
+  int rc = ws_get(ctx, bpx_ctx::WS_SCALARS, (size_t)nv * ctx->esize, &d_out);
   if (rc) return rc;
+  *d_out_p = d_out;
   if (ops_packed) {
     std::vector<int64_t> op_off(nv + 1, 0);
     for (int64_t v = 0; v < nv; ++v) op_off[v + 1] = op_off[v] + (int64_t)ctx->phys_dim[v] * ctx->phys_dim[v];
-    if ((rc = upload(ctx, &d_op_off, op_off)) || (rc = dev_alloc(ctx, &d_ops, (size_t)op_off[nv] * ctx->esize))) {
-      cudaFree(d_out);
-      cudaFree(d_op_off);
+    if ((rc = ws_upload(ctx, bpx_ctx::WS_OP_OFF, op_off, &d_op_off)) || (rc = ws_get(ctx, bpx_ctx::WS_OPS, (size_t)op_off[nv] * ctx->esize, &d_ops)))
       return rc;
-    }
-    cudaMemcpyAsync(d_ops, ops_packed, (size_t)op_off[nv] * ctx->esize, cudaMemcpyHostToDevice, ctx->stream);
+    BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // op_off is a local
+    BPX_CUDA(ctx, cudaMemcpyAsync(d_ops, ops_packed, (size_t)op_off[nv] * ctx->esize, cudaMemcpyHostToDevice, ctx->stream));
   }
   // partitioned contexts hold (and know the in-messages of) their own vertices only: the others are reported as 0
   BPX_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)nv * ctx->esize, ctx->stream));
@@ -1439,17 +1496,14 @@ static int vertex_scalars_impl(bpx_ctx* ctx, const void* ops_packed, void* out) 
   if (on_update_kernels) {
     // plain vertex scalars: at sweep speed on the buckets' own (tensor-pipe) kernels; the generic scalar kernel below then
     // only visits vertices without a link (their scalar is the plain norm of the tensor)
-    if ((rc = belief_sweep(ctx, d_out))) {
-      cudaFree(d_out);
-      return rc;
-    }
+    if ((rc = belief_sweep(ctx, d_out))) return rc;
     std::vector<int32_t> iso;
     for (int64_t v = 0; v < nv; ++v)
       if (ctx->out_edge[v].empty() && (ctx->owner.empty() || ctx->owner[v] == ctx->rank)) iso.push_back((int32_t)v);
     n_isolated = (int64_t)iso.size();
-    if (n_isolated > 0 && (rc = upload(ctx, &d_isolated, iso))) {
-      cudaFree(d_out);
-      return rc;
+    if (n_isolated > 0) {
+      if ((rc = ws_upload(ctx, bpx_ctx::WS_LIST, iso, &d_isolated))) return rc;
+      BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // iso is a local
     }
   }
   GenericArgs g = on_update_kernels
@@ -1470,15 +1524,24 @@ static int vertex_scalars_impl(bpx_ctx* ctx, const void* ops_packed, void* out) 
       if (!rc) bp_vertex_scalar_generic<c64><<<grid, 256, ctx->gen_smem_bytes, ctx->stream>>>(g);
     }
     ctx->n_launches++;
+    if (rc) return rc;
+    BPX_CUDA(ctx, cudaGetLastError());
   }
-  cudaError_t ce = cudaGetLastError();
-  if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_out, (size_t)nv * ctx->esize, cudaMemcpyDeviceToHost, ctx->stream);
-  cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_out);
-  cudaFree(d_ops);
-  cudaFree(d_op_off);
-  cudaFree(d_isolated);
-  if (rc) return rc;
+  return BPX_OK;
+}
+
+static int vertex_scalars_impl(bpx_ctx* ctx, const void* ops_packed, void* out) {
+  const int64_t nv = ctx->nv;
+  if (nv == 0) return BPX_OK;
+  REQUIRE(ctx, out, "vertex scalars: out is NULL");
+  char* d_out = nullptr;
+  int rc = vertex_scalars_enqueue(ctx, ops_packed, &d_out);
+  if (rc) {
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+  }
+  const cudaError_t ce = cudaMemcpyAsync(out, d_out, (size_t)nv * ctx->esize, cudaMemcpyDeviceToHost, ctx->stream);
+  const cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
   BPX_CUDA(ctx, ce);
   BPX_CUDA(ctx, ce2);
   return BPX_OK;
@@ -1500,16 +1563,14 @@ extern "C" int bpx_vertex_expect_numerators(bpx_ctx* ctx, const void* ops_packed
   return vertex_scalars_impl(ctx, ops_packed, out);
 }
 
-extern "C" int bpx_edge_scalars(bpx_ctx* ctx, void* out) {
-  MULTI(ctx, bpx::multi::edge_scalars(ctx, out));
-  NEED_DIMS(ctx, "bpx_edge_scalars");
-  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
+// edge scalars of all undirected edges into WS_EDGE_SCALARS (device only)
+static int edge_scalars_enqueue(bpx_ctx* ctx, char** d_out_p) {
   const int64_t n = ctx->n_und;
-  if (n == 0) return BPX_OK;
-  REQUIRE(ctx, out, "bpx_edge_scalars: out is NULL");
   char* d_out = nullptr;
-  int rc = dev_alloc(ctx, &d_out, (size_t)n * ctx->esize);
+  int rc = ws_get(ctx, bpx_ctx::WS_EDGE_SCALARS, (size_t)n * ctx->esize, &d_out);
   if (rc) return rc;
+  *d_out_p = d_out;
+  if (n == 0) return BPX_OK;
   const int threads = 256;
   const int64_t blocks = (n * 32 + threads - 1) / threads;
   if (ctx->dtype == BPX_F64)
@@ -1519,12 +1580,154 @@ extern "C" int bpx_edge_scalars(bpx_ctx* ctx, void* out) {
     bp_edge_scalar<c64><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const c64*)ctx->d_msg[ctx->cur], ctx->d_msg_off,
                                                                       ctx->d_und_edge, ctx->d_rev, n, (c64*)d_out);
   ctx->n_launches++;
-  cudaError_t ce = cudaGetLastError();
-  if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, d_out, (size_t)n * ctx->esize, cudaMemcpyDeviceToHost, ctx->stream);
-  cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_out);
+  BPX_CUDA(ctx, cudaGetLastError());
+  return BPX_OK;
+}
+
+extern "C" int bpx_edge_scalars(bpx_ctx* ctx, void* out) {
+  MULTI(ctx, bpx::multi::edge_scalars(ctx, out));
+  NEED_DIMS(ctx, "bpx_edge_scalars");
+  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
+  const int64_t n = ctx->n_und;
+  if (n == 0) return BPX_OK;
+  REQUIRE(ctx, out, "bpx_edge_scalars: out is NULL");
+  char* d_out = nullptr;
+  int rc = edge_scalars_enqueue(ctx, &d_out);
+  if (rc) {
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+  }
+  const cudaError_t ce = cudaMemcpyAsync(out, d_out, (size_t)n * ctx->esize, cudaMemcpyDeviceToHost, ctx->stream);
+  const cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
   BPX_CUDA(ctx, ce);
   BPX_CUDA(ctx, ce2);
+  return BPX_OK;
+}
+
+// ---- bethe_free_energy fully on the device (messagecache.jl:185-201) ---------------------------------------------------
+// One CTA reduces log|t| and arg(t) over the vertex terms this rank owns and over the undirected edges whose first
+// orientation starts at an owned vertex, in a fixed order (deterministic); 7 doubles come back:
+//   [0] sum log|num|  [1] sum arg(num)  [2] sum log|den|  [3] sum arg(den)  [4] any real(num) < 0  [5] any real(den) < 0
+//   [6] any den == 0
+template <typename T>
+__global__ void bp_bethe_logsum(const T* __restrict__ vs, const int32_t* __restrict__ vlist, int64_t n_v,
+                                const T* __restrict__ es, const int32_t* __restrict__ und_edge, const int32_t* __restrict__ src,
+                                const int32_t* __restrict__ owner, int rank, int64_t n_e, double* __restrict__ out) {
+  using E = Elem<T>;
+  __shared__ double red[7][32];
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = threadIdx.x; i < n_v; i += blockDim.x) {
+    const T t = vs[vlist ? vlist[i] : i];
+    const double re = E::real(t), im = E::imag(t);
+    acc[0] += log(hypot(re, im));
+    acc[1] += atan2(im, re);
+    if (re < 0) acc[4] = 1.0;
+  }
+  for (int64_t i = threadIdx.x; i < n_e; i += blockDim.x) {
+    if (owner && owner[src[und_edge[i]]] != rank) continue;
+    const T t = es[i];
+    const double re = E::real(t), im = E::imag(t);
+    acc[2] += log(hypot(re, im));
+    acc[3] += atan2(im, re);
+    if (re < 0) acc[5] = 1.0;
+    if (re == 0 && im == 0) acc[6] = 1.0;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = 0; k < 7; ++k) {
+    double x = acc[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_down_sync(0xffffffffu, x, o);
+      x = k < 4 ? x + y : fmax(x, y);
+    }
+    if (lane == 0) red[k][w] = x;
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int k = 0; k < 7; ++k) {
+      double x = lane < nw ? red[k][lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) {
+        const double y = __shfl_down_sync(0xffffffffu, x, o);
+        x = k < 4 ? x + y : fmax(x, y);
+      }
+      if (lane == 0) out[k] = x;
+    }
+  }
+}
+
+extern "C" int bpx_bethe_free_energy_parts(bpx_ctx* ctx, double parts[7]) {
+  REQUIRE(ctx, parts, "bpx_bethe_free_energy_parts: parts is NULL");
+  if (ctx && !ctx->children.empty()) {
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (bpx_ctx* c : ctx->children) {
+      cudaSetDevice(c->device);
+      double p[7];
+      const int rc = bpx_bethe_free_energy_parts(c, p);
+      if (rc) return bpx::multi::fail(ctx, c, rc);
+      for (int k = 0; k < 4; ++k) acc[k] += p[k];
+      for (int k = 4; k < 7; ++k) acc[k] = std::max(acc[k], p[k]);
+    }
+    memcpy(parts, acc, sizeof(acc));
+    return BPX_OK;
+  }
+  NEED_DIMS(ctx, "bpx_bethe_free_energy");
+  { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
+  NvtxScope nvtx("bpx:bethe_free_energy");
+  char *d_vs = nullptr, *d_es = nullptr;
+  double* d_out = nullptr;
+  int rc = vertex_scalars_enqueue(ctx, nullptr, &d_vs);
+  if (!rc) rc = edge_scalars_enqueue(ctx, &d_es);
+  if (!rc) rc = ws_get(ctx, bpx_ctx::WS_LOGSUM, 8 * sizeof(double), &d_out);
+  if (!rc && !ctx->h_logsum && cudaMallocHost(&ctx->h_logsum, 8 * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    set_error(ctx, "bpx_bethe_free_energy: cudaMallocHost failed");
+    rc = BPX_ERR_ALLOC;
+  }
+  if (rc) {
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+  }
+  const bool part = ctx->nranks > 1;
+  int32_t* d_owner = nullptr;
+  if (part) {
+    if ((rc = ws_upload(ctx, bpx_ctx::WS_OUT, ctx->owner, &d_owner))) return rc;
+  }
+  const int64_t n_v = part ? ctx->n_owned_vertices : ctx->nv;
+  const int32_t* vlist = part ? ctx->d_owned_vertices : nullptr;
+  if (ctx->dtype == BPX_F64)
+    bp_bethe_logsum<double><<<1, 1024, 0, ctx->stream>>>((const double*)d_vs, vlist, n_v, (const double*)d_es, ctx->d_und_edge, ctx->d_src,
+                                                         d_owner, ctx->rank, ctx->n_und, d_out);
+  else
+    bp_bethe_logsum<c64><<<1, 1024, 0, ctx->stream>>>((const c64*)d_vs, vlist, n_v, (const c64*)d_es, ctx->d_und_edge, ctx->d_src,
+                                                      d_owner, ctx->rank, ctx->n_und, d_out);
+  ctx->n_launches++;
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(ctx->h_logsum, d_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  const cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
+  BPX_CUDA(ctx, ce);
+  BPX_CUDA(ctx, ce2);
+  memcpy(parts, ctx->h_logsum, 7 * sizeof(double));
+  return BPX_OK;
+}
+
+extern "C" int bpx_bethe_free_energy(bpx_ctx* ctx, double out[2], int* promoted) {
+  REQUIRE(ctx, out, "bpx_bethe_free_energy: out is NULL");
+  double p[7];
+  const int rc = bpx_bethe_free_energy_parts(ctx, p);
+  if (rc) return rc;
+  const bpx_ctx* c = ctx->children.empty() ? ctx : ctx->children[0];
+  // messagecache.jl:189-194: real terms are promoted to complex only if one of them is negative; complex terms always
+  // carry their phase.  log(complex(x)) = log|x| + i arg(x)
+  const bool cplx = c->dtype != BPX_F64;
+  const bool pn = cplx || p[4] != 0.0, pd = cplx || p[5] != 0.0;
+  if (promoted) *promoted = (pn || pd) ? 1 : 0;
+  if (p[6] != 0.0) {  // :196-198
+    out[0] = -INFINITY;
+    out[1] = 0.0;
+    return BPX_OK;
+  }
+  out[0] = p[0] - p[2];
+  out[1] = (pn ? p[1] : 0.0) - (pd ? p[3] : 0.0);
   return BPX_OK;
 }
 
@@ -1653,9 +1856,10 @@ static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const v
   applyk::GateDesc* d_gates = nullptr;
   char* d_ws = nullptr;
   char* d_ops = nullptr;
-  int rc = upload(ctx, &d_gates, gates);
-  if (!rc) rc = dev_alloc(ctx, &d_ws, (size_t)max_total * ctx->esize);
-  if (!rc) rc = dev_alloc(ctx, &d_ops, ops_elems * ctx->esize);
+  // context-cached work space (grow-only; buffers above 1 GiB go back at the end of the call)
+  int rc = ws_upload(ctx, bpx_ctx::WS_DESC, gates, &d_gates);
+  if (!rc) rc = ws_get(ctx, bpx_ctx::WS_WORK, (size_t)max_total * ctx->esize, &d_ws);
+  if (!rc) rc = ws_get(ctx, bpx_ctx::WS_OPS, ops_elems * ctx->esize, &d_ops);
   cudaError_t ce = cudaSuccess;
   if (!rc) {
     ce = cudaMemcpyAsync(d_ops, ops_packed, ops_elems * ctx->esize, cudaMemcpyHostToDevice, ctx->stream);
@@ -1692,9 +1896,7 @@ static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const v
     }
   }
   const cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_gates);
-  cudaFree(d_ws);
-  cudaFree(d_ops);
+  ws_trim(ctx);
   if (rc) return rc;
   BPX_CUDA(ctx, ce);
   BPX_CUDA(ctx, ce2);
@@ -1760,20 +1962,15 @@ extern "C" int bpx_apply_two_site_gates(bpx_ctx* ctx, int64_t n_gates, const int
     sv_stride = std::max<int64_t>(sv_stride, gd.chi_b);
   }
   double* d_sv = nullptr;
-  if (singular_values_out && (rc = dev_alloc(ctx, &d_sv, (size_t)(n_gates * sv_stride)))) return rc;
+  if (singular_values_out && (rc = ws_get(ctx, bpx_ctx::WS_SV, (size_t)(n_gates * sv_stride) * sizeof(double), &d_sv))) return rc;
   rc = apply_run(ctx, gates, ops_packed, (size_t)op_off, normalize, d_sv, sv_stride);
   if (!rc && d_sv) {
     std::vector<double> h((size_t)(n_gates * sv_stride));
-    cudaError_t ce = cudaMemcpy(h.data(), d_sv, h.size() * sizeof(double), cudaMemcpyDeviceToHost);
-    if (ce != cudaSuccess) {
-      cudaFree(d_sv);
-      BPX_CUDA(ctx, ce);
-    }
+    BPX_CUDA(ctx, cudaMemcpy(h.data(), d_sv, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
     int64_t o = 0;  // packed: link_dim[edges[g]] values per gate, gate order
     for (int64_t g = 0; g < n_gates; ++g)
       for (int i = 0; i < gates[g].chi_b; ++i) singular_values_out[o++] = h[(size_t)(g * sv_stride + i)];
   }
-  cudaFree(d_sv);
   return rc;
 }
 
@@ -1853,10 +2050,10 @@ extern "C" int bpx_edge_expect(bpx_ctx* ctx, int64_t n_edges, const int64_t* edg
   chunk_begin.push_back(n_edges);
   expect2::EdgeDesc* d_desc = nullptr;
   char *d_ws = nullptr, *d_ops = nullptr, *d_out = nullptr;
-  rc = upload(ctx, &d_desc, desc);
-  if (!rc) rc = dev_alloc(ctx, &d_ws, (size_t)max_total * ctx->esize);
-  if (!rc) rc = dev_alloc(ctx, &d_ops, (size_t)op_off * ctx->esize);
-  if (!rc) rc = dev_alloc(ctx, &d_out, (size_t)(2 * n_edges) * ctx->esize);
+  rc = ws_upload(ctx, bpx_ctx::WS_DESC, desc, &d_desc);
+  if (!rc) rc = ws_get(ctx, bpx_ctx::WS_WORK, (size_t)max_total * ctx->esize, &d_ws);
+  if (!rc) rc = ws_get(ctx, bpx_ctx::WS_OPS, (size_t)op_off * ctx->esize, &d_ops);
+  if (!rc) rc = ws_get(ctx, bpx_ctx::WS_OUT, (size_t)(2 * n_edges) * ctx->esize, &d_out);
   cudaError_t ce = cudaSuccess;
   if (!rc) {
     ce = cudaMemcpyAsync(d_ops, ops_packed, (size_t)op_off * ctx->esize, cudaMemcpyHostToDevice, ctx->stream);
@@ -1883,10 +2080,7 @@ extern "C" int bpx_edge_expect(bpx_ctx* ctx, int64_t n_edges, const int64_t* edg
       ce = cudaMemcpyAsync(den_out, d_out + (size_t)n_edges * ctx->esize, (size_t)n_edges * ctx->esize, cudaMemcpyDeviceToHost, ctx->stream);
   }
   const cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_desc);
-  cudaFree(d_ws);
-  cudaFree(d_ops);
-  cudaFree(d_out);
+  ws_trim(ctx);
   if (rc) return rc;
   BPX_CUDA(ctx, ce);
   BPX_CUDA(ctx, ce2);

@@ -38,6 +38,8 @@ struct Elem<double> {
   __host__ __device__ static __forceinline__ bool is_zero(double a) { return a == 0.0; }
   __host__ __device__ static __forceinline__ double div(double a, double b) { return a / b; }
   __host__ __device__ static __forceinline__ double abs2(double a) { return a * a; }
+  __host__ __device__ static __forceinline__ double real(double a) { return a; }
+  __host__ __device__ static __forceinline__ double imag(double) { return 0.0; }
   __device__ static __forceinline__ double shfl_xor(double a, int m) { return __shfl_xor_sync(0xffffffffu, a, m); }
 };
 
@@ -69,6 +71,8 @@ struct Elem<c64> {
     }
   }
   __host__ __device__ static __forceinline__ double abs2(c64 a) { return a.re * a.re + a.im * a.im; }
+  __host__ __device__ static __forceinline__ double real(c64 a) { return a.re; }
+  __host__ __device__ static __forceinline__ double imag(c64 a) { return a.im; }
   __device__ static __forceinline__ c64 shfl_xor(c64 a, int m) {
     return make_c64(__shfl_xor_sync(0xffffffffu, a.re, m), __shfl_xor_sync(0xffffffffu, a.im, m));
   }

@@ -160,6 +160,13 @@ struct bpx_ctx {
   // counters
   int64_t n_launches = 0, n_updates = 0, n_sweeps = 0;
 
+  // grow-only work space of the belief / gate / expectation-value calls (one buffer per role; no cudaMalloc / cudaFree on
+  // the call path once warm).  Buffers above WS_KEEP_BYTES are released at the end of the call that needed them.
+  enum { WS_SCALARS = 0, WS_EDGE_SCALARS, WS_LOGSUM, WS_OPS, WS_OP_OFF, WS_LIST, WS_DESC, WS_WORK, WS_SV, WS_OUT, WS_COUNT };
+  void* ws[WS_COUNT] = {};
+  size_t ws_bytes[WS_COUNT] = {};
+  void* h_logsum = nullptr;  // pinned: result block of bpx_bethe_free_energy
+
   // single-process multi-GPU (bpx_create_multi, bpx_multi.cuh): the parent owns one partitioned child per device and holds
   // no device memory itself
   std::vector<bpx_ctx*> children;

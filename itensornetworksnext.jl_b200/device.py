@@ -283,6 +283,19 @@ class BPXContext:
         self._check(self.lib.bpx_edge_scalars(self.h, _ptr(out)))
         return out
 
+    def bethe_free_energy(self):
+        """messagecache.jl:185-201 reduced on the device (bpx_bethe_free_energy): a float, or a complex number when the
+        reference's promotion rule applies."""
+        out = (C.c_double * 2)()
+        promoted = C.c_int()
+        self._check(self.lib.bpx_bethe_free_energy(self.h, out, C.byref(promoted)))
+        return complex(out[0], out[1]) if promoted.value else float(out[0])
+
+    def bethe_free_energy_parts(self) -> np.ndarray:
+        out = (C.c_double * 7)()
+        self._check(self.lib.bpx_bethe_free_energy_parts(self.h, out))
+        return np.array(out[:])
+
     def vertex_expect_numerators(self, ops: Sequence[np.ndarray]) -> np.ndarray:
         flat = np.concatenate([cast_to(o, self.dtype, "operator").ravel(order="F") for o in ops]) if len(ops) else np.empty(0, self.dtype)
         out = np.empty(self.nv, dtype=self.dtype)

@@ -318,6 +318,19 @@ function edge_scalars(alg::B200MessageUpdate, ::Type{E} = Float64) where {E}
     return out
 end
 
+"""
+    bethe_free_energy(alg::B200MessageUpdate)
+`bethe_free_energy(factors, messages)` (messagecache.jl:185-201) of the resident iterate, reduced on the device: a
+`Float64`, or a `ComplexF64` when the reference's promotion rule applies (complex element type or a negative term).
+"""
+function bethe_free_energy(alg::B200MessageUpdate)
+    out = zeros(Float64, 2)
+    promoted = Ref{Cint}(0)
+    GC.@preserve out check(alg.ctx, ccall((:bpx_bethe_free_energy, libbpx), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cint}),
+        alg.ctx, out, promoted))
+    return promoted[] != 0 ? complex(out[1], out[2]) : out[1]
+end
+
 # ---- gate application on the device (src/apply/apply_operators.jl:150-283) ---------------------------------------
 # Plug-in point: "abstract type ApplyOperatorAlgorithm" (:150) with `apply_operator!(algorithm, dest, operator, state, env)`
 # (:185-194) and `initialize_output` (:204-208); an instance passed as `apply_operator(op, state, env; alg = X)` reaches
