@@ -209,6 +209,10 @@ int bpx_apply_two_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* edges
                              int max_rank, int normalize, double* singular_values_out);
 int bpx_apply_one_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* vertices, const void* ops_packed,
                              int normalize);
+/* how the two-site gates of this context were applied so far: out[0] = by the Gram-path kernel (version 3,
+ * csrc/bpx_apply3.cuh), out[1] = declined by it at run time (rank-deficient / indefinite boundary message, ill-conditioned
+ * Gram matrix) and applied by the step-by-step kernel instead.  reset != 0 clears the counters. */
+int bpx_apply_stats(bpx_ctx* ctx, int64_t out[2], int reset);
 /* download one site tensor (canonical layout) -- `state[v]` after gates were applied */
 int bpx_get_site_tensor(bpx_ctx* ctx, int64_t v, void* data);
 

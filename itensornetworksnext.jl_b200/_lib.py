@@ -83,6 +83,7 @@ def load() -> C.CDLL:
         "bpx_iterate_diff": (C.c_int, [vp, vp, P(dbl)]),
         "bpx_vertex_scalars": (C.c_int, [vp, vp]),
         "bpx_edge_scalars": (C.c_int, [vp, vp]),
+        "bpx_apply_stats": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int]),
         "bpx_bethe_free_energy": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
         "bpx_bethe_free_energy_parts": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "bpx_vertex_expect_numerators": (C.c_int, [vp, vp, vp]),

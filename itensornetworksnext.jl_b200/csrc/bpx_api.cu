@@ -18,6 +18,7 @@
 #include "bpx_halo.cuh"
 #include "bpx_apply.cuh"
 #include "bpx_apply2.cuh"
+#include "bpx_apply3.cuh"
 #include "bpx_expect2.cuh"
 
 using namespace bpx;
@@ -1819,18 +1820,105 @@ static void apply_fill_side(bpx_ctx* ctx, applyk::Side& s, int64_t v, int bond_s
   applyk::finish_side(s, chi_b);
 }
 
-// gates: descriptors with ws_off still unset.  Runs them in chunks bounded by the work-space budget.
-static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const void* ops_packed, size_t ops_elems,
-                     int normalize, double* sv_dev, int64_t sv_stride, bool needs_ws = true) {
+// Version 3 of the two-site kernel (bpx_apply3.cuh, the Gram path): ONE launch for the whole batch, a work space per
+// CTA.  Gates it declines (status 1: rank-deficient / indefinite message, ill-conditioned Gram matrix) come back in
+// `rest` for the step-by-step versions.  *taken = false: the batch has a shape the kernel does not take (nothing ran).
+static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates, const applyk::GateDesc* d_gates, const char* d_ops,
+                        int normalize, double* sv_dev, int64_t sv_stride, std::vector<applyk::GateDesc>& rest, bool* taken) {
+  *taken = false;
   const int64_t ng = (int64_t)gates.size();
-  if (ng == 0) return BPX_OK;
+  const bool cplx = ctx->dtype != BPX_F64;
+  int64_t smem_elems = 0, ws_stride = 0;
+  for (int64_t g = 0; g < ng; ++g) {
+    const int64_t need = applyk3::smem_need(gates[g], cplx);
+    if (need == 0) return BPX_OK;
+    smem_elems = std::max(smem_elems, need);
+    ws_stride = std::max(ws_stride, applyk3::layout3_of(gates[g]).total);
+  }
+  const int bytes = (int)(smem_elems * ctx->esize);
+  if (bytes > ctx->max_smem_optin - 1024) return BPX_OK;
+  int rc, per_sm = 0;
+  if (ctx->dtype == BPX_F64) {
+    if ((rc = set_smem(ctx, applyk3::bp_apply_gates_v3<double>, bytes))) return rc;
+    BPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, applyk3::bp_apply_gates_v3<double>, applyk::NT, bytes));
+  } else {
+    if ((rc = set_smem(ctx, applyk3::bp_apply_gates_v3<c64>, bytes))) return rc;
+    BPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, applyk3::bp_apply_gates_v3<c64>, applyk::NT, bytes));
+  }
+  if (per_sm < 1) return BPX_OK;
+  const int grid = (int)std::min<int64_t>(ng, (int64_t)ctx->num_sms * per_sm);
+  char* d_ws = nullptr;
+  int32_t* d_status = nullptr;
+  if ((rc = ws_get(ctx, bpx_ctx::WS_WORK, (size_t)grid * ws_stride * ctx->esize, &d_ws))) return rc;
+  if ((rc = ws_get(ctx, bpx_ctx::WS_LIST, (size_t)ng * sizeof(int32_t), &d_status))) return rc;
+  applyk3::ApplyArgs3 a3;
+  a3.base.gates = d_gates;
+  a3.base.n_gates = ng;
+  a3.base.sites = ctx->d_sites;
+  a3.base.msgs = ctx->d_msg[ctx->cur];
+  a3.base.ops = d_ops;
+  a3.base.ws = d_ws;
+  a3.base.sv_out = sv_dev;
+  a3.base.sv_stride = sv_stride;
+  a3.base.normalize = normalize;
+  a3.ws_stride = ws_stride;
+  a3.status = d_status;
+  if (ctx->dtype == BPX_F64)
+    applyk3::bp_apply_gates_v3<double><<<grid, applyk::NT, bytes, ctx->stream>>>(a3);
+  else
+    applyk3::bp_apply_gates_v3<c64><<<grid, applyk::NT, bytes, ctx->stream>>>(a3);
+  ctx->n_launches++;
+  BPX_CUDA(ctx, cudaGetLastError());
+  std::vector<int32_t> status((size_t)ng);
+  BPX_CUDA(ctx, cudaMemcpyAsync(status.data(), d_status, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *taken = true;
+  for (int64_t g = 0; g < ng; ++g)
+    if (status[g] != 0) rest.push_back(gates[g]);
+  ctx->n_gates_v3 += ng - (int64_t)rest.size();
+  ctx->n_gates_declined += (int64_t)rest.size();
+  return BPX_OK;
+}
+
+// gates: descriptors with ws_off still unset.  Two-site batches go to version 3 first (BPX_APPLY_V3=0 disables it); what
+// is left runs on version 1 (or the opt-in version 2) in chunks bounded by the work-space budget.
+static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates_in, const void* ops_packed, size_t ops_elems,
+                     int normalize, double* sv_dev, int64_t sv_stride, bool needs_ws = true) {
+  if (gates_in.empty()) return BPX_OK;
+  for (size_t g = 0; g < gates_in.size(); ++g) gates_in[g].sv_row_p1 = (int32_t)(g + 1);
+  char* d_ops = nullptr;
+  int rc = ws_get(ctx, bpx_ctx::WS_OPS, ops_elems * ctx->esize, &d_ops);
+  if (rc) return rc;
+  BPX_CUDA(ctx, cudaMemcpyAsync(d_ops, ops_packed, ops_elems * ctx->esize, cudaMemcpyHostToDevice, ctx->stream));
+  applyk::GateDesc* d_gates = nullptr;
+  std::vector<applyk::GateDesc> rest;
+  std::vector<applyk::GateDesc>* gates_p = &gates_in;
+  const char* v3env = getenv("BPX_APPLY_V3");
+  if (needs_ws && gates_in[0].nsides == 2 && !(v3env && atoi(v3env) == 0)) {
+    if ((rc = ws_upload(ctx, bpx_ctx::WS_DESC, gates_in, &d_gates))) return rc;
+    bool taken = false;
+    if ((rc = apply_run_v3(ctx, gates_in, d_gates, d_ops, normalize, sv_dev, sv_stride, rest, &taken))) {
+      cudaStreamSynchronize(ctx->stream);
+      return rc;
+    }
+    if (taken) {
+      ctx->sites_dirty = true;
+      if (rest.empty()) {
+        ws_trim(ctx);
+        return BPX_OK;
+      }
+      gates_p = &rest;
+    }
+  }
+  std::vector<applyk::GateDesc>& gates = *gates_p;
+  const int64_t ng = (int64_t)gates.size();
   // chunks: consecutive gates whose work space fits the budget (at least one gate per chunk)
   size_t free_b = 0, total_b = 0;
   BPX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  free_b += ctx->ws_bytes[bpx_ctx::WS_WORK];  // the cached work space is ours to re-use
   int64_t budget = (int64_t)std::max<size_t>(std::min<size_t>(free_b / 2, (size_t)8 << 30), (size_t)1 << 20) / ctx->esize;
   if (const char* e = getenv("BPX_APPLY_WS_BYTES")) budget = std::max<int64_t>(1, atoll(e) / ctx->esize);  // tests: force several chunks
-  // OPT-IN version 2 of the two-site kernel (bpx_apply2.cuh: gauging and TSQR staged through shared memory); the
-  // default stays version 1 until version 2 has been run and measured on a B200
+  // OPT-IN version 2 of the two-site kernel (bpx_apply2.cuh: gauging and TSQR staged through shared memory)
   const char* v2env = getenv("BPX_APPLY_V2");
   bool v2 = v2env && atoi(v2env) != 0 && needs_ws;
   int64_t smem_elems = ((int64_t)ctx->max_smem_optin - 2048) / ctx->esize;
@@ -1853,16 +1941,12 @@ static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const v
     max_total = std::max(max_total, cur_total);
   }
   chunk_begin.push_back(ng);
-  applyk::GateDesc* d_gates = nullptr;
   char* d_ws = nullptr;
-  char* d_ops = nullptr;
   // context-cached work space (grow-only; buffers above 1 GiB go back at the end of the call)
-  int rc = ws_upload(ctx, bpx_ctx::WS_DESC, gates, &d_gates);
+  rc = ws_upload(ctx, bpx_ctx::WS_DESC, gates, &d_gates);
   if (!rc) rc = ws_get(ctx, bpx_ctx::WS_WORK, (size_t)max_total * ctx->esize, &d_ws);
-  if (!rc) rc = ws_get(ctx, bpx_ctx::WS_OPS, ops_elems * ctx->esize, &d_ops);
   cudaError_t ce = cudaSuccess;
   if (!rc) {
-    ce = cudaMemcpyAsync(d_ops, ops_packed, ops_elems * ctx->esize, cudaMemcpyHostToDevice, ctx->stream);
     for (size_t c = 0; c + 1 < chunk_begin.size() && ce == cudaSuccess; ++c) {
       applyk::ApplyArgs a;
       a.gates = d_gates + chunk_begin[c];
@@ -1871,7 +1955,7 @@ static int apply_run(bpx_ctx* ctx, std::vector<applyk::GateDesc>& gates, const v
       a.msgs = ctx->d_msg[ctx->cur];
       a.ops = d_ops;
       a.ws = d_ws;
-      a.sv_out = sv_dev ? sv_dev + chunk_begin[c] * sv_stride : nullptr;
+      a.sv_out = sv_dev;  // rows through GateDesc::sv_row_p1
       a.sv_stride = sv_stride;
       a.normalize = normalize;
       const int grid = (int)std::min<int64_t>(a.n_gates, (int64_t)ctx->num_sms * 8);
@@ -2001,6 +2085,25 @@ extern "C" int bpx_apply_one_site_gates(bpx_ctx* ctx, int64_t n_gates, const int
     op_off += (int64_t)gd.s[0].d * gd.s[0].d;
   }
   return apply_run(ctx, gates, ops_packed, (size_t)op_off, normalize, nullptr, 0, normalize != 0);
+}
+
+extern "C" int bpx_apply_stats(bpx_ctx* ctx, int64_t out[2], int reset) {
+  if (!ctx) return BPX_ERR_INVALID;
+  int64_t acc[2] = {0, 0};
+  if (!ctx->children.empty()) {
+    for (bpx_ctx* c : ctx->children) {
+      int64_t t[2];
+      bpx_apply_stats(c, t, reset);
+      acc[0] += t[0];
+      acc[1] += t[1];
+    }
+  } else {
+    acc[0] = ctx->n_gates_v3;
+    acc[1] = ctx->n_gates_declined;
+    if (reset) ctx->n_gates_v3 = ctx->n_gates_declined = 0;
+  }
+  if (out) memcpy(out, acc, sizeof(acc));
+  return BPX_OK;
 }
 
 // ---- two-site expectation values in the BP environment (bpx_expect2.cuh) ------------------------------------

@@ -123,7 +123,7 @@ struct GateDesc {
   int32_t nsides;         // 1 or 2
   int32_t chi_b;          // bond dimension (stays the leg's dimension; the kept rank k is zero-padded up to it)
   int32_t k;              // kept rank: min(max_rank, chi_b, m, n)
-  int32_t pad_;
+  int32_t sv_row_p1;      // 1 + row of sv_out that receives this gate's singular values (0: the gate's index in the launch)
 };
 
 __host__ __device__ inline int64_t gauge_elems(const Side& s) {  // per external leg: B (-> X), V (-> Xinv), eigenvalues
@@ -715,7 +715,8 @@ __global__ void __launch_bounds__(NT) bp_apply_gates(ApplyArgs a) {
   for (int64_t g = blockIdx.x; g < a.n_gates; g += gridDim.x) {
     const GateDesc& gd = a.gates[g];
     run_gate<T>(tm, gd, static_cast<T*>(a.sites), static_cast<T*>(a.msgs), static_cast<const T*>(a.ops),
-                static_cast<T*>(a.ws), a.sv_out ? a.sv_out + g * a.sv_stride : nullptr, a.normalize, &flag, &ssum);
+                static_cast<T*>(a.ws), a.sv_out ? a.sv_out + (gd.sv_row_p1 > 0 ? gd.sv_row_p1 - 1 : g) * a.sv_stride : nullptr,
+                a.normalize, &flag, &ssum);
     __syncthreads();
   }
 }

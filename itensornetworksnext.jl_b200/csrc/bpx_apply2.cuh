@@ -480,8 +480,9 @@ __global__ void __launch_bounds__(NT) bp_apply_gates_v2(ApplyArgs2 a2) {
   tm.wid = threadIdx.x >> 5;
   tm.nw = NT / 32;
   for (int64_t g = blockIdx.x; g < a.n_gates; g += gridDim.x) {
+    const int64_t sv_row = a.gates[g].sv_row_p1 > 0 ? a.gates[g].sv_row_p1 - 1 : g;
     run_two_site_v2<T>(tm, a.gates[g], static_cast<T*>(a.sites), static_cast<T*>(a.msgs), static_cast<const T*>(a.ops),
-                       static_cast<T*>(a.ws), a.sv_out ? a.sv_out + g * a.sv_stride : nullptr, a.normalize, &flag,
+                       static_cast<T*>(a.ws), a.sv_out ? a.sv_out + sv_row * a.sv_stride : nullptr, a.normalize, &flag,
                        reinterpret_cast<T*>(dyn_smem), a2.smem_elems);
     __syncthreads();
   }

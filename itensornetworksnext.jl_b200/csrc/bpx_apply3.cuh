@@ -1,0 +1,819 @@
+// Two-site gate application, version 3: the GRAM path (default for the shapes it takes; versions 1 / 2 stay as the fallback
+// for everything else and for gates this kernel declines at run time).
+//
+// Same result as apply_operators.jl:246-283, different route.  With full-rank boundary messages M_i = X_i^H X_i the
+// reference's chain  gauge -> QR -> gate/SVD -> Q R' -> inverse gauge  collapses algebraically:
+//     P = (X_1 x X_2 x ..) A                gauged matrix view, rows = external legs, cols = (s, bond)
+//     G = P^H P = A^H (M_1 x M_2 x ..) A    the "vertex environment with the site and bond legs open": messages absorbed
+//                                           AS THEY ARE -- no eigen-decomposition of the messages, no X, no X^-1
+//     G = V diag(lam) V^H,  R = diag(sqrt(lam)) V^H   (any R with R^H R = G is a valid "R factor": P = Q R with Q = P R^+)
+//     theta = R_1 R_2 -> gate -> SVD -> Y_a (the new R factors), exactly as in versions 1 / 2
+//     A'_a = X^-1 Q_a Y_a = X^-1 X A R^+ Y_a = A (R^+ Y_a) = A W_a          (X^-1 X = 1 for full-rank messages)
+// so per side the heavy work is three passes of plain dense contractions over the tensor -- absorb the messages (column
+// by column in shared memory), one (rows x cols)^H (rows x cols) Gram product, one (rows x cols)(cols x cols) product --
+// instead of ~80 (version 1) or 8 (version 2) latency-bound Householder passes.  No Householder QR, no TSQR, no Q.
+//
+// When the shortcut is NOT taken (the gate is left untouched and reported in `status`, the caller re-runs it on version 2 /
+// 1, which follow the reference step by step):
+//   * a boundary message is not safely positive definite (Cholesky pivot <= PIVOT_MIN * largest diagonal entry): the
+//     reference then projects on the message's support (pinv), X^-1 X != 1;
+//   * a kept eigenvalue of G is below COND_MIN * the largest: forming G squares the condition number of P, the error of a
+//     singular direction with weight sigma is eps * sigma_max / sigma relative to the tensor -- 1e-11 at the threshold;
+//   * the Jacobi iteration did not converge.
+// Exactly zero eigenvalues of G (zero-padded bonds) are dropped like the reference's pinv does.
+//
+// Serial parts: one-sided Jacobi WITHOUT accumulating V (for Hermitian G the rotated columns are lam_j v_j themselves; for
+// the bond matrix only the k kept right singular vectors are needed: v_j = theta^H u_j / s_j), pairs handled by sub-warp
+// lane groups so that one step of the round-robin schedule is one pass of the CTA (versions 1 / 2: one warp per pair).
+// Written against the `Team` abstraction like versions 1 / 2: tests/native/apply_host.cu runs it on the host.
+#pragma once
+#include "bpx_apply2.cuh"
+
+namespace bpx {
+namespace applyk3 {
+
+using namespace bpx::applyk;
+
+constexpr int PC = 32;               // padded column count of the tiles; the fast path takes sides with cols <= PC
+constexpr int TRG = 128;             // rows per tile of the Gram pass
+constexpr double COND_MIN = 1e-10;   // smallest kept eigenvalue of G relative to the largest
+constexpr double PIVOT_MIN = 1e-12;  // smallest Cholesky pivot of a message relative to its largest diagonal entry
+constexpr int MAXDIM = 16;           // largest external link dimension (a fibre lives in registers)
+
+struct Layout3 {
+  int64_t t;            // T = (M_1 x M_2 x ..) A, same (canonical) layout as A; shared by the two sides
+  int64_t h[2];         // Hermitian parts of the boundary messages, slot order, chi^2 each
+  int64_t g[2];         // G (cols x cols) and its rotated copy
+  int64_t gb[2];
+  int64_t ev[2];        // eigenvalues (doubles; cols T-slots reserved)
+  int64_t r[2];         // R (cols x cols): row q = sqrt(lam_q) v_q^H (zero rows for dropped eigenvalues)
+  int64_t rinv[2];      // R^+ (cols x cols): column q = v_q / sqrt(lam_q)
+  int64_t y[2];         // Y (cols x d k) then W = R^+ Y (cols x PC, zero padded)
+  int64_t w[2];
+  int64_t theta[3], sig, order;
+  int64_t total;
+};
+
+__host__ __device__ inline int64_t herm_elems(const Side& s) {
+  int64_t t = 0;
+  for (int i = 0; i < s.z; ++i)
+    if (i != s.bond_slot) t += (int64_t)s.dim[i] * s.dim[i];
+  return t;
+}
+
+__host__ __device__ inline Layout3 layout3_of(const GateDesc& g) {
+  Layout3 L;
+  int64_t o = 0;
+  L.t = o; o += g.s[0].n > g.s[1].n ? g.s[0].n : g.s[1].n;
+  for (int a = 0; a < 2; ++a) {
+    const Side& s = g.s[a];
+    const int64_t cc = (int64_t)s.cols * s.cols;
+    L.h[a] = o; o += herm_elems(s);
+    L.g[a] = o; o += cc;
+    L.gb[a] = o; o += cc;
+    L.ev[a] = o; o += s.cols;
+    L.r[a] = o; o += cc;
+    L.rinv[a] = o; o += cc;
+    L.y[a] = o; o += (int64_t)s.cols * PC;
+    L.w[a] = o; o += (int64_t)PC * PC;
+  }
+  const int64_t m = (int64_t)g.s[0].cols * g.s[0].d, n = (int64_t)g.s[1].cols * g.s[1].d;
+  for (int i = 0; i < 3; ++i) { L.theta[i] = o; o += m * n; }
+  L.sig = o; o += n;
+  L.order = o; o += n;
+  L.total = (o + 1) & ~(int64_t)1;  // keep every gate's work space 16-byte aligned for both element types
+  return L;
+}
+
+// Can the fast path take this gate, and how much shared memory (elements of T) does it want?  0: not supported.
+__host__ __device__ inline int64_t smem_need(const GateDesc& g, bool cplx) {
+  if (g.nsides != 2) return 0;
+  int64_t need = 0;
+  for (int a = 0; a < 2; ++a) {
+    const Side& s = g.s[a];
+    if (s.cols > PC || s.cols < 1) return 0;
+    int64_t hsum = 0;
+    for (int i = 0; i < s.z; ++i)
+      if (i != s.bond_slot) {
+        if (s.dim[i] > MAXDIM) return 0;
+        hsum += (int64_t)s.dim[i] * s.dim[i];
+      }
+    const int64_t cb = (!cplx && (s.cols % 2 == 0)) ? 2 : 1;
+    const int64_t absorb = cb * s.rows + hsum;                 // column batch + the messages
+    const int64_t gram = 2 * (int64_t)TRG * PC + TRG;          // A tile, T tile (the reduction re-uses them), row table
+    const int64_t trf = cplx ? 128 : 256;
+    const int64_t fin = trf * PC + (int64_t)PC * PC + trf;     // A tile, W, row table
+    need = need > absorb ? need : absorb;
+    need = need > gram ? need : gram;
+    need = need > fin ? need : fin;
+  }
+  const int64_t m = (int64_t)g.s[0].cols * g.s[0].d, n = (int64_t)g.s[1].cols * g.s[1].d;
+  const int64_t ldb = (m % 16 == 0) ? m + 8 : m;
+  const int64_t svd = ldb * n;
+  need = need > svd ? need : svd;
+  const int64_t gramf = (int64_t)(PC + 8) * PC + (int64_t)PC * PC;  // rotated + unrotated Gram matrix
+  need = need > gramf ? need : gramf;
+  // the cross-warp reduction of the Gram pass: 8 partial tiles of PC x (PC or PC/2) elements
+  const int64_t red = 8 * (int64_t)PC * (cplx ? PC / 2 : PC);
+  need = need > red ? need : red;
+  return (need + 1) & ~(int64_t)1;
+}
+
+// ---- canonical addressing of the matrix view: element (row, col) of side `sd` sits at rowaddr(row) + coladdr(col) --------
+struct Walk {
+  int64_t rstride[MAXZ];  // canonical strides (elements) of the external legs, slot order
+  int32_t rdim[MAXZ];
+  int32_t next;           // external legs
+  int64_t bstride;        // canonical stride of the bond leg
+  int32_t d;
+};
+__host__ __device__ inline Walk walk_of(const Side& sd) {
+  Walk w;
+  w.next = 0;
+  w.bstride = 0;
+  w.d = sd.d;
+  int64_t stride = sd.d;
+  for (int k = 0; k < sd.z; ++k) {
+    if (k == sd.bond_slot) {
+      w.bstride = stride;
+    } else {
+      w.rstride[w.next] = stride;
+      w.rdim[w.next] = sd.dim[k];
+      ++w.next;
+    }
+    stride *= sd.dim[k];
+  }
+  return w;
+}
+__host__ __device__ __forceinline__ int64_t rowaddr(const Walk& w, int64_t row) {
+  int64_t a = 0;
+  for (int k = 0; k < w.next; ++k) {
+    a += (row % w.rdim[k]) * w.rstride[k];
+    row /= w.rdim[k];
+  }
+  return a;
+}
+__host__ __device__ __forceinline__ int64_t coladdr(const Walk& w, int col) { return (col % w.d) + (col / w.d) * w.bstride; }
+
+// rows [row0, row0 + tr) x all columns of the matrix view -> tile[r * rs + c * cs]; rows beyond the matrix and columns
+// cols..PC-1 are zero.  `rtab`: tr int64 slots of shared memory (canonical row offsets, computed once per row).
+template <typename T>
+__host__ __device__ void load_tile(const Team& tm, const Side& sd, const Walk& wk, const T* src, int64_t row0, int tr, T* tile,
+                                   int rs, int cs, int64_t* rtab) {
+  using E = Elem<T>;
+  for (int r = tm.tid(); r < tr; r += tm.nt()) rtab[r] = (row0 + r < sd.rows) ? rowaddr(wk, row0 + r) : -1;
+  tm.sync();
+  const int cols = sd.cols;
+  // order of the flat loop: the faster index is the one that is contiguous in the canonical layout
+  const bool col_fast = wk.next == 0 || wk.bstride < wk.rstride[0];
+  const int d = wk.d, nb = cols / d;
+  const int total = tr * PC;
+  for (int i = tm.tid(); i < total; i += tm.nt()) {
+    int r, c;
+    if (col_fast) {
+      c = i % PC;
+      r = i / PC;
+    } else {  // (s, r, bond): s fastest, then the row, then the bond index; padding columns last
+      if (i < tr * cols) {
+        const int s = i % d, rest = i / d;
+        r = rest % tr;
+        c = s + d * (rest / tr);
+      } else {
+        const int j = i - tr * cols;
+        r = j % tr;
+        c = cols + j / tr;
+      }
+    }
+    (void)nb;
+    T v = E::zero();
+    if (c < cols && rtab[r] >= 0) v = src[rtab[r] + coladdr(wk, c)];
+    tile[(int64_t)r * rs + (int64_t)c * cs] = v;
+  }
+  tm.sync();
+}
+
+// ---- messages: Hermitian part + positive-definiteness check ---------------------------------------------------------------
+// One warp per message: right-looking Cholesky on a scratch copy; *bad is set when a pivot is not safely positive.
+template <typename T>
+__host__ __device__ void message_check(const Team& tm, const Side& sd, const T* msgs, T* H, T* scratch, int* bad) {
+  using E = Elem<T>;
+  const int L = tm.lanes();
+  int64_t off = 0;
+  int leg = 0;
+  for (int i = 0; i < sd.z; ++i) {
+    if (i == sd.bond_slot) continue;
+    const int chi = sd.dim[i];
+    const T* m = msgs + sd.in_msg[i];
+    T* h = H + off;
+    for (int e = tm.tid(); e < chi * chi; e += tm.nt()) {
+      const int r = e % chi, c = e / chi;
+      const T v = scal(E::add(m[r + c * chi], E::conj(m[c + r * chi])), 0.5);
+      h[e] = v;
+      scratch[off + e] = v;
+    }
+    off += (int64_t)chi * chi;
+    ++leg;
+  }
+  tm.sync();
+  off = 0;
+  leg = 0;
+  for (int i = 0; i < sd.z; ++i) {
+    if (i == sd.bond_slot) continue;
+    const int chi = sd.dim[i];
+    if (leg % tm.nw == tm.wid) {
+      T* a = scratch + off;  // lower triangle, column-major
+      double dmax = 0.0;
+      for (int j = 0; j < chi; ++j) {
+        const double x = real_of(a[j + j * chi]);
+        dmax = x > dmax ? x : dmax;
+      }
+      const double thr = PIVOT_MIN * dmax;
+      bool ok = dmax > 0.0;
+      for (int j = 0; j < chi && ok; ++j) {
+        const double piv = real_of(a[j + j * chi]);
+        if (!(piv > thr)) {
+          ok = false;
+          break;
+        }
+        const double inv = 1.0 / sqrt(piv);
+#ifdef __CUDA_ARCH__
+        __syncwarp();
+#endif
+        for (int r = j + tm.lane; r < chi; r += L) a[r + j * chi] = scal(a[r + j * chi], inv);
+#ifdef __CUDA_ARCH__
+        __syncwarp();
+#endif
+        // trailing update: a[r, c] -= l[r] conj(l[c]) for j < c <= r
+        const int nt = chi - j - 1;
+        for (int e = tm.lane; e < nt * nt; e += L) {
+          const int r = j + 1 + e % nt, c = j + 1 + e / nt;
+          if (r >= c) a[r + c * chi] = sub(a[r + c * chi], E::mul(a[r + j * chi], E::conj(a[c + j * chi])));
+        }
+#ifdef __CUDA_ARCH__
+        __syncwarp();
+#endif
+      }
+      if (!ok && tm.lane == 0) BPX_FLAG_SET(bad);
+    }
+    off += (int64_t)chi * chi;
+    ++leg;
+  }
+  tm.sync();
+}
+
+// ---- absorb: T[:, c] = (M_1 x M_2 x ..) A[:, c], CB columns at a time, in place in shared memory ---------------------------
+// A thread owns whole fibres (the chi elements along one leg) of all CB columns: inputs to registers, outputs back to the
+// same places -- no ping-pong buffer; every matrix element it loads (a broadcast) feeds CB FMAs.
+template <typename T, int CB, int CHI>
+__host__ __device__ __forceinline__ void absorb_leg_fixed(const Team& tm, T* col, int64_t rows, int64_t st, const T* x) {
+  using E = Elem<T>;
+  const int64_t nf = rows / CHI;
+  for (int64_t f = tm.tid(); f < nf; f += tm.nt()) {
+    const int64_t lo = f % st, hi = f / st, base = hi * st * CHI + lo;
+    T v[CB][CHI];
+#pragma unroll
+    for (int b = 0; b < CB; ++b)
+#pragma unroll
+      for (int l = 0; l < CHI; ++l) v[b][l] = col[b * rows + base + l * st];
+#pragma unroll 1
+    for (int g = 0; g < CHI; ++g) {
+      T acc[CB];
+#pragma unroll
+      for (int b = 0; b < CB; ++b) acc[b] = E::zero();
+#pragma unroll
+      for (int l = 0; l < CHI; ++l) {
+        const T xv = x[g + CHI * l];
+#pragma unroll
+        for (int b = 0; b < CB; ++b) acc[b] = E::fma(xv, v[b][l], acc[b]);
+      }
+#pragma unroll
+      for (int b = 0; b < CB; ++b) col[b * rows + base + g * st] = acc[b];
+    }
+  }
+  tm.sync();
+}
+template <typename T, int CB>
+__host__ __device__ void absorb_leg_any(const Team& tm, T* col, int64_t rows, int64_t st, int chi, const T* x) {
+  using E = Elem<T>;
+  const int64_t nf = rows / chi;
+  for (int64_t f = tm.tid(); f < nf; f += tm.nt()) {
+    const int64_t lo = f % st, hi = f / st, base = hi * st * chi + lo;
+    for (int b = 0; b < CB; ++b) {
+      T v[MAXDIM], o[MAXDIM];
+      for (int l = 0; l < chi; ++l) v[l] = col[b * rows + base + l * st];
+      for (int g = 0; g < chi; ++g) {
+        T acc = E::zero();
+        for (int l = 0; l < chi; ++l) acc = E::fma(x[g + chi * l], v[l], acc);
+        o[g] = acc;
+      }
+      for (int g = 0; g < chi; ++g) col[b * rows + base + g * st] = o[g];
+    }
+  }
+  tm.sync();
+}
+template <typename T, int CB>
+__host__ __device__ void absorb_leg(const Team& tm, T* col, int64_t rows, int64_t st, int chi, const T* x) {
+  switch (chi) {
+    case 2: absorb_leg_fixed<T, CB, 2>(tm, col, rows, st, x); break;
+    case 4: absorb_leg_fixed<T, CB, 4>(tm, col, rows, st, x); break;
+    case 8: absorb_leg_fixed<T, CB, 8>(tm, col, rows, st, x); break;
+    case 16: absorb_leg_fixed<T, CB, 16>(tm, col, rows, st, x); break;
+    default: absorb_leg_any<T, CB>(tm, col, rows, st, chi, x);
+  }
+}
+
+template <typename T, int CB>
+__host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk& wk, const T* a, const T* H, T* tout, T* smem) {
+  T* col = smem;                       // CB * rows
+  T* hs = smem + (int64_t)CB * sd.rows;  // the messages
+  const int64_t hn = herm_elems(sd);
+  for (int64_t i = tm.tid(); i < hn; i += tm.nt()) hs[i] = H[i];
+  tm.sync();
+  const int64_t rows = sd.rows;
+  for (int c0 = 0; c0 < sd.cols; c0 += CB) {
+    for (int64_t i = tm.tid(); i < rows * CB; i += tm.nt()) {
+      const int b = (int)(i % CB);
+      const int64_t r = i / CB;
+      col[b * rows + r] = a[rowaddr(wk, r) + coladdr(wk, c0 + b)];
+    }
+    tm.sync();
+    int64_t st = 1, off = 0;
+    for (int k = 0; k < wk.next; ++k) {
+      const int chi = wk.rdim[k];
+      absorb_leg<T, CB>(tm, col, rows, st, chi, hs + off);
+      st *= chi;
+      off += (int64_t)chi * chi;
+    }
+    for (int64_t i = tm.tid(); i < rows * CB; i += tm.nt()) {
+      const int b = (int)(i % CB);
+      const int64_t r = i / CB;
+      tout[rowaddr(wk, r) + coladdr(wk, c0 + b)] = col[b * rows + r];
+    }
+    tm.sync();
+  }
+}
+
+// ---- Gram pass: G[c', c] = sum_rows conj(A[row, c']) T[row, c] -------------------------------------------------------------
+// Tiles of TRG rows, both operands as [row][PC] in shared memory.  A warp takes every nw-th row of the tile; lane (i, j) of
+// an 8 x 4 lane grid accumulates the 4 x TJ block G[4 i .., TJ (j + 4 pass) ..]: per row 4 + TJ operand loads (broadcast
+// within the lane groups) feed 4 TJ FMAs.  The nw partial tiles are summed through shared memory at the end.
+template <typename T, int TJ>
+__host__ __device__ void gram_side(const Team& tm, const Side& sd, const Walk& wk, const T* a, const T* t, T* G, T* smem) {
+  using E = Elem<T>;
+  constexpr int NPASS = PC / (4 * TJ);
+  T* sA = smem;
+  T* sT = smem + (int64_t)TRG * PC;
+  int64_t* rtab = reinterpret_cast<int64_t*>(smem + 2 * (int64_t)TRG * PC);
+  const int L = tm.lanes();
+  const int cols = sd.cols;
+  for (int pass = 0; pass < NPASS; ++pass) {
+    // host lanes (L = 1): one lane plays all 32 roles in turn, so the accumulators live in an array indexed by role
+#ifdef __CUDA_ARCH__
+    T acc[4][TJ];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < TJ; ++y) acc[x][y] = E::zero();
+#else
+    std::vector<T> hacc((size_t)32 * 4 * TJ, E::zero());
+#endif
+    for (int64_t row0 = 0; row0 < sd.rows; row0 += TRG) {
+      load_tile<T>(tm, sd, wk, a, row0, TRG, sA, PC, 1, rtab);
+      load_tile<T>(tm, sd, wk, t, row0, TRG, sT, PC, 1, rtab);
+      const int nr = (int)((sd.rows - row0) < TRG ? (sd.rows - row0) : TRG);
+#ifdef __CUDA_ARCH__
+      const int li = tm.lane >> 2, lj = tm.lane & 3;
+      const T* pa = sA + 4 * li;
+      const T* pt = sT + TJ * (lj + 4 * pass);
+      for (int r = tm.wid; r < nr; r += tm.nw) {
+        T av[4], tv[TJ];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) av[x] = E::conj(pa[r * PC + x]);
+#pragma unroll
+        for (int y = 0; y < TJ; ++y) tv[y] = pt[r * PC + y];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < TJ; ++y) acc[x][y] = E::fma(av[x], tv[y], acc[x][y]);
+      }
+#else
+      for (int role = 0; role < 32; ++role) {
+        const int li = role >> 2, lj = role & 3;
+        for (int r = tm.wid; r < nr; r += tm.nw)
+          for (int x = 0; x < 4; ++x)
+            for (int y = 0; y < TJ; ++y) {
+              T& o = hacc[(size_t)(role * 4 + x) * TJ + y];
+              o = E::fma(E::conj(sA[r * PC + 4 * li + x]), sT[r * PC + TJ * (lj + 4 * pass) + y], o);
+            }
+      }
+      (void)L;
+#endif
+      tm.sync();
+    }
+    // cross-warp reduction: red[w][c'][y-block]
+    constexpr int PW = 4 * TJ;  // columns of G covered by one pass
+    T* red = smem;
+#ifdef __CUDA_ARCH__
+    {
+      const int li = tm.lane >> 2, lj = tm.lane & 3;
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < TJ; ++y) red[((int64_t)tm.wid * PC + 4 * li + x) * PW + TJ * lj + y] = acc[x][y];
+    }
+#else
+    for (int role = 0; role < 32; ++role) {
+      const int li = role >> 2, lj = role & 3;
+      for (int x = 0; x < 4; ++x)
+        for (int y = 0; y < TJ; ++y) red[((int64_t)tm.wid * PC + 4 * li + x) * PW + TJ * lj + y] = hacc[(size_t)(role * 4 + x) * TJ + y];
+    }
+#endif
+    tm.sync();
+    for (int e = tm.tid(); e < PC * PW; e += tm.nt()) {
+      const int cp = e / PW, cc = pass * PW + e % PW;
+      T s = E::zero();
+      for (int w = 0; w < tm.nw; ++w) s = E::add(s, red[(int64_t)w * PC * PW + e]);
+      if (cp < cols && cc < cols) G[cp + cols * cc] = s;
+    }
+    tm.sync();
+  }
+}
+
+// ---- one-sided Jacobi without V, pairs on sub-warp lane groups ---------------------------------------------------------------
+// B (m x n, leading dimension ld, shared memory) is rotated until its columns are mutually orthogonal.  Returns through
+// *flag_out whether the last sweep still rotated (not converged within the sweep budget).
+template <typename T>
+__host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int ld, int* flag, int* not_converged) {
+  using E = Elem<T>;
+  if (n < 2) return;
+  const int L = tm.lanes();
+  const int np = (n + 1) & ~1, npairs = np / 2;
+  // lanes per pair: as many as keep every pair of a step in flight at once
+  int GS = 1;
+  while (GS * 2 <= L && (tm.nw * (L / (GS * 2))) >= npairs) GS *= 2;
+  const int gpw = L / GS;                // groups per warp
+  const int sl = tm.lane % GS, grp = tm.lane / GS;
+  const double tol2 = (double)m * EPS * EPS;
+  double fro2 = 0.0;
+  for (int64_t i = tm.lane; i < (int64_t)m * n; i += L) fro2 += E::abs2(B[(i % m) + (int64_t)ld * (i / m)]);
+  fro2 = tm.sum(fro2);
+  const double zero2 = (double)n * n * EPS * EPS * fro2;
+  tm.sync();
+  int f = 1;
+  for (int sweep = 0; sweep < MAX_JACOBI_SWEEPS && f; ++sweep) {
+    if (tm.tid() == 0) *flag = 0;
+    tm.sync();
+    for (int step = 0; step < np - 1; ++step) {
+      for (int base = tm.wid * gpw; base < npairs; base += tm.nw * gpw) {  // warp-uniform bound: shuffles stay converged
+        const int idx = base + grp;
+        int p = 0, q = 1;
+        bool active = idx < npairs;
+        if (active) {
+          if (idx == 0) {
+            p = np - 1;
+            q = step;
+          } else {
+            p = (step + idx) % (np - 1);
+            q = (step - idx + (np - 1)) % (np - 1);
+          }
+          if (p > q) { const int t = p; p = q; q = t; }
+          if (q >= n) { active = false; p = 0; q = 1; }
+        }
+        T* bp = B + (int64_t)p * ld;
+        T* bq = B + (int64_t)q * ld;
+        double a = 0.0, b = 0.0;
+        T g = E::zero();
+        for (int r = sl; r < m; r += GS) {
+          const T x = bp[r], y = bq[r];
+          a += E::abs2(x);
+          b += E::abs2(y);
+          g = E::fma(E::conj(x), y, g);
+        }
+#ifdef __CUDA_ARCH__
+        for (int o = GS >> 1; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+          g = E::add(g, E::shfl_xor(g, o));
+        }
+#endif
+        const double g2 = E::abs2(g);
+        if (!active || !(g2 > tol2 * a * b) || !(a > zero2) || !(b > zero2)) continue;  // group-uniform, no shuffles below
+        const double ga = sqrt(g2);
+        const T ph = scal(g, 1.0 / ga);
+        const double zeta = (b - a) / (2.0 * ga);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        const T sph = scal(ph, s), scph = scal(E::conj(ph), s);
+        for (int r = sl; r < m; r += GS) {
+          const T x = bp[r], y = bq[r];
+          bp[r] = sub(scal(x, c), E::mul(y, scph));
+          bq[r] = E::add(E::mul(x, sph), scal(y, c));
+        }
+        if (sl == 0) BPX_FLAG_SET(flag);
+      }
+      tm.sync();
+    }
+    f = *flag;
+    tm.sync();
+  }
+  if (f && tm.tid() == 0) BPX_FLAG_SET(not_converged);
+  tm.sync();
+}
+
+// ---- eigen-decomposition of the Gram matrix -> R, R^+ ------------------------------------------------------------------------
+// G Hermitian (cols x cols, global).  Rotating the columns of G: G V = V diag(lam), so column j of the rotated copy is
+// lam_j v_j: |lam_j| = |b_j|, sign from Re(b_j^H G b_j) (a slightly indefinite G).  *bad: conditioning / convergence.
+template <typename T>
+__host__ __device__ void gram_factor(const Team& tm, int cols, int rank_max, const T* G, T* Gb, double* ev, T* R, T* Rinv, T* smem, int* flag,
+                                     int* bad) {
+  using E = Elem<T>;
+  const int ld = (cols % 16 == 0) ? cols + 8 : cols;
+  T* sb = smem;
+  T* sg = smem + (int64_t)ld * cols;  // the unrotated matrix, for the Rayleigh quotients
+  for (int i = tm.tid(); i < cols * cols; i += tm.nt()) {
+    const T v = G[i];
+    sb[(i % cols) + ld * (i / cols)] = v;
+    sg[i] = v;
+  }
+  tm.sync();
+  jacobi_groups<T>(tm, sb, cols, cols, ld, flag, bad);
+  for (int i = tm.tid(); i < cols * cols; i += tm.nt()) Gb[i] = sb[(i % cols) + ld * (i / cols)];
+  tm.sync();
+  for (int j = tm.tid(); j < cols; j += tm.nt()) {
+    const T* b = sb + (int64_t)ld * j;
+    double nb = 0.0;
+    for (int r = 0; r < cols; ++r) nb += E::abs2(b[r]);
+    T acc = E::zero();  // b^H G b,  (G b)[r] = sum_c G[r, c] b[c]
+    for (int r = 0; r < cols; ++r) {
+      T gb = E::zero();
+      for (int c = 0; c < cols; ++c) gb = E::fma(sg[r + cols * c], b[c], gb);
+      acc = E::fma(E::conj(b[r]), gb, acc);
+    }
+    // |lam_j| = |b_j| (b_j = lam_j v_j); the Rayleigh quotient only supplies the sign -- for a column that the iteration
+    // left at rounding level its VALUE would be an average of all eigenvalues, not small
+    ev[j] = real_of(acc) >= 0.0 ? sqrt(nb) : -sqrt(nb);
+  }
+  tm.sync();
+  double dmax = 0.0, dmin = INFINITY;
+  for (int j = 0; j < cols; ++j) dmax = ev[j] > dmax ? ev[j] : dmax;
+  const double cut = EPS * cols * dmax;
+  // rank bound: G = P^H P with P rows x cols has at most `rank_max` non-zero eigenvalues; whatever the iteration left in
+  // the other directions is rounding noise (it may exceed `cut` by a small factor), so only the largest rank_max count
+  tm.sync();
+  for (int j = tm.tid(); j < cols; j += tm.nt()) {
+    int before = 0;
+    for (int i = 0; i < cols; ++i) before += (ev[i] > ev[j] || (ev[i] == ev[j] && i < j)) ? 1 : 0;
+    if (before >= rank_max || !(ev[j] > cut)) ev[j] = 0.0;
+  }
+  tm.sync();
+  for (int j = 0; j < cols; ++j)
+    if (ev[j] > 0.0 && ev[j] < dmin) dmin = ev[j];
+  if (!(dmax > 0.0) || dmin < COND_MIN * dmax) {
+    if (tm.tid() == 0) BPX_FLAG_SET(bad);
+  }
+  for (int i = tm.tid(); i < cols * cols; i += tm.nt()) {
+    const int q = i % cols, c = i / cols;  // R[q, c] = sqrt(lam_q) conj(v_q[c]),  v_q = b_q / |b_q|
+    const double lam = ev[q];
+    T r = E::zero(), ri = E::zero();
+    if (lam > 0.0) {
+      const T* b = sb + (int64_t)ld * q;
+      double nb = 0.0;
+      for (int rr = 0; rr < cols; ++rr) nb += E::abs2(b[rr]);
+      const double inv = 1.0 / sqrt(nb);
+      const T v = scal(b[c], inv);
+      r = scal(E::conj(v), sqrt(lam));
+      ri = scal(v, 1.0 / sqrt(lam));
+    }
+    R[q + cols * c] = r;
+    Rinv[c + cols * q] = ri;
+  }
+  tm.sync();
+}
+
+// ---- final pass: A'[row, c'] = sum_c A[row, c] W[c, c'] in place -----------------------------------------------------------
+template <typename T, int TRF, int RT, int NO>
+__host__ __device__ void final_side(const Team& tm, const Side& sd, const Walk& wk, T* a, const T* W, T* smem) {
+  using E = Elem<T>;
+  T* sA = smem;                                  // [c][TRF]
+  T* sW = smem + (int64_t)TRF * PC;              // [c][PC]
+  int64_t* rtab = reinterpret_cast<int64_t*>(sW + (int64_t)PC * PC);
+  for (int i = tm.tid(); i < PC * PC; i += tm.nt()) sW[i] = W[i];
+  tm.sync();
+  const int cols = sd.cols;
+  constexpr int RG = TRF / RT;                   // row groups: thread rows rg, rg + RG, ..
+  constexpr int OG = PC / NO;                    // output groups
+  for (int64_t row0 = 0; row0 < sd.rows; row0 += TRF) {
+    load_tile<T>(tm, sd, wk, a, row0, TRF, sA, 1, TRF, rtab);
+    for (int item = tm.tid(); item < RG * OG; item += tm.nt()) {
+      const int rg = item % RG, og = item / RG;
+      if (og * NO >= cols) continue;
+      T acc[RT][NO];
+#pragma unroll
+      for (int x = 0; x < RT; ++x)
+#pragma unroll
+        for (int y = 0; y < NO; ++y) acc[x][y] = E::zero();
+      for (int c = 0; c < cols; ++c) {
+        T av[RT];
+#pragma unroll
+        for (int x = 0; x < RT; ++x) av[x] = sA[c * TRF + rg + x * RG];
+        const T* pw = sW + c * PC + og * NO;
+#pragma unroll
+        for (int y = 0; y < NO; ++y) {
+          const T wv = pw[y];
+#pragma unroll
+          for (int x = 0; x < RT; ++x) acc[x][y] = E::fma(av[x], wv, acc[x][y]);
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < RT; ++x) {
+        const int r = rg + x * RG;
+        const int64_t ra = rtab[r];
+        if (ra < 0) continue;
+#pragma unroll
+        for (int y = 0; y < NO; ++y) {
+          const int cp = og * NO + y;
+          if (cp < cols) a[ra + coladdr(wk, cp)] = acc[x][y];
+        }
+      }
+    }
+    tm.sync();
+  }
+}
+
+// One two-site gate.  Returns (to every thread) 0 when the gate was applied, 1 when it was left untouched for the fallback.
+template <typename T>
+__host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* sites, T* msgs, const T* ops, T* w /* this CTA's work space */,
+                                        double* sv_out, int normalize, int* flag, int* bad, T* smem) {
+  using E = Elem<T>;
+  constexpr bool CPLX = Elem<T>::is_complex;
+  const Layout3 L = layout3_of(gd);
+  if (tm.tid() == 0) *bad = 0;
+  tm.sync();
+  Walk wk[2];
+  for (int a = 0; a < 2; ++a) {
+    const Side& sd = gd.s[a];
+    wk[a] = walk_of(sd);
+    message_check<T>(tm, sd, msgs, w + L.h[a], smem, bad);
+    if (*bad) return 1;
+    const T* A = sites + sd.site_off;
+    if (!CPLX && sd.cols % 2 == 0)
+      absorb_side<T, 2>(tm, sd, wk[a], A, w + L.h[a], w + L.t, smem);
+    else
+      absorb_side<T, 1>(tm, sd, wk[a], A, w + L.h[a], w + L.t, smem);
+    gram_side<T, CPLX ? 4 : 8>(tm, sd, wk[a], A, w + L.t, w + L.g[a], smem);
+    gram_factor<T>(tm, sd.cols, sd.nref, w + L.g[a], w + L.gb[a], reinterpret_cast<double*>(w + L.ev[a]), w + L.r[a], w + L.rinv[a], smem,
+                   flag, bad);
+    if (*bad) return 1;
+  }
+  // ---- the bond problem (apply_operators.jl:260-268), R factors with cols rows each -----------------------------------
+  const Side& s1 = gd.s[0];
+  const Side& s2 = gd.s[1];
+  const int d1 = s1.d, d2 = s2.d, n1 = s1.cols, n2 = s2.cols, chi = gd.chi_b;
+  const int m = n1 * d1, n = n2 * d2;
+  const T* R1 = w + L.r[0];
+  const T* R2 = w + L.r[1];
+  T* th0 = w + L.theta[0];
+  T* th1 = w + L.theta[1];  // theta after the gate (kept: V = theta^H U / s)
+  T* th2 = w + L.theta[2];  // rotated copy: U diag(s)
+  for (int i = tm.tid(); i < m * n; i += tm.nt()) {
+    const int row = i % m, col = i / m;
+    const int q1 = row % n1, x1 = row / n1, q2 = col % n2, x2 = col / n2;
+    T acc = E::zero();
+    for (int b = 0; b < chi; ++b) acc = E::fma(R1[q1 + n1 * (x1 + d1 * b)], R2[q2 + n2 * (x2 + d2 * b)], acc);
+    th0[i] = acc;
+  }
+  tm.sync();
+  const T* op = ops + gd.op_off;
+  const int dd = d1 * d2;
+  const int ldb = (m % 16 == 0) ? m + 8 : m;
+  T* sb = smem;
+  for (int i = tm.tid(); i < m * n; i += tm.nt()) {
+    const int row = i % m, col = i / m;
+    const int q1 = row % n1, o1 = row / n1, q2 = col % n2, o2 = col / n2;
+    T acc = E::zero();
+    for (int x2 = 0; x2 < d2; ++x2)
+      for (int x1 = 0; x1 < d1; ++x1)
+        acc = E::fma(op[o1 + d1 * o2 + dd * (x1 + d1 * x2)], th0[(q1 + n1 * x1) + m * (q2 + n2 * x2)], acc);
+    th1[i] = acc;
+    sb[row + (int64_t)ldb * col] = acc;
+  }
+  tm.sync();
+  jacobi_groups<T>(tm, sb, m, n, ldb, flag, bad);
+  if (*bad) return 1;
+  double* sig = reinterpret_cast<double*>(w + L.sig);
+  int32_t* order = reinterpret_cast<int32_t*>(w + L.order);
+  for (int i = tm.tid(); i < m * n; i += tm.nt()) th2[i] = sb[(i % m) + (int64_t)ldb * (i / m)];
+  for (int j = tm.tid(); j < n; j += tm.nt()) {
+    double a = 0.0;
+    for (int r = 0; r < m; ++r) a += E::abs2(sb[r + (int64_t)ldb * j]);
+    sig[j] = sqrt(a);
+  }
+  tm.sync();
+  if (tm.tid() == 0) {
+    for (int j = 0; j < n; ++j) {
+      int pos = j;
+      while (pos > 0 && sig[order[pos - 1]] < sig[j]) {
+        order[pos] = order[pos - 1];
+        --pos;
+      }
+      order[pos] = j;
+    }
+  }
+  tm.sync();
+  const int k = gd.k;
+  double nrm = 1.0;
+  if (normalize) {
+    double a = 0.0;
+    for (int j = 0; j < k; ++j) a += sig[order[j]] * sig[order[j]];
+    nrm = a > 0.0 ? sqrt(a) : 1.0;
+  }
+  // Y_1[q1, (x, kk)] = U[(q1, x), j] sqrt(s'_j);  Y_2[q2, (x, kk)] = sqrt(s'_j) conj(V[(q2, x), j]),  V_j = theta^H u_j / s_j
+  for (int a = 0; a < 2; ++a) {
+    const Side& sd = gd.s[a];
+    T* y = w + L.y[a];
+    const int na = sd.cols, da = sd.d;
+    for (int i = tm.tid(); i < na * da * k; i += tm.nt()) {
+      const int q = i % na, c = i / na, x = c % da, kk = c / da, j = order[kk];
+      const double sj = sig[j], snew = sj / nrm;
+      T v = E::zero();
+      if (sj > 0.0) {
+        if (a == 0) {
+          v = scal(th2[(q + na * x) + (int64_t)m * j], sqrt(snew) / sj);
+        } else {
+          // conj(V[c2, j]) = sum_r theta[r, c2] conj(u_j[r]) / s_j,  u_j = th2[:, j] / s_j
+          const int c2 = q + na * x;
+          T acc = E::zero();
+          for (int r = 0; r < m; ++r) acc = E::fma(th1[r + (int64_t)m * c2], E::conj(th2[r + (int64_t)m * j]), acc);
+          v = scal(acc, sqrt(snew) / (sj * sj));
+        }
+      }
+      y[i] = v;
+    }
+  }
+  tm.sync();
+  // W_a = R_a^+ Y_a, zero padded to PC x PC ([c][c'] row-major for the final pass)
+  for (int a = 0; a < 2; ++a) {
+    const Side& sd = gd.s[a];
+    const int na = sd.cols, nc = sd.d * k;
+    const T* y = w + L.y[a];
+    const T* ri = w + L.rinv[a];
+    T* W = w + L.w[a];
+    for (int i = tm.tid(); i < PC * PC; i += tm.nt()) {
+      const int cp = i % PC, c = i / PC;
+      T acc = E::zero();
+      if (c < na && cp < nc)
+        for (int q = 0; q < na; ++q) acc = E::fma(ri[c + na * q], y[q + na * cp], acc);
+      W[c * PC + cp] = acc;
+    }
+  }
+  tm.sync();
+  for (int a = 0; a < 2; ++a) {
+    const Side& sd = gd.s[a];
+    T* A = sites + sd.site_off;
+    if (CPLX)
+      final_side<T, 128, 1, 8>(tm, sd, wk[a], A, w + L.w[a], smem);
+    else
+      final_side<T, 256, 2, 16>(tm, sd, wk[a], A, w + L.w[a], smem);
+  }
+  for (int i = tm.tid(); i < chi * chi; i += tm.nt()) {
+    const int r = i % chi, c = i / chi;
+    const T v = (r == c && r < k) ? from_real<T>(sig[order[r]] / nrm) : E::zero();
+    msgs[gd.msg12 + i] = v;
+    msgs[gd.msg21 + i] = v;
+  }
+  if (sv_out)
+    for (int i = tm.tid(); i < chi; i += tm.nt()) sv_out[i] = i < k ? sig[order[i]] / nrm : 0.0;
+  tm.sync();
+  return 0;
+}
+
+#ifdef __CUDACC__
+struct ApplyArgs3 {
+  ApplyArgs base;       // base.ws: one work space of ws_stride elements PER CTA (not per gate: a layer is one launch)
+  int64_t ws_stride;
+  int32_t* status;      // per gate: 0 applied, 1 left for the fallback
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NT, 2) bp_apply_gates_v3(ApplyArgs3 a3) {
+  extern __shared__ __align__(16) unsigned char dyn_smem3[];
+  __shared__ int flag, bad;
+  const ApplyArgs& a = a3.base;
+  Team tm;
+  tm.lane = threadIdx.x & 31;
+  tm.wid = threadIdx.x >> 5;
+  tm.nw = NT / 32;
+  for (int64_t g = blockIdx.x; g < a.n_gates; g += gridDim.x) {
+    const int64_t sv_row = a.gates[g].sv_row_p1 > 0 ? a.gates[g].sv_row_p1 - 1 : g;
+    const int st = run_two_site_v3<T>(tm, a.gates[g], static_cast<T*>(a.sites), static_cast<T*>(a.msgs), static_cast<const T*>(a.ops),
+                                      static_cast<T*>(a.ws) + (int64_t)blockIdx.x * a3.ws_stride,
+                                      a.sv_out ? a.sv_out + sv_row * a.sv_stride : nullptr, a.normalize, &flag, &bad,
+                                      reinterpret_cast<T*>(dyn_smem3));
+    if (threadIdx.x == 0) a3.status[g] = st;
+    __syncthreads();
+  }
+}
+#endif
+
+}  // namespace applyk3
+}  // namespace bpx

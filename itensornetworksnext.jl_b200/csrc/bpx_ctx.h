@@ -159,6 +159,7 @@ struct bpx_ctx {
 
   // counters
   int64_t n_launches = 0, n_updates = 0, n_sweeps = 0;
+  int64_t n_gates_v3 = 0, n_gates_declined = 0;  // two-site gates applied by version 3 / handed on to versions 1, 2
 
   // grow-only work space of the belief / gate / expectation-value calls (one buffer per role; no cudaMalloc / cudaFree on
   // the call path once warm).  Buffers above WS_KEEP_BYTES are released at the end of the call that needed them.

@@ -195,6 +195,12 @@ class BPXContext:
             o += c
         return out
 
+    def apply_stats(self, reset: bool = False):
+        """(two-site gates applied by the Gram-path kernel, gates it declined and the step-by-step kernel applied)."""
+        out = (C.c_int64 * 2)()
+        self._check(self.lib.bpx_apply_stats(self.h, out, int(bool(reset))))
+        return int(out[0]), int(out[1])
+
     def apply_one_site_gates(self, vertices: Sequence[int], ops: Sequence[np.ndarray], normalize: bool = False):
         v = np.ascontiguousarray(vertices, dtype=np.int64)
         flat = (np.concatenate([cast_to(o, self.dtype, "operator").ravel(order="F") for o in ops]) if len(ops)

@@ -6,7 +6,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../itensornetworksnext.jl_b200/csrc/bpx_apply2.cuh"
+#include "../../itensornetworksnext.jl_b200/csrc/bpx_apply3.cuh"
 #include "../../itensornetworksnext.jl_b200/csrc/bpx_expect2.cuh"
 
 using namespace bpx;
@@ -23,7 +23,7 @@ static Team host_team() {
 template <typename T>
 static int two_site(int z1, int d1, int slot1, const int32_t* dims1, T* site1, const T* msgs1, int z2, int d2, int slot2,
                      const int32_t* dims2, T* site2, const T* msgs2, const T* op, int max_rank, int normalize,
-                     T* msg_out, double* sv_out, int64_t smem_elems = 0) {
+                     T* msg_out, double* sv_out, int64_t smem_elems = 0, int version3 = 0) {
   GateDesc g;
   memset(&g, 0, sizeof(g));
   g.nsides = 2;
@@ -61,7 +61,16 @@ static int two_site(int z1, int d1, int slot1, const int32_t* dims1, T* site1, c
   g.k = k;
   int flag = 0;
   double ssum = 0.0;
-  if (smem_elems > 0) {  // version 2 (bpx_apply2.cuh): `smem_elems` elements of T stand in for the CTA's shared memory
+  int status = 0;
+  if (version3) {  // version 3 (bpx_apply3.cuh): status 1 = the gate was declined (left untouched for the fallback)
+    const int64_t need = applyk3::smem_need(g, Elem<T>::is_complex);
+    if (need == 0) return -2;
+    const applyk3::Layout3 L3 = applyk3::layout3_of(g);
+    std::vector<T> ws((size_t)L3.total + 1), smem((size_t)need);
+    int bad = 0;
+    status = applyk3::run_two_site_v3<T>(host_team(), g, sites.data(), msgs.data(), op, ws.data(), sv_out, normalize, &flag, &bad,
+                                         smem.data());
+  } else if (smem_elems > 0) {  // version 2 (bpx_apply2.cuh): `smem_elems` elements of T stand in for the CTA's shared memory
     if (applyk2::block_rows(g.s[0], smem_elems) == 0 || applyk2::block_rows(g.s[1], smem_elems) == 0) return -2;
     const applyk2::Layout2 L2 = applyk2::layout2_of(g, smem_elems);
     std::vector<T> ws((size_t)L2.total + 1), smem((size_t)smem_elems);
@@ -75,7 +84,7 @@ static int two_site(int z1, int d1, int slot1, const int32_t* dims1, T* site1, c
   memcpy(site1, sites.data() + g.s[0].site_off, sizeof(T) * g.s[0].n);
   memcpy(site2, sites.data() + g.s[1].site_off, sizeof(T) * g.s[1].n);
   memcpy(msg_out, msgs.data() + g.msg12, sizeof(T) * chi * chi);
-  return 0;
+  return status;
 }
 
 template <typename T>
@@ -176,6 +185,18 @@ int apply_host_two_site_v2(int dtype, int z1, int d1, int slot1, const int32_t* 
                             (const double*)msgs2, (const double*)op, max_rank, normalize, (double*)msg_out, sv_out, smem_elems);
   return two_site<c64>(z1, d1, slot1, dims1, (c64*)site1, (const c64*)msgs1, z2, d2, slot2, dims2, (c64*)site2,
                        (const c64*)msgs2, (const c64*)op, max_rank, normalize, (c64*)msg_out, sv_out, smem_elems);
+}
+
+// version 3 (Gram path): 0 = applied, 1 = declined (nothing modified), -2 = shapes not supported
+int apply_host_two_site_v3(int dtype, int z1, int d1, int slot1, const int32_t* dims1, void* site1, const void* msgs1, int z2,
+                           int d2, int slot2, const int32_t* dims2, void* site2, const void* msgs2, const void* op,
+                           int max_rank, int normalize, void* msg_out, double* sv_out) {
+  if (dims1[slot1] != dims2[slot2]) return -1;
+  if (dtype == 0)
+    return two_site<double>(z1, d1, slot1, dims1, (double*)site1, (const double*)msgs1, z2, d2, slot2, dims2, (double*)site2,
+                            (const double*)msgs2, (const double*)op, max_rank, normalize, (double*)msg_out, sv_out, 0, 1);
+  return two_site<c64>(z1, d1, slot1, dims1, (c64*)site1, (const c64*)msgs1, z2, d2, slot2, dims2, (c64*)site2,
+                       (const c64*)msgs2, (const c64*)op, max_rank, normalize, (c64*)msg_out, sv_out, 0, 1);
 }
 
 int apply_host_one_site(int dtype, int z, int d, const int32_t* dims, void* site, const void* msgs, const void* op,

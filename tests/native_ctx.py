@@ -15,13 +15,14 @@ SRC = os.path.join(HERE, "native", "apply_host.cu")
 HDR = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_apply.cuh")
 HDR2 = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_apply2.cuh")
 HDR3 = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_expect2.cuh")
+HDR4 = os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", "bpx_apply3.cuh")
 OUT = os.path.join(HERE, "native", "_build", "libapply_host.so")
 
 
 def build_hostlib() -> ctypes.CDLL:
     """Compile tests/native/apply_host.cu (the device code of csrc/bpx_apply.cuh for the host) if stale; load it."""
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    stale = not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in (SRC, HDR, HDR2, HDR3))
+    stale = not os.path.exists(OUT) or any(os.path.getmtime(f) > os.path.getmtime(OUT) for f in (SRC, HDR, HDR2, HDR3, HDR4))
     if stale:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",

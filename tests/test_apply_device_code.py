@@ -122,11 +122,13 @@ def two_site(hostlib, variant, dtype, a1, a2, op, max_rank, normalize, msg_out, 
             ptr(a2[5]), ptr(op), int(max_rank), int(normalize), ptr(msg_out), sv.ctypes.data_as(P))
     if variant == "v1":
         return hostlib.apply_host_two_site(*args)
+    if variant == "v3":
+        return hostlib.apply_host_two_site_v3(*args)
     smem = smem_for([(a[0], a[1], a[2], a[3]) for a in (a1, a2)], variant[1])
     return hostlib.apply_host_two_site_v2(*args, ctypes.c_int64(smem))
 
 
-VARIANTS = ["v1", ("v2", 1), ("v2", 3), ("v2", 8), ("v2", 4096)]
+VARIANTS = ["v1", ("v2", 1), ("v2", 3), ("v2", 8), ("v2", 4096), "v3"]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -222,7 +224,7 @@ def test_two_site_gate_matches_oracle(hostlib, variant, dtype, chi_bond, chi_oth
     assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
 
 
-@pytest.mark.parametrize("variant", ["v1", ("v2", 1), ("v2", 64)], ids=str)
+@pytest.mark.parametrize("variant", ["v1", ("v2", 1), ("v2", 64), "v3"], ids=str)
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_two_site_gate_on_a_leaf_pair(hostlib, variant, dtype):
     """Both vertices have no external legs (a 2-site chain): rows = 1, no reflectors, no gauges."""
@@ -289,7 +291,7 @@ def test_two_site_gate_cfg5_shape(hostlib, variant, dtype):
     assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
 
 
-@pytest.mark.parametrize("variant", ["v1", ("v2", 224), ("v2", 96)], ids=str)
+@pytest.mark.parametrize("variant", ["v1", ("v2", 224), ("v2", 96), "v3"], ids=str)
 def test_identity_gate_at_the_true_cfg5_shape(hostlib, variant):
     """BASELINE config 5's bulk shape for real: degree 4, chi = 16, d = 2 (1 MiB per tensor, 4096 x 32 matrix view).  The
     identity gate with the full rank kept must leave the pair invariant (checked through random probes on the external
@@ -363,7 +365,7 @@ def run_pair(hostlib, variant, dtype, adj, state, env, o, max_rank, normalize):
     return got, sv
 
 
-@pytest.mark.parametrize("variant", ["v1", ("v2", 32), ("v2", 100000)], ids=str)
+@pytest.mark.parametrize("variant", ["v1", ("v2", 32), ("v2", 100000), "v3"], ids=str)
 @pytest.mark.parametrize("dtype,z,chi,d", [(np.float64, 6, 4, 2), (np.complex128, 3, 16, 2), (np.float64, 4, 8, 2),
                                           (np.complex128, 4, 8, 2)], ids=["cfg4", "cfg3", "cfg2", "cfg2c"])
 def test_two_site_gate_baseline_shapes(hostlib, variant, dtype, z, chi, d):
@@ -415,7 +417,7 @@ def test_two_site_gate_with_ill_conditioned_environments(hostlib, variant, decad
     assert np.abs(x - y).max() <= (20 * (err_oracle + err_device) + 1e-9) * np.abs(y).max()
 
 
-@pytest.mark.parametrize("variant", ["v1", ("v2", 16)], ids=str)
+@pytest.mark.parametrize("variant", ["v1", ("v2", 16), "v3"], ids=str)
 def test_two_site_gate_with_degenerate_singular_values(hostlib, variant):
     """A gate that leaves an exactly degenerate spectrum on the bond (identity on a product state of Bell-like pairs):
     any basis of the degenerate subspace is a valid answer; the pair product and S are unique."""
@@ -519,6 +521,95 @@ def test_edge_expect_is_exact_on_a_tree(oracle, hostlib, dtype):
         opsi = np.tensordot(o, moved, axes=([2, 3], [0, 1]))
         exact = np.vdot(moved.ravel(), opsi.ravel()) / np.vdot(psi, psi)
         assert np.isclose(num[0] / den[0], exact, rtol=1e-10, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# version 3 (the Gram path, csrc/bpx_apply3.cuh): what it declines, and how accurate it is where it does not
+# ---------------------------------------------------------------------------------------------------------------
+def run_pair_v3(hostlib, dtype, adj, state, env, o, max_rank, normalize):
+    """-> (status, new state or None, singular values); a declined gate (status 1) must leave every input untouched."""
+    a1, a2 = side_args(state, env, adj, 0, 1), side_args(state, env, adj, 1, 0)
+    before = (a1[4].copy(), a2[4].copy())
+    chi_b = int(a1[3][a1[2]])
+    msg_out, sv = np.zeros(chi_b * chi_b, dtype=dtype), np.zeros(chi_b)
+    op = fcopy(o).ravel(order="F").copy()
+    rc = two_site(hostlib, "v3", dtype, a1, a2, op, max_rank, normalize, msg_out, sv)
+    assert rc in (0, 1)
+    if rc == 1:
+        assert np.array_equal(a1[4], before[0]) and np.array_equal(a2[4], before[1]) and not msg_out.any()
+        return 1, None, sv
+    got = dict(state)
+    got[0] = (a1[4].reshape(state[0][0].shape, order="F"), state[0][1])
+    got[1] = (a2[4].reshape(state[1][0].shape, order="F"), state[1][1])
+    return 0, got, sv
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_v3_declines_a_rank_deficient_message(hostlib, dtype):
+    """The reference projects on the support of a rank-deficient message (pinv, apply_operators.jl:250-253); the Gram
+    shortcut assumes X^-1 X = 1, so version 3 must hand such a gate back untouched (the caller re-runs it on version 2)."""
+    rng = np.random.default_rng(77)
+    adj, state, env = star_pair(rng, dtype, 4, 4, 2)
+    f = randn(rng, dtype, (3, 4))
+    env[(2, 0)] = (f.conj().T @ f).astype(dtype)  # rank 3 of 4
+    o = randn(rng, dtype, (2, 2, 2, 2))
+    rc, got, _ = run_pair_v3(hostlib, dtype, adj, state, env, o, 4, True)
+    assert rc == 1
+    # an indefinite message is declined too (the reference keeps its positive part only)
+    adj, state, env = star_pair(rng, dtype, 3, 3, 2)
+    env[(2, 0)] = np.diag([1.0, 0.5, -0.2]).astype(dtype)
+    rc, got, _ = run_pair_v3(hostlib, dtype, adj, state, env, o, 3, False)
+    assert rc == 1
+
+
+@pytest.mark.parametrize("decades", [2, 4, 6, 10, 13])
+def test_v3_on_ill_conditioned_environments(hostlib, decades):
+    """Graded message spectra: version 3 either declines the gate (conditioning of the Gram matrix, COND_MIN) or is as
+    accurate as the identity-gate yardstick demands (same bounds as versions 1 / 2 above)."""
+    rng = np.random.default_rng(decades)
+    dtype = np.complex128
+    adj, state, env = star_pair(rng, dtype, 3, 4, 2, msg=graded_message(decades))
+    names = (("s", 0), ("s", 1))
+    ident = np.eye(4).reshape(2, 2, 2, 2).astype(dtype)
+    y0 = bond_product(state, 0, 1)
+    rc, got, _ = run_pair_v3(hostlib, dtype, adj, state, env, ident, 4, False)
+    if decades >= 10:
+        assert rc == 1  # three messages of 10 decades each: far beyond what a Gram matrix resolves
+        return
+    if rc == 1:
+        return
+    err = np.abs(bond_product(got, 0, 1) - y0).max() / np.abs(y0).max()
+    assert err <= {2: 1e-12, 4: 1e-10, 6: 1e-8}[decades], err
+    o = randn(rng, dtype, (2, 2, 2, 2))
+    want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=4, normalize=True)
+    rc, got, sv = run_pair_v3(hostlib, dtype, adj, state, env, o, 4, True)
+    assert rc == 0
+    assert np.allclose(sv, np.diag(want_env[(0, 1)]).real, rtol=1e-8, atol=1e-12)
+    x, y = bond_product(got, 0, 1), bond_product(want_state, 0, 1)
+    assert np.abs(x - y).max() <= 1e-7 * np.abs(y).max()
+
+
+def test_v3_fuzz(hostlib):
+    """Random shapes like test_two_site_gate_fuzz: version 3 takes every well-conditioned case and agrees with the oracle."""
+    rng = np.random.default_rng(4048)
+    worst, applied = 0.0, 0
+    for it in range(80):
+        dtype = DTYPES[it % 2]
+        z, chi, chib, d = int(rng.integers(1, 5)), int(rng.integers(1, 5)), int(rng.integers(1, 6)), int(rng.integers(1, 4))
+        adj, state, env = star_pair(rng, dtype, z, chi, d, chi_bond=chib)
+        o = randn(rng, dtype, (d, d, d, d))
+        k, norm = int(rng.integers(1, chib + 1)), bool(rng.integers(0, 2))
+        names = (("s", 0), ("s", 1))
+        want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=k, normalize=norm)
+        s_want = np.diag(want_env[(0, 1)]).real
+        y = bond_product(want_state, 0, 1)
+        rc, got, sv = run_pair_v3(hostlib, dtype, adj, state, env, o, k, norm)
+        if rc == 0:
+            applied += 1
+            worst = max(worst, np.abs(sv[:len(s_want)] - s_want).max() / s_want.max(),
+                        np.abs(bond_product(got, 0, 1) - y).max() / np.abs(y).max())
+    assert applied >= 76, applied  # random_network's messages are well conditioned (F^H F with F = randn + 1.5 I)
+    assert worst < 1e-9, worst
 
 
 def test_two_site_gate_fuzz(hostlib):

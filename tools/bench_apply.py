@@ -74,12 +74,14 @@ def main():
                 times.append(dt)
                 gates += len(es)
         res, _ = ctx.sweep(1, 0.0, True)
+        stats = ctx.apply_stats()
     out = {
         "metric": "bp_simple_update_gates_per_s", "value": gates / sum(times), "unit": "gates/s",
         "config": {"workload": f"{nx}x{ny} square-lattice PEPS, chi={a.chi}, d={a.d}, {a.dtype}; layers = the four matchings",
                    "gates_per_layer": [len(l) for l in layers], "layers_timed": a.layers,
                    "timing": "host wall clock around the synchronous C-ABI call"},
         "ms_per_layer": 1e3 * sum(times) / len(times), "residual_of_next_sweep": res,
+        "gates_on_gram_kernel": stats[0], "gates_declined_to_stepwise_kernel": stats[1],
     }
     if a.oracle_gates > 0:  # CPU baseline: the numpy oracle of the reference algorithm, one thread, a few gates of layer 0
         from oracle import apply_oracle as A
