@@ -36,6 +36,7 @@ using namespace bpx::applyk;
 
 constexpr int PC = 32;               // padded column count of the tiles; the fast path takes sides with cols <= PC
 constexpr int TRG = 128;             // rows per tile of the Gram pass
+constexpr int PCP = PC + 2;          // row stride of the Gram tiles: 16-byte aligned rows, stores two wavefronts per warp
 constexpr double COND_MIN = 1e-10;   // smallest kept eigenvalue of G relative to the largest
 constexpr double PIVOT_MIN = 1e-12;  // smallest Cholesky pivot of a message relative to its largest diagonal entry
 constexpr int MAXDIM = 16;           // largest external link dimension (a fibre lives in registers)
@@ -51,6 +52,7 @@ struct Layout3 {
   int64_t y[2];         // Y (cols x d k) then W = R^+ Y (cols x PC, zero padded)
   int64_t w[2];
   int64_t theta[3], sig, order;
+  int64_t tab[2];       // int32 address tables per side: rowtab[rows], coltab[PC]
   int64_t total;
 };
 
@@ -81,6 +83,7 @@ __host__ __device__ inline Layout3 layout3_of(const GateDesc& g) {
   for (int i = 0; i < 3; ++i) { L.theta[i] = o; o += m * n; }
   L.sig = o; o += n;
   L.order = o; o += n;
+  for (int a = 0; a < 2; ++a) { L.tab[a] = o; o += (g.s[a].rows + PC) / 2 + 2; }  // int32 entries in slots of >= 8 bytes
   L.total = (o + 1) & ~(int64_t)1;  // keep every gate's work space 16-byte aligned for both element types
   return L;
 }
@@ -99,10 +102,13 @@ __host__ __device__ inline int64_t smem_need(const GateDesc& g, bool cplx) {
         hsum += (int64_t)s.dim[i] * s.dim[i];
       }
     const int64_t cb = (!cplx && (s.cols % 2 == 0)) ? 2 : 1;
-    const int64_t absorb = cb * s.rows + hsum;                 // column batch + the messages
-    const int64_t gram = 2 * (int64_t)TRG * PC + TRG;          // A tile, T tile (the reduction re-uses them), row table
+    int64_t dim0 = 1;
+    for (int i = 0; i < s.z; ++i)
+      if (i != s.bond_slot) { dim0 = s.dim[i]; break; }
+    const int64_t absorb = cb * (s.rows + s.rows / dim0) + 2 + hsum;  // padded column batch + the messages
+    const int64_t gram = 2 * (int64_t)TRG * PCP;               // A tile, T tile (the reduction re-uses them)
     const int64_t trf = cplx ? 128 : 256;
-    const int64_t fin = trf * PC + (int64_t)PC * PC + trf;     // A tile, W, row table
+    const int64_t fin = (trf + 1) * PC + (int64_t)PC * PC;     // A tile (padded column stride), W
     need = need > absorb ? need : absorb;
     need = need > gram ? need : gram;
     need = need > fin ? need : fin;
@@ -155,39 +161,60 @@ __host__ __device__ __forceinline__ int64_t rowaddr(const Walk& w, int64_t row) 
 }
 __host__ __device__ __forceinline__ int64_t coladdr(const Walk& w, int col) { return (col % w.d) + (col / w.d) * w.bstride; }
 
-// rows [row0, row0 + tr) x all columns of the matrix view -> tile[r * rs + c * cs]; rows beyond the matrix and columns
-// cols..PC-1 are zero.  `rtab`: tr int64 slots of shared memory (canonical row offsets, computed once per row).
+// Address tables of one side (global work space, L1 / L2 resident): the hot loops look addresses up instead of
+// decomposing indices.  rowtab[row] = canonical offset of the row, coltab[c] = offset of the column (0 for c >= cols).
+struct Tabs {
+  const int32_t* row;
+  const int32_t* col;
+  bool col_fast;  // the columns (s, bond) are contiguous in the canonical layout (bond leg first); else (s, first row leg)
+};
 template <typename T>
-__host__ __device__ void load_tile(const Team& tm, const Side& sd, const Walk& wk, const T* src, int64_t row0, int tr, T* tile,
-                                   int rs, int cs, int64_t* rtab) {
-  using E = Elem<T>;
-  for (int r = tm.tid(); r < tr; r += tm.nt()) rtab[r] = (row0 + r < sd.rows) ? rowaddr(wk, row0 + r) : -1;
+__host__ __device__ Tabs build_tabs(const Team& tm, const Side& sd, const Walk& wk, T* slot) {
+  int32_t* rt = reinterpret_cast<int32_t*>(slot);
+  int32_t* ct = rt + sd.rows;
+  for (int64_t r = tm.tid(); r < sd.rows; r += tm.nt()) rt[r] = (int32_t)rowaddr(wk, r);
+  for (int c = tm.tid(); c < PC; c += tm.nt()) ct[c] = c < sd.cols ? (int32_t)coladdr(wk, c) : 0;
   tm.sync();
+  Tabs t;
+  t.row = rt;
+  t.col = ct;
+  t.col_fast = wk.next == 0 || wk.bstride < wk.rstride[0];
+  return t;
+}
+
+// rows [row0, row0 + tr) x all columns of the matrix view -> tile[r * rs + c * cs]; rows beyond the matrix and columns
+// cols..PC-1 are zero.  Global reads follow the canonical layout's contiguous direction.
+template <typename T>
+__host__ __device__ void load_tile(const Team& tm, const Side& sd, const Tabs& tb, const T* src, int64_t row0, int tr, T* tile,
+                                   int rs, int cs) {
+  using E = Elem<T>;
   const int cols = sd.cols;
-  // order of the flat loop: the faster index is the one that is contiguous in the canonical layout
-  const bool col_fast = wk.next == 0 || wk.bstride < wk.rstride[0];
-  const int d = wk.d, nb = cols / d;
-  const int total = tr * PC;
-  for (int i = tm.tid(); i < total; i += tm.nt()) {
-    int r, c;
-    if (col_fast) {
-      c = i % PC;
-      r = i / PC;
-    } else {  // (s, r, bond): s fastest, then the row, then the bond index; padding columns last
-      if (i < tr * cols) {
-        const int s = i % d, rest = i / d;
-        r = rest % tr;
-        c = s + d * (rest / tr);
+  const int nrows = (int)((sd.rows - row0) < tr ? (sd.rows - row0) : tr);
+  if (tb.col_fast) {
+    for (int i = tm.tid(); i < tr * PC; i += tm.nt()) {
+      const int c = i & (PC - 1), r = i / PC;
+      T v = E::zero();
+      if (c < cols && r < nrows) v = src[tb.row[row0 + r] + tb.col[c]];
+      tile[r * rs + c * cs] = v;
+    }
+  } else {
+    const int d = sd.d, nb = cols / d;
+    for (int pr = tm.tid(); pr < d * tr; pr += tm.nt()) {  // (s, row) pairs, s fastest: contiguous in memory
+      const int sx = pr % d, r = pr / d;
+      if (r < nrows) {
+        const T* base = src + tb.row[row0 + r];
+        for (int b = 0; b < nb; ++b) {
+          const int c = sx + d * b;
+          tile[r * rs + c * cs] = base[tb.col[c]];
+        }
       } else {
-        const int j = i - tr * cols;
-        r = j % tr;
-        c = cols + j / tr;
+        for (int b = 0; b < nb; ++b) tile[r * rs + (sx + d * b) * cs] = E::zero();
       }
     }
-    (void)nb;
-    T v = E::zero();
-    if (c < cols && rtab[r] >= 0) v = src[rtab[r] + coladdr(wk, c)];
-    tile[(int64_t)r * rs + (int64_t)c * cs] = v;
+    for (int i = tm.tid(); i < tr * (PC - cols); i += tm.nt()) {
+      const int r = i % tr, c = cols + i / tr;
+      tile[r * rs + c * cs] = E::zero();
+    }
   }
   tm.sync();
 }
@@ -261,93 +288,118 @@ __host__ __device__ void message_check(const Team& tm, const Side& sd, const T* 
   tm.sync();
 }
 
+// division by a run-time constant that is usually a power of two (link dimensions): a shift when it is
+struct FastDiv {
+  int d, sh;
+  __host__ __device__ explicit FastDiv(int dd) : d(dd), sh(-1) {
+    if (dd > 0 && (dd & (dd - 1)) == 0) {
+      sh = 0;
+      while ((1 << sh) < dd) ++sh;
+    }
+  }
+  __host__ __device__ __forceinline__ int div(int x) const { return sh >= 0 ? (x >> sh) : x / d; }
+  __host__ __device__ __forceinline__ int mod(int x) const { return sh >= 0 ? (x & (d - 1)) : x % d; }
+};
+
 // ---- absorb: T[:, c] = (M_1 x M_2 x ..) A[:, c], CB columns at a time, in place in shared memory ---------------------------
 // A thread owns whole fibres (the chi elements along one leg) of all CB columns: inputs to registers, outputs back to the
 // same places -- no ping-pong buffer; every matrix element it loads (a broadcast) feeds CB FMAs.
 template <typename T, int CB, int CHI>
-__host__ __device__ __forceinline__ void absorb_leg_fixed(const Team& tm, T* col, int64_t rows, int64_t st, const T* x) {
+__host__ __device__ __forceinline__ void absorb_leg_fixed(const Team& tm, T* col, int rows, int prow, int st, int pad0, const T* x) {
   using E = Elem<T>;
-  const int64_t nf = rows / CHI;
-  for (int64_t f = tm.tid(); f < nf; f += tm.nt()) {
-    const int64_t lo = f % st, hi = f / st, base = hi * st * CHI + lo;
+  const int nf = rows / CHI;
+  const int pst = st >= pad0 ? st + st / pad0 : st;  // stride of the leg in the padded column (see absorb_side)
+  const FastDiv dst(st), dpad(pad0);
+  for (int f = tm.tid(); f < nf; f += tm.nt()) {
+    const int lo = dst.mod(f), hi = dst.div(f), base0 = hi * st * CHI + lo, base = base0 + dpad.div(base0);
     T v[CB][CHI];
 #pragma unroll
     for (int b = 0; b < CB; ++b)
 #pragma unroll
-      for (int l = 0; l < CHI; ++l) v[b][l] = col[b * rows + base + l * st];
+      for (int l = 0; l < CHI; ++l) v[b][l] = col[b * prow + base + l * pst];
 #pragma unroll 1
     for (int g = 0; g < CHI; ++g) {
       T acc[CB];
 #pragma unroll
       for (int b = 0; b < CB; ++b) acc[b] = E::zero();
+      // x is Hermitian: x[g, l] = conj(x[l, g]), and x[l + CHI g] is contiguous in l (vector loads, one broadcast each)
+      const T* xr = x + CHI * g;
 #pragma unroll
       for (int l = 0; l < CHI; ++l) {
-        const T xv = x[g + CHI * l];
+        const T xv = E::conj(xr[l]);
 #pragma unroll
         for (int b = 0; b < CB; ++b) acc[b] = E::fma(xv, v[b][l], acc[b]);
       }
 #pragma unroll
-      for (int b = 0; b < CB; ++b) col[b * rows + base + g * st] = acc[b];
+      for (int b = 0; b < CB; ++b) col[b * prow + base + g * pst] = acc[b];
     }
   }
   tm.sync();
 }
 template <typename T, int CB>
-__host__ __device__ void absorb_leg_any(const Team& tm, T* col, int64_t rows, int64_t st, int chi, const T* x) {
+__host__ __device__ void absorb_leg_any(const Team& tm, T* col, int rows, int prow, int st, int pad0, int chi, const T* x) {
   using E = Elem<T>;
-  const int64_t nf = rows / chi;
-  for (int64_t f = tm.tid(); f < nf; f += tm.nt()) {
-    const int64_t lo = f % st, hi = f / st, base = hi * st * chi + lo;
+  const int nf = rows / chi;
+  const int pst = st >= pad0 ? st + st / pad0 : st;
+  const FastDiv dst(st), dpad(pad0);
+  for (int f = tm.tid(); f < nf; f += tm.nt()) {
+    const int lo = dst.mod(f), hi = dst.div(f), base0 = hi * st * chi + lo, base = base0 + dpad.div(base0);
     for (int b = 0; b < CB; ++b) {
       T v[MAXDIM], o[MAXDIM];
-      for (int l = 0; l < chi; ++l) v[l] = col[b * rows + base + l * st];
+      for (int l = 0; l < chi; ++l) v[l] = col[b * prow + base + l * pst];
       for (int g = 0; g < chi; ++g) {
         T acc = E::zero();
         for (int l = 0; l < chi; ++l) acc = E::fma(x[g + chi * l], v[l], acc);
         o[g] = acc;
       }
-      for (int g = 0; g < chi; ++g) col[b * rows + base + g * st] = o[g];
+      for (int g = 0; g < chi; ++g) col[b * prow + base + g * pst] = o[g];
     }
   }
   tm.sync();
 }
 template <typename T, int CB>
-__host__ __device__ void absorb_leg(const Team& tm, T* col, int64_t rows, int64_t st, int chi, const T* x) {
+__host__ __device__ void absorb_leg(const Team& tm, T* col, int rows, int prow, int st, int pad0, int chi, const T* x) {
   switch (chi) {
-    case 2: absorb_leg_fixed<T, CB, 2>(tm, col, rows, st, x); break;
-    case 4: absorb_leg_fixed<T, CB, 4>(tm, col, rows, st, x); break;
-    case 8: absorb_leg_fixed<T, CB, 8>(tm, col, rows, st, x); break;
-    case 16: absorb_leg_fixed<T, CB, 16>(tm, col, rows, st, x); break;
-    default: absorb_leg_any<T, CB>(tm, col, rows, st, chi, x);
+    case 2: absorb_leg_fixed<T, CB, 2>(tm, col, rows, prow, st, pad0, x); break;
+    case 4: absorb_leg_fixed<T, CB, 4>(tm, col, rows, prow, st, pad0, x); break;
+    case 8: absorb_leg_fixed<T, CB, 8>(tm, col, rows, prow, st, pad0, x); break;
+    case 16: absorb_leg_fixed<T, CB, 16>(tm, col, rows, prow, st, pad0, x); break;
+    default: absorb_leg_any<T, CB>(tm, col, rows, prow, st, pad0, chi, x);
   }
 }
 
+// The gathered column is padded by one element after every rdim[0] rows (index r + r / rdim[0]): the fibres of the first leg
+// then start an odd number of elements apart (no bank conflicts; unpadded, a warp's 32 fibres of 16 doubles share one
+// bank), and every other leg keeps a uniform stride st + st / rdim[0].
 template <typename T, int CB>
-__host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk& wk, const T* a, const T* H, T* tout, T* smem) {
-  T* col = smem;                       // CB * rows
-  T* hs = smem + (int64_t)CB * sd.rows;  // the messages
+__host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk& wk, const Tabs& tb, const T* a, const T* H, T* tout,
+                                     T* smem) {
+  const int rows = (int)sd.rows;
+  const int pad0 = wk.next > 0 ? wk.rdim[0] : 1;
+  const int prow = rows + rows / pad0;
+  const FastDiv dpad(pad0);
+  T* col = smem;                             // CB * prow
+  T* hs = smem + (((int64_t)CB * prow + 1) & ~(int64_t)1);  // the messages (16-byte aligned)
   const int64_t hn = herm_elems(sd);
   for (int64_t i = tm.tid(); i < hn; i += tm.nt()) hs[i] = H[i];
   tm.sync();
-  const int64_t rows = sd.rows;
   for (int c0 = 0; c0 < sd.cols; c0 += CB) {
-    for (int64_t i = tm.tid(); i < rows * CB; i += tm.nt()) {
-      const int b = (int)(i % CB);
-      const int64_t r = i / CB;
-      col[b * rows + r] = a[rowaddr(wk, r) + coladdr(wk, c0 + b)];
+    for (int i = tm.tid(); i < rows * CB; i += tm.nt()) {
+      const int b = i % CB, r = i / CB;
+      col[b * prow + r + dpad.div(r)] = a[tb.row[r] + tb.col[c0 + b]];
     }
     tm.sync();
-    int64_t st = 1, off = 0;
+    int st = 1;
+    int64_t off = 0;
     for (int k = 0; k < wk.next; ++k) {
       const int chi = wk.rdim[k];
-      absorb_leg<T, CB>(tm, col, rows, st, chi, hs + off);
+      absorb_leg<T, CB>(tm, col, rows, prow, st, pad0, chi, hs + off);
       st *= chi;
       off += (int64_t)chi * chi;
     }
-    for (int64_t i = tm.tid(); i < rows * CB; i += tm.nt()) {
-      const int b = (int)(i % CB);
-      const int64_t r = i / CB;
-      tout[rowaddr(wk, r) + coladdr(wk, c0 + b)] = col[b * rows + r];
+    for (int i = tm.tid(); i < rows * CB; i += tm.nt()) {
+      const int b = i % CB, r = i / CB;
+      tout[tb.row[r] + tb.col[c0 + b]] = col[b * prow + r + dpad.div(r)];
     }
     tm.sync();
   }
@@ -358,12 +410,11 @@ __host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk&
 // an 8 x 4 lane grid accumulates the 4 x TJ block G[4 i .., TJ (j + 4 pass) ..]: per row 4 + TJ operand loads (broadcast
 // within the lane groups) feed 4 TJ FMAs.  The nw partial tiles are summed through shared memory at the end.
 template <typename T, int TJ>
-__host__ __device__ void gram_side(const Team& tm, const Side& sd, const Walk& wk, const T* a, const T* t, T* G, T* smem) {
+__host__ __device__ void gram_side(const Team& tm, const Side& sd, const Tabs& tb, const T* a, const T* t, T* G, T* smem) {
   using E = Elem<T>;
   constexpr int NPASS = PC / (4 * TJ);
   T* sA = smem;
-  T* sT = smem + (int64_t)TRG * PC;
-  int64_t* rtab = reinterpret_cast<int64_t*>(smem + 2 * (int64_t)TRG * PC);
+  T* sT = smem + (int64_t)TRG * PCP;
   const int L = tm.lanes();
   const int cols = sd.cols;
   for (int pass = 0; pass < NPASS; ++pass) {
@@ -378,8 +429,8 @@ __host__ __device__ void gram_side(const Team& tm, const Side& sd, const Walk& w
     std::vector<T> hacc((size_t)32 * 4 * TJ, E::zero());
 #endif
     for (int64_t row0 = 0; row0 < sd.rows; row0 += TRG) {
-      load_tile<T>(tm, sd, wk, a, row0, TRG, sA, PC, 1, rtab);
-      load_tile<T>(tm, sd, wk, t, row0, TRG, sT, PC, 1, rtab);
+      load_tile<T>(tm, sd, tb, a, row0, TRG, sA, PCP, 1);
+      load_tile<T>(tm, sd, tb, t, row0, TRG, sT, PCP, 1);
       const int nr = (int)((sd.rows - row0) < TRG ? (sd.rows - row0) : TRG);
 #ifdef __CUDA_ARCH__
       const int li = tm.lane >> 2, lj = tm.lane & 3;
@@ -387,10 +438,35 @@ __host__ __device__ void gram_side(const Team& tm, const Side& sd, const Walk& w
       const T* pt = sT + TJ * (lj + 4 * pass);
       for (int r = tm.wid; r < nr; r += tm.nw) {
         T av[4], tv[TJ];
+        if constexpr (!E::is_complex) {  // rows of the tiles are 16-byte aligned (PCP even)
+          const double2* a2 = reinterpret_cast<const double2*>(pa + r * PCP);
+          const double2* t2 = reinterpret_cast<const double2*>(pt + r * PCP);
 #pragma unroll
-        for (int x = 0; x < 4; ++x) av[x] = E::conj(pa[r * PC + x]);
+          for (int x = 0; x < 2; ++x) {
+            const double2 q = a2[x];
+            av[2 * x] = q.x;
+            av[2 * x + 1] = q.y;
+          }
 #pragma unroll
-        for (int y = 0; y < TJ; ++y) tv[y] = pt[r * PC + y];
+          for (int y = 0; y < TJ / 2; ++y) {
+            const double2 q = t2[y];
+            tv[2 * y] = q.x;
+            tv[2 * y + 1] = q.y;
+          }
+        } else {
+          const double2* a2 = reinterpret_cast<const double2*>(pa + r * PCP);
+          const double2* t2 = reinterpret_cast<const double2*>(pt + r * PCP);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const double2 q = a2[x];
+            av[x] = E::conj(*reinterpret_cast<const T*>(&q));
+          }
+#pragma unroll
+          for (int y = 0; y < TJ; ++y) {
+            const double2 q = t2[y];
+            tv[y] = *reinterpret_cast<const T*>(&q);
+          }
+        }
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -403,7 +479,7 @@ __host__ __device__ void gram_side(const Team& tm, const Side& sd, const Walk& w
           for (int x = 0; x < 4; ++x)
             for (int y = 0; y < TJ; ++y) {
               T& o = hacc[(size_t)(role * 4 + x) * TJ + y];
-              o = E::fma(E::conj(sA[r * PC + 4 * li + x]), sT[r * PC + TJ * (lj + 4 * pass) + y], o);
+              o = E::fma(E::conj(sA[r * PCP + 4 * li + x]), sT[r * PCP + TJ * (lj + 4 * pass) + y], o);
             }
       }
       (void)L;
@@ -592,18 +668,18 @@ __host__ __device__ void gram_factor(const Team& tm, int cols, int rank_max, con
 
 // ---- final pass: A'[row, c'] = sum_c A[row, c] W[c, c'] in place -----------------------------------------------------------
 template <typename T, int TRF, int RT, int NO>
-__host__ __device__ void final_side(const Team& tm, const Side& sd, const Walk& wk, T* a, const T* W, T* smem) {
+__host__ __device__ void final_side(const Team& tm, const Side& sd, const Tabs& tb, T* a, const T* W, T* smem) {
   using E = Elem<T>;
-  T* sA = smem;                                  // [c][TRF]
-  T* sW = smem + (int64_t)TRF * PC;              // [c][PC]
-  int64_t* rtab = reinterpret_cast<int64_t*>(sW + (int64_t)PC * PC);
+  constexpr int TRFP = TRF + 1;                  // padded column stride: conflict-free stores in both load orders
+  T* sA = smem;                                  // [c][TRFP]
+  T* sW = smem + (int64_t)TRFP * PC;             // [c][PC]
   for (int i = tm.tid(); i < PC * PC; i += tm.nt()) sW[i] = W[i];
   tm.sync();
   const int cols = sd.cols;
   constexpr int RG = TRF / RT;                   // row groups: thread rows rg, rg + RG, ..
   constexpr int OG = PC / NO;                    // output groups
   for (int64_t row0 = 0; row0 < sd.rows; row0 += TRF) {
-    load_tile<T>(tm, sd, wk, a, row0, TRF, sA, 1, TRF, rtab);
+    load_tile<T>(tm, sd, tb, a, row0, TRF, sA, 1, TRFP);
     for (int item = tm.tid(); item < RG * OG; item += tm.nt()) {
       const int rg = item % RG, og = item / RG;
       if (og * NO >= cols) continue;
@@ -615,24 +691,33 @@ __host__ __device__ void final_side(const Team& tm, const Side& sd, const Walk& 
       for (int c = 0; c < cols; ++c) {
         T av[RT];
 #pragma unroll
-        for (int x = 0; x < RT; ++x) av[x] = sA[c * TRF + rg + x * RG];
+        for (int x = 0; x < RT; ++x) av[x] = sA[c * TRFP + rg + x * RG];
         const T* pw = sW + c * PC + og * NO;
+        T wv[NO];
+#ifdef __CUDA_ARCH__
+        {  // 16-byte aligned rows of W: vector loads, one broadcast each
+          const double2* p2 = reinterpret_cast<const double2*>(pw);
+          double2* w2 = reinterpret_cast<double2*>(wv);
 #pragma unroll
-        for (int y = 0; y < NO; ++y) {
-          const T wv = pw[y];
-#pragma unroll
-          for (int x = 0; x < RT; ++x) acc[x][y] = E::fma(av[x], wv, acc[x][y]);
+          for (int y = 0; y < (int)(NO * sizeof(T) / 16); ++y) w2[y] = p2[y];
         }
+#else
+        for (int y = 0; y < NO; ++y) wv[y] = pw[y];
+#endif
+#pragma unroll
+        for (int y = 0; y < NO; ++y)
+#pragma unroll
+          for (int x = 0; x < RT; ++x) acc[x][y] = E::fma(av[x], wv[y], acc[x][y]);
       }
 #pragma unroll
       for (int x = 0; x < RT; ++x) {
         const int r = rg + x * RG;
-        const int64_t ra = rtab[r];
-        if (ra < 0) continue;
+        if (row0 + r >= sd.rows) continue;
+        const int64_t ra = tb.row[row0 + r];
 #pragma unroll
         for (int y = 0; y < NO; ++y) {
           const int cp = og * NO + y;
-          if (cp < cols) a[ra + coladdr(wk, cp)] = acc[x][y];
+          if (cp < cols) a[ra + tb.col[cp]] = acc[x][y];
         }
       }
     }
@@ -649,18 +734,19 @@ __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* s
   const Layout3 L = layout3_of(gd);
   if (tm.tid() == 0) *bad = 0;
   tm.sync();
-  Walk wk[2];
+  Tabs tb[2];
   for (int a = 0; a < 2; ++a) {
     const Side& sd = gd.s[a];
-    wk[a] = walk_of(sd);
+    const Walk wka = walk_of(sd);
+    tb[a] = build_tabs<T>(tm, sd, wka, w + L.tab[a]);
     message_check<T>(tm, sd, msgs, w + L.h[a], smem, bad);
     if (*bad) return 1;
     const T* A = sites + sd.site_off;
     if (!CPLX && sd.cols % 2 == 0)
-      absorb_side<T, 2>(tm, sd, wk[a], A, w + L.h[a], w + L.t, smem);
+      absorb_side<T, 2>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.t, smem);
     else
-      absorb_side<T, 1>(tm, sd, wk[a], A, w + L.h[a], w + L.t, smem);
-    gram_side<T, CPLX ? 4 : 8>(tm, sd, wk[a], A, w + L.t, w + L.g[a], smem);
+      absorb_side<T, 1>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.t, smem);
+    gram_side<T, CPLX ? 4 : 8>(tm, sd, tb[a], A, w + L.t, w + L.g[a], smem);
     gram_factor<T>(tm, sd.cols, sd.nref, w + L.g[a], w + L.gb[a], reinterpret_cast<double*>(w + L.ev[a]), w + L.r[a], w + L.rinv[a], smem,
                    flag, bad);
     if (*bad) return 1;
@@ -771,9 +857,9 @@ __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* s
     const Side& sd = gd.s[a];
     T* A = sites + sd.site_off;
     if (CPLX)
-      final_side<T, 128, 1, 8>(tm, sd, wk[a], A, w + L.w[a], smem);
+      final_side<T, 128, 1, 8>(tm, sd, tb[a], A, w + L.w[a], smem);
     else
-      final_side<T, 256, 2, 16>(tm, sd, wk[a], A, w + L.w[a], smem);
+      final_side<T, 256, 2, 16>(tm, sd, tb[a], A, w + L.w[a], smem);
   }
   for (int i = tm.tid(); i < chi * chi; i += tm.nt()) {
     const int r = i % chi, c = i / chi;

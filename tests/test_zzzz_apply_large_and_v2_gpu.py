@@ -67,12 +67,14 @@ def test_v2_matches_v1(monkeypatch, dtype, lattice, chi, max_rank, normalize):
     edges = matching(p.ga, rng)
     ops = [randn(rng, dtype, (2, 2, 2, 2)) for _ in edges]
     results = []
+    monkeypatch.setenv("BPX_APPLY_V3", "0")  # versions 1 / 2 are what version 3 hands its declined gates to
     for v2 in ("0", "1"):
         monkeypatch.setenv("BPX_APPLY_V2", v2)
         with B.BPXContext(0) as ctx:
             problems.upload(ctx, p)
             ctx.sweep(5, 0.0, True)
             svs = ctx.apply_two_site_gates(edges, ops, max_rank=max_rank, normalize=normalize)
+            assert ctx.apply_stats() == (0, 0)
             results.append((svs, device_tensors(ctx, p), ctx.get_messages()))
     (sv1, t1, m1), (sv2, t2, m2) = results
     s1, s2 = oracle_state(p, t1), oracle_state(p, t2)
@@ -93,6 +95,7 @@ def test_chunked_layers_equal_one_launch(monkeypatch, v2):
     edges = matching(p.ga, rng)
     ops = [randn(rng, np.float64, (2, 2, 2, 2)) for _ in edges]
     monkeypatch.setenv("BPX_APPLY_V2", v2)
+    monkeypatch.setenv("BPX_APPLY_V3", "0")  # (version 3 has one work space per CTA and never chunks)
     out = []
     for budget in (None, str(64 * 1024)):
         if budget is None:
@@ -107,6 +110,61 @@ def test_chunked_layers_equal_one_launch(monkeypatch, v2):
             out.append((svs, device_tensors(ctx, p), ctx.get_messages(), ctx.counters()["launches"] - before))
     (sv_a, t_a, m_a, n_a), (sv_b, t_b, m_b, n_b) = out
     assert n_a == 1 and n_b > 1
+    assert all(np.array_equal(x, y) for x, y in zip(sv_a, sv_b))
+    assert all(np.array_equal(x, y) for x, y in zip(t_a, t_b))
+    assert all(np.array_equal(x, y) for x, y in zip(m_a, m_b))
+
+
+# ---- version 3 (the Gram path, csrc/bpx_apply3.cuh): the default ------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("lattice,chi,max_rank,normalize", [((4, 4), 4, 0, False), ((3, 5), 3, 2, True), ((4, 4), 8, 8, True),
+                                                           ((4, 4), 2, 0, True), ((2, 6), 5, 3, False)])
+def test_v3_matches_v1(monkeypatch, dtype, lattice, chi, max_rank, normalize):
+    """The default kernel against the step-by-step version 1 on a converged-ish BP environment: every gate of the layer is
+    taken by the Gram path, singular values / new messages agree, tensors agree in the gauge-invariant pair product."""
+    rng = np.random.default_rng(chi + max_rank)
+    p = problems.synthetic_peps(graphs.named_grid(lattice), chi, 2, dtype, init="positive")
+    edges = matching(p.ga, rng)
+    ops = [randn(rng, dtype, (2, 2, 2, 2)) for _ in edges]
+    results = []
+    for v3 in ("0", "1"):
+        monkeypatch.setenv("BPX_APPLY_V3", v3)
+        with B.BPXContext(0) as ctx:
+            problems.upload(ctx, p)
+            ctx.sweep(5, 0.0, True)
+            svs = ctx.apply_two_site_gates(edges, ops, max_rank=max_rank, normalize=normalize)
+            assert ctx.apply_stats() == ((len(edges), 0) if v3 == "1" else (0, 0))
+            res, _ = ctx.sweep(1, 0.0, True)  # the update kernels see the new tensors (private images rebuilt)
+            results.append((svs, device_tensors(ctx, p), ctx.get_messages(), res))
+    (sv1, t1, m1, r1), (sv3, t3, m3, r3) = results
+    s1, s3 = oracle_state(p, t1), oracle_state(p, t3)
+    for e, a, b in zip(edges, sv1, sv3):
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-13)
+        v, w = p.ga.src[e], p.ga.dst[e]
+        x, y = bond_invariant(s1, v, w), bond_invariant(s3, v, w)
+        assert np.abs(x - y).max() <= 1e-9 * np.abs(x).max()
+    assert all(np.allclose(a, b, rtol=1e-8, atol=1e-12) for a, b in zip(m1, m3))
+    assert abs(r1 - r3) <= 1e-9
+
+
+def test_v3_declined_gates_fall_back_to_v1_bit_for_bit(monkeypatch):
+    """An all-ones environment (test/test_apply_operator.jl:72) is rank one: the reference projects on the messages'
+    support, the Gram path declines every gate, and the result is exactly what version 1 alone produces; mixed layers
+    (some messages replaced by a full-rank one) split between the two kernels."""
+    rng = np.random.default_rng(8)
+    p = problems.synthetic_peps(graphs.named_grid((4, 4)), 3, 2, np.float64, init="ones")
+    edges = matching(p.ga, rng)
+    ops = [randn(rng, np.float64, (2, 2, 2, 2)) for _ in edges]
+    out = []
+    for v3 in ("0", "1"):
+        monkeypatch.setenv("BPX_APPLY_V3", v3)
+        with B.BPXContext(0) as ctx:
+            problems.upload(ctx, p)
+            svs = ctx.apply_two_site_gates(edges, ops, max_rank=3, normalize=True)
+            if v3 == "1":
+                assert ctx.apply_stats() == (0, len(edges))
+            out.append((svs, device_tensors(ctx, p), ctx.get_messages()))
+    (sv_a, t_a, m_a), (sv_b, t_b, m_b) = out
     assert all(np.array_equal(x, y) for x, y in zip(sv_a, sv_b))
     assert all(np.array_equal(x, y) for x, y in zip(t_a, t_b))
     assert all(np.array_equal(x, y) for x, y in zip(m_a, m_b))
