@@ -190,12 +190,22 @@ __host__ __device__ void load_tile(const Team& tm, const Side& sd, const Tabs& t
   using E = Elem<T>;
   const int cols = sd.cols;
   const int nrows = (int)((sd.rows - row0) < tr ? (sd.rows - row0) : tr);
+  constexpr int U = 8;  // independent loads in flight per thread (the address-table lookups sit in the dependency chain)
   if (tb.col_fast) {
-    for (int i = tm.tid(); i < tr * PC; i += tm.nt()) {
-      const int c = i & (PC - 1), r = i / PC;
-      T v = E::zero();
-      if (c < cols && r < nrows) v = src[tb.row[row0 + r] + tb.col[c]];
-      tile[r * rs + c * cs] = v;
+    const int total = tr * PC, nt = tm.nt();
+    for (int i0 = tm.tid(); i0 < total; i0 += U * nt) {
+      T v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nt, c = i & (PC - 1), r = i / PC;
+        v[u] = E::zero();
+        if (i < total && c < cols && r < nrows) v[u] = src[tb.row[row0 + r] + tb.col[c]];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nt, c = i & (PC - 1), r = i / PC;
+        if (i < total) tile[r * rs + c * cs] = v[u];
+      }
     }
   } else {
     const int d = sd.d, nb = cols / d;
@@ -203,9 +213,14 @@ __host__ __device__ void load_tile(const Team& tm, const Side& sd, const Tabs& t
       const int sx = pr % d, r = pr / d;
       if (r < nrows) {
         const T* base = src + tb.row[row0 + r];
-        for (int b = 0; b < nb; ++b) {
-          const int c = sx + d * b;
-          tile[r * rs + c * cs] = base[tb.col[c]];
+        for (int b0 = 0; b0 < nb; b0 += U) {
+          T v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (b0 + u < nb) v[u] = base[tb.col[sx + d * (b0 + u)]];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (b0 + u < nb) tile[r * rs + (sx + d * (b0 + u)) * cs] = v[u];
         }
       } else {
         for (int b = 0; b < nb; ++b) tile[r * rs + (sx + d * b) * cs] = E::zero();
@@ -384,9 +399,20 @@ __host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk&
   for (int64_t i = tm.tid(); i < hn; i += tm.nt()) hs[i] = H[i];
   tm.sync();
   for (int c0 = 0; c0 < sd.cols; c0 += CB) {
-    for (int i = tm.tid(); i < rows * CB; i += tm.nt()) {
-      const int b = i % CB, r = i / CB;
-      col[b * prow + r + dpad.div(r)] = a[tb.row[r] + tb.col[c0 + b]];
+    constexpr int U = 8;
+    const int total = rows * CB, nt = tm.nt();
+    for (int i0 = tm.tid(); i0 < total; i0 += U * nt) {
+      T v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nt, b = i % CB, r = i / CB;
+        if (i < total) v[u] = a[tb.row[r] + tb.col[c0 + b]];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nt, b = i % CB, r = i / CB;
+        if (i < total) col[b * prow + r + dpad.div(r)] = v[u];
+      }
     }
     tm.sync();
     int st = 1;
@@ -397,9 +423,18 @@ __host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk&
       st *= chi;
       off += (int64_t)chi * chi;
     }
-    for (int i = tm.tid(); i < rows * CB; i += tm.nt()) {
-      const int b = i % CB, r = i / CB;
-      tout[tb.row[r] + tb.col[c0 + b]] = col[b * prow + r + dpad.div(r)];
+    for (int i0 = tm.tid(); i0 < total; i0 += U * nt) {
+      int addr[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nt, b = i % CB, r = i / CB;
+        if (i < total) addr[u] = tb.row[r] + tb.col[c0 + b];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nt, b = i % CB, r = i / CB;
+        if (i < total) tout[addr[u]] = col[b * prow + r + dpad.div(r)];
+      }
     }
     tm.sync();
   }
@@ -515,6 +550,14 @@ __host__ __device__ void gram_side(const Team& tm, const Side& sd, const Tabs& t
   }
 }
 
+__host__ __device__ __forceinline__ double rsqrt_d(double x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 // ---- one-sided Jacobi without V, pairs on sub-warp lane groups ---------------------------------------------------------------
 // B (m x n, leading dimension ld, shared memory) is rotated until its columns are mutually orthogonal.  Returns through
 // *flag_out whether the last sweep still rotated (not converged within the sweep budget).
@@ -574,11 +617,12 @@ __host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int l
 #endif
         const double g2 = E::abs2(g);
         if (!active || !(g2 > tol2 * a * b) || !(a > zero2) || !(b > zero2)) continue;  // group-uniform, no shuffles below
-        const double ga = sqrt(g2);
-        const T ph = scal(g, 1.0 / ga);
-        const double zeta = (b - a) / (2.0 * ga);
+        // rotation parameters with reciprocal square roots (two rsqrt, one sqrt, one division per pair)
+        const double inv_ga = rsqrt_d(g2);
+        const T ph = scal(g, inv_ga);
+        const double zeta = 0.5 * (b - a) * inv_ga;
         const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        const double c = rsqrt_d(1.0 + t * t), s = c * t;
         const T sph = scal(ph, s), scph = scal(E::conj(ph), s);
         for (int r = sl; r < m; r += GS) {
           const T x = bp[r], y = bq[r];

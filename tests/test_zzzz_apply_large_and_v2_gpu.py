@@ -134,8 +134,11 @@ def test_v3_matches_v1(monkeypatch, dtype, lattice, chi, max_rank, normalize):
             ctx.sweep(5, 0.0, True)
             svs = ctx.apply_two_site_gates(edges, ops, max_rank=max_rank, normalize=normalize)
             assert ctx.apply_stats() == ((len(edges), 0) if v3 == "1" else (0, 0))
-            res, _ = ctx.sweep(1, 0.0, True)  # the update kernels see the new tensors (private images rebuilt)
-            results.append((svs, device_tensors(ctx, p), ctx.get_messages(), res))
+            msgs = ctx.get_messages()
+            # the update kernels see the new tensors (private images rebuilt); the bond gauge (signs / phases of the singular
+            # vectors) differs between the kernels, so only gauge-invariant results of the next sweep are compared
+            res, _ = ctx.sweep(1, 0.0, True)
+            results.append((svs, device_tensors(ctx, p), msgs, (res, ctx.bethe_free_energy())))
     (sv1, t1, m1, r1), (sv3, t3, m3, r3) = results
     s1, s3 = oracle_state(p, t1), oracle_state(p, t3)
     for e, a, b in zip(edges, sv1, sv3):
@@ -144,7 +147,7 @@ def test_v3_matches_v1(monkeypatch, dtype, lattice, chi, max_rank, normalize):
         x, y = bond_invariant(s1, v, w), bond_invariant(s3, v, w)
         assert np.abs(x - y).max() <= 1e-9 * np.abs(x).max()
     assert all(np.allclose(a, b, rtol=1e-8, atol=1e-12) for a, b in zip(m1, m3))
-    assert abs(r1 - r3) <= 1e-9
+    assert abs(r1[0] - r3[0]) <= 1e-9 and abs(r1[1] - r3[1]) <= 1e-8 * max(1.0, abs(r1[1]))
 
 
 def test_v3_declined_gates_fall_back_to_v1_bit_for_bit(monkeypatch):
