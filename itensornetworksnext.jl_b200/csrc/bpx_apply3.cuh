@@ -550,11 +550,34 @@ __host__ __device__ void gram_side(const Team& tm, const Side& sd, const Tabs& t
   }
 }
 
+// 1 / sqrt(x) and 1 / x to full double accuracy from the hardware's 20-bit approximations + two Newton steps: a short
+// dependent chain (the IEEE sqrt / division sequences cost several hundred cycles of latency each, and the Jacobi steps
+// below are pure latency).  Outside the safe exponent range the exact functions are used.
 __host__ __device__ __forceinline__ double rsqrt_d(double x) {
 #ifdef __CUDA_ARCH__
-  return rsqrt(x);
+  if (!(x > 1e-280 && x < 1e280)) return rsqrt(x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-x * y, y, 1.0);  // 1 - x y^2
+    y = fma(0.5 * y, e, fma(0.375 * y, e * e, y));  // second-order step: y (1 + e/2 + 3 e^2 / 8)
+  }
+  return y;
 #else
   return 1.0 / sqrt(x);
+#endif
+}
+__host__ __device__ __forceinline__ double rcp_d(double x) {
+#ifdef __CUDA_ARCH__
+  if (!(fabs(x) > 1e-280 && fabs(x) < 1e280)) return 1.0 / x;
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) y = fma(y, fma(-x, y, 1.0), y);
+  return y;
+#else
+  return 1.0 / x;
 #endif
 }
 
@@ -602,11 +625,31 @@ __host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int l
         T* bq = B + (int64_t)q * ld;
         double a = 0.0, b = 0.0;
         T g = E::zero();
-        for (int r = sl; r < m; r += GS) {
-          const T x = bp[r], y = bq[r];
-          a += E::abs2(x);
-          b += E::abs2(y);
-          g = E::fma(E::conj(x), y, g);
+        // the lane's rows of both columns stay in registers between the inner products and the rotation
+        constexpr int RC = 8;
+        const bool cached = m <= GS * RC;
+        T xr[RC], yr[RC];
+        if (cached) {
+#pragma unroll
+          for (int j = 0; j < RC; ++j) {
+            const int r = sl + j * GS;
+            xr[j] = E::zero();
+            yr[j] = E::zero();
+            if (r < m) {
+              xr[j] = bp[r];
+              yr[j] = bq[r];
+            }
+            a += E::abs2(xr[j]);
+            b += E::abs2(yr[j]);
+            g = E::fma(E::conj(xr[j]), yr[j], g);
+          }
+        } else {
+          for (int r = sl; r < m; r += GS) {
+            const T x = bp[r], y = bq[r];
+            a += E::abs2(x);
+            b += E::abs2(y);
+            g = E::fma(E::conj(x), y, g);
+          }
         }
 #ifdef __CUDA_ARCH__
         for (int o = GS >> 1; o > 0; o >>= 1) {
@@ -617,17 +660,35 @@ __host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int l
 #endif
         const double g2 = E::abs2(g);
         if (!active || !(g2 > tol2 * a * b) || !(a > zero2) || !(b > zero2)) continue;  // group-uniform, no shuffles below
-        // rotation parameters with reciprocal square roots (two rsqrt, one sqrt, one division per pair)
+        // rotation parameters on short dependent chains (rsqrt_d / rcp_d)
         const double inv_ga = rsqrt_d(g2);
         const T ph = scal(g, inv_ga);
-        const double zeta = 0.5 * (b - a) * inv_ga;
-        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = rsqrt_d(1.0 + t * t), s = c * t;
+        const double zeta = 0.5 * (b - a) * inv_ga, az = fabs(zeta);
+        double t;
+        if (az < 1e100) {
+          const double w1 = fma(zeta, zeta, 1.0);
+          t = rcp_d(az + w1 * rsqrt_d(w1));  // 1 / (|zeta| + sqrt(1 + zeta^2))
+        } else {
+          t = 0.5 * rcp_d(az);
+        }
+        if (zeta < 0.0) t = -t;
+        const double c = rsqrt_d(fma(t, t, 1.0)), s = c * t;
         const T sph = scal(ph, s), scph = scal(E::conj(ph), s);
-        for (int r = sl; r < m; r += GS) {
-          const T x = bp[r], y = bq[r];
-          bp[r] = sub(scal(x, c), E::mul(y, scph));
-          bq[r] = E::add(E::mul(x, sph), scal(y, c));
+        if (cached) {
+#pragma unroll
+          for (int j = 0; j < RC; ++j) {
+            const int r = sl + j * GS;
+            if (r < m) {
+              bp[r] = sub(scal(xr[j], c), E::mul(yr[j], scph));
+              bq[r] = E::add(E::mul(xr[j], sph), scal(yr[j], c));
+            }
+          }
+        } else {
+          for (int r = sl; r < m; r += GS) {
+            const T x = bp[r], y = bq[r];
+            bp[r] = sub(scal(x, c), E::mul(y, scph));
+            bq[r] = E::add(E::mul(x, sph), scal(y, c));
+          }
         }
         if (sl == 0) BPX_FLAG_SET(flag);
       }
