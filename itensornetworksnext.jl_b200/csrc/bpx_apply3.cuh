@@ -42,7 +42,8 @@ constexpr double PIVOT_MIN = 1e-12;  // smallest Cholesky pivot of a message rel
 constexpr int MAXDIM = 16;           // largest external link dimension (a fibre lives in registers)
 
 struct Layout3 {
-  int64_t t;            // T = (M_1 x M_2 x ..) A, same (canonical) layout as A; shared by the two sides
+  int64_t at[2];        // per side: the matrix view of A as a row-major rows x PCP matrix (tiles of rows are contiguous)
+  int64_t tt;           // T = (M_1 x M_2 x ..) A in the same layout; shared by the two sides
   int64_t h[2];         // Hermitian parts of the boundary messages, slot order, chi^2 each
   int64_t g[2];         // G (cols x cols) and its rotated copy
   int64_t gb[2];
@@ -66,7 +67,8 @@ __host__ __device__ inline int64_t herm_elems(const Side& s) {
 __host__ __device__ inline Layout3 layout3_of(const GateDesc& g) {
   Layout3 L;
   int64_t o = 0;
-  L.t = o; o += g.s[0].n > g.s[1].n ? g.s[0].n : g.s[1].n;
+  for (int a = 0; a < 2; ++a) { L.at[a] = o; o += g.s[a].rows * PCP; }
+  L.tt = o; o += (g.s[0].rows > g.s[1].rows ? g.s[0].rows : g.s[1].rows) * PCP;
   for (int a = 0; a < 2; ++a) {
     const Side& s = g.s[a];
     const int64_t cc = (int64_t)s.cols * s.cols;
@@ -108,7 +110,7 @@ __host__ __device__ inline int64_t smem_need(const GateDesc& g, bool cplx) {
     const int64_t absorb = cb * (s.rows + s.rows / dim0) + 2 + hsum;  // padded column batch + the messages
     const int64_t gram = 2 * (int64_t)TRG * PCP;               // A tile, T tile (the reduction re-uses them)
     const int64_t trf = cplx ? 128 : 256;
-    const int64_t fin = (trf + 1) * PC + (int64_t)PC * PC;     // A tile (padded column stride), W
+    const int64_t fin = trf * PCP + (int64_t)PC * PC;          // A tile, W
     need = need > absorb ? need : absorb;
     need = need > gram ? need : gram;
     need = need > fin ? need : fin;
@@ -182,55 +184,26 @@ __host__ __device__ Tabs build_tabs(const Team& tm, const Side& sd, const Walk& 
   return t;
 }
 
-// rows [row0, row0 + tr) x all columns of the matrix view -> tile[r * rs + c * cs]; rows beyond the matrix and columns
-// cols..PC-1 are zero.  Global reads follow the canonical layout's contiguous direction.
+// contiguous copy global -> shared in 16-byte pieces (both 16-byte aligned; n elements, n * sizeof(T) a multiple of 16)
 template <typename T>
-__host__ __device__ void load_tile(const Team& tm, const Side& sd, const Tabs& tb, const T* src, int64_t row0, int tr, T* tile,
-                                   int rs, int cs) {
-  using E = Elem<T>;
-  const int cols = sd.cols;
-  const int nrows = (int)((sd.rows - row0) < tr ? (sd.rows - row0) : tr);
-  constexpr int U = 8;  // independent loads in flight per thread (the address-table lookups sit in the dependency chain)
-  if (tb.col_fast) {
-    const int total = tr * PC, nt = tm.nt();
-    for (int i0 = tm.tid(); i0 < total; i0 += U * nt) {
-      T v[U];
+__host__ __device__ void copy_tile(const Team& tm, T* dst, const T* src, int64_t n) {
+#ifdef __CUDA_ARCH__
+  const int n16 = (int)(n * sizeof(T) / 16), nt = tm.nt();
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+  double2* d2 = reinterpret_cast<double2*>(dst);
+  constexpr int U = 4;
+  for (int i0 = tm.tid(); i0 < n16; i0 += U * nt) {
+    double2 v[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * nt, c = i & (PC - 1), r = i / PC;
-        v[u] = E::zero();
-        if (i < total && c < cols && r < nrows) v[u] = src[tb.row[row0 + r] + tb.col[c]];
-      }
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * nt < n16) v[u] = s2[i0 + u * nt];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * nt, c = i & (PC - 1), r = i / PC;
-        if (i < total) tile[r * rs + c * cs] = v[u];
-      }
-    }
-  } else {
-    const int d = sd.d, nb = cols / d;
-    for (int pr = tm.tid(); pr < d * tr; pr += tm.nt()) {  // (s, row) pairs, s fastest: contiguous in memory
-      const int sx = pr % d, r = pr / d;
-      if (r < nrows) {
-        const T* base = src + tb.row[row0 + r];
-        for (int b0 = 0; b0 < nb; b0 += U) {
-          T v[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (b0 + u < nb) v[u] = base[tb.col[sx + d * (b0 + u)]];
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (b0 + u < nb) tile[r * rs + (sx + d * (b0 + u)) * cs] = v[u];
-        }
-      } else {
-        for (int b = 0; b < nb; ++b) tile[r * rs + (sx + d * b) * cs] = E::zero();
-      }
-    }
-    for (int i = tm.tid(); i < tr * (PC - cols); i += tm.nt()) {
-      const int r = i % tr, c = cols + i / tr;
-      tile[r * rs + c * cs] = E::zero();
-    }
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * nt < n16) d2[i0 + u * nt] = v[u];
   }
+#else
+  for (int64_t i = tm.tid(); i < n; i += tm.nt()) dst[i] = src[i];
+#endif
   tm.sync();
 }
 
@@ -387,8 +360,8 @@ __host__ __device__ void absorb_leg(const Team& tm, T* col, int rows, int prow, 
 // then start an odd number of elements apart (no bank conflicts; unpadded, a warp's 32 fibres of 16 doubles share one
 // bank), and every other leg keeps a uniform stride st + st / rdim[0].
 template <typename T, int CB>
-__host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk& wk, const Tabs& tb, const T* a, const T* H, T* tout,
-                                     T* smem) {
+__host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk& wk, const Tabs& tb, const T* a, const T* H, T* aout,
+                                     T* tout, T* smem) {
   const int rows = (int)sd.rows;
   const int pad0 = wk.next > 0 ? wk.rdim[0] : 1;
   const int prow = rows + rows / pad0;
@@ -411,7 +384,10 @@ __host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk&
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = i0 + u * nt, b = i % CB, r = i / CB;
-        if (i < total) col[b * prow + r + dpad.div(r)] = v[u];
+        if (i < total) {
+          col[b * prow + r + dpad.div(r)] = v[u];
+          aout[(int64_t)r * PCP + c0 + b] = v[u];  // the matrix view, row-major: the Gram and final passes read plain tiles
+        }
       }
     }
     tm.sync();
@@ -423,18 +399,9 @@ __host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk&
       st *= chi;
       off += (int64_t)chi * chi;
     }
-    for (int i0 = tm.tid(); i0 < total; i0 += U * nt) {
-      int addr[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * nt, b = i % CB, r = i / CB;
-        if (i < total) addr[u] = tb.row[r] + tb.col[c0 + b];
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * nt, b = i % CB, r = i / CB;
-        if (i < total) tout[addr[u]] = col[b * prow + r + dpad.div(r)];
-      }
+    for (int i = tm.tid(); i < total; i += nt) {
+      const int b = i % CB, r = i / CB;
+      tout[(int64_t)r * PCP + c0 + b] = col[b * prow + r + dpad.div(r)];
     }
     tm.sync();
   }
@@ -445,7 +412,7 @@ __host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk&
 // an 8 x 4 lane grid accumulates the 4 x TJ block G[4 i .., TJ (j + 4 pass) ..]: per row 4 + TJ operand loads (broadcast
 // within the lane groups) feed 4 TJ FMAs.  The nw partial tiles are summed through shared memory at the end.
 template <typename T, int TJ>
-__host__ __device__ void gram_side(const Team& tm, const Side& sd, const Tabs& tb, const T* a, const T* t, T* G, T* smem) {
+__host__ __device__ void gram_side(const Team& tm, const Side& sd, const T* at, const T* tt, T* G, T* smem) {
   using E = Elem<T>;
   constexpr int NPASS = PC / (4 * TJ);
   T* sA = smem;
@@ -464,9 +431,9 @@ __host__ __device__ void gram_side(const Team& tm, const Side& sd, const Tabs& t
     std::vector<T> hacc((size_t)32 * 4 * TJ, E::zero());
 #endif
     for (int64_t row0 = 0; row0 < sd.rows; row0 += TRG) {
-      load_tile<T>(tm, sd, tb, a, row0, TRG, sA, PCP, 1);
-      load_tile<T>(tm, sd, tb, t, row0, TRG, sT, PCP, 1);
       const int nr = (int)((sd.rows - row0) < TRG ? (sd.rows - row0) : TRG);
+      copy_tile<T>(tm, sA, at + row0 * PCP, (int64_t)nr * PCP);
+      copy_tile<T>(tm, sT, tt + row0 * PCP, (int64_t)nr * PCP);
 #ifdef __CUDA_ARCH__
       const int li = tm.lane >> 2, lj = tm.lane & 3;
       const T* pa = sA + 4 * li;
@@ -582,19 +549,21 @@ __host__ __device__ __forceinline__ double rcp_d(double x) {
 }
 
 // ---- one-sided Jacobi without V, pairs on sub-warp lane groups ---------------------------------------------------------------
-// B (m x n, leading dimension ld, shared memory) is rotated until its columns are mutually orthogonal.  Returns through
-// *flag_out whether the last sweep still rotated (not converged within the sweep budget).
-template <typename T>
-__host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int ld, int* flag, int* not_converged) {
+// B (m x n, leading dimension ld, shared memory) is rotated until its columns are mutually orthogonal; *not_converged is
+// set when the last sweep of the budget still rotated.  A group of GS lanes owns one column pair of the current
+// round-robin step.  The iteration is ISSUE bound (every warp pays ~200 instructions of rotation parameters, shuffles and
+// pair bookkeeping per step whatever the amount of data), so the groups are kept SMALL: few lanes per pair, many pairs
+// per warp, few warps busy (64 columns: 32 pairs on 4 warps of 8 groups) -- the other warps wait at the step barrier and
+// the co-resident CTA gets the issue slots.  A lane's rows of both columns stay in registers between the inner products
+// and the rotation (RC per column).
+template <typename T, int GS, int RC>
+__host__ __device__ __noinline__ void jacobi_groups_t(const Team& tm, T* B, int m, int n, int ld, int* flag, int* not_converged) {
   using E = Elem<T>;
-  if (n < 2) return;
   const int L = tm.lanes();
   const int np = (n + 1) & ~1, npairs = np / 2;
-  // lanes per pair: as many as keep every pair of a step in flight at once
-  int GS = 1;
-  while (GS * 2 <= L && (tm.nw * (L / (GS * 2))) >= npairs) GS *= 2;
   const int gpw = L / GS;                // groups per warp
   const int sl = tm.lane % GS, grp = tm.lane / GS;
+  const bool cached = m <= GS * RC;
   const double tol2 = (double)m * EPS * EPS;
   double fro2 = 0.0;
   for (int64_t i = tm.lane; i < (int64_t)m * n; i += L) fro2 += E::abs2(B[(i % m) + (int64_t)ld * (i / m)]);
@@ -615,19 +584,18 @@ __host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int l
             p = np - 1;
             q = step;
           } else {
-            p = (step + idx) % (np - 1);
-            q = (step - idx + (np - 1)) % (np - 1);
+            p = step + idx;
+            if (p >= np - 1) p -= np - 1;
+            q = step - idx;
+            if (q < 0) q += np - 1;
           }
           if (p > q) { const int t = p; p = q; q = t; }
           if (q >= n) { active = false; p = 0; q = 1; }
         }
-        T* bp = B + (int64_t)p * ld;
-        T* bq = B + (int64_t)q * ld;
+        T* bp = B + p * ld;
+        T* bq = B + q * ld;
         double a = 0.0, b = 0.0;
         T g = E::zero();
-        // the lane's rows of both columns stay in registers between the inner products and the rotation
-        constexpr int RC = 8;
-        const bool cached = m <= GS * RC;
         T xr[RC], yr[RC];
         if (cached) {
 #pragma unroll
@@ -652,6 +620,7 @@ __host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int l
           }
         }
 #ifdef __CUDA_ARCH__
+#pragma unroll
         for (int o = GS >> 1; o > 0; o >>= 1) {
           a += __shfl_xor_sync(0xffffffffu, a, o);
           b += __shfl_xor_sync(0xffffffffu, b, o);
@@ -699,6 +668,23 @@ __host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int l
   }
   if (f && tm.tid() == 0) BPX_FLAG_SET(not_converged);
   tm.sync();
+}
+
+template <typename T>
+__host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int ld, int* flag, int* not_converged) {
+  if (n < 2) return;
+#ifdef __CUDA_ARCH__
+  constexpr int RC = Elem<T>::is_complex ? 8 : 16;
+  const int npairs = (n + 1) / 2;
+  if (npairs >= 16)
+    jacobi_groups_t<T, 4, RC>(tm, B, m, n, ld, flag, not_converged);
+  else if (npairs >= 4)
+    jacobi_groups_t<T, 8, RC>(tm, B, m, n, ld, flag, not_converged);
+  else
+    jacobi_groups_t<T, 16, RC>(tm, B, m, n, ld, flag, not_converged);
+#else
+  jacobi_groups_t<T, 1, 1>(tm, B, m, n, ld, flag, not_converged);  // host lanes: one lane per pair
+#endif
 }
 
 // ---- eigen-decomposition of the Gram matrix -> R, R^+ ------------------------------------------------------------------------
@@ -771,20 +757,22 @@ __host__ __device__ void gram_factor(const Team& tm, int cols, int rank_max, con
   tm.sync();
 }
 
-// ---- final pass: A'[row, c'] = sum_c A[row, c] W[c, c'] in place -----------------------------------------------------------
+// ---- final pass: A'[row, c'] = sum_c A[row, c] W[c, c'], A from its row-major scratch copy, A' into the canonical tensor ----
+// Tiles of TRF rows as [row][PCP] in shared memory (plain contiguous copies).  A thread owns RT rows x NO outputs: per
+// column pair RT 16-byte operand loads (rows 272 bytes apart: conflict free) and NO 16-byte broadcast loads of W feed 2 RT NO
+// FMAs.
 template <typename T, int TRF, int RT, int NO>
-__host__ __device__ void final_side(const Team& tm, const Side& sd, const Tabs& tb, T* a, const T* W, T* smem) {
+__host__ __device__ void final_side(const Team& tm, const Side& sd, const Tabs& tb, const T* at, T* a, const T* W, T* smem) {
   using E = Elem<T>;
-  constexpr int TRFP = TRF + 1;                  // padded column stride: conflict-free stores in both load orders
-  T* sA = smem;                                  // [c][TRFP]
-  T* sW = smem + (int64_t)TRFP * PC;             // [c][PC]
+  T* sA = smem;                                  // [r][PCP]
+  T* sW = smem + (int64_t)TRF * PCP;             // [c][PC]
   for (int i = tm.tid(); i < PC * PC; i += tm.nt()) sW[i] = W[i];
-  tm.sync();
   const int cols = sd.cols;
   constexpr int RG = TRF / RT;                   // row groups: thread rows rg, rg + RG, ..
   constexpr int OG = PC / NO;                    // output groups
   for (int64_t row0 = 0; row0 < sd.rows; row0 += TRF) {
-    load_tile<T>(tm, sd, tb, a, row0, TRF, sA, 1, TRFP);
+    const int nr = (int)((sd.rows - row0) < TRF ? (sd.rows - row0) : TRF);
+    copy_tile<T>(tm, sA, at + row0 * PCP, (int64_t)nr * PCP);
     for (int item = tm.tid(); item < RG * OG; item += tm.nt()) {
       const int rg = item % RG, og = item / RG;
       if (og * NO >= cols) continue;
@@ -793,31 +781,60 @@ __host__ __device__ void final_side(const Team& tm, const Side& sd, const Tabs& 
       for (int x = 0; x < RT; ++x)
 #pragma unroll
         for (int y = 0; y < NO; ++y) acc[x][y] = E::zero();
-      for (int c = 0; c < cols; ++c) {
-        T av[RT];
+      for (int c = 0; c < cols; c += 2) {
+        const bool two = c + 1 < cols;  // (columns >= cols of the scratch copy are not initialised)
+        T a0[RT], a1[RT];
 #pragma unroll
-        for (int x = 0; x < RT; ++x) av[x] = sA[c * TRFP + rg + x * RG];
+        for (int x = 0; x < RT; ++x) {
+          const T* pa = sA + (rg + x * RG) * PCP + c;
+#ifdef __CUDA_ARCH__
+          if constexpr (!E::is_complex) {
+            const double2 q = *reinterpret_cast<const double2*>(pa);
+            a0[x] = q.x;
+            a1[x] = two ? q.y : 0.0;
+          } else {
+            const double2 q0 = reinterpret_cast<const double2*>(pa)[0];
+            a0[x] = *reinterpret_cast<const T*>(&q0);
+            a1[x] = E::zero();
+            if (two) {
+              const double2 q1 = reinterpret_cast<const double2*>(pa)[1];
+              a1[x] = *reinterpret_cast<const T*>(&q1);
+            }
+          }
+#else
+          a0[x] = pa[0];
+          a1[x] = two ? pa[1] : E::zero();
+#endif
+        }
         const T* pw = sW + c * PC + og * NO;
-        T wv[NO];
+        T w0[NO], w1[NO];
 #ifdef __CUDA_ARCH__
         {  // 16-byte aligned rows of W: vector loads, one broadcast each
-          const double2* p2 = reinterpret_cast<const double2*>(pw);
-          double2* w2 = reinterpret_cast<double2*>(wv);
+          const double2* p0 = reinterpret_cast<const double2*>(pw);
+          const double2* p1 = reinterpret_cast<const double2*>(pw + PC);
+          double2* v0 = reinterpret_cast<double2*>(w0);
+          double2* v1 = reinterpret_cast<double2*>(w1);
 #pragma unroll
-          for (int y = 0; y < (int)(NO * sizeof(T) / 16); ++y) w2[y] = p2[y];
+          for (int y = 0; y < (int)(NO * sizeof(T) / 16); ++y) {
+            v0[y] = p0[y];
+            v1[y] = p1[y];
+          }
         }
 #else
-        for (int y = 0; y < NO; ++y) wv[y] = pw[y];
+        for (int y = 0; y < NO; ++y) {
+          w0[y] = pw[y];
+          w1[y] = pw[PC + y];
+        }
 #endif
 #pragma unroll
         for (int y = 0; y < NO; ++y)
 #pragma unroll
-          for (int x = 0; x < RT; ++x) acc[x][y] = E::fma(av[x], wv[y], acc[x][y]);
+          for (int x = 0; x < RT; ++x) acc[x][y] = E::fma(a1[x], w1[y], E::fma(a0[x], w0[y], acc[x][y]));
       }
 #pragma unroll
       for (int x = 0; x < RT; ++x) {
         const int r = rg + x * RG;
-        if (row0 + r >= sd.rows) continue;
+        if (r >= nr) continue;
         const int64_t ra = tb.row[row0 + r];
 #pragma unroll
         for (int y = 0; y < NO; ++y) {
@@ -848,10 +865,10 @@ __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* s
     if (*bad) return 1;
     const T* A = sites + sd.site_off;
     if (!CPLX && sd.cols % 2 == 0)
-      absorb_side<T, 2>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.t, smem);
+      absorb_side<T, 2>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.at[a], w + L.tt, smem);
     else
-      absorb_side<T, 1>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.t, smem);
-    gram_side<T, CPLX ? 4 : 8>(tm, sd, tb[a], A, w + L.t, w + L.g[a], smem);
+      absorb_side<T, 1>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.at[a], w + L.tt, smem);
+    gram_side<T, CPLX ? 4 : 8>(tm, sd, w + L.at[a], w + L.tt, w + L.g[a], smem);
     gram_factor<T>(tm, sd.cols, sd.nref, w + L.g[a], w + L.gb[a], reinterpret_cast<double*>(w + L.ev[a]), w + L.r[a], w + L.rinv[a], smem,
                    flag, bad);
     if (*bad) return 1;
@@ -962,9 +979,9 @@ __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* s
     const Side& sd = gd.s[a];
     T* A = sites + sd.site_off;
     if (CPLX)
-      final_side<T, 128, 1, 8>(tm, sd, tb[a], A, w + L.w[a], smem);
+      final_side<T, 128, 1, 8>(tm, sd, tb[a], w + L.at[a], A, w + L.w[a], smem);
     else
-      final_side<T, 256, 2, 16>(tm, sd, tb[a], A, w + L.w[a], smem);
+      final_side<T, 256, 2, 16>(tm, sd, tb[a], w + L.at[a], A, w + L.w[a], smem);
   }
   for (int i = tm.tid(); i < chi * chi; i += tm.nt()) {
     const int r = i % chi, c = i / chi;
