@@ -15,4 +15,4 @@ ncu -i $O/${T}_apply_v3_chi16.ncu-rep --page raw --csv > $O/${T}_apply_v3_chi16.
 ncu -i $O/${T}_apply_v3_chi16.ncu-rep --page source --csv > $O/${T}_apply_v3_chi16.source.csv 2>/dev/null
 python tools/ncu_summary.py $O/${T}_apply_v3_chi16.raw.csv $O/${T}_apply_v3_chi16_ncu_summary.csv bp_apply_gates 2>&1 | tail -1
 rm -f $O/${T}_apply_v3_chi16.ncu-rep
-cp itensornetworksnext.jl_b200/csrc/libbpx.so $O/${T}_libbpx.so
+
