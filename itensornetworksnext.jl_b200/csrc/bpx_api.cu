@@ -1863,6 +1863,14 @@ static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates
   a3.base.normalize = normalize;
   a3.ws_stride = ws_stride;
   a3.status = d_status;
+  a3.stamps = nullptr;
+  long long* d_stamps = nullptr;
+  const bool timing = getenv("BPX_APPLY_TIMING") != nullptr;  // debug: per-phase clock64 stamps, summary on stderr
+  if (timing) {
+    if ((rc = ws_get(ctx, bpx_ctx::WS_OUT, (size_t)ng * 16 * sizeof(long long), &d_stamps))) return rc;
+    BPX_CUDA(ctx, cudaMemsetAsync(d_stamps, 0, (size_t)ng * 16 * sizeof(long long), ctx->stream));
+    a3.stamps = d_stamps;
+  }
   if (ctx->dtype == BPX_F64)
     applyk3::bp_apply_gates_v3<double><<<grid, applyk::NT, bytes, ctx->stream>>>(a3);
   else
@@ -1872,6 +1880,26 @@ static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates
   std::vector<int32_t> status((size_t)ng);
   BPX_CUDA(ctx, cudaMemcpyAsync(status.data(), d_status, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (timing) {
+    std::vector<long long> st((size_t)ng * 16);
+    BPX_CUDA(ctx, cudaMemcpy(st.data(), d_stamps, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    static const char* names[13] = {"", "msg check 0", "absorb 0", "gram 0", "eig 0", "msg check 1", "absorb 1", "gram 1", "eig 1",
+                                    "theta + gate", "svd", "Y, W", "final x 2 + msgs"};
+    double acc[13] = {0};
+    int64_t cnt = 0;
+    for (int64_t g = 0; g < ng; ++g) {
+      const long long* t = st.data() + 16 * g;
+      if (status[g] != 0 || t[12] == 0) continue;
+      for (int i = 1; i <= 12; ++i) acc[i] += (double)(t[i] - t[i - 1]);
+      ++cnt;
+    }
+    double tot = 0;
+    for (int i = 1; i <= 12; ++i) tot += acc[i];
+    fprintf(stderr, "bp_apply_gates_v3 phase clocks (mean over %lld gates, grid %d, %d CTA/SM): total %.0f\n", (long long)cnt, grid, per_sm,
+            tot / std::max<int64_t>(cnt, 1));
+    for (int i = 1; i <= 12; ++i)
+      fprintf(stderr, "  %-18s %10.0f  %5.1f %%\n", names[i], acc[i] / std::max<int64_t>(cnt, 1), 100.0 * acc[i] / std::max(tot, 1.0));
+  }
   *taken = true;
   for (int64_t g = 0; g < ng; ++g)
     if (status[g] != 0) rest.push_back(gates[g]);

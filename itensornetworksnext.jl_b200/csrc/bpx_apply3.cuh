@@ -850,10 +850,16 @@ __host__ __device__ void final_side(const Team& tm, const Side& sd, const Tabs& 
 // One two-site gate.  Returns (to every thread) 0 when the gate was applied, 1 when it was left untouched for the fallback.
 template <typename T>
 __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* sites, T* msgs, const T* ops, T* w /* this CTA's work space */,
-                                        double* sv_out, int normalize, int* flag, int* bad, T* smem) {
+                                        double* sv_out, int normalize, int* flag, int* bad, T* smem, long long* stamps = nullptr) {
   using E = Elem<T>;
   constexpr bool CPLX = Elem<T>::is_complex;
   const Layout3 L = layout3_of(gd);
+#ifdef __CUDA_ARCH__
+#define BPX_STAMP(i) do { if (stamps && tm.tid() == 0) stamps[i] = clock64(); } while (0)
+#else
+#define BPX_STAMP(i) do { (void)stamps; } while (0)
+#endif
+  BPX_STAMP(0);
   if (tm.tid() == 0) *bad = 0;
   tm.sync();
   Tabs tb[2];
@@ -863,15 +869,19 @@ __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* s
     tb[a] = build_tabs<T>(tm, sd, wka, w + L.tab[a]);
     message_check<T>(tm, sd, msgs, w + L.h[a], smem, bad);
     if (*bad) return 1;
+    BPX_STAMP(1 + 4 * a);
     const T* A = sites + sd.site_off;
     if (!CPLX && sd.cols % 2 == 0)
       absorb_side<T, 2>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.at[a], w + L.tt, smem);
     else
       absorb_side<T, 1>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.at[a], w + L.tt, smem);
+    BPX_STAMP(2 + 4 * a);
     gram_side<T, CPLX ? 4 : 8>(tm, sd, w + L.at[a], w + L.tt, w + L.g[a], smem);
+    BPX_STAMP(3 + 4 * a);
     gram_factor<T>(tm, sd.cols, sd.nref, w + L.g[a], w + L.gb[a], reinterpret_cast<double*>(w + L.ev[a]), w + L.r[a], w + L.rinv[a], smem,
                    flag, bad);
     if (*bad) return 1;
+    BPX_STAMP(4 + 4 * a);
   }
   // ---- the bond problem (apply_operators.jl:260-268), R factors with cols rows each -----------------------------------
   const Side& s1 = gd.s[0];
@@ -906,8 +916,10 @@ __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* s
     sb[row + (int64_t)ldb * col] = acc;
   }
   tm.sync();
+  BPX_STAMP(9);
   jacobi_groups<T>(tm, sb, m, n, ldb, flag, bad);
   if (*bad) return 1;
+  BPX_STAMP(10);
   double* sig = reinterpret_cast<double*>(w + L.sig);
   int32_t* order = reinterpret_cast<int32_t*>(w + L.order);
   for (int i = tm.tid(); i < m * n; i += tm.nt()) th2[i] = sb[(i % m) + (int64_t)ldb * (i / m)];
@@ -975,6 +987,7 @@ __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* s
     }
   }
   tm.sync();
+  BPX_STAMP(11);
   for (int a = 0; a < 2; ++a) {
     const Side& sd = gd.s[a];
     T* A = sites + sd.site_off;
@@ -1000,6 +1013,7 @@ struct ApplyArgs3 {
   ApplyArgs base;       // base.ws: one work space of ws_stride elements PER CTA (not per gate: a layer is one launch)
   int64_t ws_stride;
   int32_t* status;      // per gate: 0 applied, 1 left for the fallback
+  long long* stamps;    // debug (BPX_APPLY_TIMING=1): 16 clock64 stamps per gate, or NULL
 };
 
 template <typename T>
@@ -1016,7 +1030,7 @@ __global__ void __launch_bounds__(NT, 2) bp_apply_gates_v3(ApplyArgs3 a3) {
     const int st = run_two_site_v3<T>(tm, a.gates[g], static_cast<T*>(a.sites), static_cast<T*>(a.msgs), static_cast<const T*>(a.ops),
                                       static_cast<T*>(a.ws) + (int64_t)blockIdx.x * a3.ws_stride,
                                       a.sv_out ? a.sv_out + sv_row * a.sv_stride : nullptr, a.normalize, &flag, &bad,
-                                      reinterpret_cast<T*>(dyn_smem3));
+                                      reinterpret_cast<T*>(dyn_smem3), a3.stamps ? a3.stamps + 16 * g : nullptr);
     if (threadIdx.x == 0) a3.status[g] = st;
     __syncthreads();
   }
