@@ -1867,8 +1867,8 @@ static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates
   long long* d_stamps = nullptr;
   const bool timing = getenv("BPX_APPLY_TIMING") != nullptr;  // debug: per-phase clock64 stamps, summary on stderr
   if (timing) {
-    if ((rc = ws_get(ctx, bpx_ctx::WS_OUT, (size_t)ng * 16 * sizeof(long long), &d_stamps))) return rc;
-    BPX_CUDA(ctx, cudaMemsetAsync(d_stamps, 0, (size_t)ng * 16 * sizeof(long long), ctx->stream));
+    if ((rc = ws_get(ctx, bpx_ctx::WS_OUT, (size_t)ng * 32 * sizeof(long long), &d_stamps))) return rc;
+    BPX_CUDA(ctx, cudaMemsetAsync(d_stamps, 0, (size_t)ng * 32 * sizeof(long long), ctx->stream));
     a3.stamps = d_stamps;
   }
   if (ctx->dtype == BPX_F64)
@@ -1881,16 +1881,20 @@ static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates
   BPX_CUDA(ctx, cudaMemcpyAsync(status.data(), d_status, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (timing) {
-    std::vector<long long> st((size_t)ng * 16);
+    std::vector<long long> st((size_t)ng * 32);
     BPX_CUDA(ctx, cudaMemcpy(st.data(), d_stamps, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     static const char* names[13] = {"", "msg check 0", "absorb 0", "gram 0", "eig 0", "msg check 1", "absorb 1", "gram 1", "eig 1",
                                     "theta + gate", "svd", "Y, W", "final x 2 + msgs"};
-    double acc[13] = {0};
+    double acc[13] = {0}, sw[3] = {0}, ab[5] = {0};
     int64_t cnt = 0;
     for (int64_t g = 0; g < ng; ++g) {
-      const long long* t = st.data() + 16 * g;
+      const long long* t = st.data() + 32 * g;
       if (status[g] != 0 || t[12] == 0) continue;
       for (int i = 1; i <= 12; ++i) acc[i] += (double)(t[i] - t[i - 1]);
+      for (int i = 0; i < 3; ++i) sw[i] += (double)t[13 + i];
+      ab[0] += (double)(t[17] - t[16]);
+      for (int i = 1; i < 4; ++i) ab[i] += (double)(t[17 + i] - t[16 + i]);
+      ab[4] += (double)(t[23] - t[20]);
       ++cnt;
     }
     double tot = 0;
@@ -1899,6 +1903,9 @@ static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates
             tot / std::max<int64_t>(cnt, 1));
     for (int i = 1; i <= 12; ++i)
       fprintf(stderr, "  %-18s %10.0f  %5.1f %%\n", names[i], acc[i] / std::max<int64_t>(cnt, 1), 100.0 * acc[i] / std::max(tot, 1.0));
+    const double c1 = (double)std::max<int64_t>(cnt, 1);
+    fprintf(stderr, "  Jacobi sweeps: svd %.1f, eig %.1f / %.1f;  first column batch of absorb 0: gather %.0f, legs %.0f %.0f %.0f, scatter %.0f\n",
+            sw[0] / c1, sw[1] / c1, sw[2] / c1, ab[0] / c1, ab[1] / c1, ab[2] / c1, ab[3] / c1, ab[4] / c1);
   }
   *taken = true;
   for (int64_t g = 0; g < ng; ++g)

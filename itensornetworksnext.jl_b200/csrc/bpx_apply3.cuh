@@ -171,7 +171,7 @@ struct Tabs {
   bool col_fast;  // the columns (s, bond) are contiguous in the canonical layout (bond leg first); else (s, first row leg)
 };
 template <typename T>
-__host__ __device__ Tabs build_tabs(const Team& tm, const Side& sd, const Walk& wk, T* slot) {
+__host__ __device__ __noinline__ Tabs build_tabs(const Team tm, const Side& sd, const Walk& wk, T* slot) {
   int32_t* rt = reinterpret_cast<int32_t*>(slot);
   int32_t* ct = rt + sd.rows;
   for (int64_t r = tm.tid(); r < sd.rows; r += tm.nt()) rt[r] = (int32_t)rowaddr(wk, r);
@@ -186,21 +186,21 @@ __host__ __device__ Tabs build_tabs(const Team& tm, const Side& sd, const Walk& 
 
 // contiguous copy global -> shared in 16-byte pieces (both 16-byte aligned; n elements, n * sizeof(T) a multiple of 16)
 template <typename T>
-__host__ __device__ void copy_tile(const Team& tm, T* dst, const T* src, int64_t n) {
+__host__ __device__ __noinline__ void copy_tile(const Team tm, T* dst, const T* src, int64_t n) {
 #ifdef __CUDA_ARCH__
-  const int n16 = (int)(n * sizeof(T) / 16), nt = tm.nt();
-  const double2* s2 = reinterpret_cast<const double2*>(src);
-  double2* d2 = reinterpret_cast<double2*>(dst);
+  const int n16 = (int)(n * sizeof(T) / 16), nt = tm.nt(), tid = tm.tid();
+  const double2* __restrict__ s2 = reinterpret_cast<const double2*>(src);
+  double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
   constexpr int U = 4;
-  for (int i0 = tm.tid(); i0 < n16; i0 += U * nt) {
+  const int nfull = n16 / (U * nt) * (U * nt);
+  for (int i0 = tid; i0 < nfull; i0 += U * nt) {  // no predicates: the staging registers stay registers
     double2 v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (i0 + u * nt < n16) v[u] = s2[i0 + u * nt];
+    for (int u = 0; u < U; ++u) v[u] = s2[i0 + u * nt];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (i0 + u * nt < n16) d2[i0 + u * nt] = v[u];
+    for (int u = 0; u < U; ++u) d2[i0 + u * nt] = v[u];
   }
+  for (int i = nfull + tid; i < n16; i += nt) d2[i] = s2[i];
 #else
   for (int64_t i = tm.tid(); i < n; i += tm.nt()) dst[i] = src[i];
 #endif
@@ -210,7 +210,7 @@ __host__ __device__ void copy_tile(const Team& tm, T* dst, const T* src, int64_t
 // ---- messages: Hermitian part + positive-definiteness check ---------------------------------------------------------------
 // One warp per message: right-looking Cholesky on a scratch copy; *bad is set when a pivot is not safely positive.
 template <typename T>
-__host__ __device__ void message_check(const Team& tm, const Side& sd, const T* msgs, T* H, T* scratch, int* bad) {
+__host__ __device__ __noinline__ void message_check(const Team tm, const Side& sd, const T* msgs, T* H, T* scratch, int* bad) {
   using E = Elem<T>;
   const int L = tm.lanes();
   int64_t off = 0;
@@ -293,7 +293,7 @@ struct FastDiv {
 // A thread owns whole fibres (the chi elements along one leg) of all CB columns: inputs to registers, outputs back to the
 // same places -- no ping-pong buffer; every matrix element it loads (a broadcast) feeds CB FMAs.
 template <typename T, int CB, int CHI>
-__host__ __device__ __forceinline__ void absorb_leg_fixed(const Team& tm, T* col, int rows, int prow, int st, int pad0, const T* x) {
+__host__ __device__ __forceinline__ void absorb_leg_fixed(const Team tm, T* col, int rows, int prow, int st, int pad0, const T* x) {
   using E = Elem<T>;
   const int nf = rows / CHI;
   const int pst = st >= pad0 ? st + st / pad0 : st;  // stride of the leg in the padded column (see absorb_side)
@@ -325,7 +325,7 @@ __host__ __device__ __forceinline__ void absorb_leg_fixed(const Team& tm, T* col
   tm.sync();
 }
 template <typename T, int CB>
-__host__ __device__ void absorb_leg_any(const Team& tm, T* col, int rows, int prow, int st, int pad0, int chi, const T* x) {
+__host__ __device__ void absorb_leg_any(const Team tm, T* col, int rows, int prow, int st, int pad0, int chi, const T* x) {
   using E = Elem<T>;
   const int nf = rows / chi;
   const int pst = st >= pad0 ? st + st / pad0 : st;
@@ -346,7 +346,7 @@ __host__ __device__ void absorb_leg_any(const Team& tm, T* col, int rows, int pr
   tm.sync();
 }
 template <typename T, int CB>
-__host__ __device__ void absorb_leg(const Team& tm, T* col, int rows, int prow, int st, int pad0, int chi, const T* x) {
+__host__ __device__ void absorb_leg(const Team tm, T* col, int rows, int prow, int st, int pad0, int chi, const T* x) {
   switch (chi) {
     case 2: absorb_leg_fixed<T, CB, 2>(tm, col, rows, prow, st, pad0, x); break;
     case 4: absorb_leg_fixed<T, CB, 4>(tm, col, rows, prow, st, pad0, x); break;
@@ -360,9 +360,16 @@ __host__ __device__ void absorb_leg(const Team& tm, T* col, int rows, int prow, 
 // then start an odd number of elements apart (no bank conflicts; unpadded, a warp's 32 fibres of 16 doubles share one
 // bank), and every other leg keeps a uniform stride st + st / rdim[0].
 template <typename T, int CB>
-__host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk& wk, const Tabs& tb, const T* a, const T* H, T* aout,
-                                     T* tout, T* smem) {
-  const int rows = (int)sd.rows;
+__host__ __device__ __noinline__ void absorb_side(const Team tm, const Side& sd, const Walk& wk, const Tabs tb, const T* a, const T* H, T* aout,
+                                     T* tout, T* smem, long long* stamps = nullptr) {
+#ifdef __CUDA_ARCH__
+#define BPX_ASTAMP(i) do { if (stamps && tm.tid() == 0 && c0 == 0) stamps[i] = clock64(); } while (0)
+#else
+#define BPX_ASTAMP(i) do { (void)stamps; } while (0)
+#endif
+  const int rows = (int)sd.rows, ncols = sd.cols;
+  const int32_t* __restrict__ rowt = tb.row;
+  const int32_t* __restrict__ colt = tb.col;
   const int pad0 = wk.next > 0 ? wk.rdim[0] : 1;
   const int prow = rows + rows / pad0;
   const FastDiv dpad(pad0);
@@ -371,26 +378,39 @@ __host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk&
   const int64_t hn = herm_elems(sd);
   for (int64_t i = tm.tid(); i < hn; i += tm.nt()) hs[i] = H[i];
   tm.sync();
-  for (int c0 = 0; c0 < sd.cols; c0 += CB) {
+  for (int c0 = 0; c0 < ncols; c0 += CB) {
     constexpr int U = 8;
-    const int total = rows * CB, nt = tm.nt();
-    for (int i0 = tm.tid(); i0 < total; i0 += U * nt) {
+    const int total = rows * CB, nt = tm.nt(), tid = tm.tid();
+    BPX_ASTAMP(0);
+    int cofs[CB];
+#pragma unroll
+    for (int b = 0; b < CB; ++b) cofs[b] = colt[c0 + b];
+    const int nfull = total / (U * nt) * (U * nt);
+    for (int i0 = tid; i0 < nfull; i0 += U * nt) {  // no predicates: U independent loads in flight, staged in registers
+      int ad[U];
       T v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * nt, b = i % CB, r = i / CB;
-        if (i < total) v[u] = a[tb.row[r] + tb.col[c0 + b]];
+        const int i = i0 + u * nt;
+        ad[u] = rowt[i / CB] + cofs[i % CB];
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = a[ad[u]];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = i0 + u * nt, b = i % CB, r = i / CB;
-        if (i < total) {
-          col[b * prow + r + dpad.div(r)] = v[u];
-          aout[(int64_t)r * PCP + c0 + b] = v[u];  // the matrix view, row-major: the Gram and final passes read plain tiles
-        }
+        col[b * prow + r + dpad.div(r)] = v[u];
+        aout[(int64_t)r * PCP + c0 + b] = v[u];  // the matrix view, row-major: the Gram and final passes read plain tiles
       }
     }
+    for (int i = nfull + tid; i < total; i += nt) {
+      const int b = i % CB, r = i / CB;
+      const T v = a[rowt[r] + cofs[b]];
+      col[b * prow + r + dpad.div(r)] = v;
+      aout[(int64_t)r * PCP + c0 + b] = v;
+    }
     tm.sync();
+    BPX_ASTAMP(1);
     int st = 1;
     int64_t off = 0;
     for (int k = 0; k < wk.next; ++k) {
@@ -398,13 +418,16 @@ __host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk&
       absorb_leg<T, CB>(tm, col, rows, prow, st, pad0, chi, hs + off);
       st *= chi;
       off += (int64_t)chi * chi;
+      BPX_ASTAMP(2 + k);
     }
     for (int i = tm.tid(); i < total; i += nt) {
       const int b = i % CB, r = i / CB;
       tout[(int64_t)r * PCP + c0 + b] = col[b * prow + r + dpad.div(r)];
     }
     tm.sync();
+    BPX_ASTAMP(7);
   }
+#undef BPX_ASTAMP
 }
 
 // ---- Gram pass: G[c', c] = sum_rows conj(A[row, c']) T[row, c] -------------------------------------------------------------
@@ -412,13 +435,14 @@ __host__ __device__ void absorb_side(const Team& tm, const Side& sd, const Walk&
 // an 8 x 4 lane grid accumulates the 4 x TJ block G[4 i .., TJ (j + 4 pass) ..]: per row 4 + TJ operand loads (broadcast
 // within the lane groups) feed 4 TJ FMAs.  The nw partial tiles are summed through shared memory at the end.
 template <typename T, int TJ>
-__host__ __device__ void gram_side(const Team& tm, const Side& sd, const T* at, const T* tt, T* G, T* smem) {
+__host__ __device__ __noinline__ void gram_side(const Team tm, const Side& sd, const T* at, const T* tt, T* G, T* smem) {
   using E = Elem<T>;
   constexpr int NPASS = PC / (4 * TJ);
   T* sA = smem;
   T* sT = smem + (int64_t)TRG * PCP;
   const int L = tm.lanes();
   const int cols = sd.cols;
+  const int64_t rows_all = sd.rows;
   for (int pass = 0; pass < NPASS; ++pass) {
     // host lanes (L = 1): one lane plays all 32 roles in turn, so the accumulators live in an array indexed by role
 #ifdef __CUDA_ARCH__
@@ -430,8 +454,8 @@ __host__ __device__ void gram_side(const Team& tm, const Side& sd, const T* at, 
 #else
     std::vector<T> hacc((size_t)32 * 4 * TJ, E::zero());
 #endif
-    for (int64_t row0 = 0; row0 < sd.rows; row0 += TRG) {
-      const int nr = (int)((sd.rows - row0) < TRG ? (sd.rows - row0) : TRG);
+    for (int64_t row0 = 0; row0 < rows_all; row0 += TRG) {
+      const int nr = (int)((rows_all - row0) < TRG ? (rows_all - row0) : TRG);
       copy_tile<T>(tm, sA, at + row0 * PCP, (int64_t)nr * PCP);
       copy_tile<T>(tm, sT, tt + row0 * PCP, (int64_t)nr * PCP);
 #ifdef __CUDA_ARCH__
@@ -557,7 +581,8 @@ __host__ __device__ __forceinline__ double rcp_d(double x) {
 // the co-resident CTA gets the issue slots.  A lane's rows of both columns stay in registers between the inner products
 // and the rotation (RC per column).
 template <typename T, int GS, int RC>
-__host__ __device__ __noinline__ void jacobi_groups_t(const Team& tm, T* B, int m, int n, int ld, int* flag, int* not_converged) {
+__host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m, int n, int ld, int* flag, int* not_converged,
+                                                      long long* sweeps_out) {
   using E = Elem<T>;
   const int L = tm.lanes();
   const int np = (n + 1) & ~1, npairs = np / 2;
@@ -570,8 +595,9 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team& tm, T* B, int 
   fro2 = tm.sum(fro2);
   const double zero2 = (double)n * n * EPS * EPS * fro2;
   tm.sync();
-  int f = 1;
+  int f = 1, nsweeps = 0;
   for (int sweep = 0; sweep < MAX_JACOBI_SWEEPS && f; ++sweep) {
+    ++nsweeps;
     if (tm.tid() == 0) *flag = 0;
     tm.sync();
     for (int step = 0; step < np - 1; ++step) {
@@ -667,23 +693,25 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team& tm, T* B, int 
     tm.sync();
   }
   if (f && tm.tid() == 0) BPX_FLAG_SET(not_converged);
+  if (sweeps_out && tm.tid() == 0) *sweeps_out = nsweeps;
   tm.sync();
 }
 
 template <typename T>
-__host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int ld, int* flag, int* not_converged) {
+__host__ __device__ void jacobi_groups(const Team tm, T* B, int m, int n, int ld, int* flag, int* not_converged,
+                                       long long* sweeps_out = nullptr) {
   if (n < 2) return;
 #ifdef __CUDA_ARCH__
   constexpr int RC = Elem<T>::is_complex ? 8 : 16;
   const int npairs = (n + 1) / 2;
   if (npairs >= 16)
-    jacobi_groups_t<T, 4, RC>(tm, B, m, n, ld, flag, not_converged);
+    jacobi_groups_t<T, 4, RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out);
   else if (npairs >= 4)
-    jacobi_groups_t<T, 8, RC>(tm, B, m, n, ld, flag, not_converged);
+    jacobi_groups_t<T, 8, RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out);
   else
-    jacobi_groups_t<T, 16, RC>(tm, B, m, n, ld, flag, not_converged);
+    jacobi_groups_t<T, 16, RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out);
 #else
-  jacobi_groups_t<T, 1, 1>(tm, B, m, n, ld, flag, not_converged);  // host lanes: one lane per pair
+  jacobi_groups_t<T, 1, 1>(tm, B, m, n, ld, flag, not_converged, sweeps_out);  // host lanes: one lane per pair
 #endif
 }
 
@@ -691,8 +719,8 @@ __host__ __device__ void jacobi_groups(const Team& tm, T* B, int m, int n, int l
 // G Hermitian (cols x cols, global).  Rotating the columns of G: G V = V diag(lam), so column j of the rotated copy is
 // lam_j v_j: |lam_j| = |b_j|, sign from Re(b_j^H G b_j) (a slightly indefinite G).  *bad: conditioning / convergence.
 template <typename T>
-__host__ __device__ void gram_factor(const Team& tm, int cols, int rank_max, const T* G, T* Gb, double* ev, T* R, T* Rinv, T* smem, int* flag,
-                                     int* bad) {
+__host__ __device__ __noinline__ void gram_factor(const Team tm, int cols, int rank_max, const T* G, T* Gb, double* ev, T* R, T* Rinv, T* smem, int* flag,
+                                     int* bad, long long* sweeps_out = nullptr) {
   using E = Elem<T>;
   const int ld = (cols % 16 == 0) ? cols + 8 : cols;
   T* sb = smem;
@@ -703,7 +731,7 @@ __host__ __device__ void gram_factor(const Team& tm, int cols, int rank_max, con
     sg[i] = v;
   }
   tm.sync();
-  jacobi_groups<T>(tm, sb, cols, cols, ld, flag, bad);
+  jacobi_groups<T>(tm, sb, cols, cols, ld, flag, bad, sweeps_out);
   for (int i = tm.tid(); i < cols * cols; i += tm.nt()) Gb[i] = sb[(i % cols) + ld * (i / cols)];
   tm.sync();
   for (int j = tm.tid(); j < cols; j += tm.nt()) {
@@ -762,16 +790,19 @@ __host__ __device__ void gram_factor(const Team& tm, int cols, int rank_max, con
 // column pair RT 16-byte operand loads (rows 272 bytes apart: conflict free) and NO 16-byte broadcast loads of W feed 2 RT NO
 // FMAs.
 template <typename T, int TRF, int RT, int NO>
-__host__ __device__ void final_side(const Team& tm, const Side& sd, const Tabs& tb, const T* at, T* a, const T* W, T* smem) {
+__host__ __device__ __noinline__ void final_side(const Team tm, const Side& sd, const Tabs tb, const T* at, T* a, const T* W, T* smem) {
   using E = Elem<T>;
   T* sA = smem;                                  // [r][PCP]
   T* sW = smem + (int64_t)TRF * PCP;             // [c][PC]
   for (int i = tm.tid(); i < PC * PC; i += tm.nt()) sW[i] = W[i];
   const int cols = sd.cols;
+  const int64_t rows_all = sd.rows;
+  const int32_t* __restrict__ rowt = tb.row;
+  const int32_t* __restrict__ colt = tb.col;
   constexpr int RG = TRF / RT;                   // row groups: thread rows rg, rg + RG, ..
   constexpr int OG = PC / NO;                    // output groups
-  for (int64_t row0 = 0; row0 < sd.rows; row0 += TRF) {
-    const int nr = (int)((sd.rows - row0) < TRF ? (sd.rows - row0) : TRF);
+  for (int64_t row0 = 0; row0 < rows_all; row0 += TRF) {
+    const int nr = (int)((rows_all - row0) < TRF ? (rows_all - row0) : TRF);
     copy_tile<T>(tm, sA, at + row0 * PCP, (int64_t)nr * PCP);
     for (int item = tm.tid(); item < RG * OG; item += tm.nt()) {
       const int rg = item % RG, og = item / RG;
@@ -835,11 +866,11 @@ __host__ __device__ void final_side(const Team& tm, const Side& sd, const Tabs& 
       for (int x = 0; x < RT; ++x) {
         const int r = rg + x * RG;
         if (r >= nr) continue;
-        const int64_t ra = tb.row[row0 + r];
+        const int64_t ra = rowt[row0 + r];
 #pragma unroll
         for (int y = 0; y < NO; ++y) {
           const int cp = og * NO + y;
-          if (cp < cols) a[ra + tb.col[cp]] = acc[x][y];
+          if (cp < cols) a[ra + colt[cp]] = acc[x][y];
         }
       }
     }
@@ -849,7 +880,7 @@ __host__ __device__ void final_side(const Team& tm, const Side& sd, const Tabs& 
 
 // One two-site gate.  Returns (to every thread) 0 when the gate was applied, 1 when it was left untouched for the fallback.
 template <typename T>
-__host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* sites, T* msgs, const T* ops, T* w /* this CTA's work space */,
+__host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* sites, T* msgs, const T* ops, T* w /* this CTA's work space */,
                                         double* sv_out, int normalize, int* flag, int* bad, T* smem, long long* stamps = nullptr) {
   using E = Elem<T>;
   constexpr bool CPLX = Elem<T>::is_complex;
@@ -872,14 +903,14 @@ __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* s
     BPX_STAMP(1 + 4 * a);
     const T* A = sites + sd.site_off;
     if (!CPLX && sd.cols % 2 == 0)
-      absorb_side<T, 2>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.at[a], w + L.tt, smem);
+      absorb_side<T, 2>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.at[a], w + L.tt, smem, (stamps && a == 0) ? stamps + 16 : nullptr);
     else
       absorb_side<T, 1>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.at[a], w + L.tt, smem);
     BPX_STAMP(2 + 4 * a);
     gram_side<T, CPLX ? 4 : 8>(tm, sd, w + L.at[a], w + L.tt, w + L.g[a], smem);
     BPX_STAMP(3 + 4 * a);
     gram_factor<T>(tm, sd.cols, sd.nref, w + L.g[a], w + L.gb[a], reinterpret_cast<double*>(w + L.ev[a]), w + L.r[a], w + L.rinv[a], smem,
-                   flag, bad);
+                   flag, bad, stamps ? stamps + 14 + a : nullptr);
     if (*bad) return 1;
     BPX_STAMP(4 + 4 * a);
   }
@@ -917,7 +948,7 @@ __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* s
   }
   tm.sync();
   BPX_STAMP(9);
-  jacobi_groups<T>(tm, sb, m, n, ldb, flag, bad);
+  jacobi_groups<T>(tm, sb, m, n, ldb, flag, bad, stamps ? stamps + 13 : nullptr);
   if (*bad) return 1;
   BPX_STAMP(10);
   double* sig = reinterpret_cast<double*>(w + L.sig);
@@ -1005,6 +1036,8 @@ __host__ __device__ int run_two_site_v3(const Team& tm, const GateDesc& gd, T* s
   if (sv_out)
     for (int i = tm.tid(); i < chi; i += tm.nt()) sv_out[i] = i < k ? sig[order[i]] / nrm : 0.0;
   tm.sync();
+  BPX_STAMP(12);
+#undef BPX_STAMP
   return 0;
 }
 
@@ -1030,7 +1063,7 @@ __global__ void __launch_bounds__(NT, 2) bp_apply_gates_v3(ApplyArgs3 a3) {
     const int st = run_two_site_v3<T>(tm, a.gates[g], static_cast<T*>(a.sites), static_cast<T*>(a.msgs), static_cast<const T*>(a.ops),
                                       static_cast<T*>(a.ws) + (int64_t)blockIdx.x * a3.ws_stride,
                                       a.sv_out ? a.sv_out + sv_row * a.sv_stride : nullptr, a.normalize, &flag, &bad,
-                                      reinterpret_cast<T*>(dyn_smem3), a3.stamps ? a3.stamps + 16 * g : nullptr);
+                                      reinterpret_cast<T*>(dyn_smem3), a3.stamps ? a3.stamps + 32 * g : nullptr);
     if (threadIdx.x == 0) a3.status[g] = st;
     __syncthreads();
   }
