@@ -90,6 +90,18 @@ __host__ __device__ inline Layout3 layout3_of(const GateDesc& g) {
   return L;
 }
 
+// Leading dimension of a Jacobi operand (m rows, n columns) in shared memory: with GS lanes per pair (see jacobi_groups)
+// consecutive columns must start GS doubles apart modulo the 16 double-wide banks, so that the groups of a warp hit
+// disjoint banks (ld = m puts every column of a 64-row matrix on the same banks: 4-way conflicts on every access).
+__host__ __device__ inline int jacobi_ld(int m, int n) {
+  const int npairs = (n + 1) / 2;
+  const int gs = npairs >= 16 ? 4 : (npairs >= 4 ? 8 : 16);
+  if (gs >= 16) return m;
+  int ld = m;
+  while (ld % 16 != gs) ++ld;
+  return ld;
+}
+
 // Can the fast path take this gate, and how much shared memory (elements of T) does it want?  0: not supported.
 __host__ __device__ inline int64_t smem_need(const GateDesc& g, bool cplx) {
   if (g.nsides != 2) return 0;
@@ -116,10 +128,10 @@ __host__ __device__ inline int64_t smem_need(const GateDesc& g, bool cplx) {
     need = need > fin ? need : fin;
   }
   const int64_t m = (int64_t)g.s[0].cols * g.s[0].d, n = (int64_t)g.s[1].cols * g.s[1].d;
-  const int64_t ldb = (m % 16 == 0) ? m + 8 : m;
+  const int64_t ldb = jacobi_ld((int)m, (int)n);
   const int64_t svd = ldb * n;
   need = need > svd ? need : svd;
-  const int64_t gramf = (int64_t)(PC + 8) * PC + (int64_t)PC * PC;  // rotated + unrotated Gram matrix
+  const int64_t gramf = (int64_t)(PC + 16) * PC + (int64_t)PC * PC;  // rotated + unrotated Gram matrix
   need = need > gramf ? need : gramf;
   // the cross-warp reduction of the Gram pass: 8 partial tiles of PC x (PC or PC/2) elements
   const int64_t red = 8 * (int64_t)PC * (cplx ? PC / 2 : PC);
@@ -305,21 +317,28 @@ __host__ __device__ __forceinline__ void absorb_leg_fixed(const Team tm, T* col,
     for (int b = 0; b < CB; ++b)
 #pragma unroll
       for (int l = 0; l < CHI; ++l) v[b][l] = col[b * prow + base + l * pst];
+    constexpr int GU = CHI >= 4 ? 4 : CHI;  // outputs per pass: GU * CB independent FMA chains (one chain per output is latency bound)
 #pragma unroll 1
-    for (int g = 0; g < CHI; ++g) {
-      T acc[CB];
+    for (int g0 = 0; g0 < CHI; g0 += GU) {
+      T acc[GU][CB];
 #pragma unroll
-      for (int b = 0; b < CB; ++b) acc[b] = E::zero();
+      for (int gu = 0; gu < GU; ++gu)
+#pragma unroll
+        for (int b = 0; b < CB; ++b) acc[gu][b] = E::zero();
       // x is Hermitian: x[g, l] = conj(x[l, g]), and x[l + CHI g] is contiguous in l (vector loads, one broadcast each)
-      const T* xr = x + CHI * g;
 #pragma unroll
       for (int l = 0; l < CHI; ++l) {
-        const T xv = E::conj(xr[l]);
 #pragma unroll
-        for (int b = 0; b < CB; ++b) acc[b] = E::fma(xv, v[b][l], acc[b]);
+        for (int gu = 0; gu < GU; ++gu) {
+          const T xv = E::conj(x[CHI * (g0 + gu) + l]);
+#pragma unroll
+          for (int b = 0; b < CB; ++b) acc[gu][b] = E::fma(xv, v[b][l], acc[gu][b]);
+        }
       }
 #pragma unroll
-      for (int b = 0; b < CB; ++b) col[b * prow + base + g * pst] = acc[b];
+      for (int gu = 0; gu < GU; ++gu)
+#pragma unroll
+        for (int b = 0; b < CB; ++b) col[b * prow + base + (g0 + gu) * pst] = acc[gu][b];
     }
   }
   tm.sync();
@@ -379,7 +398,7 @@ __host__ __device__ __noinline__ void absorb_side(const Team tm, const Side& sd,
   for (int64_t i = tm.tid(); i < hn; i += tm.nt()) hs[i] = H[i];
   tm.sync();
   for (int c0 = 0; c0 < ncols; c0 += CB) {
-    constexpr int U = 8;
+    constexpr int U = 16;
     const int total = rows * CB, nt = tm.nt(), tid = tm.tid();
     BPX_ASTAMP(0);
     int cofs[CB];
@@ -544,13 +563,14 @@ __host__ __device__ __noinline__ void gram_side(const Team tm, const Side& sd, c
 // 1 / sqrt(x) and 1 / x to full double accuracy from the hardware's 20-bit approximations + two Newton steps: a short
 // dependent chain (the IEEE sqrt / division sequences cost several hundred cycles of latency each, and the Jacobi steps
 // below are pure latency).  Outside the safe exponent range the exact functions are used.
+template <int STEPS = 2>
 __host__ __device__ __forceinline__ double rsqrt_d(double x) {
 #ifdef __CUDA_ARCH__
   if (!(x > 1e-280 && x < 1e280)) return rsqrt(x);
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {
+  for (int it = 0; it < STEPS; ++it) {
     const double e = fma(-x * y, y, 1.0);  // 1 - x y^2
     y = fma(0.5 * y, e, fma(0.375 * y, e * e, y));  // second-order step: y (1 + e/2 + 3 e^2 / 8)
   }
@@ -559,13 +579,14 @@ __host__ __device__ __forceinline__ double rsqrt_d(double x) {
   return 1.0 / sqrt(x);
 #endif
 }
+template <int STEPS = 2>
 __host__ __device__ __forceinline__ double rcp_d(double x) {
 #ifdef __CUDA_ARCH__
   if (!(fabs(x) > 1e-280 && fabs(x) < 1e280)) return 1.0 / x;
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #pragma unroll
-  for (int it = 0; it < 2; ++it) y = fma(y, fma(-x, y, 1.0), y);
+  for (int it = 0; it < STEPS; ++it) y = fma(y, fma(-x, y, 1.0), y);
   return y;
 #else
   return 1.0 / x;
@@ -624,6 +645,8 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
         T g = E::zero();
         T xr[RC], yr[RC];
         if (cached) {
+          double a1 = 0.0, b1 = 0.0;  // two partial sums per inner product: half the dependent-chain length
+          T g1 = E::zero();
 #pragma unroll
           for (int j = 0; j < RC; ++j) {
             const int r = sl + j * GS;
@@ -633,10 +656,19 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
               xr[j] = bp[r];
               yr[j] = bq[r];
             }
-            a += E::abs2(xr[j]);
-            b += E::abs2(yr[j]);
-            g = E::fma(E::conj(xr[j]), yr[j], g);
+            if (j & 1) {
+              a1 += E::abs2(xr[j]);
+              b1 += E::abs2(yr[j]);
+              g1 = E::fma(E::conj(xr[j]), yr[j], g1);
+            } else {
+              a += E::abs2(xr[j]);
+              b += E::abs2(yr[j]);
+              g = E::fma(E::conj(xr[j]), yr[j], g);
+            }
           }
+          a += a1;
+          b += b1;
+          g = E::add(g, g1);
         } else {
           for (int r = sl; r < m; r += GS) {
             const T x = bp[r], y = bq[r];
@@ -656,18 +688,22 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
         const double g2 = E::abs2(g);
         if (!active || !(g2 > tol2 * a * b) || !(a > zero2) || !(b > zero2)) continue;  // group-uniform, no shuffles below
         // rotation parameters on short dependent chains (rsqrt_d / rcp_d)
-        const double inv_ga = rsqrt_d(g2);
-        const T ph = scal(g, inv_ga);
+        // Any angle gives an exactly unitary rotation as long as c = 1 / sqrt(1 + t^2), s = c t and the phase are accurate:
+        // the angle itself (zeta, t) is computed with one Newton step (~1e-12, no effect on the quadratic convergence)
+        const double inv_ga = rsqrt_d<E::is_complex ? 2 : 1>(g2);
+        T ph;
+        if constexpr (E::is_complex) ph = scal(g, inv_ga);
+        else ph = from_real<T>(real_of(g) >= 0.0 ? 1.0 : -1.0);
         const double zeta = 0.5 * (b - a) * inv_ga, az = fabs(zeta);
         double t;
         if (az < 1e100) {
           const double w1 = fma(zeta, zeta, 1.0);
-          t = rcp_d(az + w1 * rsqrt_d(w1));  // 1 / (|zeta| + sqrt(1 + zeta^2))
+          t = rcp_d<1>(az + w1 * rsqrt_d<1>(w1));  // 1 / (|zeta| + sqrt(1 + zeta^2))
         } else {
-          t = 0.5 * rcp_d(az);
+          t = 0.5 * rcp_d<1>(az);
         }
         if (zeta < 0.0) t = -t;
-        const double c = rsqrt_d(fma(t, t, 1.0)), s = c * t;
+        const double c = rsqrt_d<2>(fma(t, t, 1.0)), s = c * t;
         const T sph = scal(ph, s), scph = scal(E::conj(ph), s);
         if (cached) {
 #pragma unroll
@@ -722,7 +758,7 @@ template <typename T>
 __host__ __device__ __noinline__ void gram_factor(const Team tm, int cols, int rank_max, const T* G, T* Gb, double* ev, T* R, T* Rinv, T* smem, int* flag,
                                      int* bad, long long* sweeps_out = nullptr) {
   using E = Elem<T>;
-  const int ld = (cols % 16 == 0) ? cols + 8 : cols;
+  const int ld = jacobi_ld(cols, cols);
   T* sb = smem;
   T* sg = smem + (int64_t)ld * cols;  // the unrotated matrix, for the Rayleigh quotients
   for (int i = tm.tid(); i < cols * cols; i += tm.nt()) {
@@ -934,7 +970,7 @@ __host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* si
   tm.sync();
   const T* op = ops + gd.op_off;
   const int dd = d1 * d2;
-  const int ldb = (m % 16 == 0) ? m + 8 : m;
+  const int ldb = jacobi_ld(m, n);
   T* sb = smem;
   for (int i = tm.tid(); i < m * n; i += tm.nt()) {
     const int row = i % m, col = i / m;
