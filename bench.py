@@ -76,7 +76,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg2w", "cfg3", "cfg4", "cfg5", "cfg5s", "cfg2c", "ising"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg2w", "cfg3", "cfg4", "cfg5", "cfg5s", "cfg2c", "ising", "apply"])
     ap.add_argument("--kernel", type=int, default=0, help="force a kernel family (include/bpx.h BPX_KERNEL_*)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -816,6 +816,112 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         sys.exit(3)
 
 
+def run_apply(args):
+    """`--workload apply`: layers of vertex-disjoint two-site gates (the four matchings of
+    a 64x64 chi = 16 PEPS = one Trotter step of a nearest-neighbour Hamiltonian) through bpx_apply_two_site_gates.  A step =
+    one layer.  Not BASELINE.json's metric (that is the default run); one JSON line with the gate path's own metric."""
+    import torch
+
+    pkg = entry.import_package()
+    from itnn_b200 import graphs, problems
+
+    nx = ny = 64
+    chi, d = 16, 2
+    p = problems.synthetic_peps(graphs.named_grid((nx, ny)), chi, d, np.float64)
+    ga = p.ga
+    rng = np.random.default_rng(0)
+    vid = {v: i for i, v in enumerate(ga.vertices)}
+    layers = []
+    for axis in (0, 1):
+        for parity in (0, 1):
+            es = []
+            for x in range(1, nx + 1):
+                for y in range(1, ny + 1):
+                    w = (x + 1, y) if axis == 0 else (x, y + 1)
+                    if (x if axis == 0 else y) % 2 == parity and w in vid:
+                        es.append(ga.edge_index[(vid[(x, y)], vid[w])])
+            layers.append(es)
+    dd = d * d
+
+    def ops_for(n):
+        o = rng.standard_normal((n, dd * dd))
+        return [(np.eye(dd).ravel() + 0.1 * o[i]).reshape((d,) * 4, order="F") for i in range(n)]
+
+    stream = torch.cuda.current_stream()
+    mon = ClockSampler(0)
+    with pkg.BPXContext(0) as ctx:
+        problems.upload(ctx, p)
+        ctx.sweep(3, 0.0, True)
+        times, gates = [], 0
+        for it in range(args.warmup + args.steps):
+            es = layers[it % 4]
+            ops = ops_for(len(es))
+            if it == args.warmup:
+                mon.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0.record(stream)
+            ctx.apply_two_site_gates(es, ops, max_rank=chi, normalize=True)  # synchronous C-ABI call on the library's stream
+            e1.record(stream)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+                gates += len(es)
+        clocks = mon.stop()
+        res, _ = ctx.sweep(1, 0.0, True)
+        stats = ctx.apply_stats()
+        launches = ctx.counters()["launches"]
+    value = gates / sum(times)
+    # dense work of one bulk gate on the Gram path (DESIGN.md 4.9): per tensor absorb 3 rows cols chi + Gram + final rows cols^2
+    rows, cols = chi ** 3, d * chi
+    flops_per_gate = 2.0 * 2.0 * (3 * rows * cols * chi + 2 * rows * cols * cols)
+    peaks = measure_fp64_peaks(torch)
+    out = {
+        "metric": "bp_simple_update_gates_per_s", "value": value, "unit": "gates/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{nx}x{ny} square-lattice PEPS, chi={chi}, d={d}, Float64: gate layers = the four matchings (one Trotter step)",
+                   "gates_per_step": [len(l) for l in layers],
+                   "timing": "host wall clock around the synchronous C-ABI call (operator upload, descriptors, kernel, status read-back)"},
+        "roofline": {"bound": "tensor", "achieved": value * flops_per_gate * 1e-12, "peak": peaks["sustained"], "unit": "TFLOP/s",
+                     "frac": value * flops_per_gate * 1e-12 / peaks["sustained"], "traffic": 22.1e6 * sum(len(l) for l in layers) / 4,
+                     "traffic_source": "profiles/r2y_apply_v3_chi16_ncu_summary.csv (DRAM bytes per gate x gates of a layer)",
+                     "kernel": "bp_apply_gates_v3", "flops_per_gate": flops_per_gate, "peak_source": peaks["how"]},
+        "cpu_baseline": None,
+        "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": int(np.mean([len(l) for l in layers]) * dd * dd * 8),
+                "d2h_bytes_per_step": int(np.mean([len(l) for l in layers]) * (chi * 8 + 4)),
+                "what": "the same call: gate operators from host memory in, singular values and per-gate status back; state and "
+                        "environment stay resident (they are the iterate of a simple-update evolution)"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "gates_on_gram_kernel": stats[0], "gates_declined_to_stepwise_kernel": stats[1], "residual_of_next_sweep": res,
+    }
+    if not args.no_cpu_baseline:
+        from oracle import apply_oracle as A
+
+        with pkg.BPXContext(0) as ctx:  # a fresh state for the oracle sample (the timed one has been evolved)
+            problems.upload(ctx, p)
+            ctx.sweep(3, 0.0, True)
+            msgs0 = ctx.get_messages()
+        link = lambda v, w: ("l", min(v, w), max(v, w))
+        state = {}
+        for v in range(ga.nv):
+            nb = [ga.dst[e] for e in range(ga.row_ptr[v], ga.row_ptr[v + 1])]
+            state[v] = (np.asarray(p.tensors[v]), (("s", v),) + tuple(link(v, w) for w in nb))
+        env = {(ga.src[e], ga.dst[e]): msgs0[e] for e in range(ga.ne)}
+        es = layers[0][len(layers[0]) // 2:][:2]
+        ops = ops_for(len(es))
+        t0 = time.perf_counter()
+        for e, op in zip(es, ops):
+            names = (("s", ga.src[e]), ("s", ga.dst[e]))
+            A.apply_operator((op, names, names), state, env, trunc=chi, normalize=True)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": len(es) / dt, "unit": "gates/s", "cores": 1, "kind": "port",
+                               "sample": f"{len(es)} bulk gates of layer 0, numpy oracle of apply_operators.jl:246-283 (oracle/apply_oracle.py)"}
+    print(json.dumps(out))
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -823,6 +929,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "apply":
+        if world > 1:
+            raise SystemExit("--workload apply is a single-GPU workload")
+        run_apply(args)
     elif args.single_process and args.gpus > 1 and world == 1:
         from tools import bench_single_process  # the single-process, multi-device variant (bpx_create_multi)
 
