@@ -79,7 +79,7 @@ static int upload(bpx_ctx* ctx, T** dptr, const std::vector<T>& h) {
 }
 
 // Context-cached work space: returns a buffer of at least `bytes` for role `slot`, growing it when needed.
-static const size_t WS_KEEP_BYTES = (size_t)1 << 30;
+static const size_t WS_KEEP_BYTES = (size_t)2 << 30;  // (the gate kernel wants 1.1 GiB at cfg5 shape: 296 CTAs x 3.8 MB)
 template <typename T>
 static int ws_get(bpx_ctx* ctx, int slot, size_t bytes, T** out) {
   if (bytes == 0) bytes = 8;

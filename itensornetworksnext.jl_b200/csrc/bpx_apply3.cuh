@@ -751,6 +751,28 @@ __host__ __device__ void jacobi_groups(const Team tm, T* B, int m, int n, int ld
 #endif
 }
 
+// Column order for a Jacobi operand: position of every column when they are sorted by decreasing norm (de Rijk's
+// ordering: graded matrices converge in fewer sweeps when the large columns come first).  src: m x n, leading dimension m,
+// global or shared; nrm (n doubles) and pos (n ints) are scratch / result.  Any column order is a valid input of the
+// iteration -- the callers only use order-independent results.
+template <typename T>
+__host__ __device__ void column_order(const Team tm, const T* src, int m, int n, double* nrm, int32_t* pos) {
+  using E = Elem<T>;
+  for (int j = tm.tid(); j < n; j += tm.nt()) {
+    double a = 0.0;
+    for (int r = 0; r < m; ++r) a += E::abs2(src[r + (int64_t)m * j]);
+    nrm[j] = a;
+  }
+  tm.sync();
+  for (int j = tm.tid(); j < n; j += tm.nt()) {
+    int before = 0;
+    const double a = nrm[j];
+    for (int i = 0; i < n; ++i) before += (nrm[i] > a || (nrm[i] == a && i < j)) ? 1 : 0;
+    pos[j] = before;
+  }
+  tm.sync();
+}
+
 // ---- eigen-decomposition of the Gram matrix -> R, R^+ ------------------------------------------------------------------------
 // G Hermitian (cols x cols, global).  Rotating the columns of G: G V = V diag(lam), so column j of the rotated copy is
 // lam_j v_j: |lam_j| = |b_j|, sign from Re(b_j^H G b_j) (a slightly indefinite G).  *bad: conditioning / convergence.
@@ -761,9 +783,11 @@ __host__ __device__ __noinline__ void gram_factor(const Team tm, int cols, int r
   const int ld = jacobi_ld(cols, cols);
   T* sb = smem;
   T* sg = smem + (int64_t)ld * cols;  // the unrotated matrix, for the Rayleigh quotients
+  int32_t* pos = reinterpret_cast<int32_t*>(Gb);  // (Gb is written after the iteration)
+  column_order<T>(tm, G, cols, cols, ev, pos);
   for (int i = tm.tid(); i < cols * cols; i += tm.nt()) {
     const T v = G[i];
-    sb[(i % cols) + ld * (i / cols)] = v;
+    sb[(i % cols) + ld * pos[i / cols]] = v;
     sg[i] = v;
   }
   tm.sync();
@@ -980,7 +1004,13 @@ __host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* si
       for (int x1 = 0; x1 < d1; ++x1)
         acc = E::fma(op[o1 + d1 * o2 + dd * (x1 + d1 * x2)], th0[(q1 + n1 * x1) + m * (q2 + n2 * x2)], acc);
     th1[i] = acc;
-    sb[row + (int64_t)ldb * col] = acc;
+  }
+  tm.sync();
+  {
+    double* nrm = reinterpret_cast<double*>(w + L.sig);   // (both are overwritten after the iteration)
+    int32_t* pos = reinterpret_cast<int32_t*>(w + L.order);
+    column_order<T>(tm, th1, m, n, nrm, pos);
+    for (int i = tm.tid(); i < m * n; i += tm.nt()) sb[(i % m) + (int64_t)ldb * pos[i / m]] = th1[i];
   }
   tm.sync();
   BPX_STAMP(9);
