@@ -105,22 +105,29 @@ __global__ void swizzle_sites_z3(const ItemDesc* items, int n_items, const doubl
   }
 }
 
-// compute warps: cross-warp sum of a 16x16 partial tile -> raw, handed to the epilogue warps
+// compute warps: cross-warp sum of a 16x16 partial tile -> raw, handed to the epilogue warps.
+// The partial tiles are stored in FRAGMENT order (value kk = i + 2 h + 4 mt of lane l at l + 32 kk): lane-contiguous,
+// conflict-free stores.  (In the natural order (g + 8 mt) + 16 (2 t + i + 8 h) the four t of a row land on one bank: every
+// one of the 8 stores of every warp was a 4-way conflict -- 4.7 M excessive wavefronts per cfg4 sweep,
+// profiles/r2n_onchip_smem_conflicts.txt.)  Thread el = 32 kk + l sums element el of the NCW16 tiles and puts the result
+// at its natural position in `raw`, which the epilogue warps read.
 __device__ __forceinline__ void publish16(double* red, double* raw, const double (&acc)[2][2][2], int warp, int g, int t) {
   double* mine = red + warp * MSG;
+  const int lane = 4 * g + t;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int i = 0; i < 2; ++i) mine[(g + 8 * mt) + CHI * (2 * t + i + 8 * h)] = acc[mt][h][i];
+      for (int i = 0; i < 2; ++i) mine[lane + 32 * (i + 2 * h + 4 * mt)] = acc[mt][h][i];
   onchip::bar_sync(BAR_C16, NCT16);  // partial tiles visible; every compute warp is done with X / A of this phase
-  const int el = threadIdx.x;
+  const int el = threadIdx.x;        // = 32 warp + lane for the compute warps: fragment value kk = warp of lane `lane`
   double s = 0;
 #pragma unroll
   for (int w = 0; w < NCW16; ++w) s += red[w * MSG + el];
   onchip::bar_sync(BAR_RAW_FREE16, NRAW16);  // epilogue warps have consumed the previous tile (also: red fully read)
-  raw[el] = s;
+  const int kk = warp, ki = kk & 1, kh = (kk >> 1) & 1, kmt = kk >> 2;
+  raw[(g + 8 * kmt) + CHI * (2 * t + ki + 8 * kh)] = s;
   onchip::bar_arrive(BAR_RAW_FULL16, NRAW16);
 }
 
