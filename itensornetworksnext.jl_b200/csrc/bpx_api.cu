@@ -1864,6 +1864,10 @@ static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates
   a3.ws_stride = ws_stride;
   a3.status = d_status;
   a3.stamps = nullptr;
+  if (const char* e = getenv("BPX_APPLY_GS_SHIFT")) {  // debug knob: narrower Jacobi lane groups
+    const int sh = atoi(e);
+    BPX_CUDA(ctx, cudaMemcpyToSymbol(applyk3::g_jacobi_gs_shift, &sh, sizeof(int)));
+  }
   long long* d_stamps = nullptr;
   const bool timing = getenv("BPX_APPLY_TIMING") != nullptr;  // debug: per-phase clock64 stamps, summary on stderr
   if (timing) {

@@ -93,12 +93,28 @@ __host__ __device__ inline Layout3 layout3_of(const GateDesc& g) {
 // Leading dimension of a Jacobi operand (m rows, n columns) in shared memory: with GS lanes per pair (see jacobi_groups)
 // consecutive columns must start GS doubles apart modulo the 16 double-wide banks, so that the groups of a warp hit
 // disjoint banks (ld = m puts every column of a 64-row matrix on the same banks: 4-way conflicts on every access).
-__host__ __device__ inline int jacobi_ld(int m, int n) {
+#ifdef __CUDACC__
+__device__ int g_jacobi_gs_shift = 0;  // debug knob (BPX_APPLY_GS_SHIFT): halve the lane-group width this many times
+#endif
+__host__ __device__ inline int jacobi_gs(int n, int nw) {  // lanes per column pair (measured: narrow groups win)
   const int npairs = (n + 1) / 2;
-  const int gs = npairs >= 16 ? 4 : (npairs >= 4 ? 8 : 16);
+  (void)nw;
+  int gs = npairs >= 16 ? 4 : (npairs >= 4 ? 8 : 16);
+#ifdef __CUDA_ARCH__
+  gs >>= g_jacobi_gs_shift;
+  if (gs < 1) gs = 1;
+#endif
+  return gs;
+}
+__host__ __device__ inline int jacobi_ld(int m, int n, int nw = NT / 32) {
+  const int gs = jacobi_gs(n, nw);
   if (gs >= 16) return m;
   int ld = m;
-  while (ld % 16 != gs) ++ld;
+  while (ld % 16 != 8) ++ld;  // sized for the widest rule on the host; the kernel only needs callers and callee to agree
+#ifdef __CUDA_ARCH__
+  ld = m;
+  while (ld % 16 != (gs < 2 ? 1 : gs)) ++ld;
+#endif
   return ld;
 }
 
@@ -596,10 +612,9 @@ __host__ __device__ __forceinline__ double rcp_d(double x) {
 // ---- one-sided Jacobi without V, pairs on sub-warp lane groups ---------------------------------------------------------------
 // B (m x n, leading dimension ld, shared memory) is rotated until its columns are mutually orthogonal; *not_converged is
 // set when the last sweep of the budget still rotated.  A group of GS lanes owns one column pair of the current
-// round-robin step.  The iteration is ISSUE bound (every warp pays ~200 instructions of rotation parameters, shuffles and
-// pair bookkeeping per step whatever the amount of data), so the groups are kept SMALL: few lanes per pair, many pairs
-// per warp, few warps busy (64 columns: 32 pairs on 4 warps of 8 groups) -- the other warps wait at the step barrier and
-// the co-resident CTA gets the issue slots.  A lane's rows of both columns stay in registers between the inner products
+// round-robin step.  The iteration is LATENCY bound (one dependent chain per step: loads, inner products, shuffles, rotation
+// parameters, rotation, barrier), so the groups are as wide as the team allows (64 columns on 8 warps: 8 lanes per pair,
+// 8 rows per lane): the shortest per-lane chains.  A lane's rows of both columns stay in registers between the inner products
 // and the rotation (RC per column).
 template <typename T, int GS, int RC>
 __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m, int n, int ld, int* flag, int* not_converged,
@@ -652,7 +667,7 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
             const int r = sl + j * GS;
             xr[j] = E::zero();
             yr[j] = E::zero();
-            if (r < m) {
+            if (active && r < m) {  // (groups without a pair this step must not touch the matrix: another group owns columns 0, 1)
               xr[j] = bp[r];
               yr[j] = bq[r];
             }
@@ -670,7 +685,7 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
           b += b1;
           g = E::add(g, g1);
         } else {
-          for (int r = sl; r < m; r += GS) {
+          for (int r = sl; r < m && active; r += GS) {
             const T x = bp[r], y = bq[r];
             a += E::abs2(x);
             b += E::abs2(y);
@@ -738,14 +753,14 @@ __host__ __device__ void jacobi_groups(const Team tm, T* B, int m, int n, int ld
                                        long long* sweeps_out = nullptr) {
   if (n < 2) return;
 #ifdef __CUDA_ARCH__
-  constexpr int RC = Elem<T>::is_complex ? 8 : 16;
-  const int npairs = (n + 1) / 2;
-  if (npairs >= 16)
-    jacobi_groups_t<T, 4, RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out);
-  else if (npairs >= 4)
-    jacobi_groups_t<T, 8, RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out);
-  else
-    jacobi_groups_t<T, 16, RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out);
+  constexpr int RC = 8;
+  switch (jacobi_gs(n, tm.nw)) {
+    case 1: jacobi_groups_t<T, 1, 2 * RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out); break;
+    case 2: jacobi_groups_t<T, 2, 2 * RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out); break;
+    case 4: jacobi_groups_t<T, 4, 2 * RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out); break;
+    case 8: jacobi_groups_t<T, 8, RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out); break;
+    default: jacobi_groups_t<T, 16, RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out); break;
+  }
 #else
   jacobi_groups_t<T, 1, 1>(tm, B, m, n, ld, flag, not_converged, sweeps_out);  // host lanes: one lane per pair
 #endif
