@@ -193,6 +193,12 @@ static void free_problem(bpx_ctx* c) {
   c->dims_set = false;
 }
 
+#include "bpx_pad.cuh"  // internal zero-padding of link dims 9..15 (thin parent context + one padded child)
+#define PAD(ctx, expr)                                \
+  do {                                                \
+    if ((ctx) && (ctx)->pad_active) return (expr);    \
+  } while (0)
+
 extern "C" int bpx_version(void) { return BPX_VERSION; }
 
 extern "C" int bpx_create(int device, bpx_ctx** out) {
@@ -270,6 +276,7 @@ extern "C" const char* bpx_last_error(const bpx_ctx* ctx) { return ctx ? ctx->er
 // ---- problem description -----------------------------------------------------------------------
 extern "C" int bpx_set_graph(bpx_ctx* ctx, int64_t nv, int64_t ne, const int64_t* src, const int64_t* dst,
                              const int32_t* slot) {
+  if (ctx && ctx->pad_active) bpx::pad::teardown(ctx);  // a new graph: back to a plain context
   MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_set_graph(c, nv, ne, src, dst, slot); }));
   if (!ctx) return BPX_ERR_INVALID;
   REQUIRE(ctx, nv >= 0 && ne >= 0 && (ne == 0 || (src && dst && slot)), "bpx_set_graph: bad arguments");
@@ -318,6 +325,7 @@ extern "C" int bpx_set_graph(bpx_ctx* ctx, int64_t nv, int64_t ne, const int64_t
 static int pick_kernel(bpx_ctx* ctx, const Bucket& b);
 
 extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* phys_dim, const int32_t* link_dim) {
+  if (ctx && ctx->pad_active) bpx::pad::teardown(ctx);  // dims are re-declared: decide again
   MULTI(ctx, bpx::multi::set_dims(ctx, dtype, mode, phys_dim, link_dim));
   if (!ctx) return BPX_ERR_INVALID;
   REQUIRE(ctx, ctx->graph_set, "bpx_set_dims: call bpx_set_graph first");
@@ -326,6 +334,14 @@ extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* ph
   REQUIRE(ctx, ctx->ne == 0 || link_dim, "bpx_set_dims: link_dim is NULL");
   REQUIRE(ctx, mode == BPX_MODE_SINGLE || ctx->nv == 0 || phys_dim, "bpx_set_dims: phys_dim is NULL");
   BPX_CUDA(ctx, cudaSetDevice(ctx->device));
+  {
+    std::vector<int32_t> idim;  // link dims 9..15 of degree-4 Float64 vertices: zero-padded to 16 in a child context
+    if (bpx::pad::wanted(ctx, dtype, mode, phys_dim, link_dim, idim)) {
+      for (int64_t e = 0; e < ctx->ne; ++e)
+        REQUIRE(ctx, link_dim[e] >= 1 && link_dim[e] == link_dim[ctx->rev[e]], "bpx_set_dims: bad link_dim[%lld]", (long long)e);
+      return bpx::pad::wrap(ctx, dtype, mode, phys_dim, link_dim, idim);
+    }
+  }
   free_problem(ctx);
   ctx->dtype = dtype;
   ctx->mode = mode;
@@ -577,6 +593,7 @@ extern "C" int64_t bpx_rev(const bpx_ctx* ctx, int64_t e) {
   return (ctx && ctx->graph_set && e >= 0 && e < ctx->ne) ? ctx->rev[e] : -1;
 }
 extern "C" int64_t bpx_site_offset(const bpx_ctx* ctx, int64_t v) {
+  if (ctx && ctx->pad_active) return (v >= 0 && v <= ctx->nv) ? ctx->site_off[v] : -1;  // the caller's layout
   if (ctx && !ctx->children.empty()) return bpx_site_offset(ctx->children[0], v);
   return (ctx && ctx->dims_set && v >= 0 && v <= ctx->nv) ? ctx->site_off[v] : -1;
 }
@@ -585,6 +602,7 @@ extern "C" int64_t bpx_site_device_offset(const bpx_ctx* ctx, int64_t v) {
   return (ctx && ctx->dims_set && v >= 0 && v < ctx->nv) ? ctx->dev_site_off[v] : -1;
 }
 extern "C" int64_t bpx_message_offset(const bpx_ctx* ctx, int64_t e) {
+  if (ctx && ctx->pad_active) return (e >= 0 && e <= ctx->ne) ? ctx->msg_off[e] : -1;  // the caller's layout
   if (ctx && !ctx->children.empty()) return bpx_message_offset(ctx->children[0], e);
   return (ctx && ctx->dims_set && e >= 0 && e <= ctx->ne) ? ctx->msg_off[e] : -1;
 }
@@ -597,6 +615,7 @@ extern "C" int64_t bpx_message_offset(const bpx_ctx* ctx, int64_t e) {
   } while (0)
 
 extern "C" int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed) {
+  PAD(ctx, bpx::pad::set_site_tensors(ctx, packed));
   MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_set_site_tensors(c, packed); }));
   NEED_DIMS(ctx, "bpx_set_site_tensors");
   REQUIRE(ctx, packed || ctx->site_off[ctx->nv] == 0, "bpx_set_site_tensors: NULL data");
@@ -622,6 +641,7 @@ extern "C" int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed) {
 }
 
 extern "C" int bpx_set_site_tensor(bpx_ctx* ctx, int64_t v, const void* data) {
+  PAD(ctx, bpx::pad::set_site_tensor(ctx, v, data));
   MULTI(ctx, (v < 0 || v >= ctx->nv) ? (int)BPX_ERR_INVALID : bpx::multi::fail(ctx, bpx::multi::owner_of(ctx, v), bpx_set_site_tensor(bpx::multi::owner_of(ctx, v), v, data)));
   NEED_DIMS(ctx, "bpx_set_site_tensor");
   REQUIRE(ctx, v >= 0 && v < ctx->nv && data, "bpx_set_site_tensor: bad arguments");
@@ -634,6 +654,7 @@ extern "C" int bpx_set_site_tensor(bpx_ctx* ctx, int64_t v, const void* data) {
 }
 
 extern "C" int bpx_set_messages(bpx_ctx* ctx, const void* packed) {
+  PAD(ctx, bpx::pad::set_messages(ctx, packed));
   MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_set_messages(c, packed); }));
   NEED_DIMS(ctx, "bpx_set_messages");
   REQUIRE(ctx, packed || ctx->msg_off[ctx->ne] == 0, "bpx_set_messages: NULL data");
@@ -796,6 +817,7 @@ static int sweep_host_staged_finish(bpx_ctx* ctx, double* residual_out) {
 }
 
 extern "C" int bpx_sweep_host(bpx_ctx* ctx, const void* packed_in, void* packed_out, int normalize, double* residual_out) {
+  PAD(ctx, bpx::pad::sweep_host(ctx, packed_in, packed_out, normalize, residual_out));
   MULTI(ctx, bpx::multi::sweep_host(ctx, packed_in, packed_out, normalize, residual_out));
   NEED_DIMS(ctx, "bpx_sweep_host");
   REQUIRE(ctx, (packed_in && packed_out) || ctx->msg_off[ctx->ne] == 0, "bpx_sweep_host: NULL buffer");
@@ -924,6 +946,7 @@ extern "C" int bpx_host_unregister(bpx_ctx* ctx, void* ptr) {
 }
 
 extern "C" int bpx_get_messages(bpx_ctx* ctx, void* packed) {
+  PAD(ctx, bpx::pad::get_messages(ctx, packed));
   MULTI(ctx, bpx::multi::get_messages(ctx, packed));
   NEED_DIMS(ctx, "bpx_get_messages");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
@@ -935,6 +958,7 @@ extern "C" int bpx_get_messages(bpx_ctx* ctx, void* packed) {
 }
 
 extern "C" int bpx_get_message(bpx_ctx* ctx, int64_t e, void* data) {
+  PAD(ctx, bpx::pad::get_message(ctx, e, data));
   MULTI(ctx, (e < 0 || e >= ctx->ne) ? (int)BPX_ERR_INVALID : bpx::multi::fail(ctx, bpx::multi::owner_of(ctx, MULTI0(ctx)->src[e]), bpx_get_message(bpx::multi::owner_of(ctx, MULTI0(ctx)->src[e]), e, data)));
   NEED_DIMS(ctx, "bpx_get_message");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
@@ -1387,6 +1411,7 @@ extern "C" int bpx_last_residual(bpx_ctx* ctx, double* out) {
 }
 
 extern "C" int bpx_iterate_diff(bpx_ctx* ctx, const void* other_packed, double* out) {
+  PAD(ctx, bpx::pad::iterate_diff(ctx, other_packed, out));
   MULTI(ctx, bpx::multi::fail(ctx, MULTI0(ctx), bpx_iterate_diff(MULTI0(ctx), other_packed, out)));
   NEED_DIMS(ctx, "bpx_iterate_diff");
   { int rc_ = halo_gate(ctx); if (rc_) return rc_; }
@@ -1797,6 +1822,7 @@ extern "C" int bpx_set_stream(bpx_ctx* ctx, void* cuda_stream) {
 
 // ---- the consumer of the messages: BP simple-update gate application (bpx_apply.cuh) ---------------------------
 extern "C" int bpx_get_site_tensor(bpx_ctx* ctx, int64_t v, void* data) {
+  PAD(ctx, bpx::pad::get_site_tensor(ctx, v, data));
   MULTI(ctx, (v < 0 || v >= ctx->nv) ? (int)BPX_ERR_INVALID : bpx::multi::fail(ctx, bpx::multi::owner_of(ctx, v), bpx_get_site_tensor(bpx::multi::owner_of(ctx, v), v, data)));
   NEED_DIMS(ctx, "bpx_get_site_tensor");
   REQUIRE(ctx, v >= 0 && v < ctx->nv && data, "bpx_get_site_tensor: bad arguments");
@@ -2048,6 +2074,7 @@ static int apply_owned_check(bpx_ctx* ctx, const char* name, int64_t g, int64_t 
 
 extern "C" int bpx_apply_two_site_gates(bpx_ctx* ctx, int64_t n_gates, const int64_t* edges, const void* ops_packed,
                                         int max_rank, int normalize, double* singular_values_out) {
+  PAD(ctx, bpx::pad::apply_two(ctx, n_gates, edges, ops_packed, max_rank, normalize, singular_values_out));
   MULTI(ctx, bpx::multi::apply_two(ctx, n_gates, edges, ops_packed, max_rank, normalize, singular_values_out));
   NEED_DIMS(ctx, "bpx_apply_two_site_gates");
   int rc = apply_common_checks(ctx, "bpx_apply_two_site_gates");
@@ -2252,6 +2279,7 @@ extern "C" int bpx_synchronize(bpx_ctx* ctx) {
 
 // ---- device-side synthetic inputs (benchmarks at sizes the host cannot stage) ----------------------------------
 extern "C" int bpx_fill_synthetic(bpx_ctx* ctx, uint64_t seed) {
+  PAD(ctx, bpx::pad::fill_synthetic(ctx, seed));
   MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_fill_synthetic(c, seed); }));
   NEED_DIMS(ctx, "bpx_fill_synthetic");
   REQUIRE(ctx, ctx->mode == BPX_MODE_NORM, "bpx_fill_synthetic: NORM mode only");

@@ -173,6 +173,10 @@ struct bpx_ctx {
   std::vector<bpx_ctx*> children;
   std::vector<int32_t> multi_owner;  // owner[v] = index of the child that updates the out-edges of v
   bool is_child = false;
+  // internal zero-padding of link dims 9..15 to 16 (bpx_pad.cuh): this context is a thin parent that keeps the caller's
+  // dims / packed layouts (link_dim, phys_dim, site_off, msg_off) and owns ONE child with the padded problem
+  bool pad_active = false;
+  bool no_pad = false;  // never pad (children of multi-device / padding parents)
   // children only: element runs of the messages on cut edges that point INTO this device's block; a host iterate
   // (bpx_sweep_host) uploads them too, so that one call depends on its host buffer alone
   std::vector<std::pair<int64_t, int64_t>> halo_in_runs;

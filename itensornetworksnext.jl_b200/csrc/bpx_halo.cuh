@@ -193,6 +193,7 @@ inline void halo_release(bpx_ctx* ctx) {
 }  // namespace bpx
 
 extern "C" int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32_t* owner) {
+  if (ctx && ctx->pad_active) ctx = ctx->children[0];  // zero-padded problem (bpx_pad.cuh): the child is the partitioned context
   if (!ctx) return BPX_ERR_INVALID;
   if (!ctx->children.empty()) {
     bpx::set_error(ctx, "multi-device contexts partition themselves (bpx_set_owner); the per-rank halo calls do not apply");
@@ -255,6 +256,7 @@ extern "C" int bpx_set_partition(bpx_ctx* ctx, int rank, int nranks, const int32
 
 // handles: [0..63] message set 0, [64..127] message set 1, [128..191] mailbox
 extern "C" int bpx_halo_export(bpx_ctx* ctx, void* handles_3x64) {
+  if (ctx && ctx->pad_active) ctx = ctx->children[0];  // zero-padded problem (bpx_pad.cuh): the child is the partitioned context
   if (!ctx || !handles_3x64) return BPX_ERR_INVALID;
   if (!ctx->children.empty()) {
     bpx::set_error(ctx, "multi-device contexts partition themselves (bpx_set_owner); the per-rank halo calls do not apply");
@@ -277,6 +279,7 @@ extern "C" int bpx_halo_export(bpx_ctx* ctx, void* handles_3x64) {
 // Connect peer `peer_rank` (handles from ITS bpx_halo_export).  Must be called for every rank != own rank;
 // the last call finalises the device-side peer tables.
 extern "C" int bpx_halo_connect(bpx_ctx* ctx, int peer_rank, const void* handles_3x64) {
+  if (ctx && ctx->pad_active) ctx = ctx->children[0];  // zero-padded problem (bpx_pad.cuh): the child is the partitioned context
   if (!ctx || !handles_3x64) return BPX_ERR_INVALID;
   if (!ctx->children.empty()) {
     bpx::set_error(ctx, "multi-device contexts partition themselves (bpx_set_owner); the per-rank halo calls do not apply");
@@ -305,6 +308,7 @@ extern "C" int bpx_halo_connect(bpx_ctx* ctx, int peer_rank, const void* handles
 }
 
 extern "C" int64_t bpx_num_cut_edges(const bpx_ctx* ctx) {
+  if (ctx && ctx->pad_active) ctx = ctx->children[0];
   if (ctx && !ctx->children.empty()) {
     int64_t n = 0;
     for (const bpx_ctx* c : ctx->children) n += c->n_cut;
@@ -315,6 +319,7 @@ extern "C" int64_t bpx_num_cut_edges(const bpx_ctx* ctx) {
 
 // Enqueue a cross-rank barrier on the context's stream (every rank must call it the same number of times).
 extern "C" int bpx_peer_barrier(bpx_ctx* ctx) {
+  if (ctx && ctx->pad_active) ctx = ctx->children[0];  // zero-padded problem (bpx_pad.cuh): the child is the partitioned context
   if (!ctx) return BPX_ERR_INVALID;
   if (!ctx->children.empty()) {
     for (bpx_ctx* c : ctx->children) {

@@ -122,6 +122,7 @@ static int create(const int* devices, int ndev, bpx_ctx** out) {
       return rc;  // (the create error string is already set)
     }
     c->is_child = true;
+    c->no_pad = true;  // (the parent's host-side merges use the children's own layouts)
     m->children.push_back(c);
   }
   // peer access between every pair of distinct devices (the data path of a sweep is st.global / ld.acquire.sys on peers)
