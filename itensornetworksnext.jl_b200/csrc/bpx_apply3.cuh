@@ -277,8 +277,9 @@ __host__ __device__ __noinline__ void message_check(const Team tm, const Side& s
         if (!(piv > thr)) {
           // an EXACTLY zero row / column is a zero-padded link index (the tensor is zero there too, so the reference's
           // projector on the message's support acts as the identity on it): skip it; anything else declines the gate
+          const T* h0 = H + off;  // the message itself (the scratch copy has been eliminated up to column j)
           bool zero = true;
-          for (int r = j; r < chi; ++r) zero = zero && E::is_zero(a[r + j * chi]);
+          for (int r = 0; r < chi; ++r) zero = zero && E::is_zero(h0[r + j * chi]) && E::is_zero(h0[j + r * chi]);
           if (zero) continue;
           ok = false;
           break;

@@ -186,6 +186,27 @@ def test_ragged_link_dims_and_degree_one(oracle, dtype):
     check_sweeps(oracle, ga, dtype, "norm", phys, link_dim, tensors, msgs, 2, kernel=_lib.BPX_KERNEL_GENERIC)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_ragged_link_dims_9_to_16_on_degree_3_graphs(oracle, dtype):
+    """Per-leg different link dims in 9..16 on vertices of degree 1..3 (no degree-4 vertex, so nothing is padded by
+    bpx_pad.cuh): the 16-wide slice kernels mask message fragments and stores to the true dims."""
+    g = graphs.named_comb_tree((3, 3))
+    g.add_edge((1, 3), (2, 3))
+    ga = graphs.graph_arrays(g)
+    rng = np.random.default_rng(4)
+    link_dim = [0] * ga.ne
+    for e in range(ga.ne):
+        link_dim[e] = link_dim[ga.rev[e]] = 9 + (min(e, ga.rev[e]) % 8)
+    phys = [2] * ga.nv
+    tensors = []
+    for v in range(ga.nv):
+        dims = [link_dim[f] for f in range(ga.row_ptr[v], ga.row_ptr[v + 1])]
+        tensors.append(randn(rng, dtype, (2, *dims)) / np.sqrt(np.prod(dims)))
+    msgs = positive_messages(ga, link_dim, dtype, rng)
+    buckets = check_sweeps(oracle, ga, dtype, "norm", phys, link_dim, tensors, msgs, 3)
+    assert all(b["kernel"] == _lib.BPX_KERNEL_ONCHIP for b in buckets), buckets
+
+
 def test_isolated_vertex_and_empty_graph(oracle):
     with B.BPXContext(0) as ctx:
         ctx.set_graph([], [], [], 0)
