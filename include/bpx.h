@@ -99,7 +99,10 @@ int bpx_set_graph(bpx_ctx* ctx, int64_t nv, int64_t ne, const int64_t* src, cons
                   const int32_t* slot);
 /* phys_dim[nv] (ignored, may be NULL, in SINGLE mode); link_dim[ne] with link_dim[e] == link_dim[rev e].
  * Allocates device storage for site tensors and two message sets (synchronous ping-pong), buckets the
- * directed edges by (degree, link dims, physical dim). */
+ * directed edges by (degree, link dims, physical dim).
+ * Link dimensions 9..15 on degree-4 Float64 vertices are zero-padded to 16 INSIDE the library (the chi = 16 tensor-pipe
+ * kernels then serve them; exact, see csrc/bpx_pad.cuh): every packed layout at this ABI keeps the caller's dimensions;
+ * bpx_bucket_info and the raw device pointers (bpx_device_*) show the internal ones.  BPX_NO_PAD=1 disables it. */
 int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* phys_dim, const int32_t* link_dim);
 
 int64_t bpx_num_vertices(const bpx_ctx* ctx);

@@ -222,26 +222,49 @@ static int iterate_diff(bpx_ctx* p, const void* other_packed, double* out) {
   return multi::fail(p, p->children[0], bpx_iterate_diff(p->children[0], big.data(), out));
 }
 
-// singular values come back packed by the CALLER's link dims (the padded tail is exactly zero)
+// The kept rank is capped by the CALLER's link dimension (in the child the link has 16 entries and would keep up to 16
+// singular values of the gated bond): gates are grouped by that dimension, one child call per group.  Singular values come
+// back packed by the caller's link dims.
 static int apply_two(bpx_ctx* p, int64_t n, const int64_t* edges, const void* ops, int max_rank, int normalize, double* sv_out) {
   bpx_ctx* c = p->children[0];
-  REQUIRE(p, n >= 0 && (n == 0 || (edges && ops)), "bpx_apply_two_site_gates: bad arguments");
-  if (!sv_out || n == 0) return multi::fail(p, c, bpx_apply_two_site_gates(c, n, edges, ops, max_rank, normalize, nullptr));
-  int64_t tot = 0;
+  REQUIRE(p, n >= 0 && max_rank >= 0 && (n == 0 || (edges && ops)), "bpx_apply_two_site_gates: bad arguments");
+  if (n == 0) return BPX_OK;
+  std::vector<char> used((size_t)p->nv, 0);
+  std::vector<int64_t> op_off((size_t)n + 1, 0), sv_off((size_t)n + 1, 0);
+  std::map<int, std::vector<int64_t>> groups;  // caller's link dim -> gates
   for (int64_t g = 0; g < n; ++g) {
-    REQUIRE(p, edges[g] >= 0 && edges[g] < p->ne, "bpx_apply_two_site_gates: gate %lld: edge %lld out of range", (long long)g, (long long)edges[g]);
-    tot += c->link_dim[edges[g]];
+    const int64_t e = edges[g];
+    REQUIRE(p, e >= 0 && e < p->ne, "bpx_apply_two_site_gates: gate %lld: edge %lld out of range", (long long)g, (long long)e);
+    const int32_t v1 = p->src[e], v2 = p->dst[e];
+    REQUIRE(p, !used[v1] && !used[v2], "bpx_apply_two_site_gates: gate %lld shares a vertex with an earlier gate of the batch", (long long)g);
+    used[v1] = used[v2] = 1;
+    const int64_t dd = (int64_t)p->phys_dim[v1] * p->phys_dim[v2];
+    op_off[g + 1] = op_off[g] + dd * dd;
+    sv_off[g + 1] = sv_off[g] + p->link_dim[e];
+    groups[p->link_dim[e]].push_back(g);
   }
-  std::vector<double> sv((size_t)tot);
-  // a kept rank beyond the caller's link dimension would only keep zero singular values: cap it
-  const int rc = bpx_apply_two_site_gates(c, n, edges, ops, max_rank, normalize, sv.data());
-  if (rc) return multi::fail(p, c, rc);
-  int64_t oi = 0, ou = 0;
-  for (int64_t g = 0; g < n; ++g) {
-    const int ui = p->link_dim[edges[g]], ii = c->link_dim[edges[g]];
-    memcpy(sv_out + ou, sv.data() + oi, (size_t)ui * sizeof(double));
-    ou += ui;
-    oi += ii;
+  for (auto& kv : groups) {
+    const int chi_u = kv.first;
+    const std::vector<int64_t>& gs = kv.second;
+    std::vector<int64_t> ed;
+    std::vector<double> op, sv;
+    int64_t svn = 0;
+    for (int64_t g : gs) {
+      ed.push_back(edges[g]);
+      op.insert(op.end(), (const double*)ops + op_off[g], (const double*)ops + op_off[g + 1]);
+      svn += c->link_dim[edges[g]];
+    }
+    sv.assign((size_t)svn, 0.0);
+    const int k = max_rank > 0 ? std::min(max_rank, chi_u) : chi_u;
+    const int rc = bpx_apply_two_site_gates(c, (int64_t)ed.size(), ed.data(), op.data(), k, normalize, sv_out ? sv.data() : nullptr);
+    if (rc) return multi::fail(p, c, rc);
+    if (sv_out) {
+      int64_t oi = 0;
+      for (int64_t g : gs) {
+        memcpy(sv_out + sv_off[g], sv.data() + oi, (size_t)chi_u * sizeof(double));
+        oi += c->link_dim[edges[g]];
+      }
+    }
   }
   return BPX_OK;
 }
