@@ -326,6 +326,10 @@ static int pick_kernel(bpx_ctx* ctx, const Bucket& b);
 
 extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* phys_dim, const int32_t* link_dim) {
   if (ctx && ctx->pad_active) bpx::pad::teardown(ctx);  // dims are re-declared: decide again
+  if (ctx && (dtype == BPX_F64 || dtype == BPX_C64) && (mode == BPX_MODE_NORM || mode == BPX_MODE_SINGLE)) {
+    std::vector<int32_t> idim;  // link dims 9..15 of degree-4 Float64 vertices: zero-padded to 16 in a child context
+    if (bpx::pad::wanted(ctx, dtype, mode, phys_dim, link_dim, idim)) return bpx::pad::wrap(ctx, dtype, mode, phys_dim, link_dim, idim);
+  }
   MULTI(ctx, bpx::multi::set_dims(ctx, dtype, mode, phys_dim, link_dim));
   if (!ctx) return BPX_ERR_INVALID;
   REQUIRE(ctx, ctx->graph_set, "bpx_set_dims: call bpx_set_graph first");
@@ -334,14 +338,6 @@ extern "C" int bpx_set_dims(bpx_ctx* ctx, int dtype, int mode, const int32_t* ph
   REQUIRE(ctx, ctx->ne == 0 || link_dim, "bpx_set_dims: link_dim is NULL");
   REQUIRE(ctx, mode == BPX_MODE_SINGLE || ctx->nv == 0 || phys_dim, "bpx_set_dims: phys_dim is NULL");
   BPX_CUDA(ctx, cudaSetDevice(ctx->device));
-  {
-    std::vector<int32_t> idim;  // link dims 9..15 of degree-4 Float64 vertices: zero-padded to 16 in a child context
-    if (bpx::pad::wanted(ctx, dtype, mode, phys_dim, link_dim, idim)) {
-      for (int64_t e = 0; e < ctx->ne; ++e)
-        REQUIRE(ctx, link_dim[e] >= 1 && link_dim[e] == link_dim[ctx->rev[e]], "bpx_set_dims: bad link_dim[%lld]", (long long)e);
-      return bpx::pad::wrap(ctx, dtype, mode, phys_dim, link_dim, idim);
-    }
-  }
   free_problem(ctx);
   ctx->dtype = dtype;
   ctx->mode = mode;

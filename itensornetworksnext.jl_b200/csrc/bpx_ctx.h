@@ -176,6 +176,7 @@ struct bpx_ctx {
   // internal zero-padding of link dims 9..15 to 16 (bpx_pad.cuh): this context is a thin parent that keeps the caller's
   // dims / packed layouts (link_dim, phys_dim, site_off, msg_off) and owns ONE child with the padded problem
   bool pad_active = false;
+  std::vector<int> pad_devices;  // the caller created this context with bpx_create_multi: its device list (the child is a multi context)
   bool no_pad = false;  // never pad (children of multi-device / padding parents)
   // children only: element runs of the messages on cut edges that point INTO this device's block; a host iterate
   // (bpx_sweep_host) uploads them too, so that one call depends on its host buffer alone

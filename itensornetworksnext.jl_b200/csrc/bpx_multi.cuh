@@ -439,10 +439,14 @@ static int edge_expect(bpx_ctx* m, int64_t n, const int64_t* edges, const void* 
 
 extern "C" int bpx_create_multi(const int* devices, int ndev, bpx_ctx** out) { return bpx::multi::create(devices, ndev, out); }
 
-extern "C" int bpx_num_devices(const bpx_ctx* ctx) { return !ctx ? -1 : (ctx->children.empty() ? 1 : (int)ctx->children.size()); }
+extern "C" int bpx_num_devices(const bpx_ctx* ctx) {
+  if (ctx && ctx->pad_active) ctx = ctx->children[0];  // zero-padded problem: the child is the (multi-device) context
+  return !ctx ? -1 : (ctx->children.empty() ? 1 : (int)ctx->children.size());
+}
 
 extern "C" int bpx_set_owner(bpx_ctx* ctx, const int32_t* owner) {
   if (!ctx) return BPX_ERR_INVALID;
+  if (ctx->pad_active) ctx = ctx->children[0];
   REQUIRE(ctx, !ctx->children.empty(), "bpx_set_owner: not a multi-device context (use bpx_set_partition on per-rank contexts)");
   REQUIRE(ctx, ctx->dims_set, "bpx_set_owner: call bpx_set_dims first");
   return bpx::multi::partition(ctx, owner);
@@ -450,6 +454,7 @@ extern "C" int bpx_set_owner(bpx_ctx* ctx, const int32_t* owner) {
 
 extern "C" int bpx_get_owner(const bpx_ctx* ctx, int32_t* owner_out) {
   if (!ctx || !owner_out) return BPX_ERR_INVALID;
+  if (ctx->pad_active) ctx = ctx->children[0];
   if (ctx->children.empty()) {
     for (int64_t v = 0; v < ctx->nv; ++v) owner_out[v] = ctx->owner.empty() ? 0 : ctx->owner[v];
     return BPX_OK;

@@ -8,8 +8,9 @@
 // out; everything else (sweeps, residuals, beliefs, gates) runs in the child unchanged -- all BP quantities of a
 // zero-padded network equal those of the original one exactly (padded tensor entries are zero, so every padded message
 // entry stays exactly zero, sums, inner products and norms are unchanged).  Cost: (16/chi)^4 more memory and flops for the
-// padded tensors, against a 10-40 x faster kernel.  BPX_NO_PAD=1, a forced kernel policy, complex / single-layer
-// problems and the children of a multi-device context do not pad.
+// padded tensors, against a 10 x faster kernel.  BPX_NO_PAD=1, a forced kernel policy and complex / single-layer problems
+// do not pad.  A context made by bpx_create_multi pads the same way: its child is then a multi-device context over the same
+// device list (the per-device contexts themselves never pad).
 //
 // Included by bpx_api.cu after bpx_multi.cuh (uses that file's static helpers and the public entry points).
 #pragma once
@@ -18,15 +19,20 @@ namespace bpx {
 namespace pad {
 
 // does this problem want padding?  idim = internal link dims (per directed edge)
+static bpx_ctx* lay(bpx_ctx* c) { return c->children.empty() ? c : c->children[0]; }  // who holds graph / host layouts
+
 static bool wanted(bpx_ctx* ctx, int dtype, int mode, const int32_t* phys, const int32_t* link, std::vector<int32_t>& idim) {
-  if (ctx->no_pad || getenv("BPX_NO_PAD") || ctx->kernel_policy != BPX_KERNEL_AUTO) return false;
-  if (dtype != BPX_F64 || mode != BPX_MODE_NORM || ctx->ne == 0 || !phys || !link) return false;
-  idim.assign(link, link + ctx->ne);
+  const bpx_ctx* g = lay(ctx);  // a multi-device parent keeps the graph in its children
+  if (ctx->no_pad || !g->graph_set || getenv("BPX_NO_PAD") || g->kernel_policy != BPX_KERNEL_AUTO) return false;
+  if (dtype != BPX_F64 || mode != BPX_MODE_NORM || g->ne == 0 || !phys || !link) return false;
+  for (int64_t e = 0; e < g->ne; ++e)
+    if (link[e] < 1 || link[e] != link[g->rev[e]]) return false;  // (reported by the plain path)
+  idim.assign(link, link + g->ne);
   bool any = false;
-  for (int64_t v = 0; v < ctx->nv; ++v) {
-    if (ctx->deg[v] != 4 || phys[v] != 2) continue;
+  for (int64_t v = 0; v < g->nv; ++v) {
+    if (g->deg[v] != 4 || phys[v] != 2) continue;
     bool in_range = true, all16 = true;
-    for (int32_t e : ctx->out_edge[v]) {
+    for (int32_t e : g->out_edge[v]) {
       if (link[e] < 9 || link[e] > 16) in_range = false;
       if (link[e] != 16) all16 = false;
     }
@@ -36,39 +42,77 @@ static bool wanted(bpx_ctx* ctx, int dtype, int mode, const int32_t* phys, const
   // pad EVERY link of dimension 9..15: the boundary vertices then have uniform dimension 16 as well (the tuned on-chip
   // kernel instead of ragged slices), and the padded problem is exactly the shape BASELINE config 5 exercises
   if (any)
-    for (int64_t e = 0; e < ctx->ne; ++e)
+    for (int64_t e = 0; e < g->ne; ++e)
       if (link[e] >= 9 && link[e] <= 15) idim[e] = 16;
   return any;
 }
 
+static int replay_graph(bpx_ctx* p, bpx_ctx* c) {
+  std::vector<int64_t> s64(p->src.begin(), p->src.end()), d64(p->dst.begin(), p->dst.end());
+  return bpx_set_graph(c, p->nv, p->ne, s64.data(), d64.data(), p->slot.data());
+}
+
+// back to what the caller created: a plain context, or a multi-device parent with fresh per-device children
 static void teardown(bpx_ctx* p) {
   if (!p->pad_active) return;
   for (bpx_ctx* c : p->children) bpx_destroy(c);
   p->children.clear();
   p->pad_active = false;
   p->dims_set = false;
+  for (int dev : p->pad_devices) {
+    bpx_ctx* c = nullptr;
+    if (bpx_create(dev, &c)) continue;
+    c->is_child = true;
+    c->no_pad = true;
+    if (p->graph_set) replay_graph(p, c);
+    p->children.push_back(c);
+  }
+  p->pad_devices.clear();
 }
 
-// the caller's dims and packed layouts live in the parent; the child gets the padded problem
+// the caller's dims and packed layouts live in the parent; the child (a plain context, or a multi-device context over the
+// same device list) gets the padded problem
 static int wrap(bpx_ctx* p, int dtype, int mode, const int32_t* phys, const int32_t* link, const std::vector<int32_t>& idim) {
+  const bool was_multi = !p->children.empty();
+  std::vector<int> devs;
+  std::vector<bpx_ctx*> old = p->children;
+  if (was_multi) {  // take the graph over from the children (identical in all of them)
+    const bpx_ctx* g = old[0];
+    for (bpx_ctx* c : old) devs.push_back(c->device);
+    p->nv = g->nv;
+    p->ne = g->ne;
+    p->src = g->src;
+    p->dst = g->dst;
+    p->slot = g->slot;
+    p->rev = g->rev;
+    p->deg = g->deg;
+    p->out_edge = g->out_edge;
+    p->graph_set = true;
+  }
   const int64_t nv = p->nv, ne = p->ne;
   bpx_ctx* c = nullptr;
-  int rc = bpx_create(p->device, &c);
+  int rc = was_multi ? bpx_create_multi(devs.data(), (int)devs.size(), &c) : bpx_create(p->device, &c);
   if (rc) {
     set_error(p, "bpx_set_dims: creating the padded context failed: %s", bpx_last_error(nullptr));
     return rc;
   }
   c->no_pad = true;
-  std::vector<int64_t> s64(p->src.begin(), p->src.end()), d64(p->dst.begin(), p->dst.end());
-  rc = bpx_set_graph(c, nv, ne, s64.data(), d64.data(), p->slot.data());
-  if (!rc && p->stream != p->own_stream) rc = bpx_set_stream(c, (void*)p->stream);
+  rc = replay_graph(p, c);
+  if (!rc && !was_multi && p->stream != p->own_stream) rc = bpx_set_stream(c, (void*)p->stream);
   if (!rc) rc = bpx_set_dims(c, dtype, mode, phys, idim.data());
   if (rc) {
     p->err = c->err;
     bpx_destroy(c);
     return rc;
   }
-  free_problem(p);  // the parent holds no device memory
+  if (was_multi) {
+    for (bpx_ctx* k : old) bpx_destroy(k);
+    p->children.clear();
+    p->multi_owner.clear();
+  } else {
+    free_problem(p);  // the parent holds no device memory
+  }
+  p->pad_devices = devs;
   p->dtype = dtype;
   p->mode = mode;
   p->esize = 8;
@@ -82,7 +126,7 @@ static int wrap(bpx_ctx* p, int dtype, int mode, const int32_t* phys, const int3
     p->site_off[v + 1] = p->site_off[v] + n;
   }
   for (int64_t e = 0; e < ne; ++e) p->msg_off[e + 1] = p->msg_off[e] + (int64_t)link[e] * link[e];
-  p->n_und = c->n_und;
+  p->n_und = lay(c)->n_und;
   p->children.push_back(c);
   p->pad_active = true;
   p->dims_set = true;
@@ -119,7 +163,7 @@ static int site_dims(bpx_ctx* p, int64_t v, int* udim, int* idim) {
   ++nd;
   for (int32_t e : p->out_edge[v]) {
     udim[nd] = p->link_dim[e];
-    idim[nd] = c->link_dim[e];
+    idim[nd] = lay(c)->link_dim[e];
     ++nd;
   }
   return nd;
@@ -130,7 +174,7 @@ static int set_site_tensor(bpx_ctx* p, int64_t v, const void* data) {
   bpx_ctx* c = p->children[0];
   int udim[BPX_MAX_DEGREE + 2], idim[BPX_MAX_DEGREE + 2];
   const int nd = site_dims(p, v, udim, idim);
-  std::vector<double> big((size_t)(c->site_off[v + 1] - c->site_off[v]), 0.0);
+  std::vector<double> big((size_t)(lay(c)->site_off[v + 1] - lay(c)->site_off[v]), 0.0);
   copy_block(big.data(), idim, const_cast<double*>((const double*)data), udim, nd, true);
   return multi::fail(p, c, bpx_set_site_tensor(c, v, big.data()));
 }
@@ -149,7 +193,7 @@ static int get_site_tensor(bpx_ctx* p, int64_t v, void* data) {
   bpx_ctx* c = p->children[0];
   int udim[BPX_MAX_DEGREE + 2], idim[BPX_MAX_DEGREE + 2];
   const int nd = site_dims(p, v, udim, idim);
-  std::vector<double> big((size_t)(c->site_off[v + 1] - c->site_off[v]));
+  std::vector<double> big((size_t)(lay(c)->site_off[v + 1] - lay(c)->site_off[v]));
   const int rc = bpx_get_site_tensor(c, v, big.data());
   if (rc) return multi::fail(p, c, rc);
   copy_block(big.data(), idim, (double*)data, udim, nd, false);
@@ -158,7 +202,7 @@ static int get_site_tensor(bpx_ctx* p, int64_t v, void* data) {
 
 // whole message sets: user packed <-> internal packed (host)
 static void embed_messages(bpx_ctx* p, const double* user, std::vector<double>& big) {
-  bpx_ctx* c = p->children[0];
+  bpx_ctx* c = lay(p->children[0]);
   big.assign((size_t)c->msg_off[c->ne], 0.0);
   for (int64_t e = 0; e < p->ne; ++e) {
     const int ud[2] = {p->link_dim[e], p->link_dim[e]}, id[2] = {c->link_dim[e], c->link_dim[e]};
@@ -166,7 +210,7 @@ static void embed_messages(bpx_ctx* p, const double* user, std::vector<double>& 
   }
 }
 static void slice_messages(bpx_ctx* p, std::vector<double>& big, double* user) {
-  bpx_ctx* c = p->children[0];
+  bpx_ctx* c = lay(p->children[0]);
   for (int64_t e = 0; e < p->ne; ++e) {
     const int ud[2] = {p->link_dim[e], p->link_dim[e]}, id[2] = {c->link_dim[e], c->link_dim[e]};
     copy_block(big.data() + c->msg_off[e], id, user + p->msg_off[e], ud, 2, false);
@@ -183,7 +227,7 @@ static int set_messages(bpx_ctx* p, const void* packed) {
 static int get_messages(bpx_ctx* p, void* packed) {
   REQUIRE(p, packed || p->msg_off[p->ne] == 0, "bpx_get_messages: NULL buffer");
   bpx_ctx* c = p->children[0];
-  std::vector<double> big((size_t)c->msg_off[c->ne]);
+  std::vector<double> big((size_t)lay(c)->msg_off[lay(c)->ne]);
   const int rc = bpx_get_messages(c, big.data());
   if (rc) return multi::fail(p, c, rc);
   slice_messages(p, big, (double*)packed);
@@ -193,10 +237,10 @@ static int get_messages(bpx_ctx* p, void* packed) {
 static int get_message(bpx_ctx* p, int64_t e, void* data) {
   REQUIRE(p, e >= 0 && e < p->ne && data, "bpx_get_message: bad arguments");
   bpx_ctx* c = p->children[0];
-  std::vector<double> big((size_t)(c->msg_off[e + 1] - c->msg_off[e]));
+  std::vector<double> big((size_t)(lay(c)->msg_off[e + 1] - lay(c)->msg_off[e]));
   const int rc = bpx_get_message(c, e, big.data());
   if (rc) return multi::fail(p, c, rc);
-  const int ud[2] = {p->link_dim[e], p->link_dim[e]}, id[2] = {c->link_dim[e], c->link_dim[e]};
+  const int ud[2] = {p->link_dim[e], p->link_dim[e]}, id[2] = {lay(c)->link_dim[e], lay(c)->link_dim[e]};
   copy_block(big.data(), id, (double*)data, ud, 2, false);
   return BPX_OK;
 }
@@ -252,7 +296,7 @@ static int apply_two(bpx_ctx* p, int64_t n, const int64_t* edges, const void* op
     for (int64_t g : gs) {
       ed.push_back(edges[g]);
       op.insert(op.end(), (const double*)ops + op_off[g], (const double*)ops + op_off[g + 1]);
-      svn += c->link_dim[edges[g]];
+      svn += lay(c)->link_dim[edges[g]];
     }
     sv.assign((size_t)svn, 0.0);
     const int k = max_rank > 0 ? std::min(max_rank, chi_u) : chi_u;
@@ -262,7 +306,7 @@ static int apply_two(bpx_ctx* p, int64_t n, const int64_t* edges, const void* op
       int64_t oi = 0;
       for (int64_t g : gs) {
         memcpy(sv_out + sv_off[g], sv.data() + oi, (size_t)chi_u * sizeof(double));
-        oi += c->link_dim[edges[g]];
+        oi += lay(c)->link_dim[edges[g]];
       }
     }
   }
@@ -305,23 +349,27 @@ static int fill_synthetic(bpx_ctx* p, uint64_t seed) {
   std::vector<int32_t> ud((size_t)p->nv * BPX_MAX_DEGREE, 0);
   for (int64_t v = 0; v < p->nv; ++v)
     for (int k = 0; k < p->deg[v]; ++k) ud[(size_t)v * BPX_MAX_DEGREE + k] = p->link_dim[p->out_edge[v][k]];
-  int32_t *d_ud = nullptr, *d_ul = nullptr, *d_il = nullptr;
-  if ((rc = upload(c, &d_ud, ud)) || (rc = upload(c, &d_ul, p->link_dim)) || (rc = upload(c, &d_il, c->link_dim))) {
+  std::vector<bpx_ctx*> leaves = c->children.empty() ? std::vector<bpx_ctx*>{c} : c->children;
+  for (bpx_ctx* l : leaves) {  // every device masks the tensors it holds and its copies of the message sets
+    BPX_CUDA(p, cudaSetDevice(l->device));
+    int32_t *d_ud = nullptr, *d_ul = nullptr, *d_il = nullptr;
+    if ((rc = upload(l, &d_ud, ud)) || (rc = upload(l, &d_ul, p->link_dim)) || (rc = upload(l, &d_il, l->link_dim))) {
+      cudaFree(d_ud);
+      cudaFree(d_ul);
+      return multi::fail(p, l, rc);
+    }
+    dim3 grid(32, (unsigned)std::min<int64_t>(std::max<int64_t>(p->nv, 1), 4096));
+    mask_sites<<<grid, 256, 0, l->stream>>>(l->d_vdesc, l->nv, d_ud, (double*)l->d_sites);
+    if (p->ne > 0)
+      mask_messages<<<(unsigned)p->ne, 128, 0, l->stream>>>(l->d_msg_off, d_il, d_ul, p->ne, (double*)l->d_msg[0], (double*)l->d_msg[1]);
+    const cudaError_t ce = cudaGetLastError(), ce2 = cudaStreamSynchronize(l->stream);
     cudaFree(d_ud);
     cudaFree(d_ul);
-    return multi::fail(p, c, rc);
+    cudaFree(d_il);
+    l->sites_dirty = true;
+    BPX_CUDA(p, ce);
+    BPX_CUDA(p, ce2);
   }
-  dim3 grid(32, (unsigned)std::min<int64_t>(std::max<int64_t>(p->nv, 1), 4096));
-  mask_sites<<<grid, 256, 0, c->stream>>>(c->d_vdesc, c->nv, d_ud, (double*)c->d_sites);
-  if (p->ne > 0)
-    mask_messages<<<(unsigned)p->ne, 128, 0, c->stream>>>(c->d_msg_off, d_il, d_ul, p->ne, (double*)c->d_msg[0], (double*)c->d_msg[1]);
-  const cudaError_t ce = cudaGetLastError(), ce2 = cudaStreamSynchronize(c->stream);
-  cudaFree(d_ud);
-  cudaFree(d_ul);
-  cudaFree(d_il);
-  c->sites_dirty = true;
-  BPX_CUDA(p, ce);
-  BPX_CUDA(p, ce2);
   return BPX_OK;
 }
 

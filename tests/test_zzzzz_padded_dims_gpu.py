@@ -145,15 +145,37 @@ def test_padded_synthetic_data_is_zero_outside_the_callers_dims():
         assert np.isfinite(ctx.bethe_free_energy())
 
 
-def test_children_of_a_multi_device_context_do_not_pad(oracle):
+def test_multi_device_context_pads_too(oracle):
+    """A context over two devices: the padded child is a multi-device context over the same device list (the per-device
+    contexts themselves never pad).  Needs two GPUs (two sliced kernels cannot share one device)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
     rng = np.random.default_rng(3)
-    ga, link, tensors = lattice((4, 4), CASES["chi12"], rng)
+    ga, link, tensors = lattice((6, 6), CASES["chi12"], rng)
     msgs = positive_messages(rng, link)
     p = oracle.make_problem(ga, tensors, "norm")
-    with B.BPXContext(devices=[0, 0]) as ctx:
+    with B.BPXContext(devices=[0, 1]) as ctx:
         ctx.set_graph(ga.src, ga.dst, ga.slot, ga.nv)
         ctx.set_dims(np.float64, "norm", [2] * ga.nv, link)
+        assert ctx.lib.bpx_num_devices(ctx.h) == 2
+        kinds = {b["degree"]: (b["kernel"], b["chi"]) for b in ctx.buckets()}
+        assert kinds[4] == (_lib.BPX_KERNEL_SLICED, 16)
         ctx.set_site_tensors(tensors)
         ctx.set_messages(msgs)
-        ctx.sweep(1, 0.0, True)
-        assert rel_err(ctx.get_messages(), oracle.sweep_jacobi(p, msgs, True)) < MSG_RTOL
+        want = list(msgs)
+        for k in range(2):
+            prev, want = want, oracle.sweep_jacobi(p, want, True)
+            res, done = ctx.sweep(1, 0.0, True)
+            assert rel_err(ctx.get_messages(), want) < MSG_RTOL
+            assert abs(res - oracle.iterate_diff(want, prev)) < 1e-11
+        assert np.allclose(ctx.vertex_scalars(), oracle.vertex_scalars(p, want), rtol=1e-10)
+        f = ctx.bethe_free_energy()
+        assert abs(f - oracle.bethe_free_energy(p, want)) <= 1e-10 * abs(f)
+        assert np.array_equal(ctx.get_site_tensor(ga.nv // 2), np.asarray(tensors[ga.nv // 2]).ravel(order="F"))
+        # re-declaring the dims (here: unpadded shape 8) turns the handle back into a plain two-device context
+        link8 = [8] * ga.ne
+        ctx.set_dims(np.float64, "norm", [2] * ga.nv, link8)
+        assert ctx.lib.bpx_num_devices(ctx.h) == 2
+        assert {b["degree"]: b["chi"] for b in ctx.buckets()}[4] == 8
