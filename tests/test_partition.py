@@ -132,12 +132,12 @@ def test_plan_counts_strips():
 
 
 # ---------------------------------------------------------------------------------------------------
-def _worker_gpu(rank, world, port, nsweeps, q):
+def _worker_gpu(rank, world, port, nsweeps, q, chi=8):
     pkg, o = _setup(rank, world, port, "gloo")
     from itnn_b200 import partition, problems
 
     torch.cuda.set_device(rank)
-    g, p = _problem(pkg, dims=(8, 12), chi=8)
+    g, p = _problem(pkg, dims=(8, 12), chi=chi)
     owner = partition.strip_owner(p.ga.vertices, world, axis=1)
     ctx = pkg.BPXContext(rank)
     problems.upload(ctx, p)
@@ -173,14 +173,15 @@ def _worker_gpu(rank, world, port, nsweeps, q):
 
 
 @pytest.mark.gpu
-def test_two_rank_partition_gpu_peer_halo():
+@pytest.mark.parametrize("chi", [8, 12])  # 12: every rank's context zero-pads its links to 16 (csrc/bpx_pad.cuh)
+def test_two_rank_partition_gpu_peer_halo(chi):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world, nsweeps = 2, 3
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_gpu, args=(r, world, port, nsweeps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker_gpu, args=(r, world, port, nsweeps, q, chi)) for r in range(world)]
     for pr in procs:
         pr.start()
     results = [q.get(timeout=300) for _ in range(world)]
@@ -191,7 +192,7 @@ def test_two_rank_partition_gpu_peer_halo():
     import __graft_entry__ as entry
 
     pkg, o = entry.import_package(), entry.import_oracle()
-    g, p = _problem(pkg, dims=(8, 12), chi=8)
+    g, p = _problem(pkg, dims=(8, 12), chi=chi)
     op = o.make_problem(p.ga, p.tensors, "norm")
     want = list(p.messages)
     hist = []
