@@ -160,6 +160,7 @@ class MessageCache:
     def __init__(self, messages=None):
         self._m: Dict[NamedEdge, object] = {}
         self._session: Optional["_Session"] = None
+        self._session_version = -1  # version of the session's device message set that equals this cache's values
         if messages is not None:
             items = messages.items() if hasattr(messages, "items") else messages
             for e, m in items:
@@ -283,6 +284,10 @@ class _Session:
         self.ctx.set_dims(self.cp.dtype, self.cp.mode, self.cp.phys_dim if self.cp.mode == "norm" else None,
                           self.cp.link_dim)
         self.ctx.set_site_tensors(self.cp.tensors)
+        self.version = 0  # bumped whenever the device message set changes (uploads, sweeps, single updates)
+
+    def touched(self):
+        self.version += 1
 
     def _msg_array(self, e: int, m) -> np.ndarray:
         if isinstance(m, ITensor):
@@ -300,6 +305,8 @@ class _Session:
                 raise KeyError(f"no message on edge {ne_!r}")
             msgs.append(self._msg_array(e, cache[ne_]))
         self.ctx.set_messages(msgs)
+        self.touched()
+        cache._session_version = self.version
 
     def download_messages(self, like: MessageCache) -> MessageCache:
         ga = self.cp.ga
@@ -320,12 +327,16 @@ class _Session:
             out[ne_] = ITensor(arrs[e], inds)
         c = MessageCache(out)
         c._session = self
+        c._session_version = self.version
         return c
 
 
 def _session_for(factors, cache: MessageCache, device: int = 0) -> _Session:
     s = cache._session
     if s is not None and s.factors is factors:
+        # the session may have moved on (another cache swept or updated it): make the device set equal THIS cache again
+        if cache._session_version != s.version:
+            s.upload_messages(cache)
         return s
     s = _Session(factors, device)
     s.upload_messages(cache)
@@ -382,11 +393,13 @@ def beliefpropagation(factors, messages, *, edges=None, stopping_criterion=None,
         if edges is not None:
             raise ArgumentError("`edges` selects the sequential schedule; the synchronous sweep updates every edge")
         res, done = session.ctx.sweep(maxiter, tol if tol is not None else 0.0, alg.normalize)
+        session.touched()
     elif alg.schedule == "sequential":
         if edges is None:
             edges = default_beliefpropagation_edges(factors)
         seq = [session.cp.ga.edge_id(e) for e in edges]
         res, done = session.ctx.sweep_sequence(seq, maxiter, tol if tol is not None else 0.0, alg.normalize)
+        session.touched()
     else:
         raise ArgumentError(f"unknown schedule {alg.schedule!r}")
     if info is not None:
@@ -527,6 +540,7 @@ class DeviceMessageCache(MessageCache):
         else:
             seq = [ga.edge_id(e) for e in (edges if edges is not None else default_beliefpropagation_edges(self._session.factors))]
             res, _ = ctx.sweep_sequence(seq, 1, 0.0, alg.normalize)
+        self._session.touched()
         self._version += 1
         self._last_residual = res
         return res
@@ -564,9 +578,11 @@ def message_update(cache: MessageCache, factors, edge, alg=None, **kwargs) -> Me
     s = _session_for(factors, cache, alg.device)
     e = to_edge(edge)
     s.ctx.sweep_sequence([s.cp.ga.edge_id(e)], 1, 0.0, alg.normalize)
+    s.touched()
     new = s.download_messages(cache)
     cache._m[e] = new[e]
     cache._session = s
+    cache._session_version = s.version
     return cache
 
 
@@ -575,6 +591,8 @@ def iterate_diff(cache1: MessageCache, cache2: MessageCache) -> float:
     s = cache1._session
     if s is None:
         raise ArgumentError("iterate_diff needs a cache produced by (or uploaded for) a device session")
+    if cache1._session_version != s.version:  # the session has moved on: the device set must equal cache1
+        s.upload_messages(cache1)
     ga = s.cp.ga
     other = [s._msg_array(e, cache2[ga.named_edge(e)]) for e in range(ga.ne)]
     return s.ctx.iterate_diff(other)
@@ -600,6 +618,8 @@ def _edge_session(messages: MessageCache, factors=None) -> _Session:
         return _session_for(factors, messages)
     if messages._session is None:
         raise ArgumentError("edge scalars run on the device: pass `factors=` or a cache returned by beliefpropagation")
+    if messages._session_version != messages._session.version:
+        messages._session.upload_messages(messages)
     return messages._session
 
 

@@ -43,3 +43,28 @@ def test_bp_ai_layer_gpu(schedule):
     from test_algorithmsinterface import check_bp_ai_layer
 
     check_bp_ai_layer(schedule)
+
+
+def test_a_cache_keeps_its_own_values_when_its_session_moves_on(oracle):
+    """Two host caches share one device session (beliefpropagation.py `_session_for`): after the session has swept for the
+    second cache, beliefs of the FIRST cache must still be those of the first cache's messages (the session is
+    tagged with a version and re-uploads the cache that asks)."""
+    import itnn_b200 as B
+    from itnn_b200 import graphs
+
+    g = graphs.named_grid((3, 3))
+    tn, _, _ = B.random_state(np.float64, g, d=2, chi=3, rng=np.random.default_rng(5))
+    nn = B.normnetwork(tn)
+    env0 = B.message_environment(B.ones_message, nn)
+    env1 = B.beliefpropagation(nn, env0, stopping_criterion=dict(maxiter=1), message_update_algorithm=B.B200MessageUpdate())
+    f1 = B.bethe_free_energy(nn, env1)
+    vs1 = np.array(B.vertex_scalars(nn, env1))
+    # advance the SAME session through another cache (single-edge updates re-use env1's session)
+    env2 = B.MessageCache(dict(env1.items()))
+    env2._session, env2._session_version = env1._session, env1._session_version
+    e = next(iter(dict(env2.items())))
+    for _ in range(3):
+        B.message_update(env2, nn, e)
+    assert env2._session is env1._session and env1._session_version != env1._session.version
+    assert np.allclose(np.array(B.vertex_scalars(nn, env1)), vs1, rtol=1e-13)
+    assert abs(B.bethe_free_energy(nn, env1) - f1) <= 1e-12 * abs(f1)
