@@ -886,9 +886,10 @@ def run_apply(args):
                    "gates_per_step": [len(l) for l in layers],
                    "timing": "host wall clock around the synchronous C-ABI call (operator upload, descriptors, kernel, status read-back)"},
         "roofline": {"bound": "tensor", "achieved": value * flops_per_gate * 1e-12, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                     "frac": value * flops_per_gate * 1e-12 / peaks["sustained"], "traffic": 22.1e6 * sum(len(l) for l in layers) / 4,
-                     "traffic_source": "profiles/r2y_apply_v3_chi16_ncu_summary.csv (DRAM bytes per gate x gates of a layer)",
-                     "kernel": "bp_apply_gates_v3", "flops_per_gate": flops_per_gate, "peak_source": peaks["how"]},
+                     "frac": value * flops_per_gate * 1e-12 / peaks["sustained"], "traffic": None,
+                     "traffic_source": "not captured for the three-kernel path (the one-kernel version moved 22.1 MB of DRAM traffic per "
+                                       "gate: profiles/r2y_apply_v3_chi16_ncu_summary.csv)",
+                     "kernel": "bp_apply3_sides + bp_apply3_bond + bp_apply3_final", "flops_per_gate": flops_per_gate, "peak_source": peaks["how"]},
         "cpu_baseline": None,
         "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": int(np.mean([len(l) for l in layers]) * dd * dd * 8),
                 "d2h_bytes_per_step": int(np.mean([len(l) for l in layers]) * (chi * 8 + 4)),

@@ -1842,37 +1842,88 @@ static void apply_fill_side(bpx_ctx* ctx, applyk::Side& s, int64_t v, int bond_s
   applyk::finish_side(s, chi_b);
 }
 
-// Version 3 of the two-site kernel (bpx_apply3.cuh, the Gram path): ONE launch for the whole batch, a work space per
-// CTA.  Gates it declines (status 1: rank-deficient / indefinite message, ill-conditioned Gram matrix) come back in
-// `rest` for the step-by-step versions.  *taken = false: the batch has a shape the kernel does not take (nothing ran).
+// Version 3 of the two-site gates (bpx_apply3.cuh, the Gram path): three kernels per chunk of the batch -- (gate, side)
+// CTAs absorb the messages and form the Gram matrices, one small CTA per gate solves the bond problem, (gate, side) CTAs
+// write A' = A W -- with a work space per gate of the chunk.  Gates it declines (status 1: rank-deficient / indefinite
+// message, ill-conditioned Gram matrix) come back in `rest` for the step-by-step versions, untouched.
+// *taken = false: the batch has a shape the kernels do not take (nothing ran).
+template <typename T>
+static int apply_launch_v3(bpx_ctx* ctx, const applyk3::ApplyArgs3& a3, const int bytes[3], const int grid[3], int bond_ctas,
+                           cudaEvent_t* ev /* 4 events (debug timing) or NULL */) {
+  const int64_t ng = a3.g1 - a3.g0;
+  if (ev) cudaEventRecord(ev[0], ctx->stream);
+  applyk3::bp_apply3_sides<T><<<(int)std::min<int64_t>(2 * ng, grid[0]), applyk::NT, bytes[0], ctx->stream>>>(a3);
+  if (ev) cudaEventRecord(ev[1], ctx->stream);
+  const int gb = (int)std::min<int64_t>(ng, grid[1]);
+  constexpr int HI = Elem<T>::is_complex ? 3 : 5;
+  if (bond_ctas >= HI)
+    applyk3::bp_apply3_bond<T, HI><<<gb, applyk3::NT_BOND, bytes[1], ctx->stream>>>(a3);
+  else
+    applyk3::bp_apply3_bond<T, HI - 1><<<gb, applyk3::NT_BOND, bytes[1], ctx->stream>>>(a3);
+  if (ev) cudaEventRecord(ev[2], ctx->stream);
+  applyk3::bp_apply3_final<T><<<(int)std::min<int64_t>(2 * ng, grid[2]), applyk::NT, bytes[2], ctx->stream>>>(a3);
+  if (ev) cudaEventRecord(ev[3], ctx->stream);
+  ctx->n_launches += 3;
+  BPX_CUDA(ctx, cudaGetLastError());
+  return BPX_OK;
+}
+template <typename T>
+static int apply_prepare_v3(bpx_ctx* ctx, const int bytes[3], int bond_ctas, int per_sm[3]) {
+  int rc;
+  constexpr int HI = Elem<T>::is_complex ? 3 : 5;
+  if ((rc = set_smem(ctx, applyk3::bp_apply3_sides<T>, bytes[0]))) return rc;
+  if ((rc = set_smem(ctx, applyk3::bp_apply3_final<T>, bytes[2]))) return rc;
+  BPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], applyk3::bp_apply3_sides<T>, applyk::NT, bytes[0]));
+  BPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], applyk3::bp_apply3_final<T>, applyk::NT, bytes[2]));
+  if (bond_ctas >= HI) {
+    if ((rc = set_smem(ctx, applyk3::bp_apply3_bond<T, HI>, bytes[1]))) return rc;
+    BPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], applyk3::bp_apply3_bond<T, HI>, applyk3::NT_BOND, bytes[1]));
+  } else {
+    if ((rc = set_smem(ctx, applyk3::bp_apply3_bond<T, HI - 1>, bytes[1]))) return rc;
+    BPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], applyk3::bp_apply3_bond<T, HI - 1>, applyk3::NT_BOND, bytes[1]));
+  }
+  return BPX_OK;
+}
+
 static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates, const applyk::GateDesc* d_gates, const char* d_ops,
                         int normalize, double* sv_dev, int64_t sv_stride, std::vector<applyk::GateDesc>& rest, bool* taken) {
   *taken = false;
   const int64_t ng = (int64_t)gates.size();
   const bool cplx = ctx->dtype != BPX_F64;
-  int64_t smem_elems = 0, ws_stride = 0;
+  applyk3::SmemNeed3 need = {0, 0, 0};
+  int64_t ws_stride = 0, tt_stride = 0;
   for (int64_t g = 0; g < ng; ++g) {
-    const int64_t need = applyk3::smem_need(gates[g], cplx);
-    if (need == 0) return BPX_OK;
-    smem_elems = std::max(smem_elems, need);
-    ws_stride = std::max(ws_stride, applyk3::layout3_of(gates[g]).total);
+    const applyk3::SmemNeed3 nd = applyk3::smem_need3(gates[g], cplx);
+    if (nd.all() == 0) return BPX_OK;
+    need.sides = std::max(need.sides, nd.sides);
+    need.bond = std::max(need.bond, nd.bond);
+    need.fin = std::max(need.fin, nd.fin);
+    ws_stride = std::max(ws_stride, applyk3::layout3_of(gates[g], false).total);
+    tt_stride = std::max(tt_stride, (applyk3::tt_elems(gates[g]) + 1) & ~(int64_t)1);
   }
-  const int bytes = (int)(smem_elems * ctx->esize);
-  if (bytes > ctx->max_smem_optin - 1024) return BPX_OK;
-  int rc, per_sm = 0;
-  if (ctx->dtype == BPX_F64) {
-    if ((rc = set_smem(ctx, applyk3::bp_apply_gates_v3<double>, bytes))) return rc;
-    BPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, applyk3::bp_apply_gates_v3<double>, applyk::NT, bytes));
-  } else {
-    if ((rc = set_smem(ctx, applyk3::bp_apply_gates_v3<c64>, bytes))) return rc;
-    BPX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, applyk3::bp_apply_gates_v3<c64>, applyk::NT, bytes));
-  }
-  if (per_sm < 1) return BPX_OK;
-  const int grid = (int)std::min<int64_t>(ng, (int64_t)ctx->num_sms * per_sm);
-  char* d_ws = nullptr;
+  const int bytes[3] = {(int)(need.sides * ctx->esize), (int)(need.bond * ctx->esize), (int)(need.fin * ctx->esize)};
+  for (int i = 0; i < 3; ++i)
+    if (bytes[i] > ctx->max_smem_optin - 1024) return BPX_OK;
+  // resident CTAs per SM the bond kernel is compiled for: 4 (128 registers) / 2 for ComplexF64; one more (96 registers,
+  // spills in the Jacobi steps) measured 20 % / 3 % slower (profiles/r2as_*); BPX_APPLY_BOND_CTAS=5 / 3 selects it
+  int bond_ctas = cplx ? 2 : 4;
+  if (const char* e = getenv("BPX_APPLY_BOND_CTAS")) bond_ctas = atoi(e);
+  int rc, per_sm[3] = {0, 0, 0};
+  if ((rc = cplx ? apply_prepare_v3<c64>(ctx, bytes, bond_ctas, per_sm) : apply_prepare_v3<double>(ctx, bytes, bond_ctas, per_sm))) return rc;
+  if (per_sm[0] < 1 || per_sm[1] < 1 || per_sm[2] < 1) return BPX_OK;
+  const int grid[3] = {ctx->num_sms * per_sm[0], ctx->num_sms * per_sm[1], ctx->num_sms * per_sm[2]};
+  // chunks: as many gates as fit the work-space budget, in whole waves of the side kernel when there are several chunks
+  int64_t budget = (int64_t)3 << 29;  // 1.5 GiB: stays in the context's cached arena
+  if (const char* e = getenv("BPX_APPLY_WS_BYTES")) budget = std::max<int64_t>(1, atoll(e));  // tests: force several chunks
+  int64_t chunk = std::max<int64_t>(1, budget / (ws_stride * ctx->esize));
+  if (chunk < ng && chunk > grid[0] / 2) chunk -= chunk % (grid[0] / 2);
+  chunk = std::min(chunk, ng);
+  char *d_ws = nullptr, *d_tt = nullptr;
   int32_t* d_status = nullptr;
-  if ((rc = ws_get(ctx, bpx_ctx::WS_WORK, (size_t)grid * ws_stride * ctx->esize, &d_ws))) return rc;
+  if ((rc = ws_get(ctx, bpx_ctx::WS_WORK, (size_t)chunk * ws_stride * ctx->esize, &d_ws))) return rc;
+  if ((rc = ws_get(ctx, bpx_ctx::WS_SCRATCH, (size_t)std::min<int64_t>(2 * chunk, grid[0]) * tt_stride * ctx->esize, &d_tt))) return rc;
   if ((rc = ws_get(ctx, bpx_ctx::WS_LIST, (size_t)ng * sizeof(int32_t), &d_status))) return rc;
+  BPX_CUDA(ctx, cudaMemsetAsync(d_status, 0, (size_t)ng * sizeof(int32_t), ctx->stream));
   applyk3::ApplyArgs3 a3;
   a3.base.gates = d_gates;
   a3.base.n_gates = ng;
@@ -1884,54 +1935,74 @@ static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates
   a3.base.sv_stride = sv_stride;
   a3.base.normalize = normalize;
   a3.ws_stride = ws_stride;
+  a3.tt = d_tt;
+  a3.tt_stride = tt_stride;
   a3.status = d_status;
   a3.stamps = nullptr;
-  if (const char* e = getenv("BPX_APPLY_GS_SHIFT")) {  // debug knob: narrower Jacobi lane groups
-    const int sh = atoi(e);
-    BPX_CUDA(ctx, cudaMemcpyToSymbol(applyk3::g_jacobi_gs_shift, &sh, sizeof(int)));
-  }
+  constexpr int SS = applyk3::STAMP_SLOTS;
   long long* d_stamps = nullptr;
   const bool timing = getenv("BPX_APPLY_TIMING") != nullptr;  // debug: per-phase clock64 stamps, summary on stderr
   if (timing) {
-    if ((rc = ws_get(ctx, bpx_ctx::WS_OUT, (size_t)ng * 32 * sizeof(long long), &d_stamps))) return rc;
-    BPX_CUDA(ctx, cudaMemsetAsync(d_stamps, 0, (size_t)ng * 32 * sizeof(long long), ctx->stream));
+    if ((rc = ws_get(ctx, bpx_ctx::WS_OUT, (size_t)ng * SS * sizeof(long long), &d_stamps))) return rc;
+    BPX_CUDA(ctx, cudaMemsetAsync(d_stamps, 0, (size_t)ng * SS * sizeof(long long), ctx->stream));
     a3.stamps = d_stamps;
   }
-  if (ctx->dtype == BPX_F64)
-    applyk3::bp_apply_gates_v3<double><<<grid, applyk::NT, bytes, ctx->stream>>>(a3);
-  else
-    applyk3::bp_apply_gates_v3<c64><<<grid, applyk::NT, bytes, ctx->stream>>>(a3);
-  ctx->n_launches++;
-  BPX_CUDA(ctx, cudaGetLastError());
+  std::vector<cudaEvent_t> evs;
+  for (int64_t g0 = 0; g0 < ng; g0 += chunk) {
+    a3.g0 = g0;
+    a3.g1 = std::min(ng, g0 + chunk);
+    cudaEvent_t* ev = nullptr;
+    if (timing) {
+      evs.resize(evs.size() + 4);
+      ev = evs.data() + evs.size() - 4;
+      for (int i = 0; i < 4; ++i) BPX_CUDA(ctx, cudaEventCreate(&ev[i]));
+    }
+    if ((rc = cplx ? apply_launch_v3<c64>(ctx, a3, bytes, grid, bond_ctas, ev) : apply_launch_v3<double>(ctx, a3, bytes, grid, bond_ctas, ev)))
+      return rc;
+  }
   std::vector<int32_t> status((size_t)ng);
   BPX_CUDA(ctx, cudaMemcpyAsync(status.data(), d_status, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (timing) {
-    std::vector<long long> st((size_t)ng * 32);
+    float ms[3] = {0, 0, 0};
+    for (size_t c = 0; c + 3 < evs.size(); c += 4)
+      for (int i = 0; i < 3; ++i) {
+        float t = 0;
+        cudaEventElapsedTime(&t, evs[c + i], evs[c + i + 1]);
+        ms[i] += t;
+      }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    fprintf(stderr, "gate kernels v3: %lld gates in %zu chunk(s); kernel time sides %.3f ms, bond %.3f ms, final %.3f ms\n", (long long)ng,
+            evs.size() / 4, ms[0], ms[1], ms[2]);
+    std::vector<long long> st((size_t)ng * SS);
     BPX_CUDA(ctx, cudaMemcpy(st.data(), d_stamps, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    static const char* names[13] = {"", "msg check 0", "absorb 0", "gram 0", "eig 0", "msg check 1", "absorb 1", "gram 1", "eig 1",
-                                    "theta + gate", "svd", "Y, W", "final x 2 + msgs"};
-    double acc[13] = {0}, sw[3] = {0}, ab[5] = {0};
+    // (clock64 is per SM: only differences inside one kernel of one gate / side mean anything)
+    static const struct { const char* name; int from, to; } ph[] = {
+        {"sides: msg check 0", 0, 1}, {"sides: absorb 0", 1, 2},   {"sides: gram 0", 2, 3},    {"sides: msg check 1", 8, 9},
+        {"sides: absorb 1", 9, 10},   {"sides: gram 1", 10, 11},   {"bond: eig x 2", 16, 17},  {"bond: theta + gate", 17, 18},
+        {"bond: svd", 18, 19},        {"bond: Y, W", 19, 20},      {"final: side 0 + msgs", 24, 25}, {"final: side 1", 26, 27}};
+    constexpr int NP = sizeof(ph) / sizeof(ph[0]);
+    double acc[NP] = {0}, sw[2] = {0}, ab[5] = {0};
     int64_t cnt = 0;
     for (int64_t g = 0; g < ng; ++g) {
-      const long long* t = st.data() + 32 * g;
-      if (status[g] != 0 || t[12] == 0) continue;
-      for (int i = 1; i <= 12; ++i) acc[i] += (double)(t[i] - t[i - 1]);
-      for (int i = 0; i < 3; ++i) sw[i] += (double)t[13 + i];
-      ab[0] += (double)(t[17] - t[16]);
-      for (int i = 1; i < 4; ++i) ab[i] += (double)(t[17 + i] - t[16 + i]);
-      ab[4] += (double)(t[23] - t[20]);
+      const long long* t = st.data() + SS * g;
+      if (status[g] != 0 || t[27] == 0) continue;
+      for (int i = 0; i < NP; ++i) acc[i] += (double)(t[ph[i].to] - t[ph[i].from]);
+      sw[0] += (double)t[21];
+      sw[1] += (double)t[22];
+      for (int i = 0; i < 4; ++i) ab[i] += (double)(t[33 + i] - t[32 + i]);
+      ab[4] += (double)(t[39] - t[36]);
       ++cnt;
     }
-    double tot = 0;
-    for (int i = 1; i <= 12; ++i) tot += acc[i];
-    fprintf(stderr, "bp_apply_gates_v3 phase clocks (mean over %lld gates, grid %d, %d CTA/SM): total %.0f\n", (long long)cnt, grid, per_sm,
-            tot / std::max<int64_t>(cnt, 1));
-    for (int i = 1; i <= 12; ++i)
-      fprintf(stderr, "  %-18s %10.0f  %5.1f %%\n", names[i], acc[i] / std::max<int64_t>(cnt, 1), 100.0 * acc[i] / std::max(tot, 1.0));
     const double c1 = (double)std::max<int64_t>(cnt, 1);
-    fprintf(stderr, "  Jacobi sweeps: svd %.1f, eig %.1f / %.1f;  first column batch of absorb 0: gather %.0f, legs %.0f %.0f %.0f, scatter %.0f\n",
-            sw[0] / c1, sw[1] / c1, sw[2] / c1, ab[0] / c1, ab[1] / c1, ab[2] / c1, ab[3] / c1, ab[4] / c1);
+    double tot = 0;
+    for (int i = 0; i < NP; ++i) tot += acc[i];
+    fprintf(stderr,
+            "gate kernels v3, phase clocks per gate (mean over %lld gates; chunk %lld; CTAs/SM sides %d bond %d final %d): sum %.0f\n",
+            (long long)cnt, (long long)chunk, per_sm[0], per_sm[1], per_sm[2], tot / c1);
+    for (int i = 0; i < NP; ++i) fprintf(stderr, "  %-22s %10.0f  %5.1f %%\n", ph[i].name, acc[i] / c1, 100.0 * acc[i] / std::max(tot, 1.0));
+    fprintf(stderr, "  Jacobi sweeps: svd %.1f, eig %.1f;  first column batch of absorb 0: gather %.0f, legs %.0f %.0f %.0f, scatter %.0f\n",
+            sw[0] / c1, sw[1] / c1, ab[0] / c1, ab[1] / c1, ab[2] / c1, ab[3] / c1, ab[4] / c1);
   }
   *taken = true;
   for (int64_t g = 0; g < ng; ++g)

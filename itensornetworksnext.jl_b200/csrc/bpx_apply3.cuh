@@ -64,11 +64,13 @@ __host__ __device__ inline int64_t herm_elems(const Side& s) {
   return t;
 }
 
-__host__ __device__ inline Layout3 layout3_of(const GateDesc& g) {
+__host__ __device__ inline int64_t tt_elems(const GateDesc& g) { return (g.s[0].rows > g.s[1].rows ? g.s[0].rows : g.s[1].rows) * PCP; }
+// with_tt = false: the per-GATE work space of the device kernels (T lives in a per-CTA scratch buffer there)
+__host__ __device__ inline Layout3 layout3_of(const GateDesc& g, bool with_tt = true) {
   Layout3 L;
   int64_t o = 0;
   for (int a = 0; a < 2; ++a) { L.at[a] = o; o += g.s[a].rows * PCP; }
-  L.tt = o; o += (g.s[0].rows > g.s[1].rows ? g.s[0].rows : g.s[1].rows) * PCP;
+  L.tt = o; o += with_tt ? tt_elems(g) : 0;
   for (int a = 0; a < 2; ++a) {
     const Side& s = g.s[a];
     const int64_t cc = (int64_t)s.cols * s.cols;
@@ -93,42 +95,46 @@ __host__ __device__ inline Layout3 layout3_of(const GateDesc& g) {
 // Leading dimension of a Jacobi operand (m rows, n columns) in shared memory: with GS lanes per pair (see jacobi_groups)
 // consecutive columns must start GS doubles apart modulo the 16 double-wide banks, so that the groups of a warp hit
 // disjoint banks (ld = m puts every column of a 64-row matrix on the same banks: 4-way conflicts on every access).
-#ifdef __CUDACC__
-__device__ int g_jacobi_gs_shift = 0;  // debug knob (BPX_APPLY_GS_SHIFT): halve the lane-group width this many times
-#endif
-__host__ __device__ inline int jacobi_gs(int n, int nw) {  // lanes per column pair (measured: narrow groups win)
-  const int npairs = (n + 1) / 2;
-  (void)nw;
+// Lanes per column pair.  Measured: narrow groups win as long as a lane's rows of the pair fit its register
+// batch (rb rows per column: 8 Float64 / 4 ComplexF64); taller operands get wider groups so that the rotation does not
+// have to re-load them -- the iteration is bound by shared-memory wavefronts.
+__host__ __device__ inline int jacobi_gs(int n, int nprob, int m, int rb) {
+  const int npairs = (n + 1) / 2 * nprob;
   int gs = npairs >= 16 ? 4 : (npairs >= 4 ? 8 : 16);
-#ifdef __CUDA_ARCH__
-  gs >>= g_jacobi_gs_shift;
-  if (gs < 1) gs = 1;
-#endif
+  (void)m;  // (measured, round 2: widening the groups of tall operands so that their rows stay in registers -- 8 lanes for
+  (void)rb; // the 64 x 64 bond matrix -- changes nothing for Float64 and costs ComplexF64 15 %)
   return gs;
 }
-__host__ __device__ inline int jacobi_ld(int m, int n, int nw = NT / 32) {
-  const int gs = jacobi_gs(n, nw);
-  if (gs >= 16) return m;
+__host__ __device__ inline int jacobi_ld(int m, int n, int nprob = 1, int rb = 0) {
   int ld = m;
   while (ld % 16 != 8) ++ld;  // sized for the widest rule on the host; the kernel only needs callers and callee to agree
 #ifdef __CUDA_ARCH__
+  const int gs = jacobi_gs(n, nprob, m, rb);
   ld = m;
-  while (ld % 16 != (gs < 2 ? 1 : gs)) ++ld;
+  if (gs < 16)
+    while (ld % 16 != gs) ++ld;
 #endif
   return ld;
 }
+template <typename T>
+__host__ __device__ constexpr int jacobi_rb() { return Elem<T>::is_complex ? 4 : 8; }
 
-// Can the fast path take this gate, and how much shared memory (elements of T) does it want?  0: not supported.
-__host__ __device__ inline int64_t smem_need(const GateDesc& g, bool cplx) {
-  if (g.nsides != 2) return 0;
-  int64_t need = 0;
+// Can the fast path take this gate, and how much shared memory (elements of T) do its three kernels want?  0: not supported.
+struct SmemNeed3 {
+  int64_t sides, bond, fin;  // bp_apply3_sides / bp_apply3_bond / bp_apply3_final
+  __host__ __device__ int64_t all() const { return sides > bond ? (sides > fin ? sides : fin) : (bond > fin ? bond : fin); }
+};
+__host__ __device__ inline SmemNeed3 smem_need3(const GateDesc& g, bool cplx) {
+  SmemNeed3 nd = {0, 0, 0};
+  if (g.nsides != 2) return nd;
+  int64_t sides = 0, fin = 0, bond = 0;
   for (int a = 0; a < 2; ++a) {
     const Side& s = g.s[a];
-    if (s.cols > PC || s.cols < 1) return 0;
+    if (s.cols > PC || s.cols < 1) return nd;
     int64_t hsum = 0;
     for (int i = 0; i < s.z; ++i)
       if (i != s.bond_slot) {
-        if (s.dim[i] > MAXDIM) return 0;
+        if (s.dim[i] > MAXDIM) return nd;
         hsum += (int64_t)s.dim[i] * s.dim[i];
       }
     const int64_t cb = (!cplx && (s.cols % 2 == 0)) ? 2 : 1;
@@ -138,22 +144,25 @@ __host__ __device__ inline int64_t smem_need(const GateDesc& g, bool cplx) {
     const int64_t absorb = cb * (s.rows + s.rows / dim0) + 2 + hsum;  // padded column batch + the messages
     const int64_t gram = 2 * (int64_t)TRG * PCP;               // A tile, T tile (the reduction re-uses them)
     const int64_t trf = cplx ? 128 : 256;
-    const int64_t fin = trf * PCP + (int64_t)PC * PC;          // A tile, W
-    need = need > absorb ? need : absorb;
-    need = need > gram ? need : gram;
-    need = need > fin ? need : fin;
+    const int64_t f = trf * PCP + (int64_t)PC * PC;            // A tile, W
+    sides = sides > absorb ? sides : absorb;
+    sides = sides > gram ? sides : gram;
+    fin = fin > f ? fin : f;
   }
-  const int64_t m = (int64_t)g.s[0].cols * g.s[0].d, n = (int64_t)g.s[1].cols * g.s[1].d;
-  const int64_t ldb = jacobi_ld((int)m, (int)n);
-  const int64_t svd = ldb * n;
-  need = need > svd ? need : svd;
-  const int64_t gramf = (int64_t)(PC + 16) * PC + (int64_t)PC * PC;  // rotated + unrotated Gram matrix
-  need = need > gramf ? need : gramf;
   // the cross-warp reduction of the Gram pass: 8 partial tiles of PC x (PC or PC/2) elements
   const int64_t red = 8 * (int64_t)PC * (cplx ? PC / 2 : PC);
-  need = need > red ? need : red;
-  return (need + 1) & ~(int64_t)1;
+  sides = sides > red ? sides : red;
+  const int64_t m = (int64_t)g.s[0].cols * g.s[0].d, n = (int64_t)g.s[1].cols * g.s[1].d;
+  const int64_t ldb = jacobi_ld((int)m, (int)n);
+  bond = ldb * n;
+  const int64_t gramf = 2 * ((int64_t)(PC + 16) * PC + (int64_t)PC * PC);  // rotated + unrotated Gram matrix, both sides
+  bond = bond > gramf ? bond : gramf;
+  nd.sides = (sides + 1) & ~(int64_t)1;
+  nd.bond = (bond + 1) & ~(int64_t)1;
+  nd.fin = (fin + 1) & ~(int64_t)1;
+  return nd;
 }
+__host__ __device__ inline int64_t smem_need(const GateDesc& g, bool cplx) { return smem_need3(g, cplx).all(); }
 
 // ---- canonical addressing of the matrix view: element (row, col) of side `sd` sits at rowaddr(row) + coladdr(col) --------
 struct Walk {
@@ -199,7 +208,7 @@ struct Tabs {
   bool col_fast;  // the columns (s, bond) are contiguous in the canonical layout (bond leg first); else (s, first row leg)
 };
 template <typename T>
-__host__ __device__ __noinline__ Tabs build_tabs(const Team tm, const Side& sd, const Walk& wk, T* slot) {
+__host__ __device__ __forceinline__ Tabs build_tabs(const Team tm, const Side& sd, const Walk& wk, T* slot) {
   int32_t* rt = reinterpret_cast<int32_t*>(slot);
   int32_t* ct = rt + sd.rows;
   for (int64_t r = tm.tid(); r < sd.rows; r += tm.nt()) rt[r] = (int32_t)rowaddr(wk, r);
@@ -212,9 +221,19 @@ __host__ __device__ __noinline__ Tabs build_tabs(const Team tm, const Side& sd, 
   return t;
 }
 
+// the tables build_tabs left in `slot` (another kernel of the same gate)
+template <typename T>
+__host__ __device__ __forceinline__ Tabs tabs_at(const Side& sd, const Walk& wk, T* slot) {
+  Tabs t;
+  t.row = reinterpret_cast<const int32_t*>(slot);
+  t.col = t.row + sd.rows;
+  t.col_fast = wk.next == 0 || wk.bstride < wk.rstride[0];
+  return t;
+}
+
 // contiguous copy global -> shared in 16-byte pieces (both 16-byte aligned; n elements, n * sizeof(T) a multiple of 16)
 template <typename T>
-__host__ __device__ __noinline__ void copy_tile(const Team tm, T* dst, const T* src, int64_t n) {
+__host__ __device__ __forceinline__ void copy_tile(const Team tm, T* dst, const T* src, int64_t n) {
 #ifdef __CUDA_ARCH__
   const int n16 = (int)(n * sizeof(T) / 16), nt = tm.nt(), tid = tm.tid();
   const double2* __restrict__ s2 = reinterpret_cast<const double2*>(src);
@@ -238,7 +257,7 @@ __host__ __device__ __noinline__ void copy_tile(const Team tm, T* dst, const T* 
 // ---- messages: Hermitian part + positive-definiteness check ---------------------------------------------------------------
 // One warp per message: right-looking Cholesky on a scratch copy; *bad is set when a pivot is not safely positive.
 template <typename T>
-__host__ __device__ __noinline__ void message_check(const Team tm, const Side& sd, const T* msgs, T* H, T* scratch, int* bad) {
+__host__ __device__ __forceinline__ void message_check(const Team tm, const Side& sd, const T* msgs, T* H, T* scratch, int* bad) {
   using E = Elem<T>;
   const int L = tm.lanes();
   int64_t off = 0;
@@ -401,7 +420,7 @@ __host__ __device__ void absorb_leg(const Team tm, T* col, int rows, int prow, i
 // then start an odd number of elements apart (no bank conflicts; unpadded, a warp's 32 fibres of 16 doubles share one
 // bank), and every other leg keeps a uniform stride st + st / rdim[0].
 template <typename T, int CB>
-__host__ __device__ __noinline__ void absorb_side(const Team tm, const Side& sd, const Walk& wk, const Tabs tb, const T* a, const T* H, T* aout,
+__host__ __device__ __forceinline__ void absorb_side(const Team tm, const Side& sd, const Walk& wk, const Tabs tb, const T* a, const T* H, T* aout,
                                      T* tout, T* smem, long long* stamps = nullptr) {
 #ifdef __CUDA_ARCH__
 #define BPX_ASTAMP(i) do { if (stamps && tm.tid() == 0 && c0 == 0) stamps[i] = clock64(); } while (0)
@@ -476,7 +495,7 @@ __host__ __device__ __noinline__ void absorb_side(const Team tm, const Side& sd,
 // an 8 x 4 lane grid accumulates the 4 x TJ block G[4 i .., TJ (j + 4 pass) ..]: per row 4 + TJ operand loads (broadcast
 // within the lane groups) feed 4 TJ FMAs.  The nw partial tiles are summed through shared memory at the end.
 template <typename T, int TJ>
-__host__ __device__ __noinline__ void gram_side(const Team tm, const Side& sd, const T* at, const T* tt, T* G, T* smem) {
+__host__ __device__ __forceinline__ void gram_side(const Team tm, const Side& sd, const T* at, const T* tt, T* G, T* smem) {
   using E = Elem<T>;
   constexpr int NPASS = PC / (4 * TJ);
   T* sA = smem;
@@ -585,10 +604,12 @@ __host__ __device__ __noinline__ void gram_side(const Team tm, const Side& sd, c
 // 1 / sqrt(x) and 1 / x to full double accuracy from the hardware's 20-bit approximations + two Newton steps: a short
 // dependent chain (the IEEE sqrt / division sequences cost several hundred cycles of latency each, and the Jacobi steps
 // below are pure latency).  Outside the safe exponent range the exact functions are used.
-template <int STEPS = 2>
+// GUARD = false: the caller knows that x is in the safe range (the exact fallbacks are function calls: every register live
+// across them is spilled around the call)
+template <int STEPS = 2, bool GUARD = true>
 __host__ __device__ __forceinline__ double rsqrt_d(double x) {
 #ifdef __CUDA_ARCH__
-  if (!(x > 1e-280 && x < 1e280)) return rsqrt(x);
+  if (GUARD && !(x > 1e-280 && x < 1e280)) return rsqrt(x);
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #pragma unroll
@@ -601,10 +622,10 @@ __host__ __device__ __forceinline__ double rsqrt_d(double x) {
   return 1.0 / sqrt(x);
 #endif
 }
-template <int STEPS = 2>
+template <int STEPS = 2, bool GUARD = true>
 __host__ __device__ __forceinline__ double rcp_d(double x) {
 #ifdef __CUDA_ARCH__
-  if (!(fabs(x) > 1e-280 && fabs(x) < 1e280)) return 1.0 / x;
+  if (GUARD && !(fabs(x) > 1e-280 && fabs(x) < 1e280)) return 1.0 / x;
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #pragma unroll
@@ -618,24 +639,37 @@ __host__ __device__ __forceinline__ double rcp_d(double x) {
 // ---- one-sided Jacobi without V, pairs on sub-warp lane groups ---------------------------------------------------------------
 // B (m x n, leading dimension ld, shared memory) is rotated until its columns are mutually orthogonal; *not_converged is
 // set when the last sweep of the budget still rotated.  A group of GS lanes owns one column pair of the current
-// round-robin step.  The iteration is LATENCY bound (one dependent chain per step: loads, inner products, shuffles, rotation
-// parameters, rotation, barrier), so the groups are as wide as the team allows (64 columns on 8 warps: 8 lanes per pair,
-// 8 rows per lane): the shortest per-lane chains.  A lane's rows of both columns stay in registers between the inner products
-// and the rotation (RC per column).
-template <typename T, int GS, int RC>
-__host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m, int n, int ld, int* flag, int* not_converged,
-                                                      long long* sweeps_out) {
+// round-robin step; a lane walks its rows of the pair in batches of RB rows held in registers: when one batch covers them
+// (m <= GS RB) they stay there between the inner products and the rotation, otherwise the rotation re-loads them.
+// `nprob` (1 or 2) independent problems of the same shape, `pstride` elements apart, share the steps and the barriers: the
+// two Gram matrices of a gate are diagonalised together.  A problem that has converged only fails the rotation test in the
+// remaining sweeps, so the result is bit-identical to running the problems one after the other.
+// NOT inlined, on purpose: measured on the B200 (round 2, profiles/r2a*_apply*), this form -- a called function with plain
+// pointers -- beats every "cleaner" variant tried: inlined into the bond kernel (+35 % kernel time: the kernel's other
+// phases share its register allocation), 32-bit shared addresses through inline PTX with a predicate-free path for full
+// batches (+60 %), unordered pairs for conflict-free banks (no change), wider groups for tall operands (no change for
+// Float64, -15 % for ComplexF64).
+template <typename T, int GS, int RB>
+__host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m, int n, int ld, int nprob, int pstride, int* flag,
+                                                      int* not_converged, long long* sweeps_out) {
   using E = Elem<T>;
   const int L = tm.lanes();
-  const int np = (n + 1) & ~1, npairs = np / 2;
+  const int np = (n + 1) & ~1, npairs = np / 2, npt = npairs * nprob;
   const int gpw = L / GS;                // groups per warp
   const int sl = tm.lane % GS, grp = tm.lane / GS;
-  const bool cached = m <= GS * RC;
+  const int rpl = (m + GS - 1) / GS;     // rows per lane
+  const bool single = rpl <= RB;
   const double tol2 = (double)m * EPS * EPS;
-  double fro2 = 0.0;
-  for (int64_t i = tm.lane; i < (int64_t)m * n; i += L) fro2 += E::abs2(B[(i % m) + (int64_t)ld * (i / m)]);
-  fro2 = tm.sum(fro2);
-  const double zero2 = (double)n * n * EPS * EPS * fro2;
+  double zero2[2] = {0.0, 0.0};
+  for (int k = 0; k < nprob; ++k) {
+    double fro2 = 0.0;
+    const T* Bk = B + (int64_t)k * pstride;
+    for (int j = 0; j < n; ++j)
+      for (int r = tm.lane; r < m; r += L) fro2 += E::abs2(Bk[r + ld * j]);
+    fro2 = tm.sum(fro2);
+    zero2[k] = (double)n * n * EPS * EPS * fro2;
+  }
+  const double zero2a = zero2[0], zero2b = zero2[1];
   tm.sync();
   int f = 1, nsweeps = 0;
   for (int sweep = 0; sweep < MAX_JACOBI_SWEEPS && f; ++sweep) {
@@ -643,10 +677,12 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
     if (tm.tid() == 0) *flag = 0;
     tm.sync();
     for (int step = 0; step < np - 1; ++step) {
-      for (int base = tm.wid * gpw; base < npairs; base += tm.nw * gpw) {  // warp-uniform bound: shuffles stay converged
-        const int idx = base + grp;
+      for (int base = tm.wid * gpw; base < npt; base += tm.nw * gpw) {  // warp-uniform bound: shuffles stay converged
+        const int gi = base + grp;
+        const bool second = gi >= npairs;
+        const int idx = second ? gi - npairs : gi;
         int p = 0, q = 1;
-        bool active = idx < npairs;
+        bool active = gi < npt;
         if (active) {
           if (idx == 0) {
             p = np - 1;
@@ -660,23 +696,21 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
           if (p > q) { const int t = p; p = q; q = t; }
           if (q >= n) { active = false; p = 0; q = 1; }
         }
-        T* bp = B + p * ld;
-        T* bq = B + q * ld;
-        double a = 0.0, b = 0.0;
-        T g = E::zero();
-        T xr[RC], yr[RC];
-        if (cached) {
-          double a1 = 0.0, b1 = 0.0;  // two partial sums per inner product: half the dependent-chain length
-          T g1 = E::zero();
+        T* bp = B + (second ? pstride : 0) + p * ld + sl;
+        T* bq = B + (second ? pstride : 0) + q * ld + sl;
+        double a = 0.0, b = 0.0, a1 = 0.0, b1 = 0.0;  // two partial sums per inner product: half the dependent-chain length
+        T g = E::zero(), g1 = E::zero();
+        T xr[RB], yr[RB];
+        // (groups without a pair this step must not touch the matrix: another group owns columns 0, 1)
+        for (int j0 = 0; j0 < rpl; j0 += RB) {
 #pragma unroll
-          for (int j = 0; j < RC; ++j) {
-            const int r = sl + j * GS;
-            xr[j] = E::zero();
-            yr[j] = E::zero();
-            if (active && r < m) {  // (groups without a pair this step must not touch the matrix: another group owns columns 0, 1)
-              xr[j] = bp[r];
-              yr[j] = bq[r];
-            }
+          for (int j = 0; j < RB; ++j) {
+            const bool ok = active && sl + (j0 + j) * GS < m;
+            xr[j] = ok ? bp[(j0 + j) * GS] : E::zero();
+            yr[j] = ok ? bq[(j0 + j) * GS] : E::zero();
+          }
+#pragma unroll
+          for (int j = 0; j < RB; ++j) {
             if (j & 1) {
               a1 += E::abs2(xr[j]);
               b1 += E::abs2(yr[j]);
@@ -687,17 +721,10 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
               g = E::fma(E::conj(xr[j]), yr[j], g);
             }
           }
-          a += a1;
-          b += b1;
-          g = E::add(g, g1);
-        } else {
-          for (int r = sl; r < m && active; r += GS) {
-            const T x = bp[r], y = bq[r];
-            a += E::abs2(x);
-            b += E::abs2(y);
-            g = E::fma(E::conj(x), y, g);
-          }
         }
+        a += a1;
+        b += b1;
+        g = E::add(g, g1);
 #ifdef __CUDA_ARCH__
 #pragma unroll
         for (int o = GS >> 1; o > 0; o >>= 1) {
@@ -706,8 +733,8 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
           g = E::add(g, E::shfl_xor(g, o));
         }
 #endif
-        const double g2 = E::abs2(g);
-        if (!active || !(g2 > tol2 * a * b) || !(a > zero2) || !(b > zero2)) continue;  // group-uniform, no shuffles below
+        const double g2 = E::abs2(g), z2 = second ? zero2b : zero2a;
+        if (!active || !(g2 > tol2 * a * b) || !(a > z2) || !(b > z2)) continue;  // group-uniform, no shuffles below
         // rotation parameters on short dependent chains (rsqrt_d / rcp_d)
         // Any angle gives an exactly unitary rotation as long as c = 1 / sqrt(1 + t^2), s = c t and the phase are accurate:
         // the angle itself (zeta, t) is computed with one Newton step (~1e-12, no effect on the quadratic convergence)
@@ -726,20 +753,27 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
         if (zeta < 0.0) t = -t;
         const double c = rsqrt_d<2>(fma(t, t, 1.0)), s = c * t;
         const T sph = scal(ph, s), scph = scal(E::conj(ph), s);
-        if (cached) {
+        for (int j0 = 0; j0 < rpl; j0 += RB) {
+          if (!single) {
 #pragma unroll
-          for (int j = 0; j < RC; ++j) {
-            const int r = sl + j * GS;
-            if (r < m) {
-              bp[r] = sub(scal(xr[j], c), E::mul(yr[j], scph));
-              bq[r] = E::add(E::mul(xr[j], sph), scal(yr[j], c));
+            for (int j = 0; j < RB; ++j) {
+              const bool ok = sl + (j0 + j) * GS < m;
+              xr[j] = ok ? bp[(j0 + j) * GS] : E::zero();
+              yr[j] = ok ? bq[(j0 + j) * GS] : E::zero();
             }
           }
-        } else {
-          for (int r = sl; r < m; r += GS) {
-            const T x = bp[r], y = bq[r];
-            bp[r] = sub(scal(x, c), E::mul(y, scph));
-            bq[r] = E::add(E::mul(x, sph), scal(y, c));
+#pragma unroll
+          for (int j = 0; j < RB; ++j) {  // all outputs first, then the stores: independent temporaries
+            const T x = xr[j], y = yr[j];
+            xr[j] = sub(scal(x, c), E::mul(y, scph));
+            yr[j] = E::add(E::mul(x, sph), scal(y, c));
+          }
+#pragma unroll
+          for (int j = 0; j < RB; ++j) {
+            if (sl + (j0 + j) * GS < m) {
+              bp[(j0 + j) * GS] = xr[j];
+              bq[(j0 + j) * GS] = yr[j];
+            }
           }
         }
         if (sl == 0) BPX_FLAG_SET(flag);
@@ -756,19 +790,17 @@ __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m
 
 template <typename T>
 __host__ __device__ void jacobi_groups(const Team tm, T* B, int m, int n, int ld, int* flag, int* not_converged,
-                                       long long* sweeps_out = nullptr) {
+                                       long long* sweeps_out = nullptr, int nprob = 1, int pstride = 0) {
   if (n < 2) return;
 #ifdef __CUDA_ARCH__
-  constexpr int RC = 8;
-  switch (jacobi_gs(n, tm.nw)) {
-    case 1: jacobi_groups_t<T, 1, 2 * RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out); break;
-    case 2: jacobi_groups_t<T, 2, 2 * RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out); break;
-    case 4: jacobi_groups_t<T, 4, 2 * RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out); break;
-    case 8: jacobi_groups_t<T, 8, RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out); break;
-    default: jacobi_groups_t<T, 16, RC>(tm, B, m, n, ld, flag, not_converged, sweeps_out); break;
+  constexpr int RB = jacobi_rb<T>();
+  switch (jacobi_gs(n, nprob, m, RB)) {
+    case 4: jacobi_groups_t<T, 4, RB>(tm, B, m, n, ld, nprob, pstride, flag, not_converged, sweeps_out); break;
+    case 8: jacobi_groups_t<T, 8, RB>(tm, B, m, n, ld, nprob, pstride, flag, not_converged, sweeps_out); break;
+    default: jacobi_groups_t<T, 16, RB>(tm, B, m, n, ld, nprob, pstride, flag, not_converged, sweeps_out); break;
   }
 #else
-  jacobi_groups_t<T, 1, 1>(tm, B, m, n, ld, flag, not_converged, sweeps_out);  // host lanes: one lane per pair
+  jacobi_groups_t<T, 1, 4>(tm, B, m, n, ld, nprob, pstride, flag, not_converged, sweeps_out);  // host lanes: one lane per pair
 #endif
 }
 
@@ -797,13 +829,10 @@ __host__ __device__ void column_order(const Team tm, const T* src, int m, int n,
 // ---- eigen-decomposition of the Gram matrix -> R, R^+ ------------------------------------------------------------------------
 // G Hermitian (cols x cols, global).  Rotating the columns of G: G V = V diag(lam), so column j of the rotated copy is
 // lam_j v_j: |lam_j| = |b_j|, sign from Re(b_j^H G b_j) (a slightly indefinite G).  *bad: conditioning / convergence.
+// Split in two so that the two sides of a gate share ONE iteration (jacobi_groups, nprob = 2): `gram_factor_load` puts G
+// (columns sorted by norm) and an unrotated copy into shared memory, `gram_factor_finish` turns the rotated copy into R, R^+.
 template <typename T>
-__host__ __device__ __noinline__ void gram_factor(const Team tm, int cols, int rank_max, const T* G, T* Gb, double* ev, T* R, T* Rinv, T* smem, int* flag,
-                                     int* bad, long long* sweeps_out = nullptr) {
-  using E = Elem<T>;
-  const int ld = jacobi_ld(cols, cols);
-  T* sb = smem;
-  T* sg = smem + (int64_t)ld * cols;  // the unrotated matrix, for the Rayleigh quotients
+__host__ __device__ __forceinline__ void gram_factor_load(const Team tm, int cols, const T* G, T* Gb, double* ev, T* sb, T* sg, int ld) {
   int32_t* pos = reinterpret_cast<int32_t*>(Gb);  // (Gb is written after the iteration)
   column_order<T>(tm, G, cols, cols, ev, pos);
   for (int i = tm.tid(); i < cols * cols; i += tm.nt()) {
@@ -812,7 +841,11 @@ __host__ __device__ __noinline__ void gram_factor(const Team tm, int cols, int r
     sg[i] = v;
   }
   tm.sync();
-  jacobi_groups<T>(tm, sb, cols, cols, ld, flag, bad, sweeps_out);
+}
+template <typename T>
+__host__ __device__ __forceinline__ void gram_factor_finish(const Team tm, int cols, int rank_max, T* Gb, double* ev, T* R, T* Rinv, const T* sb,
+                                                         const T* sg, int ld, int* bad) {
+  using E = Elem<T>;
   for (int i = tm.tid(); i < cols * cols; i += tm.nt()) Gb[i] = sb[(i % cols) + ld * (i / cols)];
   tm.sync();
   for (int j = tm.tid(); j < cols; j += tm.nt()) {
@@ -871,7 +904,7 @@ __host__ __device__ __noinline__ void gram_factor(const Team tm, int cols, int r
 // column pair RT 16-byte operand loads (rows 272 bytes apart: conflict free) and NO 16-byte broadcast loads of W feed 2 RT NO
 // FMAs.
 template <typename T, int TRF, int RT, int NO>
-__host__ __device__ __noinline__ void final_side(const Team tm, const Side& sd, const Tabs tb, const T* at, T* a, const T* W, T* smem) {
+__host__ __device__ __forceinline__ void final_side(const Team tm, const Side& sd, const Tabs tb, const T* at, T* a, const T* W, T* smem) {
   using E = Elem<T>;
   T* sA = smem;                                  // [r][PCP]
   T* sW = smem + (int64_t)TRF * PCP;             // [c][PC]
@@ -959,43 +992,120 @@ __host__ __device__ __noinline__ void final_side(const Team tm, const Side& sd, 
   }
 }
 
-// One two-site gate.  Returns (to every thread) 0 when the gate was applied, 1 when it was left untouched for the fallback.
+// ---- one two-site gate -----------------------------------------------------------------------------------------------------------
+// Everything the phases of one gate share; in shared memory on the device.  The gate runs as THREE kernels (bottom of this
+// file): bp_apply3_sides -- one CTA per (gate, side): tables, message check, absorb, Gram product; bp_apply3_bond -- one
+// small CTA per gate: the two eigen-decompositions, the bond problem and its SVD, W_a; bp_apply3_final -- one CTA per
+// (gate, side): A' = A W.  Each kernel inlines its phases (one call site each) and has the occupancy its phase wants: the
+// Jacobi iterations are pure latency chains and get 5 resident CTAs of 4 warps with every lane busy, the dense passes 2 CTAs
+// of 8 warps.  Why not one kernel walking all phases (round 2's first version): with the phases as non-inlined functions
+// ptxas's calling convention left each of them ~75 of the 128 registers (the Gram pass spilled its accumulators, whatever
+// the caller kept live came off every callee's budget, and the outcome changed with unrelated edits:
+// tools/sass_loop_spills.py); fully inlined, the one big function spilled loop state; and half (SVD) or three quarters
+// (eigen-decompositions) of the CTA's warps idled at the step barriers of the Jacobi phases.
+// The dynamic shared memory of the kernel.  The phases re-derive it from the symbol instead of loading the pointer from the
+// context: the compiler then knows the address space (LDS / STS instead of generic loads) in them and in what they call.
 template <typename T>
-__host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* sites, T* msgs, const T* ops, T* w /* this CTA's work space */,
-                                        double* sv_out, int normalize, int* flag, int* bad, T* smem, long long* stamps = nullptr) {
-  using E = Elem<T>;
-  constexpr bool CPLX = Elem<T>::is_complex;
-  const Layout3 L = layout3_of(gd);
+__host__ __device__ __forceinline__ T* phase_smem(T* from_context) {
 #ifdef __CUDA_ARCH__
-#define BPX_STAMP(i) do { if (stamps && tm.tid() == 0) stamps[i] = clock64(); } while (0)
+  extern __shared__ __align__(16) unsigned char dyn_smem3[];
+  (void)from_context;
+  return reinterpret_cast<T*>(dyn_smem3);
 #else
-#define BPX_STAMP(i) do { (void)stamps; } while (0)
+  return from_context;
 #endif
-  BPX_STAMP(0);
-  if (tm.tid() == 0) *bad = 0;
-  tm.sync();
+}
+
+template <typename T>
+struct Gate3 {
+  const GateDesc* gd;
+  T* sites;
+  T* msgs;
+  const T* ops;
+  T* w;   // this gate's work space (Layout3)
+  T* tt;  // T = (M_1 x M_2 x ..) A of the side in flight (scratch of the CTA)
+  double* sv_out;
+  T* smem;
+  int* flag;
+  int* bad;
+  long long* stamps;
+  int normalize;
+  Layout3 L;
   Tabs tb[2];
-  for (int a = 0; a < 2; ++a) {
-    const Side& sd = gd.s[a];
-    const Walk wka = walk_of(sd);
-    tb[a] = build_tabs<T>(tm, sd, wka, w + L.tab[a]);
-    message_check<T>(tm, sd, msgs, w + L.h[a], smem, bad);
-    if (*bad) return 1;
-    BPX_STAMP(1 + 4 * a);
-    const T* A = sites + sd.site_off;
-    if (!CPLX && sd.cols % 2 == 0)
-      absorb_side<T, 2>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.at[a], w + L.tt, smem, (stamps && a == 0) ? stamps + 16 : nullptr);
-    else
-      absorb_side<T, 1>(tm, sd, wka, tb[a], A, w + L.h[a], w + L.at[a], w + L.tt, smem);
-    BPX_STAMP(2 + 4 * a);
-    gram_side<T, CPLX ? 4 : 8>(tm, sd, w + L.at[a], w + L.tt, w + L.g[a], smem);
-    BPX_STAMP(3 + 4 * a);
-    gram_factor<T>(tm, sd.cols, sd.nref, w + L.g[a], w + L.gb[a], reinterpret_cast<double*>(w + L.ev[a]), w + L.r[a], w + L.rinv[a], smem,
-                   flag, bad, stamps ? stamps + 14 + a : nullptr);
-    if (*bad) return 1;
-    BPX_STAMP(4 + 4 * a);
+};
+
+// debug stamps (BPX_APPLY_TIMING=1), STAMP_SLOTS clock64 values per gate: side a: 8 a + {0 start, 1 message check, 2 absorb,
+// 3 Gram}; bond kernel: 16 start, 17 eigen-decompositions, 18 theta + gate, 19 SVD, 20 Y / W; Jacobi sweeps: 21 SVD, 22 eig;
+// final kernel, side a: 24 + 2 a start, 25 + 2 a end; 32..39: the first column batch of absorb on side 0
+constexpr int STAMP_SLOTS = 48;
+#ifdef __CUDA_ARCH__
+#define BPX_STAMP(i) do { if (c.stamps && tm.tid() == 0) c.stamps[i] = clock64(); } while (0)
+#else
+#define BPX_STAMP(i) do { } while (0)
+#endif
+
+// tables, message check, absorb, Gram product of side a
+template <typename T>
+__host__ __device__ __forceinline__ void phase_side(const Team tm, Gate3<T>& c, int a) {
+  constexpr bool CPLX = Elem<T>::is_complex;
+  const Side& sd = c.gd->s[a];
+  const Layout3& L = c.L;
+  T* w = c.w;
+  T* smem = phase_smem<T>(c.smem);
+  const Walk wka = walk_of(sd);
+  {
+    const Tabs t = build_tabs<T>(tm, sd, wka, w + L.tab[a]);
+#ifdef __CUDA_ARCH__
+    if (tm.tid() == 0) c.tb[a] = t;
+    tm.sync();
+#else
+    c.tb[a] = t;
+#endif
   }
-  // ---- the bond problem (apply_operators.jl:260-268), R factors with cols rows each -----------------------------------
+  message_check<T>(tm, sd, c.msgs, w + L.h[a], smem, c.bad);
+  if (*c.bad) return;
+  BPX_STAMP(8 * a + 1);
+  const T* A = c.sites + sd.site_off;
+  if (!CPLX && sd.cols % 2 == 0)
+    absorb_side<T, 2>(tm, sd, wka, c.tb[a], A, w + L.h[a], w + L.at[a], c.tt, smem, (c.stamps && a == 0) ? c.stamps + 32 : nullptr);
+  else
+    absorb_side<T, 1>(tm, sd, wka, c.tb[a], A, w + L.h[a], w + L.at[a], c.tt, smem);
+  BPX_STAMP(8 * a + 2);
+  gram_side<T, CPLX ? 4 : 8>(tm, sd, w + L.at[a], c.tt, w + L.g[a], smem);
+  BPX_STAMP(8 * a + 3);
+}
+
+// G_a = V diag(lam) V^H for both sides: one joint iteration when the shapes agree (they do unless the physical dimensions
+// differ), each problem in its own slot of shared memory
+template <typename T>
+__host__ __device__ __forceinline__ void phase_eig(const Team tm, Gate3<T>& c) {
+  const GateDesc& gd = *c.gd;
+  const Layout3& L = c.L;
+  T* w = c.w;
+  T* smem = phase_smem<T>(c.smem);
+  const bool joint = gd.s[0].cols == gd.s[1].cols;
+  for (int a = 0; a < 2; a += joint ? 2 : 1) {
+    const int np = joint ? 2 : 1, cols = gd.s[a].cols;
+    const int ld = jacobi_ld(cols, cols, np, jacobi_rb<T>());
+    const int slot = ld * cols + cols * cols;
+    for (int k = 0; k < np; ++k)
+      gram_factor_load<T>(tm, cols, w + L.g[a + k], w + L.gb[a + k], reinterpret_cast<double*>(w + L.ev[a + k]), smem + k * slot,
+                          smem + k * slot + ld * cols, ld);
+    jacobi_groups<T>(tm, smem, cols, cols, ld, c.flag, c.bad, c.stamps ? c.stamps + 22 : nullptr, np, slot);
+    for (int k = 0; k < np; ++k)
+      gram_factor_finish<T>(tm, cols, gd.s[a + k].nref, w + L.gb[a + k], reinterpret_cast<double*>(w + L.ev[a + k]), w + L.r[a + k],
+                            w + L.rinv[a + k], smem + k * slot, smem + k * slot + ld * cols, ld, c.bad);
+  }
+}
+
+// the bond problem (apply_operators.jl:260-268), R factors with cols rows each: theta = R_1 R_2, the gate, and the operand
+// of the SVD iteration (columns sorted by norm) in shared memory
+template <typename T>
+__host__ __device__ __forceinline__ void phase_bond_pre(const Team tm, Gate3<T>& c) {
+  using E = Elem<T>;
+  const GateDesc& gd = *c.gd;
+  const Layout3& L = c.L;
+  T* w = c.w;
   const Side& s1 = gd.s[0];
   const Side& s2 = gd.s[1];
   const int d1 = s1.d, d2 = s2.d, n1 = s1.cols, n2 = s2.cols, chi = gd.chi_b;
@@ -1004,7 +1114,6 @@ __host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* si
   const T* R2 = w + L.r[1];
   T* th0 = w + L.theta[0];
   T* th1 = w + L.theta[1];  // theta after the gate (kept: V = theta^H U / s)
-  T* th2 = w + L.theta[2];  // rotated copy: U diag(s)
   for (int i = tm.tid(); i < m * n; i += tm.nt()) {
     const int row = i % m, col = i / m;
     const int q1 = row % n1, x1 = row / n1, q2 = col % n2, x2 = col / n2;
@@ -1013,10 +1122,10 @@ __host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* si
     th0[i] = acc;
   }
   tm.sync();
-  const T* op = ops + gd.op_off;
+  const T* op = c.ops + gd.op_off;
   const int dd = d1 * d2;
-  const int ldb = jacobi_ld(m, n);
-  T* sb = smem;
+  const int ldb = jacobi_ld(m, n, 1, jacobi_rb<T>());
+  T* sb = phase_smem<T>(c.smem);
   for (int i = tm.tid(); i < m * n; i += tm.nt()) {
     const int row = i % m, col = i / m;
     const int q1 = row % n1, o1 = row / n1, q2 = col % n2, o2 = col / n2;
@@ -1027,23 +1136,31 @@ __host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* si
     th1[i] = acc;
   }
   tm.sync();
-  {
-    double* nrm = reinterpret_cast<double*>(w + L.sig);   // (both are overwritten after the iteration)
-    int32_t* pos = reinterpret_cast<int32_t*>(w + L.order);
-    column_order<T>(tm, th1, m, n, nrm, pos);
-    for (int i = tm.tid(); i < m * n; i += tm.nt()) sb[(i % m) + (int64_t)ldb * pos[i / m]] = th1[i];
-  }
+  double* nrm = reinterpret_cast<double*>(w + L.sig);   // (both are overwritten after the iteration)
+  int32_t* pos = reinterpret_cast<int32_t*>(w + L.order);
+  column_order<T>(tm, th1, m, n, nrm, pos);
+  for (int i = tm.tid(); i < m * n; i += tm.nt()) sb[(i % m) + ldb * pos[i / m]] = th1[i];
   tm.sync();
-  BPX_STAMP(9);
-  jacobi_groups<T>(tm, sb, m, n, ldb, flag, bad, stamps ? stamps + 13 : nullptr);
-  if (*bad) return 1;
-  BPX_STAMP(10);
+}
+
+// singular values, their order, Y_a (the new R factors) and W_a = R_a^+ Y_a from the rotated operand in shared memory
+template <typename T>
+__host__ __device__ __forceinline__ void phase_bond_post(const Team tm, Gate3<T>& c) {
+  using E = Elem<T>;
+  const GateDesc& gd = *c.gd;
+  const Layout3& L = c.L;
+  T* w = c.w;
+  const int m = gd.s[0].cols * gd.s[0].d, n = gd.s[1].cols * gd.s[1].d;
+  const int ldb = jacobi_ld(m, n, 1, jacobi_rb<T>());
+  const T* sb = phase_smem<T>(c.smem);
+  const T* th1 = w + L.theta[1];
+  T* th2 = w + L.theta[2];  // rotated copy: U diag(s)
   double* sig = reinterpret_cast<double*>(w + L.sig);
   int32_t* order = reinterpret_cast<int32_t*>(w + L.order);
-  for (int i = tm.tid(); i < m * n; i += tm.nt()) th2[i] = sb[(i % m) + (int64_t)ldb * (i / m)];
+  for (int i = tm.tid(); i < m * n; i += tm.nt()) th2[i] = sb[(i % m) + ldb * (i / m)];
   for (int j = tm.tid(); j < n; j += tm.nt()) {
     double a = 0.0;
-    for (int r = 0; r < m; ++r) a += E::abs2(sb[r + (int64_t)ldb * j]);
+    for (int r = 0; r < m; ++r) a += E::abs2(sb[r + ldb * j]);
     sig[j] = sqrt(a);
   }
   tm.sync();
@@ -1060,7 +1177,7 @@ __host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* si
   tm.sync();
   const int k = gd.k;
   double nrm = 1.0;
-  if (normalize) {
+  if (c.normalize) {
     double a = 0.0;
     for (int j = 0; j < k; ++j) a += sig[order[j]] * sig[order[j]];
     nrm = a > 0.0 ? sqrt(a) : 1.0;
@@ -1071,17 +1188,17 @@ __host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* si
     T* y = w + L.y[a];
     const int na = sd.cols, da = sd.d;
     for (int i = tm.tid(); i < na * da * k; i += tm.nt()) {
-      const int q = i % na, c = i / na, x = c % da, kk = c / da, j = order[kk];
+      const int q = i % na, cc = i / na, x = cc % da, kk = cc / da, j = order[kk];
       const double sj = sig[j], snew = sj / nrm;
       T v = E::zero();
       if (sj > 0.0) {
         if (a == 0) {
-          v = scal(th2[(q + na * x) + (int64_t)m * j], sqrt(snew) / sj);
+          v = scal(th2[(q + na * x) + m * j], sqrt(snew) / sj);
         } else {
           // conj(V[c2, j]) = sum_r theta[r, c2] conj(u_j[r]) / s_j,  u_j = th2[:, j] / s_j
           const int c2 = q + na * x;
           T acc = E::zero();
-          for (int r = 0; r < m; ++r) acc = E::fma(th1[r + (int64_t)m * c2], E::conj(th2[r + (int64_t)m * j]), acc);
+          for (int r = 0; r < m; ++r) acc = E::fma(th1[r + m * c2], E::conj(th2[r + m * j]), acc);
           v = scal(acc, sqrt(snew) / (sj * sj));
         }
       }
@@ -1097,64 +1214,222 @@ __host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* si
     const T* ri = w + L.rinv[a];
     T* W = w + L.w[a];
     for (int i = tm.tid(); i < PC * PC; i += tm.nt()) {
-      const int cp = i % PC, c = i / PC;
+      const int cp = i % PC, cc = i / PC;
       T acc = E::zero();
-      if (c < na && cp < nc)
-        for (int q = 0; q < na; ++q) acc = E::fma(ri[c + na * q], y[q + na * cp], acc);
-      W[c * PC + cp] = acc;
+      if (cc < na && cp < nc)
+        for (int q = 0; q < na; ++q) acc = E::fma(ri[cc + na * q], y[q + na * cp], acc);
+      W[cc * PC + cp] = acc;
     }
   }
   tm.sync();
-  BPX_STAMP(11);
-  for (int a = 0; a < 2; ++a) {
-    const Side& sd = gd.s[a];
-    T* A = sites + sd.site_off;
-    if (CPLX)
-      final_side<T, 128, 1, 8>(tm, sd, tb[a], w + L.at[a], A, w + L.w[a], smem);
-    else
-      final_side<T, 256, 2, 16>(tm, sd, tb[a], w + L.at[a], A, w + L.w[a], smem);
+}
+
+// A'_a = A_a W_a in place
+template <typename T>
+__host__ __device__ __forceinline__ void phase_final_side(const Team tm, Gate3<T>& c, int a) {
+  constexpr bool CPLX = Elem<T>::is_complex;
+  const Side& sd = c.gd->s[a];
+  const Layout3& L = c.L;
+  T* w = c.w;
+  T* smem = phase_smem<T>(c.smem);
+  T* A = c.sites + sd.site_off;
+  if (CPLX)
+    final_side<T, 128, 1, 8>(tm, sd, c.tb[a], w + L.at[a], A, w + L.w[a], smem);
+  else
+    final_side<T, 256, 2, 16>(tm, sd, c.tb[a], w + L.at[a], A, w + L.w[a], smem);
+}
+// the two messages of the gate edge = diag(S / |S|), the singular values
+template <typename T>
+__host__ __device__ __forceinline__ void phase_final_bond(const Team tm, Gate3<T>& c) {
+  using E = Elem<T>;
+  const GateDesc& gd = *c.gd;
+  const Layout3& L = c.L;
+  T* w = c.w;
+  const double* sig = reinterpret_cast<const double*>(w + L.sig);
+  const int32_t* order = reinterpret_cast<const int32_t*>(w + L.order);
+  const int chi = gd.chi_b, k = gd.k;
+  double nrm = 1.0;
+  if (c.normalize) {
+    double a = 0.0;
+    for (int j = 0; j < k; ++j) a += sig[order[j]] * sig[order[j]];
+    nrm = a > 0.0 ? sqrt(a) : 1.0;
   }
+  T* msgs = c.msgs;
   for (int i = tm.tid(); i < chi * chi; i += tm.nt()) {
-    const int r = i % chi, c = i / chi;
-    const T v = (r == c && r < k) ? from_real<T>(sig[order[r]] / nrm) : E::zero();
+    const int r = i % chi, cc = i / chi;
+    const T v = (r == cc && r < k) ? from_real<T>(sig[order[r]] / nrm) : E::zero();
     msgs[gd.msg12 + i] = v;
     msgs[gd.msg21 + i] = v;
   }
-  if (sv_out)
-    for (int i = tm.tid(); i < chi; i += tm.nt()) sv_out[i] = i < k ? sig[order[i]] / nrm : 0.0;
+  if (c.sv_out)
+    for (int i = tm.tid(); i < chi; i += tm.nt()) c.sv_out[i] = i < k ? sig[order[i]] / nrm : 0.0;
   tm.sync();
-  BPX_STAMP(12);
-#undef BPX_STAMP
+}
+// the SVD iteration of the bond matrix (operand in shared memory, left there by phase_bond_pre)
+template <typename T>
+__host__ __device__ __forceinline__ void phase_bond_svd(const Team tm, Gate3<T>& c) {
+  const GateDesc& gd = *c.gd;
+  const int m = gd.s[0].cols * gd.s[0].d, n = gd.s[1].cols * gd.s[1].d;
+  jacobi_groups<T>(tm, phase_smem<T>(c.smem), m, n, jacobi_ld(m, n, 1, jacobi_rb<T>()), c.flag, c.bad, c.stamps ? c.stamps + 21 : nullptr);
+}
+
+// One gate from start to end on ONE team: the host entry (tests/native/apply_host.cu runs exactly the device code of the
+// phases).  Returns (to every thread) 0 when the gate was applied, 1 when it was left untouched for the fallback.
+template <typename T>
+__host__ __device__ int run_two_site_v3(const Team tm, const GateDesc& gd, T* sites, T* msgs, const T* ops, T* w, double* sv_out,
+                                        int normalize, int* flag, int* bad, T* smem, long long* stamps = nullptr) {
+  Gate3<T> c;
+  c.gd = &gd;
+  c.sites = sites;
+  c.msgs = msgs;
+  c.ops = ops;
+  c.w = w;
+  c.sv_out = sv_out;
+  c.smem = smem;
+  c.flag = flag;
+  c.bad = bad;
+  c.stamps = stamps;
+  c.normalize = normalize;
+  c.L = layout3_of(gd);
+  c.tt = w + c.L.tt;
+  if (tm.tid() == 0) *bad = 0;
+  tm.sync();
+  for (int a = 0; a < 2; ++a) {
+    phase_side<T>(tm, c, a);
+    if (*c.bad) return 1;
+  }
+  phase_eig<T>(tm, c);
+  if (*c.bad) return 1;
+  phase_bond_pre<T>(tm, c);
+  phase_bond_svd<T>(tm, c);
+  if (*c.bad) return 1;
+  phase_bond_post<T>(tm, c);
+  for (int a = 0; a < 2; ++a) phase_final_side<T>(tm, c, a);
+  phase_final_bond<T>(tm, c);
   return 0;
 }
 
 #ifdef __CUDACC__
 struct ApplyArgs3 {
-  ApplyArgs base;       // base.ws: one work space of ws_stride elements PER CTA (not per gate: a layer is one launch)
+  ApplyArgs base;       // base.ws: one work space of ws_stride elements PER GATE of the chunk [g0, g1)
   int64_t ws_stride;
-  int32_t* status;      // per gate: 0 applied, 1 left for the fallback
-  long long* stamps;    // debug (BPX_APPLY_TIMING=1): 16 clock64 stamps per gate, or NULL
+  void* tt;             // bp_apply3_sides: one scratch buffer of tt_stride elements per CTA
+  int64_t tt_stride;
+  int64_t g0, g1;       // the gates of this launch
+  int32_t* status;      // per gate of the batch: 0 applied, 1 left for the fallback (zeroed before the first kernel)
+  long long* stamps;    // debug (BPX_APPLY_TIMING=1): STAMP_SLOTS clock64 stamps per gate, or NULL
 };
 
+constexpr int NT_BOND = 128;  // bp_apply3_bond: 64 columns = 32 pairs x 4 lanes
+
 template <typename T>
-__global__ void __launch_bounds__(NT, 2) bp_apply_gates_v3(ApplyArgs3 a3) {
+__device__ __forceinline__ void gate3_fill(Gate3<T>& c, const ApplyArgs3& a3, int64_t g, int* flag, int* bad) {
   extern __shared__ __align__(16) unsigned char dyn_smem3[];
-  __shared__ int flag, bad;
   const ApplyArgs& a = a3.base;
+  const GateDesc& gd = a.gates[g];
+  const int64_t sv_row = gd.sv_row_p1 > 0 ? gd.sv_row_p1 - 1 : g;
+  c.gd = &gd;
+  c.sites = static_cast<T*>(a.sites);
+  c.msgs = static_cast<T*>(a.msgs);
+  c.ops = static_cast<const T*>(a.ops);
+  c.w = static_cast<T*>(a.ws) + (g - a3.g0) * a3.ws_stride;
+  c.tt = static_cast<T*>(a3.tt) + (int64_t)blockIdx.x * a3.tt_stride;
+  c.sv_out = a.sv_out ? a.sv_out + sv_row * a.sv_stride : nullptr;
+  c.smem = reinterpret_cast<T*>(dyn_smem3);
+  c.flag = flag;
+  c.bad = bad;
+  c.stamps = a3.stamps ? a3.stamps + STAMP_SLOTS * g : nullptr;
+  c.normalize = a.normalize;
+  c.L = layout3_of(gd, false);
+  *bad = 0;
+}
+#undef BPX_STAMP
+#define BPX_STAMP(i) do { if (c.stamps && threadIdx.x == 0) c.stamps[i] = clock64(); } while (0)
+
+// (gate, side) items: tables, message check, absorb, Gram product -> at[a], G_a in the gate's work space
+template <typename T>
+__global__ void __launch_bounds__(NT, 2) bp_apply3_sides(ApplyArgs3 a3) {
+  __shared__ int flag, bad;
+  __shared__ Gate3<T> c;
   Team tm;
   tm.lane = threadIdx.x & 31;
   tm.wid = threadIdx.x >> 5;
   tm.nw = NT / 32;
-  for (int64_t g = blockIdx.x; g < a.n_gates; g += gridDim.x) {
-    const int64_t sv_row = a.gates[g].sv_row_p1 > 0 ? a.gates[g].sv_row_p1 - 1 : g;
-    const int st = run_two_site_v3<T>(tm, a.gates[g], static_cast<T*>(a.sites), static_cast<T*>(a.msgs), static_cast<const T*>(a.ops),
-                                      static_cast<T*>(a.ws) + (int64_t)blockIdx.x * a3.ws_stride,
-                                      a.sv_out ? a.sv_out + sv_row * a.sv_stride : nullptr, a.normalize, &flag, &bad,
-                                      reinterpret_cast<T*>(dyn_smem3), a3.stamps ? a3.stamps + 32 * g : nullptr);
-    if (threadIdx.x == 0) a3.status[g] = st;
+  const int64_t nitems = 2 * (a3.g1 - a3.g0);
+  for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int64_t g = a3.g0 + (it >> 1);
+    const int a = (int)(it & 1);
     __syncthreads();
+    if (threadIdx.x == 0) gate3_fill<T>(c, a3, g, &flag, &bad);
+    __syncthreads();
+    BPX_STAMP(8 * a);
+    phase_side<T>(tm, c, a);
+    __syncthreads();
+    if (threadIdx.x == 0 && bad) a3.status[g] = 1;  // (both sides may store the same 1)
   }
 }
+
+// one gate per CTA: G_a -> R_a, R_a^+; the bond problem; W_a
+template <typename T, int CTAS>
+__global__ void __launch_bounds__(NT_BOND, CTAS) bp_apply3_bond(ApplyArgs3 a3) {
+  __shared__ int flag, bad;
+  __shared__ Gate3<T> c;
+  Team tm;
+  tm.lane = threadIdx.x & 31;
+  tm.wid = threadIdx.x >> 5;
+  tm.nw = NT_BOND / 32;
+  for (int64_t g = a3.g0 + blockIdx.x; g < a3.g1; g += gridDim.x) {
+    if (a3.status[g] != 0) continue;  // (uniform: written by the previous kernel)
+    __syncthreads();
+    if (threadIdx.x == 0) gate3_fill<T>(c, a3, g, &flag, &bad);
+    __syncthreads();
+    BPX_STAMP(16);
+    phase_eig<T>(tm, c);
+    BPX_STAMP(17);
+    if (!bad) {
+      phase_bond_pre<T>(tm, c);
+      BPX_STAMP(18);
+      phase_bond_svd<T>(tm, c);
+      BPX_STAMP(19);
+    }
+    if (!bad) {
+      phase_bond_post<T>(tm, c);
+      BPX_STAMP(20);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bad) a3.status[g] = 1;
+  }
+}
+
+// (gate, side) items: A'_a = A_a W_a; the item of side 0 also writes the messages and the singular values
+template <typename T>
+__global__ void __launch_bounds__(NT, 2) bp_apply3_final(ApplyArgs3 a3) {
+  __shared__ int flag, bad;
+  __shared__ Gate3<T> c;
+  Team tm;
+  tm.lane = threadIdx.x & 31;
+  tm.wid = threadIdx.x >> 5;
+  tm.nw = NT / 32;
+  const int64_t nitems = 2 * (a3.g1 - a3.g0);
+  for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int64_t g = a3.g0 + (it >> 1);
+    const int a = (int)(it & 1);
+    if (a3.status[g] != 0) continue;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      gate3_fill<T>(c, a3, g, &flag, &bad);
+      const Side& sd = c.gd->s[a];
+      const Walk wk = walk_of(sd);
+      c.tb[a] = tabs_at<T>(sd, wk, c.w + c.L.tab[a]);
+    }
+    __syncthreads();
+    BPX_STAMP(24 + 2 * a);
+    phase_final_side<T>(tm, c, a);
+    if (a == 0) phase_final_bond<T>(tm, c);
+    BPX_STAMP(25 + 2 * a);
+  }
+}
+#undef BPX_STAMP
 #endif
 
 }  // namespace applyk3

@@ -163,7 +163,7 @@ struct bpx_ctx {
 
   // grow-only work space of the belief / gate / expectation-value calls (one buffer per role; no cudaMalloc / cudaFree on
   // the call path once warm).  Buffers above WS_KEEP_BYTES (2 GiB) are released at the end of the call that needed them.
-  enum { WS_SCALARS = 0, WS_EDGE_SCALARS, WS_LOGSUM, WS_OPS, WS_OP_OFF, WS_LIST, WS_DESC, WS_WORK, WS_SV, WS_OUT, WS_COUNT };
+  enum { WS_SCALARS = 0, WS_EDGE_SCALARS, WS_LOGSUM, WS_OPS, WS_OP_OFF, WS_LIST, WS_DESC, WS_WORK, WS_SCRATCH, WS_SV, WS_OUT, WS_COUNT };
   void* ws[WS_COUNT] = {};
   size_t ws_bytes[WS_COUNT] = {};
   void* h_logsum = nullptr;  // pinned: result block of bpx_bethe_free_energy
