@@ -601,6 +601,126 @@ __host__ __device__ __forceinline__ void gram_side(const Team tm, const Side& sd
   }
 }
 
+#ifdef __CUDACC__
+// ---- Gram pass on the FP64 tensor pipe (Float64, device only) --------------------------------------------------------------
+// G = A^H T as DMMA.8x8x4: M = c' (4 blocks of 8), N = c (4 blocks of 8), K = rows.  A warp takes every nw-th group of 4
+// rows of a tile and keeps all 16 accumulator tiles (32 doubles); per group 4 + 4 fragment loads (one element per lane each:
+// A^H[c' = 8 mb + lane / 4][row = lane % 4], T[row = lane % 4][c = 8 nb + lane / 4]) feed 16 DMMAs = 4096 MACs -- against
+// 12 operand loads per 32 FMAs = 1024 MACs per warp instruction group of the FMA version.  Partial tiles of the warps are
+// summed through shared memory exactly like there.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// The tiles arrive by TMA bulk copies (they are contiguous row ranges of the scratch copies), two stages of TRG / 2 rows, one
+// mbarrier per stage: the loads of the next tile overlap the DMMAs of this one (the register-staged synchronous copies of the
+// FMA version left the pass waiting on L2 / DRAM round trips most of the time: 26 k clocks per 70 KB tile pair).
+__device__ __forceinline__ uint32_t smem_u32_3(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct GramPipe {
+  uint64_t* bar;     // two mbarriers in shared memory, initialised once per kernel (gram_pipe_init)
+  uint32_t used[2];  // completed phases per stage (the same in every thread)
+};
+__device__ __forceinline__ void gram_pipe_init(GramPipe& gp, uint64_t* bar) {
+  gp.bar = bar;
+  gp.used[0] = gp.used[1] = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32_3(bar + i)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void gram_side_mma(const Team tm, const Side& sd, const double* at, const double* tt, double* G, double* smem,
+                                              GramPipe& gp) {
+  static_assert(PC == 32, "4 x 4 blocks of 8 x 8");
+  constexpr int TR = TRG / 2;
+  const int cols = sd.cols;
+  const int64_t rows_all = sd.rows;
+  const int ntile = (int)((rows_all + TR - 1) / TR);
+  const int g = tm.lane >> 2, t = tm.lane & 3;
+  auto issue = [&](int i) {  // thread 0: both tiles of row block i into stage i & 1
+    const int s = i & 1;
+    const int64_t row0 = (int64_t)i * TR;
+    const uint32_t bytes = (uint32_t)(((rows_all - row0) < TR ? (rows_all - row0) : TR) * PCP * sizeof(double));
+    const uint32_t bar = smem_u32_3(gp.bar + s), dst = smem_u32_3(smem + (int64_t)s * 2 * TR * PCP);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2 * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(at + row0 * PCP), "r"(bytes), "r"(bar)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     dst + (uint32_t)(TR * PCP * sizeof(double))),
+                 "l"(tt + row0 * PCP), "r"(bytes), "r"(bar)
+                 : "memory");
+  };
+  tm.sync();  // (the scratch copies were written by this CTA's ordinary stores: visible after the barrier; shared memory is free)
+  if (tm.tid() == 0) {
+    asm volatile("fence.proxy.async;\n" ::: "memory");  // generic-proxy writes (global and shared) before the async-proxy copies
+    issue(0);
+    if (ntile > 1) issue(1);
+  }
+  double acc[4][4][2];
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+  for (int i = 0; i < ntile; ++i) {
+    const int s = i & 1;
+    const int nr = (int)((rows_all - (int64_t)i * TR) < TR ? (rows_all - (int64_t)i * TR) : TR);
+    {
+      const uint32_t bar = smem_u32_3(gp.bar + s), parity = gp.used[s] & 1;
+      uint32_t ok;
+      do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+      } while (!ok);
+      gp.used[s]++;
+    }
+    const double* sA = smem + (int64_t)s * 2 * TR * PCP;
+    const double* sT = sA + TR * PCP;
+    // (columns >= cols of the tiles are uninitialised: their products land in rows / columns of G that are never read)
+    for (int r0 = 4 * tm.wid; r0 < nr; r0 += 4 * tm.nw) {
+      const bool ok = r0 + t < nr;
+      const double* pa = sA + (r0 + t) * PCP + g;
+      const double* pt = sT + (r0 + t) * PCP + g;
+      double fa[4], fb[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        fa[b] = ok ? pa[8 * b] : 0.0;
+        fb[b] = ok ? pt[8 * b] : 0.0;
+      }
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], fa[mb], fb[nb]);
+    }
+    tm.sync();  // every warp is done with stage s
+    if (tm.tid() == 0 && i + 2 < ntile) issue(i + 2);
+  }
+  double* red = smem;  // red[w][c'][c]
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      double* o = red + ((int64_t)tm.wid * PC + 8 * mb + g) * PC + 8 * nb + 2 * t;
+      o[0] = acc[mb][nb][0];
+      o[1] = acc[mb][nb][1];
+    }
+  tm.sync();
+  for (int e = tm.tid(); e < PC * PC; e += tm.nt()) {
+    const int cp = e / PC, cc = e % PC;
+    double s = 0.0;
+    for (int w = 0; w < tm.nw; ++w) s += red[(int64_t)w * PC * PC + e];
+    if (cp < cols && cc < cols) G[cp + cols * cc] = s;
+  }
+  tm.sync();
+}
+#endif
+
 // 1 / sqrt(x) and 1 / x to full double accuracy from the hardware's 20-bit approximations + two Newton steps: a short
 // dependent chain (the IEEE sqrt / division sequences cost several hundred cycles of latency each, and the Jacobi steps
 // below are pure latency).  Outside the safe exponent range the exact functions are used.
@@ -1033,6 +1153,9 @@ struct Gate3 {
   Layout3 L;
   Tabs tb[2];
 };
+#ifdef __CUDACC__
+struct GramPipe;
+#endif
 
 // debug stamps (BPX_APPLY_TIMING=1), STAMP_SLOTS clock64 values per gate: side a: 8 a + {0 start, 1 message check, 2 absorb,
 // 3 Gram}; bond kernel: 16 start, 17 eigen-decompositions, 18 theta + gate, 19 SVD, 20 Y / W; Jacobi sweeps: 21 SVD, 22 eig;
@@ -1046,7 +1169,7 @@ constexpr int STAMP_SLOTS = 48;
 
 // tables, message check, absorb, Gram product of side a
 template <typename T>
-__host__ __device__ __forceinline__ void phase_side(const Team tm, Gate3<T>& c, int a) {
+__host__ __device__ __forceinline__ void phase_side(const Team tm, Gate3<T>& c, int a, void* gram_pipe = nullptr) {
   constexpr bool CPLX = Elem<T>::is_complex;
   const Side& sd = c.gd->s[a];
   const Layout3& L = c.L;
@@ -1071,7 +1194,12 @@ __host__ __device__ __forceinline__ void phase_side(const Team tm, Gate3<T>& c, 
   else
     absorb_side<T, 1>(tm, sd, wka, c.tb[a], A, w + L.h[a], w + L.at[a], c.tt, smem);
   BPX_STAMP(8 * a + 2);
-  gram_side<T, CPLX ? 4 : 8>(tm, sd, w + L.at[a], c.tt, w + L.g[a], smem);
+#ifdef __CUDA_ARCH__
+  if constexpr (!CPLX)
+    gram_side_mma(tm, sd, w + L.at[a], c.tt, w + L.g[a], smem, *static_cast<GramPipe*>(gram_pipe));
+  else
+#endif
+    gram_side<T, CPLX ? 4 : 8>(tm, sd, w + L.at[a], c.tt, w + L.g[a], smem);
   BPX_STAMP(8 * a + 3);
 }
 
@@ -1355,6 +1483,9 @@ __global__ void __launch_bounds__(NT, 2) bp_apply3_sides(ApplyArgs3 a3) {
   tm.lane = threadIdx.x & 31;
   tm.wid = threadIdx.x >> 5;
   tm.nw = NT / 32;
+  __shared__ uint64_t gram_bar[2];
+  GramPipe gp;
+  gram_pipe_init(gp, gram_bar);
   const int64_t nitems = 2 * (a3.g1 - a3.g0);
   for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
     const int64_t g = a3.g0 + (it >> 1);
@@ -1363,7 +1494,7 @@ __global__ void __launch_bounds__(NT, 2) bp_apply3_sides(ApplyArgs3 a3) {
     if (threadIdx.x == 0) gate3_fill<T>(c, a3, g, &flag, &bad);
     __syncthreads();
     BPX_STAMP(8 * a);
-    phase_side<T>(tm, c, a);
+    phase_side<T>(tm, c, a, &gp);
     __syncthreads();
     if (threadIdx.x == 0 && bad) a3.status[g] = 1;  // (both sides may store the same 1)
   }
