@@ -1911,7 +1911,8 @@ static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates
   int rc, per_sm[3] = {0, 0, 0};
   if ((rc = cplx ? apply_prepare_v3<c64>(ctx, bytes, bond_ctas, per_sm) : apply_prepare_v3<double>(ctx, bytes, bond_ctas, per_sm))) return rc;
   if (per_sm[0] < 1 || per_sm[1] < 1 || per_sm[2] < 1) return BPX_OK;
-  const int grid[3] = {ctx->num_sms * per_sm[0], ctx->num_sms * per_sm[1], ctx->num_sms * per_sm[2]};
+  int grid[3] = {ctx->num_sms * per_sm[0], ctx->num_sms * per_sm[1], ctx->num_sms * per_sm[2]};
+  if (const char* e = getenv("BPX_APPLY_SIDES_GRID")) grid[0] = std::max(1, std::min(grid[0], atoi(e)));  // experiment: fewer CTAs in flight
   // chunks: as many gates as fit the work-space budget, in whole waves of the side kernel when there are several chunks
   int64_t budget = (int64_t)3 << 29;  // 1.5 GiB: stays in the context's cached arena
   if (const char* e = getenv("BPX_APPLY_WS_BYTES")) budget = std::max<int64_t>(1, atoll(e));  // tests: force several chunks

@@ -36,13 +36,25 @@ using namespace bpx::applyk;
 
 constexpr int PC = 32;               // padded column count of the tiles; the fast path takes sides with cols <= PC
 constexpr int TRG = 128;             // rows per tile of the Gram pass
-constexpr int PCP = PC + 2;          // row stride of the Gram tiles: 16-byte aligned rows, stores two wavefronts per warp
+constexpr int PCP = PC + 2;          // row stride of the scratch copies: 16-byte aligned rows
 constexpr double COND_MIN = 1e-10;   // smallest kept eigenvalue of G relative to the largest
 constexpr double PIVOT_MIN = 1e-12;  // smallest Cholesky pivot of a message relative to its largest diagonal entry
 constexpr int MAXDIM = 16;           // largest external link dimension (a fibre lives in registers)
 
+// Layout of the scratch copies `at` / `tt` (the matrix view, rows x PCP): two rows and one column group (the CG columns an
+// absorb batch produces: 2 Float64, 1 ComplexF64) are 32 contiguous bytes, so that the batch's stores fill whole DRAM sectors
+// -- with plain row-major rows every store was half a sector, the L2 did not keep the lines until the other half arrived
+// (write hit rate 8 %), and every half went to DRAM as a read-modify-write: 11.2 MB of traffic per tensor instead of 5.4
+// (ncu, profiles/r2av_apply3_sides_ncu_summary.csv).  Row ranges starting at an even row stay contiguous (tiles by bulk copy).
+template <typename T>
+__host__ __device__ __forceinline__ int64_t sidx(int64_t r, int c) {
+  constexpr int CG = Elem<T>::is_complex ? 1 : 2;
+  return (r >> 1) * (2 * PCP) + (c / CG) * (2 * CG) + (r & 1) * CG + (c % CG);
+}
+__host__ __device__ __forceinline__ int64_t scratch_elems(int64_t rows) { return ((rows + 1) & ~(int64_t)1) * PCP; }
+
 struct Layout3 {
-  int64_t at[2];        // per side: the matrix view of A as a row-major rows x PCP matrix (tiles of rows are contiguous)
+  int64_t at[2];        // per side: the matrix view of A, rows x PCP in the sidx() layout (tiles of rows are contiguous)
   int64_t tt;           // T = (M_1 x M_2 x ..) A in the same layout; shared by the two sides
   int64_t h[2];         // Hermitian parts of the boundary messages, slot order, chi^2 each
   int64_t g[2];         // G (cols x cols) and its rotated copy
@@ -64,12 +76,12 @@ __host__ __device__ inline int64_t herm_elems(const Side& s) {
   return t;
 }
 
-__host__ __device__ inline int64_t tt_elems(const GateDesc& g) { return (g.s[0].rows > g.s[1].rows ? g.s[0].rows : g.s[1].rows) * PCP; }
+__host__ __device__ inline int64_t tt_elems(const GateDesc& g) { return scratch_elems(g.s[0].rows > g.s[1].rows ? g.s[0].rows : g.s[1].rows); }
 // with_tt = false: the per-GATE work space of the device kernels (T lives in a per-CTA scratch buffer there)
 __host__ __device__ inline Layout3 layout3_of(const GateDesc& g, bool with_tt = true) {
   Layout3 L;
   int64_t o = 0;
-  for (int a = 0; a < 2; ++a) { L.at[a] = o; o += g.s[a].rows * PCP; }
+  for (int a = 0; a < 2; ++a) { L.at[a] = o; o += scratch_elems(g.s[a].rows); }
   L.tt = o; o += with_tt ? tt_elems(g) : 0;
   for (int a = 0; a < 2; ++a) {
     const Side& s = g.s[a];
@@ -460,14 +472,14 @@ __host__ __device__ __forceinline__ void absorb_side(const Team tm, const Side& 
       for (int u = 0; u < U; ++u) {
         const int i = i0 + u * nt, b = i % CB, r = i / CB;
         col[b * prow + r + dpad.div(r)] = v[u];
-        aout[(int64_t)r * PCP + c0 + b] = v[u];  // the matrix view, row-major: the Gram and final passes read plain tiles
+        aout[sidx<T>(r, c0 + b)] = v[u];  // the matrix view: the Gram and final passes read plain tiles
       }
     }
     for (int i = nfull + tid; i < total; i += nt) {
       const int b = i % CB, r = i / CB;
       const T v = a[rowt[r] + cofs[b]];
       col[b * prow + r + dpad.div(r)] = v;
-      aout[(int64_t)r * PCP + c0 + b] = v;
+      aout[sidx<T>(r, c0 + b)] = v;
     }
     tm.sync();
     BPX_ASTAMP(1);
@@ -482,7 +494,7 @@ __host__ __device__ __forceinline__ void absorb_side(const Team tm, const Side& 
     }
     for (int i = tm.tid(); i < total; i += nt) {
       const int b = i % CB, r = i / CB;
-      tout[(int64_t)r * PCP + c0 + b] = col[b * prow + r + dpad.div(r)];
+      tout[sidx<T>(r, c0 + b)] = col[b * prow + r + dpad.div(r)];
     }
     tm.sync();
     BPX_ASTAMP(7);
@@ -516,40 +528,34 @@ __host__ __device__ __forceinline__ void gram_side(const Team tm, const Side& sd
 #endif
     for (int64_t row0 = 0; row0 < rows_all; row0 += TRG) {
       const int nr = (int)((rows_all - row0) < TRG ? (rows_all - row0) : TRG);
-      copy_tile<T>(tm, sA, at + row0 * PCP, (int64_t)nr * PCP);
-      copy_tile<T>(tm, sT, tt + row0 * PCP, (int64_t)nr * PCP);
+      copy_tile<T>(tm, sA, at + sidx<T>(row0, 0), scratch_elems(nr));
+      copy_tile<T>(tm, sT, tt + sidx<T>(row0, 0), scratch_elems(nr));
 #ifdef __CUDA_ARCH__
       const int li = tm.lane >> 2, lj = tm.lane & 3;
-      const T* pa = sA + 4 * li;
-      const T* pt = sT + TJ * (lj + 4 * pass);
       for (int r = tm.wid; r < nr; r += tm.nw) {
         T av[4], tv[TJ];
-        if constexpr (!E::is_complex) {  // rows of the tiles are 16-byte aligned (PCP even)
-          const double2* a2 = reinterpret_cast<const double2*>(pa + r * PCP);
-          const double2* t2 = reinterpret_cast<const double2*>(pt + r * PCP);
+        if constexpr (!E::is_complex) {  // column pairs (c even, c + 1) are 16 contiguous, aligned bytes
 #pragma unroll
           for (int x = 0; x < 2; ++x) {
-            const double2 q = a2[x];
+            const double2 q = *reinterpret_cast<const double2*>(sA + sidx<T>(r, 4 * li + 2 * x));
             av[2 * x] = q.x;
             av[2 * x + 1] = q.y;
           }
 #pragma unroll
           for (int y = 0; y < TJ / 2; ++y) {
-            const double2 q = t2[y];
+            const double2 q = *reinterpret_cast<const double2*>(sT + sidx<T>(r, TJ * (lj + 4 * pass) + 2 * y));
             tv[2 * y] = q.x;
             tv[2 * y + 1] = q.y;
           }
         } else {
-          const double2* a2 = reinterpret_cast<const double2*>(pa + r * PCP);
-          const double2* t2 = reinterpret_cast<const double2*>(pt + r * PCP);
 #pragma unroll
           for (int x = 0; x < 4; ++x) {
-            const double2 q = a2[x];
+            const double2 q = *reinterpret_cast<const double2*>(sA + sidx<T>(r, 4 * li + x));
             av[x] = E::conj(*reinterpret_cast<const T*>(&q));
           }
 #pragma unroll
           for (int y = 0; y < TJ; ++y) {
-            const double2 q = t2[y];
+            const double2 q = *reinterpret_cast<const double2*>(sT + sidx<T>(r, TJ * (lj + 4 * pass) + y));
             tv[y] = *reinterpret_cast<const T*>(&q);
           }
         }
@@ -565,7 +571,7 @@ __host__ __device__ __forceinline__ void gram_side(const Team tm, const Side& sd
           for (int x = 0; x < 4; ++x)
             for (int y = 0; y < TJ; ++y) {
               T& o = hacc[(size_t)(role * 4 + x) * TJ + y];
-              o = E::fma(E::conj(sA[r * PCP + 4 * li + x]), sT[r * PCP + TJ * (lj + 4 * pass) + y], o);
+              o = E::fma(E::conj(sA[sidx<T>(r, 4 * li + x)]), sT[sidx<T>(r, TJ * (lj + 4 * pass) + y)], o);
             }
       }
       (void)L;
@@ -639,15 +645,15 @@ __device__ __forceinline__ void gram_side_mma(const Team tm, const Side& sd, con
   auto issue = [&](int i) {  // thread 0: both tiles of row block i into stage i & 1
     const int s = i & 1;
     const int64_t row0 = (int64_t)i * TR;
-    const uint32_t bytes = (uint32_t)(((rows_all - row0) < TR ? (rows_all - row0) : TR) * PCP * sizeof(double));
+    const uint32_t bytes = (uint32_t)(scratch_elems((rows_all - row0) < TR ? (rows_all - row0) : TR) * sizeof(double));
     const uint32_t bar = smem_u32_3(gp.bar + s), dst = smem_u32_3(smem + (int64_t)s * 2 * TR * PCP);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2 * bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
-                 "l"(at + row0 * PCP), "r"(bytes), "r"(bar)
+                 "l"(at + sidx<double>(row0, 0)), "r"(bytes), "r"(bar)
                  : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                      dst + (uint32_t)(TR * PCP * sizeof(double))),
-                 "l"(tt + row0 * PCP), "r"(bytes), "r"(bar)
+                 "l"(tt + sidx<double>(row0, 0)), "r"(bytes), "r"(bar)
                  : "memory");
   };
   tm.sync();  // (the scratch copies were written by this CTA's ordinary stores: visible after the barrier; shared memory is free)
@@ -685,13 +691,12 @@ __device__ __forceinline__ void gram_side_mma(const Team tm, const Side& sd, con
     // (columns >= cols of the tiles are uninitialised: their products land in rows / columns of G that are never read)
     for (int r0 = 4 * tm.wid; r0 < nr; r0 += 4 * tm.nw) {
       const bool ok = r0 + t < nr;
-      const double* pa = sA + (r0 + t) * PCP + g;
-      const double* pt = sT + (r0 + t) * PCP + g;
+      const int64_t o = sidx<double>(r0 + t, g);  // (column 8 b + g: + 16 b)
       double fa[4], fb[4];
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        fa[b] = ok ? pa[8 * b] : 0.0;
-        fb[b] = ok ? pt[8 * b] : 0.0;
+        fa[b] = ok ? sA[o + 16 * b] : 0.0;
+        fb[b] = ok ? sT[o + 16 * b] : 0.0;
       }
 #pragma unroll
       for (int mb = 0; mb < 4; ++mb)
@@ -1020,13 +1025,13 @@ __host__ __device__ __forceinline__ void gram_factor_finish(const Team tm, int c
 }
 
 // ---- final pass: A'[row, c'] = sum_c A[row, c] W[c, c'], A from its row-major scratch copy, A' into the canonical tensor ----
-// Tiles of TRF rows as [row][PCP] in shared memory (plain contiguous copies).  A thread owns RT rows x NO outputs: per
+// Tiles of TRF rows in shared memory (plain contiguous copies, sidx() layout).  A thread owns RT rows x NO outputs: per
 // column pair RT 16-byte operand loads (rows 272 bytes apart: conflict free) and NO 16-byte broadcast loads of W feed 2 RT NO
 // FMAs.
 template <typename T, int TRF, int RT, int NO>
 __host__ __device__ __forceinline__ void final_side(const Team tm, const Side& sd, const Tabs tb, const T* at, T* a, const T* W, T* smem) {
   using E = Elem<T>;
-  T* sA = smem;                                  // [r][PCP]
+  T* sA = smem;                                  // sidx(r, c)
   T* sW = smem + (int64_t)TRF * PCP;             // [c][PC]
   for (int i = tm.tid(); i < PC * PC; i += tm.nt()) sW[i] = W[i];
   const int cols = sd.cols;
@@ -1037,7 +1042,7 @@ __host__ __device__ __forceinline__ void final_side(const Team tm, const Side& s
   constexpr int OG = PC / NO;                    // output groups
   for (int64_t row0 = 0; row0 < rows_all; row0 += TRF) {
     const int nr = (int)((rows_all - row0) < TRF ? (rows_all - row0) : TRF);
-    copy_tile<T>(tm, sA, at + row0 * PCP, (int64_t)nr * PCP);
+    copy_tile<T>(tm, sA, at + sidx<T>(row0, 0), scratch_elems(nr));
     for (int item = tm.tid(); item < RG * OG; item += tm.nt()) {
       const int rg = item % RG, og = item / RG;
       if (og * NO >= cols) continue;
@@ -1051,24 +1056,25 @@ __host__ __device__ __forceinline__ void final_side(const Team tm, const Side& s
         T a0[RT], a1[RT];
 #pragma unroll
         for (int x = 0; x < RT; ++x) {
-          const T* pa = sA + (rg + x * RG) * PCP + c;
+          const T* pa = sA + sidx<T>(rg + x * RG, c);  // (c is even)
+          const T* pb = sA + sidx<T>(rg + x * RG, c + 1);
 #ifdef __CUDA_ARCH__
           if constexpr (!E::is_complex) {
-            const double2 q = *reinterpret_cast<const double2*>(pa);
+            const double2 q = *reinterpret_cast<const double2*>(pa);  // the pair (c, c + 1): 16 contiguous, aligned bytes
             a0[x] = q.x;
             a1[x] = two ? q.y : 0.0;
           } else {
-            const double2 q0 = reinterpret_cast<const double2*>(pa)[0];
+            const double2 q0 = *reinterpret_cast<const double2*>(pa);
             a0[x] = *reinterpret_cast<const T*>(&q0);
             a1[x] = E::zero();
             if (two) {
-              const double2 q1 = reinterpret_cast<const double2*>(pa)[1];
+              const double2 q1 = *reinterpret_cast<const double2*>(pb);
               a1[x] = *reinterpret_cast<const T*>(&q1);
             }
           }
 #else
           a0[x] = pa[0];
-          a1[x] = two ? pa[1] : E::zero();
+          a1[x] = two ? pb[0] : E::zero();
 #endif
         }
         const T* pw = sW + c * PC + og * NO;
