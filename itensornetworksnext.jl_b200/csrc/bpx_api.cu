@@ -259,6 +259,7 @@ extern "C" int bpx_destroy(bpx_ctx* ctx) {
   free_problem(ctx);
   ws_release(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->apply_stream) cudaStreamDestroy(ctx->apply_stream);
   for (auto& g : ctx->io_graphs) cudaGraphExecDestroy(g.exec);
   if (ctx->copy_stream) {
     cudaStreamDestroy(ctx->copy_stream);
@@ -1848,23 +1849,78 @@ static void apply_fill_side(bpx_ctx* ctx, applyk::Side& s, int64_t v, int bond_s
 // message, ill-conditioned Gram matrix) come back in `rest` for the step-by-step versions, untouched.
 // *taken = false: the batch has a shape the kernels do not take (nothing ran).
 template <typename T>
-static int apply_launch_v3(bpx_ctx* ctx, const applyk3::ApplyArgs3& a3, const int bytes[3], const int grid[3], int bond_ctas,
-                           cudaEvent_t* ev /* 4 events (debug timing) or NULL */) {
-  const int64_t ng = a3.g1 - a3.g0;
-  if (ev) cudaEventRecord(ev[0], ctx->stream);
-  applyk3::bp_apply3_sides<T><<<(int)std::min<int64_t>(2 * ng, grid[0]), applyk::NT, bytes[0], ctx->stream>>>(a3);
-  if (ev) cudaEventRecord(ev[1], ctx->stream);
-  const int gb = (int)std::min<int64_t>(ng, grid[1]);
+static void apply_launch_sides(const applyk3::ApplyArgs3& a3, int bytes, int grid, cudaStream_t st) {
+  applyk3::bp_apply3_sides<T><<<(int)std::min<int64_t>(2 * (a3.g1 - a3.g0), grid), applyk::NT, bytes, st>>>(a3);
+}
+template <typename T>
+static void apply_launch_bond(const applyk3::ApplyArgs3& a3, int bytes, int grid, int bond_ctas, cudaStream_t st) {
+  const int gb = (int)std::min<int64_t>(a3.g1 - a3.g0, grid);
   constexpr int HI = Elem<T>::is_complex ? 3 : 5;
   if (bond_ctas >= HI)
-    applyk3::bp_apply3_bond<T, HI><<<gb, applyk3::NT_BOND, bytes[1], ctx->stream>>>(a3);
+    applyk3::bp_apply3_bond<T, HI><<<gb, applyk3::NT_BOND, bytes, st>>>(a3);
   else
-    applyk3::bp_apply3_bond<T, HI - 1><<<gb, applyk3::NT_BOND, bytes[1], ctx->stream>>>(a3);
+    applyk3::bp_apply3_bond<T, HI - 1><<<gb, applyk3::NT_BOND, bytes, st>>>(a3);
+}
+template <typename T>
+static void apply_launch_final(const applyk3::ApplyArgs3& a3, int bytes, int grid, cudaStream_t st) {
+  applyk3::bp_apply3_final<T><<<(int)std::min<int64_t>(2 * (a3.g1 - a3.g0), grid), applyk::NT, bytes, st>>>(a3);
+}
+template <typename T>
+static int apply_launch_v3(bpx_ctx* ctx, const applyk3::ApplyArgs3& a3, const int bytes[3], const int grid[3], int bond_ctas,
+                           cudaEvent_t* ev /* 4 events (debug timing) or NULL */) {
+  if (ev) cudaEventRecord(ev[0], ctx->stream);
+  apply_launch_sides<T>(a3, bytes[0], grid[0], ctx->stream);
+  if (ev) cudaEventRecord(ev[1], ctx->stream);
+  apply_launch_bond<T>(a3, bytes[1], grid[1], bond_ctas, ctx->stream);
   if (ev) cudaEventRecord(ev[2], ctx->stream);
-  applyk3::bp_apply3_final<T><<<(int)std::min<int64_t>(2 * ng, grid[2]), applyk::NT, bytes[2], ctx->stream>>>(a3);
+  apply_launch_final<T>(a3, bytes[2], grid[2], ctx->stream);
   if (ev) cudaEventRecord(ev[3], ctx->stream);
   ctx->n_launches += 3;
   BPX_CUDA(ctx, cudaGetLastError());
+  return BPX_OK;
+}
+// Long batches: the bond kernel (pure latency chains, no DRAM traffic) of chunk i runs BESIDE the side kernel (bound by the
+// memory system) of chunk i + 1 and the final kernel of chunk i - 1: half-sized chunks, the dense kernels with one CTA per SM
+// on the context's stream (S0 S1 F0 S2 F1 ..), the bond kernel with two CTAs per SM on a second stream (B0 B1 ..), events
+// S_i -> B_i -> F_i; two work-space buffers suffice (S_{i+2} follows F_i in stream order).
+template <typename T>
+static int apply_overlapped_v3(bpx_ctx* ctx, applyk3::ApplyArgs3 a3, const int bytes[3], int bond_ctas, int64_t ng, int64_t chunk,
+                               char* ws[2]) {
+  if (!ctx->apply_stream) BPX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->apply_stream, cudaStreamNonBlocking));
+  const int64_t nchunks = (ng + chunk - 1) / chunk;
+  std::vector<cudaEvent_t> ev((size_t)(2 * nchunks + 1));
+  for (auto& e : ev) BPX_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  const int gd = ctx->num_sms, gbond = 2 * ctx->num_sms;
+  BPX_CUDA(ctx, cudaEventRecord(ev[2 * nchunks], ctx->stream));  // uploads, the zeroed status
+  BPX_CUDA(ctx, cudaStreamWaitEvent(ctx->apply_stream, ev[2 * nchunks], 0));
+  auto args = [&](int64_t i) {
+    applyk3::ApplyArgs3 a = a3;
+    a.g0 = i * chunk;
+    a.g1 = std::min(ng, a.g0 + chunk);
+    a.base.ws = ws[i & 1];
+    return a;
+  };
+  auto sides = [&](int64_t i) {
+    apply_launch_sides<T>(args(i), bytes[0], gd, ctx->stream);
+    cudaEventRecord(ev[2 * i], ctx->stream);
+    cudaStreamWaitEvent(ctx->apply_stream, ev[2 * i], 0);
+    apply_launch_bond<T>(args(i), bytes[1], gbond, bond_ctas, ctx->apply_stream);
+    cudaEventRecord(ev[2 * i + 1], ctx->apply_stream);
+  };
+  auto fin = [&](int64_t i) {
+    cudaStreamWaitEvent(ctx->stream, ev[2 * i + 1], 0);
+    apply_launch_final<T>(args(i), bytes[2], gd, ctx->stream);
+  };
+  sides(0);
+  for (int64_t i = 1; i < nchunks; ++i) {
+    sides(i);
+    fin(i - 1);
+  }
+  fin(nchunks - 1);
+  ctx->n_launches += 3 * nchunks;
+  const cudaError_t ce = cudaGetLastError();
+  for (auto& e : ev) cudaEventDestroy(e);  // (released when the recorded work has completed)
+  BPX_CUDA(ctx, ce);
   return BPX_OK;
 }
 template <typename T>
@@ -1912,16 +1968,28 @@ static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates
   if ((rc = cplx ? apply_prepare_v3<c64>(ctx, bytes, bond_ctas, per_sm) : apply_prepare_v3<double>(ctx, bytes, bond_ctas, per_sm))) return rc;
   if (per_sm[0] < 1 || per_sm[1] < 1 || per_sm[2] < 1) return BPX_OK;
   int grid[3] = {ctx->num_sms * per_sm[0], ctx->num_sms * per_sm[1], ctx->num_sms * per_sm[2]};
-  if (const char* e = getenv("BPX_APPLY_SIDES_GRID")) grid[0] = std::max(1, std::min(grid[0], atoi(e)));  // experiment: fewer CTAs in flight
+  // experiments: fewer CTAs in flight (is a kernel bound by latency or by a shared resource?)
+  if (const char* e = getenv("BPX_APPLY_SIDES_GRID")) grid[0] = std::max(1, std::min(grid[0], atoi(e)));
+  if (const char* e = getenv("BPX_APPLY_BOND_GRID")) grid[1] = std::max(1, std::min(grid[1], atoi(e)));
+  if (const char* e = getenv("BPX_APPLY_FINAL_GRID")) grid[2] = std::max(1, std::min(grid[2], atoi(e)));
   // chunks: as many gates as fit the work-space budget, in whole waves of the side kernel when there are several chunks
   int64_t budget = (int64_t)3 << 29;  // 1.5 GiB: stays in the context's cached arena
   if (const char* e = getenv("BPX_APPLY_WS_BYTES")) budget = std::max<int64_t>(1, atoll(e));  // tests: force several chunks
   int64_t chunk = std::max<int64_t>(1, budget / (ws_stride * ctx->esize));
   if (chunk < ng && chunk > grid[0] / 2) chunk -= chunk % (grid[0] / 2);
   chunk = std::min(chunk, ng);
+  const bool timing = getenv("BPX_APPLY_TIMING") != nullptr;  // debug: per-phase clock64 stamps, summary on stderr
+  // OPT-IN (BPX_APPLY_OVERLAP=1), more than one chunk: the bond kernel beside the dense kernels of the neighbouring chunks
+  // (apply_overlapped_v3).  Measured 7 - 16 % SLOWER than the kernels one after the other (profiles/r2bb_overlap.log).
+  bool overlap = false;
+  if (const char* e = getenv("BPX_APPLY_OVERLAP")) overlap = atoi(e) != 0 && chunk < ng && !timing && chunk >= 2;
+  if (overlap) {
+    chunk = chunk / 2;
+    if (chunk > ctx->num_sms) chunk -= chunk % ctx->num_sms;  // whole waves of the one-CTA-per-SM side kernel (2 items per gate)
+  }
   char *d_ws = nullptr, *d_tt = nullptr;
   int32_t* d_status = nullptr;
-  if ((rc = ws_get(ctx, bpx_ctx::WS_WORK, (size_t)chunk * ws_stride * ctx->esize, &d_ws))) return rc;
+  if ((rc = ws_get(ctx, bpx_ctx::WS_WORK, (size_t)chunk * (overlap ? 2 : 1) * ws_stride * ctx->esize, &d_ws))) return rc;
   if ((rc = ws_get(ctx, bpx_ctx::WS_SCRATCH, (size_t)std::min<int64_t>(2 * chunk, grid[0]) * tt_stride * ctx->esize, &d_tt))) return rc;
   if ((rc = ws_get(ctx, bpx_ctx::WS_LIST, (size_t)ng * sizeof(int32_t), &d_status))) return rc;
   BPX_CUDA(ctx, cudaMemsetAsync(d_status, 0, (size_t)ng * sizeof(int32_t), ctx->stream));
@@ -1942,14 +2010,19 @@ static int apply_run_v3(bpx_ctx* ctx, const std::vector<applyk::GateDesc>& gates
   a3.stamps = nullptr;
   constexpr int SS = applyk3::STAMP_SLOTS;
   long long* d_stamps = nullptr;
-  const bool timing = getenv("BPX_APPLY_TIMING") != nullptr;  // debug: per-phase clock64 stamps, summary on stderr
   if (timing) {
     if ((rc = ws_get(ctx, bpx_ctx::WS_OUT, (size_t)ng * SS * sizeof(long long), &d_stamps))) return rc;
     BPX_CUDA(ctx, cudaMemsetAsync(d_stamps, 0, (size_t)ng * SS * sizeof(long long), ctx->stream));
     a3.stamps = d_stamps;
   }
   std::vector<cudaEvent_t> evs;
-  for (int64_t g0 = 0; g0 < ng; g0 += chunk) {
+  if (overlap) {
+    char* ws2[2] = {d_ws, d_ws + (size_t)chunk * ws_stride * ctx->esize};
+    if ((rc = cplx ? apply_overlapped_v3<c64>(ctx, a3, bytes, bond_ctas, ng, chunk, ws2)
+                   : apply_overlapped_v3<double>(ctx, a3, bytes, bond_ctas, ng, chunk, ws2)))
+      return rc;
+  }
+  for (int64_t g0 = 0; g0 < ng && !overlap; g0 += chunk) {
     a3.g0 = g0;
     a3.g1 = std::min(ng, g0 + chunk);
     cudaEvent_t* ev = nullptr;

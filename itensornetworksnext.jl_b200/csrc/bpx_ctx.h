@@ -132,6 +132,7 @@ struct bpx_ctx {
 
   // streamed host I/O (bpx_sweep_host with pinned buffers)
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t apply_stream = nullptr;  // second stream of the gate kernels (bond kernel of chunk i beside the side kernel of chunk i + 1)
   cudaEvent_t ev_io_start = nullptr, ev_io_done = nullptr;
   long long* d_io_progress = nullptr;
   long long* h_io_progress = nullptr;  // pinned: cumulative element counts, one per chunk; [32] residual key, [33] error flag
