@@ -120,6 +120,9 @@ int bpx_set_site_tensors(bpx_ctx* ctx, const void* packed);
 int bpx_set_site_tensor(bpx_ctx* ctx, int64_t v, const void* data);
 /* The iterate: `MessageCache(messages)` (beliefpropagation.jl:76, messagecache.jl:33-49). */
 int bpx_set_messages(bpx_ctx* ctx, const void* packed);
+/* (On connected ranks of a partitioned run -- bpx_halo_connect -- bpx_set_messages and bpx_fill_synthetic are COLLECTIVE: they
+ * end with a cross-rank barrier, so that no rank starts sweeping into this rank's halo slots before every rank has
+ * rewritten its message sets.) */
 int bpx_get_messages(bpx_ctx* ctx, void* packed);
 int bpx_get_message(bpx_ctx* ctx, int64_t e, void* data);
 

@@ -650,6 +650,17 @@ extern "C" int bpx_set_site_tensor(bpx_ctx* ctx, int64_t v, const void* data) {
   return BPX_OK;
 }
 
+// Connected ranks of a partitioned run store halo messages straight into each other's message sets during a sweep.  A call
+// that REWRITES this rank's sets (bpx_set_messages, bpx_fill_synthetic) is therefore collective: it ends with a cross-rank
+// barrier on the stream, so that no rank starts sweeping -- and storing into this rank's halo slots -- before every rank
+// has finished rewriting (seen on two B200s with a cold second rank: the late rank's upload overwrote the first halo
+// messages of the early one, a wrong third sweep).  One process driving several devices (bpx_create_multi) serialises
+// these calls on the host and needs no barrier.
+static int collective_fence(bpx_ctx* ctx) {
+  if (ctx->nranks > 1 && ctx->halo_connected && !ctx->is_child) return bpx_peer_barrier(ctx);
+  return BPX_OK;
+}
+
 extern "C" int bpx_set_messages(bpx_ctx* ctx, const void* packed) {
   PAD(ctx, bpx::pad::set_messages(ctx, packed));
   MULTI(ctx, bpx::multi::each(ctx, [&](bpx_ctx* c) -> int { return bpx_set_messages(c, packed); }));
@@ -662,6 +673,8 @@ extern "C" int bpx_set_messages(bpx_ctx* ctx, const void* packed) {
   // ping-pong (a single rank rewrites every message each sweep, and the sequential path re-syncs the sets itself)
   if (ctx->nranks > 1)
     BPX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg[ctx->cur ^ 1], ctx->d_msg[ctx->cur], n, cudaMemcpyDeviceToDevice, ctx->stream));
+  const int rc = collective_fence(ctx);
+  if (rc) return rc;
   BPX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return BPX_OK;
 }
@@ -2444,6 +2457,7 @@ extern "C" int bpx_fill_synthetic(bpx_ctx* ctx, uint64_t seed) {
     cudaError_t ce = cudaGetLastError();
     if (ce == cudaSuccess)
       ce = cudaMemcpyAsync(ctx->d_msg[1], ctx->d_msg[0], (size_t)ctx->msg_off[ctx->ne] * ctx->esize, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (ce == cudaSuccess && collective_fence(ctx) != BPX_OK) ce = cudaErrorUnknown;
     cudaError_t ce2 = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_chi);
     BPX_CUDA(ctx, ce);
