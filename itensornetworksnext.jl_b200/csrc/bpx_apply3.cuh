@@ -156,7 +156,7 @@ __host__ __device__ inline SmemNeed3 smem_need3(const GateDesc& g, bool cplx) {
     const int64_t absorb = cb * (s.rows + s.rows / dim0) + 2 + hsum;  // padded column batch + the messages
     const int64_t gram = 2 * (int64_t)TRG * PCP;               // A tile, T tile (the reduction re-uses them)
     const int64_t trf = cplx ? 128 : 256;
-    const int64_t f = trf * PCP + (int64_t)PC * PC;            // A tile, W
+    const int64_t f = trf * PCP + (int64_t)PC * (PC + 4);      // A tile(s), W (padded rows in the tensor-pipe version)
     sides = sides > absorb ? sides : absorb;
     sides = sides > gram ? sides : gram;
     fin = fin > f ? fin : f;
@@ -1118,6 +1118,111 @@ __host__ __device__ __forceinline__ void final_side(const Team tm, const Side& s
   }
 }
 
+#ifdef __CUDACC__
+// ---- final pass on the FP64 tensor pipe (Float64, device only) -------------------------------------------------------------
+// A'[rows of the tile, :] = at_tile (128 x 32) W (32 x 32) as DMMA.8x8x4: a warp owns 16 rows (two M blocks), walks K = c in 8
+// steps and N = c' in two halves of two blocks; the tiles arrive by TMA bulk copies like in gram_side_mma (two stages of
+// 128 rows); W sits in shared memory with a leading dimension of PC + 4 (conflict-free B fragments).  A lane's accumulator
+// pair is (c' = 2 t, 2 t + 1) of one row: the two physical components of one bond index, contiguous in the canonical tensor
+// when d is even -- one 16-byte store.
+constexpr int PCW = PC + 4;
+__device__ __forceinline__ void final_side_mma(const Team tm, const Side& sd, const Tabs tb, const double* at, double* a, const double* W,
+                                               double* smem, GramPipe& gp) {
+  constexpr int TR = 128;
+  double* sW = smem + (int64_t)2 * TR * PCP;  // [c][PCW]
+  const int cols = sd.cols;
+  const int64_t rows_all = sd.rows;
+  const int ntile = (int)((rows_all + TR - 1) / TR);
+  const int g = tm.lane >> 2, t = tm.lane & 3;
+  const int32_t* __restrict__ rowt = tb.row;
+  const int32_t* __restrict__ colt = tb.col;
+  auto issue = [&](int i) {
+    const int s = i & 1;
+    const int64_t row0 = (int64_t)i * TR;
+    const uint32_t bytes = (uint32_t)(scratch_elems((rows_all - row0) < TR ? (rows_all - row0) : TR) * sizeof(double));
+    const uint32_t bar = smem_u32_3(gp.bar + s), dst = smem_u32_3(smem + (int64_t)s * TR * PCP);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(at + sidx<double>(row0, 0)), "r"(bytes), "r"(bar)
+                 : "memory");
+  };
+  tm.sync();
+  if (tm.tid() == 0) {
+    asm volatile("fence.proxy.async;\n" ::: "memory");
+    issue(0);
+    if (ntile > 1) issue(1);
+  }
+  for (int i = tm.tid(); i < PC * PC; i += tm.nt()) sW[(i / PC) * PCW + (i % PC)] = W[i];
+  tm.sync();
+  // the pair (c', c' + 1), c' even, is one 16-byte piece of the canonical tensor?
+  const bool pair16 = (sd.d % 2 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
+  for (int i = 0; i < ntile; ++i) {
+    const int s = i & 1;
+    const int64_t row0 = (int64_t)i * TR;
+    const int nr = (int)((rows_all - row0) < TR ? (rows_all - row0) : TR);
+    {
+      const uint32_t bar = smem_u32_3(gp.bar + s), parity = gp.used[s] & 1;
+      uint32_t ok;
+      do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+      } while (!ok);
+      gp.used[s]++;
+    }
+    const double* sA = smem + (int64_t)s * TR * PCP;
+    const int rb = 16 * tm.wid;  // this warp's rows of the tile (8 warps x 16 rows)
+    if (rb < nr) {
+      const bool ok0 = rb + g < nr, ok1 = rb + 8 + g < nr;
+      const int64_t o0 = sidx<double>(rb + g, t), o1 = sidx<double>(rb + 8 + g, t);  // (column 4 ks + t: + 8 ks)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        double acc[2][2][2];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          // (columns >= cols of the scratch copy are not initialised: W's rows there are zero, so mask them)
+          const bool kin = 4 * ks + t < cols;
+          const double fa0 = (ok0 && kin) ? sA[o0 + 8 * ks] : 0.0, fa1 = (ok1 && kin) ? sA[o1 + 8 * ks] : 0.0;
+          const double fb0 = sW[(4 * ks + t) * PCW + 16 * half + g], fb1 = sW[(4 * ks + t) * PCW + 16 * half + 8 + g];
+          dmma884(acc[0][0][0], acc[0][0][1], fa0, fb0);
+          dmma884(acc[0][1][0], acc[0][1][1], fa0, fb1);
+          dmma884(acc[1][0][0], acc[1][0][1], fa1, fb0);
+          dmma884(acc[1][1][0], acc[1][1][1], fa1, fb1);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          const int r = rb + 8 * mb + g;
+          if (r >= nr) continue;
+          const int64_t ra = rowt[row0 + r];
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+            const int cp = 16 * half + 8 * nb + 2 * t;
+            if (cp + 1 < cols && pair16 && colt[cp + 1] == colt[cp] + 1) {
+              *reinterpret_cast<double2*>(a + ra + colt[cp]) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+            } else {
+              if (cp < cols) a[ra + colt[cp]] = acc[mb][nb][0];
+              if (cp + 1 < cols) a[ra + colt[cp + 1]] = acc[mb][nb][1];
+            }
+          }
+        }
+      }
+    }
+    tm.sync();  // every warp is done with stage s
+    if (tm.tid() == 0 && i + 2 < ntile) issue(i + 2);
+  }
+}
+#endif
+
 // ---- one two-site gate -----------------------------------------------------------------------------------------------------------
 // Everything the phases of one gate share; in shared memory on the device.  The gate runs as THREE kernels (bottom of this
 // file): bp_apply3_sides -- one CTA per (gate, side): tables, message check, absorb, Gram product; bp_apply3_bond -- one
@@ -1360,13 +1465,22 @@ __host__ __device__ __forceinline__ void phase_bond_post(const Team tm, Gate3<T>
 
 // A'_a = A_a W_a in place
 template <typename T>
-__host__ __device__ __forceinline__ void phase_final_side(const Team tm, Gate3<T>& c, int a) {
+__host__ __device__ __forceinline__ void phase_final_side(const Team tm, Gate3<T>& c, int a, void* pipe = nullptr) {
   constexpr bool CPLX = Elem<T>::is_complex;
   const Side& sd = c.gd->s[a];
   const Layout3& L = c.L;
   T* w = c.w;
   T* smem = phase_smem<T>(c.smem);
   T* A = c.sites + sd.site_off;
+#ifdef __CUDA_ARCH__
+  if constexpr (!CPLX) {
+    if (pipe) {
+      final_side_mma(tm, sd, c.tb[a], w + L.at[a], A, w + L.w[a], smem, *static_cast<GramPipe*>(pipe));
+      return;
+    }
+  }
+#endif
+  (void)pipe;
   if (CPLX)
     final_side<T, 128, 1, 8>(tm, sd, c.tb[a], w + L.at[a], A, w + L.w[a], smem);
   else
@@ -1547,6 +1661,9 @@ __global__ void __launch_bounds__(NT, 2) bp_apply3_final(ApplyArgs3 a3) {
   tm.lane = threadIdx.x & 31;
   tm.wid = threadIdx.x >> 5;
   tm.nw = NT / 32;
+  __shared__ uint64_t tile_bar[2];
+  GramPipe gp;
+  gram_pipe_init(gp, tile_bar);
   const int64_t nitems = 2 * (a3.g1 - a3.g0);
   for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
     const int64_t g = a3.g0 + (it >> 1);
@@ -1561,7 +1678,7 @@ __global__ void __launch_bounds__(NT, 2) bp_apply3_final(ApplyArgs3 a3) {
     }
     __syncthreads();
     BPX_STAMP(24 + 2 * a);
-    phase_final_side<T>(tm, c, a);
+    phase_final_side<T>(tm, c, a, &gp);
     if (a == 0) phase_final_bond<T>(tm, c);
     BPX_STAMP(25 + 2 * a);
   }
