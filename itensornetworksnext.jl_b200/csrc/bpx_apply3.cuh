@@ -41,20 +41,31 @@ constexpr double COND_MIN = 1e-10;   // smallest kept eigenvalue of G relative t
 constexpr double PIVOT_MIN = 1e-12;  // smallest Cholesky pivot of a message relative to its largest diagonal entry
 constexpr int MAXDIM = 16;           // largest external link dimension (a fibre lives in registers)
 
-// Layout of the scratch copies `at` / `tt` (the matrix view, rows x PCP): two rows and one column group (the CG columns an
-// absorb batch produces: 2 Float64, 1 ComplexF64) are 32 contiguous bytes, so that the batch's stores fill whole DRAM sectors
-// -- with plain row-major rows every store was half a sector, the L2 did not keep the lines until the other half arrived
-// (write hit rate 8 %), and every half went to DRAM as a read-modify-write: 11.2 MB of traffic per tensor instead of 5.4
-// (ncu, profiles/r2av_apply3_sides_ncu_summary.csv).  Row ranges starting at an even row stay contiguous (tiles by bulk copy).
+// Layout of the scratch copies `at` / `tt` (the matrix view, rows x cols): COLUMN-GROUP major.  A group is what an absorb
+// batch produces -- 2 columns Float64, 1 column ComplexF64: 16 bytes per row -- and the copy is an array of 16-byte vectors
+// V[group][row].  A batch's stores are then one contiguous stream (256 bytes per warp instruction), a tile of rows is one
+// contiguous piece per group (bulk copies), and in shared memory the groups of a tile are `tile_stride16` vectors apart
+// (TR + 4: the DMMA fragment loads of the Gram and final passes are conflict free).
+// History (ncu, profiles/r2av_* / r2bg_*): plain row-major rows made every batch store half a 32-byte sector, the L2 did not
+// keep the lines until the other half arrived (write hit rate 8 %) and every half went to DRAM as a read-modify-write:
+// 11.2 MB of traffic per tensor instead of 5.4, the side kernel bound by it; pairing two rows per sector fixed the traffic
+// (side kernel 2 x faster) but left 32-byte pieces 544 bytes apart.
 template <typename T>
-__host__ __device__ __forceinline__ int64_t sidx(int64_t r, int c) {
-  constexpr int CG = Elem<T>::is_complex ? 1 : 2;
-  return (r >> 1) * (2 * PCP) + (c / CG) * (2 * CG) + (r & 1) * CG + (c % CG);
+__host__ __device__ __forceinline__ int64_t gidx(int64_t r, int c, int64_t rows_e) {  // element (r, c) of a scratch copy
+  if (Elem<T>::is_complex) return (int64_t)c * rows_e + r;
+  return (((int64_t)(c >> 1) * rows_e + r) << 1) + (c & 1);
 }
-__host__ __device__ __forceinline__ int64_t scratch_elems(int64_t rows) { return ((rows + 1) & ~(int64_t)1) * PCP; }
+__host__ __device__ __forceinline__ int tile_stride16(bool cplx, int tr) { return cplx ? tr + 1 : tr + 4; }
+template <typename T>
+__host__ __device__ __forceinline__ int tidx(int r, int c, int tr) {  // element (r, c) of a tile of tr rows in shared memory
+  if (Elem<T>::is_complex) return c * (tr + 1) + r;
+  return (((c >> 1) * (tr + 4) + r) << 1) + (c & 1);
+}
+__host__ __device__ __forceinline__ int64_t rows_even(int64_t rows) { return (rows + 1) & ~(int64_t)1; }
+__host__ __device__ __forceinline__ int64_t scratch_elems(int64_t rows) { return rows_even(rows) * PCP; }
 
 struct Layout3 {
-  int64_t at[2];        // per side: the matrix view of A, rows x PCP in the sidx() layout (tiles of rows are contiguous)
+  int64_t at[2];        // per side: the matrix view of A, column-group major (gidx())
   int64_t tt;           // T = (M_1 x M_2 x ..) A in the same layout; shared by the two sides
   int64_t h[2];         // Hermitian parts of the boundary messages, slot order, chi^2 each
   int64_t g[2];         // G (cols x cols) and its rotated copy
@@ -266,6 +277,44 @@ __host__ __device__ __forceinline__ void copy_tile(const Team tm, T* dst, const 
   tm.sync();
 }
 
+// rows [row0, row0 + nr) of a scratch copy -> a tile of tr rows in shared memory, one contiguous piece per column group
+template <typename T>
+__host__ __device__ __forceinline__ void copy_tile_groups(const Team tm, T* dst, const T* src, int64_t row0, int nr, int64_t rows_e, int cols,
+                                                          int tr) {
+  constexpr bool CPLX = Elem<T>::is_complex;
+  const int ncg = CPLX ? cols : (cols + 1) / 2, ts = tile_stride16(CPLX, tr);
+#ifdef __CUDA_ARCH__
+  const double2* __restrict__ s2 = reinterpret_cast<const double2*>(src);
+  double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
+  const int total = ncg * nr, nt = tm.nt(), tid = tm.tid();
+  constexpr int U = 4;
+  const int nfull = total / (U * nt) * (U * nt);
+  for (int i0 = tid; i0 < nfull; i0 += U * nt) {  // no predicates: the staging registers stay registers
+    double2 v[U];
+    int o[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * nt, j = i / nr, k = i - j * nr;
+      v[u] = s2[(int64_t)j * rows_e + row0 + k];
+      o[u] = j * ts + k;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) d2[o[u]] = v[u];
+  }
+  for (int i = nfull + tid; i < total; i += nt) {
+    const int j = i / nr, k = i - j * nr;
+    d2[j * ts + k] = s2[(int64_t)j * rows_e + row0 + k];
+  }
+#else
+  constexpr int CG = CPLX ? 1 : 2;
+  for (int64_t i = tm.tid(); i < (int64_t)ncg * nr * CG; i += tm.nt()) {
+    const int j = (int)(i / (nr * CG)), k = (int)(i % (nr * CG));
+    dst[(int64_t)j * ts * CG + k] = src[((int64_t)j * rows_e + row0) * CG + k];
+  }
+#endif
+  tm.sync();
+}
+
 // ---- messages: Hermitian part + positive-definiteness check ---------------------------------------------------------------
 // One warp per message: right-looking Cholesky on a scratch copy; *bad is set when a pivot is not safely positive.
 template <typename T>
@@ -440,6 +489,7 @@ __host__ __device__ __forceinline__ void absorb_side(const Team tm, const Side& 
 #define BPX_ASTAMP(i) do { (void)stamps; } while (0)
 #endif
   const int rows = (int)sd.rows, ncols = sd.cols;
+  const int64_t rows_e = rows_even(sd.rows);
   const int32_t* __restrict__ rowt = tb.row;
   const int32_t* __restrict__ colt = tb.col;
   const int pad0 = wk.next > 0 ? wk.rdim[0] : 1;
@@ -472,14 +522,14 @@ __host__ __device__ __forceinline__ void absorb_side(const Team tm, const Side& 
       for (int u = 0; u < U; ++u) {
         const int i = i0 + u * nt, b = i % CB, r = i / CB;
         col[b * prow + r + dpad.div(r)] = v[u];
-        aout[sidx<T>(r, c0 + b)] = v[u];  // the matrix view: the Gram and final passes read plain tiles
+        aout[gidx<T>(r, c0 + b, rows_e)] = v[u];  // the matrix view: the Gram and final passes read plain tiles
       }
     }
     for (int i = nfull + tid; i < total; i += nt) {
       const int b = i % CB, r = i / CB;
       const T v = a[rowt[r] + cofs[b]];
       col[b * prow + r + dpad.div(r)] = v;
-      aout[sidx<T>(r, c0 + b)] = v;
+      aout[gidx<T>(r, c0 + b, rows_e)] = v;
     }
     tm.sync();
     BPX_ASTAMP(1);
@@ -494,7 +544,7 @@ __host__ __device__ __forceinline__ void absorb_side(const Team tm, const Side& 
     }
     for (int i = tm.tid(); i < total; i += nt) {
       const int b = i % CB, r = i / CB;
-      tout[sidx<T>(r, c0 + b)] = col[b * prow + r + dpad.div(r)];
+      tout[gidx<T>(r, c0 + b, rows_e)] = col[b * prow + r + dpad.div(r)];
     }
     tm.sync();
     BPX_ASTAMP(7);
@@ -528,8 +578,8 @@ __host__ __device__ __forceinline__ void gram_side(const Team tm, const Side& sd
 #endif
     for (int64_t row0 = 0; row0 < rows_all; row0 += TRG) {
       const int nr = (int)((rows_all - row0) < TRG ? (rows_all - row0) : TRG);
-      copy_tile<T>(tm, sA, at + sidx<T>(row0, 0), scratch_elems(nr));
-      copy_tile<T>(tm, sT, tt + sidx<T>(row0, 0), scratch_elems(nr));
+      copy_tile_groups<T>(tm, sA, at, row0, nr, rows_even(rows_all), cols, TRG);
+      copy_tile_groups<T>(tm, sT, tt, row0, nr, rows_even(rows_all), cols, TRG);
 #ifdef __CUDA_ARCH__
       const int li = tm.lane >> 2, lj = tm.lane & 3;
       for (int r = tm.wid; r < nr; r += tm.nw) {
@@ -537,25 +587,25 @@ __host__ __device__ __forceinline__ void gram_side(const Team tm, const Side& sd
         if constexpr (!E::is_complex) {  // column pairs (c even, c + 1) are 16 contiguous, aligned bytes
 #pragma unroll
           for (int x = 0; x < 2; ++x) {
-            const double2 q = *reinterpret_cast<const double2*>(sA + sidx<T>(r, 4 * li + 2 * x));
+            const double2 q = *reinterpret_cast<const double2*>(sA + tidx<T>(r, 4 * li + 2 * x, TRG));
             av[2 * x] = q.x;
             av[2 * x + 1] = q.y;
           }
 #pragma unroll
           for (int y = 0; y < TJ / 2; ++y) {
-            const double2 q = *reinterpret_cast<const double2*>(sT + sidx<T>(r, TJ * (lj + 4 * pass) + 2 * y));
+            const double2 q = *reinterpret_cast<const double2*>(sT + tidx<T>(r, TJ * (lj + 4 * pass) + 2 * y, TRG));
             tv[2 * y] = q.x;
             tv[2 * y + 1] = q.y;
           }
         } else {
 #pragma unroll
           for (int x = 0; x < 4; ++x) {
-            const double2 q = *reinterpret_cast<const double2*>(sA + sidx<T>(r, 4 * li + x));
+            const double2 q = *reinterpret_cast<const double2*>(sA + tidx<T>(r, 4 * li + x, TRG));
             av[x] = E::conj(*reinterpret_cast<const T*>(&q));
           }
 #pragma unroll
           for (int y = 0; y < TJ; ++y) {
-            const double2 q = *reinterpret_cast<const double2*>(sT + sidx<T>(r, TJ * (lj + 4 * pass) + y));
+            const double2 q = *reinterpret_cast<const double2*>(sT + tidx<T>(r, TJ * (lj + 4 * pass) + y, TRG));
             tv[y] = *reinterpret_cast<const T*>(&q);
           }
         }
@@ -571,7 +621,7 @@ __host__ __device__ __forceinline__ void gram_side(const Team tm, const Side& sd
           for (int x = 0; x < 4; ++x)
             for (int y = 0; y < TJ; ++y) {
               T& o = hacc[(size_t)(role * 4 + x) * TJ + y];
-              o = E::fma(E::conj(sA[sidx<T>(r, 4 * li + x)]), sT[sidx<T>(r, TJ * (lj + 4 * pass) + y)], o);
+              o = E::fma(E::conj(sA[tidx<T>(r, 4 * li + x, TRG)]), sT[tidx<T>(r, TJ * (lj + 4 * pass) + y, TRG)], o);
             }
       }
       (void)L;
@@ -642,22 +692,27 @@ __device__ __forceinline__ void gram_side_mma(const Team tm, const Side& sd, con
   const int64_t rows_all = sd.rows;
   const int ntile = (int)((rows_all + TR - 1) / TR);
   const int g = tm.lane >> 2, t = tm.lane & 3;
-  auto issue = [&](int i) {  // thread 0: both tiles of row block i into stage i & 1
+  const int ncg = (cols + 1) / 2;                 // column groups (16-byte vectors per row)
+  const int64_t rows_e = rows_even(rows_all);
+  constexpr int TS16 = TR + 4;                    // tile_stride16(false, TR)
+  auto issue = [&](int i) {  // warp 0: both tiles of row block i into stage i & 1, one bulk copy per lane (group, A | T)
     const int s = i & 1;
     const int64_t row0 = (int64_t)i * TR;
-    const uint32_t bytes = (uint32_t)(scratch_elems((rows_all - row0) < TR ? (rows_all - row0) : TR) * sizeof(double));
+    const uint32_t nr = (uint32_t)((rows_all - row0) < TR ? (rows_all - row0) : TR);
     const uint32_t bar = smem_u32_3(gp.bar + s), dst = smem_u32_3(smem + (int64_t)s * 2 * TR * PCP);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2 * bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
-                 "l"(at + sidx<double>(row0, 0)), "r"(bytes), "r"(bar)
-                 : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     dst + (uint32_t)(TR * PCP * sizeof(double))),
-                 "l"(tt + sidx<double>(row0, 0)), "r"(bytes), "r"(bar)
-                 : "memory");
+    if (tm.lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2 * ncg * nr * 16) : "memory");
+    __syncwarp();
+    const int j = tm.lane & 15;
+    if (j < ncg) {
+      const double* src = ((tm.lane < 16) ? at : tt) + (((int64_t)j * rows_e + row0) << 1);
+      const uint32_t d = dst + (uint32_t)((tm.lane < 16 ? 0 : TR * PCP) * sizeof(double)) + (uint32_t)(j * TS16 * 16);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d), "l"(src),
+                   "r"(nr * 16), "r"(bar)
+                   : "memory");
+    }
   };
   tm.sync();  // (the scratch copies were written by this CTA's ordinary stores: visible after the barrier; shared memory is free)
-  if (tm.tid() == 0) {
+  if (tm.wid == 0) {
     asm volatile("fence.proxy.async;\n" ::: "memory");  // generic-proxy writes (global and shared) before the async-proxy copies
     issue(0);
     if (ntile > 1) issue(1);
@@ -691,12 +746,12 @@ __device__ __forceinline__ void gram_side_mma(const Team tm, const Side& sd, con
     // (columns >= cols of the tiles are uninitialised: their products land in rows / columns of G that are never read)
     for (int r0 = 4 * tm.wid; r0 < nr; r0 += 4 * tm.nw) {
       const bool ok = r0 + t < nr;
-      const int64_t o = sidx<double>(r0 + t, g);  // (column 8 b + g: + 16 b)
+      const int o = tidx<double>(r0 + t, g, TR);  // (column 8 b + g: 4 b groups further)
       double fa[4], fb[4];
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        fa[b] = ok ? sA[o + 16 * b] : 0.0;
-        fb[b] = ok ? sT[o + 16 * b] : 0.0;
+        fa[b] = ok ? sA[o + 8 * b * TS16] : 0.0;
+        fb[b] = ok ? sT[o + 8 * b * TS16] : 0.0;
       }
 #pragma unroll
       for (int mb = 0; mb < 4; ++mb)
@@ -704,7 +759,7 @@ __device__ __forceinline__ void gram_side_mma(const Team tm, const Side& sd, con
         for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], fa[mb], fb[nb]);
     }
     tm.sync();  // every warp is done with stage s
-    if (tm.tid() == 0 && i + 2 < ntile) issue(i + 2);
+    if (tm.wid == 0 && i + 2 < ntile) issue(i + 2);
   }
   double* red = smem;  // red[w][c'][c]
 #pragma unroll
@@ -1025,13 +1080,13 @@ __host__ __device__ __forceinline__ void gram_factor_finish(const Team tm, int c
 }
 
 // ---- final pass: A'[row, c'] = sum_c A[row, c] W[c, c'], A from its row-major scratch copy, A' into the canonical tensor ----
-// Tiles of TRF rows in shared memory (plain contiguous copies, sidx() layout).  A thread owns RT rows x NO outputs: per
+// Tiles of TRF rows in shared memory (tidx() layout).  A thread owns RT rows x NO outputs: per
 // column pair RT 16-byte operand loads (rows 272 bytes apart: conflict free) and NO 16-byte broadcast loads of W feed 2 RT NO
 // FMAs.
 template <typename T, int TRF, int RT, int NO>
 __host__ __device__ __forceinline__ void final_side(const Team tm, const Side& sd, const Tabs tb, const T* at, T* a, const T* W, T* smem) {
   using E = Elem<T>;
-  T* sA = smem;                                  // sidx(r, c)
+  T* sA = smem;                                  // tidx(r, c, TRF)
   T* sW = smem + (int64_t)TRF * PCP;             // [c][PC]
   for (int i = tm.tid(); i < PC * PC; i += tm.nt()) sW[i] = W[i];
   const int cols = sd.cols;
@@ -1042,7 +1097,7 @@ __host__ __device__ __forceinline__ void final_side(const Team tm, const Side& s
   constexpr int OG = PC / NO;                    // output groups
   for (int64_t row0 = 0; row0 < rows_all; row0 += TRF) {
     const int nr = (int)((rows_all - row0) < TRF ? (rows_all - row0) : TRF);
-    copy_tile<T>(tm, sA, at + sidx<T>(row0, 0), scratch_elems(nr));
+    copy_tile_groups<T>(tm, sA, at, row0, nr, rows_even(rows_all), cols, TRF);
     for (int item = tm.tid(); item < RG * OG; item += tm.nt()) {
       const int rg = item % RG, og = item / RG;
       if (og * NO >= cols) continue;
@@ -1056,8 +1111,8 @@ __host__ __device__ __forceinline__ void final_side(const Team tm, const Side& s
         T a0[RT], a1[RT];
 #pragma unroll
         for (int x = 0; x < RT; ++x) {
-          const T* pa = sA + sidx<T>(rg + x * RG, c);  // (c is even)
-          const T* pb = sA + sidx<T>(rg + x * RG, c + 1);
+          const T* pa = sA + tidx<T>(rg + x * RG, c, TRF);  // (c is even)
+          const T* pb = sA + tidx<T>(rg + x * RG, c + 1, TRF);
 #ifdef __CUDA_ARCH__
           if constexpr (!E::is_complex) {
             const double2 q = *reinterpret_cast<const double2*>(pa);  // the pair (c, c + 1): 16 contiguous, aligned bytes
@@ -1136,18 +1191,24 @@ __device__ __forceinline__ void final_side_mma(const Team tm, const Side& sd, co
   const int g = tm.lane >> 2, t = tm.lane & 3;
   const int32_t* __restrict__ rowt = tb.row;
   const int32_t* __restrict__ colt = tb.col;
-  auto issue = [&](int i) {
+  const int ncg = (cols + 1) / 2;
+  const int64_t rows_e = rows_even(rows_all);
+  constexpr int TS16 = TR + 4;
+  auto issue = [&](int i) {  // warp 0: row block i into stage i & 1, one bulk copy per lane (column group)
     const int s = i & 1;
     const int64_t row0 = (int64_t)i * TR;
-    const uint32_t bytes = (uint32_t)(scratch_elems((rows_all - row0) < TR ? (rows_all - row0) : TR) * sizeof(double));
+    const uint32_t nr = (uint32_t)((rows_all - row0) < TR ? (rows_all - row0) : TR);
     const uint32_t bar = smem_u32_3(gp.bar + s), dst = smem_u32_3(smem + (int64_t)s * TR * PCP);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
-                 "l"(at + sidx<double>(row0, 0)), "r"(bytes), "r"(bar)
-                 : "memory");
+    if (tm.lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(ncg * nr * 16) : "memory");
+    __syncwarp();
+    if (tm.lane < ncg)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                       dst + (uint32_t)(tm.lane * TS16 * 16)),
+                   "l"(at + (((int64_t)tm.lane * rows_e + row0) << 1)), "r"(nr * 16), "r"(bar)
+                   : "memory");
   };
   tm.sync();
-  if (tm.tid() == 0) {
+  if (tm.wid == 0) {
     asm volatile("fence.proxy.async;\n" ::: "memory");
     issue(0);
     if (ntile > 1) issue(1);
@@ -1180,7 +1241,7 @@ __device__ __forceinline__ void final_side_mma(const Team tm, const Side& sd, co
     const int rb = 16 * tm.wid;  // this warp's rows of the tile (8 warps x 16 rows)
     if (rb < nr) {
       const bool ok0 = rb + g < nr, ok1 = rb + 8 + g < nr;
-      const int64_t o0 = sidx<double>(rb + g, t), o1 = sidx<double>(rb + 8 + g, t);  // (column 4 ks + t: + 8 ks)
+      const int o0 = tidx<double>(rb + g, t, TR), o1 = tidx<double>(rb + 8 + g, t, TR);  // (column 4 ks + t: 2 ks groups further)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         double acc[2][2][2];
@@ -1192,7 +1253,7 @@ __device__ __forceinline__ void final_side_mma(const Team tm, const Side& sd, co
         for (int ks = 0; ks < 8; ++ks) {
           // (columns >= cols of the scratch copy are not initialised: W's rows there are zero, so mask them)
           const bool kin = 4 * ks + t < cols;
-          const double fa0 = (ok0 && kin) ? sA[o0 + 8 * ks] : 0.0, fa1 = (ok1 && kin) ? sA[o1 + 8 * ks] : 0.0;
+          const double fa0 = (ok0 && kin) ? sA[o0 + 4 * ks * TS16] : 0.0, fa1 = (ok1 && kin) ? sA[o1 + 4 * ks * TS16] : 0.0;
           const double fb0 = sW[(4 * ks + t) * PCW + 16 * half + g], fb1 = sW[(4 * ks + t) * PCW + 16 * half + 8 + g];
           dmma884(acc[0][0][0], acc[0][0][1], fa0, fb0);
           dmma884(acc[0][1][0], acc[0][1][1], fa0, fb1);
@@ -1218,7 +1279,7 @@ __device__ __forceinline__ void final_side_mma(const Team tm, const Side& sd, co
       }
     }
     tm.sync();  // every warp is done with stage s
-    if (tm.tid() == 0 && i + 2 < ntile) issue(i + 2);
+    if (tm.wid == 0 && i + 2 < ntile) issue(i + 2);
   }
 }
 #endif
