@@ -828,7 +828,9 @@ __host__ __device__ __forceinline__ double rcp_d(double x) {
 // pointers -- beats every "cleaner" variant tried: inlined into the bond kernel (+35 % kernel time: the kernel's other
 // phases share its register allocation), 32-bit shared addresses through inline PTX with a predicate-free path for full
 // batches (+60 %), unordered pairs for conflict-free banks (no change), wider groups for tall operands (no change for
-// Float64, -15 % for ComplexF64).
+// Float64, -15 % for ComplexF64), and -- keeping this very form -- instances without the bounds predicates and the zero fill
+// for operands whose rows fill the batches, idle groups reading a zero column (18 % fewer instructions, +12 % kernel time:
+// profiles/r2bn_jacobi_full_instances.txt).
 template <typename T, int GS, int RB>
 __host__ __device__ __noinline__ void jacobi_groups_t(const Team tm, T* B, int m, int n, int ld, int nprob, int pstride, int* flag,
                                                       int* not_converged, long long* sweeps_out) {
