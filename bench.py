@@ -886,8 +886,8 @@ def run_apply(args):
                    "gates_per_step": [len(l) for l in layers],
                    "timing": "host wall clock around the synchronous C-ABI call (operator upload, descriptors, kernel, status read-back)"},
         "roofline": {"bound": "tensor", "achieved": value * flops_per_gate * 1e-12, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                     "frac": value * flops_per_gate * 1e-12 / peaks["sustained"], "traffic": (6.76e9 / 592 + 2.47e9 / 592) * sum(len(l) for l in layers) / 4,
-                     "traffic_source": "DRAM bytes of one launch over 592 gates: side kernel 6.76 GB (profiles/r2bg_apply3_sides_ncu_summary.csv)"
+                     "frac": value * flops_per_gate * 1e-12 / peaks["sustained"], "traffic": (6.28e9 / 592 + 2.47e9 / 592) * sum(len(l) for l in layers) / 4,
+                     "traffic_source": "DRAM bytes of one launch over 592 gates: side kernel 6.28 GB (profiles/r2bq_apply3_sides_ncu_summary.csv)"
                                        " + final kernel 2.47 GB (r2av_apply3_final_ncu_summary.csv; same traffic after its rewrite) + bond "
                                        "kernel 0.1 GB, per gate x gates of a layer",
                      "kernel": "bp_apply3_sides + bp_apply3_bond + bp_apply3_final", "flops_per_gate": flops_per_gate, "peak_source": peaks["how"]},

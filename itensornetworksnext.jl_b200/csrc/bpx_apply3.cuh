@@ -25,7 +25,11 @@
 // Serial parts: one-sided Jacobi WITHOUT accumulating V (for Hermitian G the rotated columns are lam_j v_j themselves; for
 // the bond matrix only the k kept right singular vectors are needed: v_j = theta^H u_j / s_j), pairs handled by sub-warp
 // lane groups so that one step of the round-robin schedule is one pass of the CTA (versions 1 / 2: one warp per pair).
-// Written against the `Team` abstraction like versions 1 / 2: tests/native/apply_host.cu runs it on the host.
+// Written against the `Team` abstraction like versions 1 / 2: tests/native/apply_host.cu runs the phases on the host
+// (run_two_site_v3).  On the device a gate runs as three kernels (bottom of the file: bp_apply3_sides / _bond / _final);
+// the Float64 Gram and final passes have device-only tensor-pipe versions (gram_side_mma, final_side_mma: DMMA.8x8x4 fed by
+// TMA bulk copies), checked against the step-by-step kernels and the oracle on the GPU (tests/test_zz_gpu_apply.py,
+// tests/test_zzzz_apply_large_and_v2_gpu.py).
 #pragma once
 #include "bpx_apply2.cuh"
 
@@ -252,29 +256,6 @@ __host__ __device__ __forceinline__ Tabs tabs_at(const Side& sd, const Walk& wk,
   t.col = t.row + sd.rows;
   t.col_fast = wk.next == 0 || wk.bstride < wk.rstride[0];
   return t;
-}
-
-// contiguous copy global -> shared in 16-byte pieces (both 16-byte aligned; n elements, n * sizeof(T) a multiple of 16)
-template <typename T>
-__host__ __device__ __forceinline__ void copy_tile(const Team tm, T* dst, const T* src, int64_t n) {
-#ifdef __CUDA_ARCH__
-  const int n16 = (int)(n * sizeof(T) / 16), nt = tm.nt(), tid = tm.tid();
-  const double2* __restrict__ s2 = reinterpret_cast<const double2*>(src);
-  double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
-  constexpr int U = 4;
-  const int nfull = n16 / (U * nt) * (U * nt);
-  for (int i0 = tid; i0 < nfull; i0 += U * nt) {  // no predicates: the staging registers stay registers
-    double2 v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = s2[i0 + u * nt];
-#pragma unroll
-    for (int u = 0; u < U; ++u) d2[i0 + u * nt] = v[u];
-  }
-  for (int i = nfull + tid; i < n16; i += nt) d2[i] = s2[i];
-#else
-  for (int64_t i = tm.tid(); i < n; i += tm.nt()) dst[i] = src[i];
-#endif
-  tm.sync();
 }
 
 // rows [row0, row0 + nr) of a scratch copy -> a tile of tr rows in shared memory, one contiguous piece per column group
