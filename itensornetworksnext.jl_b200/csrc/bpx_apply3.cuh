@@ -1437,10 +1437,9 @@ __host__ __device__ __forceinline__ void phase_bond_post(const Team tm, Gate3<T>
   const int ldb = jacobi_ld(m, n, 1, jacobi_rb<T>());
   const T* sb = phase_smem<T>(c.smem);
   const T* th1 = w + L.theta[1];
-  T* th2 = w + L.theta[2];  // rotated copy: U diag(s)
+  // (the rotated operand U diag(s) is read where the iteration left it, in shared memory)
   double* sig = reinterpret_cast<double*>(w + L.sig);
   int32_t* order = reinterpret_cast<int32_t*>(w + L.order);
-  for (int i = tm.tid(); i < m * n; i += tm.nt()) th2[i] = sb[(i % m) + ldb * (i / m)];
   for (int j = tm.tid(); j < n; j += tm.nt()) {
     double a = 0.0;
     for (int r = 0; r < m; ++r) a += E::abs2(sb[r + ldb * j]);
@@ -1476,12 +1475,12 @@ __host__ __device__ __forceinline__ void phase_bond_post(const Team tm, Gate3<T>
       T v = E::zero();
       if (sj > 0.0) {
         if (a == 0) {
-          v = scal(th2[(q + na * x) + m * j], sqrt(snew) / sj);
+          v = scal(sb[(q + na * x) + ldb * j], sqrt(snew) / sj);
         } else {
-          // conj(V[c2, j]) = sum_r theta[r, c2] conj(u_j[r]) / s_j,  u_j = th2[:, j] / s_j
+          // conj(V[c2, j]) = sum_r theta[r, c2] conj(u_j[r]) / s_j,  u_j = sb[:, j] / s_j
           const int c2 = q + na * x;
           T acc = E::zero();
-          for (int r = 0; r < m; ++r) acc = E::fma(th1[r + m * c2], E::conj(th2[r + m * j]), acc);
+          for (int r = 0; r < m; ++r) acc = E::fma(th1[r + m * c2], E::conj(sb[r + ldb * j]), acc);
           v = scal(acc, sqrt(snew) / (sj * sj));
         }
       }
