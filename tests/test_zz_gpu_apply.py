@@ -94,7 +94,7 @@ def test_two_site_layer_matches_oracle(oracle, dtype, lattice, chi, max_rank, no
     for e in range(ga.ne):
         if e not in touched_edges:
             assert np.array_equal(new_msgs[e], msgs[e])
-    assert launches >= 7  # 6 sweeps + the gate layer in one launch
+    assert launches >= 7  # 6 sweeps + the gate layer (three launches on the Gram path)
     # one more sweep from the device's own new tensors and messages
     op_ = oracle.make_problem(ga, new_tensors, "norm")
     want_swept = oracle.sweep_jacobi(op_, new_msgs)

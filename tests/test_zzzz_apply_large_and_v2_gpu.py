@@ -150,6 +150,40 @@ def test_v3_matches_v1(monkeypatch, dtype, lattice, chi, max_rank, normalize):
     assert abs(r1[0] - r3[0]) <= 1e-9 and abs(r1[1] - r3[1]) <= 1e-8 * max(1.0, abs(r1[1]))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_v3_chunked_layer_is_bit_identical_to_one_chunk(monkeypatch, dtype):
+    """The three gate kernels run once per CHUNK of the layer (per-gate work spaces, `status` indexed by the gate's position
+    in the batch): a work-space budget that forces one, two or three gates per chunk -- with a last, smaller chunk -- must
+    give exactly the tensors, messages and singular values of the single-chunk run."""
+    rng = np.random.default_rng(21)
+    p = problems.synthetic_peps(graphs.named_grid((5, 6)), 4, 2, dtype, init="positive")
+    edges = matching(p.ga, rng)
+    assert len(edges) >= 7
+    ops = [randn(rng, dtype, (2, 2, 2, 2)) for _ in edges]
+    out = []
+    for budget in (None, "1", "300000", "450000"):   # bytes: default (one chunk), one gate per chunk, 2 - 6 gates per chunk
+        if budget is None:
+            monkeypatch.delenv("BPX_APPLY_WS_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("BPX_APPLY_WS_BYTES", budget)
+        with B.BPXContext(0) as ctx:
+            problems.upload(ctx, p)
+            ctx.sweep(4, 0.0, True)
+            launches0 = ctx.counters()["launches"]
+            svs = ctx.apply_two_site_gates(edges, ops, max_rank=3, normalize=True)
+            launches = ctx.counters()["launches"] - launches0
+            assert ctx.apply_stats() == (len(edges), 0)
+            out.append((svs, device_tensors(ctx, p), ctx.get_messages(), launches))
+    sv0, t0, m0, l0 = out[0]
+    assert l0 == 3                                     # sides, bond, final
+    assert out[1][3] == 3 * len(edges)                 # one gate per chunk
+    assert 3 < out[2][3] < 3 * len(edges) and 3 < out[3][3] < 3 * len(edges)
+    for svs, ts, ms, _ in out[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(sv0, svs))
+        assert all(np.array_equal(a, b) for a, b in zip(t0, ts))
+        assert all(np.array_equal(a, b) for a, b in zip(m0, ms))
+
+
 def test_v3_declined_gates_fall_back_to_v1_bit_for_bit(monkeypatch):
     """An all-ones environment (test/test_apply_operator.jl:72) is rank one: the reference projects on the messages'
     support, the Gram path declines every gate, and the result is exactly what version 1 alone produces; mixed layers
