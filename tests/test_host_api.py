@@ -164,3 +164,27 @@ def test_synthetic_ising_workload_is_the_generator_network(oracle):
     q = problems.synthetic_ising((8, 8))
     assert q.mode == "single" and q.bytes_per_sweep() == 64 * 16 * 8 + 3 * 256 * 2 * 8   # factors + 3 x messages
     assert q.flops_per_sweep() == 256 * 2 * (16 + 8 + 4)                                # absorb 3 legs: 16 + 8 + 4 MACs
+
+
+def test_pack_operators_stacked_fast_path_equals_the_per_operator_loop():
+    """device.pack_operators: a batch of same-shaped operators is packed in one stacked transpose; ragged batches, lists and
+    dtype promotion go through the per-operator loop -- same bytes either way, and a complex operator for a Float64
+    context is still refused."""
+    import pytest
+
+    from itnn_b200.device import cast_to, pack_operators
+
+    rng = np.random.default_rng(0)
+    for dt_in, dt_out in ((np.float64, np.float64), (np.float64, np.complex128), (np.complex128, np.complex128)):
+        for shape in ((2, 2, 2, 2), (2, 3, 2, 3), (3, 3)):
+            ops = [(rng.standard_normal(shape) + (1j * rng.standard_normal(shape) if dt_in == np.complex128 else 0)).astype(dt_in)
+                   for _ in range(7)]
+            want = np.concatenate([cast_to(o, dt_out, "operator").ravel(order="F") for o in ops])
+            got = pack_operators(ops, dt_out)
+            assert got.dtype == np.dtype(dt_out) and got.flags.c_contiguous and np.array_equal(got, want)
+    ragged = [rng.standard_normal((2, 2, 2, 2)), rng.standard_normal((3, 3, 3, 3))]
+    assert np.array_equal(pack_operators(ragged, np.float64), np.concatenate([o.ravel(order="F") for o in ragged]))
+    assert pack_operators([], np.float64).size == 0
+    assert np.array_equal(pack_operators([[[1.0, 2.0], [3.0, 4.0]]], np.float64), [1.0, 3.0, 2.0, 4.0])  # nested lists
+    with pytest.raises(TypeError):
+        pack_operators([np.ones((2, 2), np.complex128) * 1j] * 3, np.float64)
