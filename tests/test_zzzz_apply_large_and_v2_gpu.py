@@ -151,6 +151,36 @@ def test_v3_matches_v1(monkeypatch, dtype, lattice, chi, max_rank, normalize):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("lattice,chi,d,max_rank", [((3, 4), 3, 3, 0), ((4, 4), 5, 3, 4), ((3, 3), 2, 5, 0)])
+def test_v3_matches_v1_with_an_odd_physical_dimension(monkeypatch, dtype, lattice, chi, d, max_rank):
+    """d = 3 / 5: the matrix view has an odd number of columns (d chi), the absorb pass falls back to one column per batch and
+    the last column group of the scratch copies is half empty -- the tensor-pipe Gram and final passes must mask it."""
+    rng = np.random.default_rng(chi + d)
+    p = problems.synthetic_peps(graphs.named_grid(lattice), chi, d, dtype, init="positive")
+    edges = matching(p.ga, rng)
+    ops = [np.eye(d * d).reshape(d, d, d, d) + 0.3 * randn(rng, dtype, (d, d, d, d)) for _ in edges]
+    results = []
+    for v3 in ("0", "1"):
+        monkeypatch.setenv("BPX_APPLY_V3", v3)
+        with B.BPXContext(0) as ctx:
+            problems.upload(ctx, p)
+            ctx.sweep(5, 0.0, True)
+            svs = ctx.apply_two_site_gates(edges, ops, max_rank=max_rank, normalize=True)
+            taken, declined = ctx.apply_stats()
+            assert (taken + declined == len(edges) and taken > 0) if v3 == "1" else (taken, declined) == (0, 0)
+            res, _ = ctx.sweep(1, 0.0, True)
+            results.append((svs, device_tensors(ctx, p), (res, ctx.bethe_free_energy())))
+    (sv1, t1, r1), (sv3, t3, r3) = results
+    s1, s3 = oracle_state(p, t1), oracle_state(p, t3)
+    for e, a, b in zip(edges, sv1, sv3):
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-13)
+        v, w = p.ga.src[e], p.ga.dst[e]
+        x, y = bond_invariant(s1, v, w), bond_invariant(s3, v, w)
+        assert np.abs(x - y).max() <= 1e-9 * np.abs(x).max()
+    assert abs(r1[0] - r3[0]) <= 1e-9 and abs(r1[1] - r3[1]) <= 1e-8 * max(1.0, abs(r1[1]))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
 def test_v3_chunked_layer_is_bit_identical_to_one_chunk(monkeypatch, dtype):
     """The three gate kernels run once per CHUNK of the layer (per-gate work spaces, `status` indexed by the gate's position
     in the batch): a work-space budget that forces one, two or three gates per chunk -- with a last, smaller chunk -- must
