@@ -214,6 +214,37 @@ def test_v3_chunked_layer_is_bit_identical_to_one_chunk(monkeypatch, dtype):
         assert all(np.array_equal(a, b) for a, b in zip(m0, ms))
 
 
+def test_v3_chunks_of_whole_waves_at_cfg5_shape_are_bit_identical(monkeypatch):
+    """chi = 16, d = 2 on a 24 x 24 lattice (the bulk gates have cfg5's shape: 4096 x 32 matrix views, full TMA tiles): a
+    work-space budget that splits the layer into chunks of 148 gates (whole waves of the side kernel) and a last smaller one
+    gives exactly the singular values, messages and tensors of the single-chunk run."""
+    rng = np.random.default_rng(4)
+    p = problems.synthetic_peps(graphs.named_grid((24, 24)), 16, 2, np.float64, host_data=False)
+    edges = matching(p.ga, rng)
+    ops = [np.eye(4).reshape(2, 2, 2, 2) + 0.2 * randn(rng, np.float64, (2, 2, 2, 2)) for _ in edges]
+    probe = sorted({int(p.ga.src[e]) for e in edges[::17]} | {int(p.ga.dst[e]) for e in edges[::17]})
+    out = []
+    for budget in (None, str(400 << 20)):
+        if budget is None:
+            monkeypatch.delenv("BPX_APPLY_WS_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("BPX_APPLY_WS_BYTES", budget)
+        with B.BPXContext(0) as ctx:
+            problems.upload(ctx, p)
+            ctx.sweep(3, 0.0, True)
+            launches0 = ctx.counters()["launches"]
+            svs = ctx.apply_two_site_gates(edges, ops, max_rank=16, normalize=True)
+            launches = ctx.counters()["launches"] - launches0
+            assert ctx.apply_stats() == (len(edges), 0)
+            res, _ = ctx.sweep(1, 0.0, True)
+            out.append((np.stack(svs), [ctx.get_site_tensor(v) for v in probe], ctx.get_messages_flat(), res, launches))
+    (sv0, t0, m0, r0, l0), (sv1, t1, m1, r1, l1) = out
+    assert l0 == 3 and l1 == 3 * -(-len(edges) // 148), (l0, l1, len(edges))
+    assert np.array_equal(sv0, sv1) and np.array_equal(m0, m1) and r0 == r1
+    assert all(np.array_equal(a, b) for a, b in zip(t0, t1))
+    assert np.all(sv0[:, 0] > 0) and np.allclose((sv0 ** 2).sum(axis=1), 1.0, rtol=1e-12)   # normalised singular values
+
+
 def test_v3_declined_gates_fall_back_to_v1_bit_for_bit(monkeypatch):
     """An all-ones environment (test/test_apply_operator.jl:72) is rank one: the reference projects on the messages'
     support, the Gram path declines every gate, and the result is exactly what version 1 alone produces; mixed layers
