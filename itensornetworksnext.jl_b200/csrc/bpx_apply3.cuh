@@ -1031,11 +1031,13 @@ __host__ __device__ __forceinline__ void gram_factor_finish(const Team tm, int c
   const double cut = EPS * cols * dmax;
   // rank bound: G = P^H P with P rows x cols has at most `rank_max` non-zero eigenvalues; whatever the iteration left in
   // the other directions is rounding noise (it may exceed `cut` by a small factor), so only the largest rank_max count
+  double evl[PC];  // a private copy: the loop below zeroes entries of ev that other threads still rank against
+  for (int i = 0; i < cols; ++i) evl[i] = ev[i];
   tm.sync();
   for (int j = tm.tid(); j < cols; j += tm.nt()) {
     int before = 0;
-    for (int i = 0; i < cols; ++i) before += (ev[i] > ev[j] || (ev[i] == ev[j] && i < j)) ? 1 : 0;
-    if (before >= rank_max || !(ev[j] > cut)) ev[j] = 0.0;
+    for (int i = 0; i < cols; ++i) before += (evl[i] > evl[j] || (evl[i] == evl[j] && i < j)) ? 1 : 0;
+    if (before >= rank_max || !(evl[j] > cut)) ev[j] = 0.0;
   }
   tm.sync();
   for (int j = 0; j < cols; ++j)

@@ -1,4 +1,5 @@
-// TEST INFRASTRUCTURE: the gate-application device code (csrc/bpx_apply.cuh, csrc/bpx_apply2.cuh) run on the host with one
+// TEST INFRASTRUCTURE: the gate-application device code (csrc/bpx_apply.cuh, csrc/bpx_apply2.cuh, the phases of
+// csrc/bpx_apply3.cuh with one lane per warp) run on the host with one
 // THREAD PER WARP and a real barrier behind Team::sync(), under ThreadSanitizer.  What the single-lane host harness
 // (apply_host.cu) cannot see -- a missing barrier between phases executed by different warps -- shows up here as a data
 // race report or as a result that differs from the sequential run.  Schedules with several LANES per warp (threads too,
@@ -56,7 +57,7 @@ static inline double host_warp_sum(int lane, double x) {
 namespace bpx { struct c64; }
 static inline bpx::c64 host_warp_sum(int lane, bpx::c64 x);
 
-#include "../../itensornetworksnext.jl_b200/csrc/bpx_apply2.cuh"
+#include "../../itensornetworksnext.jl_b200/csrc/bpx_apply3.cuh"
 #include "../../itensornetworksnext.jl_b200/csrc/bpx_expect2.cuh"
 
 using namespace bpx;
@@ -245,6 +246,70 @@ static int check(const char* name, int z, int chi, int chi_b, int d, int64_t rb)
   return bad;
 }
 
+// version 3 (the Gram path, csrc/bpx_apply3.cuh): the phases of one gate on `nw` warps of ONE lane each (its host code plays
+// all lane roles on one lane).  The partial sums of the Gram pass are combined per warp, so the result depends on nw in the
+// last bits: agreement to rounding, and no race report.
+template <typename T>
+static int run3(Problem<T> p, int nw, std::vector<T>& sites_out, std::vector<double>& sv) {
+  g_lanes = 1;
+  sv.assign(p.g.chi_b, 0.0);
+  const int64_t need = applyk3::smem_need(p.g, Elem<T>::is_complex);
+  if (need == 0) return -1;
+  std::vector<T> ws((size_t)applyk3::layout3_of(p.g).total + 2), smem((size_t)need);
+  int flag = 0, bad = 0;
+  std::vector<int> status(nw, -1);
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, nw);
+  auto body = [&](int t) {
+    g_barrier = nw > 1 ? &bar : nullptr;
+    g_warp = nullptr;
+    Team tm;
+    tm.lane = 0;
+    tm.wid = t;
+    tm.nw = nw;
+    status[t] = applyk3::run_two_site_v3<T>(tm, p.g, p.sites.data(), p.msgs.data(), p.op.data(), ws.data(), sv.data(), 1, &flag, &bad,
+                                            smem.data());
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nw; ++t) th.emplace_back(body, t);
+  body(0);
+  for (auto& t : th) t.join();
+  pthread_barrier_destroy(&bar);
+  sites_out = p.sites;
+  for (int t = 0; t < nw; ++t)
+    if (status[t] != status[0]) return -2;  // every warp must see the same verdict
+  return status[0];
+}
+
+template <typename T>
+static int check3(const char* name, int z, int chi, int chi_b, int d) {
+  Problem<T> p = make_problem<T>(z, chi, chi_b, d, 4242 + z * 100 + chi);
+  std::vector<T> ref, got;
+  std::vector<double> sv_ref, sv_got;
+  const int st = run3<T>(p, 1, ref, sv_ref);
+  if (st != 0) {
+    printf("%-34s sequential run: status %d (the Gram path must take this gate)\n", name, st);
+    return 1;
+  }
+  ref = pair_product<T>(p.g, ref);
+  int bad = 0;
+  for (int nw : {2, 5, 8}) {
+    const int s2 = run3<T>(p, nw, got, sv_got);
+    got = pair_product<T>(p.g, got);
+    double err = 0.0, scale = 0.0, sverr = 0.0;
+    for (size_t i = 0; i < ref.size(); ++i) {
+      err = fmax(err, sqrt(Elem<T>::abs2(sub(ref[i], got[i]))));
+      scale = fmax(scale, sqrt(Elem<T>::abs2(ref[i])));
+    }
+    for (size_t i = 0; i < sv_ref.size(); ++i) sverr = fmax(sverr, fabs(sv_ref[i] - sv_got[i]));
+    const bool ok = s2 == 0 && err <= 1e-9 * scale && sverr <= 1e-9;
+    printf("%-34s warps=%d lanes=1  status %d, max |diff| = %.2e (scale %.2e), sv diff %.2e  %s\n", name, nw, s2, err, scale, sverr,
+           ok ? "ok" : "MISMATCH");
+    bad += !ok;
+  }
+  return bad;
+}
+
 // two-site expectation kernel (csrc/bpx_expect2.cuh) under the same schedules
 template <typename T>
 static int check_expect(const char* name, int z, int chi, int chi_b, int d) {
@@ -310,6 +375,10 @@ int main() {
   bad += check<c64>("v2 c128 z=3 chi=4 bond=3 d=2 rb=3", 3, 4, 3, 2, 3);
   bad += check<c64>("v2 c128 z=3 chi=8 bond=2 d=3 rb=16", 3, 8, 2, 3, 16);
   bad += check<double>("v2 f64  z=1 (leaf pair) bond=3 rb=1", 1, 3, 3, 2, 1);
+  bad += check3<double>("v3 f64  z=4 chi=3 bond=4 d=2", 4, 3, 4, 2);
+  bad += check3<c64>("v3 c128 z=3 chi=4 bond=3 d=2", 3, 4, 3, 2);
+  bad += check3<double>("v3 f64  z=3 chi=5 bond=3 d=3 (odd columns)", 3, 5, 3, 3);
+  bad += check3<double>("v3 f64  z=1 (leaf pair) bond=3", 1, 3, 3, 2);
   printf(bad ? "FAILED: %d mismatches\n" : "all schedules agree\n", bad);
   return bad ? 1 : 0;
 }

@@ -1,4 +1,5 @@
-"""Inter-warp synchronisation of the gate-application kernels (csrc/bpx_apply.cuh, csrc/bpx_apply2.cuh) checked WITHOUT a
+"""Inter-warp synchronisation of the gate-application kernels (csrc/bpx_apply.cuh, csrc/bpx_apply2.cuh, the phases of
+csrc/bpx_apply3.cuh on warps of one lane) checked WITHOUT a
 GPU: tests/native/apply_race_check.cu runs the same `__host__ __device__` code with one thread per warp -- or per LANE,
 with warp barriers standing in for `__syncwarp()` and the shuffle reductions -- and a real barrier behind `Team::sync()`,
 under ThreadSanitizer.  A missing barrier between two phases executed by different warps is a
@@ -13,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "native", "apply_race_check.cu")
 EXE = os.path.join(HERE, "native", "_build", "apply_race_check")
 HDRS = [os.path.join(HERE, "..", "itensornetworksnext.jl_b200", "csrc", f)
-        for f in ("bpx_apply.cuh", "bpx_apply2.cuh", "bpx_expect2.cuh", "bpx_common.cuh")]
+        for f in ("bpx_apply.cuh", "bpx_apply2.cuh", "bpx_apply3.cuh", "bpx_expect2.cuh", "bpx_common.cuh")]
 
 
 def test_gate_kernels_are_race_free_across_warps():
@@ -29,4 +30,5 @@ def test_gate_kernels_are_race_free_across_warps():
         pytest.skip("ThreadSanitizer cannot run in this environment: " + out.strip().splitlines()[0])
     assert "ThreadSanitizer: data race" not in out, out[-3000:]
     assert r.returncode == 0 and "all schedules agree" in out, out[-3000:]
-    assert out.count(" ok") >= 50 and "MISMATCH" not in out  # (8 gate problems + 2 expectation problems) x 5 schedules
+    # (8 gate problems + 2 expectation problems) x 5 schedules + 4 Gram-path problems x 3 schedules
+    assert out.count(" ok") >= 62 and "MISMATCH" not in out
