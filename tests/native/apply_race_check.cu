@@ -379,6 +379,9 @@ int main() {
   bad += check3<c64>("v3 c128 z=3 chi=4 bond=3 d=2", 3, 4, 3, 2);
   bad += check3<double>("v3 f64  z=3 chi=5 bond=3 d=3 (odd columns)", 3, 5, 3, 3);
   bad += check3<double>("v3 f64  z=1 (leaf pair) bond=3", 1, 3, 3, 2);
+  bad += check3<c64>("v3 c128 z=1 (leaf pair) bond=4", 1, 4, 4, 2);
+  bad += check3<double>("v3 f64  z=2 chi=2 bond=5 (rows < cols)", 2, 2, 5, 2);
+  bad += check3<c64>("v3 c128 z=4 chi=2 bond=3 d=3", 4, 2, 3, 3);
   printf(bad ? "FAILED: %d mismatches\n" : "all schedules agree\n", bad);
   return bad ? 1 : 0;
 }

@@ -30,5 +30,5 @@ def test_gate_kernels_are_race_free_across_warps():
         pytest.skip("ThreadSanitizer cannot run in this environment: " + out.strip().splitlines()[0])
     assert "ThreadSanitizer: data race" not in out, out[-3000:]
     assert r.returncode == 0 and "all schedules agree" in out, out[-3000:]
-    # (8 gate problems + 2 expectation problems) x 5 schedules + 4 Gram-path problems x 3 schedules
-    assert out.count(" ok") >= 62 and "MISMATCH" not in out
+    # (8 gate problems + 2 expectation problems) x 5 schedules + 7 Gram-path problems x 3 schedules
+    assert out.count(" ok") >= 71 and "MISMATCH" not in out
