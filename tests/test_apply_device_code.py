@@ -652,3 +652,24 @@ def test_edge_expect_fuzz(oracle, hostlib):
                                        ptr(a2[3]), ptr(a2[4]), ptr(a2[5]), ptr(op), ptr(num), ptr(den))
         assert np.isclose(den[0], want_den, rtol=1e-11)
         assert np.isclose(num[0], want_num, rtol=1e-10, atol=1e-13 * abs(want_den))
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f64", "c128"])
+@pytest.mark.parametrize("z,chi,chib,d", [(4, 6, 5, 2), (4, 7, 4, 2), (3, 13, 6, 2), (3, 15, 3, 3)],
+                         ids=["rows216", "rows343", "rows169", "rows225_d3"])
+def test_v3_row_counts_that_end_in_a_partial_tile(hostlib, dtype, z, chi, chib, d):
+    """Matrix views of 169 .. 343 rows: one or two full 128-row tiles of the Gram and final passes followed by a partial one
+    (the scratch copies are column-group major: a tile is one piece per group, `copy_tile_groups`), odd row counts, and an
+    odd column count (d = 3)."""
+    rng = np.random.default_rng(z * 100 + chi)
+    adj, state, env = star_pair(rng, dtype, z, chi, d, chi_bond=chib)
+    o = randn(rng, dtype, (d, d, d, d))
+    names = (("s", 0), ("s", 1))
+    k = max(1, chib - 1)
+    want_state, want_env = A.apply_operator((o, names, names), state, env, trunc=k, normalize=True)
+    s_want = np.diag(want_env[(0, 1)]).real
+    y = bond_product(want_state, 0, 1)
+    rc, got, sv = run_pair_v3(hostlib, dtype, adj, state, env, o, k, True)
+    assert rc == 0
+    assert np.abs(sv[:len(s_want)] - s_want).max() <= 1e-9 * s_want.max()
+    assert np.abs(bond_product(got, 0, 1) - y).max() <= 1e-9 * np.abs(y).max()
